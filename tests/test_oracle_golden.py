@@ -1,0 +1,146 @@
+"""Pins oracle/refine_oracle.py against outputs of the UNMODIFIED reference (tests/golden/*.npz,
+written by tests/golden/make_golden.py in the build container).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import refine_oracle as O
+from rnnpose_b200 import synthetic as S
+from tests.util import load_update_weights, golden
+
+torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_g1_corr_pyramid_and_lookup():
+    g = golden("corr_lookup.npz")
+    B, D, h, w, s1, s2 = [int(v) for v in g["meta"]]
+    f1 = S.hash_features((B, D, h, w), s1); f2 = S.hash_features((B, D, h, w), s2)
+    pyr = O.corr_pyramid(f1, f2)
+    assert [tuple(p.shape[-2:]) for p in pyr] == [(17, 22), (8, 11), (4, 5), (2, 2)]   # floor pooling
+    for lvl, key in ((0, "pyr0"), (1, "pyr1"), (3, "pyr3")):
+        torch.testing.assert_close(pyr[lvl], T(g[key]), rtol=1e-5, atol=2e-6)
+    out = O.corr_lookup(pyr, T(g["coords"]))
+    assert out.shape == (B, 324, h, w)
+    torch.testing.assert_close(out, T(g["out"]), rtol=1e-5, atol=5e-6)
+
+
+def test_g2_update_block():
+    g = golden("update_block.npz")
+    B, h, w, s1, s2, s3, s4 = [int(v) for v in g["meta"]]
+    net = torch.tanh(S.hash_features((B, 128, h, w), s1)); inp = torch.relu(S.hash_features((B, 128, h, w), s2))
+    corr = S.hash_features((B, 324, h, w), s3, 2.0); flow = S.hash_features((B, 2, h, w), s4, 4.0)
+    net2, mask, dflow = O.update_block(load_update_weights(), net, inp, corr, flow)
+    torch.testing.assert_close(net2, T(g["net_out"]), rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(mask, T(g["mask"]), rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(dflow, T(g["dflow"]), rtol=1e-4, atol=2e-5)
+
+
+def test_g3_cfnet_sequence_state_carry():
+    g = golden("cfnet_seq.npz")
+    B, H, W, s1, s2, s3, s4 = [int(v) for v in g["meta"]]
+    h, w = H // 8, W // 8
+    f1 = S.hash_features((B, 256, h, w), s1); f2 = S.hash_features((B, 256, h, w), s2)
+    ctx = S.hash_features((B, 256, H, W), s3, 0.1)
+    st = O.RefineState(); wts = load_update_weights()
+    for it in range(3):
+        fi = S.hash_features((B, 2, H, W), s4 + it, 6.0)
+        fl_lr = O.downsample_align_corners(fi / 8.0, 8)          # CFNet.py:138-142
+        flow_up, low = O.cf_net_forward(wts, st, f1, f2, fl_lr, ctx, update_corr_fn=(it == 0))
+        torch.testing.assert_close(flow_up, T(g["flow_up"][it]), rtol=1e-4, atol=2e-4)
+        torch.testing.assert_close(st.net, T(g["net"][it]), rtol=1e-4, atol=2e-5)
+
+
+def test_g4_convex_upsample():
+    g = golden("upsample.npz")
+    B, h, w, s1, s2 = [int(v) for v in g["meta"]]
+    out = O.convex_upsample(S.hash_features((B, 2, h, w), s1, 3.0), S.hash_features((B, 576, h, w), s2, 2.0))
+    torch.testing.assert_close(out, T(g["out"]), rtol=1e-5, atol=1e-5)
+
+
+def test_g5_corr_weight():
+    g = golden("weight.npz")
+    B, C, H, W, s1, s2, s3, s4 = [int(v) for v in g["meta"]]
+    g1 = S.hash_features((B, C, H, W), s1); g1 = g1 / g1.norm(dim=1, keepdim=True)
+    g2 = S.hash_features((B, C, H, W), s2); g2 = g2 / g2.norm(dim=1, keepdim=True)
+    yy, xx = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    tgt = torch.stack([xx, yy], -1)[None].repeat(B, 1, 1, 1) + S.hash_features((B, 1, H, W, 2), s3, 5.0)[:, 0]
+    tgt[0, 0, 0] = torch.tensor([-3.0, -2.0]); tgt[0, 0, 1] = torch.tensor([W + 1.5, 3.0])
+    depth = (S.hash_features((B, 1, H, W), s4) > -0.3).float() * 0.9
+    wgt = O.corr_weight(g1, g2, tgt, depth[:, 0], float(g["sigma"]))
+    torch.testing.assert_close(wgt, T(g["weight"]), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_g6_lm_steps(n):
+    g = golden("lm.npz")
+    depth, target, weight, K = T(g["depth"]), T(g["target"]), T(g["weight"]), T(g["K"])
+    G = T(g["G_in"]).clone()
+    eye = torch.eye(6, dtype=torch.float64)
+    for it in range(n):
+        Gn, delta, Hm, bv = O.lm_step(depth, target, weight, K, G)
+        Hd = Hm + O.EP_LMBDA * eye + O.LM_LMBDA * Hm * eye
+        torch.testing.assert_close(Hd, T(g[f"Hd_{n}"][it]), rtol=1e-9, atol=1e-6)
+        torch.testing.assert_close(bv, T(g[f"b_{n}"][it]), rtol=1e-6, atol=1e-4)
+        G = Gn
+    torch.testing.assert_close(G, T(g[f"G_out_{n}"]), rtol=0, atol=2e-6)
+
+
+def test_g6_lm_near_plane_cutoffs():
+    g = golden("lm.npz")
+    depth, target, weight, K = T(g["depth"]), T(g["target"]), T(g["weight"]), T(g["K"])
+    G = T(g["G_in_near"]).clone()
+    for it in range(2):
+        G, delta, Hm, bv = O.lm_step(depth, target, weight, K, G)
+        torch.testing.assert_close(bv, T(g["b_near"][it]), rtol=1e-6, atol=1e-3)
+    torch.testing.assert_close(G, T(g["G_out_near"]), rtol=0, atol=5e-6)
+
+
+def test_g6_lm_nan_is_absorbed():
+    """torch>=1.8 raises inside torch.cholesky on a NaN matrix; the reference's intent
+    (geometry/cholesky.py:42-45, torch 1.7 semantics) is NaN -> zero update, which the oracle keeps."""
+    g = golden("lm.npz")
+    depth, target, weight, K = T(g["depth"]), T(g["target"]), T(g["weight"]).clone(), T(g["K"])
+    weight[0, 5, 5] = float("nan")
+    G = T(g["G_in"]).clone()
+    Gn, delta, _, _ = O.lm_step(depth, target, weight, K, G)
+    assert torch.all(delta[0] == 0) and torch.isfinite(Gn).all()
+    torch.testing.assert_close(Gn[0], G[0])
+    assert (delta[1] != 0).any()
+
+
+def test_g7_se3_exp_both_branches():
+    g = golden("expm.npz")
+    torch.testing.assert_close(O.se3_exp(T(g["xi"])), T(g["G"]), rtol=1e-6, atol=1e-7)
+
+
+def test_g9_cholesky_solve_clamp():
+    g = golden("cholesky.npz")
+    x3 = O.cholesky_solve6(T(g["H3"])[None], T(g["b3"])[None])[0]
+    torch.testing.assert_close(x3, T(g["x3"]), rtol=1e-6, atol=1e-7)
+    assert x3[0] == -1.0 and x3[1] == 1.0            # the +-1 clamp (x = [-1, 1, -0.1821])
+    torch.testing.assert_close(O.cholesky_solve6(T(g["H6"]), T(g["b6"])), T(g["x6"]), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["refine_cfg0_240x320_1x1.npz", "refine_128x160_4x3.npz",
+                                  "refine_240x320_4x3.npz", "refine_occl_128x160_8x3.npz"])
+def test_g8_full_inner_loop(name):
+    """Oracle inner loop == reference PoseRefiner.forward (B=1 calls) on the same scenes:
+    final SE3 within 1e-4 abs (BASELINE north_star tolerance; observed ~1e-6)."""
+    g = golden(name)
+    H, W, n_iters, n_lm, seed, occl = [int(v) for v in g["meta"]]
+    idxs = [int(i) for i in g["idxs"]]
+    mb = S.make_batch(idxs, H, W, seed, bool(occl), with_images=False)
+    res = O.refine_inner_loop(load_update_weights(), T(g["fmap1"]), T(g["fmap2"]), mb["context"], mb["geofea1"],
+                              mb["geofea2"], mb["depth"], mb["K"], T(g["G0"]), sigma=1.0, n_iters=n_iters, n_lm=n_lm)
+    Ti_pred = torch.matmul(res["G"], mb["T_init"])                # PoseRefiner.py:365
+    err = (Ti_pred - T(g["Ti_pred"])).abs().max().item()
+    assert err < 1e-4, err
+    assert err < 2e-5, f"oracle drifted from the reference more than expected: {err}"
+    torch.testing.assert_close(res["flows"][-1][:, :, ::4, ::4], T(g["flow_last"]), rtol=1e-3, atol=5e-3)
+    torch.testing.assert_close(res["weight"][:, ::4, ::4], T(g["weight"]), rtol=1e-3, atol=1e-4)
