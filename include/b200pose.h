@@ -1,0 +1,169 @@
+/*
+ * b200pose.h -- C ABI of libb200pose.so: the RNNPose recurrent pose-refinement inner loop as
+ * hand-written sm_100a CUDA kernels.
+ *
+ * The reference (DecaYale/RNNPose) has no native interface on this path: every operation below is a
+ * chain of PyTorch calls inside PoseRefiner.forward (reference model/PoseRefiner.py:315-365).  Its
+ * only FFI precedent is thirdparty/nn/src/ext.h:1-10 (plain C function, raw pointers + ints).  This
+ * header follows that shape and SURVEY.md section 8(b):
+ *   - plain pointers and sizes only (no torch types), every pointer is a DEVICE pointer unless its
+ *     name ends in _host;
+ *   - every function returns int: 0 = ok, negative = invalid argument (B200POSE_E_*), positive = the
+ *     cudaError_t of a failed launch / API call;  nothing exits, throws or allocates;
+ *   - work is enqueued on the caller's stream (cudaStream_t passed as void*), no device-wide sync,
+ *     graph-capturable (except where noted); scratch memory comes from the caller
+ *     (b200pose_workspace_bytes);
+ *   - the library keeps no global state.
+ *
+ * Internal activation layout ("PXC"): pixel-major, channels contiguous: [B*h*w][C] float32, where
+ * h = H/8, w = W/8 is the 1/8-resolution grid.  Boundary tensors keep the reference's NCHW layout.
+ * The per-operator entry points use PXC for the low-resolution maps; the fused entry point
+ * b200pose_refine_iters consumes exactly what the reference's inner loop consumes.
+ */
+#ifndef B200POSE_H
+#define B200POSE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200POSE_VERSION 1
+
+/* error codes (negative); positive return values are cudaError_t */
+#define B200POSE_OK            0
+#define B200POSE_E_NULL       (-1)   /* a required pointer is NULL */
+#define B200POSE_E_SHAPE      (-2)   /* unsupported shape (see each function) */
+#define B200POSE_E_WORKSPACE  (-3)   /* workspace too small / misaligned */
+#define B200POSE_E_ARG        (-4)   /* bad scalar argument */
+
+#define B200POSE_CORR_LEVELS   4     /* reference model/CFNet.py:59 */
+#define B200POSE_CORR_RADIUS   4     /* reference model/CFNet.py:60 */
+#define B200POSE_CORR_CH       324   /* 4 * 9 * 9 lookup channels */
+#define B200POSE_CORR_PITCH    328   /* PXC pitch of the lookup output (pad channels are zero) */
+#define B200POSE_NUM_WEIGHT_TENSORS 30
+
+int b200pose_version(void);
+const char* b200pose_error_string(int code);
+
+/* ---- weights ----------------------------------------------------------------------------------
+ * Replaces: nn.Conv2d parameter storage of BasicUpdateBlock (reference thirdparty/raft/update.py:
+ * 164-177), loaded from weights/gru_update.pth at model/CFNet.py:71-74.
+ * `tensors` = 30 device pointers in state-dict order, reference layouts
+ * ([Cout,Cin,KH,KW] weight, [Cout] bias):
+ *   encoder.convc1, encoder.convc2, encoder.convf1, encoder.convf2, encoder.conv,
+ *   gru.convz1, gru.convr1, gru.convq1, gru.convz2, gru.convr2, gru.convq2,
+ *   flow_head.conv1, flow_head.conv2, mask.0, mask.2          (each: weight then bias)
+ * `packed` = caller-owned device buffer of b200pose_packed_weights_bytes() bytes (256-B aligned)
+ * that receives the kernel-side layouts; it stays valid as long as the caller keeps it.          */
+size_t b200pose_packed_weights_bytes(void);
+int b200pose_pack_weights(const float* const* tensors_host /* host array of 30 device ptrs */,
+                          void* packed, void* stream);
+
+/* ---- a1: correlation volume + pyramid ---------------------------------------------------------
+ * Replaces CorrBlock.__init__ / CorrBlock.corr (reference thirdparty/raft/corr.py:13-34,60-67).
+ * fmap1,fmap2: [B,D,h,w] NCHW.  pyramid: b200pose_pyramid_floats(B,h,w) floats; level l holds
+ * [B][h*w][hl*wl] with hl = h>>l, wl = w>>l (floor), levels stored back to back.
+ * Requires h>>3 >= 2 and w>>3 >= 2 (the reference divides by (wl-1) in its sampler).             */
+size_t b200pose_pyramid_floats(int B, int h, int w);
+int b200pose_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int h, int w,
+                          float* pyramid, void* stream);
+
+/* ---- a2: pyramid lookup -----------------------------------------------------------------------
+ * Replaces CorrBlock.__call__ + bilinear_sampler (corr.py:36-57, utils/utils.py:57-71).
+ * coords: [B*h*w][2] (x,y) PXC.  out: [B*h*w][328] PXC; channel l*81 + i*9 + j samples
+ * (x/2^l + i-4, y/2^l + j-4); channels 324..327 are written as 0.                               */
+int b200pose_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w,
+                         float* out, void* stream);
+
+/* ---- a6 (part): hidden state / context init ---------------------------------------------------
+ * Replaces the 1/8 bilinear (align_corners=True) resample + tanh/relu split, model/CFNet.py:124-133.
+ * context: [B,256,H,W] NCHW (already multiplied by 0.1, PoseRefiner.py:283).
+ * net: [B*h*w][128] = tanh(ctx[:128]);  xbuf: [B*h*w][256], channels 0..127 = relu(ctx[128:]).   */
+int b200pose_context_init(const float* context, int B, int H, int W, float* net, float* xbuf, void* stream);
+
+/* ---- a8 + a6: reprojection flow-init at 1/8 resolution ----------------------------------------
+ * Replaces SE3.transform + flow_init (PoseRefiner.py:324-328, transformation.py:184-198) and the
+ * "/8 then 1/8 bilinear align_corners=True" of model/CFNet.py:138-144.
+ * depth: [B,H,W] (syn_depth, WITHOUT the +1e-5; added inside), K: [B,3,3], G: [B,4,4] row-major.
+ * coords1: [B*h*w][2] = coords0 + resampled flow_init/8;  flow: [B*h*w][2] = coords1 - coords0.  */
+int b200pose_flow_init(const float* depth, const float* K, const float* G, int B, int H, int W,
+                       float* coords1, float* flow, void* stream);
+
+/* ---- a3-a5: update block ----------------------------------------------------------------------
+ * Replaces BasicUpdateBlock.forward (thirdparty/raft/update.py:179-188).
+ * net: [P][128] in/out (hidden state);  xbuf: [P][256], channels 0..127 = inp (input), channels
+ * 128..255 are scratch (motion features);  corr: [P][328];  coords1: [P][2] in/out
+ * (coords1 += delta_flow, CFNet.py:157);  flow: [P][2] in = coords1-coords0 (CFNet.py:151),
+ * out = new coords1-coords0 (CFNet.py:166);  mask: [P][576] out (already x0.25).
+ * workspace: b200pose_update_workspace_bytes(B,h,w).                                             */
+size_t b200pose_update_workspace_bytes(int B, int h, int w);
+int b200pose_update_block(const void* packed_weights, float* net, float* xbuf, const float* corr,
+                          float* coords1, float* flow, float* mask, float* dflow_out /* [P][2] or NULL */,
+                          int B, int h, int w, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a7 + a9: convex upsampling fused with the correspondence weight --------------------------
+ * Replaces GRU_CFUpdator.upsample_flow (model/CFNet.py:95-106), target = flow + grid
+ * (PoseRefiner.py:335-338) and the descriptor-similarity weight (PoseRefiner.py:342-345).
+ * flow: [P][2] low-res flow, mask: [P][576]; geofea1, geofea2: [B,C,H,W] NCHW (may both be NULL
+ * together with weight: then only flow_up/target are produced); depth: [B,H,W] (syn_depth).
+ * Outputs (each may be NULL): flow_up [B,2,H,W] NCHW; target [B,H,W,2]; weight [B,H,W].          */
+int b200pose_upsample_weight(const float* flow, const float* mask, const float* geofea1,
+                             const float* geofea2, const float* depth, float sigma,
+                             int B, int C, int H, int W,
+                             float* flow_up, float* target, float* weight, void* stream);
+
+/* ---- a10-a12: Levenberg-Marquardt steps --------------------------------------------------------
+ * Replaces SE3Sequence.reprojction_optim (geometry/transformation.py:265-316): residual/Jacobian,
+ * fp64 H = sum v w J^T J, b = sum v w J^T r, damping H += ep*I + lm*diag(H), geometry/cholesky.py
+ * solve (NaN -> 0, clamp +-1), se3 exponential retraction G <- exp(delta) G (geometry/se3.py).
+ * depth: [B,H,W]; depth_offset is added to it before use: pass 1e-5f with the raw syn_depth, 0 with the
+ * reference's `depths = syn_depth + EPS` (PoseRefiner.py:313); target: [B,H,W,2]; weight: [B,H,W]; K: [B,3,3];
+ * G: [B,4,4] updated IN PLACE n_steps times.  Optional taps (may be NULL), each written per step:
+ * H_out [n_steps][B][36] fp64 (un-damped), b_out [n_steps][B][6] fp64, delta_out [n_steps][B][6].
+ * workspace: b200pose_lm_workspace_bytes(B,H,W).                                                 */
+size_t b200pose_lm_workspace_bytes(int B, int H, int W);
+int b200pose_lm_solve(const float* depth, const float* target, const float* weight, const float* K,
+                      float* G, int B, int H, int W, float depth_offset, int n_steps, double ep_lmbda, double lm_lmbda,
+                      double* H_out, double* b_out, float* delta_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a14: the fused inner loop ----------------------------------------------------------------
+ * Replaces the body of `for i in range(cfg.ITER_COUNT)` in PoseRefiner.forward
+ * (model/PoseRefiner.py:315-362) for one render iteration, natively batched.
+ * Inputs (device, fp32): fmap1,fmap2 [B,256,h,w]; context [B,256,H,W] (x0.1 applied);
+ * geofea1,geofea2 [B,C,H,W]; depth [B,H,W]; K [B,3,3]; G [B,4,4] = Tij at loop entry, overwritten
+ * with Tij at loop exit.  Optional outputs: flow_first [B,2,H,W] (full-res flow of recurrent
+ * iteration 0, the "flow" entry of the reference's return dict), flow_last [B,2,H,W],
+ * weight_last [B,H,W].  n_iters = ITER_COUNT, n_lm = OPTIM_ITER_COUNT.                            */
+size_t b200pose_refine_workspace_bytes(int B, int H, int W);
+int b200pose_refine_iters(const void* packed_weights,
+                          const float* fmap1, const float* fmap2, const float* context,
+                          const float* geofea1, const float* geofea2, const float* depth,
+                          const float* K, float* G, float sigma,
+                          int B, int C_geo, int H, int W, int n_iters, int n_lm,
+                          double ep_lmbda, double lm_lmbda,
+                          float* flow_first, float* flow_last, float* weight_last,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): uploads the inputs, runs the loop, downloads G.
+ * This is the end-to-end entry a caller without device-resident tensors uses (bench.py "e2e").
+ * device_scratch must hold b200pose_refine_host_scratch_bytes(B,C_geo,H,W) bytes.                 */
+size_t b200pose_refine_host_scratch_bytes(int B, int C_geo, int H, int W);
+int b200pose_refine_iters_host(const void* packed_weights,
+                               const float* fmap1_host, const float* fmap2_host, const float* context_host,
+                               const float* geofea1_host, const float* geofea2_host, const float* depth_host,
+                               const float* K_host, float* G_host, float sigma,
+                               int B, int C_geo, int H, int W, int n_iters, int n_lm,
+                               double ep_lmbda, double lm_lmbda,
+                               void* device_scratch, size_t device_scratch_bytes, void* stream);
+
+/* number of kernel launches b200pose_refine_iters enqueues (for bench.py's gpu_launches) */
+int b200pose_refine_launch_count(int n_iters, int n_lm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200POSE_H */

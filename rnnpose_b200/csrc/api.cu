@@ -1,0 +1,324 @@
+// C-ABI entry points of libb200pose.so (declared in include/b200pose.h) and the host-side sequencing of
+// the inner loop (reference model/PoseRefiner.py:315-362, model/CFNet.py:109-173).
+#include "common.cuh"
+
+#include <stdio.h>
+
+namespace {
+
+struct Carver {
+    char* base; size_t off; size_t cap;
+    Carver(void* p, size_t c) : base(reinterpret_cast<char*>(p)), off(0), cap(c) {}
+    template <typename T> T* take(size_t n) {
+        off = align_up(off, 256);
+        T* r = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return r;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+struct UpdateWs {
+    float *col, *c1, *corflo, *f1o, *zbuf, *rhbuf, *hm;
+};
+
+size_t update_ws_layout(int B, int h, int w, void* ws, size_t cap, UpdateWs* out) {
+    const size_t P = (size_t)B * h * w;
+    Carver c(ws, cap);
+    UpdateWs u;
+    u.col = c.take<float>(P * 112);
+    u.c1 = c.take<float>(P * 256);
+    u.corflo = c.take<float>(P * 256);
+    u.f1o = c.take<float>(P * 128);
+    u.zbuf = c.take<float>(P * 128);
+    u.rhbuf = c.take<float>(P * 128);
+    u.hm = c.take<float>(P * 512);
+    if (out) *out = u;
+    return align_up(c.off, 256);
+}
+
+inline bool shape_ok(int B, int H, int W) {
+    return B >= 1 && H >= 128 && W >= 128 && (H % 8) == 0 && (W % 8) == 0;   // (H/8)>>3 >= 2: the reference's
+}                                                                             // sampler divides by (w_l - 1)
+
+int run_update_block(const float* wts, float* net, float* xbuf, const float* corr, float* coords1, float* flow,
+                     float* mask, float* dflow_out, int B, int h, int w, const UpdateWs& u, cudaStream_t s) {
+    const B2PWeightLayout& L = b2p_weight_layout();
+    int rc;
+    auto conv = [&](int id, const float* s0, int p0, int c0, const float* s1, int p1, int c1n, float* dst, int dpitch,
+                    int epi, float scale) -> int {
+        const B2PConvDesc& d = L.cv[id];
+        ConvParams p;
+        p.src0 = s0; p.pitch0 = p0; p.c0 = c0; p.src1 = s1; p.pitch1 = p1; p.c1 = c1n;
+        p.wgt = wts + d.w_off; p.bias = wts + d.b_off; p.dst = dst; p.dst_pitch = dpitch;
+        p.cout = d.cout; p.cout_pad = d.cout_pad; p.cin_pad = d.cin_pad;
+        p.B = B; p.h = h; p.w = w; p.kh = d.kh; p.kw = d.kw; p.epi = epi; p.scale = scale;
+        p.zbuf = u.zbuf; p.rhbuf = u.rhbuf; p.hbuf = net;
+        return b2p_launch_conv(p, s);
+    };
+    // motion encoder (update.py:89-97)
+    if ((rc = b2p_im2col_f1(flow, B, h, w, u.col, xbuf, s))) return rc;                               // + cat[out, flow]
+    if ((rc = conv(CV_C1, corr, B200POSE_CORR_PITCH, 324, nullptr, 0, 0, u.c1, 256, EPI_RELU, 1.f))) return rc;
+    if ((rc = conv(CV_C2, u.c1, 256, 256, nullptr, 0, 0, u.corflo, 256, EPI_RELU, 1.f))) return rc;    // cor -> [0,192)
+    if ((rc = conv(CV_F1, u.col, 112, 98, nullptr, 0, 0, u.f1o, 128, EPI_RELU, 1.f))) return rc;
+    if ((rc = conv(CV_F2, u.f1o, 128, 128, nullptr, 0, 0, u.corflo + 192, 256, EPI_RELU, 1.f))) return rc;  // flo -> [192,256)
+    if ((rc = conv(CV_ENC, u.corflo, 256, 256, nullptr, 0, 0, xbuf + 128, 256, EPI_RELU, 1.f))) return rc;  // out -> x[128,254)
+    // SepConvGRU (update.py:45-60): hx = [h | inp | motion]
+    if ((rc = conv(CV_ZR1, net, 128, 128, xbuf, 256, 256, nullptr, 0, EPI_GRU_ZR, 1.f))) return rc;
+    if ((rc = conv(CV_Q1, u.rhbuf, 128, 128, xbuf, 256, 256, nullptr, 0, EPI_GRU_Q, 1.f))) return rc;
+    if ((rc = conv(CV_ZR2, net, 128, 128, xbuf, 256, 256, nullptr, 0, EPI_GRU_ZR, 1.f))) return rc;
+    if ((rc = conv(CV_Q2, u.rhbuf, 128, 128, xbuf, 256, 256, nullptr, 0, EPI_GRU_Q, 1.f))) return rc;
+    // heads (update.py:13-14, 172-176, 187)
+    if ((rc = conv(CV_HEADS, net, 128, 128, nullptr, 0, 0, u.hm, 512, EPI_RELU, 1.f))) return rc;
+    if ((rc = b2p_flow_head2(u.hm, wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, B, h, w, s))) return rc;
+    if ((rc = conv(CV_MASK2, u.hm + 256, 512, 256, nullptr, 0, 0, mask, 576, EPI_SCALE, 0.25f))) return rc;
+    return 0;
+}
+constexpr int UPDATE_LAUNCHES = 13;
+
+struct RefineWs {
+    float *pyr, *net, *xbuf, *corr, *coords1, *flow, *mask, *target, *weight;
+    void* lm;
+    UpdateWs u;
+};
+
+size_t refine_ws_layout(int B, int H, int W, void* ws, size_t cap, RefineWs* out) {
+    const int h = H / 8, w = W / 8;
+    const size_t P = (size_t)B * h * w, N = (size_t)B * H * W;
+    Carver c(ws, cap);
+    RefineWs r;
+    r.pyr = c.take<float>(b200pose_pyramid_floats(B, h, w));
+    r.net = c.take<float>(P * 128);
+    r.xbuf = c.take<float>(P * 256);
+    r.corr = c.take<float>(P * B200POSE_CORR_PITCH);
+    r.coords1 = c.take<float>(P * 2);
+    r.flow = c.take<float>(P * 2);
+    r.mask = c.take<float>(P * 576);
+    r.target = c.take<float>(N * 2);
+    r.weight = c.take<float>(N);
+    r.lm = c.take<char>(b2p_lm_ws_bytes(B, H, W));
+    c.off = align_up(c.off, 256);
+    const size_t used = update_ws_layout(B, h, w, ws ? c.base + c.off : nullptr, cap > c.off ? cap - c.off : 0, &r.u);
+    if (out) *out = r;
+    return c.off + used;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200pose_version(void) { return B200POSE_VERSION; }
+
+const char* b200pose_error_string(int code) {
+    switch (code) {
+        case B200POSE_OK: return "ok";
+        case B200POSE_E_NULL: return "b200pose: required pointer is NULL";
+        case B200POSE_E_SHAPE: return "b200pose: unsupported shape (need B>=1, H,W multiples of 8 and >= 128)";
+        case B200POSE_E_WORKSPACE: return "b200pose: workspace too small or misaligned";
+        case B200POSE_E_ARG: return "b200pose: bad scalar argument";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "b200pose: unknown error";
+    }
+}
+
+size_t b200pose_packed_weights_bytes(void) { return b2p_weight_layout().total_floats * sizeof(float); }
+
+int b200pose_pack_weights(const float* const* tensors_host, void* packed, void* stream) {
+    if (!tensors_host || !packed) return B200POSE_E_NULL;
+    for (int i = 0; i < B200POSE_NUM_WEIGHT_TENSORS; ++i)
+        if (!tensors_host[i]) return B200POSE_E_NULL;
+    return b2p_pack_weights(tensors_host, reinterpret_cast<float*>(packed), (cudaStream_t)stream);
+}
+
+size_t b200pose_pyramid_floats(int B, int h, int w) {
+    size_t per = 0;
+    int hl = h, wl = w;
+    for (int l = 0; l < B200POSE_CORR_LEVELS; ++l) { per += (size_t)hl * wl; hl >>= 1; wl >>= 1; }
+    return (size_t)B * h * w * per;
+}
+
+int b200pose_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int h, int w, float* pyramid,
+                          void* stream) {
+    if (!fmap1 || !fmap2 || !pyramid) return B200POSE_E_NULL;
+    if (B < 1 || D < 1 || (h >> 3) < 2 || (w >> 3) < 2) return B200POSE_E_SHAPE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int P = h * w;
+    int rc;
+    if ((rc = b2p_corr_volume(fmap1, fmap2, B, D, P, pyramid, s))) return rc;
+    float* src = pyramid;
+    int hl = h, wl = w;
+    for (int l = 1; l < B200POSE_CORR_LEVELS; ++l) {
+        float* dst = src + (size_t)B * P * hl * wl;
+        if ((rc = b2p_corr_pool(src, B * P, hl, wl, dst, s))) return rc;
+        src = dst; hl >>= 1; wl >>= 1;
+    }
+    return 0;
+}
+
+int b200pose_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, void* stream) {
+    if (!pyramid || !coords || !out) return B200POSE_E_NULL;
+    if (B < 1 || (h >> 3) < 2 || (w >> 3) < 2) return B200POSE_E_SHAPE;
+    return b2p_corr_lookup(pyramid, coords, B, h, w, out, (cudaStream_t)stream);
+}
+
+int b200pose_context_init(const float* context, int B, int H, int W, float* net, float* xbuf, void* stream) {
+    if (!context || !net || !xbuf) return B200POSE_E_NULL;
+    if (B < 1 || H < 16 || W < 16 || (H % 8) || (W % 8)) return B200POSE_E_SHAPE;
+    return b2p_context_init(context, B, H, W, net, xbuf, (cudaStream_t)stream);
+}
+
+int b200pose_flow_init(const float* depth, const float* K, const float* G, int B, int H, int W, float* coords1,
+                       float* flow, void* stream) {
+    if (!depth || !K || !G || !coords1 || !flow) return B200POSE_E_NULL;
+    if (B < 1 || H < 16 || W < 16 || (H % 8) || (W % 8)) return B200POSE_E_SHAPE;
+    return b2p_flow_init(depth, K, G, B, H, W, coords1, flow, (cudaStream_t)stream);
+}
+
+size_t b200pose_update_workspace_bytes(int B, int h, int w) { return update_ws_layout(B, h, w, nullptr, 0, nullptr); }
+
+int b200pose_update_block(const void* packed_weights, float* net, float* xbuf, const float* corr, float* coords1,
+                          float* flow, float* mask, float* dflow_out, int B, int h, int w, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    if (!packed_weights || !net || !xbuf || !corr || !coords1 || !flow || !mask || !workspace) return B200POSE_E_NULL;
+    if (B < 1 || h < 1 || w < 1) return B200POSE_E_SHAPE;
+    if (((uintptr_t)workspace & 255) || workspace_bytes < b200pose_update_workspace_bytes(B, h, w)) return B200POSE_E_WORKSPACE;
+    UpdateWs u;
+    update_ws_layout(B, h, w, workspace, workspace_bytes, &u);
+    return run_update_block(reinterpret_cast<const float*>(packed_weights), net, xbuf, corr, coords1, flow, mask, dflow_out,
+                            B, h, w, u, (cudaStream_t)stream);
+}
+
+int b200pose_upsample_weight(const float* flow, const float* mask, const float* geofea1, const float* geofea2,
+                             const float* depth, float sigma, int B, int C, int H, int W, float* flow_up, float* target,
+                             float* weight, void* stream) {
+    if (!flow || !mask) return B200POSE_E_NULL;
+    if (weight && (!geofea1 || !geofea2 || !depth)) return B200POSE_E_NULL;
+    if (B < 1 || H < 8 || W < 8 || (H % 8) || (W % 8) || (weight && C < 1)) return B200POSE_E_SHAPE;
+    return b2p_upsample_weight(flow, mask, geofea1, geofea2, depth, sigma, B, C, H, W, flow_up, target, weight,
+                               (cudaStream_t)stream);
+}
+
+size_t b200pose_lm_workspace_bytes(int B, int H, int W) { return b2p_lm_ws_bytes(B, H, W); }
+
+int b200pose_lm_solve(const float* depth, const float* target, const float* weight, const float* K, float* G, int B,
+                      int H, int W, float depth_offset, int n_steps, double ep_lmbda, double lm_lmbda, double* H_out,
+                      double* b_out, float* delta_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!depth || !target || !weight || !K || !G || !workspace) return B200POSE_E_NULL;
+    if (B < 1 || H < 1 || W < 1) return B200POSE_E_SHAPE;
+    if (n_steps < 0) return B200POSE_E_ARG;
+    if (((uintptr_t)workspace & 255) || workspace_bytes < b2p_lm_ws_bytes(B, H, W)) return B200POSE_E_WORKSPACE;
+    for (int i = 0; i < n_steps; ++i) {
+        int rc = b2p_lm_step(depth, target, weight, K, G, B, H, W, depth_offset, ep_lmbda, lm_lmbda,
+                             H_out ? H_out + (size_t)i * B * 36 : nullptr, b_out ? b_out + (size_t)i * B * 6 : nullptr,
+                             delta_out ? delta_out + (size_t)i * B * 6 : nullptr, workspace, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+size_t b200pose_refine_workspace_bytes(int B, int H, int W) { return refine_ws_layout(B, H, W, nullptr, 0, nullptr); }
+
+int b200pose_refine_launch_count(int n_iters, int n_lm) {
+    // per render iteration: volume + 3 pools + context;  per recurrent iteration: flow_init, lookup,
+    // update block, upsample+weight, 2 launches per LM step
+    return 5 + n_iters * (2 + UPDATE_LAUNCHES + 1 + 2 * n_lm);
+}
+
+int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const float* fmap2, const float* context,
+                          const float* geofea1, const float* geofea2, const float* depth, const float* K, float* G,
+                          float sigma, int B, int C_geo, int H, int W, int n_iters, int n_lm, double ep_lmbda,
+                          double lm_lmbda, float* flow_first, float* flow_last, float* weight_last, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    if (!packed_weights || !fmap1 || !fmap2 || !context || !geofea1 || !geofea2 || !depth || !K || !G || !workspace)
+        return B200POSE_E_NULL;
+    if (!shape_ok(B, H, W) || C_geo < 1) return B200POSE_E_SHAPE;
+    if (n_iters < 0 || n_lm < 0 || !(sigma > 0.f)) return B200POSE_E_ARG;
+    if (((uintptr_t)workspace & 255) || workspace_bytes < b200pose_refine_workspace_bytes(B, H, W)) return B200POSE_E_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int h = H / 8, w = W / 8;
+    const float* wts = reinterpret_cast<const float*>(packed_weights);
+    RefineWs r;
+    refine_ws_layout(B, H, W, workspace, workspace_bytes, &r);
+    int rc;
+    // update_corr_fn == True part (CFNet.py:115-133): pyramid + hidden-state reset, once per render iteration
+    if ((rc = b200pose_corr_pyramid(fmap1, fmap2, B, 256, h, w, r.pyr, stream))) return rc;
+    if ((rc = b2p_context_init(context, B, H, W, r.net, r.xbuf, s))) return rc;
+    for (int it = 0; it < n_iters; ++it) {
+        if ((rc = b2p_flow_init(depth, K, G, B, H, W, r.coords1, r.flow, s))) return rc;
+        if ((rc = b2p_corr_lookup(r.pyr, r.coords1, B, h, w, r.corr, s))) return rc;
+        if ((rc = run_update_block(wts, r.net, r.xbuf, r.corr, r.coords1, r.flow, r.mask, nullptr, B, h, w, r.u, s))) return rc;
+        float* fu = (it == 0 && flow_first) ? flow_first : ((it == n_iters - 1) ? flow_last : nullptr);
+        if ((rc = b2p_upsample_weight(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, fu, r.target,
+                                      r.weight, s))) return rc;
+        if (it == 0 && it == n_iters - 1 && flow_first && flow_last)
+            B2P_CUDA(cudaMemcpyAsync(flow_last, flow_first, (size_t)B * 2 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        for (int k = 0; k < n_lm; ++k)
+            if ((rc = b2p_lm_step(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, nullptr, nullptr, nullptr,
+                                  r.lm, s))) return rc;
+    }
+    if (weight_last && n_iters > 0)
+        B2P_CUDA(cudaMemcpyAsync(weight_last, r.weight, (size_t)B * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+namespace {
+struct HostScratch {
+    float *fmap1, *fmap2, *context, *geo1, *geo2, *depth, *K, *G;
+    void* ws; size_t ws_bytes;
+};
+size_t host_scratch_layout(int B, int C, int H, int W, void* p, size_t cap, HostScratch* out) {
+    const int h = H / 8, w = W / 8;
+    Carver c(p, cap);
+    HostScratch hs;
+    hs.fmap1 = c.take<float>((size_t)B * 256 * h * w);
+    hs.fmap2 = c.take<float>((size_t)B * 256 * h * w);
+    hs.context = c.take<float>((size_t)B * 256 * H * W);
+    hs.geo1 = c.take<float>((size_t)B * C * H * W);
+    hs.geo2 = c.take<float>((size_t)B * C * H * W);
+    hs.depth = c.take<float>((size_t)B * H * W);
+    hs.K = c.take<float>((size_t)B * 9);
+    hs.G = c.take<float>((size_t)B * 16);
+    hs.ws_bytes = refine_ws_layout(B, H, W, nullptr, 0, nullptr);
+    hs.ws = c.take<char>(hs.ws_bytes);
+    if (out) *out = hs;
+    return align_up(c.off, 256);
+}
+}  // namespace
+
+size_t b200pose_refine_host_scratch_bytes(int B, int C_geo, int H, int W) {
+    return host_scratch_layout(B, C_geo, H, W, nullptr, 0, nullptr);
+}
+
+int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_host, const float* fmap2_host,
+                               const float* context_host, const float* geofea1_host, const float* geofea2_host,
+                               const float* depth_host, const float* K_host, float* G_host, float sigma, int B,
+                               int C_geo, int H, int W, int n_iters, int n_lm, double ep_lmbda, double lm_lmbda,
+                               void* device_scratch, size_t device_scratch_bytes, void* stream) {
+    if (!packed_weights || !fmap1_host || !fmap2_host || !context_host || !geofea1_host || !geofea2_host ||
+        !depth_host || !K_host || !G_host || !device_scratch)
+        return B200POSE_E_NULL;
+    if (!shape_ok(B, H, W) || C_geo < 1) return B200POSE_E_SHAPE;
+    if (((uintptr_t)device_scratch & 255) || device_scratch_bytes < b200pose_refine_host_scratch_bytes(B, C_geo, H, W))
+        return B200POSE_E_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    HostScratch hs;
+    host_scratch_layout(B, C_geo, H, W, device_scratch, device_scratch_bytes, &hs);
+    const int h = H / 8, w = W / 8;
+    const size_t f = sizeof(float);
+    B2P_CUDA(cudaMemcpyAsync(hs.fmap1, fmap1_host, (size_t)B * 256 * h * w * f, cudaMemcpyHostToDevice, s));
+    B2P_CUDA(cudaMemcpyAsync(hs.fmap2, fmap2_host, (size_t)B * 256 * h * w * f, cudaMemcpyHostToDevice, s));
+    B2P_CUDA(cudaMemcpyAsync(hs.context, context_host, (size_t)B * 256 * H * W * f, cudaMemcpyHostToDevice, s));
+    B2P_CUDA(cudaMemcpyAsync(hs.geo1, geofea1_host, (size_t)B * C_geo * H * W * f, cudaMemcpyHostToDevice, s));
+    B2P_CUDA(cudaMemcpyAsync(hs.geo2, geofea2_host, (size_t)B * C_geo * H * W * f, cudaMemcpyHostToDevice, s));
+    B2P_CUDA(cudaMemcpyAsync(hs.depth, depth_host, (size_t)B * H * W * f, cudaMemcpyHostToDevice, s));
+    B2P_CUDA(cudaMemcpyAsync(hs.K, K_host, (size_t)B * 9 * f, cudaMemcpyHostToDevice, s));
+    B2P_CUDA(cudaMemcpyAsync(hs.G, G_host, (size_t)B * 16 * f, cudaMemcpyHostToDevice, s));
+    int rc = b200pose_refine_iters(packed_weights, hs.fmap1, hs.fmap2, hs.context, hs.geo1, hs.geo2, hs.depth, hs.K, hs.G,
+                                   sigma, B, C_geo, H, W, n_iters, n_lm, ep_lmbda, lm_lmbda, nullptr, nullptr, nullptr,
+                                   hs.ws, hs.ws_bytes, stream);
+    if (rc) return rc;
+    B2P_CUDA(cudaMemcpyAsync(G_host, hs.G, (size_t)B * 16 * f, cudaMemcpyDeviceToHost, s));
+    B2P_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// Shared declarations for the libb200pose.so kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/b200pose.h"
+
+#define B2P_LAUNCH_CHECK()                                   \
+    do {                                                     \
+        cudaError_t e__ = cudaGetLastError();                \
+        if (e__ != cudaSuccess) return (int)e__;             \
+    } while (0)
+
+#define B2P_CUDA(call)                                       \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return (int)e__;             \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// Packed weight blob (device).  All conv weights are stored GEMM-ready:
+//   W[tap][cin_pad][cout_pad]  (cout contiguous), cin_pad = roundup(cin,16), cout_pad = roundup(cout,64)
+// plus bias[cout_pad].  Fused layers: GRU z|r (cout 256), flow_head.conv1|mask.0 (cout 512).
+// ------------------------------------------------------------------------------------------------
+enum B2PConvId {
+    CV_C1 = 0,   // encoder.convc1 1x1  324 -> 256
+    CV_C2,       // encoder.convc2 3x3  256 -> 192
+    CV_F1,       // encoder.convf1 7x7  2 -> 128, stored as 1x1 over a 98(+14)-wide im2col
+    CV_F2,       // encoder.convf2 3x3  128 -> 64
+    CV_ENC,      // encoder.conv   3x3  256 -> 126
+    CV_ZR1,      // gru.convz1|convr1 1x5 384 -> 256
+    CV_Q1,       // gru.convq1 1x5 384 -> 128
+    CV_ZR2,      // gru.convz2|convr2 5x1
+    CV_Q2,       // gru.convq2 5x1
+    CV_HEADS,    // flow_head.conv1|mask.0 3x3 128 -> 512
+    CV_MASK2,    // mask.2 1x1 256 -> 576
+    CV_COUNT
+};
+
+struct B2PConvDesc {
+    int kh, kw, cin, cout, cin_pad, cout_pad;
+    size_t w_off, b_off;   // float offsets into the packed blob
+};
+
+struct B2PWeightLayout {
+    B2PConvDesc cv[CV_COUNT];
+    size_t fh2_w_off;      // flow_head.conv2 as [2][9][256]
+    size_t fh2_b_off;      // [2]
+    size_t total_floats;
+};
+
+const B2PWeightLayout& b2p_weight_layout();
+
+// conv epilogues
+enum { EPI_NONE = 0, EPI_RELU = 1, EPI_SCALE = 2, EPI_GRU_ZR = 3, EPI_GRU_Q = 4 };
+
+struct ConvParams {
+    const float* src0; int pitch0; int c0;   // input segment 0 (PXC): pointer at first channel, pixel pitch, channels
+    const float* src1; int pitch1; int c1;   // optional segment 1 (c1 = 0 when unused)
+    const float* wgt;                         // [taps][cin_pad][cout_pad]
+    const float* bias;                        // [cout_pad]
+    float* dst; int dst_pitch;                // output (pointer at first channel), pixel pitch
+    int cout, cout_pad, cin_pad;
+    int B, h, w, kh, kw;
+    int epi; float scale;
+    float* zbuf;                              // GRU: z gate [P][128]
+    float* rhbuf;                             // GRU: r*h    [P][128]
+    float* hbuf;                              // GRU: hidden state [P][128] (read; written by EPI_GRU_Q)
+};
+
+int b2p_launch_conv(const ConvParams& p, cudaStream_t s);
+
+// kernels implemented across the .cu files (host launchers; all return 0 / cudaError_t)
+int b2p_corr_volume(const float* f1, const float* f2, int B, int D, int P, float* level0, cudaStream_t s);
+int b2p_corr_pool(const float* src, int NP, int hs, int ws, float* dst, cudaStream_t s);
+int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, cudaStream_t s);
+int b2p_context_init(const float* ctx, int B, int H, int W, float* net, float* xbuf, cudaStream_t s);
+int b2p_flow_init(const float* depth, const float* K, const float* G, int B, int H, int W,
+                  float* coords1, float* flow, cudaStream_t s);
+int b2p_im2col_f1(const float* flow, int B, int h, int w, float* col /*[P][112]*/, float* xbuf /*[P][256] ch 254,255*/,
+                  cudaStream_t s);
+int b2p_flow_head2(const float* hm /*[P][512], first 256 = flow-head features*/, const float* w2, const float* b2,
+                   float* coords1 /*[P][2] in/out*/, float* flow /*[P][2] out = coords1 - coords0*/, float* dflow_out,
+                   int B, int h, int w, cudaStream_t s);
+int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth,
+                        float sigma, int B, int C, int H, int W, float* flow_up, float* target, float* weight,
+                        cudaStream_t s);
+int b2p_lm_step(const float* depth, const float* target, const float* weight, const float* K, float* G,
+                int B, int H, int W, float depth_add, double ep, double lm, double* H_out, double* b_out,
+                float* delta_out, void* ws, cudaStream_t s);
+size_t b2p_lm_ws_bytes(int B, int H, int W);
+int b2p_pack_weights(const float* const* t, float* packed, cudaStream_t s);

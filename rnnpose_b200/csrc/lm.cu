@@ -1,0 +1,250 @@
+// One Levenberg-Marquardt step of the reprojection objective, fully on device:
+//   per-pixel residual + 2x6 SE(3) Jacobian (fp32 geometry, as the reference), fp64 accumulation of
+//   H = sum v w J^T J and b = sum v w J^T r, damping, 6x6 Cholesky solve (NaN -> 0, clamp +-1),
+//   se3 exponential and the left-multiplicative retraction G <- exp(delta) G.
+// reference geometry/transformation.py:265-316 (reprojction_optim), :27-46 (jac_local_perturb),
+//   geometry/projective_ops.py:68-131, geometry/cholesky.py:32-50, geometry/se3.py:228-306.
+// Reduction: registers -> warp shuffles -> shared memory -> per-block partials in global memory; the last
+// block of each sample (ticket counter) sums the partials in a fixed order (deterministic), solves and
+// retracts, so one launch per LM step suffices and nothing returns to the host.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LM_THREADS = 256;
+constexpr int LM_PX_PER_THREAD = 4;
+constexpr int LM_PX_PER_BLOCK = LM_THREADS * LM_PX_PER_THREAD;
+constexpr int NACC = 27;   // 21 upper-triangular entries of H + 6 of b
+
+__device__ __forceinline__ int tri_idx(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }
+
+// fp32 se3 exponential, reference geometry/se3.py:228-281 (Taylor branch below MIN_THETA = 1e-4)
+__device__ void se3_exp_f32(const float* xi, float* dG /*12: rows of [R|t]*/) {
+    const float v0 = xi[0], v1 = xi[1], v2 = xi[2];
+    const float w0 = xi[3], w1 = xi[4], w2 = xi[5];
+    const float th2 = (w0 * w0 + w1 * w1) + w2 * w2;
+    const float th = sqrtf(th2);
+    const float th4 = th2 * th2;
+    const float wx[9] = {0.f, -w2, w1, w2, 0.f, -w0, -w1, w0, 0.f};
+    float wx2[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) wx2[i * 3 + j] = wx[i * 3 + 0] * wx[0 * 3 + j] + wx[i * 3 + 1] * wx[1 * 3 + j] + wx[i * 3 + 2] * wx[2 * 3 + j];
+    float ra, rb, va, vb;
+    if (th < 1e-4f) {
+        ra = 1.0f - (1.0f / 6.0f) * th2 + (1.0f / 120.0f) * th4;
+        rb = 0.5f - (1.0f / 12.0f) * th2 + (1.0f / 720.0f) * th4;
+        va = 0.5f - (1.0f / 24.0f) * th2 + (1.0f / 720.0f) * th4;
+        vb = (1.0f / 6.0f) - (1.0f / 120.0f) * th2 + (1.0f / 5040.0f) * th4;
+    } else {
+        const float eps = 1e-12f;
+        const float s = sinf(th), c = cosf(th);
+        ra = s / (th + eps);
+        rb = (1.f - c) / (th2 + eps);
+        va = (1.f - c) / (th2 + eps);
+        vb = (th - s) / (th2 * th + eps);
+    }
+    float R[9], V[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const float I = (i == 0 || i == 4 || i == 8) ? 1.f : 0.f;
+        R[i] = I + ra * wx[i] + rb * wx2[i];
+        V[i] = I + va * wx[i] + vb * wx2[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        dG[i * 4 + 0] = R[i * 3 + 0]; dG[i * 4 + 1] = R[i * 3 + 1]; dG[i * 4 + 2] = R[i * 3 + 2];
+        dG[i * 4 + 3] = V[i * 3 + 0] * v0 + V[i * 3 + 1] * v1 + V[i * 3 + 2] * v2;
+    }
+}
+
+__global__ void __launch_bounds__(LM_THREADS) lm_step_kernel(
+    const float* __restrict__ depth, const float* __restrict__ target, const float* __restrict__ weight,
+    const float* __restrict__ K, float* __restrict__ G, int B, int H, int W, float depth_add, double ep, double lm,
+    double* __restrict__ partials, unsigned* __restrict__ counters, int nblk,
+    double* __restrict__ H_out, double* __restrict__ b_out, float* __restrict__ delta_out) {
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int N = H * W;
+    const float* Kb = K + b * 9;
+    const float fx = Kb[0], fy = Kb[4], cx = Kb[2], cy = Kb[5];
+    float Gm[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Gm[i] = G[b * 16 + i];
+
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+
+    const float* dptr = depth + (size_t)b * N;
+    const float2* tptr = reinterpret_cast<const float2*>(target) + (size_t)b * N;
+    const float* wptr = weight + (size_t)b * N;
+
+#pragma unroll
+    for (int it = 0; it < LM_PX_PER_THREAD; ++it) {
+        const int px = blockIdx.x * LM_PX_PER_BLOCK + it * LM_THREADS + tid;
+        if (px >= N) break;
+        const int v = px / W, u = px - v * W;
+        const float Z = __ldg(dptr + px) + depth_add;
+        const float2 tg = __ldg(tptr + px);
+        const float wv = __ldg(wptr + px);
+        const float X = Z * ((float)u - cx) / fx;
+        const float Y = Z * ((float)v - cy) / fy;
+        const float X1 = Gm[0] * X + Gm[1] * Y + Gm[2] * Z + Gm[3];
+        const float Y1 = Gm[4] * X + Gm[5] * Y + Gm[6] * Z + Gm[7];
+        const float Z1 = Gm[8] * X + Gm[9] * Y + Gm[10] * Z + Gm[11];
+        const double valid = (Z > 0.1f && Z1 > 0.1f) ? 1.0 : 0.0;
+        const float Zc = fmaxf(Z1, 0.01f);
+        const float x1 = fx * (X1 / Zc) + cx;
+        const float y1 = fy * (Y1 / Zc) + cy;
+        const bool cut = Zc <= 0.02f;
+        const float zi1 = cut ? 0.f : 1.0f / Zc;
+        const float zi2 = cut ? 0.f : 1.0f / (Zc * Zc);
+        const double A = (double)(fx * zi1), C = (double)((-fx * X1) * zi2);
+        const double Bq = (double)(fy * zi1), D = (double)((-fy * Y1) * zi2);
+        const double dX = (double)X1, dY = (double)Y1, dZ = (double)Z1;
+        double J0[6], J1[6];
+        J0[0] = A;   J0[1] = 0.0; J0[2] = C; J0[3] = C * dY;            J0[4] = A * dZ + C * (-dX); J0[5] = A * (-dY);
+        J1[0] = 0.0; J1[1] = Bq;  J1[2] = D; J1[3] = Bq * (-dZ) + D * dY; J1[4] = D * (-dX);          J1[5] = Bq * dX;
+        const double r0 = (double)tg.x - (double)x1;
+        const double r1 = (double)tg.y - (double)y1;
+        const double vw = valid * (double)wv;
+        double wJ0[6], wJ1[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { wJ0[i] = vw * J0[i]; wJ1[i] = vw * J1[i]; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = i; j < 6; ++j) acc[tri_idx(i, j)] += wJ0[i] * J0[j] + wJ1[i] * J1[j];
+            acc[21 + i] += wJ0[i] * r0 + wJ1[i] * r1;
+        }
+    }
+
+    // ---- block reduction (fixed order)
+    __shared__ double red[LM_THREADS / 32][NACC];
+    __shared__ double tot[NACC];
+    __shared__ bool is_last;
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) red[wid][i] = v;
+    }
+    __syncthreads();
+    if (tid < NACC) {
+        double s = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < LM_THREADS / 32; ++wv) s += red[wv][tid];
+        partials[((size_t)b * nblk + blockIdx.x) * NACC + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(&counters[b], 1u);
+        is_last = (t == (unsigned)nblk - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tid < NACC) {
+        double s = 0.0;
+        const double* pp = partials + (size_t)b * nblk * NACC + tid;
+        for (int k = 0; k < nblk; ++k) s += __ldcg(pp + (size_t)k * NACC);
+        tot[tid] = s;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    counters[b] = 0;   // self-cleaning for the next step
+
+    double Hm[6][6], bv[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        bv[i] = tot[21 + i];
+#pragma unroll
+        for (int j = i; j < 6; ++j) { Hm[i][j] = tot[tri_idx(i, j)]; Hm[j][i] = Hm[i][j]; }
+    }
+    if (H_out)
+        for (int i = 0; i < 36; ++i) H_out[(size_t)b * 36 + i] = Hm[i / 6][i % 6];
+    if (b_out)
+        for (int i = 0; i < 6; ++i) b_out[(size_t)b * 6 + i] = bv[i];
+    // damping: H += ep*I + lm*H*I   (transformation.py:300)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Hm[i][i] = Hm[i][i] + (ep + lm * Hm[i][i]);
+    // Cholesky H = L L^T, forward/back substitution (fp64)
+    double L[6][6];
+    for (int j = 0; j < 6; ++j) {
+        double s = Hm[j][j];
+        for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+        const double d = sqrt(s);
+        L[j][j] = d;
+        for (int i = j + 1; i < 6; ++i) {
+            double t = Hm[i][j];
+            for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+            L[i][j] = t / d;
+        }
+    }
+    double yv[6], xv[6];
+    for (int i = 0; i < 6; ++i) {
+        double t = bv[i];
+        for (int k = 0; k < i; ++k) t -= L[i][k] * yv[k];
+        yv[i] = t / L[i][i];
+    }
+    for (int i = 5; i >= 0; --i) {
+        double t = yv[i];
+        for (int k = i + 1; k < 6; ++k) t -= L[k][i] * xv[k];
+        xv[i] = t / L[i][i];
+    }
+    float xi[6];
+    for (int i = 0; i < 6; ++i) {
+        double x = xv[i];
+        if (x != x) x = 0.0;                       // NaN -> 0 (cholesky.py:42-43)
+        x = fmin(fmax(x, -1.0), 1.0);               // clamp to +-max_update (cholesky.py:45)
+        xi[i] = (float)x;
+    }
+    if (delta_out)
+        for (int i = 0; i < 6; ++i) delta_out[(size_t)b * 6 + i] = xi[i];
+    float dG[12];
+    se3_exp_f32(xi, dG);
+    float Gn[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float s = dG[i * 4 + 0] * Gm[0 * 4 + j] + dG[i * 4 + 1] * Gm[1 * 4 + j] + dG[i * 4 + 2] * Gm[2 * 4 + j];
+            if (j == 3) s += dG[i * 4 + 3];       // last row of G is (0,0,0,1)
+            Gn[i * 4 + j] = s;
+        }
+    for (int i = 0; i < 12; ++i) G[b * 16 + i] = Gn[i];
+    G[b * 16 + 12] = 0.f; G[b * 16 + 13] = 0.f; G[b * 16 + 14] = 0.f; G[b * 16 + 15] = 1.f;
+}
+
+__global__ void zero_u32_kernel(unsigned* p, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0u;
+}
+
+}  // namespace
+
+static inline int lm_nblk(int H, int W) { return ceil_div(H * W, LM_PX_PER_BLOCK); }
+
+size_t b2p_lm_ws_bytes(int B, int H, int W) {
+    return align_up((size_t)B * lm_nblk(H, W) * NACC * sizeof(double), 256) + align_up((size_t)B * sizeof(unsigned), 256);
+}
+
+int b2p_lm_step(const float* depth, const float* target, const float* weight, const float* K, float* G, int B, int H,
+                int W, float depth_add, double ep, double lm, double* H_out, double* b_out, float* delta_out, void* ws,
+                cudaStream_t s) {
+    const int nblk = lm_nblk(H, W);
+    double* partials = reinterpret_cast<double*>(ws);
+    unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) +
+                                                     align_up((size_t)B * nblk * NACC * sizeof(double), 256));
+    zero_u32_kernel<<<ceil_div(B, 256), 256, 0, s>>>(counters, B);
+    dim3 grid(nblk, B);
+    lm_step_kernel<<<grid, LM_THREADS, 0, s>>>(depth, target, weight, K, G, B, H, W, depth_add, ep, lm, partials, counters, nblk,
+                                               H_out, b_out, delta_out);
+    B2P_LAUNCH_CHECK();
+    return 0;
+}

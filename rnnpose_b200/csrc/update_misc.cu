@@ -1,0 +1,192 @@
+// Weight packing and the two "skinny" layers of the update block that do not fit the GEMM tile:
+//   encoder.convf1 (7x7, Cin=2): lowered to a 98-wide im2col + 1x1 GEMM,
+//   flow_head.conv2 (3x3, Cout=2): warp-per-pixel dot products, fused with coords1 += delta_flow.
+// reference thirdparty/raft/update.py:13-14,83-97 ; model/CFNet.py:157.
+#include "common.cuh"
+
+namespace {
+
+// dst[tap][c][n_off + n] = src[n][c][ky][kx]     (tap = ky*kw + kx)
+__global__ void pack_conv_kernel(const float* __restrict__ src, int cout, int cin, int kh, int kw,
+                                 float* __restrict__ dst, int cin_pad, int cout_pad, int n_off, int flatten_taps) {
+    const size_t total = (size_t)cout * cin * kh * kw;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int kx = (int)(i % kw); size_t t = i / kw;
+    const int ky = (int)(t % kh); t /= kh;
+    const int c = (int)(t % cin);
+    const int n = (int)(t / cin);
+    const int tap = ky * kw + kx;
+    size_t o;
+    if (flatten_taps) o = ((size_t)(tap * cin + c)) * cout_pad + n_off + n;            // 1x1 over im2col, k = tap*cin + c
+    else o = ((size_t)tap * cin_pad + c) * cout_pad + n_off + n;
+    dst[o] = src[i];
+}
+
+__global__ void pack_vec_kernel(const float* __restrict__ src, int n, float* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+// flow_head.conv2 [2][256][3][3] -> [2][9][256]
+__global__ void pack_fh2_kernel(const float* __restrict__ src, float* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * 256 * 9) return;
+    const int tap = i % 9; int t = i / 9;
+    const int c = t % 256; const int o = t / 256;
+    dst[(o * 9 + tap) * 256 + c] = src[i];
+}
+
+__global__ void __launch_bounds__(256) im2col_f1_kernel(const float* __restrict__ flow, int B, int h, int w,
+                                                        float* __restrict__ col, float* __restrict__ xbuf) {
+    const size_t total = (size_t)B * h * w * 56;          // 56 float2 slots per pixel (49 taps + 7 zero pads)
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int slot = (int)(i % 56);
+    const size_t pix = i / 56;
+    const int hw = h * w;
+    const int b = (int)(pix / hw); const int r = (int)(pix - (size_t)b * hw);
+    const int y = r / w, x = r - y * w;
+    float2 v = make_float2(0.f, 0.f);
+    if (slot < 49) {
+        const int ky = slot / 7, kx = slot - ky * 7;
+        const int sy = y + ky - 3, sx = x + kx - 3;
+        if (sy >= 0 && sy < h && sx >= 0 && sx < w)
+            v = *reinterpret_cast<const float2*>(flow + ((size_t)(b * h + sy) * w + sx) * 2);
+        if (slot == 24) *reinterpret_cast<float2*>(xbuf + pix * 256 + 254) = v;   // centre tap = flow itself -> cat[out, flow]
+    }
+    *reinterpret_cast<float2*>(col + pix * 112 + slot * 2) = v;
+}
+
+__global__ void __launch_bounds__(256) flow_head2_kernel(const float* __restrict__ hm, const float* __restrict__ w2,
+                                                         const float* __restrict__ b2, float* __restrict__ coords1,
+                                                         float* __restrict__ flow,
+                                                         float* __restrict__ dflow_out, int B, int h, int w) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int hw = h * w;
+    if (warp >= B * hw) return;
+    const int b = warp / hw, r = warp - b * hw;
+    const int y = r / w, x = r - y * w;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int sy = y + tap / 3 - 1, sx = x + tap % 3 - 1;
+        if (sy < 0 || sy >= h || sx < 0 || sx >= w) continue;
+        const float* src = hm + ((size_t)(b * h + sy) * w + sx) * 512;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int c = half * 128 + lane * 4;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + c));
+            const float4 u0 = __ldg(reinterpret_cast<const float4*>(w2 + (0 * 9 + tap) * 256 + c));
+            const float4 u1 = __ldg(reinterpret_cast<const float4*>(w2 + (1 * 9 + tap) * 256 + c));
+            s0 += a.x * u0.x + a.y * u0.y + a.z * u0.z + a.w * u0.w;
+            s1 += a.x * u1.x + a.y * u1.y + a.z * u1.z + a.w * u1.w;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane == 0) {
+        const float d0 = s0 + b2[0], d1 = s1 + b2[1];
+        if (dflow_out) { dflow_out[(size_t)warp * 2] = d0; dflow_out[(size_t)warp * 2 + 1] = d1; }
+        // coords1 = coords1 + delta ; flow_lr = coords1 - coords0  (model/CFNet.py:157,166)
+        const float c1x = coords1[(size_t)warp * 2] + d0;
+        const float c1y = coords1[(size_t)warp * 2 + 1] + d1;
+        coords1[(size_t)warp * 2] = c1x;
+        coords1[(size_t)warp * 2 + 1] = c1y;
+        flow[(size_t)warp * 2] = c1x - (float)x;
+        flow[(size_t)warp * 2 + 1] = c1y - (float)y;
+    }
+}
+
+B2PWeightLayout make_layout() {
+    B2PWeightLayout L;
+    auto set = [&](int id, int kh, int kw, int cin, int cout) {
+        B2PConvDesc& d = L.cv[id];
+        d.kh = kh; d.kw = kw; d.cin = cin; d.cout = cout;
+        d.cin_pad = (cin + 15) / 16 * 16; d.cout_pad = (cout + 63) / 64 * 64;
+    };
+    set(CV_C1, 1, 1, 324, 256);
+    set(CV_C2, 3, 3, 256, 192);
+    set(CV_F1, 1, 1, 98, 128);
+    set(CV_F2, 3, 3, 128, 64);
+    set(CV_ENC, 3, 3, 256, 126);
+    set(CV_ZR1, 1, 5, 384, 256);
+    set(CV_Q1, 1, 5, 384, 128);
+    set(CV_ZR2, 5, 1, 384, 256);
+    set(CV_Q2, 5, 1, 384, 128);
+    set(CV_HEADS, 3, 3, 128, 512);
+    set(CV_MASK2, 1, 1, 256, 576);
+    size_t off = 0;
+    for (int i = 0; i < CV_COUNT; ++i) {
+        B2PConvDesc& d = L.cv[i];
+        d.w_off = off; off += (size_t)d.kh * d.kw * d.cin_pad * d.cout_pad;
+        d.b_off = off; off += d.cout_pad;
+        off = (off + 63) / 64 * 64;
+    }
+    L.fh2_w_off = off; off += 2 * 9 * 256;
+    L.fh2_b_off = off; off += 64;
+    L.total_floats = off;
+    return L;
+}
+
+}  // namespace
+
+const B2PWeightLayout& b2p_weight_layout() {
+    static const B2PWeightLayout L = make_layout();
+    return L;
+}
+
+// tensor order (state-dict order):
+//  0,1 convc1 | 2,3 convc2 | 4,5 convf1 | 6,7 convf2 | 8,9 conv | 10,11 convz1 | 12,13 convr1 | 14,15 convq1
+//  16,17 convz2 | 18,19 convr2 | 20,21 convq2 | 22,23 flow_head.conv1 | 24,25 flow_head.conv2 | 26,27 mask.0 | 28,29 mask.2
+int b2p_pack_weights(const float* const* t, float* packed, cudaStream_t s) {
+    const B2PWeightLayout& L = b2p_weight_layout();
+    B2P_CUDA(cudaMemsetAsync(packed, 0, L.total_floats * sizeof(float), s));
+    auto pack = [&](int id, const float* w, const float* b, int cout_src, int cin_src, int kh, int kw, int n_off,
+                    int flatten) -> int {
+        const B2PConvDesc& d = L.cv[id];
+        const size_t total = (size_t)cout_src * cin_src * kh * kw;
+        pack_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, cout_src, cin_src, kh, kw, packed + d.w_off,
+                                                                         d.cin_pad, d.cout_pad, n_off, flatten);
+        pack_vec_kernel<<<ceil_div(cout_src, 256), 256, 0, s>>>(b, cout_src, packed + d.b_off + n_off);
+        B2P_LAUNCH_CHECK();
+        return 0;
+    };
+    int rc = 0;
+    if ((rc = pack(CV_C1, t[0], t[1], 256, 324, 1, 1, 0, 0))) return rc;
+    if ((rc = pack(CV_C2, t[2], t[3], 192, 256, 3, 3, 0, 0))) return rc;
+    if ((rc = pack(CV_F1, t[4], t[5], 128, 2, 7, 7, 0, 1))) return rc;
+    if ((rc = pack(CV_F2, t[6], t[7], 64, 128, 3, 3, 0, 0))) return rc;
+    if ((rc = pack(CV_ENC, t[8], t[9], 126, 256, 3, 3, 0, 0))) return rc;
+    if ((rc = pack(CV_ZR1, t[10], t[11], 128, 384, 1, 5, 0, 0))) return rc;
+    if ((rc = pack(CV_ZR1, t[12], t[13], 128, 384, 1, 5, 128, 0))) return rc;
+    if ((rc = pack(CV_Q1, t[14], t[15], 128, 384, 1, 5, 0, 0))) return rc;
+    if ((rc = pack(CV_ZR2, t[16], t[17], 128, 384, 5, 1, 0, 0))) return rc;
+    if ((rc = pack(CV_ZR2, t[18], t[19], 128, 384, 5, 1, 128, 0))) return rc;
+    if ((rc = pack(CV_Q2, t[20], t[21], 128, 384, 5, 1, 0, 0))) return rc;
+    if ((rc = pack(CV_HEADS, t[22], t[23], 256, 128, 3, 3, 0, 0))) return rc;
+    if ((rc = pack(CV_HEADS, t[26], t[27], 256, 128, 3, 3, 256, 0))) return rc;
+    if ((rc = pack(CV_MASK2, t[28], t[29], 576, 256, 1, 1, 0, 0))) return rc;
+    pack_fh2_kernel<<<ceil_div(2 * 256 * 9, 256), 256, 0, s>>>(t[24], packed + L.fh2_w_off);
+    pack_vec_kernel<<<1, 256, 0, s>>>(t[25], 2, packed + L.fh2_b_off);
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2p_im2col_f1(const float* flow, int B, int h, int w, float* col, float* xbuf, cudaStream_t s) {
+    const size_t total = (size_t)B * h * w * 56;
+    im2col_f1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(flow, B, h, w, col, xbuf);
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2p_flow_head2(const float* hm, const float* w2, const float* b2, float* coords1, float* flow, float* dflow_out,
+                   int B, int h, int w, cudaStream_t s) {
+    flow_head2_kernel<<<ceil_div(B * h * w, 8), 256, 0, s>>>(hm, w2, b2, coords1, flow, dflow_out, B, h, w);
+    B2P_LAUNCH_CHECK();
+    return 0;
+}

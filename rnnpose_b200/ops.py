@@ -1,0 +1,236 @@
+"""Thin torch <-> C-ABI glue: each function hands raw device pointers, sizes and the current CUDA stream
+to libb200pose.so.  torch is used for device memory and streams only; all arithmetic happens in the
+library's kernels.  Layouts: "PXC" = [B*h*w, C] pixel-major (see include/b200pose.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+CORR_PITCH = 328
+WEIGHT_KEYS: List[str] = [
+    "encoder.convc1", "encoder.convc2", "encoder.convf1", "encoder.convf2", "encoder.conv",
+    "gru.convz1", "gru.convr1", "gru.convq1", "gru.convz2", "gru.convr2", "gru.convq2",
+    "flow_head.conv1", "flow_head.conv2", "mask.0", "mask.2",
+]
+LM_LMBDA = 1e-4   # reference config/default.py:54
+EP_LMBDA = 100.0  # reference config/default.py:55
+
+
+def _need_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("rnnpose_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError(f"{name}: expected a contiguous CUDA {dtype} tensor, got {t.device} {t.dtype} "
+                         f"contiguous={t.is_contiguous()}")
+    return t
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def pack_weights(state: Dict[str, torch.Tensor], device="cuda") -> torch.Tensor:
+    """state: ``cf_net.update_block`` state dict (keys 'encoder.convc1.weight', ...).  Returns the packed
+    device blob consumed by update_block / refine_iters."""
+    _need_cuda()
+    L = _lib.lib()
+    tens = []
+    for k in WEIGHT_KEYS:
+        for sfx in (".weight", ".bias"):
+            tens.append(state[k + sfx].detach().to(device=device, dtype=torch.float32).contiguous())
+    arr = (C.c_void_p * len(tens))(*[t.data_ptr() for t in tens])
+    blob = torch.empty(L.b200pose_packed_weights_bytes(), dtype=torch.uint8, device=device)
+    _lib.check(L.b200pose_pack_weights(arr, blob.data_ptr(), _stream()), "b200pose_pack_weights")
+    torch.cuda.current_stream().synchronize()      # `tens` must outlive the packing kernels
+    return blob
+
+
+def pyramid_level_views(pyr: torch.Tensor, B: int, h: int, w: int) -> List[torch.Tensor]:
+    out, off, hl, wl = [], 0, h, w
+    for _ in range(4):
+        n = B * h * w * hl * wl
+        out.append(pyr[off:off + n].view(B, h * w, hl, wl))
+        off += n; hl //= 2; wl //= 2
+    return out
+
+
+def corr_pyramid(fmap1: torch.Tensor, fmap2: torch.Tensor) -> torch.Tensor:
+    _need_cuda()
+    L = _lib.lib()
+    _chk(fmap1, "fmap1"); _chk(fmap2, "fmap2")
+    B, D, h, w = fmap1.shape
+    pyr = torch.empty(L.b200pose_pyramid_floats(B, h, w), dtype=torch.float32, device=fmap1.device)
+    _lib.check(L.b200pose_corr_pyramid(fmap1.data_ptr(), fmap2.data_ptr(), B, D, h, w, pyr.data_ptr(), _stream()),
+               "b200pose_corr_pyramid")
+    return pyr
+
+
+def corr_lookup(pyr: torch.Tensor, coords: torch.Tensor, B: int, h: int, w: int) -> torch.Tensor:
+    L = _lib.lib()
+    _chk(pyr, "pyramid"); _chk(coords, "coords")
+    out = torch.empty(B * h * w, CORR_PITCH, dtype=torch.float32, device=pyr.device)
+    _lib.check(L.b200pose_corr_lookup(pyr.data_ptr(), coords.data_ptr(), B, h, w, out.data_ptr(), _stream()),
+               "b200pose_corr_lookup")
+    return out
+
+
+def context_init(context: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    L = _lib.lib()
+    _chk(context, "context")
+    B, Cc, H, W = context.shape
+    assert Cc == 256
+    P = B * (H // 8) * (W // 8)
+    net = torch.empty(P, 128, dtype=torch.float32, device=context.device)
+    xbuf = torch.zeros(P, 256, dtype=torch.float32, device=context.device)
+    _lib.check(L.b200pose_context_init(context.data_ptr(), B, H, W, net.data_ptr(), xbuf.data_ptr(), _stream()),
+               "b200pose_context_init")
+    return net, xbuf
+
+
+def flow_init(depth: torch.Tensor, K: torch.Tensor, G: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    L = _lib.lib()
+    _chk(depth, "depth"); _chk(K, "K"); _chk(G, "G")
+    B, H, W = depth.shape
+    P = B * (H // 8) * (W // 8)
+    coords1 = torch.empty(P, 2, dtype=torch.float32, device=depth.device)
+    flow = torch.empty(P, 2, dtype=torch.float32, device=depth.device)
+    _lib.check(L.b200pose_flow_init(depth.data_ptr(), K.data_ptr(), G.data_ptr(), B, H, W, coords1.data_ptr(),
+                                    flow.data_ptr(), _stream()), "b200pose_flow_init")
+    return coords1, flow
+
+
+def update_block(packed: torch.Tensor, net: torch.Tensor, xbuf: torch.Tensor, corr: torch.Tensor,
+                 coords1: torch.Tensor, flow: torch.Tensor, B: int, h: int, w: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """In place on net / coords1 / flow; returns (mask [P,576], dflow [P,2])."""
+    L = _lib.lib()
+    for t, n in ((net, "net"), (xbuf, "xbuf"), (corr, "corr"), (coords1, "coords1"), (flow, "flow")):
+        _chk(t, n)
+    P = B * h * w
+    mask = torch.empty(P, 576, dtype=torch.float32, device=net.device)
+    dflow = torch.empty(P, 2, dtype=torch.float32, device=net.device)
+    nb = L.b200pose_update_workspace_bytes(B, h, w)
+    ws = _ws(nb, net.device)
+    _lib.check(L.b200pose_update_block(packed.data_ptr(), net.data_ptr(), xbuf.data_ptr(), corr.data_ptr(),
+                                       coords1.data_ptr(), flow.data_ptr(), mask.data_ptr(), dflow.data_ptr(),
+                                       B, h, w, ws.data_ptr(), nb, _stream()), "b200pose_update_block")
+    return mask, dflow
+
+
+def upsample_weight(flow: torch.Tensor, mask: torch.Tensor, geofea1: Optional[torch.Tensor],
+                    geofea2: Optional[torch.Tensor], depth: Optional[torch.Tensor], sigma: float,
+                    B: int, H: int, W: int, want_flow_up: bool = True):
+    L = _lib.lib()
+    _chk(flow, "flow"); _chk(mask, "mask")
+    dev = flow.device
+    flow_up = torch.empty(B, 2, H, W, dtype=torch.float32, device=dev) if want_flow_up else None
+    target = torch.empty(B, H, W, 2, dtype=torch.float32, device=dev)
+    weight = None
+    Cg = 0
+    if geofea1 is not None:
+        _chk(geofea1, "geofea1"); _chk(geofea2, "geofea2"); _chk(depth, "depth")
+        Cg = geofea1.shape[1]
+        weight = torch.empty(B, H, W, dtype=torch.float32, device=dev)
+    _lib.check(L.b200pose_upsample_weight(flow.data_ptr(), mask.data_ptr(), _p(geofea1), _p(geofea2), _p(depth),
+                                          float(sigma), B, Cg, H, W, _p(flow_up), target.data_ptr(), _p(weight),
+                                          _stream()), "b200pose_upsample_weight")
+    return flow_up, target, weight
+
+
+def lm_solve(depth: torch.Tensor, target: torch.Tensor, weight: torch.Tensor, K: torch.Tensor, G: torch.Tensor,
+             n_steps: int, ep_lmbda: float = EP_LMBDA, lm_lmbda: float = LM_LMBDA, taps: bool = False,
+             depth_offset: float = 0.0):
+    """Mirrors SE3Sequence.reprojction_optim(target, weight, depth, intrinsics, num_iters): ``depth`` is what the
+    reference passes there (syn_depth + 1e-5) unless depth_offset is given.  G [B,4,4] is updated in place.  With taps=True also returns (H [n,B,6,6] f64, b [n,B,6] f64, delta [n,B,6])."""
+    L = _lib.lib()
+    for t, n in ((depth, "depth"), (target, "target"), (weight, "weight"), (K, "K"), (G, "G")):
+        _chk(t, n)
+    B, H, W = depth.shape
+    dev = depth.device
+    Ho = bo = do = None
+    if taps:
+        Ho = torch.zeros(n_steps, B, 6, 6, dtype=torch.float64, device=dev)
+        bo = torch.zeros(n_steps, B, 6, dtype=torch.float64, device=dev)
+        do = torch.zeros(n_steps, B, 6, dtype=torch.float32, device=dev)
+    nb = L.b200pose_lm_workspace_bytes(B, H, W)
+    ws = _ws(nb, dev)
+    _lib.check(L.b200pose_lm_solve(depth.data_ptr(), target.data_ptr(), weight.data_ptr(), K.data_ptr(), G.data_ptr(),
+                                   B, H, W, float(depth_offset), n_steps, float(ep_lmbda), float(lm_lmbda), _p(Ho), _p(bo), _p(do),
+                                   ws.data_ptr(), nb, _stream()), "b200pose_lm_solve")
+    return (G, Ho, bo, do) if taps else G
+
+
+class RefineWorkspace:
+    """Caller-owned scratch for refine_iters (re-used across calls of the same shape)."""
+
+    def __init__(self, B: int, H: int, W: int, device="cuda"):
+        self.key = (B, H, W)
+        self.nbytes = _lib.lib().b200pose_refine_workspace_bytes(B, H, W)
+        self.buf = _ws(self.nbytes, device)
+
+
+def refine_iters(packed: torch.Tensor, fmap1, fmap2, context, geofea1, geofea2, depth, K, G, sigma: float,
+                 n_iters: int, n_lm: int, ep_lmbda: float = EP_LMBDA, lm_lmbda: float = LM_LMBDA,
+                 workspace: Optional[RefineWorkspace] = None, want_flows: bool = False, want_weight: bool = False):
+    """The fused inner loop (b200pose_refine_iters).  depth [B,H,W]; G [B,4,4] updated in place.
+    Returns dict(G=..., flow_first=..., flow_last=..., weight=...)."""
+    _need_cuda()
+    L = _lib.lib()
+    for t, n in ((fmap1, "fmap1"), (fmap2, "fmap2"), (context, "context"), (geofea1, "geofea1"), (geofea2, "geofea2"),
+                 (depth, "depth"), (K, "K"), (G, "G")):
+        _chk(t, n)
+    B, H, W = depth.shape
+    Cg = geofea1.shape[1]
+    dev = depth.device
+    if workspace is None or workspace.key != (B, H, W):
+        workspace = RefineWorkspace(B, H, W, dev)
+    ff = torch.empty(B, 2, H, W, dtype=torch.float32, device=dev) if want_flows else None
+    fl = torch.empty(B, 2, H, W, dtype=torch.float32, device=dev) if want_flows else None
+    wl = torch.empty(B, H, W, dtype=torch.float32, device=dev) if want_weight else None
+    _lib.check(L.b200pose_refine_iters(packed.data_ptr(), fmap1.data_ptr(), fmap2.data_ptr(), context.data_ptr(),
+                                       geofea1.data_ptr(), geofea2.data_ptr(), depth.data_ptr(), K.data_ptr(),
+                                       G.data_ptr(), float(sigma), B, Cg, H, W, n_iters, n_lm, float(ep_lmbda),
+                                       float(lm_lmbda), _p(ff), _p(fl), _p(wl), workspace.buf.data_ptr(),
+                                       workspace.nbytes, _stream()), "b200pose_refine_iters")
+    return dict(G=G, flow_first=ff, flow_last=fl, weight=wl, workspace=workspace)
+
+
+def refine_iters_host(packed: torch.Tensor, fmap1, fmap2, context, geofea1, geofea2, depth, K, G, sigma: float,
+                      n_iters: int, n_lm: int, ep_lmbda: float = EP_LMBDA, lm_lmbda: float = LM_LMBDA,
+                      scratch: Optional[torch.Tensor] = None):
+    """Host-buffer entry point (b200pose_refine_iters_host): all tensors are CPU float32 (pinned for full
+    copy speed); G [B,4,4] is overwritten on the host.  Synchronises the stream before returning."""
+    _need_cuda()
+    L = _lib.lib()
+    for t in (fmap1, fmap2, context, geofea1, geofea2, depth, K, G):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("refine_iters_host expects contiguous CPU float32 tensors")
+    B, H, W = depth.shape
+    Cg = geofea1.shape[1]
+    nb = L.b200pose_refine_host_scratch_bytes(B, Cg, H, W)
+    if scratch is None or scratch.numel() < nb:
+        scratch = _ws(nb, packed.device)
+    _lib.check(L.b200pose_refine_iters_host(packed.data_ptr(), fmap1.data_ptr(), fmap2.data_ptr(), context.data_ptr(),
+                                            geofea1.data_ptr(), geofea2.data_ptr(), depth.data_ptr(), K.data_ptr(),
+                                            G.data_ptr(), float(sigma), B, Cg, H, W, n_iters, n_lm, float(ep_lmbda),
+                                            float(lm_lmbda), scratch.data_ptr(), scratch.numel(), _stream()),
+               "b200pose_refine_iters_host")
+    return G, scratch
+
+
+def launch_count(n_iters: int, n_lm: int) -> int:
+    return _lib.lib().b200pose_refine_launch_count(n_iters, n_lm)

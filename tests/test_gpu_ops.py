@@ -1,0 +1,224 @@
+"""Parity of every CUDA entry point (through the C-ABI) with the oracle and with the golden vectors of
+the executed reference.  Run on the B200 box:  python -m pytest tests -m gpu"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import refine_oracle as O
+from rnnpose_b200 import synthetic as S
+from tests.util import golden, load_update_weights
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def to_pxc(x):      # [B,C,h,w] -> [B*h*w, C]
+    B, C, h, w = x.shape
+    return x.permute(0, 2, 3, 1).reshape(B * h * w, C).contiguous()
+
+
+def from_pxc(x, B, h, w):
+    return x.view(B, h, w, -1).permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from rnnpose_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def packed(ops):
+    return ops.pack_weights(load_update_weights(), dev())
+
+
+def test_corr_pyramid_and_lookup_golden(ops):
+    g = golden("corr_lookup.npz")
+    B, D, h, w, s1, s2 = [int(v) for v in g["meta"]]
+    f1 = S.hash_features((B, D, h, w), s1).to(dev()); f2 = S.hash_features((B, D, h, w), s2).to(dev())
+    pyr = ops.corr_pyramid(f1, f2)
+    lv = ops.pyramid_level_views(pyr, B, h, w)
+    assert [tuple(v.shape[-2:]) for v in lv] == [(17, 22), (8, 11), (4, 5), (2, 2)]
+    for l, key in ((0, "pyr0"), (1, "pyr1"), (3, "pyr3")):
+        torch.testing.assert_close(lv[l].cpu(), T(g[key]), rtol=1e-5, atol=3e-6)
+    ref = O.corr_pyramid(f1.cpu(), f2.cpu())
+    for l in range(4):
+        torch.testing.assert_close(lv[l].cpu(), ref[l], rtol=1e-5, atol=3e-6)
+    coords = T(g["coords"]).to(dev())
+    out = ops.corr_lookup(pyr, to_pxc(coords), B, h, w)
+    assert out.shape == (B * h * w, 328)
+    assert torch.all(out[:, 324:] == 0)
+    torch.testing.assert_close(from_pxc(out[:, :324].contiguous(), B, h, w).cpu(), T(g["out"]), rtol=1e-5, atol=5e-6)
+
+
+def test_corr_pyramid_full_size_vs_oracle(ops):
+    B, D, h, w = 2, 256, 30, 40
+    f1 = S.hash_features((B, D, h, w), 11).to(dev()); f2 = S.hash_features((B, D, h, w), 12).to(dev())
+    lv = ops.pyramid_level_views(ops.corr_pyramid(f1, f2), B, h, w)
+    ref = O.corr_pyramid(f1.cpu(), f2.cpu())
+    assert [tuple(v.shape[-2:]) for v in lv] == [(30, 40), (15, 20), (7, 10), (3, 5)]
+    for l in range(4):
+        torch.testing.assert_close(lv[l].cpu(), ref[l], rtol=2e-5, atol=2e-5)
+
+
+def test_context_init(ops):
+    B, H, W = 2, 128, 160
+    ctx = S.hash_features((B, 256, H, W), 21, 0.5).to(dev())
+    net, xbuf = ops.context_init(ctx)
+    rnet, rinp = O.context_init(ctx.cpu(), W // 8)
+    torch.testing.assert_close(from_pxc(net, B, H // 8, W // 8).cpu(), rnet, rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(from_pxc(xbuf[:, :128].contiguous(), B, H // 8, W // 8).cpu(), rinp, rtol=1e-5, atol=2e-6)
+
+
+def test_flow_init(ops):
+    mb = S.make_batch([0, 3], 128, 160, with_images=False)
+    depth = mb["depth"][:, 0].contiguous()
+    G = O.se3_exp(torch.tensor([[0.01, -0.02, 0.015, 0.02, -0.01, 0.03], [-0.03, 0.01, 0.0, -0.015, 0.025, -0.02]]))
+    c1, fl = ops.flow_init(depth.to(dev()), mb["K"].to(dev()), G.to(dev()))
+    ref = O.flow_init_lowres(depth + O.EPS_DEPTH, mb["K"], G)
+    B, h, w = 2, 16, 20
+    torch.testing.assert_close(from_pxc(fl, B, h, w).cpu(), ref, rtol=1e-4, atol=2e-5)
+    u, v = O.pixel_grid(h, w)
+    torch.testing.assert_close(from_pxc(c1, B, h, w).cpu(), ref + torch.stack([u, v])[None], rtol=1e-5, atol=2e-5)
+
+
+def test_update_block_golden(ops, packed):
+    g = golden("update_block.npz")
+    B, h, w, s1, s2, s3, s4 = [int(v) for v in g["meta"]]
+    net = torch.tanh(S.hash_features((B, 128, h, w), s1)); inp = torch.relu(S.hash_features((B, 128, h, w), s2))
+    corr = S.hash_features((B, 324, h, w), s3, 2.0); flow = S.hash_features((B, 2, h, w), s4, 4.0)
+    P = B * h * w
+    netd = to_pxc(net).to(dev())
+    xbuf = torch.zeros(P, 256, device=dev()); xbuf[:, :128] = to_pxc(inp).to(dev())
+    corrd = torch.zeros(P, 328, device=dev()); corrd[:, :324] = to_pxc(corr).to(dev())
+    u, v = O.pixel_grid(h, w)
+    flowd = to_pxc(flow).to(dev())
+    coords1 = (to_pxc(torch.stack([u, v])[None].expand(B, 2, h, w)).to(dev()) + flowd).contiguous()
+    mask, dflow = ops.update_block(packed, netd, xbuf, corrd, coords1, flowd, B, h, w)
+    torch.testing.assert_close(from_pxc(netd, B, h, w).cpu(), T(g["net_out"]), rtol=1e-4, atol=3e-5)
+    torch.testing.assert_close(from_pxc(mask, B, h, w).cpu(), T(g["mask"]), rtol=1e-4, atol=3e-5)
+    torch.testing.assert_close(from_pxc(dflow, B, h, w).cpu(), T(g["dflow"]), rtol=1e-4, atol=3e-5)
+    # flow out = (coords1 + dflow) - coords0
+    torch.testing.assert_close(from_pxc(flowd, B, h, w).cpu(), flow + T(g["dflow"]), rtol=1e-4, atol=5e-5)
+
+
+def test_update_block_ragged_tile(ops, packed):
+    """P not a multiple of the 128-pixel tile and a 1-row map: exercises the M-tail and the halo predicates."""
+    wts = load_update_weights()
+    for (B, h, w) in ((1, 1, 5), (3, 7, 13)):
+        net = torch.tanh(S.hash_features((B, 128, h, w), 31)); inp = torch.relu(S.hash_features((B, 128, h, w), 32))
+        corr = S.hash_features((B, 324, h, w), 33, 2.0); flow = S.hash_features((B, 2, h, w), 34, 4.0)
+        rn, rm, rd = O.update_block(wts, net, inp, corr, flow)
+        P = B * h * w
+        netd = to_pxc(net).to(dev())
+        xbuf = torch.zeros(P, 256, device=dev()); xbuf[:, :128] = to_pxc(inp).to(dev())
+        corrd = torch.zeros(P, 328, device=dev()); corrd[:, :324] = to_pxc(corr).to(dev())
+        flowd = to_pxc(flow).to(dev())
+        coords1 = flowd.clone()
+        mask, dflow = ops.update_block(packed, netd, xbuf, corrd, coords1, flowd, B, h, w)
+        torch.testing.assert_close(from_pxc(netd, B, h, w).cpu(), rn, rtol=1e-4, atol=3e-5)
+        torch.testing.assert_close(from_pxc(mask, B, h, w).cpu(), rm, rtol=1e-4, atol=3e-5)
+        torch.testing.assert_close(from_pxc(dflow, B, h, w).cpu(), rd, rtol=1e-4, atol=3e-5)
+
+
+def test_upsample_golden(ops):
+    g = golden("upsample.npz")
+    B, h, w, s1, s2 = [int(v) for v in g["meta"]]
+    fl = S.hash_features((B, 2, h, w), s1, 3.0); mk = S.hash_features((B, 576, h, w), s2, 2.0)
+    fu, tgt, wgt = ops.upsample_weight(to_pxc(fl).to(dev()), to_pxc(mk).to(dev()), None, None, None, 1.0, B, 8 * h, 8 * w)
+    assert wgt is None
+    torch.testing.assert_close(fu.cpu(), T(g["out"]), rtol=1e-5, atol=1e-5)
+    u, v = O.pixel_grid(8 * h, 8 * w)
+    torch.testing.assert_close(tgt.cpu(), torch.stack([T(g["out"])[:, 0] + u, T(g["out"])[:, 1] + v], -1), rtol=1e-5, atol=2e-5)
+
+
+def test_upsample_weight_vs_oracle(ops):
+    B, C, h, w = 2, 32, 6, 9
+    H, W = 8 * h, 8 * w
+    fl = S.hash_features((B, 2, h, w), 41, 2.5); fl[0, :, 0, 0] = torch.tensor([-9.0, -7.0]); fl[1, :, -1, -1] = 11.0
+    mk = S.hash_features((B, 576, h, w), 42, 2.0)
+    g1 = S.hash_features((B, C, H, W), 43); g1 = g1 / g1.norm(dim=1, keepdim=True)
+    g2 = S.hash_features((B, C, H, W), 44); g2 = g2 / g2.norm(dim=1, keepdim=True)
+    depth = (S.hash_features((B, H, W), 45) > -0.3).float() * 0.9
+    fu, tgt, wgt = ops.upsample_weight(to_pxc(fl).to(dev()), to_pxc(mk).to(dev()), g1.to(dev()), g2.to(dev()),
+                                       depth.to(dev()), 0.7, B, H, W)
+    rfu = O.convex_upsample(fl, mk)
+    u, v = O.pixel_grid(H, W)
+    rt = torch.stack([rfu[:, 0] + u, rfu[:, 1] + v], -1)
+    torch.testing.assert_close(fu.cpu(), rfu, rtol=1e-5, atol=1e-5)
+    rw = O.corr_weight(g1, g2, rt, depth, 0.7)
+    torch.testing.assert_close(wgt.cpu(), rw, rtol=1e-4, atol=1e-5)
+    assert torch.all(wgt.cpu()[depth == 0] == 0)
+
+
+def test_weight_golden_via_identity_mask(ops):
+    """G5 fixture: drive the fused kernel with a mask that selects the centre tap (softmax -> one-hot) so
+    that target = grid + 8*flow, then compare the weight with the executed reference."""
+    g = golden("weight.npz")
+    B, C, H, W, s1, s2, s3, s4 = [int(v) for v in g["meta"]]
+    h, w = H // 8, W // 8
+    g1 = S.hash_features((B, C, H, W), s1); g1 = g1 / g1.norm(dim=1, keepdim=True)
+    g2 = S.hash_features((B, C, H, W), s2); g2 = g2 / g2.norm(dim=1, keepdim=True)
+    depth = (S.hash_features((B, 1, H, W), s4) > -0.3).float()[:, 0] * 0.9
+    # oracle weight on the kernel's own target (flow piecewise constant over 8x8 blocks)
+    fl = S.hash_features((B, 2, h, w), 77, 0.6)
+    mk = torch.full((B, 9, 64, h, w), -200.0); mk[:, 4] = 200.0
+    fu, tgt, wgt = ops.upsample_weight(to_pxc(fl).to(dev()), to_pxc(mk.reshape(B, 576, h, w)).to(dev()), g1.to(dev()),
+                                       g2.to(dev()), depth.to(dev()), float(g["sigma"]), B, H, W)
+    rw = O.corr_weight(g1, g2, tgt.cpu(), depth, float(g["sigma"]))
+    torch.testing.assert_close(wgt.cpu(), rw, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_lm_golden(ops, n):
+    g = golden("lm.npz")
+    depth = T(g["depth"])                               # = syn_depth + EPS, as reprojction_optim receives it
+    tgt, wgt, K = T(g["target"]), T(g["weight"]), T(g["K"])
+    G = T(g["G_in"]).clone().to(dev())
+    G, Ho, bo, do = ops.lm_solve(depth.to(dev()), tgt.to(dev()), wgt.to(dev()), K.to(dev()), G, n, taps=True)
+    eye = torch.eye(6, dtype=torch.float64)
+    for it in range(n):
+        Hd = Ho[it].cpu() + 100.0 * eye + 1e-4 * Ho[it].cpu() * eye
+        torch.testing.assert_close(Hd, T(g[f"Hd_{n}"][it]), rtol=1e-7, atol=1e-3)
+        torch.testing.assert_close(bo[it].cpu(), T(g[f"b_{n}"][it]), rtol=1e-6, atol=1e-2)
+    torch.testing.assert_close(G.cpu(), T(g[f"G_out_{n}"]), rtol=0, atol=5e-6)
+
+
+def test_lm_near_plane_and_nan(ops):
+    g = golden("lm.npz")
+    depth = T(g["depth"])
+    tgt, wgt, K = T(g["target"]), T(g["weight"]), T(g["K"])
+    G = T(g["G_in_near"]).clone().to(dev())
+    G = ops.lm_solve(depth.to(dev()), tgt.to(dev()), wgt.to(dev()), K.to(dev()), G, 2)
+    torch.testing.assert_close(G.cpu(), T(g["G_out_near"]), rtol=0, atol=1e-5)
+    # NaN weight in sample 0: zero update for sample 0 (cholesky.py:42-45), sample 1 unaffected
+    w2 = wgt.clone(); w2[0, 5, 5] = float("nan")
+    G0 = T(g["G_in"]).clone()
+    Gd, Ho, bo, do = ops.lm_solve(depth.to(dev()), tgt.to(dev()), w2.to(dev()), K.to(dev()), G0.clone().to(dev()), 1, taps=True)
+    assert torch.all(do[0, 0] == 0)
+    torch.testing.assert_close(Gd[0].cpu(), G0[0], rtol=0, atol=1e-7)
+    torch.testing.assert_close(Gd[1].cpu(), T(g["G_out_1"])[1], rtol=0, atol=5e-6)
+
+
+def test_lm_vs_oracle_random(ops):
+    mb = S.make_batch([1, 2, 4], 128, 160, with_images=False)
+    depth = mb["depth"][:, 0].contiguous()
+    B, H, W = depth.shape
+    u, v = O.pixel_grid(H, W)
+    tgt = torch.stack([u, v], -1)[None].repeat(B, 1, 1, 1) + S.hash_features((B, H, W, 2), 51, 1.5)
+    wgt = torch.rand(B, H, W, generator=torch.Generator().manual_seed(5)) * (depth > 0)
+    G = O.se3_exp(S.hash_features((B, 6), 52, 0.02))
+    Gr = G.clone()
+    for _ in range(3):
+        Gr, _, Hm, bv = O.lm_step(depth + O.EPS_DEPTH, tgt, wgt, mb["K"], Gr)
+    Gd = ops.lm_solve(depth.to(dev()), tgt.to(dev()), wgt.to(dev()), mb["K"].to(dev()), G.clone().to(dev()), 3,
+                      depth_offset=1e-5)
+    torch.testing.assert_close(Gd.cpu(), Gr, rtol=0, atol=5e-6)

@@ -1,0 +1,134 @@
+"""End-to-end parity of the fused inner loop (b200pose_refine_iters through the C-ABI) with
+(1) the golden outputs of the executed reference, (2) the oracle on batched inputs, and size-independent
+properties at the BASELINE.json sizes.  Tolerance (north_star): final SE3 within 1e-4 abs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import refine_oracle as O
+from rnnpose_b200 import synthetic as S
+from tests.util import golden, load_update_weights
+
+pytestmark = pytest.mark.gpu
+SE3_TOL = 1e-4
+
+
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from rnnpose_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def packed(ops):
+    return ops.pack_weights(load_update_weights(), dev())
+
+
+def run_gpu(ops, packed, fmap1, fmap2, mb, G0, n_iters, n_lm, **kw):
+    d = dev()
+    G = G0.clone().to(d).contiguous()
+    res = ops.refine_iters(packed, fmap1.to(d).contiguous(), fmap2.to(d).contiguous(), mb["context"].to(d),
+                           mb["geofea1"].to(d), mb["geofea2"].to(d), mb["depth"][:, 0].contiguous().to(d),
+                           mb["K"].to(d), G, 1.0, n_iters, n_lm, **kw)
+    torch.cuda.synchronize()
+    return res
+
+
+@pytest.mark.parametrize("name", ["refine_cfg0_240x320_1x1.npz", "refine_128x160_4x3.npz",
+                                  "refine_240x320_4x3.npz", "refine_occl_128x160_8x3.npz"])
+def test_refine_matches_reference_golden(ops, packed, name):
+    g = golden(name)
+    H, W, n_iters, n_lm, seed, occl = [int(v) for v in g["meta"]]
+    idxs = [int(i) for i in g["idxs"]]
+    mb = S.make_batch(idxs, H, W, seed, bool(occl), with_images=False)
+    res = run_gpu(ops, packed, T(g["fmap1"]), T(g["fmap2"]), mb, T(g["G0"]), n_iters, n_lm, want_flows=True, want_weight=True)
+    Tij = res["G"].cpu()
+    Ti_pred = torch.matmul(Tij, mb["T_init"])                       # PoseRefiner.py:365
+    err = (Ti_pred - T(g["Ti_pred"])).abs().max().item()
+    assert err < SE3_TOL, f"final SE3 differs from the reference by {err}"
+    assert (Tij - T(g["Tij"])).abs().max().item() < SE3_TOL
+    torch.testing.assert_close(res["flow_last"].cpu()[:, :, ::4, ::4], T(g["flow_last"]), rtol=1e-3, atol=2e-2)
+    torch.testing.assert_close(res["flow_first"].cpu()[:, :, ::4, ::4], T(g["flow_first"]), rtol=1e-3, atol=2e-2)
+    torch.testing.assert_close(res["weight"].cpu()[:, ::4, ::4], T(g["weight"]), rtol=1e-3, atol=1e-3)
+    # ADD(-S) of prediction vs ground truth must agree with the reference to 4 decimals (in units of the diameter)
+    for k, idx in enumerate(idxs):
+        sc = S.make_scene(idx, H, W, seed, bool(occl))
+        pts = torch.from_numpy(S.model_points(sc))
+        Tg = mb["T_gt"][k:k + 1]
+        for sym in (False, True):
+            a = O.add_metric(Ti_pred[k:k + 1, :3, :3], Ti_pred[k:k + 1, :3, 3], Tg[:, :3, :3], Tg[:, :3, 3], pts, sym)
+            r = T(g["Ti_pred"])[k:k + 1]
+            b = O.add_metric(r[:, :3, :3], r[:, :3, 3], Tg[:, :3, :3], Tg[:, :3, 3], pts, sym)
+            assert abs(a.item() - b.item()) / sc.diameter < 5e-5
+
+
+def test_refine_batched_vs_oracle(ops, packed):
+    """A native batch of 3 different scenes equals three oracle (= reference B=1) runs."""
+    H, W, idxs = 128, 160, [7, 8, 9]
+    mb = S.make_batch(idxs, H, W, with_images=False)
+    f1 = S.hash_features((3, 256, H // 8, W // 8), 61); f2 = S.hash_features((3, 256, H // 8, W // 8), 62)
+    G0 = torch.eye(4)[None].repeat(3, 1, 1)
+    ref = O.refine_inner_loop(load_update_weights(), f1, f2, mb["context"], mb["geofea1"], mb["geofea2"], mb["depth"],
+                              mb["K"], G0, n_iters=2, n_lm=2)
+    res = run_gpu(ops, packed, f1, f2, mb, G0, 2, 2, want_flows=True)
+    assert (res["G"].cpu() - ref["G"]).abs().max().item() < SE3_TOL
+    torch.testing.assert_close(res["flow_last"].cpu(), ref["flows"][-1], rtol=1e-3, atol=2e-2)
+
+
+def test_refine_full_size_batch_properties(ops, packed):
+    """BASELINE configs[1] shape (B=32, 240x320, 4x3): per-sample results do not depend on batch position or
+    batch size (bit-exact), outputs are finite rigid transforms, and a subset agrees with the oracle."""
+    H, W, B = 240, 320, 32
+    uniq = S.make_batch([0, 1, 2, 3], H, W, with_images=False)
+    rep = {k: v.repeat(8, *([1] * (v.dim() - 1))) for k, v in uniq.items() if k != "diameter"}
+    f1u = S.hash_features((4, 256, H // 8, W // 8), 71); f2u = S.hash_features((4, 256, H // 8, W // 8), 72)
+    f1 = f1u.repeat(8, 1, 1, 1); f2 = f2u.repeat(8, 1, 1, 1)
+    G0 = torch.eye(4)[None].repeat(B, 1, 1)
+    G = run_gpu(ops, packed, f1, f2, rep, G0, 4, 3)["G"].cpu()
+    assert torch.isfinite(G).all()
+    for k in range(4, B):
+        assert torch.equal(G[k], G[k % 4]), f"sample {k} differs from its copy {k % 4}"
+    R = G[:, :3, :3]
+    torch.testing.assert_close(torch.matmul(R, R.transpose(1, 2)), torch.eye(3)[None].repeat(B, 1, 1), rtol=0, atol=1e-5)
+    assert torch.all(G[:, 3] == torch.tensor([0.0, 0.0, 0.0, 1.0]))
+    # batch of 1 == slot 0 of the batch of 32
+    one = {k: v[:1].contiguous() for k, v in uniq.items() if k != "diameter"}
+    G1 = run_gpu(ops, packed, f1u[:1], f2u[:1], one, G0[:1], 4, 3)["G"].cpu()
+    assert torch.equal(G1[0], G[0])
+    # oracle on two of the samples
+    sub = {k: v[:2].contiguous() for k, v in uniq.items() if k != "diameter"}
+    ref = O.refine_inner_loop(load_update_weights(), f1u[:2], f2u[:2], sub["context"], sub["geofea1"], sub["geofea2"],
+                              sub["depth"], sub["K"], G0[:2], n_iters=4, n_lm=3)
+    assert (G[:2] - ref["G"]).abs().max().item() < SE3_TOL
+
+
+def test_refine_host_entry_matches_device_entry(ops, packed):
+    H, W, idxs = 128, 160, [11, 12]
+    mb = S.make_batch(idxs, H, W, with_images=False)
+    f1 = S.hash_features((2, 256, H // 8, W // 8), 81); f2 = S.hash_features((2, 256, H // 8, W // 8), 82)
+    G0 = torch.eye(4)[None].repeat(2, 1, 1)
+    Gd = run_gpu(ops, packed, f1, f2, mb, G0, 2, 1)["G"].cpu()
+    Gh = G0.clone()
+    ops.refine_iters_host(packed, f1, f2, mb["context"], mb["geofea1"], mb["geofea2"], mb["depth"][:, 0].contiguous(),
+                          mb["K"], Gh, 1.0, 2, 1)
+    assert torch.equal(Gh, Gd)
+
+
+def test_error_codes(ops, packed):
+    from rnnpose_b200 import _lib
+    L = _lib.lib()
+    assert L.b200pose_refine_iters(None, None, None, None, None, None, None, None, None, 1.0, 1, 32, 128, 160, 1, 1,
+                                   100.0, 1e-4, None, None, None, None, 0, None) == -1
+    mb = S.make_batch([0], 64, 64, with_images=False)       # h/8 = 8 -> level 3 is 1x1: rejected like the reference's NaN
+    f = S.hash_features((1, 256, 8, 8), 1)
+    with pytest.raises(RuntimeError, match="unsupported shape"):
+        run_gpu(ops, packed, f, f, mb, torch.eye(4)[None], 1, 1)
