@@ -422,3 +422,105 @@ def rotation_angle_deg(R_p, R_g) -> torch.Tensor:
     """utils/geometric.py:36-40: 2*asin(||R_g - R_p||_F / sqrt(8)) in degrees."""
     n = (R_g - R_p).reshape(R_p.shape[0], -1).norm(dim=1)
     return 2 * torch.asin(torch.clamp(n / math.sqrt(8.0), max=1.0)) * 180.0 / math.pi
+
+
+# ----------------------------------------------------------------------------- timing variant
+# The functions above spell every resampling / pooling / solve out explicitly so that the restatement is
+# independent of the ATen calls the reference makes.  For the CPU *timing* baseline that would be unfair
+# (explicit gathers are ~3x slower than grid_sample), so `refine_inner_loop_aten` below issues the SAME ATen
+# op sequence as the reference (grid_sample, interpolate, avg_pool2d, unfold, einsum in fp64,
+# linalg.cholesky / cholesky_solve) -- it is what bench.py times as the CPU baseline / reference arm, and
+# tests/test_oracle_golden.py checks that it agrees with the explicit restatement and the golden vectors.
+def _bilinear_sampler_aten(img, coords):
+    """thirdparty/raft/utils/utils.py:57-65."""
+    Hs, Ws = img.shape[-2:]
+    xg, yg = coords.split([1, 1], dim=-1)
+    grid = torch.cat([2 * xg / (Ws - 1) - 1, 2 * yg / (Hs - 1) - 1], dim=-1)
+    return F.grid_sample(img, grid, align_corners=True)
+
+
+def refine_inner_loop_aten(wts, fmap1, fmap2, context_fea, geofea1, geofea2, syn_depth, K, G0, sigma=1.0,
+                           n_iters=4, n_lm=3, lm_lmbda=LM_LMBDA, ep_lmbda=EP_LMBDA):
+    """Same contract as refine_inner_loop; op sequence of model/PoseRefiner.py:313-365, model/CFNet.py:109-173,
+    thirdparty/raft/corr.py:13-57, geometry/transformation.py:265-316 for batch size 1 (as the reference)."""
+    assert fmap1.shape[0] == 1, "the reference path is batch-size-1 only (SURVEY finding 1)"
+    B, D, h, w = fmap1.shape
+    H, W = syn_depth.shape[-2:]
+    # CorrBlock.__init__
+    corr = torch.matmul(fmap1.view(B, D, h * w).transpose(1, 2), fmap2.view(B, D, h * w)).view(B * h * w, 1, h, w)
+    corr = corr / torch.sqrt(torch.tensor(D).float())
+    pyr = [corr]
+    for _ in range(CORR_LEVELS - 1):
+        corr = F.avg_pool2d(corr, 2, stride=2)
+        pyr.append(corr)
+    cnet = F.interpolate(context_fea, scale_factor=1 / 8, mode="bilinear", align_corners=True)
+    net, inp = torch.split(cnet, [128, 128], dim=1)
+    net = torch.tanh(net); inp = torch.relu(inp)
+    depths = syn_depth + EPS_DEPTH                                    # [B,1,H,W]
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    grid_full = torch.stack([xx.float(), yy.float()], dim=-1)[None, None]     # [1,1,H,W,2]
+    yl, xl = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    coords0 = torch.stack([xl, yl], dim=0).float()[None]
+    fx, fy, cx, cy = (K[:, 0, 0].view(B, 1, 1, 1), K[:, 1, 1].view(B, 1, 1, 1), K[:, 0, 2].view(B, 1, 1, 1), K[:, 1, 2].view(B, 1, 1, 1))
+    G = G0.clone()[:, None]                                            # [B,1,4,4]
+    eye6 = torch.eye(6, dtype=torch.float64)
+    flows = []
+    r = CORR_RADIUS
+    for it in range(n_iters):
+        X0 = torch.stack([depths * (grid_full[..., 0] - cx) / fx, depths * (grid_full[..., 1] - cy) / fy, depths], dim=-1)
+        Xh = torch.cat([X0, torch.ones_like(X0[..., :1])], dim=-1)
+        X1 = torch.einsum("aijk,ai...k->ai...j", G[..., :3, :], Xh)
+        Zc = torch.clamp(X1[..., 2], min=MIN_DEPTH_PROJ)
+        reproj = torch.stack([fx * (X1[..., 0] / Zc) + cx, fy * (X1[..., 1] / Zc) + cy], dim=-1)
+        flow_init = torch.einsum("...ijk->...kij", reproj - grid_full) * (depths > EPS_DEPTH)
+        flow_init = flow_init.squeeze(1) / 8
+        flow_init = F.interpolate(flow_init, scale_factor=1 / 8, mode="bilinear", align_corners=True)
+        coords1 = coords0 + flow_init
+        # CorrBlock.__call__
+        cperm = coords1.permute(0, 2, 3, 1)
+        outp = []
+        for i in range(CORR_LEVELS):
+            dx = torch.linspace(-r, r, 2 * r + 1); dy = torch.linspace(-r, r, 2 * r + 1)
+            delta = torch.stack(torch.meshgrid(dy, dx, indexing="ij"), axis=-1)
+            cl = cperm.reshape(B * h * w, 1, 1, 2) / 2 ** i + delta.view(1, 2 * r + 1, 2 * r + 1, 2)
+            outp.append(_bilinear_sampler_aten(pyr[i], cl).view(B, h, w, -1))
+        corr_f = torch.cat(outp, dim=-1).permute(0, 3, 1, 2).contiguous().float()
+        net, up_mask, dflow = update_block(wts, net, inp, corr_f, coords1 - coords0)
+        coords1 = coords1 + dflow
+        # upsample_flow
+        mask = torch.softmax(up_mask.view(B, 1, 9, 8, 8, h, w), dim=2)
+        up = F.unfold(8 * (coords1 - coords0), [3, 3], padding=1).view(B, 2, 9, 1, 1, h, w)
+        flow_up = torch.sum(mask * up, dim=2).permute(0, 1, 4, 2, 5, 3).reshape(B, 2, H, W)
+        flows.append(flow_up)
+        target = torch.einsum("...ijk->...jki", flow_up[:, None]) + grid_full
+        tn = target.clone()
+        tn[..., 0] = 2 * tn[..., 0] / (W - 1) - 1; tn[..., 1] = 2 * tn[..., 1] / (H - 1) - 1
+        warp = F.grid_sample(geofea2, tn.squeeze(1))
+        cw = torch.sum(geofea1 * warp, dim=1, keepdim=True).permute(0, 2, 3, 1)[:, None]
+        cw = torch.exp(-torch.abs(1 - cw) / sigma) * (syn_depth > 0)[..., None].float()
+        # reprojction_optim
+        tgt64 = target.double(); w64 = cw.double()[..., None]
+        for _ in range(n_lm):
+            X1 = torch.einsum("aijk,ai...k->ai...j", G[..., :3, :], Xh)
+            Xc, Yc, Zr = X1[..., 0], X1[..., 1], X1[..., 2]
+            Zc = torch.clamp(Zr, min=MIN_DEPTH_PROJ)
+            x1 = torch.stack([fx * (Xc / Zc) + cx, fy * (Yc / Zc) + cy], dim=-1)
+            o = torch.zeros_like(Zc); one = torch.ones_like(Zc)
+            zi1 = torch.where(Zc <= MIN_DEPTH_PROJ + .01, o, 1.0 / Zc); zi2 = torch.where(Zc <= MIN_DEPTH_PROJ + .01, o, 1.0 / Zc ** 2)
+            jproj = torch.stack([torch.stack([fx * zi1, o, -fx * Xc * zi2], -1), torch.stack([o, fy * zi1, -fy * Yc * zi2], -1)], -2)
+            jtran = torch.stack([torch.cat([one[..., None], o[..., None], o[..., None]], -1), torch.cat([o[..., None], one[..., None], o[..., None]], -1),
+                                 torch.cat([o[..., None], o[..., None], one[..., None]], -1), torch.stack([o, -Zr, Yc], -1),
+                                 torch.stack([Zr, o, -Xc], -1), torch.stack([-Yc, Xc, o], -1)], dim=-1)
+            v = ((X0[..., -1] > MIN_DEPTH_VALID) & (Zr > MIN_DEPTH_VALID)).double()[..., None, None]
+            J = torch.einsum("...ij,...jk->...ik", jproj.double(), jtran.double())
+            Hm = torch.einsum("aixyrj,aixyrk->aijk", v * w64 * J, J)
+            bv = torch.einsum("aixyrj,aixyr->aij", v * w64 * J, tgt64 - x1)
+            Hm = Hm + ep_lmbda * eye6 + lm_lmbda * Hm * eye6
+            try:
+                x = torch.cholesky_solve(bv.unsqueeze(-1), torch.linalg.cholesky(Hm))
+            except Exception:
+                x = torch.full_like(bv.unsqueeze(-1), float("nan"))
+            x = torch.where(torch.isnan(x), torch.zeros_like(x), x)
+            delta = torch.clamp(x, -1.0, 1.0).squeeze(-1).float()
+            G = torch.matmul(se3_exp(delta.reshape(-1, 6)).view(B, 1, 4, 4), G)
+    return dict(G=G[:, 0], flows=flows, weight=cw[:, 0, :, :, 0])

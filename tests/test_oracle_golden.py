@@ -144,3 +144,19 @@ def test_g8_full_inner_loop(name):
     assert err < 2e-5, f"oracle drifted from the reference more than expected: {err}"
     torch.testing.assert_close(res["flows"][-1][:, :, ::4, ::4], T(g["flow_last"]), rtol=1e-3, atol=5e-3)
     torch.testing.assert_close(res["weight"][:, ::4, ::4], T(g["weight"]), rtol=1e-3, atol=1e-4)
+
+
+def test_aten_sequence_variant_matches_reference_and_restatement():
+    """refine_inner_loop_aten (what bench.py times as the CPU baseline: the reference's own ATen op sequence)
+    agrees with the executed reference and with the explicit restatement."""
+    g = golden("refine_128x160_4x3.npz")
+    H, W, n_iters, n_lm, seed, occl = [int(v) for v in g["meta"]]
+    idxs = [int(i) for i in g["idxs"]]
+    mb = S.make_batch(idxs[:1], H, W, seed, bool(occl), with_images=False)
+    args = (load_update_weights(), T(g["fmap1"])[:1], T(g["fmap2"])[:1], mb["context"], mb["geofea1"], mb["geofea2"],
+            mb["depth"], mb["K"], T(g["G0"])[:1])
+    a = O.refine_inner_loop_aten(*args, n_iters=n_iters, n_lm=n_lm)
+    b = O.refine_inner_loop(*args, n_iters=n_iters, n_lm=n_lm)
+    Ti = torch.matmul(a["G"], mb["T_init"])
+    assert (Ti - T(g["Ti_pred"])[:1]).abs().max().item() < 2e-5
+    assert (a["G"] - b["G"]).abs().max().item() < 2e-5
