@@ -45,6 +45,11 @@ extern "C" {
 #define B200POSE_CORR_PITCH    328   /* PXC pitch of the lookup output (pad channels are zero) */
 #define B200POSE_NUM_WEIGHT_TENSORS 30
 
+/* `flags` bits of b200pose_update_block / b200pose_refine_iters[_host] */
+#define B200POSE_FLAG_EXACT_FP32    0   /* CUDA-core FFMA convolutions, fp32 throughout (LM step fp64) */
+#define B200POSE_FLAG_TENSOR_CORES  1   /* tcgen05 convolutions, fp16 hi/lo split operands (x ~= hi+lo, 3 MMAs,
+                                           fp32 TMEM accumulate): fp32-level accuracy, see DESIGN.md section 5 */
+
 int b200pose_version(void);
 const char* b200pose_error_string(int code);
 
@@ -57,7 +62,7 @@ const char* b200pose_error_string(int code);
  *   gru.convz1, gru.convr1, gru.convq1, gru.convz2, gru.convr2, gru.convq2,
  *   flow_head.conv1, flow_head.conv2, mask.0, mask.2          (each: weight then bias)
  * `packed` = caller-owned device buffer of b200pose_packed_weights_bytes() bytes (256-B aligned)
- * that receives the kernel-side layouts; it stays valid as long as the caller keeps it.          */
+ * that receives the kernel-side layouts (fp32 GEMM layouts + fp16 hi/lo planes); it stays valid as long as the caller keeps it.          */
 size_t b200pose_packed_weights_bytes(void);
 int b200pose_pack_weights(const float* const* tensors_host /* host array of 30 device ptrs */,
                           void* packed, void* stream);
@@ -102,7 +107,19 @@ int b200pose_flow_init(const float* depth, const float* K, const float* G, int B
 size_t b200pose_update_workspace_bytes(int B, int h, int w);
 int b200pose_update_block(const void* packed_weights, float* net, float* xbuf, const float* corr,
                           float* coords1, float* flow, float* mask, float* dflow_out /* [P][2] or NULL */,
-                          int B, int h, int w, void* workspace, size_t workspace_bytes, void* stream);
+                          int B, int h, int w, int flags, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a3-a5 (single layer; test / micro-benchmark entry) ---------------------------------------
+ * One convolution of the update block (nn.Conv2d of thirdparty/raft/update.py) WITHOUT activation:
+ * out[P][pitch] = conv(in) + bias, pitch = roundup(cout,4).  layer: 0 convc1, 1 convc2, 2 convf1 (as a
+ * 1x1 over the 98-wide im2col), 3 convf2, 4 conv, 5 convz1|convr1, 6 convq1, 7 convz2|convr2, 8 convq2,
+ * 9 flow_head.conv1|mask.0, 10 mask.2.  in0/in1: PXC fp32 inputs (in1 only for the GRU layers: in0 = h or
+ * r*h [P][128], in1 = x [P][256]).  b200pose_conv_layer_info reports the channel counts.            */
+size_t b200pose_conv_layer_workspace_bytes(int B, int h, int w);
+int b200pose_conv_layer_info(int layer, int* cin0, int* cin1, int* cout, int* kh, int* kw);
+int b200pose_conv_layer(const void* packed_weights, int layer, const float* in0, int pitch0,
+                        const float* in1, int pitch1, float* out, int B, int h, int w, int flags,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a7 + a9: convex upsampling fused with the correspondence weight --------------------------
  * Replaces GRU_CFUpdator.upsample_flow (model/CFNet.py:95-106), target = flow + grid
@@ -144,7 +161,7 @@ int b200pose_refine_iters(const void* packed_weights,
                           const float* geofea1, const float* geofea2, const float* depth,
                           const float* K, float* G, float sigma,
                           int B, int C_geo, int H, int W, int n_iters, int n_lm,
-                          double ep_lmbda, double lm_lmbda,
+                          double ep_lmbda, double lm_lmbda, int flags,
                           float* flow_first, float* flow_last, float* weight_last,
                           void* workspace, size_t workspace_bytes, void* stream);
 
@@ -157,7 +174,7 @@ int b200pose_refine_iters_host(const void* packed_weights,
                                const float* geofea1_host, const float* geofea2_host, const float* depth_host,
                                const float* K_host, float* G_host, float sigma,
                                int B, int C_geo, int H, int W, int n_iters, int n_lm,
-                               double ep_lmbda, double lm_lmbda,
+                               double ep_lmbda, double lm_lmbda, int flags,
                                void* device_scratch, size_t device_scratch_bytes, void* stream);
 
 /* number of kernel launches b200pose_refine_iters enqueues (for bench.py's gpu_launches) */

@@ -24,14 +24,17 @@ SIGNATURES = {
     "b200pose_context_init": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "b200pose_flow_init": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "b200pose_update_workspace_bytes": (_sz, [_i, _i, _i]),
-    "b200pose_update_block": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "b200pose_update_block": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "b200pose_conv_layer_workspace_bytes": (_sz, [_i, _i, _i]),
+    "b200pose_conv_layer_info": (_i, [_i] + [C.POINTER(_i)] * 5),
+    "b200pose_conv_layer": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "b200pose_upsample_weight": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "b200pose_lm_workspace_bytes": (_sz, [_i, _i, _i]),
     "b200pose_lm_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _d, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200pose_refine_workspace_bytes": (_sz, [_i, _i, _i]),
-    "b200pose_refine_iters": (_i, [_vp] * 9 + [_f, _i, _i, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200pose_refine_iters": (_i, [_vp] * 9 + [_f, _i, _i, _i, _i, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200pose_refine_host_scratch_bytes": (_sz, [_i, _i, _i, _i]),
-    "b200pose_refine_iters_host": (_i, [_vp] * 9 + [_f, _i, _i, _i, _i, _i, _i, _d, _d, _vp, _sz, _vp]),
+    "b200pose_refine_iters_host": (_i, [_vp] * 9 + [_f, _i, _i, _i, _i, _i, _i, _d, _d, _i, _vp, _sz, _vp]),
     "b200pose_refine_launch_count": (_i, [_i, _i]),
 }
 

@@ -10,16 +10,18 @@ struct Carver {
     char* base; size_t off; size_t cap;
     Carver(void* p, size_t c) : base(reinterpret_cast<char*>(p)), off(0), cap(c) {}
     template <typename T> T* take(size_t n) {
-        off = align_up(off, 256);
+        off = align_up(off, 1024);
         T* r = reinterpret_cast<T*>(base + off);
         off += n * sizeof(T);
         return r;
     }
-    bool ok() const { return off <= cap; }
 };
 
+// scratch of one update-block pass.  fp32 buffers serve the exact FFMA path; the __half hi/lo plane pairs
+// ([0] = hi, [1] = lo) serve the tensor-core path.
 struct UpdateWs {
     float *col, *c1, *corflo, *f1o, *zbuf, *rhbuf, *hm;
+    __half *corr_h[2], *col_h[2], *c1_h[2], *corflo_h[2], *f1o_h[2], *x_h[2], *net_h[2], *rh_h[2], *hm_h[2];
 };
 
 size_t update_ws_layout(int B, int h, int w, void* ws, size_t cap, UpdateWs* out) {
@@ -33,14 +35,28 @@ size_t update_ws_layout(int B, int h, int w, void* ws, size_t cap, UpdateWs* out
     u.zbuf = c.take<float>(P * 128);
     u.rhbuf = c.take<float>(P * 128);
     u.hm = c.take<float>(P * 512);
+    for (int k = 0; k < 2; ++k) {
+        u.corr_h[k] = c.take<__half>(P * B200POSE_CORR_PITCH);
+        u.col_h[k] = c.take<__half>(P * 112);
+        u.c1_h[k] = c.take<__half>(P * 256);
+        u.corflo_h[k] = c.take<__half>(P * 256);
+        u.f1o_h[k] = c.take<__half>(P * 128);
+        u.x_h[k] = c.take<__half>(P * 256);
+        u.net_h[k] = c.take<__half>(P * 128);
+        u.rh_h[k] = c.take<__half>(P * 128);
+        u.hm_h[k] = c.take<__half>(P * 512);
+    }
     if (out) *out = u;
-    return align_up(c.off, 256);
+    return align_up(c.off, 1024);
 }
 
 inline bool shape_ok(int B, int H, int W) {
     return B >= 1 && H >= 128 && W >= 128 && (H % 8) == 0 && (W % 8) == 0;   // (H/8)>>3 >= 2: the reference's
 }                                                                             // sampler divides by (w_l - 1)
 
+// ------------------------------------------------------------------------------------------------
+// exact fp32 path (CUDA-core FFMA implicit GEMM)
+// ------------------------------------------------------------------------------------------------
 int run_update_block(const float* wts, float* net, float* xbuf, const float* corr, float* coords1, float* flow,
                      float* mask, float* dflow_out, int B, int h, int w, const UpdateWs& u, cudaStream_t s) {
     const B2PWeightLayout& L = b2p_weight_layout();
@@ -57,7 +73,7 @@ int run_update_block(const float* wts, float* net, float* xbuf, const float* cor
         return b2p_launch_conv(p, s);
     };
     // motion encoder (update.py:89-97)
-    if ((rc = b2p_im2col_f1(flow, B, h, w, u.col, xbuf, s))) return rc;                               // + cat[out, flow]
+    if ((rc = b2p_im2col_f1(flow, B, h, w, u.col, xbuf, nullptr, nullptr, nullptr, nullptr, s))) return rc;   // + cat[out, flow]
     if ((rc = conv(CV_C1, corr, B200POSE_CORR_PITCH, 324, nullptr, 0, 0, u.c1, 256, EPI_RELU, 1.f))) return rc;
     if ((rc = conv(CV_C2, u.c1, 256, 256, nullptr, 0, 0, u.corflo, 256, EPI_RELU, 1.f))) return rc;    // cor -> [0,192)
     if ((rc = conv(CV_F1, u.col, 112, 98, nullptr, 0, 0, u.f1o, 128, EPI_RELU, 1.f))) return rc;
@@ -70,11 +86,51 @@ int run_update_block(const float* wts, float* net, float* xbuf, const float* cor
     if ((rc = conv(CV_Q2, u.rhbuf, 128, 128, xbuf, 256, 256, nullptr, 0, EPI_GRU_Q, 1.f))) return rc;
     // heads (update.py:13-14, 172-176, 187)
     if ((rc = conv(CV_HEADS, net, 128, 128, nullptr, 0, 0, u.hm, 512, EPI_RELU, 1.f))) return rc;
-    if ((rc = b2p_flow_head2(u.hm, wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, B, h, w, s))) return rc;
+    if ((rc = b2p_flow_head2(u.hm, nullptr, nullptr, wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, B, h, w, s))) return rc;
     if ((rc = conv(CV_MASK2, u.hm + 256, 512, 256, nullptr, 0, 0, mask, 576, EPI_SCALE, 0.25f))) return rc;
     return 0;
 }
 constexpr int UPDATE_LAUNCHES = 13;
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core path (tcgen05, fp16 hi/lo operands).  Expects u.corr_h, u.net_h and u.x_h[:, 0:128] filled.
+// ------------------------------------------------------------------------------------------------
+int run_update_block_tc(const float* wts, float* net, float* coords1, float* flow, float* mask, float* dflow_out,
+                        int B, int h, int w, const UpdateWs& u, cudaStream_t s) {
+    const B2PWeightLayout& L = b2p_weight_layout();
+    const B2PHalfLayout& HL = b2p_half_layout();
+    const __half* hbase = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(wts) + b2p_half_section_offset_bytes());
+    int rc;
+    auto conv = [&](int id, __half* const* s0, int off0, int c0, int p0, __half* const* s1, int c1n, int p1,
+                    __half* const* dst, int doff, int dpitch, int epi, float scale, float* out_f32, int f32_pitch) -> int {
+        const B2PHalfConvDesc& d = HL.cv[id];
+        UmmaConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.seg_hi[0] = s0[0] + off0; a.seg_lo[0] = s0[1] + off0; a.seg_c[0] = c0; a.seg_pitch[0] = p0;
+        if (s1) { a.seg_hi[1] = s1[0]; a.seg_lo[1] = s1[1]; a.seg_c[1] = c1n; a.seg_pitch[1] = p1; }
+        a.w_hi = hbase + d.hi_off; a.w_lo = hbase + d.lo_off; a.bias = wts + L.cv[id].b_off;
+        a.cin_pad = d.cin_pad; a.cout_pad = d.cout_pad; a.cout = d.cout; a.n_tile = d.n_tile; a.kh = d.kh; a.kw = d.kw;
+        a.B = B; a.h = h; a.w = w; a.epi = epi; a.scale = scale;
+        a.out_f32 = out_f32; a.out_f32_pitch = f32_pitch;
+        if (dst) { a.out_hi = dst[0] + doff; a.out_lo = dst[1] + doff; a.out_h_pitch = dpitch; }
+        a.zbuf = u.zbuf; a.hbuf = net;
+        return b2p_launch_conv_umma(a, s);
+    };
+    if ((rc = b2p_im2col_f1(flow, B, h, w, nullptr, nullptr, u.col_h[0], u.col_h[1], u.x_h[0], u.x_h[1], s))) return rc;
+    if ((rc = conv(CV_C1, u.corr_h, 0, B200POSE_CORR_PITCH, B200POSE_CORR_PITCH, nullptr, 0, 0, u.c1_h, 0, 256, EPI_RELU, 1.f, nullptr, 0))) return rc;
+    if ((rc = conv(CV_C2, u.c1_h, 0, 256, 256, nullptr, 0, 0, u.corflo_h, 0, 256, EPI_RELU, 1.f, nullptr, 0))) return rc;
+    if ((rc = conv(CV_F1, u.col_h, 0, 112, 112, nullptr, 0, 0, u.f1o_h, 0, 128, EPI_RELU, 1.f, nullptr, 0))) return rc;
+    if ((rc = conv(CV_F2, u.f1o_h, 0, 128, 128, nullptr, 0, 0, u.corflo_h, 192, 256, EPI_RELU, 1.f, nullptr, 0))) return rc;
+    if ((rc = conv(CV_ENC, u.corflo_h, 0, 256, 256, nullptr, 0, 0, u.x_h, 128, 256, EPI_RELU, 1.f, nullptr, 0))) return rc;
+    if ((rc = conv(CV_ZR1, u.net_h, 0, 128, 128, u.x_h, 256, 256, u.rh_h, 0, 128, EPI_GRU_ZR, 1.f, nullptr, 0))) return rc;
+    if ((rc = conv(CV_Q1, u.rh_h, 0, 128, 128, u.x_h, 256, 256, u.net_h, 0, 128, EPI_GRU_Q, 1.f, nullptr, 0))) return rc;
+    if ((rc = conv(CV_ZR2, u.net_h, 0, 128, 128, u.x_h, 256, 256, u.rh_h, 0, 128, EPI_GRU_ZR, 1.f, nullptr, 0))) return rc;
+    if ((rc = conv(CV_Q2, u.rh_h, 0, 128, 128, u.x_h, 256, 256, u.net_h, 0, 128, EPI_GRU_Q, 1.f, nullptr, 0))) return rc;
+    if ((rc = conv(CV_HEADS, u.net_h, 0, 128, 128, nullptr, 0, 0, u.hm_h, 0, 512, EPI_RELU, 1.f, nullptr, 0))) return rc;
+    if ((rc = b2p_flow_head2(nullptr, u.hm_h[0], u.hm_h[1], wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, B, h, w, s))) return rc;
+    if ((rc = conv(CV_MASK2, u.hm_h, 256, 256, 512, nullptr, 0, 0, nullptr, 0, 0, EPI_SCALE, 0.25f, mask, 576))) return rc;
+    return 0;
+}
 
 struct RefineWs {
     float *pyr, *net, *xbuf, *corr, *coords1, *flow, *mask, *target, *weight;
@@ -97,7 +153,7 @@ size_t refine_ws_layout(int B, int H, int W, void* ws, size_t cap, RefineWs* out
     r.target = c.take<float>(N * 2);
     r.weight = c.take<float>(N);
     r.lm = c.take<char>(b2p_lm_ws_bytes(B, H, W));
-    c.off = align_up(c.off, 256);
+    c.off = align_up(c.off, 1024);
     const size_t used = update_ws_layout(B, h, w, ws ? c.base + c.off : nullptr, cap > c.off ? cap - c.off : 0, &r.u);
     if (out) *out = r;
     return c.off + used;
@@ -120,10 +176,13 @@ const char* b200pose_error_string(int code) {
     }
 }
 
-size_t b200pose_packed_weights_bytes(void) { return b2p_weight_layout().total_floats * sizeof(float); }
+size_t b200pose_packed_weights_bytes(void) {
+    return b2p_half_section_offset_bytes() + b2p_half_layout().total_halves * sizeof(__half);
+}
 
 int b200pose_pack_weights(const float* const* tensors_host, void* packed, void* stream) {
     if (!tensors_host || !packed) return B200POSE_E_NULL;
+    if ((uintptr_t)packed & 255) return B200POSE_E_WORKSPACE;
     for (int i = 0; i < B200POSE_NUM_WEIGHT_TENSORS; ++i)
         if (!tensors_host[i]) return B200POSE_E_NULL;
     return b2p_pack_weights(tensors_host, reinterpret_cast<float*>(packed), (cudaStream_t)stream);
@@ -157,13 +216,13 @@ int b200pose_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, 
 int b200pose_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, void* stream) {
     if (!pyramid || !coords || !out) return B200POSE_E_NULL;
     if (B < 1 || (h >> 3) < 2 || (w >> 3) < 2) return B200POSE_E_SHAPE;
-    return b2p_corr_lookup(pyramid, coords, B, h, w, out, (cudaStream_t)stream);
+    return b2p_corr_lookup(pyramid, coords, B, h, w, out, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int b200pose_context_init(const float* context, int B, int H, int W, float* net, float* xbuf, void* stream) {
     if (!context || !net || !xbuf) return B200POSE_E_NULL;
     if (B < 1 || H < 16 || W < 16 || (H % 8) || (W % 8)) return B200POSE_E_SHAPE;
-    return b2p_context_init(context, B, H, W, net, xbuf, (cudaStream_t)stream);
+    return b2p_context_init(context, B, H, W, net, xbuf, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int b200pose_flow_init(const float* depth, const float* K, const float* G, int B, int H, int W, float* coords1,
@@ -176,15 +235,76 @@ int b200pose_flow_init(const float* depth, const float* K, const float* G, int B
 size_t b200pose_update_workspace_bytes(int B, int h, int w) { return update_ws_layout(B, h, w, nullptr, 0, nullptr); }
 
 int b200pose_update_block(const void* packed_weights, float* net, float* xbuf, const float* corr, float* coords1,
-                          float* flow, float* mask, float* dflow_out, int B, int h, int w, void* workspace,
+                          float* flow, float* mask, float* dflow_out, int B, int h, int w, int flags, void* workspace,
                           size_t workspace_bytes, void* stream) {
     if (!packed_weights || !net || !xbuf || !corr || !coords1 || !flow || !mask || !workspace) return B200POSE_E_NULL;
     if (B < 1 || h < 1 || w < 1) return B200POSE_E_SHAPE;
-    if (((uintptr_t)workspace & 255) || workspace_bytes < b200pose_update_workspace_bytes(B, h, w)) return B200POSE_E_WORKSPACE;
+    if (((uintptr_t)workspace & 1023) || workspace_bytes < b200pose_update_workspace_bytes(B, h, w)) return B200POSE_E_WORKSPACE;
     UpdateWs u;
     update_ws_layout(B, h, w, workspace, workspace_bytes, &u);
-    return run_update_block(reinterpret_cast<const float*>(packed_weights), net, xbuf, corr, coords1, flow, mask, dflow_out,
-                            B, h, w, u, (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float* wts = reinterpret_cast<const float*>(packed_weights);
+    if (!(flags & B200POSE_FLAG_TENSOR_CORES))
+        return run_update_block(wts, net, xbuf, corr, coords1, flow, mask, dflow_out, B, h, w, u, s);
+    const size_t P = (size_t)B * h * w;
+    int rc;
+    if ((rc = b2p_split_planes(corr, B200POSE_CORR_PITCH, B200POSE_CORR_PITCH, P, u.corr_h[0], u.corr_h[1], B200POSE_CORR_PITCH, s))) return rc;
+    if ((rc = b2p_split_planes(net, 128, 128, P, u.net_h[0], u.net_h[1], 128, s))) return rc;
+    if ((rc = b2p_split_planes(xbuf, 256, 128, P, u.x_h[0], u.x_h[1], 256, s))) return rc;
+    return run_update_block_tc(wts, net, coords1, flow, mask, dflow_out, B, h, w, u, s);
+}
+
+size_t b200pose_conv_layer_workspace_bytes(int B, int h, int w) { return (size_t)B * h * w * 384 * 2 * sizeof(__half) + 4096; }
+
+int b200pose_conv_layer_info(int layer, int* cin0, int* cin1, int* cout, int* kh, int* kw) {
+    if (layer < 0 || layer >= CV_COUNT || !cin0 || !cin1 || !cout || !kh || !kw) return B200POSE_E_ARG;
+    const B2PConvDesc& d = b2p_weight_layout().cv[layer];
+    const bool two = (layer == CV_ZR1 || layer == CV_Q1 || layer == CV_ZR2 || layer == CV_Q2);
+    *cin0 = two ? 128 : d.cin; *cin1 = two ? 256 : 0; *cout = d.cout; *kh = d.kh; *kw = d.kw;
+    return 0;
+}
+
+int b200pose_conv_layer(const void* packed_weights, int layer, const float* in0, int pitch0, const float* in1, int pitch1,
+                        float* out, int B, int h, int w, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!packed_weights || !in0 || !out || !workspace) return B200POSE_E_NULL;
+    if (layer < 0 || layer >= CV_COUNT) return B200POSE_E_ARG;
+    if (B < 1 || h < 1 || w < 1) return B200POSE_E_SHAPE;
+    if (((uintptr_t)workspace & 1023) || workspace_bytes < b200pose_conv_layer_workspace_bytes(B, h, w)) return B200POSE_E_WORKSPACE;
+    int c0, c1, cout, kh, kw;
+    b200pose_conv_layer_info(layer, &c0, &c1, &cout, &kh, &kw);
+    if (c1 > 0 && !in1) return B200POSE_E_NULL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const float* wts = reinterpret_cast<const float*>(packed_weights);
+    const B2PWeightLayout& L = b2p_weight_layout();
+    const B2PConvDesc& d = L.cv[layer];
+    if (!(flags & B200POSE_FLAG_TENSOR_CORES)) {
+        ConvParams p;
+        memset(&p, 0, sizeof(p));
+        p.src0 = in0; p.pitch0 = pitch0; p.c0 = c0; p.src1 = in1; p.pitch1 = pitch1; p.c1 = c1;
+        p.wgt = wts + d.w_off; p.bias = wts + d.b_off; p.dst = out; p.dst_pitch = (cout + 3) / 4 * 4;
+        p.cout = d.cout; p.cout_pad = d.cout_pad; p.cin_pad = d.cin_pad;
+        p.B = B; p.h = h; p.w = w; p.kh = d.kh; p.kw = d.kw; p.epi = EPI_NONE; p.scale = 1.f;
+        return b2p_launch_conv(p, s);
+    }
+    const size_t P = (size_t)B * h * w;
+    const int c0p = (c0 + 7) / 8 * 8, c1p = (c1 + 7) / 8 * 8;       // 16-byte row pitch for the TMA map
+    __half* base = reinterpret_cast<__half*>(workspace);
+    __half* h0[2] = {base, base + P * c0p};
+    __half* h1[2] = {base + 2 * P * c0p, base + 2 * P * c0p + P * c1p};
+    int rc;
+    B2P_CUDA(cudaMemsetAsync(base, 0, (2 * P * c0p + 2 * P * c1p) * sizeof(__half), s));
+    if ((rc = b2p_split_planes(in0, pitch0, c0, P, h0[0], h0[1], c0p, s))) return rc;
+    if (c1 && (rc = b2p_split_planes(in1, pitch1, c1, P, h1[0], h1[1], c1p, s))) return rc;
+    const B2PHalfConvDesc& hd = b2p_half_layout().cv[layer];
+    const __half* hbase = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(wts) + b2p_half_section_offset_bytes());
+    UmmaConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.seg_hi[0] = h0[0]; a.seg_lo[0] = h0[1]; a.seg_c[0] = c0p; a.seg_pitch[0] = c0p;
+    if (c1) { a.seg_hi[1] = h1[0]; a.seg_lo[1] = h1[1]; a.seg_c[1] = c1p; a.seg_pitch[1] = c1p; }
+    a.w_hi = hbase + hd.hi_off; a.w_lo = hbase + hd.lo_off; a.bias = wts + d.b_off;
+    a.cin_pad = hd.cin_pad; a.cout_pad = hd.cout_pad; a.cout = hd.cout; a.n_tile = hd.n_tile; a.kh = hd.kh; a.kw = hd.kw;
+    a.B = B; a.h = h; a.w = w; a.epi = EPI_SCALE; a.scale = 1.f; a.out_f32 = out; a.out_f32_pitch = (cout + 3) / 4 * 4;
+    return b2p_launch_conv_umma(a, s);
 }
 
 int b200pose_upsample_weight(const float* flow, const float* mask, const float* geofea1, const float* geofea2,
@@ -226,39 +346,50 @@ int b200pose_refine_launch_count(int n_iters, int n_lm) {
 int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const float* fmap2, const float* context,
                           const float* geofea1, const float* geofea2, const float* depth, const float* K, float* G,
                           float sigma, int B, int C_geo, int H, int W, int n_iters, int n_lm, double ep_lmbda,
-                          double lm_lmbda, float* flow_first, float* flow_last, float* weight_last, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+                          double lm_lmbda, int flags, float* flow_first, float* flow_last, float* weight_last,
+                          void* workspace, size_t workspace_bytes, void* stream) {
     if (!packed_weights || !fmap1 || !fmap2 || !context || !geofea1 || !geofea2 || !depth || !K || !G || !workspace)
         return B200POSE_E_NULL;
     if (!shape_ok(B, H, W) || C_geo < 1) return B200POSE_E_SHAPE;
     if (n_iters < 0 || n_lm < 0 || !(sigma > 0.f)) return B200POSE_E_ARG;
-    if (((uintptr_t)workspace & 255) || workspace_bytes < b200pose_refine_workspace_bytes(B, H, W)) return B200POSE_E_WORKSPACE;
+    if (((uintptr_t)workspace & 1023) || workspace_bytes < b200pose_refine_workspace_bytes(B, H, W)) return B200POSE_E_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
     const int h = H / 8, w = W / 8;
+    const bool tc = (flags & B200POSE_FLAG_TENSOR_CORES) != 0;
     const float* wts = reinterpret_cast<const float*>(packed_weights);
     RefineWs r;
     refine_ws_layout(B, H, W, workspace, workspace_bytes, &r);
+    const UpdateWs& u = r.u;
     int rc;
     // update_corr_fn == True part (CFNet.py:115-133): pyramid + hidden-state reset, once per render iteration
     if ((rc = b200pose_corr_pyramid(fmap1, fmap2, B, 256, h, w, r.pyr, stream))) return rc;
-    if ((rc = b2p_context_init(context, B, H, W, r.net, r.xbuf, s))) return rc;
+    if (tc) rc = b2p_context_init(context, B, H, W, r.net, nullptr, u.net_h[0], u.net_h[1], u.x_h[0], u.x_h[1], s);
+    else rc = b2p_context_init(context, B, H, W, r.net, r.xbuf, nullptr, nullptr, nullptr, nullptr, s);
+    if (rc) return rc;
     for (int it = 0; it < n_iters; ++it) {
         if ((rc = b2p_flow_init(depth, K, G, B, H, W, r.coords1, r.flow, s))) return rc;
-        if ((rc = b2p_corr_lookup(r.pyr, r.coords1, B, h, w, r.corr, s))) return rc;
-        if ((rc = run_update_block(wts, r.net, r.xbuf, r.corr, r.coords1, r.flow, r.mask, nullptr, B, h, w, r.u, s))) return rc;
+        if (tc) {
+            if ((rc = b2p_corr_lookup(r.pyr, r.coords1, B, h, w, nullptr, u.corr_h[0], u.corr_h[1], s))) return rc;
+            if ((rc = run_update_block_tc(wts, r.net, r.coords1, r.flow, r.mask, nullptr, B, h, w, u, s))) return rc;
+        } else {
+            if ((rc = b2p_corr_lookup(r.pyr, r.coords1, B, h, w, r.corr, nullptr, nullptr, s))) return rc;
+            if ((rc = run_update_block(wts, r.net, r.xbuf, r.corr, r.coords1, r.flow, r.mask, nullptr, B, h, w, u, s))) return rc;
+        }
         float* fu = (it == 0 && flow_first) ? flow_first : ((it == n_iters - 1) ? flow_last : nullptr);
         if ((rc = b2p_upsample_weight(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, fu, r.target,
                                       r.weight, s))) return rc;
         if (it == 0 && it == n_iters - 1 && flow_first && flow_last)
             B2P_CUDA(cudaMemcpyAsync(flow_last, flow_first, (size_t)B * 2 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
         for (int k = 0; k < n_lm; ++k)
-            if ((rc = b2p_lm_step(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, nullptr, nullptr, nullptr,
-                                  r.lm, s))) return rc;
+            if ((rc = b2p_lm_step(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, nullptr, nullptr,
+                                  nullptr, r.lm, s))) return rc;
     }
     if (weight_last && n_iters > 0)
         B2P_CUDA(cudaMemcpyAsync(weight_last, r.weight, (size_t)B * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return 0;
 }
+
+}  // extern "C"
 
 namespace {
 struct HostScratch {
@@ -280,9 +411,11 @@ size_t host_scratch_layout(int B, int C, int H, int W, void* p, size_t cap, Host
     hs.ws_bytes = refine_ws_layout(B, H, W, nullptr, 0, nullptr);
     hs.ws = c.take<char>(hs.ws_bytes);
     if (out) *out = hs;
-    return align_up(c.off, 256);
+    return align_up(c.off, 1024);
 }
 }  // namespace
+
+extern "C" {
 
 size_t b200pose_refine_host_scratch_bytes(int B, int C_geo, int H, int W) {
     return host_scratch_layout(B, C_geo, H, W, nullptr, 0, nullptr);
@@ -292,12 +425,12 @@ int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_ho
                                const float* context_host, const float* geofea1_host, const float* geofea2_host,
                                const float* depth_host, const float* K_host, float* G_host, float sigma, int B,
                                int C_geo, int H, int W, int n_iters, int n_lm, double ep_lmbda, double lm_lmbda,
-                               void* device_scratch, size_t device_scratch_bytes, void* stream) {
+                               int flags, void* device_scratch, size_t device_scratch_bytes, void* stream) {
     if (!packed_weights || !fmap1_host || !fmap2_host || !context_host || !geofea1_host || !geofea2_host ||
         !depth_host || !K_host || !G_host || !device_scratch)
         return B200POSE_E_NULL;
     if (!shape_ok(B, H, W) || C_geo < 1) return B200POSE_E_SHAPE;
-    if (((uintptr_t)device_scratch & 255) || device_scratch_bytes < b200pose_refine_host_scratch_bytes(B, C_geo, H, W))
+    if (((uintptr_t)device_scratch & 1023) || device_scratch_bytes < b200pose_refine_host_scratch_bytes(B, C_geo, H, W))
         return B200POSE_E_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
     HostScratch hs;
@@ -313,7 +446,7 @@ int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_ho
     B2P_CUDA(cudaMemcpyAsync(hs.K, K_host, (size_t)B * 9 * f, cudaMemcpyHostToDevice, s));
     B2P_CUDA(cudaMemcpyAsync(hs.G, G_host, (size_t)B * 16 * f, cudaMemcpyHostToDevice, s));
     int rc = b200pose_refine_iters(packed_weights, hs.fmap1, hs.fmap2, hs.context, hs.geo1, hs.geo2, hs.depth, hs.K, hs.G,
-                                   sigma, B, C_geo, H, W, n_iters, n_lm, ep_lmbda, lm_lmbda, nullptr, nullptr, nullptr,
+                                   sigma, B, C_geo, H, W, n_iters, n_lm, ep_lmbda, lm_lmbda, flags, nullptr, nullptr, nullptr,
                                    hs.ws, hs.ws_bytes, stream);
     if (rc) return rc;
     B2P_CUDA(cudaMemcpyAsync(G_host, hs.G, (size_t)B * 16 * f, cudaMemcpyDeviceToHost, s));

@@ -1,6 +1,8 @@
 // Shared declarations for the libb200pose.so kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <string.h>
 #include <stdint.h>
 #include <stddef.h>
 #include "../../include/b200pose.h"
@@ -73,18 +75,64 @@ struct ConvParams {
 
 int b2p_launch_conv(const ConvParams& p, cudaStream_t s);
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core path (conv_umma.cu): operands are fp16 hi/lo plane pairs, x ~= hi + lo.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void b2p_split_half(float v, __half& hi, __half& lo) {
+#ifdef __CUDA_ARCH__
+    unsigned short h, l;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));          // saturate instead of +-inf
+    hi = __ushort_as_half(h);
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(v - __half2float(hi)));
+    lo = __ushort_as_half(l);
+#else
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+#endif
+}
+
+// fp16 weight planes: W[tap][cout_pad][cin_pad] (cin contiguous = K-major), cin_pad multiple of 64,
+// cout_pad multiple of n_tile.
+struct B2PHalfConvDesc {
+    int kh, kw, cin, cout, cin_pad, cout_pad, n_tile;
+    size_t hi_off, lo_off;     // offsets in halves from the start of the fp16 section
+};
+struct B2PHalfLayout {
+    B2PHalfConvDesc cv[CV_COUNT];
+    size_t total_halves;
+};
+const B2PHalfLayout& b2p_half_layout();
+// byte offset of the fp16 section inside the packed blob (after the fp32 section)
+size_t b2p_half_section_offset_bytes();
+
+struct UmmaConvArgs {
+    const __half* seg_hi[2]; const __half* seg_lo[2]; int seg_c[2]; int seg_pitch[2];
+    const __half* w_hi; const __half* w_lo; const float* bias;
+    int cin_pad, cout_pad, cout, n_tile, kh, kw, B, h, w;
+    int epi; float scale;
+    float* out_f32; int out_f32_pitch;
+    __half* out_hi; __half* out_lo; int out_h_pitch;
+    float* zbuf; float* hbuf;
+};
+int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s);
+// fp32 [P][pitch_in] -> fp16 hi/lo planes [P][pitch_out] (first C channels); used by the per-operator entry
+int b2p_split_planes(const float* src, int pitch_in, int C, size_t P, __half* hi, __half* lo, int pitch_out, cudaStream_t s);
+
 // kernels implemented across the .cu files (host launchers; all return 0 / cudaError_t)
 int b2p_corr_volume(const float* f1, const float* f2, int B, int D, int P, float* level0, cudaStream_t s);
 int b2p_corr_pool(const float* src, int NP, int hs, int ws, float* dst, cudaStream_t s);
-int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, cudaStream_t s);
-int b2p_context_init(const float* ctx, int B, int H, int W, float* net, float* xbuf, cudaStream_t s);
+// hi/lo != nullptr: additionally (or instead, when out == nullptr) write fp16 hi/lo planes with the same pitch
+int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, __half* out_hi,
+                    __half* out_lo, cudaStream_t s);
+int b2p_context_init(const float* ctx, int B, int H, int W, float* net, float* xbuf, __half* net_hi, __half* net_lo,
+                     __half* x_hi, __half* x_lo, cudaStream_t s);
 int b2p_flow_init(const float* depth, const float* K, const float* G, int B, int H, int W,
                   float* coords1, float* flow, cudaStream_t s);
 int b2p_im2col_f1(const float* flow, int B, int h, int w, float* col /*[P][112]*/, float* xbuf /*[P][256] ch 254,255*/,
-                  cudaStream_t s);
-int b2p_flow_head2(const float* hm /*[P][512], first 256 = flow-head features*/, const float* w2, const float* b2,
-                   float* coords1 /*[P][2] in/out*/, float* flow /*[P][2] out = coords1 - coords0*/, float* dflow_out,
-                   int B, int h, int w, cudaStream_t s);
+                  __half* col_hi, __half* col_lo, __half* x_hi, __half* x_lo, cudaStream_t s);
+int b2p_flow_head2(const float* hm /*[P][512] fp32, first 256 = flow-head features; or nullptr*/, const __half* hm_hi,
+                   const __half* hm_lo, const float* w2, const float* b2, float* coords1 /*[P][2] in/out*/,
+                   float* flow /*[P][2] out = coords1 - coords0*/, float* dflow_out, int B, int h, int w, cudaStream_t s);
 int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth,
                         float sigma, int B, int C, int H, int W, float* flow_up, float* target, float* weight,
                         cudaStream_t s);
@@ -92,4 +140,4 @@ int b2p_lm_step(const float* depth, const float* target, const float* weight, co
                 int B, int H, int W, float depth_add, double ep, double lm, double* H_out, double* b_out,
                 float* delta_out, void* ws, cudaStream_t s);
 size_t b2p_lm_ws_bytes(int B, int H, int W);
-int b2p_pack_weights(const float* const* t, float* packed, cudaStream_t s);
+int b2p_pack_weights(const float* const* t, float* packed, cudaStream_t s);   // fp32 section + fp16 hi/lo section

@@ -1,0 +1,355 @@
+// Tensor-core implicit-GEMM convolution for the update block: tcgen05.mma (kind::f16) with fp32 accumulators
+// in TMEM, operands staged by TMA into 128B-swizzled shared memory, warp-specialised
+// (warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2-5 = epilogue).
+//
+// Precision scheme ("fp16x3"): every fp32 operand x is carried as two fp16 planes hi = fp16(x),
+// lo = fp16(x - hi) (22 significant bits together); a product is accumulated as
+//   a_lo*b_hi + a_hi*b_lo + a_hi*b_hi     (three MMAs into the same fp32 TMEM accumulator),
+// dropping only the 2^-22 lo*lo term.  Measured on the reference itself this keeps the
+// final SE(3) within 3e-7 of the fp32 path, whereas single-pass TF32/FP16 sits at 4-9e-5 (too close to the
+// 1e-4 parity bar) and BF16 fails it.
+//
+// GEMM view: D[M = 128 pixels (a 16x8 spatial patch of one sample)][N = n_tile output channels]
+//            += A[M][K] * B[N][K]^T,  K = taps x input channels, consumed 64 channels (one 128-byte row) at a
+// time.  The A tile of filter tap (ky,kx) is the same 16x8x64 box of the PXC activation tensor shifted by
+// (ky-ph, kx-pw): TMA tiled mode zero-fills everything outside the image, which implements the "same"
+// padding of reference thirdparty/raft/update.py (nn.Conv2d(padding=k//2)) without an im2col buffer.
+#include "common.cuh"
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr int UM_THREADS = 192;
+constexpr int TILE_ROWS = 16, TILE_COLS = 8;          // 128-pixel M tile
+constexpr int BKC = 64;                                // channels per K chunk (128 B of fp16)
+constexpr int A_TILE_BYTES = 128 * BKC * 2;            // 16 KB
+constexpr int TMEM_COLS = 256;
+
+struct UmmaConvParams {
+    CUtensorMap a_hi[2], a_lo[2];     // activation segments (PXC fp16 planes), rank 4: (C, w, h, B)
+    CUtensorMap b_hi, b_lo;           // weights, rank 3: (Cin_pad, Cout_pad, taps)
+    int seg0_chunks, chunks_per_tap, kh, kw;
+    int B, h, w, tiles_x, tiles_y;
+    int n_tile, cout, stages;
+    const float* bias;
+    int epi; float scale;
+    float* out_f32; int out_f32_pitch;
+    __half* out_hi; __half* out_lo; int out_h_pitch;
+    float* zbuf; float* hbuf;         // GRU side buffers, fp32 [P][128]
+};
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 26)) __trap();      // a protocol bug must fail the launch, never hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 = 1 | [32,46) SBO>>4 = 1024/16 | [46,48) version = 1 | [61,64) layout = 2
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b_tile_bytes = (uint32_t)p.n_tile * 128u;
+    const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * b_tile_bytes;
+    const uint32_t bars = smem_base + (uint32_t)p.stages * stage_bytes;     // full[S], empty[S], tmem_full, tmem_slot
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
+    const uint32_t tmem_full_bar = bars + 16u * p.stages;
+    const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+    // work item
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int bimg = blockIdx.x / tiles_per_img;
+    const int trem = blockIdx.x - bimg * tiles_per_img;
+    const int y0 = (trem / p.tiles_x) * TILE_ROWS, x0 = (trem % p.tiles_x) * TILE_COLS;
+    const int n0 = blockIdx.y * p.n_tile;
+    const int nk = p.kh * p.kw * p.chunks_per_tap;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % p.stages, ph = (kc / p.stages) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_expect_tx(full_bar(s), stage_bytes);
+                const int tap = kc / p.chunks_per_tap, cc = kc - tap * p.chunks_per_tap;
+                const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                const int seg = cc >= p.seg0_chunks ? 1 : 0;
+                const int c0 = (seg ? cc - p.seg0_chunks : cc) * BKC;
+                const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+                tma_load_4d(&p.a_hi[seg], sa, full_bar(s), c0, x0 + kx - (p.kw >> 1), y0 + ky - (p.kh >> 1), bimg);
+                tma_load_4d(&p.a_lo[seg], sa + A_TILE_BYTES, full_bar(s), c0, x0 + kx - (p.kw >> 1), y0 + ky - (p.kh >> 1), bimg);
+                tma_load_3d(&p.b_hi, sa + 2 * A_TILE_BYTES, full_bar(s), cc * BKC, n0, tap);
+                tma_load_3d(&p.b_lo, sa + 2 * A_TILE_BYTES + b_tile_bytes, full_bar(s), cc * BKC, n0, tap);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=B=F16 (0), K-major both,
+            // N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % p.stages, ph = (kc / p.stages) & 1;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+                const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE_BYTES);
+                const uint64_t b_hi = umma_desc_sw128(sa + 2 * A_TILE_BYTES);
+                const uint64_t b_lo = umma_desc_sw128(sa + 2 * A_TILE_BYTES + b_tile_bytes);
+#pragma unroll
+                for (int k = 0; k < BKC / 16; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 2);       // 16 halves = 32 B = 2 x 16 B along K inside the swizzle atom
+                    tc_mma_f16(tmem_base, a_lo + adv, b_hi + adv, idesc, (kc | k) != 0 ? 1u : 0u);
+                    tc_mma_f16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+                    tc_mma_f16(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+                }
+                tc_commit(empty_bar(s));          // frees the smem stage when these MMAs have read it
+            }
+            tc_commit(tmem_full_bar);             // accumulator complete
+        }
+    } else {
+        // ---------------------------------------------------- epilogue: TMEM -> registers -> global
+        const int q = warp & 3;                   // TMEM lane quarter this warp may access
+        const int mrow = q * 32 + lane;
+        const int yy = y0 + (mrow >> 3), xx = x0 + (mrow & 7);
+        const bool valid = yy < p.h && xx < p.w;
+        const size_t pix = ((size_t)bimg * p.h + yy) * p.w + xx;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        for (int col0 = 0; col0 < p.n_tile; col0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, r);
+            const int nb = n0 + col0;
+            if (!valid || nb >= p.cout) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(p.bias + nb + j);
+            if (p.epi == EPI_SCALE) {
+                float* d = p.out_f32 + pix * p.out_f32_pitch + nb;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (nb + j + 3 < p.cout) {
+                        *reinterpret_cast<float4*>(d + j) = make_float4(v[j] * p.scale, v[j + 1] * p.scale, v[j + 2] * p.scale, v[j + 3] * p.scale);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (nb + j + t < p.cout) d[j + t] = v[j + t] * p.scale;
+                    }
+                }
+                continue;
+            }
+            if (p.epi == EPI_GRU_ZR && nb < 128) {            // z gate, kept in fp32 for the blend
+                float* d = p.zbuf + pix * 128 + nb;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(d + j) = make_float4(sigm(v[j]), sigm(v[j + 1]), sigm(v[j + 2]), sigm(v[j + 3]));
+                continue;
+            }
+            int oc = nb;                                       // output channel of v[0]
+            if (p.epi == EPI_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (p.epi == EPI_GRU_ZR) {                  // r gate -> r * h
+                oc = nb - 128;
+                const float* hp = p.hbuf + pix * 128 + oc;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 hh = *reinterpret_cast<const float4*>(hp + j);
+                    v[j] = sigm(v[j]) * hh.x; v[j + 1] = sigm(v[j + 1]) * hh.y; v[j + 2] = sigm(v[j + 2]) * hh.z; v[j + 3] = sigm(v[j + 3]) * hh.w;
+                }
+            } else if (p.epi == EPI_GRU_Q) {                   // h <- (1-z) h + z tanh(q)
+                float* hp = p.hbuf + pix * 128 + nb;
+                const float* zp = p.zbuf + pix * 128 + nb;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 hh = *reinterpret_cast<const float4*>(hp + j);
+                    const float4 zz = *reinterpret_cast<const float4*>(zp + j);
+                    v[j] = (1.f - zz.x) * hh.x + zz.x * tanhf(v[j]);
+                    v[j + 1] = (1.f - zz.y) * hh.y + zz.y * tanhf(v[j + 1]);
+                    v[j + 2] = (1.f - zz.z) * hh.z + zz.z * tanhf(v[j + 2]);
+                    v[j + 3] = (1.f - zz.w) * hh.w + zz.w * tanhf(v[j + 3]);
+                    *reinterpret_cast<float4*>(hp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+            // fp16 hi/lo planes for the next convolution
+            __half* dh = p.out_hi + pix * p.out_h_pitch + oc;
+            __half* dl = p.out_lo + pix * p.out_h_pitch + oc;
+            const int cvalid = p.cout - nb;                    // channels of this 32-group that exist
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                __align__(16) __half hi8[8];
+                __align__(16) __half lo8[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) b2p_split_half(v[j + t], hi8[t], lo8[t]);
+                if (j + 7 < cvalid) {
+                    *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(hi8);
+                    *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(lo8);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        if (j + t < cvalid) { dh[j + t] = hi8[t]; dl[j + t] = lo8[t]; }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+int make_act_map(CUtensorMap* m, const __half* base, int C, int pitch, int B, int h, int w) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return (int)cudaErrorNotSupported;
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)w * pitch * 2, (cuuint64_t)h * w * pitch * 2};
+    cuuint32_t box[4] = {BKC, TILE_COLS, TILE_ROWS, 1};
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+int make_wgt_map(CUtensorMap* m, const __half* base, int cin_pad, int cout_pad, int taps, int n_tile) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return (int)cudaErrorNotSupported;
+    cuuint64_t gdim[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)taps};
+    cuuint64_t gstr[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cout_pad * cin_pad * 2};
+    cuuint32_t box[3] = {BKC, (cuuint32_t)n_tile, 1};
+    cuuint32_t est[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
+    UmmaConvParams p;
+    memset(&p, 0, sizeof(p));
+    int rc;
+    for (int g = 0; g < 2; ++g) {
+        if (a.seg_c[g] == 0) { p.a_hi[g] = p.a_hi[0]; p.a_lo[g] = p.a_lo[0]; continue; }
+        if ((rc = make_act_map(&p.a_hi[g], a.seg_hi[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w))) return rc;
+        if ((rc = make_act_map(&p.a_lo[g], a.seg_lo[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w))) return rc;
+    }
+    const int taps = a.kh * a.kw;
+    if ((rc = make_wgt_map(&p.b_hi, a.w_hi, a.cin_pad, a.cout_pad, taps, a.n_tile))) return rc;
+    if ((rc = make_wgt_map(&p.b_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, a.n_tile))) return rc;
+    p.seg0_chunks = (a.seg_c[0] + BKC - 1) / BKC;
+    p.chunks_per_tap = a.cin_pad / BKC;
+    p.kh = a.kh; p.kw = a.kw; p.B = a.B; p.h = a.h; p.w = a.w;
+    p.tiles_x = ceil_div(a.w, TILE_COLS); p.tiles_y = ceil_div(a.h, TILE_ROWS);
+    p.n_tile = a.n_tile; p.cout = a.cout;
+    const int stage_bytes = 2 * A_TILE_BYTES + 2 * a.n_tile * 128;
+    p.stages = (200 * 1024) / stage_bytes;
+    if (p.stages > 6) p.stages = 6;
+    p.bias = a.bias; p.epi = a.epi; p.scale = a.scale;
+    p.out_f32 = a.out_f32; p.out_f32_pitch = a.out_f32_pitch;
+    p.out_hi = a.out_hi; p.out_lo = a.out_lo; p.out_h_pitch = a.out_h_pitch;
+    p.zbuf = a.zbuf; p.hbuf = a.hbuf;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B2P_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(a.B * p.tiles_x * p.tiles_y, a.cout_pad / a.n_tile);
+    conv_umma_kernel<<<grid, UM_THREADS, smem, s>>>(p);
+    B2P_LAUNCH_CHECK();
+    return 0;
+}

@@ -27,7 +27,8 @@ __global__ void corr_pool_kernel(const float* __restrict__ src, int hs, int ws, 
 // Output channel l*81 + i*9 + j samples (cx/2^l + i - 4, cy/2^l + j - 4): the slow window index moves x
 // (reference corr.py:44-50 stacks meshgrid(dy,dx) into the (x,y) slots).
 __global__ void __launch_bounds__(256) corr_lookup_kernel(const float* __restrict__ pyr, const float* __restrict__ coords,
-                                                          int B, int h, int w, float* __restrict__ out) {
+                                                          int B, int h, int w, float* __restrict__ out,
+                                                          __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
     const int P = h * w;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -35,7 +36,9 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const float* __restric
     const int b = warp / P, p = warp - b * P;
     const float cx = coords[(size_t)warp * 2 + 0];
     const float cy = coords[(size_t)warp * 2 + 1];
-    float* o = out + (size_t)warp * B200POSE_CORR_PITCH;
+    float* o = out ? out + (size_t)warp * B200POSE_CORR_PITCH : nullptr;
+    __half* oh = out_hi ? out_hi + (size_t)warp * B200POSE_CORR_PITCH : nullptr;
+    __half* ol = out_hi ? out_lo + (size_t)warp * B200POSE_CORR_PITCH : nullptr;
     size_t lvl_off = 0;
     int hl = h, wl = w;
     float inv = 1.0f;
@@ -57,19 +60,26 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const float* __restric
             if (y0ok && x1ok) v01 = __ldg(img + yi * wl + xi + 1);
             if (y1ok && x0ok) v10 = __ldg(img + (yi + 1) * wl + xi);
             if (y1ok && x1ok) v11 = __ldg(img + (yi + 1) * wl + xi + 1);
-            o[l * 81 + k] = v00 * (1.f - fx) * (1.f - fy) + v01 * fx * (1.f - fy) + v10 * (1.f - fx) * fy + v11 * fx * fy;
+            const float val = v00 * (1.f - fx) * (1.f - fy) + v01 * fx * (1.f - fy) + v10 * (1.f - fx) * fy + v11 * fx * fy;
+            if (o) o[l * 81 + k] = val;
+            if (oh) b2p_split_half(val, oh[l * 81 + k], ol[l * 81 + k]);
         }
         lvl_off += (size_t)B * P * (size_t)(hl * wl);
         hl >>= 1; wl >>= 1; inv *= 0.5f;
     }
-    if (lane < B200POSE_CORR_PITCH - B200POSE_CORR_CH) o[B200POSE_CORR_CH + lane] = 0.f;
+    if (lane < B200POSE_CORR_PITCH - B200POSE_CORR_CH) {
+        if (o) o[B200POSE_CORR_CH + lane] = 0.f;
+        if (oh) { oh[B200POSE_CORR_CH + lane] = __float2half(0.f); ol[B200POSE_CORR_CH + lane] = __float2half(0.f); }
+    }
 }
 
 // context [B,256,H,W] --(1/8 bilinear, align_corners=True)--> net = tanh(ch 0..127) [P][128],
 // xbuf[:, 0:128] = relu(ch 128..255).   32 low-res pixels x 32 channels per block, smem transpose.
 __global__ void __launch_bounds__(256) context_init_kernel(const float* __restrict__ ctx, int B, int H, int W, int h, int w,
                                                            float sy, float sx, float* __restrict__ net,
-                                                           float* __restrict__ xbuf) {
+                                                           float* __restrict__ xbuf, __half* __restrict__ net_hi,
+                                                           __half* __restrict__ net_lo, __half* __restrict__ x_hi,
+                                                           __half* __restrict__ x_lo) {
     __shared__ float tile[32][33];
     const int P = h * w;
     const int p0 = blockIdx.x * 32;      // pixel tile within sample
@@ -102,8 +112,15 @@ __global__ void __launch_bounds__(256) context_init_kernel(const float* __restri
         const float v = tile[tx][pp];
         const int c = c0 + tx;
         const size_t pix = (size_t)b * P + pw;
-        if (c < 128) net[pix * 128 + c] = tanhf(v);
-        else xbuf[pix * 256 + (c - 128)] = fmaxf(v, 0.f);
+        if (c < 128) {
+            const float t = tanhf(v);
+            net[pix * 128 + c] = t;
+            if (net_hi) b2p_split_half(t, net_hi[pix * 128 + c], net_lo[pix * 128 + c]);
+        } else {
+            const float t = fmaxf(v, 0.f);
+            if (xbuf) xbuf[pix * 256 + (c - 128)] = t;
+            if (x_hi) b2p_split_half(t, x_hi[pix * 256 + (c - 128)], x_lo[pix * 256 + (c - 128)]);
+        }
     }
 }
 
@@ -166,19 +183,22 @@ int b2p_corr_pool(const float* src, int NP, int hs, int ws, float* dst, cudaStre
     return 0;
 }
 
-int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, cudaStream_t s) {
+int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, __half* out_hi,
+                    __half* out_lo, cudaStream_t s) {
     const int warps = B * h * w;
-    corr_lookup_kernel<<<ceil_div(warps, 8), 256, 0, s>>>(pyramid, coords, B, h, w, out);
+    corr_lookup_kernel<<<ceil_div(warps, 8), 256, 0, s>>>(pyramid, coords, B, h, w, out, out_hi, out_lo);
     B2P_LAUNCH_CHECK();
     return 0;
 }
 
 static inline float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
 
-int b2p_context_init(const float* ctx, int B, int H, int W, float* net, float* xbuf, cudaStream_t s) {
+int b2p_context_init(const float* ctx, int B, int H, int W, float* net, float* xbuf, __half* net_hi, __half* net_lo,
+                     __half* x_hi, __half* x_lo, cudaStream_t s) {
     const int h = H / 8, w = W / 8;
     dim3 grid(ceil_div(h * w, 32), 8, B);
-    context_init_kernel<<<grid, 256, 0, s>>>(ctx, B, H, W, h, w, ac_scale(H, h), ac_scale(W, w), net, xbuf);
+    context_init_kernel<<<grid, 256, 0, s>>>(ctx, B, H, W, h, w, ac_scale(H, h), ac_scale(W, w), net, xbuf, net_hi,
+                                               net_lo, x_hi, x_lo);
     B2P_LAUNCH_CHECK();
     return 0;
 }

@@ -28,6 +28,35 @@ __global__ void pack_vec_kernel(const float* __restrict__ src, int n, float* __r
     if (i < n) dst[i] = src[i];
 }
 
+// fp16 hi/lo planes: dst[tap][n_off + n][c] = split(src[n][c][ky][kx])   (K-major rows of cin_pad halves)
+__global__ void pack_conv_half_kernel(const float* __restrict__ src, int cout, int cin, int kh, int kw,
+                                      __half* __restrict__ dst_hi, __half* __restrict__ dst_lo, int cin_pad, int cout_pad,
+                                      int n_off, int flatten_taps) {
+    const size_t total = (size_t)cout * cin * kh * kw;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int kx = (int)(i % kw); size_t t = i / kw;
+    const int ky = (int)(t % kh); t /= kh;
+    const int c = (int)(t % cin);
+    const int n = (int)(t / cin);
+    const int tap = ky * kw + kx;
+    size_t o;
+    if (flatten_taps) o = (size_t)(n_off + n) * cin_pad + (tap * cin + c);           // single "tap", k = tap*cin + c
+    else o = ((size_t)tap * cout_pad + n_off + n) * cin_pad + c;
+    __half hi, lo;
+    b2p_split_half(src[i], hi, lo);
+    dst_hi[o] = hi;
+    dst_lo[o] = lo;
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ src, int pitch_in, int C, size_t P, __half* __restrict__ hi,
+                                    __half* __restrict__ lo, int pitch_out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P * (size_t)C) return;
+    const size_t p = i / C; const int c = (int)(i - p * C);
+    b2p_split_half(src[p * pitch_in + c], hi[p * pitch_out + c], lo[p * pitch_out + c]);
+}
+
 // flow_head.conv2 [2][256][3][3] -> [2][9][256]
 __global__ void pack_fh2_kernel(const float* __restrict__ src, float* __restrict__ dst) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -38,7 +67,9 @@ __global__ void pack_fh2_kernel(const float* __restrict__ src, float* __restrict
 }
 
 __global__ void __launch_bounds__(256) im2col_f1_kernel(const float* __restrict__ flow, int B, int h, int w,
-                                                        float* __restrict__ col, float* __restrict__ xbuf) {
+                                                        float* __restrict__ col, float* __restrict__ xbuf,
+                                                        __half* __restrict__ col_hi, __half* __restrict__ col_lo,
+                                                        __half* __restrict__ x_hi, __half* __restrict__ x_lo) {
     const size_t total = (size_t)B * h * w * 56;          // 56 float2 slots per pixel (49 taps + 7 zero pads)
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -53,12 +84,23 @@ __global__ void __launch_bounds__(256) im2col_f1_kernel(const float* __restrict_
         const int sy = y + ky - 3, sx = x + kx - 3;
         if (sy >= 0 && sy < h && sx >= 0 && sx < w)
             v = *reinterpret_cast<const float2*>(flow + ((size_t)(b * h + sy) * w + sx) * 2);
-        if (slot == 24) *reinterpret_cast<float2*>(xbuf + pix * 256 + 254) = v;   // centre tap = flow itself -> cat[out, flow]
+        if (slot == 24) {                                                          // centre tap = flow itself -> cat[out, flow]
+            if (xbuf) *reinterpret_cast<float2*>(xbuf + pix * 256 + 254) = v;
+            if (x_hi) {
+                b2p_split_half(v.x, x_hi[pix * 256 + 254], x_lo[pix * 256 + 254]);
+                b2p_split_half(v.y, x_hi[pix * 256 + 255], x_lo[pix * 256 + 255]);
+            }
+        }
     }
-    *reinterpret_cast<float2*>(col + pix * 112 + slot * 2) = v;
+    if (col) *reinterpret_cast<float2*>(col + pix * 112 + slot * 2) = v;
+    if (col_hi) {
+        b2p_split_half(v.x, col_hi[pix * 112 + slot * 2], col_lo[pix * 112 + slot * 2]);
+        b2p_split_half(v.y, col_hi[pix * 112 + slot * 2 + 1], col_lo[pix * 112 + slot * 2 + 1]);
+    }
 }
 
-__global__ void __launch_bounds__(256) flow_head2_kernel(const float* __restrict__ hm, const float* __restrict__ w2,
+__global__ void __launch_bounds__(256) flow_head2_kernel(const float* __restrict__ hm, const __half* __restrict__ hm_hi,
+                                                         const __half* __restrict__ hm_lo, const float* __restrict__ w2,
                                                          const float* __restrict__ b2, float* __restrict__ coords1,
                                                          float* __restrict__ flow,
                                                          float* __restrict__ dflow_out, int B, int h, int w) {
@@ -73,11 +115,21 @@ __global__ void __launch_bounds__(256) flow_head2_kernel(const float* __restrict
     for (int tap = 0; tap < 9; ++tap) {
         const int sy = y + tap / 3 - 1, sx = x + tap % 3 - 1;
         if (sy < 0 || sy >= h || sx < 0 || sx >= w) continue;
-        const float* src = hm + ((size_t)(b * h + sy) * w + sx) * 512;
+        const size_t so = ((size_t)(b * h + sy) * w + sx) * 512;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int c = half * 128 + lane * 4;
-            const float4 a = __ldg(reinterpret_cast<const float4*>(src + c));
+            float4 a;
+            if (hm) {
+                a = __ldg(reinterpret_cast<const float4*>(hm + so + c));
+            } else {
+                const uint2 uh = __ldg(reinterpret_cast<const uint2*>(hm_hi + so + c));
+                const uint2 ul = __ldg(reinterpret_cast<const uint2*>(hm_lo + so + c));
+                const __half2 h0 = *reinterpret_cast<const __half2*>(&uh.x), h1 = *reinterpret_cast<const __half2*>(&uh.y);
+                const __half2 l0 = *reinterpret_cast<const __half2*>(&ul.x), l1 = *reinterpret_cast<const __half2*>(&ul.y);
+                a.x = __low2float(h0) + __low2float(l0); a.y = __high2float(h0) + __high2float(l0);
+                a.z = __low2float(h1) + __low2float(l1); a.w = __high2float(h1) + __high2float(l1);
+            }
             const float4 u0 = __ldg(reinterpret_cast<const float4*>(w2 + (0 * 9 + tap) * 256 + c));
             const float4 u1 = __ldg(reinterpret_cast<const float4*>(w2 + (1 * 9 + tap) * 256 + c));
             s0 += a.x * u0.x + a.y * u0.y + a.z * u0.z + a.w * u0.w;
@@ -174,19 +226,80 @@ int b2p_pack_weights(const float* const* t, float* packed, cudaStream_t s) {
     pack_fh2_kernel<<<ceil_div(2 * 256 * 9, 256), 256, 0, s>>>(t[24], packed + L.fh2_w_off);
     pack_vec_kernel<<<1, 256, 0, s>>>(t[25], 2, packed + L.fh2_b_off);
     B2P_LAUNCH_CHECK();
+
+    // ---- fp16 hi/lo section for the tensor-core path: W[tap][cout_pad][cin_pad] (K-major)
+    const B2PHalfLayout& HL = b2p_half_layout();
+    __half* hbase = reinterpret_cast<__half*>(reinterpret_cast<char*>(packed) + b2p_half_section_offset_bytes());
+    B2P_CUDA(cudaMemsetAsync(hbase, 0, HL.total_halves * sizeof(__half), s));
+    auto packh = [&](int id, const float* w, int cout_src, int cin_src, int kh, int kw, int n_off, int flatten) -> int {
+        const B2PHalfConvDesc& d = HL.cv[id];
+        const size_t total = (size_t)cout_src * cin_src * kh * kw;
+        pack_conv_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, cout_src, cin_src, kh, kw, hbase + d.hi_off,
+                                                                              hbase + d.lo_off, d.cin_pad, d.cout_pad, n_off,
+                                                                              flatten);
+        B2P_LAUNCH_CHECK();
+        return 0;
+    };
+    if ((rc = packh(CV_C1, t[0], 256, 324, 1, 1, 0, 0))) return rc;
+    if ((rc = packh(CV_C2, t[2], 192, 256, 3, 3, 0, 0))) return rc;
+    if ((rc = packh(CV_F1, t[4], 128, 2, 7, 7, 0, 1))) return rc;
+    if ((rc = packh(CV_F2, t[6], 64, 128, 3, 3, 0, 0))) return rc;
+    if ((rc = packh(CV_ENC, t[8], 126, 256, 3, 3, 0, 0))) return rc;
+    if ((rc = packh(CV_ZR1, t[10], 128, 384, 1, 5, 0, 0))) return rc;
+    if ((rc = packh(CV_ZR1, t[12], 128, 384, 1, 5, 128, 0))) return rc;
+    if ((rc = packh(CV_Q1, t[14], 128, 384, 1, 5, 0, 0))) return rc;
+    if ((rc = packh(CV_ZR2, t[16], 128, 384, 5, 1, 0, 0))) return rc;
+    if ((rc = packh(CV_ZR2, t[18], 128, 384, 5, 1, 128, 0))) return rc;
+    if ((rc = packh(CV_Q2, t[20], 128, 384, 5, 1, 0, 0))) return rc;
+    if ((rc = packh(CV_HEADS, t[22], 256, 128, 3, 3, 0, 0))) return rc;
+    if ((rc = packh(CV_HEADS, t[26], 256, 128, 3, 3, 256, 0))) return rc;
+    if ((rc = packh(CV_MASK2, t[28], 576, 256, 1, 1, 0, 0))) return rc;
     return 0;
 }
 
-int b2p_im2col_f1(const float* flow, int B, int h, int w, float* col, float* xbuf, cudaStream_t s) {
-    const size_t total = (size_t)B * h * w * 56;
-    im2col_f1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(flow, B, h, w, col, xbuf);
+const B2PHalfLayout& b2p_half_layout() {
+    static const B2PHalfLayout HL = []() {
+        B2PHalfLayout H;
+        const B2PWeightLayout& L = b2p_weight_layout();
+        const int ntile[CV_COUNT] = {128, 192, 128, 64, 128, 128, 128, 128, 128, 128, 192};
+        size_t off = 0;
+        for (int i = 0; i < CV_COUNT; ++i) {
+            B2PHalfConvDesc& d = H.cv[i];
+            d.kh = L.cv[i].kh; d.kw = L.cv[i].kw; d.cin = L.cv[i].cin; d.cout = L.cv[i].cout;
+            d.n_tile = ntile[i];
+            d.cin_pad = (d.cin + 63) / 64 * 64;
+            d.cout_pad = (d.cout + d.n_tile - 1) / d.n_tile * d.n_tile;
+            const size_t n = (size_t)d.kh * d.kw * d.cout_pad * d.cin_pad;
+            d.hi_off = off; off += n;
+            d.lo_off = off; off += n;
+            off = (off + 127) / 128 * 128;
+        }
+        H.total_halves = off;
+        return H;
+    }();
+    return HL;
+}
+
+int b2p_split_planes(const float* src, int pitch_in, int C, size_t P, __half* hi, __half* lo, int pitch_out, cudaStream_t s) {
+    const size_t total = P * (size_t)C;
+    split_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, pitch_in, C, P, hi, lo, pitch_out);
     B2P_LAUNCH_CHECK();
     return 0;
 }
 
-int b2p_flow_head2(const float* hm, const float* w2, const float* b2, float* coords1, float* flow, float* dflow_out,
-                   int B, int h, int w, cudaStream_t s) {
-    flow_head2_kernel<<<ceil_div(B * h * w, 8), 256, 0, s>>>(hm, w2, b2, coords1, flow, dflow_out, B, h, w);
+size_t b2p_half_section_offset_bytes() { return align_up(b2p_weight_layout().total_floats * sizeof(float), 1024); }
+
+int b2p_im2col_f1(const float* flow, int B, int h, int w, float* col, float* xbuf, __half* col_hi, __half* col_lo,
+                  __half* x_hi, __half* x_lo, cudaStream_t s) {
+    const size_t total = (size_t)B * h * w * 56;
+    im2col_f1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(flow, B, h, w, col, xbuf, col_hi, col_lo, x_hi, x_lo);
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2p_flow_head2(const float* hm, const __half* hm_hi, const __half* hm_lo, const float* w2, const float* b2,
+                   float* coords1, float* flow, float* dflow_out, int B, int h, int w, cudaStream_t s) {
+    flow_head2_kernel<<<ceil_div(B * h * w, 8), 256, 0, s>>>(hm, hm_hi, hm_lo, w2, b2, coords1, flow, dflow_out, B, h, w);
     B2P_LAUNCH_CHECK();
     return 0;
 }

@@ -16,6 +16,9 @@ WEIGHT_KEYS: List[str] = [
     "gru.convz1", "gru.convr1", "gru.convq1", "gru.convz2", "gru.convr2", "gru.convq2",
     "flow_head.conv1", "flow_head.conv2", "mask.0", "mask.2",
 ]
+FLAG_EXACT_FP32 = 0      # CUDA-core fp32 convolutions
+FLAG_TENSOR_CORES = 1    # tcgen05 convolutions on fp16 hi/lo split operands (fp32-level accuracy)
+DEFAULT_FLAGS = FLAG_TENSOR_CORES
 LM_LMBDA = 1e-4   # reference config/default.py:54
 EP_LMBDA = 100.0  # reference config/default.py:55
 
@@ -41,7 +44,10 @@ def _stream() -> int:
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    """Scratch buffer whose data_ptr is 1024-byte aligned (TMA-staged planes live inside it)."""
+    t = torch.empty(max(int(nbytes), 256) + 1024, dtype=torch.uint8, device=device)
+    off = (-t.data_ptr()) % 1024
+    return t[off:off + max(int(nbytes), 256)]
 
 
 def pack_weights(state: Dict[str, torch.Tensor], device="cuda") -> torch.Tensor:
@@ -54,7 +60,7 @@ def pack_weights(state: Dict[str, torch.Tensor], device="cuda") -> torch.Tensor:
         for sfx in (".weight", ".bias"):
             tens.append(state[k + sfx].detach().to(device=device, dtype=torch.float32).contiguous())
     arr = (C.c_void_p * len(tens))(*[t.data_ptr() for t in tens])
-    blob = torch.empty(L.b200pose_packed_weights_bytes(), dtype=torch.uint8, device=device)
+    blob = _ws(L.b200pose_packed_weights_bytes(), device)
     _lib.check(L.b200pose_pack_weights(arr, blob.data_ptr(), _stream()), "b200pose_pack_weights")
     torch.cuda.current_stream().synchronize()      # `tens` must outlive the packing kernels
     return blob
@@ -115,7 +121,8 @@ def flow_init(depth: torch.Tensor, K: torch.Tensor, G: torch.Tensor) -> Tuple[to
 
 
 def update_block(packed: torch.Tensor, net: torch.Tensor, xbuf: torch.Tensor, corr: torch.Tensor,
-                 coords1: torch.Tensor, flow: torch.Tensor, B: int, h: int, w: int) -> Tuple[torch.Tensor, torch.Tensor]:
+                 coords1: torch.Tensor, flow: torch.Tensor, B: int, h: int, w: int,
+                 flags: int = DEFAULT_FLAGS) -> Tuple[torch.Tensor, torch.Tensor]:
     """In place on net / coords1 / flow; returns (mask [P,576], dflow [P,2])."""
     L = _lib.lib()
     for t, n in ((net, "net"), (xbuf, "xbuf"), (corr, "corr"), (coords1, "coords1"), (flow, "flow")):
@@ -127,8 +134,33 @@ def update_block(packed: torch.Tensor, net: torch.Tensor, xbuf: torch.Tensor, co
     ws = _ws(nb, net.device)
     _lib.check(L.b200pose_update_block(packed.data_ptr(), net.data_ptr(), xbuf.data_ptr(), corr.data_ptr(),
                                        coords1.data_ptr(), flow.data_ptr(), mask.data_ptr(), dflow.data_ptr(),
-                                       B, h, w, ws.data_ptr(), nb, _stream()), "b200pose_update_block")
+                                       B, h, w, int(flags), ws.data_ptr(), nb, _stream()), "b200pose_update_block")
     return mask, dflow
+
+
+def conv_layer_info(layer: int):
+    L = _lib.lib()
+    v = [C.c_int() for _ in range(5)]
+    _lib.check(L.b200pose_conv_layer_info(layer, *[C.byref(x) for x in v]), "b200pose_conv_layer_info")
+    return tuple(x.value for x in v)      # cin0, cin1, cout, kh, kw
+
+
+def conv_layer(packed: torch.Tensor, layer: int, in0: torch.Tensor, in1: Optional[torch.Tensor], B: int, h: int, w: int,
+               flags: int = DEFAULT_FLAGS, workspace: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+    """One update-block convolution (+bias, no activation) on PXC inputs; returns [P, roundup(cout,4)]."""
+    L = _lib.lib()
+    _chk(in0, "in0")
+    cin0, cin1, cout, kh, kw = conv_layer_info(layer)
+    P = B * h * w
+    if out is None:
+        out = torch.empty(P, (cout + 3) // 4 * 4, dtype=torch.float32, device=in0.device)
+    nb = L.b200pose_conv_layer_workspace_bytes(B, h, w)
+    if workspace is None:
+        workspace = _ws(nb, in0.device)
+    _lib.check(L.b200pose_conv_layer(packed.data_ptr(), layer, in0.data_ptr(), in0.shape[1], _p(in1),
+                                     in1.shape[1] if in1 is not None else 0, out.data_ptr(), B, h, w, int(flags),
+                                     workspace.data_ptr(), nb, _stream()), "b200pose_conv_layer")
+    return out
 
 
 def upsample_weight(flow: torch.Tensor, mask: torch.Tensor, geofea1: Optional[torch.Tensor],
@@ -185,7 +217,8 @@ class RefineWorkspace:
 
 def refine_iters(packed: torch.Tensor, fmap1, fmap2, context, geofea1, geofea2, depth, K, G, sigma: float,
                  n_iters: int, n_lm: int, ep_lmbda: float = EP_LMBDA, lm_lmbda: float = LM_LMBDA,
-                 workspace: Optional[RefineWorkspace] = None, want_flows: bool = False, want_weight: bool = False):
+                 workspace: Optional[RefineWorkspace] = None, want_flows: bool = False, want_weight: bool = False,
+                 flags: int = DEFAULT_FLAGS):
     """The fused inner loop (b200pose_refine_iters).  depth [B,H,W]; G [B,4,4] updated in place.
     Returns dict(G=..., flow_first=..., flow_last=..., weight=...)."""
     _need_cuda()
@@ -204,14 +237,14 @@ def refine_iters(packed: torch.Tensor, fmap1, fmap2, context, geofea1, geofea2, 
     _lib.check(L.b200pose_refine_iters(packed.data_ptr(), fmap1.data_ptr(), fmap2.data_ptr(), context.data_ptr(),
                                        geofea1.data_ptr(), geofea2.data_ptr(), depth.data_ptr(), K.data_ptr(),
                                        G.data_ptr(), float(sigma), B, Cg, H, W, n_iters, n_lm, float(ep_lmbda),
-                                       float(lm_lmbda), _p(ff), _p(fl), _p(wl), workspace.buf.data_ptr(),
+                                       float(lm_lmbda), int(flags), _p(ff), _p(fl), _p(wl), workspace.buf.data_ptr(),
                                        workspace.nbytes, _stream()), "b200pose_refine_iters")
     return dict(G=G, flow_first=ff, flow_last=fl, weight=wl, workspace=workspace)
 
 
 def refine_iters_host(packed: torch.Tensor, fmap1, fmap2, context, geofea1, geofea2, depth, K, G, sigma: float,
                       n_iters: int, n_lm: int, ep_lmbda: float = EP_LMBDA, lm_lmbda: float = LM_LMBDA,
-                      scratch: Optional[torch.Tensor] = None):
+                      scratch: Optional[torch.Tensor] = None, flags: int = DEFAULT_FLAGS):
     """Host-buffer entry point (b200pose_refine_iters_host): all tensors are CPU float32 (pinned for full
     copy speed); G [B,4,4] is overwritten on the host.  Synchronises the stream before returning."""
     _need_cuda()
@@ -227,7 +260,7 @@ def refine_iters_host(packed: torch.Tensor, fmap1, fmap2, context, geofea1, geof
     _lib.check(L.b200pose_refine_iters_host(packed.data_ptr(), fmap1.data_ptr(), fmap2.data_ptr(), context.data_ptr(),
                                             geofea1.data_ptr(), geofea2.data_ptr(), depth.data_ptr(), K.data_ptr(),
                                             G.data_ptr(), float(sigma), B, Cg, H, W, n_iters, n_lm, float(ep_lmbda),
-                                            float(lm_lmbda), scratch.data_ptr(), scratch.numel(), _stream()),
+                                            float(lm_lmbda), int(flags), scratch.data_ptr(), scratch.numel(), _stream()),
                "b200pose_refine_iters_host")
     return G, scratch
 

@@ -1,0 +1,80 @@
+"""Every convolution of the update block, one at a time, on both code paths (exact fp32 FFMA and the
+tcgen05 fp16-hi/lo tensor-core path) against torch's fp32 conv2d on the CPU (what the reference runs:
+thirdparty/raft/update.py nn.Conv2d layers with the shipped weights)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from rnnpose_b200 import synthetic as S
+from tests.util import load_update_weights
+
+pytestmark = pytest.mark.gpu
+
+# layer id -> (weight keys (fused along Cout), padding)
+LAYERS = {
+    0: (["encoder.convc1"], 0), 1: (["encoder.convc2"], 1), 3: (["encoder.convf2"], 1), 4: (["encoder.conv"], 1),
+    5: (["gru.convz1", "gru.convr1"], (0, 2)), 6: (["gru.convq1"], (0, 2)),
+    7: (["gru.convz2", "gru.convr2"], (2, 0)), 8: (["gru.convq2"], (2, 0)),
+    9: (["flow_head.conv1", "mask.0"], 1), 10: (["mask.2"], 0),
+}
+
+
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def to_pxc(x):
+    B, C, h, w = x.shape
+    return x.permute(0, 2, 3, 1).reshape(B * h * w, C).contiguous()
+
+
+def from_pxc(x, B, h, w):
+    return x.view(B, h, w, -1).permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from rnnpose_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def packed(ops):
+    return ops.pack_weights(load_update_weights(), dev())
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["fp32", "tcgen05"])
+@pytest.mark.parametrize("shape", [(2, 9, 12), (1, 30, 40), (3, 16, 20)], ids=["9x12", "30x40", "16x20"])
+@pytest.mark.parametrize("layer", sorted(LAYERS))
+def test_conv_layer(ops, packed, layer, shape, flags):
+    wts = load_update_weights()
+    keys, pad = LAYERS[layer]
+    W = torch.cat([wts[k + ".weight"] for k in keys], 0)
+    bias = torch.cat([wts[k + ".bias"] for k in keys], 0)
+    B, h, w = shape
+    cin0, cin1, cout, kh, kw = ops.conv_layer_info(layer)
+    assert W.shape == (cout, cin0 + cin1, kh, kw)
+    x = S.hash_features((B, cin0 + cin1, h, w), 100 + layer, 1.5)
+    ref = F.conv2d(x, W, bias, padding=pad)
+    in0 = to_pxc(x[:, :cin0]).to(dev())
+    in1 = to_pxc(x[:, cin0:]).to(dev()) if cin1 else None
+    out = ops.conv_layer(packed, layer, in0, in1, B, h, w, flags=flags)
+    torch.cuda.synchronize()
+    got = from_pxc(out[:, :cout].contiguous(), B, h, w).cpu()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    assert err <= 3e-6 * scale + 1e-5, f"layer {layer} flags {flags}: max err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["fp32", "tcgen05"])
+def test_convf1_via_im2col(ops, packed, flags):
+    """encoder.convf1 (7x7, Cin=2) is lowered to a 98-wide im2col + 1x1 GEMM (layer id 2)."""
+    wts = load_update_weights()
+    B, h, w = 2, 11, 13
+    flow = S.hash_features((B, 2, h, w), 7, 4.0)
+    ref = F.conv2d(flow, wts["encoder.convf1.weight"], wts["encoder.convf1.bias"], padding=3)
+    col = F.unfold(flow, 7, padding=3).view(B, 2, 49, h, w).permute(0, 2, 1, 3, 4).reshape(B, 98, h, w)   # k = tap*2 + c
+    out = ops.conv_layer(packed, 2, to_pxc(col).to(dev()), None, B, h, w, flags=flags)
+    got = from_pxc(out[:, :128].contiguous(), B, h, w).cpu()
+    assert (got - ref).abs().max().item() <= 3e-6 * ref.abs().max().item() + 1e-5
