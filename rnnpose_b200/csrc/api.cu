@@ -273,6 +273,7 @@ int b200pose_conv_layer(const void* packed_weights, int layer, const float* in0,
     int c0, c1, cout, kh, kw;
     b200pose_conv_layer_info(layer, &c0, &c1, &cout, &kh, &kw);
     if (c1 > 0 && !in1) return B200POSE_E_NULL;
+    if (pitch0 < c0 || (pitch0 & 3) || (c1 > 0 && (pitch1 < c1 || (pitch1 & 3)))) return B200POSE_E_ARG;   // float4 rows
     cudaStream_t s = (cudaStream_t)stream;
     const float* wts = reinterpret_cast<const float*>(packed_weights);
     const B2PWeightLayout& L = b2p_weight_layout();

@@ -64,7 +64,11 @@ def test_conv_layer(ops, packed, layer, shape, flags):
     got = from_pxc(out[:, :cout].contiguous(), B, h, w).cpu()
     scale = ref.abs().max().item()
     err = (got - ref).abs().max().item()
-    assert err <= 3e-6 * scale + 1e-5, f"layer {layer} flags {flags}: max err {err} (scale {scale})"
+    # fp32 path: plain fp32 rounding noise.  tcgen05 path: operands are exact to 2^-22, but the tensor core adds each
+    # 16-deep partial dot product into the fp32 TMEM accumulator with truncation, so the error grows with the number
+    # of accumulation steps (3 * K/16, up to 432 here): observed <= 1.5e-5 of the output scale.
+    tol = (3e-6 if flags == 0 else 4e-5) * scale + 1e-5
+    assert err <= tol, f"layer {layer} flags {flags}: max err {err} (scale {scale})"
 
 
 @pytest.mark.parametrize("flags", [0, 1], ids=["fp32", "tcgen05"])
@@ -75,6 +79,8 @@ def test_convf1_via_im2col(ops, packed, flags):
     flow = S.hash_features((B, 2, h, w), 7, 4.0)
     ref = F.conv2d(flow, wts["encoder.convf1.weight"], wts["encoder.convf1.bias"], padding=3)
     col = F.unfold(flow, 7, padding=3).view(B, 2, 49, h, w).permute(0, 2, 1, 3, 4).reshape(B, 98, h, w)   # k = tap*2 + c
-    out = ops.conv_layer(packed, 2, to_pxc(col).to(dev()), None, B, h, w, flags=flags)
+    colp = torch.zeros(B * h * w, 112)                      # pipeline pitch of the im2col buffer (16-byte rows)
+    colp[:, :98] = to_pxc(col)
+    out = ops.conv_layer(packed, 2, colp.to(dev()), None, B, h, w, flags=flags)
     got = from_pxc(out[:, :128].contiguous(), B, h, w).cpu()
-    assert (got - ref).abs().max().item() <= 3e-6 * ref.abs().max().item() + 1e-5
+    assert (got - ref).abs().max().item() <= (3e-6 if flags == 0 else 4e-5) * ref.abs().max().item() + 1e-5

@@ -43,17 +43,20 @@ def run_gpu(ops, packed, fmap1, fmap2, mb, G0, n_iters, n_lm, **kw):
     return res
 
 
+@pytest.mark.parametrize("flags", [0, 1], ids=["fp32", "tcgen05"])
 @pytest.mark.parametrize("name", ["refine_cfg0_240x320_1x1.npz", "refine_128x160_4x3.npz",
                                   "refine_240x320_4x3.npz", "refine_occl_128x160_8x3.npz"])
-def test_refine_matches_reference_golden(ops, packed, name):
+def test_refine_matches_reference_golden(ops, packed, name, flags):
     g = golden(name)
     H, W, n_iters, n_lm, seed, occl = [int(v) for v in g["meta"]]
     idxs = [int(i) for i in g["idxs"]]
     mb = S.make_batch(idxs, H, W, seed, bool(occl), with_images=False)
-    res = run_gpu(ops, packed, T(g["fmap1"]), T(g["fmap2"]), mb, T(g["G0"]), n_iters, n_lm, want_flows=True, want_weight=True)
+    res = run_gpu(ops, packed, T(g["fmap1"]), T(g["fmap2"]), mb, T(g["G0"]), n_iters, n_lm, want_flows=True, want_weight=True,
+                  flags=flags)
     Tij = res["G"].cpu()
     Ti_pred = torch.matmul(Tij, mb["T_init"])                       # PoseRefiner.py:365
     err = (Ti_pred - T(g["Ti_pred"])).abs().max().item()
+    print(f"[parity] {name} flags={flags}: max |dSE3| vs executed reference = {err:.3e}")
     assert err < SE3_TOL, f"final SE3 differs from the reference by {err}"
     assert (Tij - T(g["Tij"])).abs().max().item() < SE3_TOL
     torch.testing.assert_close(res["flow_last"].cpu()[:, :, ::4, ::4], T(g["flow_last"]), rtol=1e-3, atol=2e-2)
@@ -127,7 +130,7 @@ def test_error_codes(ops, packed):
     from rnnpose_b200 import _lib
     L = _lib.lib()
     assert L.b200pose_refine_iters(None, None, None, None, None, None, None, None, None, 1.0, 1, 32, 128, 160, 1, 1,
-                                   100.0, 1e-4, None, None, None, None, 0, None) == -1
+                                   100.0, 1e-4, 0, None, None, None, None, 0, None) == -1
     mb = S.make_batch([0], 64, 64, with_images=False)       # h/8 = 8 -> level 3 is 1x1: rejected like the reference's NaN
     f = S.hash_features((1, 256, 8, 8), 1)
     with pytest.raises(RuntimeError, match="unsupported shape"):
