@@ -1,0 +1,93 @@
+"""Drop-in boundary: the PoseRefiner mirror against the executed reference INCLUDING the
+reference's own zoom-crop and two render iterations (fixture tests/golden/dropin_2x2x1.npz)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from rnnpose_b200 import synthetic as S
+from rnnpose_b200.refiner import PoseRefiner, zoom_crop_params
+from rnnpose_b200.se3 import SE3Sequence
+from tests.util import golden, load_update_weights
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+IMG_HW, CROP_HW = (240, 320), (128, 160)
+
+
+def scene(idx):
+    return S.make_scene(idx, IMG_HW[0], IMG_HW[1], seed=4321, fill=0.5)
+
+
+def inputs(sc):
+    obs = S.render_observed(sc, K=sc.K_crop, H=IMG_HW[0], W=IMG_HW[1])
+    return (torch.from_numpy(obs["img"])[None], torch.from_numpy(obs["geo"])[None],
+            torch.from_numpy(sc.K_crop.astype(np.float32))[None], torch.from_numpy(sc.T_init.astype(np.float32))[None, None],
+            torch.from_numpy(sc.T_gt.astype(np.float32))[None, None])
+
+
+def test_zoom_crop_matches_reference_cv2_path():
+    """Device-side crop geometry == reference get_affine_transformation (numpy + cv2.getAffineTransform)."""
+    g = golden("dropin_2x2x1.npz")
+    for k, idx in enumerate(int(i) for i in g["idxs"]):
+        sc = scene(idx)
+        image, geo2, K, T0, _ = inputs(sc)
+        ren = S.AnalyticRenderer([sc])
+        pc = ren.render_pointcloud(None, T=T0[:, 0], K=K, render_image_size=IMG_HW)
+        theta, K_crop = zoom_crop_params(pc > 0, K, T0[:, 0], CROP_HW)
+        torch.testing.assert_close(K_crop[0], torch.from_numpy(g["K_crop"][k, 0]), rtol=1e-5, atol=1e-3)
+        grid = F.affine_grid(theta, torch.Size([1, 1, *CROP_HW]))
+        corners = grid[0, [0, 0, -1], [0, -1, 0]]
+        torch.testing.assert_close(corners, torch.from_numpy(g["theta"][k, 0]), rtol=1e-5, atol=1e-5)
+
+
+def test_state_dict_layout_matches_reference_checkpoint_keys():
+    net = PoseRefiner({"FLOW_NET": "raft"}, renderer=None, image_fea_enc=torch.nn.Identity(),
+                      render_image_size=IMG_HW, zoom_crop_size=CROP_HW)
+    sd = net.state_dict()
+    assert sd["sigma.0"].shape == (1,)
+    ref = load_update_weights()
+    for k, v in ref.items():
+        assert sd["cf_net.update_block." + k].shape == v.shape, k
+    assert len([k for k in sd if k.startswith("cf_net.update_block.")]) == 30
+    missing, unexpected = net.cf_net.load_state_dict({"update_block." + k: v for k, v in ref.items()}, strict=True), None
+
+
+class ReplayEncoder(torch.nn.Module):
+    """Stands in for the (out-of-scope) RAFT BasicEncoder: replays the feature maps the reference computed."""
+
+    def __init__(self, fmaps):
+        super().__init__()
+        self.fmaps, self.i = fmaps, 0
+
+    def forward(self, a, b):
+        f = self.fmaps[self.i]; self.i += 1
+        return f[0:1].to(a.device), f[1:2].to(a.device)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [0, 1], ids=["fp32", "tcgen05"])
+def test_pose_refiner_dropin_matches_reference(flags):
+    g = golden("dropin_2x2x1.npz")
+    n_render, n_iters, n_lm = [int(v) for v in g["meta"]]
+    dev = torch.device("cuda:0")
+    for k, idx in enumerate(int(i) for i in g["idxs"]):
+        sc = scene(idx)
+        image, geo2, K, T0, Tgt = inputs(sc)
+        cfg = {"FLOW_NET": "raft", "IS_CALIBRATED": True, "ITER_COUNT": n_iters, "RENDER_ITER_COUNT": n_render,
+               "OPTIM_ITER_COUNT": n_lm}
+        net = PoseRefiner(cfg, renderer=S.AnalyticRenderer([sc]), image_fea_enc=ReplayEncoder(torch.from_numpy(g["fmaps"][k])),
+                          render_image_size=IMG_HW, zoom_crop_size=CROP_HW)
+        net.cf_net.load_state_dict({"update_block." + kk: v for kk, v in load_update_weights().items()}, strict=True)
+        net = net.to(dev)
+        net.flags = flags
+        out = net(image.to(dev), SE3Sequence(matrix=T0.to(dev)), K.to(dev), fea_3d=torch.zeros(1, 4, 256, device=dev),
+                  Tj_gt=SE3Sequence(matrix=Tgt.to(dev)), obj_cls=None, geofea_3d=torch.zeros(1, 4, 32, device=dev),
+                  geofea_2d=geo2.to(dev))
+        err = (out["Ti_pred"].G[0, 0].cpu() - torch.from_numpy(g["Ti_pred"][k])).abs().max().item()
+        print(f"[dropin] scene {idx} flags={flags}: max |dSE3| vs executed reference = {err:.3e}")
+        assert err < 1e-4
+        assert out["weight"].shape == (1, 1, 1, *CROP_HW) and out["flow"][0].shape == (1, 2, *CROP_HW)
+        assert len(out["syn_depth"]) == n_render * n_iters and len(out["Tij_gt"]) == n_render * n_iters
