@@ -327,6 +327,7 @@ int b200pose_lm_solve(const float* depth, const float* target, const float* weig
     if (B < 1 || H < 1 || W < 1) return B200POSE_E_SHAPE;
     if (n_steps < 0) return B200POSE_E_ARG;
     if (((uintptr_t)workspace & 255) || workspace_bytes < b2p_lm_ws_bytes(B, H, W)) return B200POSE_E_WORKSPACE;
+    { int rc0 = b2p_lm_reset(workspace, B, H, W, (cudaStream_t)stream); if (rc0) return rc0; }
     for (int i = 0; i < n_steps; ++i) {
         int rc = b2p_lm_step(depth, target, weight, K, G, B, H, W, depth_offset, ep_lmbda, lm_lmbda,
                              H_out ? H_out + (size_t)i * B * 36 : nullptr, b_out ? b_out + (size_t)i * B * 6 : nullptr,
@@ -340,8 +341,8 @@ size_t b200pose_refine_workspace_bytes(int B, int H, int W) { return refine_ws_l
 
 int b200pose_refine_launch_count(int n_iters, int n_lm) {
     // per render iteration: volume + 3 pools + context;  per recurrent iteration: flow_init, lookup,
-    // update block, upsample+weight, 2 launches per LM step
-    return 5 + n_iters * (2 + UPDATE_LAUNCHES + 1 + 2 * n_lm);
+    // update block, upsample+weight, 1 launch per LM step (+1 counter reset per call)
+    return 6 + n_iters * (2 + UPDATE_LAUNCHES + 1 + n_lm);
 }
 
 int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const float* fmap2, const float* context,
@@ -363,6 +364,7 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
     const UpdateWs& u = r.u;
     int rc;
     // update_corr_fn == True part (CFNet.py:115-133): pyramid + hidden-state reset, once per render iteration
+    if ((rc = b2p_lm_reset(r.lm, B, H, W, s))) return rc;
     if ((rc = b200pose_corr_pyramid(fmap1, fmap2, B, 256, h, w, r.pyr, stream))) return rc;
     if (tc) rc = b2p_context_init(context, B, H, W, r.net, nullptr, u.net_h[0], u.net_h[1], u.x_h[0], u.x_h[1], s);
     else rc = b2p_context_init(context, B, H, W, r.net, r.xbuf, nullptr, nullptr, nullptr, nullptr, s);

@@ -89,6 +89,23 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// the "+r" operands tie the loaded registers to the wait so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -195,12 +212,33 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         tc_fence_after();
         for (int col0 = 0; col0 < p.n_tile; col0 += 32) {
             uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, r);
+            tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, r);
             const int nb = n0 + col0;
-            if (!valid || nb >= p.cout) continue;
+            const bool live = valid && nb < p.cout;
+            // side inputs of the GRU epilogues: all loads of the 32-channel group are issued back to back (one
+            // dependent-load round trip per group instead of eight) while the TMEM load is still in flight
+            float4 hh[8], zz[8];
+            const bool need_h = live && ((p.epi == EPI_GRU_ZR && nb >= 128) || p.epi == EPI_GRU_Q);
+            const bool need_z = live && p.epi == EPI_GRU_Q;
+            if (need_h) {
+                const float4* hp4 = reinterpret_cast<const float4*>(p.hbuf + pix * 128 + (nb & 127));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hh[j] = hp4[j];
+            }
+            if (need_z) {
+                const float4* zp4 = reinterpret_cast<const float4*>(p.zbuf + pix * 128 + nb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) zz[j] = __ldg(zp4 + j);
+            }
+            tmem_ld_wait(r);
+            if (!live) continue;
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(p.bias + nb + j);
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+                v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+                v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+            }
             if (p.epi == EPI_SCALE) {
                 float* d = p.out_f32 + pix * p.out_f32_pitch + nb;
 #pragma unroll
@@ -228,25 +266,22 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             } else if (p.epi == EPI_GRU_ZR) {                  // r gate -> r * h
                 oc = nb - 128;
-                const float* hp = p.hbuf + pix * 128 + oc;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 hh = *reinterpret_cast<const float4*>(hp + j);
-                    v[j] = sigm(v[j]) * hh.x; v[j + 1] = sigm(v[j + 1]) * hh.y; v[j + 2] = sigm(v[j + 2]) * hh.z; v[j + 3] = sigm(v[j + 3]) * hh.w;
+                for (int j = 0; j < 8; ++j) {
+                    v[4 * j] = sigm(v[4 * j]) * hh[j].x; v[4 * j + 1] = sigm(v[4 * j + 1]) * hh[j].y;
+                    v[4 * j + 2] = sigm(v[4 * j + 2]) * hh[j].z; v[4 * j + 3] = sigm(v[4 * j + 3]) * hh[j].w;
                 }
             } else if (p.epi == EPI_GRU_Q) {                   // h <- (1-z) h + z tanh(q)
-                float* hp = p.hbuf + pix * 128 + nb;
-                const float* zp = p.zbuf + pix * 128 + nb;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 hh = *reinterpret_cast<const float4*>(hp + j);
-                    const float4 zz = *reinterpret_cast<const float4*>(zp + j);
-                    v[j] = (1.f - zz.x) * hh.x + zz.x * tanhf(v[j]);
-                    v[j + 1] = (1.f - zz.y) * hh.y + zz.y * tanhf(v[j + 1]);
-                    v[j + 2] = (1.f - zz.z) * hh.z + zz.z * tanhf(v[j + 2]);
-                    v[j + 3] = (1.f - zz.w) * hh.w + zz.w * tanhf(v[j + 3]);
-                    *reinterpret_cast<float4*>(hp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 8; ++j) {
+                    v[4 * j] = (1.f - zz[j].x) * hh[j].x + zz[j].x * tanhf(v[4 * j]);
+                    v[4 * j + 1] = (1.f - zz[j].y) * hh[j].y + zz[j].y * tanhf(v[4 * j + 1]);
+                    v[4 * j + 2] = (1.f - zz[j].z) * hh[j].z + zz[j].z * tanhf(v[4 * j + 2]);
+                    v[4 * j + 3] = (1.f - zz[j].w) * hh[j].w + zz[j].w * tanhf(v[4 * j + 3]);
                 }
+                float4* hp4 = reinterpret_cast<float4*>(p.hbuf + pix * 128 + nb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hp4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
             // fp16 hi/lo planes for the next convolution
             __half* dh = p.out_hi + pix * p.out_h_pitch + oc;

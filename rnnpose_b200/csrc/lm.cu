@@ -89,6 +89,10 @@ __global__ void __launch_bounds__(LM_THREADS) lm_step_kernel(
         const float Z = __ldg(dptr + px) + depth_add;
         const float2 tg = __ldg(tptr + px);
         const float wv = __ldg(wptr + px);
+        // A pixel whose weight is exactly 0 adds exactly 0 to H and b (all terms finite): skip its ~100 fp64 FMAs.
+        // 65-80 % of a crop is background (weight = ... * (depth > 0)).  Non-finite inputs still take the full path so
+        // that they poison the sums exactly like the reference's arithmetic (NaN -> zero update downstream).
+        if (wv == 0.f && isfinite(Z) && isfinite(tg.x) && isfinite(tg.y)) continue;
         const float X = Z * ((float)u - cx) / fx;
         const float Y = Z * ((float)v - cy) / fy;
         const float X1 = Gm[0] * X + Gm[1] * Y + Gm[2] * Z + Gm[3];
@@ -113,11 +117,20 @@ __global__ void __launch_bounds__(LM_THREADS) lm_step_kernel(
         double wJ0[6], wJ1[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) { wJ0[i] = vw * J0[i]; wJ1[i] = vw * J1[i]; }
+        // J0[1] and J1[0] are structural zeros (jproj rows (fx/Z,0,.) and (0,fy/Z,.)): their products are dropped at
+        // compile time, 30 + 10 FMAs instead of 42 + 12
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
 #pragma unroll
-            for (int j = i; j < 6; ++j) acc[tri_idx(i, j)] += wJ0[i] * J0[j] + wJ1[i] * J1[j];
-            acc[21 + i] += wJ0[i] * r0 + wJ1[i] * r1;
+            for (int j = i; j < 6; ++j) {
+                const bool u0 = (i != 1) && (j != 1), u1 = (i != 0) && (j != 0);
+                if (u0 && u1) acc[tri_idx(i, j)] += wJ0[i] * J0[j] + wJ1[i] * J1[j];
+                else if (u0) acc[tri_idx(i, j)] += wJ0[i] * J0[j];
+                else if (u1) acc[tri_idx(i, j)] += wJ1[i] * J1[j];
+            }
+            if (i == 0) acc[21 + i] += wJ0[i] * r0;
+            else if (i == 1) acc[21 + i] += wJ1[i] * r1;
+            else acc[21 + i] += wJ0[i] * r0 + wJ1[i] * r1;
         }
     }
 
@@ -234,6 +247,15 @@ size_t b2p_lm_ws_bytes(int B, int H, int W) {
     return align_up((size_t)B * lm_nblk(H, W) * NACC * sizeof(double), 256) + align_up((size_t)B * sizeof(unsigned), 256);
 }
 
+// The per-sample ticket counters must be zero before the first step; every step leaves them zero again.
+int b2p_lm_reset(void* ws, int B, int H, int W, cudaStream_t s) {
+    unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) +
+                                                     align_up((size_t)B * lm_nblk(H, W) * NACC * sizeof(double), 256));
+    zero_u32_kernel<<<ceil_div(B, 256), 256, 0, s>>>(counters, B);
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
 int b2p_lm_step(const float* depth, const float* target, const float* weight, const float* K, float* G, int B, int H,
                 int W, float depth_add, double ep, double lm, double* H_out, double* b_out, float* delta_out, void* ws,
                 cudaStream_t s) {
@@ -241,7 +263,6 @@ int b2p_lm_step(const float* depth, const float* target, const float* weight, co
     double* partials = reinterpret_cast<double*>(ws);
     unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) +
                                                      align_up((size_t)B * nblk * NACC * sizeof(double), 256));
-    zero_u32_kernel<<<ceil_div(B, 256), 256, 0, s>>>(counters, B);
     dim3 grid(nblk, B);
     lm_step_kernel<<<grid, LM_THREADS, 0, s>>>(depth, target, weight, K, G, B, H, W, depth_add, ep, lm, partials, counters, nblk,
                                                H_out, b_out, delta_out);
