@@ -25,7 +25,8 @@ constexpr int UM_THREADS = 192;
 constexpr int TILE_ROWS = 16, TILE_COLS = 8;          // 128-pixel M tile
 constexpr int BKC = 64;                                // channels per K chunk (128 B of fp16)
 constexpr int A_TILE_BYTES = 128 * BKC * 2;            // 16 KB
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;                          // two accumulator buffers
+constexpr int TMEM_BUF_COLS = 256;
 
 struct UmmaConvParams {
     CUtensorMap a_hi[2], a_lo[2];     // activation segments (PXC fp16 planes), rank 4: (C, w, h, B)
@@ -33,6 +34,7 @@ struct UmmaConvParams {
     int seg0_chunks, chunks_per_tap, kh, kw;
     int B, h, w, tiles_x, tiles_y;
     int n_tile, cout, stages;
+    int m_tiles, total_tiles, b_batched;   // b_batched: the weight map's 3rd coordinate is the sample index (correlation volume)
     const float* bias;
     int epi; float scale;
     float* out_f32; int out_f32_pitch;
@@ -131,20 +133,26 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     const uint32_t bars = smem_base + (uint32_t)p.stages * stage_bytes;     // full[S], empty[S], tmem_full, tmem_slot
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
-    const uint32_t tmem_full_bar = bars + 16u * p.stages;
-    const uint32_t tmem_slot = tmem_full_bar + 8u;
+    // two TMEM accumulator buffers: the epilogue of tile i overlaps the main loop of tile i+1
+    auto tmem_full_bar = [&](int b) { return bars + 16u * p.stages + 8u * b; };
+    auto tmem_empty_bar = [&](int b) { return bars + 16u * p.stages + 16u + 8u * b; };
+    const uint32_t tmem_slot = bars + 16u * p.stages + 32u;
 
-    // work item
+    // persistent CTA: tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; t = n_idx * m_tiles + m_idx so that the
+    // CTAs of one round share the weight tile (L2) and walk over different pixel tiles
     const int tiles_per_img = p.tiles_x * p.tiles_y;
-    const int bimg = blockIdx.x / tiles_per_img;
-    const int trem = blockIdx.x - bimg * tiles_per_img;
-    const int y0 = (trem / p.tiles_x) * TILE_ROWS, x0 = (trem % p.tiles_x) * TILE_COLS;
-    const int n0 = blockIdx.y * p.n_tile;
     const int nk = p.kh * p.kw * p.chunks_per_tap;
+    auto decode = [&](int t, int& bimg, int& y0, int& x0, int& n0) {
+        const int n_idx = t / p.m_tiles, m_idx = t - n_idx * p.m_tiles;
+        bimg = m_idx / tiles_per_img;
+        const int trem = m_idx - bimg * tiles_per_img;
+        y0 = (trem / p.tiles_x) * TILE_ROWS; x0 = (trem % p.tiles_x) * TILE_COLS;
+        n0 = n_idx * p.n_tile;
+    };
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -160,20 +168,25 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
 
     if (warp == 0) {
         if (lane == 0) {
-            // ------------------------------------------------ TMA producer
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % p.stages, ph = (kc / p.stages) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1);
-                mbar_expect_tx(full_bar(s), stage_bytes);
-                const int tap = kc / p.chunks_per_tap, cc = kc - tap * p.chunks_per_tap;
-                const int ky = tap / p.kw, kx = tap - ky * p.kw;
-                const int seg = cc >= p.seg0_chunks ? 1 : 0;
-                const int c0 = (seg ? cc - p.seg0_chunks : cc) * BKC;
-                const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-                tma_load_4d(&p.a_hi[seg], sa, full_bar(s), c0, x0 + kx - (p.kw >> 1), y0 + ky - (p.kh >> 1), bimg);
-                tma_load_4d(&p.a_lo[seg], sa + A_TILE_BYTES, full_bar(s), c0, x0 + kx - (p.kw >> 1), y0 + ky - (p.kh >> 1), bimg);
-                tma_load_3d(&p.b_hi, sa + 2 * A_TILE_BYTES, full_bar(s), cc * BKC, n0, tap);
-                tma_load_3d(&p.b_lo, sa + 2 * A_TILE_BYTES + b_tile_bytes, full_bar(s), cc * BKC, n0, tap);
+            // ------------------------------------------------ TMA producer (runs ahead across tile boundaries)
+            uint32_t it = 0;                                   // global K-chunk counter -> ring slot and phase
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                int bimg, y0, x0, n0;
+                decode(t, bimg, y0, x0, n0);
+                for (int kc = 0; kc < nk; ++kc, ++it) {
+                    const int s = it % p.stages, ph = (it / p.stages) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), stage_bytes);
+                    const int tap = kc / p.chunks_per_tap, cc = kc - tap * p.chunks_per_tap;
+                    const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                    const int seg = cc >= p.seg0_chunks ? 1 : 0;
+                    const int c0 = (seg ? cc - p.seg0_chunks : cc) * BKC;
+                    const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+                    tma_load_4d(&p.a_hi[seg], sa, full_bar(s), c0, x0 + kx - (p.kw >> 1), y0 + ky - (p.kh >> 1), bimg);
+                    tma_load_4d(&p.a_lo[seg], sa + A_TILE_BYTES, full_bar(s), c0, x0 + kx - (p.kw >> 1), y0 + ky - (p.kh >> 1), bimg);
+                    tma_load_3d(&p.b_hi, sa + 2 * A_TILE_BYTES, full_bar(s), cc * BKC, n0, p.b_batched ? bimg : tap);
+                    tma_load_3d(&p.b_lo, sa + 2 * A_TILE_BYTES + b_tile_bytes, full_bar(s), cc * BKC, n0, p.b_batched ? bimg : tap);
+                }
             }
         }
     } else if (warp == 1) {
@@ -182,37 +195,49 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=B=F16 (0), K-major both,
             // N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % p.stages, ph = (kc / p.stages) & 1;
-                mbar_wait(full_bar(s), ph);
+            uint32_t it = 0, tile_iter = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_iter) {
+                const int buf = tile_iter & 1;
+                const uint32_t acc = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
+                mbar_wait(tmem_empty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // epilogue has drained this buffer
                 tc_fence_after();
-                const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-                const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE_BYTES);
-                const uint64_t b_hi = umma_desc_sw128(sa + 2 * A_TILE_BYTES);
-                const uint64_t b_lo = umma_desc_sw128(sa + 2 * A_TILE_BYTES + b_tile_bytes);
+                for (int kc = 0; kc < nk; ++kc, ++it) {
+                    const int s = it % p.stages, ph = (it / p.stages) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+                    const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE_BYTES);
+                    const uint64_t b_hi = umma_desc_sw128(sa + 2 * A_TILE_BYTES);
+                    const uint64_t b_lo = umma_desc_sw128(sa + 2 * A_TILE_BYTES + b_tile_bytes);
 #pragma unroll
-                for (int k = 0; k < BKC / 16; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 2);       // 16 halves = 32 B = 2 x 16 B along K inside the swizzle atom
-                    tc_mma_f16(tmem_base, a_lo + adv, b_hi + adv, idesc, (kc | k) != 0 ? 1u : 0u);
-                    tc_mma_f16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-                    tc_mma_f16(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+                    for (int k = 0; k < BKC / 16; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 2);   // 16 halves = 32 B = 2 x 16 B along K inside the swizzle atom
+                        tc_mma_f16(acc, a_lo + adv, b_hi + adv, idesc, (kc | k) != 0 ? 1u : 0u);
+                        tc_mma_f16(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                        tc_mma_f16(acc, a_hi + adv, b_hi + adv, idesc, 1u);
+                    }
+                    tc_commit(empty_bar(s));      // frees the smem stage when these MMAs have read it
                 }
-                tc_commit(empty_bar(s));          // frees the smem stage when these MMAs have read it
+                tc_commit(tmem_full_bar(buf));    // accumulator of this tile complete
             }
-            tc_commit(tmem_full_bar);             // accumulator complete
         }
     } else {
         // ---------------------------------------------------- epilogue: TMEM -> registers -> global
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
         const int mrow = q * 32 + lane;
+        uint32_t tile_iter = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_iter) {
+        int bimg, y0, x0, n0;
+        decode(t, bimg, y0, x0, n0);
+        const int buf = tile_iter & 1;
         const int yy = y0 + (mrow >> 3), xx = x0 + (mrow & 7);
         const bool valid = yy < p.h && xx < p.w;
         const size_t pix = ((size_t)bimg * p.h + yy) * p.w + xx;
-        mbar_wait(tmem_full_bar, 0);
+        mbar_wait(tmem_full_bar(buf), (tile_iter >> 1) & 1);
         tc_fence_after();
         for (int col0 = 0; col0 < p.n_tile; col0 += 32) {
             uint32_t r[32];
-            tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, r);
+            tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS + col0), r);
             const int nb = n0 + col0;
             const bool live = valid && nb < p.cout;
             // side inputs of the GRU epilogues: all loads of the 32-channel group are issued back to back (one
@@ -303,6 +328,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
                 }
             }
         }
+        // every TMEM read of this tile has completed (tcgen05.wait::ld above): hand the buffer back to the MMA warp
+        tc_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(buf)) : "memory");
+        }   // tile loop
     }
     tc_fence_before();
     __syncthreads();
@@ -378,12 +407,14 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     p.out_hi = a.out_hi; p.out_lo = a.out_lo; p.out_h_pitch = a.out_h_pitch;
     p.zbuf = a.zbuf; p.hbuf = a.hbuf;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
-        B2P_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
-    dim3 grid(a.B * p.tiles_x * p.tiles_y, a.cout_pad / a.n_tile);
+    B2P_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int dev = 0, sms = 148;
+    B2P_CUDA(cudaGetDevice(&dev));
+    B2P_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    p.m_tiles = a.B * p.tiles_x * p.tiles_y;
+    p.total_tiles = p.m_tiles * (a.cout_pad / a.n_tile);
+    p.b_batched = a.b_batched;
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;      // persistent: one CTA per SM
     conv_umma_kernel<<<grid, UM_THREADS, smem, s>>>(p);
     B2P_LAUNCH_CHECK();
     return 0;

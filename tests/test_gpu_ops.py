@@ -108,7 +108,8 @@ def test_update_block_golden(ops, packed, flags):
     torch.testing.assert_close(from_pxc(mask, B, h, w).cpu(), T(g["mask"]), rtol=1e-4, atol=(3e-5 if flags == 0 else 2e-4))
     torch.testing.assert_close(from_pxc(dflow, B, h, w).cpu(), T(g["dflow"]), rtol=1e-4, atol=(3e-5 if flags == 0 else 2e-4))
     # flow out = (coords1 + dflow) - coords0
-    torch.testing.assert_close(from_pxc(flowd, B, h, w).cpu(), flow + T(g["dflow"]), rtol=1e-4, atol=5e-5)
+    torch.testing.assert_close(from_pxc(flowd, B, h, w).cpu(), flow + T(g["dflow"]), rtol=1e-4,
+                               atol=(5e-5 if flags == 0 else 5e-4))
 
 
 @pytest.mark.parametrize("flags", [0, 1], ids=["fp32", "tcgen05"])
