@@ -75,6 +75,11 @@ int b200pose_pack_weights(const float* const* tensors_host /* host array of 30 d
 size_t b200pose_pyramid_floats(int B, int h, int w);
 int b200pose_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int h, int w,
                           float* pyramid, void* stream);
+/* Tensor-core variant (what the fused loop uses with B200POSE_FLAG_TENSOR_CORES): D = 256 only, h*w must have a
+ * divisor n <= 240 with n % 16 == 0; the volume GEMM runs on tcgen05 with fp16 hi/lo split operands.          */
+size_t b200pose_corr_pyramid_tc_workspace_bytes(int B, int h, int w);
+int b200pose_corr_pyramid_tc(const float* fmap1, const float* fmap2, int B, int h, int w,
+                             float* pyramid, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a2: pyramid lookup -----------------------------------------------------------------------
  * Replaces CorrBlock.__call__ + bilinear_sampler (corr.py:36-57, utils/utils.py:57-71).

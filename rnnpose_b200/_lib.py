@@ -20,6 +20,8 @@ SIGNATURES = {
     "b200pose_pack_weights": (_i, [C.POINTER(_vp), _vp, _vp]),
     "b200pose_pyramid_floats": (_sz, [_i, _i, _i]),
     "b200pose_corr_pyramid": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "b200pose_corr_pyramid_tc_workspace_bytes": (_sz, [_i, _i, _i]),
+    "b200pose_corr_pyramid_tc": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "b200pose_corr_lookup": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "b200pose_context_init": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "b200pose_flow_init": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -132,9 +132,65 @@ int run_update_block_tc(const float* wts, float* net, float* coords1, float* flo
     return 0;
 }
 
+// levels 1..3 of the pyramid from level 0 (2x2 floor average pooling, corr.py:32-34)
+int pool_pyramid(float* pyramid, int B, int h, int w, cudaStream_t s) {
+    const int P = h * w;
+    float* src = pyramid;
+    int hl = h, wl = w, rc;
+    for (int l = 1; l < B200POSE_CORR_LEVELS; ++l) {
+        float* dst = src + (size_t)B * P * hl * wl;
+        if ((rc = b2p_corr_pool(src, B * P, hl, wl, dst, s))) return rc;
+        src = dst; hl >>= 1; wl >>= 1;
+    }
+    return 0;
+}
+
+struct VolumeWs {                 // operands of the tensor-core correlation GEMM
+    __half* fm_h[4];              // f1 hi, f1 lo, f2 hi, f2 lo as PXC [B*P][256]
+    float* zero_bias;             // the shared epilogue adds a bias; the volume has none
+};
+
+size_t volume_ws_layout(int B, int h, int w, void* ws, size_t cap, VolumeWs* out) {
+    const size_t P = (size_t)B * h * w;
+    Carver c(ws, cap);
+    VolumeWs v;
+    for (int k = 0; k < 4; ++k) v.fm_h[k] = c.take<__half>(P * 256);
+    v.zero_bias = c.take<float>((size_t)h * w + 64);
+    if (out) *out = v;
+    return align_up(c.off, 1024);
+}
+
+// largest MMA N (multiple of 16, <= 240) that divides P; 0 if there is none
+inline int volume_ntile(int P) {
+    for (int n = 240; n >= 16; n -= 16)
+        if (P % n == 0) return n;
+    return 0;
+}
+
+// C[b][p][q] = <f1[b,:,p], f2[b,:,q]> / 16 on the tensor cores (D = 256): the conv_umma kernel run as a 1x1 "conv"
+// whose weights are the second feature map of the same sample (b_batched).
+int run_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int h, int w, float* level0, const VolumeWs& v,
+                       cudaStream_t s) {
+    const int P = h * w;
+    const int nt = volume_ntile(P);
+    int rc;
+    if ((rc = b2p_fmap_to_pxc_half(fmap1, B, 256, P, v.fm_h[0], v.fm_h[1], s))) return rc;
+    if ((rc = b2p_fmap_to_pxc_half(fmap2, B, 256, P, v.fm_h[2], v.fm_h[3], s))) return rc;
+    B2P_CUDA(cudaMemsetAsync(v.zero_bias, 0, ((size_t)P + 64) * sizeof(float), s));
+    UmmaConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.seg_hi[0] = v.fm_h[0]; a.seg_lo[0] = v.fm_h[1]; a.seg_c[0] = 256; a.seg_pitch[0] = 256;
+    a.w_hi = v.fm_h[2]; a.w_lo = v.fm_h[3]; a.bias = v.zero_bias; a.b_batched = B;
+    a.cin_pad = 256; a.cout_pad = P; a.cout = P; a.n_tile = nt; a.kh = 1; a.kw = 1;
+    a.B = B; a.h = h; a.w = w; a.epi = EPI_SCALE; a.scale = 0.0625f;     // 1/sqrt(256), exact
+    a.out_f32 = level0; a.out_f32_pitch = P;
+    return b2p_launch_conv_umma(a, s);
+}
+
 struct RefineWs {
     float *pyr, *net, *xbuf, *corr, *coords1, *flow, *mask, *target, *weight;
     void* lm;
+    VolumeWs vol;
     UpdateWs u;
 };
 
@@ -154,6 +210,7 @@ size_t refine_ws_layout(int B, int H, int W, void* ws, size_t cap, RefineWs* out
     r.weight = c.take<float>(N);
     r.lm = c.take<char>(b2p_lm_ws_bytes(B, H, W));
     c.off = align_up(c.off, 1024);
+    c.off += volume_ws_layout(B, h, w, ws ? c.base + c.off : nullptr, 0, &r.vol);
     const size_t used = update_ws_layout(B, h, w, ws ? c.base + c.off : nullptr, cap > c.off ? cap - c.off : 0, &r.u);
     if (out) *out = r;
     return c.off + used;
@@ -200,17 +257,23 @@ int b200pose_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, 
     if (!fmap1 || !fmap2 || !pyramid) return B200POSE_E_NULL;
     if (B < 1 || D < 1 || (h >> 3) < 2 || (w >> 3) < 2) return B200POSE_E_SHAPE;
     cudaStream_t s = (cudaStream_t)stream;
-    const int P = h * w;
     int rc;
-    if ((rc = b2p_corr_volume(fmap1, fmap2, B, D, P, pyramid, s))) return rc;
-    float* src = pyramid;
-    int hl = h, wl = w;
-    for (int l = 1; l < B200POSE_CORR_LEVELS; ++l) {
-        float* dst = src + (size_t)B * P * hl * wl;
-        if ((rc = b2p_corr_pool(src, B * P, hl, wl, dst, s))) return rc;
-        src = dst; hl >>= 1; wl >>= 1;
-    }
-    return 0;
+    if ((rc = b2p_corr_volume(fmap1, fmap2, B, D, h * w, pyramid, s))) return rc;
+    return pool_pyramid(pyramid, B, h, w, s);
+}
+
+size_t b200pose_corr_pyramid_tc_workspace_bytes(int B, int h, int w) { return volume_ws_layout(B, h, w, nullptr, 0, nullptr); }
+
+int b200pose_corr_pyramid_tc(const float* fmap1, const float* fmap2, int B, int h, int w, float* pyramid, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+    if (!fmap1 || !fmap2 || !pyramid || !workspace) return B200POSE_E_NULL;
+    if (B < 1 || (h >> 3) < 2 || (w >> 3) < 2 || volume_ntile(h * w) == 0) return B200POSE_E_SHAPE;
+    if (((uintptr_t)workspace & 1023) || workspace_bytes < b200pose_corr_pyramid_tc_workspace_bytes(B, h, w)) return B200POSE_E_WORKSPACE;
+    VolumeWs v;
+    volume_ws_layout(B, h, w, workspace, workspace_bytes, &v);
+    int rc;
+    if ((rc = run_corr_volume_tc(fmap1, fmap2, B, h, w, pyramid, v, (cudaStream_t)stream))) return rc;
+    return pool_pyramid(pyramid, B, h, w, (cudaStream_t)stream);
 }
 
 int b200pose_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, void* stream) {
@@ -365,7 +428,10 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
     int rc;
     // update_corr_fn == True part (CFNet.py:115-133): pyramid + hidden-state reset, once per render iteration
     if ((rc = b2p_lm_reset(r.lm, B, H, W, s))) return rc;
-    if ((rc = b200pose_corr_pyramid(fmap1, fmap2, B, 256, h, w, r.pyr, stream))) return rc;
+    if (tc && volume_ntile(h * w) > 0) {
+        if ((rc = run_corr_volume_tc(fmap1, fmap2, B, h, w, r.pyr, r.vol, s))) return rc;
+        if ((rc = pool_pyramid(r.pyr, B, h, w, s))) return rc;
+    } else if ((rc = b200pose_corr_pyramid(fmap1, fmap2, B, 256, h, w, r.pyr, stream))) return rc;
     if (tc) rc = b2p_context_init(context, B, H, W, r.net, nullptr, u.net_h[0], u.net_h[1], u.x_h[0], u.x_h[1], s);
     else rc = b2p_context_init(context, B, H, W, r.net, r.xbuf, nullptr, nullptr, nullptr, nullptr, s);
     if (rc) return rc;

@@ -122,6 +122,7 @@ int b2p_split_planes(const float* src, int pitch_in, int C, size_t P, __half* hi
 // kernels implemented across the .cu files (host launchers; all return 0 / cudaError_t)
 int b2p_corr_volume(const float* f1, const float* f2, int B, int D, int P, float* level0, cudaStream_t s);
 int b2p_corr_pool(const float* src, int NP, int hs, int ws, float* dst, cudaStream_t s);
+int b2p_fmap_to_pxc_half(const float* f, int B, int D, int P, __half* hi, __half* lo, cudaStream_t s);
 // hi/lo != nullptr: additionally (or instead, when out == nullptr) write fp16 hi/lo planes with the same pitch
 int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, __half* out_hi,
                     __half* out_lo, cudaStream_t s);

@@ -264,16 +264,19 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
                 v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
                 v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
             }
+            // channels of this 32-group that exist: bounded by the layer (cout) and by the tile (n_tile need not be a
+            // multiple of 32, e.g. 240 for the correlation volume)
+            const int lim = min(p.cout - nb, p.n_tile - col0);
             if (p.epi == EPI_SCALE) {
                 float* d = p.out_f32 + pix * p.out_f32_pitch + nb;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    if (nb + j + 3 < p.cout) {
+                    if (j + 3 < lim) {
                         *reinterpret_cast<float4*>(d + j) = make_float4(v[j] * p.scale, v[j + 1] * p.scale, v[j + 2] * p.scale, v[j + 3] * p.scale);
                     } else {
 #pragma unroll
                         for (int t = 0; t < 4; ++t)
-                            if (nb + j + t < p.cout) d[j + t] = v[j + t] * p.scale;
+                            if (j + t < lim) d[j + t] = v[j + t] * p.scale;
                     }
                 }
                 continue;
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
             // fp16 hi/lo planes for the next convolution
             __half* dh = p.out_hi + pix * p.out_h_pitch + oc;
             __half* dl = p.out_lo + pix * p.out_h_pitch + oc;
-            const int cvalid = p.cout - nb;                    // channels of this 32-group that exist
+            const int cvalid = lim;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
                 __align__(16) __half hi8[8];
@@ -391,7 +394,7 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
         if ((rc = make_act_map(&p.a_hi[g], a.seg_hi[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w))) return rc;
         if ((rc = make_act_map(&p.a_lo[g], a.seg_lo[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w))) return rc;
     }
-    const int taps = a.kh * a.kw;
+    const int taps = a.b_batched ? a.b_batched : a.kh * a.kw;     // 3rd weight-map dimension: tap, or sample
     if ((rc = make_wgt_map(&p.b_hi, a.w_hi, a.cin_pad, a.cout_pad, taps, a.n_tile))) return rc;
     if ((rc = make_wgt_map(&p.b_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, a.n_tile))) return rc;
     p.seg0_chunks = (a.seg_c[0] + BKC - 1) / BKC;

@@ -23,6 +23,26 @@ __global__ void corr_pool_kernel(const float* __restrict__ src, int hs, int ws, 
     dst[i] = sum * 0.25f;
 }
 
+// NCHW feature map [B][D][P] -> PXC fp16 hi/lo planes [B*P][D] (operands of the tensor-core correlation GEMM).
+__global__ void __launch_bounds__(256) fmap_to_pxc_half_kernel(const float* __restrict__ f, int D, int P,
+                                                               __half* __restrict__ hi, __half* __restrict__ lo) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int dd = ty; dd < 32; dd += 8) {
+        const int p = p0 + tx, d = d0 + dd;
+        tile[dd][tx] = (p < P && d < D) ? __ldg(f + ((size_t)b * D + d) * P + p) : 0.f;
+    }
+    __syncthreads();
+    for (int pp = ty; pp < 32; pp += 8) {
+        const int p = p0 + pp, d = d0 + tx;
+        if (p < P && d < D) {
+            const size_t o = ((size_t)b * P + p) * D + d;
+            b2p_split_half(tile[tx][pp], hi[o], lo[o]);
+        }
+    }
+}
+
 // One warp per low-resolution pixel; each lane produces ~10 of the 324 samples.
 // Output channel l*81 + i*9 + j samples (cx/2^l + i - 4, cy/2^l + j - 4): the slow window index moves x
 // (reference corr.py:44-50 stacks meshgrid(dy,dx) into the (x,y) slots).
@@ -173,6 +193,13 @@ __global__ void __launch_bounds__(256) flow_init_kernel(const float* __restrict_
 }
 
 }  // namespace
+
+int b2p_fmap_to_pxc_half(const float* f, int B, int D, int P, __half* hi, __half* lo, cudaStream_t s) {
+    dim3 grid(ceil_div(P, 32), ceil_div(D, 32), B);
+    fmap_to_pxc_half_kernel<<<grid, 256, 0, s>>>(f, D, P, hi, lo);
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
 
 int b2p_corr_pool(const float* src, int NP, int hs, int ws, float* dst, cudaStream_t s) {
     const int hd = hs / 2, wd = ws / 2;

@@ -86,6 +86,21 @@ def corr_pyramid(fmap1: torch.Tensor, fmap2: torch.Tensor) -> torch.Tensor:
     return pyr
 
 
+def corr_pyramid_tc(fmap1: torch.Tensor, fmap2: torch.Tensor) -> torch.Tensor:
+    """Tensor-core correlation volume + pyramid (D must be 256)."""
+    _need_cuda()
+    L = _lib.lib()
+    _chk(fmap1, "fmap1"); _chk(fmap2, "fmap2")
+    B, D, h, w = fmap1.shape
+    assert D == 256
+    pyr = torch.empty(L.b200pose_pyramid_floats(B, h, w), dtype=torch.float32, device=fmap1.device)
+    nb = L.b200pose_corr_pyramid_tc_workspace_bytes(B, h, w)
+    ws = _ws(nb, fmap1.device)
+    _lib.check(L.b200pose_corr_pyramid_tc(fmap1.data_ptr(), fmap2.data_ptr(), B, h, w, pyr.data_ptr(), ws.data_ptr(), nb,
+                                          _stream()), "b200pose_corr_pyramid_tc")
+    return pyr
+
+
 def corr_lookup(pyr: torch.Tensor, coords: torch.Tensor, B: int, h: int, w: int) -> torch.Tensor:
     L = _lib.lib()
     _chk(pyr, "pyramid"); _chk(coords, "coords")

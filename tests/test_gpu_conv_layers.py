@@ -84,3 +84,17 @@ def test_convf1_via_im2col(ops, packed, flags):
     out = ops.conv_layer(packed, 2, colp.to(dev()), None, B, h, w, flags=flags)
     got = from_pxc(out[:, :128].contiguous(), B, h, w).cpu()
     assert (got - ref).abs().max().item() <= (3e-6 if flags == 0 else 4e-5) * ref.abs().max().item() + 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 30, 40), (1, 16, 20), (2, 60, 80)], ids=["30x40", "16x20", "60x80"])
+def test_corr_pyramid_tensor_core_vs_oracle(ops, shape):
+    """All-pairs volume on tcgen05 (fp16 hi/lo) + pooling against the fp32 restatement of CorrBlock.__init__."""
+    from oracle import refine_oracle as O
+    B, h, w = shape
+    f1 = S.hash_features((B, 256, h, w), 1).to(dev()); f2 = S.hash_features((B, 256, h, w), 2).to(dev())
+    lv = ops.pyramid_level_views(ops.corr_pyramid_tc(f1, f2), B, h, w)
+    ref = O.corr_pyramid(f1.cpu(), f2.cpu())
+    for l in range(4):
+        assert lv[l].shape == ref[l].shape
+        err = (lv[l].cpu() - ref[l]).abs().max().item()
+        assert err <= 2e-5 * ref[l].abs().max().item() + 1e-5, (l, err)
