@@ -391,6 +391,9 @@ int b200pose_lm_solve(const float* depth, const float* target, const float* weig
     if (n_steps < 0) return B200POSE_E_ARG;
     if (((uintptr_t)workspace & 255) || workspace_bytes < b2p_lm_ws_bytes(B, H, W)) return B200POSE_E_WORKSPACE;
     { int rc0 = b2p_lm_reset(workspace, B, H, W, (cudaStream_t)stream); if (rc0) return rc0; }
+    if (!H_out && !b_out && !delta_out)      // no taps requested: all steps in one launch
+        return b2p_lm_steps(depth, target, weight, K, G, B, H, W, depth_offset, ep_lmbda, lm_lmbda, n_steps, workspace,
+                            (cudaStream_t)stream);
     for (int i = 0; i < n_steps; ++i) {
         int rc = b2p_lm_step(depth, target, weight, K, G, B, H, W, depth_offset, ep_lmbda, lm_lmbda,
                              H_out ? H_out + (size_t)i * B * 36 : nullptr, b_out ? b_out + (size_t)i * B * 6 : nullptr,
@@ -405,7 +408,8 @@ size_t b200pose_refine_workspace_bytes(int B, int H, int W) { return refine_ws_l
 int b200pose_refine_launch_count(int n_iters, int n_lm) {
     // per render iteration: volume + 3 pools + context;  per recurrent iteration: flow_init, lookup,
     // update block, upsample+weight, 1 launch per LM step (+1 counter reset per call)
-    return 6 + n_iters * (2 + UPDATE_LAUNCHES + 1 + n_lm);
+    // (tensor-core path: counter reset, 2 feature-map transposes, volume GEMM, 3 pools, context = 8 per call)
+    return 8 + n_iters * (2 + UPDATE_LAUNCHES + 1 + (n_lm > 1 ? 1 : n_lm));
 }
 
 int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const float* fmap2, const float* context,
@@ -449,9 +453,7 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
                                       r.weight, s))) return rc;
         if (it == 0 && it == n_iters - 1 && flow_first && flow_last)
             B2P_CUDA(cudaMemcpyAsync(flow_last, flow_first, (size_t)B * 2 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        for (int k = 0; k < n_lm; ++k)
-            if ((rc = b2p_lm_step(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, nullptr, nullptr,
-                                  nullptr, r.lm, s))) return rc;
+        if ((rc = b2p_lm_steps(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, n_lm, r.lm, s))) return rc;
     }
     if (weight_last && n_iters > 0)
         B2P_CUDA(cudaMemcpyAsync(weight_last, r.weight, (size_t)B * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));

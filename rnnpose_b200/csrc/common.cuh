@@ -141,6 +141,8 @@ int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, c
 int b2p_lm_step(const float* depth, const float* target, const float* weight, const float* K, float* G,
                 int B, int H, int W, float depth_add, double ep, double lm, double* H_out, double* b_out,
                 float* delta_out, void* ws, cudaStream_t s);
+int b2p_lm_steps(const float* depth, const float* target, const float* weight, const float* K, float* G,
+                 int B, int H, int W, float depth_add, double ep, double lm, int n_steps, void* ws, cudaStream_t s);
 size_t b2p_lm_ws_bytes(int B, int H, int W);
 int b2p_lm_reset(void* ws, int B, int H, int W, cudaStream_t s);   // once before the first b2p_lm_step on a workspace
 int b2p_pack_weights(const float* const* t, float* packed, cudaStream_t s);   // fp32 section + fp16 hi/lo section

@@ -1,12 +1,17 @@
-// One Levenberg-Marquardt step of the reprojection objective, fully on device:
+// Levenberg-Marquardt steps of the reprojection objective, fully on device:
 //   per-pixel residual + 2x6 SE(3) Jacobian (fp32 geometry, as the reference), fp64 accumulation of
 //   H = sum v w J^T J and b = sum v w J^T r, damping, 6x6 Cholesky solve (NaN -> 0, clamp +-1),
 //   se3 exponential and the left-multiplicative retraction G <- exp(delta) G.
 // reference geometry/transformation.py:265-316 (reprojction_optim), :27-46 (jac_local_perturb),
 //   geometry/projective_ops.py:68-131, geometry/cholesky.py:32-50, geometry/se3.py:228-306.
-// Reduction: registers -> warp shuffles -> shared memory -> per-block partials in global memory; the last
-// block of each sample (ticket counter) sums the partials in a fixed order (deterministic), solves and
-// retracts, so one launch per LM step suffices and nothing returns to the host.
+//
+// Two kernels share the arithmetic:
+//   lm_step_kernel   one step per launch; many small blocks, the last block of each sample (ticket counter) sums the
+//                    per-block partials in a fixed order, solves and retracts.  Provides the H / b / delta taps.
+//   lm_multi_kernel  all n steps in ONE launch: a few fat blocks per sample, all co-resident; after each step the
+//                    blocks of a sample meet at a per-sample spin barrier, every block then reduces the same partials in
+//                    the same order and solves redundantly (bit-identical), so no broadcast and no relaunch is needed.
+// Both reductions are deterministic (no floating-point atomics).
 #include "common.cuh"
 
 namespace {
@@ -15,6 +20,7 @@ constexpr int LM_THREADS = 256;
 constexpr int LM_PX_PER_THREAD = 4;
 constexpr int LM_PX_PER_BLOCK = LM_THREADS * LM_PX_PER_THREAD;
 constexpr int NACC = 27;   // 21 upper-triangular entries of H + 6 of b
+constexpr int LM_MAX_BLK_PER_SAMPLE = 64;
 
 __device__ __forceinline__ int tri_idx(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }
 
@@ -59,96 +65,57 @@ __device__ void se3_exp_f32(const float* xi, float* dG /*12: rows of [R|t]*/) {
     }
 }
 
-__global__ void __launch_bounds__(LM_THREADS) lm_step_kernel(
-    const float* __restrict__ depth, const float* __restrict__ target, const float* __restrict__ weight,
-    const float* __restrict__ K, float* __restrict__ G, int B, int H, int W, float depth_add, double ep, double lm,
-    double* __restrict__ partials, unsigned* __restrict__ counters, int nblk,
-    double* __restrict__ H_out, double* __restrict__ b_out, float* __restrict__ delta_out) {
-    const int b = blockIdx.y;
-    const int tid = threadIdx.x;
-    const int N = H * W;
-    const float* Kb = K + b * 9;
-    const float fx = Kb[0], fy = Kb[4], cx = Kb[2], cy = Kb[5];
-    float Gm[12];
+// Contribution of one pixel to the 27 accumulators.
+__device__ __forceinline__ void lm_pixel(double (&acc)[NACC], int u, int v, float Zraw, float2 tg, float wv, float depth_add,
+                                         float fx, float fy, float cx, float cy, const float (&Gm)[12]) {
+    const float Z = Zraw + depth_add;
+    // A pixel whose weight is exactly 0 adds exactly 0 to H and b (all terms finite): skip its fp64 work.
+    // 65-80 % of a crop is background (weight = ... * (depth > 0)).  Non-finite inputs still take the full path so
+    // that they poison the sums exactly like the reference's arithmetic (NaN -> zero update downstream).
+    if (wv == 0.f && isfinite(Z) && isfinite(tg.x) && isfinite(tg.y)) return;
+    const float X = Z * ((float)u - cx) / fx;
+    const float Y = Z * ((float)v - cy) / fy;
+    const float X1 = Gm[0] * X + Gm[1] * Y + Gm[2] * Z + Gm[3];
+    const float Y1 = Gm[4] * X + Gm[5] * Y + Gm[6] * Z + Gm[7];
+    const float Z1 = Gm[8] * X + Gm[9] * Y + Gm[10] * Z + Gm[11];
+    const double valid = (Z > 0.1f && Z1 > 0.1f) ? 1.0 : 0.0;
+    const float Zc = fmaxf(Z1, 0.01f);
+    const float x1 = fx * (X1 / Zc) + cx;
+    const float y1 = fy * (Y1 / Zc) + cy;
+    const bool cut = Zc <= 0.02f;
+    const float zi1 = cut ? 0.f : 1.0f / Zc;
+    const float zi2 = cut ? 0.f : 1.0f / (Zc * Zc);
+    const double A = (double)(fx * zi1), C = (double)((-fx * X1) * zi2);
+    const double Bq = (double)(fy * zi1), D = (double)((-fy * Y1) * zi2);
+    const double dX = (double)X1, dY = (double)Y1, dZ = (double)Z1;
+    double J0[6], J1[6];
+    J0[0] = A;   J0[1] = 0.0; J0[2] = C; J0[3] = C * dY;              J0[4] = A * dZ + C * (-dX); J0[5] = A * (-dY);
+    J1[0] = 0.0; J1[1] = Bq;  J1[2] = D; J1[3] = Bq * (-dZ) + D * dY; J1[4] = D * (-dX);          J1[5] = Bq * dX;
+    const double r0 = (double)tg.x - (double)x1;
+    const double r1 = (double)tg.y - (double)y1;
+    const double vw = valid * (double)wv;
+    double wJ0[6], wJ1[6];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) Gm[i] = G[b * 16 + i];
-
-    double acc[NACC];
+    for (int i = 0; i < 6; ++i) { wJ0[i] = vw * J0[i]; wJ1[i] = vw * J1[i]; }
+    // J0[1] and J1[0] are structural zeros (jproj rows (fx/Z,0,.) and (0,fy/Z,.)): their products are dropped at
+    // compile time, 30 + 10 FMAs instead of 42 + 12
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
-
-    const float* dptr = depth + (size_t)b * N;
-    const float2* tptr = reinterpret_cast<const float2*>(target) + (size_t)b * N;
-    const float* wptr = weight + (size_t)b * N;
-
-    // all loads of the thread's pixels are issued before any arithmetic (12 independent requests in flight)
-    float Zs[LM_PX_PER_THREAD], ws_[LM_PX_PER_THREAD];
-    float2 tgs[LM_PX_PER_THREAD];
+    for (int i = 0; i < 6; ++i) {
 #pragma unroll
-    for (int it = 0; it < LM_PX_PER_THREAD; ++it) {
-        const int px = blockIdx.x * LM_PX_PER_BLOCK + it * LM_THREADS + tid;
-        const bool in = px < N;
-        Zs[it] = in ? __ldg(dptr + px) : 0.f;
-        tgs[it] = in ? __ldg(tptr + px) : make_float2(0.f, 0.f);
-        ws_[it] = in ? __ldg(wptr + px) : 0.f;
-    }
-#pragma unroll
-    for (int it = 0; it < LM_PX_PER_THREAD; ++it) {
-        const int px = blockIdx.x * LM_PX_PER_BLOCK + it * LM_THREADS + tid;
-        if (px >= N) break;
-        const int v = px / W, u = px - v * W;
-        const float Z = Zs[it] + depth_add;
-        const float2 tg = tgs[it];
-        const float wv = ws_[it];
-        // A pixel whose weight is exactly 0 adds exactly 0 to H and b (all terms finite): skip its ~100 fp64 FMAs.
-        // 65-80 % of a crop is background (weight = ... * (depth > 0)).  Non-finite inputs still take the full path so
-        // that they poison the sums exactly like the reference's arithmetic (NaN -> zero update downstream).
-        if (wv == 0.f && isfinite(Z) && isfinite(tg.x) && isfinite(tg.y)) continue;
-        const float X = Z * ((float)u - cx) / fx;
-        const float Y = Z * ((float)v - cy) / fy;
-        const float X1 = Gm[0] * X + Gm[1] * Y + Gm[2] * Z + Gm[3];
-        const float Y1 = Gm[4] * X + Gm[5] * Y + Gm[6] * Z + Gm[7];
-        const float Z1 = Gm[8] * X + Gm[9] * Y + Gm[10] * Z + Gm[11];
-        const double valid = (Z > 0.1f && Z1 > 0.1f) ? 1.0 : 0.0;
-        const float Zc = fmaxf(Z1, 0.01f);
-        const float x1 = fx * (X1 / Zc) + cx;
-        const float y1 = fy * (Y1 / Zc) + cy;
-        const bool cut = Zc <= 0.02f;
-        const float zi1 = cut ? 0.f : 1.0f / Zc;
-        const float zi2 = cut ? 0.f : 1.0f / (Zc * Zc);
-        const double A = (double)(fx * zi1), C = (double)((-fx * X1) * zi2);
-        const double Bq = (double)(fy * zi1), D = (double)((-fy * Y1) * zi2);
-        const double dX = (double)X1, dY = (double)Y1, dZ = (double)Z1;
-        double J0[6], J1[6];
-        J0[0] = A;   J0[1] = 0.0; J0[2] = C; J0[3] = C * dY;            J0[4] = A * dZ + C * (-dX); J0[5] = A * (-dY);
-        J1[0] = 0.0; J1[1] = Bq;  J1[2] = D; J1[3] = Bq * (-dZ) + D * dY; J1[4] = D * (-dX);          J1[5] = Bq * dX;
-        const double r0 = (double)tg.x - (double)x1;
-        const double r1 = (double)tg.y - (double)y1;
-        const double vw = valid * (double)wv;
-        double wJ0[6], wJ1[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { wJ0[i] = vw * J0[i]; wJ1[i] = vw * J1[i]; }
-        // J0[1] and J1[0] are structural zeros (jproj rows (fx/Z,0,.) and (0,fy/Z,.)): their products are dropped at
-        // compile time, 30 + 10 FMAs instead of 42 + 12
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-#pragma unroll
-            for (int j = i; j < 6; ++j) {
-                const bool u0 = (i != 1) && (j != 1), u1 = (i != 0) && (j != 0);
-                if (u0 && u1) acc[tri_idx(i, j)] += wJ0[i] * J0[j] + wJ1[i] * J1[j];
-                else if (u0) acc[tri_idx(i, j)] += wJ0[i] * J0[j];
-                else if (u1) acc[tri_idx(i, j)] += wJ1[i] * J1[j];
-            }
-            if (i == 0) acc[21 + i] += wJ0[i] * r0;
-            else if (i == 1) acc[21 + i] += wJ1[i] * r1;
-            else acc[21 + i] += wJ0[i] * r0 + wJ1[i] * r1;
+        for (int j = i; j < 6; ++j) {
+            const bool u0 = (i != 1) && (j != 1), u1 = (i != 0) && (j != 0);
+            if (u0 && u1) acc[tri_idx(i, j)] += wJ0[i] * J0[j] + wJ1[i] * J1[j];
+            else if (u0) acc[tri_idx(i, j)] += wJ0[i] * J0[j];
+            else if (u1) acc[tri_idx(i, j)] += wJ1[i] * J1[j];
         }
+        if (i == 0) acc[21 + i] += wJ0[i] * r0;
+        else if (i == 1) acc[21 + i] += wJ1[i] * r1;
+        else acc[21 + i] += wJ0[i] * r0 + wJ1[i] * r1;
     }
+}
 
-    // ---- block reduction (fixed order)
-    __shared__ double red[LM_THREADS / 32][NACC];
-    __shared__ double tot[NACC];
-    __shared__ bool is_last;
+// Block-level fixed-order reduction of the 27 accumulators; result for value i in out[i] (valid for tid < NACC).
+__device__ __forceinline__ void lm_block_reduce(double (&acc)[NACC], double (*red)[NACC], int tid, double& out) {
     const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
     for (int i = 0; i < NACC; ++i) {
@@ -158,31 +125,16 @@ __global__ void __launch_bounds__(LM_THREADS) lm_step_kernel(
         if (lane == 0) red[wid][i] = v;
     }
     __syncthreads();
+    out = 0.0;
     if (tid < NACC) {
-        double s = 0.0;
 #pragma unroll
-        for (int wv = 0; wv < LM_THREADS / 32; ++wv) s += red[wv][tid];
-        partials[((size_t)b * nblk + blockIdx.x) * NACC + tid] = s;
+        for (int wv = 0; wv < LM_THREADS / 32; ++wv) out += red[wv][tid];
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned t = atomicAdd(&counters[b], 1u);
-        is_last = (t == (unsigned)nblk - 1u);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (tid < NACC) {
-        double s = 0.0;
-        const double* pp = partials + (size_t)b * nblk * NACC + tid;
-        for (int k = 0; k < nblk; ++k) s += __ldcg(pp + (size_t)k * NACC);
-        tot[tid] = s;
-    }
-    __syncthreads();
-    if (tid != 0) return;
-    counters[b] = 0;   // self-cleaning for the next step
+}
 
+// Damping, Cholesky solve, NaN -> 0, clamp, exp, retraction.  tot = 21 H entries + 6 b entries (un-damped).
+__device__ void lm_solve_retract(const double* tot, const float (&Gm)[12], float (&Gn)[12], double ep, double lm,
+                                 double* H_out, double* b_out, float* delta_out) {
     double Hm[6][6], bv[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -191,13 +143,12 @@ __global__ void __launch_bounds__(LM_THREADS) lm_step_kernel(
         for (int j = i; j < 6; ++j) { Hm[i][j] = tot[tri_idx(i, j)]; Hm[j][i] = Hm[i][j]; }
     }
     if (H_out)
-        for (int i = 0; i < 36; ++i) H_out[(size_t)b * 36 + i] = Hm[i / 6][i % 6];
+        for (int i = 0; i < 36; ++i) H_out[i] = Hm[i / 6][i % 6];
     if (b_out)
-        for (int i = 0; i < 6; ++i) b_out[(size_t)b * 6 + i] = bv[i];
+        for (int i = 0; i < 6; ++i) b_out[i] = bv[i];
     // damping: H += ep*I + lm*H*I   (transformation.py:300)
 #pragma unroll
     for (int i = 0; i < 6; ++i) Hm[i][i] = Hm[i][i] + (ep + lm * Hm[i][i]);
-    // Cholesky H = L L^T, forward/back substitution (fp64)
     double L[6][6];
     for (int j = 0; j < 6; ++j) {
         double s = Hm[j][j];
@@ -229,10 +180,9 @@ __global__ void __launch_bounds__(LM_THREADS) lm_step_kernel(
         xi[i] = (float)x;
     }
     if (delta_out)
-        for (int i = 0; i < 6; ++i) delta_out[(size_t)b * 6 + i] = xi[i];
+        for (int i = 0; i < 6; ++i) delta_out[i] = xi[i];
     float dG[12];
     se3_exp_f32(xi, dG);
-    float Gn[12];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -241,8 +191,174 @@ __global__ void __launch_bounds__(LM_THREADS) lm_step_kernel(
             if (j == 3) s += dG[i * 4 + 3];       // last row of G is (0,0,0,1)
             Gn[i * 4 + j] = s;
         }
-    for (int i = 0; i < 12; ++i) G[b * 16 + i] = Gn[i];
-    G[b * 16 + 12] = 0.f; G[b * 16 + 13] = 0.f; G[b * 16 + 14] = 0.f; G[b * 16 + 15] = 1.f;
+}
+
+__device__ __forceinline__ void store_G(float* G, const float (&Gn)[12]) {
+    for (int i = 0; i < 12; ++i) G[i] = Gn[i];
+    G[12] = 0.f; G[13] = 0.f; G[14] = 0.f; G[15] = 1.f;
+}
+
+// ------------------------------------------------------------------------------------------------ one step per launch
+__global__ void __launch_bounds__(LM_THREADS) lm_step_kernel(
+    const float* __restrict__ depth, const float* __restrict__ target, const float* __restrict__ weight,
+    const float* __restrict__ K, float* __restrict__ G, int B, int H, int W, float depth_add, double ep, double lm,
+    double* __restrict__ partials, unsigned* __restrict__ counters, int nblk,
+    double* __restrict__ H_out, double* __restrict__ b_out, float* __restrict__ delta_out) {
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int N = H * W;
+    const float* Kb = K + b * 9;
+    const float fx = Kb[0], fy = Kb[4], cx = Kb[2], cy = Kb[5];
+    float Gm[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Gm[i] = G[b * 16 + i];
+
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+    const float* dptr = depth + (size_t)b * N;
+    const float2* tptr = reinterpret_cast<const float2*>(target) + (size_t)b * N;
+    const float* wptr = weight + (size_t)b * N;
+
+    // all loads of the thread's pixels are issued before any arithmetic (12 independent requests in flight)
+    float Zs[LM_PX_PER_THREAD], ws_[LM_PX_PER_THREAD];
+    float2 tgs[LM_PX_PER_THREAD];
+#pragma unroll
+    for (int it = 0; it < LM_PX_PER_THREAD; ++it) {
+        const int px = blockIdx.x * LM_PX_PER_BLOCK + it * LM_THREADS + tid;
+        const bool in = px < N;
+        Zs[it] = in ? __ldg(dptr + px) : 0.f;
+        tgs[it] = in ? __ldg(tptr + px) : make_float2(0.f, 0.f);
+        ws_[it] = in ? __ldg(wptr + px) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < LM_PX_PER_THREAD; ++it) {
+        const int px = blockIdx.x * LM_PX_PER_BLOCK + it * LM_THREADS + tid;
+        if (px < N) lm_pixel(acc, px % W, px / W, Zs[it], tgs[it], ws_[it], depth_add, fx, fy, cx, cy, Gm);
+    }
+
+    __shared__ double red[LM_THREADS / 32][NACC];
+    __shared__ double tot[NACC];
+    __shared__ bool is_last;
+    double mine;
+    lm_block_reduce(acc, red, tid, mine);
+    if (tid < NACC) partials[((size_t)b * nblk + blockIdx.x) * NACC + tid] = mine;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(&counters[b], 1u);
+        is_last = (t == (unsigned)nblk - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tid < NACC) {
+        double s = 0.0;
+        const double* pp = partials + (size_t)b * nblk * NACC + tid;
+        for (int k = 0; k < nblk; ++k) s += __ldcg(pp + (size_t)k * NACC);
+        tot[tid] = s;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    counters[b] = 0;   // self-cleaning for the next step
+    float Gn[12];
+    lm_solve_retract(tot, Gm, Gn, ep, lm, H_out ? H_out + (size_t)b * 36 : nullptr, b_out ? b_out + (size_t)b * 6 : nullptr,
+                     delta_out ? delta_out + (size_t)b * 6 : nullptr);
+    store_G(G + b * 16, Gn);
+}
+
+// ------------------------------------------------------------------------------------------------ n steps per launch
+// grid (nb, B) with nb * B blocks ALL co-resident (checked on the host).  counters: [B][2] = {arrivals, finished}.
+__global__ void __launch_bounds__(LM_THREADS) lm_multi_kernel(
+    const float* __restrict__ depth, const float* __restrict__ target, const float* __restrict__ weight,
+    const float* __restrict__ K, float* __restrict__ G, int B, int H, int W, float depth_add, double ep, double lm,
+    int n_steps, double* __restrict__ partials /*[2][B][nb][27]*/, unsigned* __restrict__ counters) {
+    const int b = blockIdx.y, nb = gridDim.x, tid = threadIdx.x;
+    const int N = H * W;
+    const float* Kb = K + b * 9;
+    const float fx = Kb[0], fy = Kb[4], cx = Kb[2], cy = Kb[5];
+    __shared__ double red[LM_THREADS / 32][NACC];
+    __shared__ double tot[NACC];
+    __shared__ float Gs[12];
+    if (tid < 12) Gs[tid] = G[b * 16 + tid];
+    __syncthreads();
+    const float* dptr = depth + (size_t)b * N;
+    const float2* tptr = reinterpret_cast<const float2*>(target) + (size_t)b * N;
+    const float* wptr = weight + (size_t)b * N;
+    // contiguous pixel range of this block
+    const int per = (N + nb - 1) / nb;
+    const int p_begin = blockIdx.x * per, p_end = min(N, p_begin + per);
+    unsigned* arrive = counters + 2 * b;
+    unsigned* finished = counters + 2 * b + 1;
+
+    for (int step = 0; step < n_steps; ++step) {
+        float Gm[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) Gm[i] = Gs[i];
+        double acc[NACC];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+        for (int base = p_begin; base < p_end; base += LM_PX_PER_BLOCK) {
+            float Zs[LM_PX_PER_THREAD], ws_[LM_PX_PER_THREAD];
+            float2 tgs[LM_PX_PER_THREAD];
+#pragma unroll
+            for (int it = 0; it < LM_PX_PER_THREAD; ++it) {
+                const int px = base + it * LM_THREADS + tid;
+                const bool in = px < p_end;
+                Zs[it] = in ? __ldg(dptr + px) : 0.f;
+                tgs[it] = in ? __ldg(tptr + px) : make_float2(0.f, 0.f);
+                ws_[it] = in ? __ldg(wptr + px) : 0.f;
+            }
+#pragma unroll
+            for (int it = 0; it < LM_PX_PER_THREAD; ++it) {
+                const int px = base + it * LM_THREADS + tid;
+                if (px < p_end) lm_pixel(acc, px % W, px / W, Zs[it], tgs[it], ws_[it], depth_add, fx, fy, cx, cy, Gm);
+            }
+        }
+        double mine;
+        lm_block_reduce(acc, red, tid, mine);
+        double* mypart = partials + (((size_t)(step & 1) * B + b) * nb + blockIdx.x) * NACC;
+        if (tid < NACC) mypart[tid] = mine;
+        __threadfence();
+        __syncthreads();
+        // per-sample barrier: arrivals are monotonic over the steps of this launch
+        if (tid == 0) {
+            atomicAdd(arrive, 1u);
+            const unsigned want = (unsigned)(step + 1) * (unsigned)nb;
+            unsigned spins = 0;
+            while (*reinterpret_cast<volatile unsigned*>(arrive) < want) {
+                __nanosleep(32);
+                if (++spins > (1u << 24)) __trap();          // co-residency violated: fail loudly, never hang
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (tid < NACC) {
+            double s = 0.0;
+            const double* pp = partials + ((size_t)(step & 1) * B + b) * nb * NACC + tid;
+            for (int k = 0; k < nb; ++k) s += __ldcg(pp + (size_t)k * NACC);
+            tot[tid] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float Gn[12];
+            lm_solve_retract(tot, Gm, Gn, ep, lm, nullptr, nullptr, nullptr);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) Gs[i] = Gn[i];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (blockIdx.x == 0) {
+            float Gn[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) Gn[i] = Gs[i];
+            store_G(G + b * 16, Gn);
+        }
+        // the last block to finish resets the counters (everybody has passed the final barrier by then)
+        const unsigned f = atomicAdd(finished, 1u);
+        if (f == (unsigned)nb - 1u) { *arrive = 0u; *finished = 0u; __threadfence(); }
+    }
 }
 
 __global__ void zero_u32_kernel(unsigned* p, int n) {
@@ -253,16 +369,20 @@ __global__ void zero_u32_kernel(unsigned* p, int n) {
 }  // namespace
 
 static inline int lm_nblk(int H, int W) { return ceil_div(H * W, LM_PX_PER_BLOCK); }
-
-size_t b2p_lm_ws_bytes(int B, int H, int W) {
-    return align_up((size_t)B * lm_nblk(H, W) * NACC * sizeof(double), 256) + align_up((size_t)B * sizeof(unsigned), 256);
+static inline size_t lm_partials_bytes(int B, int H, int W) {
+    const size_t a = (size_t)B * lm_nblk(H, W) * NACC * sizeof(double);
+    const size_t m = (size_t)2 * B * LM_MAX_BLK_PER_SAMPLE * NACC * sizeof(double);
+    return align_up(a > m ? a : m, 256);
 }
 
-// The per-sample ticket counters must be zero before the first step; every step leaves them zero again.
+size_t b2p_lm_ws_bytes(int B, int H, int W) {
+    return lm_partials_bytes(B, H, W) + align_up((size_t)2 * B * sizeof(unsigned), 256);
+}
+
+// The per-sample counters must be zero before the first use of a workspace; every kernel leaves them zero again.
 int b2p_lm_reset(void* ws, int B, int H, int W, cudaStream_t s) {
-    unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) +
-                                                     align_up((size_t)B * lm_nblk(H, W) * NACC * sizeof(double), 256));
-    zero_u32_kernel<<<ceil_div(B, 256), 256, 0, s>>>(counters, B);
+    unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + lm_partials_bytes(B, H, W));
+    zero_u32_kernel<<<ceil_div(2 * B, 256), 256, 0, s>>>(counters, 2 * B);
     B2P_LAUNCH_CHECK();
     return 0;
 }
@@ -272,11 +392,39 @@ int b2p_lm_step(const float* depth, const float* target, const float* weight, co
                 cudaStream_t s) {
     const int nblk = lm_nblk(H, W);
     double* partials = reinterpret_cast<double*>(ws);
-    unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) +
-                                                     align_up((size_t)B * nblk * NACC * sizeof(double), 256));
+    unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + lm_partials_bytes(B, H, W));
     dim3 grid(nblk, B);
     lm_step_kernel<<<grid, LM_THREADS, 0, s>>>(depth, target, weight, K, G, B, H, W, depth_add, ep, lm, partials, counters, nblk,
                                                H_out, b_out, delta_out);
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+// All n_steps in one launch when the blocks can be co-resident; otherwise n_steps single-step launches.
+int b2p_lm_steps(const float* depth, const float* target, const float* weight, const float* K, float* G, int B, int H,
+                 int W, float depth_add, double ep, double lm, int n_steps, void* ws, cudaStream_t s) {
+    if (n_steps <= 0) return 0;
+    int dev = 0, sms = 0, per_sm = 0;
+    B2P_CUDA(cudaGetDevice(&dev));
+    B2P_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    B2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_multi_kernel, LM_THREADS, 0));
+    const int capacity = sms * per_sm;
+    int nb = capacity / B;
+    if (nb > LM_MAX_BLK_PER_SAMPLE) nb = LM_MAX_BLK_PER_SAMPLE;
+    const int useful = ceil_div(H * W, LM_PX_PER_BLOCK);
+    if (nb > useful) nb = useful;
+    if (nb < 1 || n_steps == 1) {
+        for (int i = 0; i < n_steps; ++i) {
+            int rc = b2p_lm_step(depth, target, weight, K, G, B, H, W, depth_add, ep, lm, nullptr, nullptr, nullptr, ws, s);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    double* partials = reinterpret_cast<double*>(ws);
+    unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + lm_partials_bytes(B, H, W));
+    dim3 grid(nb, B);
+    lm_multi_kernel<<<grid, LM_THREADS, 0, s>>>(depth, target, weight, K, G, B, H, W, depth_add, ep, lm, n_steps, partials,
+                                                counters);
     B2P_LAUNCH_CHECK();
     return 0;
 }
