@@ -377,7 +377,7 @@ int b200pose_upsample_weight(const float* flow, const float* mask, const float* 
     if (!flow || !mask) return B200POSE_E_NULL;
     if (weight && (!geofea1 || !geofea2 || !depth)) return B200POSE_E_NULL;
     if (B < 1 || H < 8 || W < 8 || (H % 8) || (W % 8) || (weight && C < 1)) return B200POSE_E_SHAPE;
-    return b2p_upsample_weight(flow, mask, geofea1, geofea2, depth, sigma, B, C, H, W, flow_up, target, weight,
+    return b2p_upsample_weight(flow, mask, geofea1, geofea2, depth, sigma, B, C, H, W, flow_up, target, weight, 0,
                                (cudaStream_t)stream);
 }
 
@@ -450,7 +450,7 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
         }
         float* fu = (it == 0 && flow_first) ? flow_first : ((it == n_iters - 1) ? flow_last : nullptr);
         if ((rc = b2p_upsample_weight(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, fu, r.target,
-                                      r.weight, s))) return rc;
+                                      r.weight, 1, s))) return rc;
         if (it == 0 && it == n_iters - 1 && flow_first && flow_last)
             B2P_CUDA(cudaMemcpyAsync(flow_last, flow_first, (size_t)B * 2 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
         if ((rc = b2p_lm_steps(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, n_lm, r.lm, s))) return rc;

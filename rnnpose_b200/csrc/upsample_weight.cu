@@ -12,7 +12,7 @@ namespace {
 __global__ void __launch_bounds__(256) upsample_weight_kernel(
     const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1,
     const float* __restrict__ g2, const float* __restrict__ depth, float sigma, int B, int C, int H, int W,
-    float* __restrict__ flow_up, float* __restrict__ target, float* __restrict__ weight) {
+    float* __restrict__ flow_up, float* __restrict__ target, float* __restrict__ weight, int lazy_background) {
     const int h = H >> 3, w = W >> 3;
     const size_t N = (size_t)H * W;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -22,6 +22,15 @@ __global__ void __launch_bounds__(256) upsample_weight_kernel(
     const int Y = r / W, X = r - Y * W;
     const int y = Y >> 3, i = Y & 7, x = X >> 3, j = X & 7;
     const size_t p = ((size_t)b * h + y) * w + x;
+
+    // Fused-loop shortcut: a background pixel (syn_depth <= 0) has weight exactly 0, so the LM step ignores its target
+    // (any finite value contributes 0 * finite = 0, as in the reference).  When the up-sampled flow itself is not an
+    // output of this iteration, skip the mask softmax and the descriptor warp for it.
+    if (lazy_background && !flow_up && depth[idx] <= 0.f) {
+        if (target) *reinterpret_cast<float2*>(target + idx * 2) = make_float2((float)X, (float)Y);
+        if (weight) weight[idx] = 0.f;
+        return;
+    }
 
     // softmax over the 9 taps of mask[p][k*64 + i*8 + j]
     const float* mp = mask + p * 576 + i * 8 + j;
@@ -73,6 +82,7 @@ __global__ void __launch_bounds__(256) upsample_weight_kernel(
         float s = 0.f;
         const float* g1p = g1 + (size_t)b * C * N + r;
         const float* g2p = g2 + (size_t)b * C * N;
+#pragma unroll 8
         for (int c = 0; c < C; ++c) {
             const float* pl = g2p + (size_t)c * N;
             float v = 0.f;
@@ -93,10 +103,10 @@ __global__ void __launch_bounds__(256) upsample_weight_kernel(
 
 int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth,
                         float sigma, int B, int C, int H, int W, float* flow_up, float* target, float* weight,
-                        cudaStream_t s) {
+                        int lazy_background, cudaStream_t s) {
     const size_t total = (size_t)B * H * W;
     upsample_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(flow, mask, g1, g2, depth, sigma, B, C, H, W,
-                                                                           flow_up, target, weight);
+                                                                           flow_up, target, weight, lazy_background);
     B2P_LAUNCH_CHECK();
     return 0;
 }
