@@ -510,13 +510,26 @@ int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_ho
     const size_t f = sizeof(float);
     B2P_CUDA(cudaMemcpyAsync(hs.fmap1, fmap1_host, (size_t)B * 256 * h * w * f, cudaMemcpyHostToDevice, s));
     B2P_CUDA(cudaMemcpyAsync(hs.fmap2, fmap2_host, (size_t)B * 256 * h * w * f, cudaMemcpyHostToDevice, s));
-    B2P_CUDA(cudaMemcpyAsync(hs.context, context_host, (size_t)B * 256 * H * W * f, cudaMemcpyHostToDevice, s));
+    // The loop only ever touches the context map at the 4 texels around each 1/8-resolution sample (CFNet.py:129), i.e.
+    // ~2 of every 8 rows.  When the caller's buffer is pinned (device-accessible through UVA) the context-init kernel
+    // reads those rows straight from host memory over PCIe instead of first copying all B*256*H*W floats.
+    const float* ctx_dev = hs.context;
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, context_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            attr.devicePointer != nullptr) {
+            ctx_dev = reinterpret_cast<const float*>(attr.devicePointer);
+        } else {
+            (void)cudaGetLastError();
+            B2P_CUDA(cudaMemcpyAsync(hs.context, context_host, (size_t)B * 256 * H * W * f, cudaMemcpyHostToDevice, s));
+        }
+    }
     B2P_CUDA(cudaMemcpyAsync(hs.geo1, geofea1_host, (size_t)B * C_geo * H * W * f, cudaMemcpyHostToDevice, s));
     B2P_CUDA(cudaMemcpyAsync(hs.geo2, geofea2_host, (size_t)B * C_geo * H * W * f, cudaMemcpyHostToDevice, s));
     B2P_CUDA(cudaMemcpyAsync(hs.depth, depth_host, (size_t)B * H * W * f, cudaMemcpyHostToDevice, s));
     B2P_CUDA(cudaMemcpyAsync(hs.K, K_host, (size_t)B * 9 * f, cudaMemcpyHostToDevice, s));
     B2P_CUDA(cudaMemcpyAsync(hs.G, G_host, (size_t)B * 16 * f, cudaMemcpyHostToDevice, s));
-    int rc = b200pose_refine_iters(packed_weights, hs.fmap1, hs.fmap2, hs.context, hs.geo1, hs.geo2, hs.depth, hs.K, hs.G,
+    int rc = b200pose_refine_iters(packed_weights, hs.fmap1, hs.fmap2, ctx_dev, hs.geo1, hs.geo2, hs.depth, hs.K, hs.G,
                                    sigma, B, C_geo, H, W, n_iters, n_lm, ep_lmbda, lm_lmbda, flags, nullptr, nullptr, nullptr,
                                    hs.ws, hs.ws_bytes, stream);
     if (rc) return rc;
