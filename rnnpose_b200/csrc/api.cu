@@ -21,6 +21,8 @@ struct Carver {
 // ([0] = hi, [1] = lo) serve the tensor-core path.
 struct UpdateWs {
     float *col, *c1, *corflo, *f1o, *zbuf, *rhbuf, *hm;
+    float* pre[4];            // GRU partial sums of the iteration-invariant `inp` channels: zr1 [P][256], q1 [P][128], zr2, q2
+    float* zero_bias;         // 1024 zeros
     __half *corr_h[2], *col_h[2], *c1_h[2], *corflo_h[2], *f1o_h[2], *x_h[2], *net_h[2], *rh_h[2], *hm_h[2];
 };
 
@@ -35,6 +37,9 @@ size_t update_ws_layout(int B, int h, int w, void* ws, size_t cap, UpdateWs* out
     u.zbuf = c.take<float>(P * 128);
     u.rhbuf = c.take<float>(P * 128);
     u.hm = c.take<float>(P * 512);
+    u.pre[0] = c.take<float>(P * 256); u.pre[1] = c.take<float>(P * 128);
+    u.pre[2] = c.take<float>(P * 256); u.pre[3] = c.take<float>(P * 128);
+    u.zero_bias = c.take<float>(1024);
     for (int k = 0; k < 2; ++k) {
         u.corr_h[k] = c.take<__half>(P * B200POSE_CORR_PITCH);
         u.col_h[k] = c.take<__half>(P * 112);
@@ -95,17 +100,22 @@ constexpr int UPDATE_LAUNCHES = 13;
 // ------------------------------------------------------------------------------------------------
 // tensor-core path (tcgen05, fp16 hi/lo operands).  Expects u.corr_h, u.net_h and u.x_h[:, 0:128] filled.
 // ------------------------------------------------------------------------------------------------
+// use_pre: the `inp` channels (chunks 2,3 of the 384-wide GRU input [h | inp | motion]) do not change between the
+// recurrent iterations of one render iteration (CFNet.py:124-133 computes inp once): their contribution to the six GRU
+// convolutions is computed once (run_gru_precompute) and added in the epilogue, so the per-iteration GEMMs skip 1/3 of K.
 int run_update_block_tc(const float* wts, float* net, float* coords1, float* flow, float* mask, float* dflow_out,
-                        int B, int h, int w, const UpdateWs& u, cudaStream_t s) {
+                        int B, int h, int w, const UpdateWs& u, bool use_pre, cudaStream_t s) {
     const B2PWeightLayout& L = b2p_weight_layout();
     const B2PHalfLayout& HL = b2p_half_layout();
     const __half* hbase = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(wts) + b2p_half_section_offset_bytes());
     int rc;
     auto conv = [&](int id, __half* const* s0, int off0, int c0, int p0, __half* const* s1, int c1n, int p1,
-                    __half* const* dst, int doff, int dpitch, int epi, float scale, float* out_f32, int f32_pitch) -> int {
+                    __half* const* dst, int doff, int dpitch, int epi, float scale, float* out_f32, int f32_pitch,
+                    const float* pre = nullptr, int pre_pitch = 0) -> int {
         const B2PHalfConvDesc& d = HL.cv[id];
         UmmaConvArgs a;
         memset(&a, 0, sizeof(a));
+        if (pre) { a.pre = pre; a.pre_pitch = pre_pitch; a.chunk_mask = 0x33u; }     // chunks {0,1,4,5}: h and motion
         a.seg_hi[0] = s0[0] + off0; a.seg_lo[0] = s0[1] + off0; a.seg_c[0] = c0; a.seg_pitch[0] = p0;
         if (s1) { a.seg_hi[1] = s1[0]; a.seg_lo[1] = s1[1]; a.seg_c[1] = c1n; a.seg_pitch[1] = p1; }
         a.w_hi = hbase + d.hi_off; a.w_lo = hbase + d.lo_off; a.bias = wts + L.cv[id].b_off;
@@ -122,13 +132,39 @@ int run_update_block_tc(const float* wts, float* net, float* coords1, float* flo
     if ((rc = conv(CV_F1, u.col_h, 0, 112, 112, nullptr, 0, 0, u.f1o_h, 0, 128, EPI_RELU, 1.f, nullptr, 0))) return rc;
     if ((rc = conv(CV_F2, u.f1o_h, 0, 128, 128, nullptr, 0, 0, u.corflo_h, 192, 256, EPI_RELU, 1.f, nullptr, 0))) return rc;
     if ((rc = conv(CV_ENC, u.corflo_h, 0, 256, 256, nullptr, 0, 0, u.x_h, 128, 256, EPI_RELU, 1.f, nullptr, 0))) return rc;
-    if ((rc = conv(CV_ZR1, u.net_h, 0, 128, 128, u.x_h, 256, 256, u.rh_h, 0, 128, EPI_GRU_ZR, 1.f, nullptr, 0))) return rc;
-    if ((rc = conv(CV_Q1, u.rh_h, 0, 128, 128, u.x_h, 256, 256, u.net_h, 0, 128, EPI_GRU_Q, 1.f, nullptr, 0))) return rc;
-    if ((rc = conv(CV_ZR2, u.net_h, 0, 128, 128, u.x_h, 256, 256, u.rh_h, 0, 128, EPI_GRU_ZR, 1.f, nullptr, 0))) return rc;
-    if ((rc = conv(CV_Q2, u.rh_h, 0, 128, 128, u.x_h, 256, 256, u.net_h, 0, 128, EPI_GRU_Q, 1.f, nullptr, 0))) return rc;
+    const float* pz1 = use_pre ? u.pre[0] : nullptr; const float* pq1 = use_pre ? u.pre[1] : nullptr;
+    const float* pz2 = use_pre ? u.pre[2] : nullptr; const float* pq2 = use_pre ? u.pre[3] : nullptr;
+    if ((rc = conv(CV_ZR1, u.net_h, 0, 128, 128, u.x_h, 256, 256, u.rh_h, 0, 128, EPI_GRU_ZR, 1.f, nullptr, 0, pz1, 256))) return rc;
+    if ((rc = conv(CV_Q1, u.rh_h, 0, 128, 128, u.x_h, 256, 256, u.net_h, 0, 128, EPI_GRU_Q, 1.f, nullptr, 0, pq1, 128))) return rc;
+    if ((rc = conv(CV_ZR2, u.net_h, 0, 128, 128, u.x_h, 256, 256, u.rh_h, 0, 128, EPI_GRU_ZR, 1.f, nullptr, 0, pz2, 256))) return rc;
+    if ((rc = conv(CV_Q2, u.rh_h, 0, 128, 128, u.x_h, 256, 256, u.net_h, 0, 128, EPI_GRU_Q, 1.f, nullptr, 0, pq2, 128))) return rc;
     if ((rc = conv(CV_HEADS, u.net_h, 0, 128, 128, nullptr, 0, 0, u.hm_h, 0, 512, EPI_RELU, 1.f, nullptr, 0))) return rc;
     if ((rc = b2p_flow_head2(nullptr, u.hm_h[0], u.hm_h[1], wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, B, h, w, s))) return rc;
     if ((rc = conv(CV_MASK2, u.hm_h, 256, 256, 512, nullptr, 0, 0, nullptr, 0, 0, EPI_SCALE, 0.25f, mask, 576))) return rc;
+    return 0;
+}
+
+// GRU partial sums over the `inp` channels only (chunks 2,3), no bias, no activation: pre[k][P][cout] fp32.
+int run_gru_precompute(const float* wts, int B, int h, int w, const UpdateWs& u, cudaStream_t s) {
+    const B2PHalfLayout& HL = b2p_half_layout();
+    const __half* hbase = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(wts) + b2p_half_section_offset_bytes());
+    B2P_CUDA(cudaMemsetAsync(u.zero_bias, 0, 1024 * sizeof(float), s));
+    const int ids[4] = {CV_ZR1, CV_Q1, CV_ZR2, CV_Q2};
+    for (int k = 0; k < 4; ++k) {
+        const B2PHalfConvDesc& d = HL.cv[ids[k]];
+        UmmaConvArgs a;
+        memset(&a, 0, sizeof(a));
+        // segment 0 is only a placeholder here (its chunks 0,1 are masked out); segment 1 = x = [inp | motion]
+        a.seg_hi[0] = u.net_h[0]; a.seg_lo[0] = u.net_h[1]; a.seg_c[0] = 128; a.seg_pitch[0] = 128;
+        a.seg_hi[1] = u.x_h[0]; a.seg_lo[1] = u.x_h[1]; a.seg_c[1] = 256; a.seg_pitch[1] = 256;
+        a.w_hi = hbase + d.hi_off; a.w_lo = hbase + d.lo_off; a.bias = u.zero_bias;
+        a.cin_pad = d.cin_pad; a.cout_pad = d.cout_pad; a.cout = d.cout; a.n_tile = d.n_tile; a.kh = d.kh; a.kw = d.kw;
+        a.B = B; a.h = h; a.w = w; a.epi = EPI_SCALE; a.scale = 1.f;
+        a.out_f32 = u.pre[k]; a.out_f32_pitch = d.cout;
+        a.chunk_mask = 0x0Cu;                                     // chunks {2,3}: the inp channels
+        int rc = b2p_launch_conv_umma(a, s);
+        if (rc) return rc;
+    }
     return 0;
 }
 
@@ -314,7 +350,7 @@ int b200pose_update_block(const void* packed_weights, float* net, float* xbuf, c
     if ((rc = b2p_split_planes(corr, B200POSE_CORR_PITCH, B200POSE_CORR_PITCH, P, u.corr_h[0], u.corr_h[1], B200POSE_CORR_PITCH, s))) return rc;
     if ((rc = b2p_split_planes(net, 128, 128, P, u.net_h[0], u.net_h[1], 128, s))) return rc;
     if ((rc = b2p_split_planes(xbuf, 256, 128, P, u.x_h[0], u.x_h[1], 256, s))) return rc;
-    return run_update_block_tc(wts, net, coords1, flow, mask, dflow_out, B, h, w, u, s);
+    return run_update_block_tc(wts, net, coords1, flow, mask, dflow_out, B, h, w, u, false, s);
 }
 
 size_t b200pose_conv_layer_workspace_bytes(int B, int h, int w) { return (size_t)B * h * w * 384 * 2 * sizeof(__half) + 4096; }
@@ -408,8 +444,9 @@ size_t b200pose_refine_workspace_bytes(int B, int H, int W) { return refine_ws_l
 int b200pose_refine_launch_count(int n_iters, int n_lm) {
     // per render iteration: volume + 3 pools + context;  per recurrent iteration: flow_init, lookup,
     // update block, upsample+weight, 1 launch per LM step (+1 counter reset per call)
-    // (tensor-core path: counter reset, 2 feature-map transposes, volume GEMM, 3 pools, context = 8 per call)
-    return 8 + n_iters * (2 + UPDATE_LAUNCHES + 1 + (n_lm > 1 ? 1 : n_lm));
+    // (tensor-core path: counter reset, 2 feature-map transposes, volume GEMM, 3 pools, context = 8 per call,
+    //  + 4 GRU partial-sum GEMMs when there is more than one recurrent iteration)
+    return 8 + (n_iters > 1 ? 4 : 0) + n_iters * (2 + UPDATE_LAUNCHES + 1 + (n_lm > 1 ? 1 : n_lm));
 }
 
 int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const float* fmap2, const float* context,
@@ -439,11 +476,12 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
     if (tc) rc = b2p_context_init(context, B, H, W, r.net, nullptr, u.net_h[0], u.net_h[1], u.x_h[0], u.x_h[1], s);
     else rc = b2p_context_init(context, B, H, W, r.net, r.xbuf, nullptr, nullptr, nullptr, nullptr, s);
     if (rc) return rc;
+    if (tc && n_iters > 1 && (rc = run_gru_precompute(wts, B, h, w, u, s))) return rc;
     for (int it = 0; it < n_iters; ++it) {
         if ((rc = b2p_flow_init(depth, K, G, B, H, W, r.coords1, r.flow, s))) return rc;
         if (tc) {
             if ((rc = b2p_corr_lookup(r.pyr, r.coords1, B, h, w, nullptr, u.corr_h[0], u.corr_h[1], s))) return rc;
-            if ((rc = run_update_block_tc(wts, r.net, r.coords1, r.flow, r.mask, nullptr, B, h, w, u, s))) return rc;
+            if ((rc = run_update_block_tc(wts, r.net, r.coords1, r.flow, r.mask, nullptr, B, h, w, u, n_iters > 1, s))) return rc;
         } else {
             if ((rc = b2p_corr_lookup(r.pyr, r.coords1, B, h, w, r.corr, nullptr, nullptr, s))) return rc;
             if ((rc = run_update_block(wts, r.net, r.xbuf, r.corr, r.coords1, r.flow, r.mask, nullptr, B, h, w, u, s))) return rc;

@@ -113,6 +113,8 @@ struct UmmaConvArgs {
     float* out_f32; int out_f32_pitch;
     __half* out_hi; __half* out_lo; int out_h_pitch;
     float* zbuf; float* hbuf;
+    unsigned chunk_mask;       // bit cc set = visit 64-channel chunk cc of every tap (0 = all chunks)
+    const float* pre; int pre_pitch;   // fp32 [P][pre_pitch] partial sums added in the epilogue (or nullptr)
     int b_batched;             // weights differ per sample: 3rd weight-map coordinate = sample index (1x1 only)
 };
 int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s);

@@ -34,6 +34,8 @@ struct UmmaConvParams {
     int seg0_chunks, chunks_per_tap, kh, kw;
     int B, h, w, tiles_x, tiles_y;
     int n_tile, cout, stages;
+    int n_active, chunk_list[8];           // channel chunks (of 64) visited per tap; the others are skipped
+    const float* pre; int pre_pitch;        // optional fp32 partial sums added before the activation ([P][pre_pitch])
     int m_tiles, total_tiles, b_batched;   // b_batched: the weight map's 3rd coordinate is the sample index (correlation volume)
     const float* bias;
     int epi; float scale;
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     // persistent CTA: tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; t = n_idx * m_tiles + m_idx so that the
     // CTAs of one round share the weight tile (L2) and walk over different pixel tiles
     const int tiles_per_img = p.tiles_x * p.tiles_y;
-    const int nk = p.kh * p.kw * p.chunks_per_tap;
+    const int nk = p.kh * p.kw * p.n_active;
     auto decode = [&](int t, int& bimg, int& y0, int& x0, int& n0) {
         const int n_idx = t / p.m_tiles, m_idx = t - n_idx * p.m_tiles;
         bimg = m_idx / tiles_per_img;
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
                     const int s = it % p.stages, ph = (it / p.stages) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1);
                     mbar_expect_tx(full_bar(s), stage_bytes);
-                    const int tap = kc / p.chunks_per_tap, cc = kc - tap * p.chunks_per_tap;
+                    const int tap = kc / p.n_active, cc = p.chunk_list[kc - tap * p.n_active];
                     const int ky = tap / p.kw, kx = tap - ky * p.kw;
                     const int seg = cc >= p.seg0_chunks ? 1 : 0;
                     const int c0 = (seg ? cc - p.seg0_chunks : cc) * BKC;
@@ -255,6 +257,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
 #pragma unroll
                 for (int j = 0; j < 8; ++j) zz[j] = __ldg(zp4 + j);
             }
+            float4 pre4[8];
+            if (live && p.pre) {
+                const float4* pp = reinterpret_cast<const float4*>(p.pre + pix * p.pre_pitch + nb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pre4[j] = __ldg(pp + j);
+            }
             tmem_ld_wait(r);
             if (!live) continue;
             float v[32];
@@ -263,6 +271,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
                 v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
                 v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+            }
+            if (p.pre) {                                       // contribution of the iteration-invariant input channels
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    v[4 * j] += pre4[j].x; v[4 * j + 1] += pre4[j].y; v[4 * j + 2] += pre4[j].z; v[4 * j + 3] += pre4[j].w;
+                }
             }
             // channels of this 32-group that exist: bounded by the layer (cout) and by the tile (n_tile need not be a
             // multiple of 32, e.g. 240 for the correlation volume)
@@ -399,6 +413,10 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     if ((rc = make_wgt_map(&p.b_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, a.n_tile))) return rc;
     p.seg0_chunks = (a.seg_c[0] + BKC - 1) / BKC;
     p.chunks_per_tap = a.cin_pad / BKC;
+    p.n_active = 0;
+    for (int cc = 0; cc < p.chunks_per_tap && cc < 8; ++cc)
+        if (a.chunk_mask == 0 || ((a.chunk_mask >> cc) & 1u)) p.chunk_list[p.n_active++] = cc;
+    p.pre = a.pre; p.pre_pitch = a.pre_pitch;
     p.kh = a.kh; p.kw = a.kw; p.B = a.B; p.h = a.h; p.w = a.w;
     p.tiles_x = ceil_div(a.w, TILE_COLS); p.tiles_y = ceil_div(a.h, TILE_ROWS);
     p.n_tile = a.n_tile; p.cout = a.cout;
