@@ -21,7 +21,7 @@
 
 namespace {
 
-constexpr int UM_THREADS = 192;
+constexpr int UM_THREADS = 320;                        // warps: 0 TMA, 1 MMA, 2-9 epilogue (two per TMEM lane quarter)
 constexpr int TILE_ROWS = 16, TILE_COLS = 8;          // 128-pixel M tile
 constexpr int BKC = 64;                                // channels per K chunk (128 B of fp16)
 constexpr int A_TILE_BYTES = 128 * BKC * 2;            // 16 KB
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 128); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         const size_t pix = ((size_t)bimg * p.h + yy) * p.w + xx;
         mbar_wait(tmem_full_bar(buf), (tile_iter >> 1) & 1);
         tc_fence_after();
-        for (int col0 = 0; col0 < p.n_tile; col0 += 32) {
+        // the two warps of a lane quarter take alternate 32-column groups
+        for (int col0 = ((warp - 2) >> 2) * 32; col0 < p.n_tile; col0 += 64) {
             uint32_t r[32];
             tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS + col0), r);
             const int nb = n0 + col0;
