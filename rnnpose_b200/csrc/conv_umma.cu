@@ -66,6 +66,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 26)) __trap();      // a protocol bug must fail the launch, never hang the GPU
     }
 }
+// same, for the long waits of the epilogue warps: back off between polls so that the eight waiting warps do not
+// compete with the single TMA / MMA issuing threads for issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+        if (++spins > (1u << 24)) __trap();
+    }
+}
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -235,7 +251,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         const int yy = y0 + (mrow >> 3), xx = x0 + (mrow & 7);
         const bool valid = yy < p.h && xx < p.w;
         const size_t pix = ((size_t)bimg * p.h + yy) * p.w + xx;
-        mbar_wait(tmem_full_bar(buf), (tile_iter >> 1) & 1);
+        mbar_wait_backoff(tmem_full_bar(buf), (tile_iter >> 1) & 1);
         tc_fence_after();
         // the two warps of a lane quarter take alternate 32-column groups
         for (int col0 = ((warp - 2) >> 2) * 32; col0 < p.n_tile; col0 += 64) {
