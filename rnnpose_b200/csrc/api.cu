@@ -501,23 +501,37 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
 }  // extern "C"
 
 namespace {
-struct HostScratch {
+// Device staging of the host entry.  The batch is processed in sub-batches so that the PCIe transfer of sub-batch
+// k+1 (on an internal copy stream) overlaps the kernels of sub-batch k (on the caller's stream); per-sample results
+// do not depend on how the batch is split (tests/test_gpu_refine.py checks this bit for bit).
+struct HostStage {
     float *fmap1, *fmap2, *context, *geo1, *geo2, *depth, *K, *G;
-    void* ws; size_t ws_bytes;
 };
-size_t host_scratch_layout(int B, int C, int H, int W, void* p, size_t cap, HostScratch* out) {
+struct HostScratch {
+    HostStage st[2];          // ping-pong input staging for sub-batches
+    void* ws; size_t ws_bytes;
+    int bs;                   // samples per sub-batch
+};
+inline int host_sub_batch(int B) { return B >= 8 ? (B + 3) / 4 : (B >= 2 ? (B + 1) / 2 : 1); }
+
+size_t host_scratch_layout(int B, int C, int H, int W, bool stage_context, void* p, size_t cap, HostScratch* out) {
     const int h = H / 8, w = W / 8;
+    const int bs = host_sub_batch(B);
     Carver c(p, cap);
     HostScratch hs;
-    hs.fmap1 = c.take<float>((size_t)B * 256 * h * w);
-    hs.fmap2 = c.take<float>((size_t)B * 256 * h * w);
-    hs.context = c.take<float>((size_t)B * 256 * H * W);
-    hs.geo1 = c.take<float>((size_t)B * C * H * W);
-    hs.geo2 = c.take<float>((size_t)B * C * H * W);
-    hs.depth = c.take<float>((size_t)B * H * W);
-    hs.K = c.take<float>((size_t)B * 9);
-    hs.G = c.take<float>((size_t)B * 16);
-    hs.ws_bytes = refine_ws_layout(B, H, W, nullptr, 0, nullptr);
+    hs.bs = bs;
+    for (int k = 0; k < 2; ++k) {
+        HostStage& st = hs.st[k];
+        st.fmap1 = c.take<float>((size_t)bs * 256 * h * w);
+        st.fmap2 = c.take<float>((size_t)bs * 256 * h * w);
+        st.context = stage_context ? c.take<float>((size_t)bs * 256 * H * W) : nullptr;
+        st.geo1 = c.take<float>((size_t)bs * C * H * W);
+        st.geo2 = c.take<float>((size_t)bs * C * H * W);
+        st.depth = c.take<float>((size_t)bs * H * W);
+        st.K = c.take<float>((size_t)bs * 9);
+        st.G = c.take<float>((size_t)bs * 16);
+    }
+    hs.ws_bytes = refine_ws_layout(bs, H, W, nullptr, 0, nullptr);
     hs.ws = c.take<char>(hs.ws_bytes);
     if (out) *out = hs;
     return align_up(c.off, 1024);
@@ -527,7 +541,7 @@ size_t host_scratch_layout(int B, int C, int H, int W, void* p, size_t cap, Host
 extern "C" {
 
 size_t b200pose_refine_host_scratch_bytes(int B, int C_geo, int H, int W) {
-    return host_scratch_layout(B, C_geo, H, W, nullptr, 0, nullptr);
+    return host_scratch_layout(B, C_geo, H, W, true, nullptr, 0, nullptr);     // worst case: context staged too
 }
 
 int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_host, const float* fmap2_host,
@@ -542,38 +556,68 @@ int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_ho
     if (((uintptr_t)device_scratch & 1023) || device_scratch_bytes < b200pose_refine_host_scratch_bytes(B, C_geo, H, W))
         return B200POSE_E_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
-    HostScratch hs;
-    host_scratch_layout(B, C_geo, H, W, device_scratch, device_scratch_bytes, &hs);
-    const int h = H / 8, w = W / 8;
-    const size_t f = sizeof(float);
-    B2P_CUDA(cudaMemcpyAsync(hs.fmap1, fmap1_host, (size_t)B * 256 * h * w * f, cudaMemcpyHostToDevice, s));
-    B2P_CUDA(cudaMemcpyAsync(hs.fmap2, fmap2_host, (size_t)B * 256 * h * w * f, cudaMemcpyHostToDevice, s));
+
     // The loop only ever touches the context map at the 4 texels around each 1/8-resolution sample (CFNet.py:129), i.e.
     // ~2 of every 8 rows.  When the caller's buffer is pinned (device-accessible through UVA) the context-init kernel
     // reads those rows straight from host memory over PCIe instead of first copying all B*256*H*W floats.
-    const float* ctx_dev = hs.context;
+    const float* ctx_mapped = nullptr;
     {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, context_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
-            attr.devicePointer != nullptr) {
-            ctx_dev = reinterpret_cast<const float*>(attr.devicePointer);
-        } else {
+            attr.devicePointer != nullptr)
+            ctx_mapped = reinterpret_cast<const float*>(attr.devicePointer);
+        else
             (void)cudaGetLastError();
-            B2P_CUDA(cudaMemcpyAsync(hs.context, context_host, (size_t)B * 256 * H * W * f, cudaMemcpyHostToDevice, s));
-        }
     }
-    B2P_CUDA(cudaMemcpyAsync(hs.geo1, geofea1_host, (size_t)B * C_geo * H * W * f, cudaMemcpyHostToDevice, s));
-    B2P_CUDA(cudaMemcpyAsync(hs.geo2, geofea2_host, (size_t)B * C_geo * H * W * f, cudaMemcpyHostToDevice, s));
-    B2P_CUDA(cudaMemcpyAsync(hs.depth, depth_host, (size_t)B * H * W * f, cudaMemcpyHostToDevice, s));
-    B2P_CUDA(cudaMemcpyAsync(hs.K, K_host, (size_t)B * 9 * f, cudaMemcpyHostToDevice, s));
-    B2P_CUDA(cudaMemcpyAsync(hs.G, G_host, (size_t)B * 16 * f, cudaMemcpyHostToDevice, s));
-    int rc = b200pose_refine_iters(packed_weights, hs.fmap1, hs.fmap2, ctx_dev, hs.geo1, hs.geo2, hs.depth, hs.K, hs.G,
-                                   sigma, B, C_geo, H, W, n_iters, n_lm, ep_lmbda, lm_lmbda, flags, nullptr, nullptr, nullptr,
-                                   hs.ws, hs.ws_bytes, stream);
-    if (rc) return rc;
-    B2P_CUDA(cudaMemcpyAsync(G_host, hs.G, (size_t)B * 16 * f, cudaMemcpyDeviceToHost, s));
-    B2P_CUDA(cudaStreamSynchronize(s));
-    return 0;
+    HostScratch hs;
+    host_scratch_layout(B, C_geo, H, W, ctx_mapped == nullptr, device_scratch, device_scratch_bytes, &hs);
+    const int h = H / 8, w = W / 8, bs = hs.bs;
+    const int nsub = (B + bs - 1) / bs;
+    const size_t f = sizeof(float);
+
+    cudaStream_t cs = nullptr;                     // internal copy stream + events, created and destroyed per call
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_start = nullptr;
+    int rc = 0;
+#define B2P_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = (int)e__; goto cleanup; } } while (0)
+    B2P_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    B2P_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) {
+        B2P_TRY(cudaEventCreateWithFlags(&ev_copy[k], cudaEventDisableTiming));
+        B2P_TRY(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+    }
+    B2P_TRY(cudaEventRecord(ev_start, s));          // the copy stream starts after the caller's prior work
+    B2P_TRY(cudaStreamWaitEvent(cs, ev_start, 0));
+    for (int k = 0; k < nsub; ++k) {
+        const int b0 = k * bs, nb = (B - b0 < bs) ? (B - b0) : bs;
+        const HostStage& st = hs.st[k & 1];
+        if (k >= 2) B2P_TRY(cudaStreamWaitEvent(cs, ev_done[k & 1], 0));        // staging buffer free again
+        B2P_TRY(cudaMemcpyAsync(st.fmap1, fmap1_host + (size_t)b0 * 256 * h * w, (size_t)nb * 256 * h * w * f, cudaMemcpyHostToDevice, cs));
+        B2P_TRY(cudaMemcpyAsync(st.fmap2, fmap2_host + (size_t)b0 * 256 * h * w, (size_t)nb * 256 * h * w * f, cudaMemcpyHostToDevice, cs));
+        if (!ctx_mapped)
+            B2P_TRY(cudaMemcpyAsync(st.context, context_host + (size_t)b0 * 256 * H * W, (size_t)nb * 256 * H * W * f, cudaMemcpyHostToDevice, cs));
+        B2P_TRY(cudaMemcpyAsync(st.geo1, geofea1_host + (size_t)b0 * C_geo * H * W, (size_t)nb * C_geo * H * W * f, cudaMemcpyHostToDevice, cs));
+        B2P_TRY(cudaMemcpyAsync(st.geo2, geofea2_host + (size_t)b0 * C_geo * H * W, (size_t)nb * C_geo * H * W * f, cudaMemcpyHostToDevice, cs));
+        B2P_TRY(cudaMemcpyAsync(st.depth, depth_host + (size_t)b0 * H * W, (size_t)nb * H * W * f, cudaMemcpyHostToDevice, cs));
+        B2P_TRY(cudaMemcpyAsync(st.K, K_host + (size_t)b0 * 9, (size_t)nb * 9 * f, cudaMemcpyHostToDevice, cs));
+        B2P_TRY(cudaMemcpyAsync(st.G, G_host + (size_t)b0 * 16, (size_t)nb * 16 * f, cudaMemcpyHostToDevice, cs));
+        B2P_TRY(cudaEventRecord(ev_copy[k & 1], cs));
+        B2P_TRY(cudaStreamWaitEvent(s, ev_copy[k & 1], 0));
+        const float* ctx = ctx_mapped ? ctx_mapped + (size_t)b0 * 256 * H * W : st.context;
+        rc = b200pose_refine_iters(packed_weights, st.fmap1, st.fmap2, ctx, st.geo1, st.geo2, st.depth, st.K, st.G, sigma, nb,
+                                   C_geo, H, W, n_iters, n_lm, ep_lmbda, lm_lmbda, flags, nullptr, nullptr, nullptr, hs.ws,
+                                   hs.ws_bytes, stream);
+        if (rc) goto cleanup;
+        B2P_TRY(cudaMemcpyAsync(G_host + (size_t)b0 * 16, st.G, (size_t)nb * 16 * f, cudaMemcpyDeviceToHost, s));
+        B2P_TRY(cudaEventRecord(ev_done[k & 1], s));
+    }
+    B2P_TRY(cudaStreamSynchronize(s));
+cleanup:
+#undef B2P_TRY
+    if (rc) { if (cs) cudaStreamSynchronize(cs); cudaStreamSynchronize(s); }
+    for (int k = 0; k < 2; ++k) { if (ev_copy[k]) cudaEventDestroy(ev_copy[k]); if (ev_done[k]) cudaEventDestroy(ev_done[k]); }
+    if (ev_start) cudaEventDestroy(ev_start);
+    if (cs) cudaStreamDestroy(cs);
+    return rc;
 }
 
 }  // extern "C"
