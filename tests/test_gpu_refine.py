@@ -135,3 +135,18 @@ def test_error_codes(ops, packed):
     f = S.hash_features((1, 256, 8, 8), 1)
     with pytest.raises(RuntimeError, match="unsupported shape"):
         run_gpu(ops, packed, f, f, mb, torch.eye(4)[None], 1, 1)
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["fp32", "tcgen05"])
+def test_refine_high_res_480x640_vs_oracle(ops, packed, flags):
+    """BASELINE configs[4] shape (480x640 crops, 4 pyramid levels: 60x80, 30x40, 15x20, 7x10) against the oracle."""
+    H, W = 480, 640
+    mb = S.make_batch([21], H, W, with_images=False)
+    f1 = S.hash_features((1, 256, H // 8, W // 8), 91); f2 = S.hash_features((1, 256, H // 8, W // 8), 92)
+    G0 = torch.eye(4)[None]
+    ref = O.refine_inner_loop(load_update_weights(), f1, f2, mb["context"], mb["geofea1"], mb["geofea2"], mb["depth"],
+                              mb["K"], G0, n_iters=2, n_lm=2)
+    res = run_gpu(ops, packed, f1, f2, mb, G0, 2, 2, flags=flags)
+    err = (res["G"].cpu() - ref["G"]).abs().max().item()
+    print(f"[parity] 480x640 flags={flags}: max |dSE3| vs oracle = {err:.3e}")
+    assert err < SE3_TOL
