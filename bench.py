@@ -38,6 +38,7 @@ import torch  # noqa: E402
 H, W, B_PER_GPU, N_ITERS, N_LM = 240, 320, 32, 4, 3
 UNIQUE_SCENES = 8            # distinct synthetic scenes per rank, tiled to the batch
 FLOP_PER_LOWRES_PX = 6236672  # update-block convolutions, SURVEY.md Appendix A.2
+NCU_TRAFFIC_BYTES_PER_PASS = 769_000_000   # profiles/r1_final_summary.md (644 MB read + 125 MB written)
 WORKLOAD = f"synthetic {H}x{W} crops, batch {B_PER_GPU}/GPU, {N_ITERS} recurrent iters x {N_LM} LM steps"
 
 
@@ -303,7 +304,10 @@ def main():
     achieved = flops / (ub_ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": f"{peak_src} (bf16 dense, sustained)",
+                "traffic": NCU_TRAFFIC_BYTES_PER_PASS if not args.exact_fp32 else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum over the 11 conv launches of one pass, "
+                                  "profiles/r1_final_conv_umma_ncu_raw.csv (B=32, 240x320; ncu flushes caches per launch)",
+                "peak_source": f"{peak_src} (bf16 dense, sustained)",
                 "kernel": conv_kernel + ": the 11 convolution launches of one update-block pass, timed back to back "
                           "(incl. the im2col / flow-head / operand-split helper launches, <3% of the pass)",
                 "algorithmic_flops_per_pass": flops, "ms_per_pass": ub_ms,
