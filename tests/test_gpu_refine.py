@@ -150,3 +150,31 @@ def test_refine_high_res_480x640_vs_oracle(ops, packed, flags):
     err = (res["G"].cpu() - ref["G"]).abs().max().item()
     print(f"[parity] 480x640 flags={flags}: max |dSE3| vs oracle = {err:.3e}")
     assert err < SE3_TOL
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["fp32", "tcgen05"])
+def test_refine_ragged_size_136x168(ops, packed, flags):
+    """h x w = 17 x 21: pixel tiles hang over the image on both axes, the pyramid pools with floor (17x21 -> 8x10 -> 4x5 ->
+    2x2) and P = 357 has no MMA-sized divisor, so the tensor-core path falls back to the fp32 volume kernel."""
+    H, W = 136, 168
+    mb = S.make_batch([31, 32], H, W, with_images=False)
+    f1 = S.hash_features((2, 256, H // 8, W // 8), 93); f2 = S.hash_features((2, 256, H // 8, W // 8), 94)
+    G0 = torch.eye(4)[None].repeat(2, 1, 1)
+    ref = O.refine_inner_loop(load_update_weights(), f1, f2, mb["context"], mb["geofea1"], mb["geofea2"], mb["depth"],
+                              mb["K"], G0, n_iters=3, n_lm=2)
+    res = run_gpu(ops, packed, f1, f2, mb, G0, 3, 2, flags=flags, want_flows=True)
+    err = (res["G"].cpu() - ref["G"]).abs().max().item()
+    print(f"[parity] 136x168 flags={flags}: max |dSE3| vs oracle = {err:.3e}")
+    assert err < SE3_TOL
+    torch.testing.assert_close(res["flow_last"].cpu(), ref["flows"][-1], rtol=1e-3, atol=2e-2)
+
+
+def test_refine_zero_iterations_and_single_object(ops, packed):
+    """n_iters = 0 leaves the pose untouched; B = 1, one iteration, zero LM steps runs the flow net only."""
+    H, W = 128, 160
+    mb = S.make_batch([33], H, W, with_images=False)
+    f = S.hash_features((1, 256, H // 8, W // 8), 95)
+    G0 = O.se3_exp(torch.tensor([[0.01, 0.0, 0.02, 0.0, 0.03, 0.0]]))
+    assert torch.equal(run_gpu(ops, packed, f, f, mb, G0, 0, 3)["G"].cpu(), G0)
+    res = run_gpu(ops, packed, f, f, mb, G0, 1, 0, want_flows=True)
+    assert torch.equal(res["G"].cpu(), G0) and torch.isfinite(res["flow_last"]).all()
