@@ -43,21 +43,16 @@ __global__ void __launch_bounds__(256) fmap_to_pxc_half_kernel(const float* __re
     }
 }
 
-// One warp per low-resolution pixel.  Per level the warp stages the 12x12 texel patch that contains every tap of the
-// 9x9 window (zero outside the map = the sampler's zero padding) in shared memory with row-coalesced loads, then each
-// lane interpolates ~3 of the 81 samples from the patch: 144 predicated global loads per level instead of 324.
+// One warp per low-resolution pixel; each lane produces ~10 of the 324 samples.
 // Output channel l*81 + i*9 + j samples (cx/2^l + i - 4, cy/2^l + j - 4): the slow window index moves x
 // (reference corr.py:44-50 stacks meshgrid(dy,dx) into the (x,y) slots).
-constexpr int LK_PATCH = 12;
 __global__ void __launch_bounds__(256) corr_lookup_kernel(const float* __restrict__ pyr, const float* __restrict__ coords,
                                                           int B, int h, int w, float* __restrict__ out,
                                                           __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-    __shared__ float patch_s[8][LK_PATCH * LK_PATCH];
     const int P = h * w;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp >= B * P) return;                                   // whole warps leave together
-    float* patch = patch_s[threadIdx.x >> 5];
+    if (warp >= B * P) return;
     const int b = warp / P, p = warp - b * P;
     const float cx = coords[(size_t)warp * 2 + 0];
     const float cy = coords[(size_t)warp * 2 + 1];
@@ -71,37 +66,24 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const float* __restric
     for (int l = 0; l < B200POSE_CORR_LEVELS; ++l) {
         const float* img = pyr + lvl_off + ((size_t)b * P + p) * (size_t)(hl * wl);
         const float x0c = cx * inv, y0c = cy * inv;      // cx / 2^l (exact: power of two)
-        // |coordinate| beyond any map: every tap is out of range (zeros); NaN coordinates propagate as NaN
-        const bool far = !(fabsf(x0c) < 1.0e6f) || !(fabsf(y0c) < 1.0e6f);
-        const bool isn = (x0c != x0c) || (y0c != y0c);
-        const int bx = far ? 0 : (int)floorf(x0c) - 5, by = far ? 0 : (int)floorf(y0c) - 5;
-        if (!far) {
-            for (int e = lane; e < LK_PATCH * LK_PATCH; e += 32) {
-                const int py = e / LK_PATCH, px = e - py * LK_PATCH;
-                const int gx = bx + px, gy = by + py;
-                patch[e] = (gx >= 0 && gx < wl && gy >= 0 && gy < hl) ? __ldg(img + gy * wl + gx) : 0.f;
-            }
-        }
-        __syncwarp();
         for (int k = lane; k < 81; k += 32) {
             const int i = k / 9, j = k - i * 9;
-            float val = 0.f;
-            if (!far) {
-                const float xs = x0c + (float)(i - 4);
-                const float ys = y0c + (float)(j - 4);
-                const float xf = floorf(xs), yf = floorf(ys);
-                const float fx = xs - xf, fy = ys - yf;
-                const int px = (int)xf - bx, py = (int)yf - by;          // in [0, 10] by construction
-                const float* q = patch + py * LK_PATCH + px;
-                val = q[0] * (1.f - fx) * (1.f - fy) + q[1] * fx * (1.f - fy) + q[LK_PATCH] * (1.f - fx) * fy +
-                      q[LK_PATCH + 1] * fx * fy;
-            } else if (isn) {
-                val = x0c + y0c;                                          // NaN
-            }
+            const float xs = x0c + (float)(i - 4);
+            const float ys = y0c + (float)(j - 4);
+            const float xf = floorf(xs), yf = floorf(ys);
+            const float fx = xs - xf, fy = ys - yf;
+            const int xi = (int)xf, yi = (int)yf;
+            float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
+            const bool x0ok = xi >= 0 && xi < wl, x1ok = xi + 1 >= 0 && xi + 1 < wl;
+            const bool y0ok = yi >= 0 && yi < hl, y1ok = yi + 1 >= 0 && yi + 1 < hl;
+            if (y0ok && x0ok) v00 = __ldg(img + yi * wl + xi);
+            if (y0ok && x1ok) v01 = __ldg(img + yi * wl + xi + 1);
+            if (y1ok && x0ok) v10 = __ldg(img + (yi + 1) * wl + xi);
+            if (y1ok && x1ok) v11 = __ldg(img + (yi + 1) * wl + xi + 1);
+            const float val = v00 * (1.f - fx) * (1.f - fy) + v01 * fx * (1.f - fy) + v10 * (1.f - fx) * fy + v11 * fx * fy;
             if (o) o[l * 81 + k] = val;
             if (oh) b2p_split_half(val, oh[l * 81 + k], ol[l * 81 + k]);
         }
-        __syncwarp();
         lvl_off += (size_t)B * P * (size_t)(hl * wl);
         hl >>= 1; wl >>= 1; inv *= 0.5f;
     }

@@ -3,17 +3,13 @@
 //   reference model/CFNet.py:95-106 (upsample_flow), model/PoseRefiner.py:335-345,
 //   geometry/projective_ops.py:11-23 (normalize_coords_grid), F.grid_sample default
 //   (align_corners=False, zeros padding) -- SURVEY Appendix A.5 / A.7.
-//
-// The kernel is latency-bound: every pixel has a dependent chain depth -> (mask, flow) -> target -> descriptor
-// gathers.  To keep many independent requests in flight, four consecutive lanes share a pixel (each takes a quarter
-// of the descriptor channels; two shuffles combine the partial dot products) and every lane group carries UW_PX
-// pixels at once (rows Y, Y + H/UW_PX, ... of the same sample), whose chains the compiler interleaves.
-// Mask reads are 32-B-sector exact, descriptor planes (NCHW) are read coalesced along x.
+// Four consecutive lanes share one full-resolution pixel (x fastest): each takes a quarter of the descriptor
+// channels (a 4-tap gather per channel) and the partial dot products meet in two shuffles.  The kernel is
+// latency-bound (dependent mask -> target -> gather chain), so the 4x thread count is what buys memory-level
+// parallelism; mask reads stay 32-B-sector exact, descriptor planes (NCHW) are read coalesced.
 #include "common.cuh"
 
 namespace {
-
-constexpr int UW_PX = 4;      // pixels per lane group (H must be a multiple of UW_PX: H % 8 == 0 guarantees it)
 
 __global__ void __launch_bounds__(256) upsample_weight_kernel(
     const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1,
@@ -21,118 +17,89 @@ __global__ void __launch_bounds__(256) upsample_weight_kernel(
     float* __restrict__ flow_up, float* __restrict__ target, float* __restrict__ weight, int lazy_background) {
     const int h = H >> 3, w = W >> 3;
     const size_t N = (size_t)H * W;
-    const int Hq = H / UW_PX;                          // rows per pixel slot
-    const size_t Nq = (size_t)Hq * W;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t grp = tid >> 2;                       // lane group -> (sample, row in [0,Hq), column)
+    const size_t idx = tid >> 2;                       // pixel
     const int sub = (int)(tid & 3);                    // channel quarter
-    const bool in_range = grp < (size_t)B * Nq;
-    const size_t gc = in_range ? grp : 0;
-    const int b = (int)(gc / Nq);
-    const int rq = (int)(gc - (size_t)b * Nq);
-    const int Yq = rq / W, X = rq - Yq * W;
-    const int x = X >> 3, j = X & 7;
-
-    int Y[UW_PX];
-    size_t idx[UW_PX];
-    float dz[UW_PX];
-#pragma unroll
-    for (int q = 0; q < UW_PX; ++q) {
-        Y[q] = Yq + q * Hq;
-        idx[q] = (size_t)b * N + (size_t)Y[q] * W + X;
-        dz[q] = depth ? __ldg(depth + idx[q]) : 1.f;
-    }
+    const bool in_range = idx < (size_t)B * N;
+    const size_t idc = in_range ? idx : 0;
+    const int b = (int)(idc / N);
+    const int r = (int)(idc - (size_t)b * N);
+    const int Y = r / W, X = r - Y * W;
+    const int y = Y >> 3, i = Y & 7, x = X >> 3, j = X & 7;
+    const size_t p = ((size_t)b * h + y) * w + x;
+    const float dz = depth ? __ldg(depth + idc) : 1.f;
 
     // Fused-loop shortcut: a background pixel (syn_depth <= 0) has weight exactly 0, so the LM step ignores its target
     // (any finite value contributes 0 * finite = 0, as in the reference).  When the up-sampled flow itself is not an
     // output of this iteration, skip the mask softmax and the descriptor warp for it.
-    bool lazy[UW_PX];
-    float tx[UW_PX], ty[UW_PX], ux[UW_PX], uy[UW_PX];
+    const bool lazy = lazy_background && !flow_up && dz <= 0.f;
+    float tx = (float)X, ty = (float)Y, ux = 0.f, uy = 0.f;
+    if (in_range && !lazy) {
+        // softmax over the 9 taps of mask[p][k*64 + i*8 + j]
+        const float* mp = mask + p * 576 + i * 8 + j;
+        float mk[9];
+        float mx = -INFINITY;
 #pragma unroll
-    for (int q = 0; q < UW_PX; ++q) {
-        lazy[q] = lazy_background && !flow_up && dz[q] <= 0.f;
-        ux[q] = 0.f; uy[q] = 0.f;
-        if (in_range && !lazy[q]) {
-            const int y = Y[q] >> 3, i = Y[q] & 7;
-            const size_t p = ((size_t)b * h + y) * w + x;
-            // softmax over the 9 taps of mask[p][k*64 + i*8 + j]
-            const float* mp = mask + p * 576 + i * 8 + j;
-            float mk[9];
-            float mx = -INFINITY;
+        for (int k = 0; k < 9; ++k) { mk[k] = __ldg(mp + k * 64); mx = fmaxf(mx, mk[k]); }
+        float den = 0.f;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) { mk[k] = __ldg(mp + k * 64); mx = fmaxf(mx, mk[k]); }
-            float den = 0.f;
+        for (int k = 0; k < 9; ++k) { mk[k] = expf(mk[k] - mx); den += mk[k]; }
 #pragma unroll
-            for (int k = 0; k < 9; ++k) { mk[k] = expf(mk[k] - mx); den += mk[k]; }
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const int ny = y + k / 3 - 1, nx = x + k % 3 - 1;
-                float2 f = make_float2(0.f, 0.f);
-                if (ny >= 0 && ny < h && nx >= 0 && nx < w)
-                    f = __ldg(reinterpret_cast<const float2*>(flow + (((size_t)b * h + ny) * w + nx) * 2));
-                const float sm = mk[k] / den;
-                ux[q] += sm * (8.f * f.x);
-                uy[q] += sm * (8.f * f.y);
-            }
+        for (int k = 0; k < 9; ++k) {
+            const int ny = y + k / 3 - 1, nx = x + k % 3 - 1;
+            float2 f = make_float2(0.f, 0.f);
+            if (ny >= 0 && ny < h && nx >= 0 && nx < w)
+                f = __ldg(reinterpret_cast<const float2*>(flow + (((size_t)b * h + ny) * w + nx) * 2));
+            const float sm = mk[k] / den;
+            ux += sm * (8.f * f.x);
+            uy += sm * (8.f * f.y);
         }
-        tx[q] = ux[q] + (float)X; ty[q] = uy[q] + (float)Y[q];
+        tx = ux + (float)X; ty = uy + (float)Y;
     }
     if (in_range && sub == 0) {
-#pragma unroll
-        for (int q = 0; q < UW_PX; ++q) {
-            const size_t r = (size_t)Y[q] * W + X;
-            if (flow_up) {
-                flow_up[((size_t)b * 2 + 0) * N + r] = ux[q];
-                flow_up[((size_t)b * 2 + 1) * N + r] = uy[q];
-            }
-            if (target) *reinterpret_cast<float2*>(target + idx[q] * 2) = make_float2(tx[q], ty[q]);
+        if (flow_up) {
+            flow_up[((size_t)b * 2 + 0) * N + r] = ux;
+            flow_up[((size_t)b * 2 + 1) * N + r] = uy;
         }
+        if (target) *reinterpret_cast<float2*>(target + idx * 2) = make_float2(tx, ty);
     }
     if (!weight) return;                                // uniform over the grid
 
-    float s[UW_PX];
-    bool fg[UW_PX];
-#pragma unroll
-    for (int q = 0; q < UW_PX; ++q) {
-        s[q] = 0.f;
-        fg[q] = in_range && !lazy[q] && dz[q] > 0.f;
-        if (fg[q]) {
-            // normalize_coords_grid then grid_sample's align_corners=False un-normalisation
-            const float gx = 2.f * tx[q] / (float)(W - 1) - 1.f;
-            const float gy = 2.f * ty[q] / (float)(H - 1) - 1.f;
-            const float ix = ((gx + 1.f) * (float)W - 1.f) / 2.f;
-            const float iy = ((gy + 1.f) * (float)H - 1.f) / 2.f;
-            const float fx0 = floorf(ix), fy0 = floorf(iy);
-            const int x0 = (int)fx0, y0 = (int)fy0;
-            const float wnw = (fx0 + 1.f - ix) * (fy0 + 1.f - iy);
-            const float wne = (ix - fx0) * (fy0 + 1.f - iy);
-            const float wsw = (fx0 + 1.f - ix) * (iy - fy0);
-            const float wse = (ix - fx0) * (iy - fy0);
-            // ix may be NaN/inf for degenerate flow: no corner is in bounds -> zero sample, like grid_sample
-            const bool fin = isfinite(ix) && isfinite(iy);
-            const bool xa = fin && x0 >= 0 && x0 < W, xb = fin && x0 + 1 >= 0 && x0 + 1 < W;
-            const bool ya = fin && y0 >= 0 && y0 < H, yb = fin && y0 + 1 >= 0 && y0 + 1 < H;
-            const size_t o00 = (size_t)y0 * W + x0;
-            const float* g1p = g1 + (size_t)b * C * N + (size_t)Y[q] * W + X;
-            const float* g2p = g2 + (size_t)b * C * N;
+    float s = 0.f;
+    const bool fg = in_range && !lazy && dz > 0.f;
+    if (fg) {
+        // normalize_coords_grid then grid_sample's align_corners=False un-normalisation
+        const float gx = 2.f * tx / (float)(W - 1) - 1.f;
+        const float gy = 2.f * ty / (float)(H - 1) - 1.f;
+        const float ix = ((gx + 1.f) * (float)W - 1.f) / 2.f;
+        const float iy = ((gy + 1.f) * (float)H - 1.f) / 2.f;
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const int x0 = (int)fx0, y0 = (int)fy0;
+        const float wnw = (fx0 + 1.f - ix) * (fy0 + 1.f - iy);
+        const float wne = (ix - fx0) * (fy0 + 1.f - iy);
+        const float wsw = (fx0 + 1.f - ix) * (iy - fy0);
+        const float wse = (ix - fx0) * (iy - fy0);
+        // ix may be NaN/inf for degenerate flow: no corner is in bounds -> zero sample, like grid_sample
+        const bool fin = isfinite(ix) && isfinite(iy);
+        const bool xa = fin && x0 >= 0 && x0 < W, xb = fin && x0 + 1 >= 0 && x0 + 1 < W;
+        const bool ya = fin && y0 >= 0 && y0 < H, yb = fin && y0 + 1 >= 0 && y0 + 1 < H;
+        const size_t o00 = (size_t)y0 * W + x0;
+        const float* g1p = g1 + (size_t)b * C * N + r;
+        const float* g2p = g2 + (size_t)b * C * N;
 #pragma unroll 8
-            for (int c = sub; c < C; c += 4) {
-                const float* pl = g2p + (size_t)c * N;
-                float v = 0.f;
-                if (ya && xa) v += __ldg(pl + o00) * wnw;
-                if (ya && xb) v += __ldg(pl + o00 + 1) * wne;
-                if (yb && xa) v += __ldg(pl + o00 + W) * wsw;
-                if (yb && xb) v += __ldg(pl + o00 + W + 1) * wse;
-                s[q] += __ldg(g1p + (size_t)c * N) * v;
-            }
+        for (int c = sub; c < C; c += 4) {
+            const float* pl = g2p + (size_t)c * N;
+            float v = 0.f;
+            if (ya && xa) v += __ldg(pl + o00) * wnw;
+            if (ya && xb) v += __ldg(pl + o00 + 1) * wne;
+            if (yb && xa) v += __ldg(pl + o00 + W) * wsw;
+            if (yb && xb) v += __ldg(pl + o00 + W + 1) * wse;
+            s += __ldg(g1p + (size_t)c * N) * v;
         }
     }
-#pragma unroll
-    for (int q = 0; q < UW_PX; ++q) {
-        s[q] += __shfl_xor_sync(0xffffffffu, s[q], 1);
-        s[q] += __shfl_xor_sync(0xffffffffu, s[q], 2);
-        if (in_range && sub == 0) weight[idx[q]] = fg[q] ? expf(-fabsf(1.f - s[q]) / sigma) : 0.f;
-    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (in_range && sub == 0) weight[idx] = fg ? expf(-fabsf(1.f - s) / sigma) : 0.f;
 }
 
 }  // namespace
@@ -140,7 +107,7 @@ __global__ void __launch_bounds__(256) upsample_weight_kernel(
 int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth,
                         float sigma, int B, int C, int H, int W, float* flow_up, float* target, float* weight,
                         int lazy_background, cudaStream_t s) {
-    const size_t total = (size_t)B * (H / UW_PX) * W * 4;
+    const size_t total = (size_t)B * H * W * 4;
     upsample_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(flow, mask, g1, g2, depth, sigma, B, C, H, W,
                                                                            flow_up, target, weight, lazy_background);
     B2P_LAUNCH_CHECK();
