@@ -225,7 +225,6 @@ int run_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int h, int
 
 struct RefineWs {
     float *pyr, *net, *xbuf, *corr, *coords1, *flow, *mask, *target, *weight;
-    float *g1t, *g2t;            // channels-last copies of the descriptors ([B][H][W][32]) for the weight kernel
     void* lm;
     VolumeWs vol;
     UpdateWs u;
@@ -245,8 +244,6 @@ size_t refine_ws_layout(int B, int H, int W, void* ws, size_t cap, RefineWs* out
     r.mask = c.take<float>(P * 576);
     r.target = c.take<float>(N * 2);
     r.weight = c.take<float>(N);
-    r.g1t = c.take<float>(N * 32);
-    r.g2t = c.take<float>(N * 32);
     r.lm = c.take<char>(b2p_lm_ws_bytes(B, H, W));
     c.off = align_up(c.off, 1024);
     c.off += volume_ws_layout(B, h, w, ws ? c.base + c.off : nullptr, 0, &r.vol);
@@ -449,7 +446,7 @@ int b200pose_refine_launch_count(int n_iters, int n_lm) {
     // update block, upsample+weight, 1 launch per LM step (+1 counter reset per call)
     // (tensor-core path: counter reset, 2 feature-map transposes, volume GEMM, 3 pools, context = 8 per call,
     //  + 4 GRU partial-sum GEMMs when there is more than one recurrent iteration)
-    return 10 + (n_iters > 1 ? 4 : 0) + n_iters * (2 + UPDATE_LAUNCHES + 1 + (n_lm > 1 ? 1 : n_lm));   // +2 descriptor transposes
+    return 8 + (n_iters > 1 ? 4 : 0) + n_iters * (2 + UPDATE_LAUNCHES + 1 + (n_lm > 1 ? 1 : n_lm));
 }
 
 int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const float* fmap2, const float* context,
@@ -480,12 +477,6 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
     else rc = b2p_context_init(context, B, H, W, r.net, r.xbuf, nullptr, nullptr, nullptr, nullptr, s);
     if (rc) return rc;
     if (tc && n_iters > 1 && (rc = run_gru_precompute(wts, B, h, w, u, s))) return rc;
-    // descriptors once per call into channels-last form (32 channels = one 128-byte line per pixel)
-    const bool nhwc = (C_geo == 32) && n_iters > 0;
-    if (nhwc) {
-        if ((rc = b2p_nchw_to_nhwc(geofea1, depth, B, 32, H, W, 1, r.g1t, s))) return rc;
-        if ((rc = b2p_nchw_to_nhwc(geofea2, depth, B, 32, H, W, 0, r.g2t, s))) return rc;
-    }
     for (int it = 0; it < n_iters; ++it) {
         if ((rc = b2p_flow_init(depth, K, G, B, H, W, r.coords1, r.flow, s))) return rc;
         if (tc) {
@@ -496,9 +487,8 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
             if ((rc = run_update_block(wts, r.net, r.xbuf, r.corr, r.coords1, r.flow, r.mask, nullptr, B, h, w, u, s))) return rc;
         }
         float* fu = (it == 0 && flow_first) ? flow_first : ((it == n_iters - 1) ? flow_last : nullptr);
-        if (nhwc) rc = b2p_upsample_weight_nhwc(r.flow, r.mask, r.g1t, r.g2t, depth, sigma, B, H, W, fu, r.target, r.weight, 1, s);
-        else rc = b2p_upsample_weight(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, fu, r.target, r.weight, 1, s);
-        if (rc) return rc;
+        if ((rc = b2p_upsample_weight(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, fu, r.target,
+                                      r.weight, 1, s))) return rc;
         if (it == 0 && it == n_iters - 1 && flow_first && flow_last)
             B2P_CUDA(cudaMemcpyAsync(flow_last, flow_first, (size_t)B * 2 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
         if ((rc = b2p_lm_steps(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, n_lm, r.lm, s))) return rc;

@@ -140,10 +140,6 @@ int b2p_flow_head2(const float* hm /*[P][512] fp32, first 256 = flow-head featur
 int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth,
                         float sigma, int B, int C, int H, int W, float* flow_up, float* target, float* weight,
                         int lazy_background, cudaStream_t s);
-int b2p_nchw_to_nhwc(const float* src, const float* depth, int B, int C, int H, int W, int only_fg, float* dst, cudaStream_t s);
-int b2p_upsample_weight_nhwc(const float* flow, const float* mask, const float* g1t, const float* g2t, const float* depth,
-                             float sigma, int B, int H, int W, float* flow_up, float* target, float* weight,
-                             int lazy_background, cudaStream_t s);
 int b2p_lm_step(const float* depth, const float* target, const float* weight, const float* K, float* G,
                 int B, int H, int W, float depth_add, double ep, double lm, double* H_out, double* b_out,
                 float* delta_out, void* ws, cudaStream_t s);
