@@ -152,6 +152,16 @@ int b200pose_lm_solve(const float* depth, const float* target, const float* weig
                       double* H_out, double* b_out, float* delta_out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- f3: per-object pose metrics ----------------------------------------------------------------
+ * Replaces the evaluator's per-object arithmetic: utils/eval_metric.py:161-192 (add_metric with the brute-force
+ * nearest neighbour of thirdparty/nn/src/nearest_neighborhood.cu:48-117 for symmetric objects, cm_degree_5_metric)
+ * and utils/geometric.py:36-40 (rotation_angle).  T_pred,T_gt: [B,4,4] row-major; pts: [B,n_pts,3] model points;
+ * diameter: [B].  out: [B,8] = {ADD, ADD-S, rotation error (deg), translation error (same unit as pts),
+ * ADD < 0.1 d, ADD-S < 0.1 d, (trans*100 < 5 and deg < 5), 0}.  workspace: b200pose_pose_metrics_workspace_bytes.   */
+size_t b200pose_pose_metrics_workspace_bytes(int B, int n_pts);
+int b200pose_pose_metrics(const float* T_pred, const float* T_gt, const float* pts, const float* diameter,
+                          int B, int n_pts, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a14: the fused inner loop ----------------------------------------------------------------
  * Replaces the body of `for i in range(cfg.ITER_COUNT)` in PoseRefiner.forward
  * (model/PoseRefiner.py:315-362) for one render iteration, natively batched.

@@ -412,7 +412,7 @@ def add_metric(R_p, t_p, R_g, t_g, pts, symmetric: bool = False) -> torch.Tensor
     pp = torch.einsum("bij,nj->bni", R_p, pts) + t_p[:, None]
     pg = torch.einsum("bij,nj->bni", R_g, pts) + t_g[:, None]
     if symmetric:
-        d = torch.cdist(pp, pg).min(dim=2).values
+        d = torch.cdist(pp, pg, compute_mode="donot_use_mm_for_euclid_dist").min(dim=2).values
     else:
         d = (pp - pg).norm(dim=-1)
     return d.mean(dim=1)

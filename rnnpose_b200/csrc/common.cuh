@@ -147,4 +147,7 @@ int b2p_lm_steps(const float* depth, const float* target, const float* weight, c
                  int B, int H, int W, float depth_add, double ep, double lm, int n_steps, void* ws, cudaStream_t s);
 size_t b2p_lm_ws_bytes(int B, int H, int W);
 int b2p_lm_reset(void* ws, int B, int H, int W, cudaStream_t s);   // once before the first b2p_lm_step on a workspace
+size_t b2p_pose_metrics_ws_bytes(int B, int n);
+int b2p_pose_metrics(const float* T_pred, const float* T_gt, const float* pts, const float* diameter, int B, int n, float* out,
+                     void* ws, cudaStream_t s);
 int b2p_pack_weights(const float* const* t, float* packed, cudaStream_t s);   // fp32 section + fp16 hi/lo section

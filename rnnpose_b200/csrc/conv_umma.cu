@@ -18,6 +18,10 @@
 
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
+#include <functional>
+#include <mutex>
+#include <unordered_map>
 
 namespace {
 
@@ -31,12 +35,17 @@ constexpr int TMEM_BUF_COLS = 256;
 struct UmmaConvParams {
     CUtensorMap a_hi[2], a_lo[2];     // activation segments (PXC fp16 planes), rank 4: (C, w, h, B)
     CUtensorMap b_hi, b_lo;           // weights, rank 3: (Cin_pad, Cout_pad, taps)
+    CUtensorMap bs_hi, bs_lo;         // same tensors with an n_sub-row box, for the split tiles of the last round
     int seg0_chunks, chunks_per_tap, kh, kw;
     int B, h, w, tiles_x, tiles_y;
     int n_tile, cout, stages;
     int n_active, chunk_list[8];           // channel chunks (of 64) visited per tap; the others are skipped
     const float* pre; int pre_pitch;        // optional fp32 partial sums added before the activation ([P][pre_pitch])
     int m_tiles, total_tiles, b_batched;   // b_batched: the weight map's 3rd coordinate is the sample index (correlation volume)
+    // Work units.  Units [0, full_units) are whole tiles (n_tile output channels).  The tiles of the last, partially
+    // filled round of the persistent grid are each cut into `split` units of n_sub channels so that the round keeps
+    // (almost) every SM busy for 1/split of a tile time instead of a few SMs for a whole one.
+    int full_units, total_units, split, n_sub;
     const float* bias;
     int epi; float scale;
     float* out_f32; int out_f32_pitch;
@@ -126,19 +135,6 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------- kernel
@@ -160,12 +156,19 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     // CTAs of one round share the weight tile (L2) and walk over different pixel tiles
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int nk = p.kh * p.kw * p.n_active;
-    auto decode = [&](int t, int& bimg, int& y0, int& x0, int& n0) {
+    auto decode = [&](int u, int& bimg, int& y0, int& x0, int& n0, int& n_cnt) {
+        int t = u, sub = 0;
+        n_cnt = p.n_tile;
+        if (u >= p.full_units) {
+            const int v = u - p.full_units;
+            t = p.full_units + v / p.split; sub = v - (v / p.split) * p.split;
+            n_cnt = p.n_sub;
+        }
         const int n_idx = t / p.m_tiles, m_idx = t - n_idx * p.m_tiles;
         bimg = m_idx / tiles_per_img;
         const int trem = m_idx - bimg * tiles_per_img;
         y0 = (trem / p.tiles_x) * TILE_ROWS; x0 = (trem % p.tiles_x) * TILE_COLS;
-        n0 = n_idx * p.n_tile;
+        n0 = n_idx * p.n_tile + sub * p.n_sub;
     };
 
     if (warp == 0 && lane == 0) {
@@ -188,13 +191,17 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         if (lane == 0) {
             // ------------------------------------------------ TMA producer (runs ahead across tile boundaries)
             uint32_t it = 0;                                   // global K-chunk counter -> ring slot and phase
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                int bimg, y0, x0, n0;
-                decode(t, bimg, y0, x0, n0);
+            for (int t = blockIdx.x; t < p.total_units; t += gridDim.x) {
+                int bimg, y0, x0, n0, n_cnt;
+                decode(t, bimg, y0, x0, n0, n_cnt);
+                const bool whole = n_cnt == p.n_tile;
+                const CUtensorMap* bh = whole ? &p.b_hi : &p.bs_hi;
+                const CUtensorMap* bl = whole ? &p.b_lo : &p.bs_lo;
+                const uint32_t tx_bytes = 2u * A_TILE_BYTES + 2u * (uint32_t)n_cnt * 128u;
                 for (int kc = 0; kc < nk; ++kc, ++it) {
                     const int s = it % p.stages, ph = (it / p.stages) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1);
-                    mbar_expect_tx(full_bar(s), stage_bytes);
+                    mbar_expect_tx(full_bar(s), tx_bytes);
                     const int tap = kc / p.n_active, cc = p.chunk_list[kc - tap * p.n_active];
                     const int ky = tap / p.kw, kx = tap - ky * p.kw;
                     const int seg = cc >= p.seg0_chunks ? 1 : 0;
@@ -202,8 +209,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
                     const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
                     tma_load_4d(&p.a_hi[seg], sa, full_bar(s), c0, x0 + kx - (p.kw >> 1), y0 + ky - (p.kh >> 1), bimg);
                     tma_load_4d(&p.a_lo[seg], sa + A_TILE_BYTES, full_bar(s), c0, x0 + kx - (p.kw >> 1), y0 + ky - (p.kh >> 1), bimg);
-                    tma_load_3d(&p.b_hi, sa + 2 * A_TILE_BYTES, full_bar(s), cc * BKC, n0, p.b_batched ? bimg : tap);
-                    tma_load_3d(&p.b_lo, sa + 2 * A_TILE_BYTES + b_tile_bytes, full_bar(s), cc * BKC, n0, p.b_batched ? bimg : tap);
+                    tma_load_3d(bh, sa + 2 * A_TILE_BYTES, full_bar(s), cc * BKC, n0, p.b_batched ? bimg : tap);
+                    tma_load_3d(bl, sa + 2 * A_TILE_BYTES + b_tile_bytes, full_bar(s), cc * BKC, n0, p.b_batched ? bimg : tap);
                 }
             }
         }
@@ -212,9 +219,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
             // ------------------------------------------------ MMA issuer
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=B=F16 (0), K-major both,
             // N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc_whole = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc_sub = (1u << 4) | ((uint32_t)(p.n_sub >> 3) << 17) | ((128u >> 4) << 24);
             uint32_t it = 0, tile_iter = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_iter) {
+            for (int t = blockIdx.x; t < p.total_units; t += gridDim.x, ++tile_iter) {
+                const uint32_t idesc = t < p.full_units ? idesc_whole : idesc_sub;
                 const int buf = tile_iter & 1;
                 const uint32_t acc = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
                 mbar_wait(tmem_empty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // epilogue has drained this buffer
@@ -244,9 +253,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
         const int mrow = q * 32 + lane;
         uint32_t tile_iter = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_iter) {
-        int bimg, y0, x0, n0;
-        decode(t, bimg, y0, x0, n0);
+        for (int t = blockIdx.x; t < p.total_units; t += gridDim.x, ++tile_iter) {
+        int bimg, y0, x0, n0, n_cnt;
+        decode(t, bimg, y0, x0, n0, n_cnt);
         const int buf = tile_iter & 1;
         const int yy = y0 + (mrow >> 3), xx = x0 + (mrow & 7);
         const bool valid = yy < p.h && xx < p.w;
@@ -254,7 +263,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         mbar_wait_backoff(tmem_full_bar(buf), (tile_iter >> 1) & 1);
         tc_fence_after();
         // the two warps of a lane quarter take alternate 32-column groups
-        for (int col0 = ((warp - 2) >> 2) * 32; col0 < p.n_tile; col0 += 64) {
+        for (int col0 = ((warp - 2) >> 2) * 32; col0 < n_cnt; col0 += 64) {
             uint32_t r[32];
             tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS + col0), r);
             const int nb = n0 + col0;
@@ -297,7 +306,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
             }
             // channels of this 32-group that exist: bounded by the layer (cout) and by the tile (n_tile need not be a
             // multiple of 32, e.g. 240 for the correlation volume)
-            const int lim = min(p.cout - nb, p.n_tile - col0);
+            const int lim = min(p.cout - nb, n_cnt - col0);
             if (p.epi == EPI_SCALE) {
                 float* d = p.out_f32 + pix * p.out_f32_pitch + nb;
 #pragma unroll
@@ -390,29 +399,84 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
+// Encoded tensor maps depend only on (base, extents, pitches, box), never on the data: keep them in a small cache so
+// that the ~90 launches of one refine call do not re-encode ~500 descriptors (matters for small batches, which are
+// bound by host launch cost).
+struct MapKey {
+    const void* base; int d[6];
+    bool operator==(const MapKey& o) const { return base == o.base && !memcmp(d, o.d, sizeof(d)); }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = std::hash<const void*>()(k.base);
+        for (int i = 0; i < 6; ++i) h = h * 1000003u ^ (size_t)(unsigned)k.d[i];
+        return h;
+    }
+};
+std::mutex g_map_mutex;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+template <class Make>
+int cached_map(CUtensorMap* m, const MapKey& key, Make make) {
+    {
+        std::lock_guard<std::mutex> lk(g_map_mutex);
+        auto it = g_map_cache.find(key);
+        if (it != g_map_cache.end()) { *m = it->second; return 0; }
+    }
+    int rc = make(m);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    if (g_map_cache.size() > 8192) g_map_cache.clear();
+    g_map_cache.emplace(key, *m);
+    return 0;
+}
+
 int make_act_map(CUtensorMap* m, const __half* base, int C, int pitch, int B, int h, int w) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return (int)cudaErrorNotSupported;
-    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
-    cuuint64_t gstr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)w * pitch * 2, (cuuint64_t)h * w * pitch * 2};
-    cuuint32_t box[4] = {BKC, TILE_COLS, TILE_ROWS, 1};
-    cuuint32_t est[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+    return cached_map(m, MapKey{base, {C, pitch, B, h, w, -1}}, [&](CUtensorMap* out) -> int {
+        EncodeTiledFn enc = get_encode();
+        if (!enc) return (int)cudaErrorNotSupported;
+        cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)w * pitch * 2, (cuuint64_t)h * w * pitch * 2};
+        cuuint32_t box[4] = {BKC, TILE_COLS, TILE_ROWS, 1};
+        cuuint32_t est[4] = {1, 1, 1, 1};
+        CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+    });
 }
 
 int make_wgt_map(CUtensorMap* m, const __half* base, int cin_pad, int cout_pad, int taps, int n_tile) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return (int)cudaErrorNotSupported;
-    cuuint64_t gdim[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)taps};
-    cuuint64_t gstr[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cout_pad * cin_pad * 2};
-    cuuint32_t box[3] = {BKC, (cuuint32_t)n_tile, 1};
-    cuuint32_t est[3] = {1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+    return cached_map(m, MapKey{base, {cin_pad, cout_pad, taps, n_tile, -2, -2}}, [&](CUtensorMap* out) -> int {
+        EncodeTiledFn enc = get_encode();
+        if (!enc) return (int)cudaErrorNotSupported;
+        cuuint64_t gdim[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)taps};
+        cuuint64_t gstr[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cout_pad * cin_pad * 2};
+        cuuint32_t box[3] = {BKC, (cuuint32_t)n_tile, 1};
+        cuuint32_t est[3] = {1, 1, 1};
+        CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+    });
 }
+
+// SM count and the shared-memory opt-in, once per device
+int device_sms() {
+    static int sms_of[64];
+    static bool done[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (!done[dev]) {
+        std::lock_guard<std::mutex> lk(g_map_mutex);
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
+        sms_of[dev] = sms; done[dev] = true;
+    }
+    return sms_of[dev];
+}
+
+// smallest channel count of a split unit (0 disables splitting); B200POSE_TAIL_MIN_N overrides it for experiments
+int g_tail_min_n = []() { const char* e = getenv("B200POSE_TAIL_MIN_N"); return e ? atoi(e) : 32; }();
 
 }  // namespace
 
@@ -445,14 +509,28 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     p.out_hi = a.out_hi; p.out_lo = a.out_lo; p.out_h_pitch = a.out_h_pitch;
     p.zbuf = a.zbuf; p.hbuf = a.hbuf;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
-    B2P_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    int dev = 0, sms = 148;
-    B2P_CUDA(cudaGetDevice(&dev));
-    B2P_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = device_sms();
+    if (sms <= 0) return (int)cudaErrorInvalidDevice;
     p.m_tiles = a.B * p.tiles_x * p.tiles_y;
     p.total_tiles = p.m_tiles * (a.cout_pad / a.n_tile);
     p.b_batched = a.b_batched;
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;      // persistent: one CTA per SM
+    // split the tiles of the last partial round (see UmmaConvParams): the largest split whose units still fit one round
+    p.full_units = p.total_tiles; p.total_units = p.total_tiles; p.split = 1; p.n_sub = a.n_tile;
+    const int tail = p.total_tiles % grid;
+    if (tail && g_tail_min_n > 0) {
+        for (int sp = a.n_tile / g_tail_min_n; sp >= 2; --sp) {
+            if (a.n_tile % sp || (a.n_tile / sp) % 32 || tail * sp > grid) continue;
+            p.split = sp; p.n_sub = a.n_tile / sp;
+            p.full_units = p.total_tiles - tail; p.total_units = p.full_units + tail * sp;
+            break;
+        }
+    }
+    p.bs_hi = p.b_hi; p.bs_lo = p.b_lo;
+    if (p.split > 1) {
+        if ((rc = make_wgt_map(&p.bs_hi, a.w_hi, a.cin_pad, a.cout_pad, taps, p.n_sub))) return rc;
+        if ((rc = make_wgt_map(&p.bs_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, p.n_sub))) return rc;
+    }
     conv_umma_kernel<<<grid, UM_THREADS, smem, s>>>(p);
     B2P_LAUNCH_CHECK();
     return 0;

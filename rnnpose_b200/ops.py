@@ -221,6 +221,24 @@ def lm_solve(depth: torch.Tensor, target: torch.Tensor, weight: torch.Tensor, K:
     return (G, Ho, bo, do) if taps else G
 
 
+def pose_metrics(T_pred: torch.Tensor, T_gt: torch.Tensor, pts: torch.Tensor, diameter: torch.Tensor) -> torch.Tensor:
+    """[B,8] = ADD, ADD-S, rotation error (deg), translation error, ADD < 0.1 d, ADD-S < 0.1 d, 5cm5deg, 0.
+    Replaces utils/eval_metric.py:161-192 + thirdparty/nn (brute-force nearest neighbour) + geometric.py:36-40."""
+    L = _lib.lib()
+    T_pred, T_gt, pts, diameter = (t.contiguous().float() for t in (T_pred, T_gt, pts, diameter))
+    for t, n in ((T_pred, "T_pred"), (T_gt, "T_gt"), (pts, "pts"), (diameter, "diameter")):
+        _chk(t, n)
+    B, n_pts = pts.shape[0], pts.shape[1]
+    if T_pred.shape != (B, 4, 4) or T_gt.shape != (B, 4, 4) or pts.shape[2] != 3 or diameter.shape != (B,):
+        raise ValueError("pose_metrics: T [B,4,4], pts [B,n,3], diameter [B]")
+    out = torch.empty(B, 8, dtype=torch.float32, device=pts.device)
+    nb = L.b200pose_pose_metrics_workspace_bytes(B, n_pts)
+    ws = _ws(nb, pts.device)
+    _lib.check(L.b200pose_pose_metrics(T_pred.data_ptr(), T_gt.data_ptr(), pts.data_ptr(), diameter.data_ptr(), B, n_pts,
+                                       out.data_ptr(), ws.data_ptr(), nb, _stream()), "b200pose_pose_metrics")
+    return out
+
+
 class RefineWorkspace:
     """Caller-owned scratch for refine_iters (re-used across calls of the same shape)."""
 

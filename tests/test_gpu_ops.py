@@ -230,3 +230,40 @@ def test_lm_vs_oracle_random(ops):
     Gd = ops.lm_solve(depth.to(dev()), tgt.to(dev()), wgt.to(dev()), mb["K"].to(dev()), G.clone().to(dev()), 3,
                       depth_offset=1e-5)
     torch.testing.assert_close(Gd.cpu(), Gr, rtol=0, atol=5e-6)
+
+
+# ----------------------------------------------------------------------------- f3: pose metrics (ADD / ADD-S kernel)
+@pytest.mark.parametrize("n_pts", [1, 50, 256, 300, 2500])
+def test_pose_metrics_vs_oracle(ops, n_pts):
+    from rnnpose_b200 import metrics as M
+    g = torch.Generator().manual_seed(n_pts)
+    B = 5
+    xi = torch.randn(B, 6, generator=g) * 0.1
+    Tp = O.se3_exp(xi); Tg = O.se3_exp(xi + 0.02 * torch.randn(B, 6, generator=g))
+    Tg[0] = Tp[0]                                                      # an exact pose: every metric 0, every flag 1
+    pts = torch.randn(n_pts, 3, generator=g) * 0.05
+    diam = torch.tensor([0.15, 0.15, 0.01, 0.15, 0.3])
+    out = ops.pose_metrics(Tp.cuda(), Tg.cuda(), pts[None].repeat(B, 1, 1).cuda(), diam.cuda()).cpu()
+    add = O.add_metric(Tp[:, :3, :3], Tp[:, :3, 3], Tg[:, :3, :3], Tg[:, :3, 3], pts, False)
+    adds = O.add_metric(Tp[:, :3, :3], Tp[:, :3, 3], Tg[:, :3, :3], Tg[:, :3, 3], pts, True)
+    torch.testing.assert_close(out[:, 0], add, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(out[:, 1], adds, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(out[:, 2], O.rotation_angle_deg(Tp[:, :3, :3], Tg[:, :3, :3]), rtol=1e-4, atol=2e-3)
+    torch.testing.assert_close(out[:, 3], (Tp[:, :3, 3] - Tg[:, :3, 3]).norm(dim=1), rtol=1e-5, atol=1e-7)
+    assert out[0, :4].abs().max() < 1e-6 and out[0, 4:7].tolist() == [1.0, 1.0, 1.0]
+    ref = M.pose_metrics_torch(Tp, Tg, pts[None].repeat(B, 1, 1), diam, torch.zeros(B))
+    margin = (ref[:, 0] - 0.1 * diam).abs() > 1e-6                     # flags can only differ on a threshold tie
+    assert torch.equal(out[margin, 4], ref[margin, 4])
+    assert torch.equal(out[:, 5][(ref[:, 1] - 0.1 * diam).abs() > 1e-6], ref[:, 5][(ref[:, 1] - 0.1 * diam).abs() > 1e-6])
+    assert torch.equal(out[:, 6], ref[:, 6])
+    full = M.pose_metrics(Tp.cuda(), Tg.cuda(), pts[None].repeat(B, 1, 1).cuda(), diam.cuda(), torch.arange(B).cuda()).cpu()
+    assert full[:, 7].tolist() == [0.0, 1.0, 2.0, 3.0, 4.0] and torch.equal(full[:, :7], out[:, :7])
+
+
+def test_pose_metrics_error_codes(ops):
+    from rnnpose_b200 import _lib
+    L = _lib.lib()
+    t = torch.zeros(64, device="cuda")
+    assert L.b200pose_pose_metrics(0, t.data_ptr(), t.data_ptr(), t.data_ptr(), 1, 4, t.data_ptr(), t.data_ptr(), 1024, 0) == -1
+    assert L.b200pose_pose_metrics(t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), 0, 4, t.data_ptr(), t.data_ptr(), 1024, 0) == -2
+    assert L.b200pose_pose_metrics(t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), 1, 4, t.data_ptr(), t.data_ptr(), 0, 0) == -3
