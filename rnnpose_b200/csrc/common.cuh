@@ -13,6 +13,25 @@
         if (e__ != cudaSuccess) return (int)e__;             \
     } while (0)
 
+// Programmatic dependent launch (PDL): a kernel launched through b2p_launch_pdl may be scheduled while the previous
+// kernel of the stream is still draining; it must execute pdl_wait() before it touches global memory (the wait returns
+// when the previous grid has completed and its writes are visible).  pdl_trigger() lets the NEXT kernel of the stream be
+// scheduled as soon as every block of this one has started.  Both are no-ops for a normally launched kernel.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t b2p_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 #define B2P_CUDA(call)                                       \
     do {                                                     \
         cudaError_t e__ = (call);                            \

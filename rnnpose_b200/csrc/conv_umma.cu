@@ -140,6 +140,7 @@ __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x))
 // ---------------------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_trigger();                       // the next kernel's blocks may take this SM as soon as this CTA retires
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t b_tile_bytes = (uint32_t)p.n_tile * 128u;
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();                          // barriers and TMEM are set up; from here on the previous kernel's output is read
 
     if (warp == 0) {
         if (lane == 0) {
@@ -514,15 +516,17 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     p.m_tiles = a.B * p.tiles_x * p.tiles_y;
     p.total_tiles = p.m_tiles * (a.cout_pad / a.n_tile);
     p.b_batched = a.b_batched;
-    const int grid = p.total_tiles < sms ? p.total_tiles : sms;      // persistent: one CTA per SM
-    // split the tiles of the last partial round (see UmmaConvParams): the largest split whose units still fit one round
+    int grid = p.total_tiles < sms ? p.total_tiles : sms;            // persistent: one CTA per SM
+    // split the tiles of the last partial round (see UmmaConvParams): the largest split whose units still fit one round.
+    // A problem with fewer tiles than SMs (small batches) is one partial round: all of its tiles are split.
     p.full_units = p.total_tiles; p.total_units = p.total_tiles; p.split = 1; p.n_sub = a.n_tile;
-    const int tail = p.total_tiles % grid;
+    const int tail = p.total_tiles < sms ? p.total_tiles : p.total_tiles % sms;
     if (tail && g_tail_min_n > 0) {
         for (int sp = a.n_tile / g_tail_min_n; sp >= 2; --sp) {
-            if (a.n_tile % sp || (a.n_tile / sp) % 32 || tail * sp > grid) continue;
+            if (a.n_tile % sp || (a.n_tile / sp) % 32 || tail * sp > sms) continue;
             p.split = sp; p.n_sub = a.n_tile / sp;
             p.full_units = p.total_tiles - tail; p.total_units = p.full_units + tail * sp;
+            if (p.total_units < sms) grid = p.total_units;
             break;
         }
     }
@@ -531,7 +535,7 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
         if ((rc = make_wgt_map(&p.bs_hi, a.w_hi, a.cin_pad, a.cout_pad, taps, p.n_sub))) return rc;
         if ((rc = make_wgt_map(&p.bs_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, p.n_sub))) return rc;
     }
-    conv_umma_kernel<<<grid, UM_THREADS, smem, s>>>(p);
+    B2P_CUDA(b2p_launch_pdl(conv_umma_kernel, dim3(grid), dim3(UM_THREADS), smem, s, p));
     B2P_LAUNCH_CHECK();
     return 0;
 }

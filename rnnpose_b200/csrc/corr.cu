@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(256) fmap_to_pxc_half_kernel(const float* __re
 __global__ void __launch_bounds__(256) corr_lookup_kernel(const float* __restrict__ pyr, const float* __restrict__ coords,
                                                           int B, int h, int w, float* __restrict__ out,
                                                           __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+    pdl_trigger();
+    pdl_wait();
     const int P = h * w;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -164,6 +166,8 @@ __global__ void __launch_bounds__(256) flow_init_kernel(const float* __restrict_
                                                         const float* __restrict__ G, int B, int H, int W, int h, int w,
                                                         float sy, float sx, float* __restrict__ coords1,
                                                         float* __restrict__ flow) {
+    pdl_trigger();
+    pdl_wait();
     const int P = h * w;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * P) return;
@@ -213,7 +217,7 @@ int b2p_corr_pool(const float* src, int NP, int hs, int ws, float* dst, cudaStre
 int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, __half* out_hi,
                     __half* out_lo, cudaStream_t s) {
     const int warps = B * h * w;
-    corr_lookup_kernel<<<ceil_div(warps, 8), 256, 0, s>>>(pyramid, coords, B, h, w, out, out_hi, out_lo);
+    B2P_CUDA(b2p_launch_pdl(corr_lookup_kernel, dim3(ceil_div(warps, 8)), dim3(256), 0, s, pyramid, coords, B, h, w, out, out_hi, out_lo));
     B2P_LAUNCH_CHECK();
     return 0;
 }
@@ -233,8 +237,8 @@ int b2p_context_init(const float* ctx, int B, int H, int W, float* net, float* x
 int b2p_flow_init(const float* depth, const float* K, const float* G, int B, int H, int W, float* coords1, float* flow,
                   cudaStream_t s) {
     const int h = H / 8, w = W / 8;
-    flow_init_kernel<<<ceil_div(B * h * w, 256), 256, 0, s>>>(depth, K, G, B, H, W, h, w, ac_scale(H, h), ac_scale(W, w),
-                                                              coords1, flow);
+    B2P_CUDA(b2p_launch_pdl(flow_init_kernel, dim3(ceil_div(B * h * w, 256)), dim3(256), 0, s, depth, K, G, B, H, W, h, w, ac_scale(H, h),
+                            ac_scale(W, w), coords1, flow));
     B2P_LAUNCH_CHECK();
     return 0;
 }

@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(LM_THREADS) lm_multi_kernel(
     const float* __restrict__ depth, const float* __restrict__ target, const float* __restrict__ weight,
     const float* __restrict__ K, float* __restrict__ G, int B, int H, int W, float depth_add, double ep, double lm,
     int n_steps, double* __restrict__ partials /*[2][B][nb][27]*/, unsigned* __restrict__ counters) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y, nb = gridDim.x, tid = threadIdx.x;
     const int N = H * W;
     const float* Kb = K + b * 9;
@@ -423,8 +425,8 @@ int b2p_lm_steps(const float* depth, const float* target, const float* weight, c
     double* partials = reinterpret_cast<double*>(ws);
     unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + lm_partials_bytes(B, H, W));
     dim3 grid(nb, B);
-    lm_multi_kernel<<<grid, LM_THREADS, 0, s>>>(depth, target, weight, K, G, B, H, W, depth_add, ep, lm, n_steps, partials,
-                                                counters);
+    B2P_CUDA(b2p_launch_pdl(lm_multi_kernel, grid, dim3(LM_THREADS), 0, s, depth, target, weight, K, G, B, H, W, depth_add, ep, lm, n_steps,
+                            partials, counters));
     B2P_LAUNCH_CHECK();
     return 0;
 }

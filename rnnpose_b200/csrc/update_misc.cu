@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(256) im2col_f1_kernel(const float* __restrict_
                                                         float* __restrict__ col, float* __restrict__ xbuf,
                                                         __half* __restrict__ col_hi, __half* __restrict__ col_lo,
                                                         __half* __restrict__ x_hi, __half* __restrict__ x_lo) {
+    pdl_trigger();
+    pdl_wait();
     const size_t total = (size_t)B * h * w * 56;          // 56 float2 slots per pixel (49 taps + 7 zero pads)
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -104,6 +106,8 @@ __global__ void __launch_bounds__(256) flow_head2_kernel(const float* __restrict
                                                          const float* __restrict__ b2, float* __restrict__ coords1,
                                                          float* __restrict__ flow,
                                                          float* __restrict__ dflow_out, int B, int h, int w) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int hw = h * w;
@@ -292,14 +296,14 @@ size_t b2p_half_section_offset_bytes() { return align_up(b2p_weight_layout().tot
 int b2p_im2col_f1(const float* flow, int B, int h, int w, float* col, float* xbuf, __half* col_hi, __half* col_lo,
                   __half* x_hi, __half* x_lo, cudaStream_t s) {
     const size_t total = (size_t)B * h * w * 56;
-    im2col_f1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(flow, B, h, w, col, xbuf, col_hi, col_lo, x_hi, x_lo);
+    B2P_CUDA(b2p_launch_pdl(im2col_f1_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, flow, B, h, w, col, xbuf, col_hi, col_lo, x_hi, x_lo));
     B2P_LAUNCH_CHECK();
     return 0;
 }
 
 int b2p_flow_head2(const float* hm, const __half* hm_hi, const __half* hm_lo, const float* w2, const float* b2,
                    float* coords1, float* flow, float* dflow_out, int B, int h, int w, cudaStream_t s) {
-    flow_head2_kernel<<<ceil_div(B * h * w, 8), 256, 0, s>>>(hm, hm_hi, hm_lo, w2, b2, coords1, flow, dflow_out, B, h, w);
+    B2P_CUDA(b2p_launch_pdl(flow_head2_kernel, dim3(ceil_div(B * h * w, 8)), dim3(256), 0, s, hm, hm_hi, hm_lo, w2, b2, coords1, flow, dflow_out, B, h, w));
     B2P_LAUNCH_CHECK();
     return 0;
 }

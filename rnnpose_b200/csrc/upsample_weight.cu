@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(64) upsample_weight_kernel(
     const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1,
     const float* __restrict__ g2, const float* __restrict__ depth, float sigma, int B, int C, int H, int W,
     float* __restrict__ flow_up, float* __restrict__ target, float* __restrict__ weight, int lazy_background) {
+    pdl_trigger();
+    pdl_wait();
     const int h = H >> 3, w = W >> 3;
     const size_t N = (size_t)H * W;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,8 +110,8 @@ int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, c
                         float sigma, int B, int C, int H, int W, float* flow_up, float* target, float* weight,
                         int lazy_background, cudaStream_t s) {
     const size_t total = (size_t)B * H * W;
-    upsample_weight_kernel<<<(unsigned)((total + 63) / 64), 64, 0, s>>>(flow, mask, g1, g2, depth, sigma, B, C, H, W,
-                                                                           flow_up, target, weight, lazy_background);
+    B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel, dim3((unsigned)((total + 63) / 64)), dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B,
+                            C, H, W, flow_up, target, weight, lazy_background));
     B2P_LAUNCH_CHECK();
     return 0;
 }
