@@ -192,7 +192,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------ TMA producer (runs ahead across tile boundaries)
-            uint32_t it = 0;                                   // global K-chunk counter -> ring slot and phase
+            // ring slot and phase are carried incrementally and the K loop is nested (tap, channel chunk): this thread is
+            // a single instruction stream, and the integer divisions of a flat K index cost more than a stage's MMAs
+            int s = 0; uint32_t ph = 0;
             for (int t = blockIdx.x; t < p.total_units; t += gridDim.x) {
                 int bimg, y0, x0, n0, n_cnt;
                 decode(t, bimg, y0, x0, n0, n_cnt);
@@ -200,19 +202,26 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
                 const CUtensorMap* bh = whole ? &p.b_hi : &p.bs_hi;
                 const CUtensorMap* bl = whole ? &p.b_lo : &p.bs_lo;
                 const uint32_t tx_bytes = 2u * A_TILE_BYTES + 2u * (uint32_t)n_cnt * 128u;
-                for (int kc = 0; kc < nk; ++kc, ++it) {
-                    const int s = it % p.stages, ph = (it / p.stages) & 1;
-                    mbar_wait(empty_bar(s), ph ^ 1);
-                    mbar_expect_tx(full_bar(s), tx_bytes);
-                    const int tap = kc / p.n_active, cc = p.chunk_list[kc - tap * p.n_active];
-                    const int ky = tap / p.kw, kx = tap - ky * p.kw;
-                    const int seg = cc >= p.seg0_chunks ? 1 : 0;
-                    const int c0 = (seg ? cc - p.seg0_chunks : cc) * BKC;
-                    const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-                    tma_load_4d(&p.a_hi[seg], sa, full_bar(s), c0, x0 + kx - (p.kw >> 1), y0 + ky - (p.kh >> 1), bimg);
-                    tma_load_4d(&p.a_lo[seg], sa + A_TILE_BYTES, full_bar(s), c0, x0 + kx - (p.kw >> 1), y0 + ky - (p.kh >> 1), bimg);
-                    tma_load_3d(bh, sa + 2 * A_TILE_BYTES, full_bar(s), cc * BKC, n0, p.b_batched ? bimg : tap);
-                    tma_load_3d(bl, sa + 2 * A_TILE_BYTES + b_tile_bytes, full_bar(s), cc * BKC, n0, p.b_batched ? bimg : tap);
+                int tap = 0;
+                for (int ky = 0; ky < p.kh; ++ky) {
+                    const int ys = y0 + ky - (p.kh >> 1);
+                    for (int kx = 0; kx < p.kw; ++kx, ++tap) {
+                        const int xs = x0 + kx - (p.kw >> 1);
+                        const int b2 = p.b_batched ? bimg : tap;
+                        for (int a = 0; a < p.n_active; ++a) {
+                            const int cc = p.chunk_list[a];
+                            const int seg = cc >= p.seg0_chunks ? 1 : 0;
+                            const int c0 = (seg ? cc - p.seg0_chunks : cc) * BKC;
+                            const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+                            mbar_wait(empty_bar(s), ph ^ 1u);
+                            mbar_expect_tx(full_bar(s), tx_bytes);
+                            tma_load_4d(&p.a_hi[seg], sa, full_bar(s), c0, xs, ys, bimg);
+                            tma_load_4d(&p.a_lo[seg], sa + A_TILE_BYTES, full_bar(s), c0, xs, ys, bimg);
+                            tma_load_3d(bh, sa + 2 * A_TILE_BYTES, full_bar(s), cc * BKC, n0, b2);
+                            tma_load_3d(bl, sa + 2 * A_TILE_BYTES + b_tile_bytes, full_bar(s), cc * BKC, n0, b2);
+                            if (++s == p.stages) { s = 0; ph ^= 1u; }
+                        }
+                    }
                 }
             }
         }
@@ -223,15 +232,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
             // N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc_whole = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t idesc_sub = (1u << 4) | ((uint32_t)(p.n_sub >> 3) << 17) | ((128u >> 4) << 24);
-            uint32_t it = 0, tile_iter = 0;
+            uint32_t tile_iter = 0;
+            int s = 0; uint32_t ph = 0;
             for (int t = blockIdx.x; t < p.total_units; t += gridDim.x, ++tile_iter) {
                 const uint32_t idesc = t < p.full_units ? idesc_whole : idesc_sub;
                 const int buf = tile_iter & 1;
                 const uint32_t acc = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
                 mbar_wait(tmem_empty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // epilogue has drained this buffer
                 tc_fence_after();
-                for (int kc = 0; kc < nk; ++kc, ++it) {
-                    const int s = it % p.stages, ph = (it / p.stages) & 1;
+                for (int kc = 0; kc < nk; ++kc) {
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
@@ -246,6 +255,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
                         tc_mma_f16(acc, a_hi + adv, b_hi + adv, idesc, 1u);
                     }
                     tc_commit(empty_bar(s));      // frees the smem stage when these MMAs have read it
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
                 tc_commit(tmem_full_bar(buf));    // accumulator of this tile complete
             }
