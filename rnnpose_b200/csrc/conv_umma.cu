@@ -51,6 +51,11 @@ struct UmmaConvParams {
     float* out_f32; int out_f32_pitch;
     __half* out_hi; __half* out_lo; int out_h_pitch;
     float* zbuf; float* hbuf;         // GRU side buffers, fp32 [P][128]
+    // conv_umma2_kernel only (separate activation / weight rings, optional CTA pair):
+    int a_taps;                        // vertical taps served by one activation box (kh when the box carries the halo rows, else 1)
+    int a_rows;                        // rows of the activation box = 16 + a_taps - 1
+    int ring_a, ring_b;                // ring depths
+    int m_groups;                      // M tiles / CTAs per cluster, rounded up (a unit = one group x one N tile)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -136,6 +141,121 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
         : "r"(taddr));
 }
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Epilogue of one tile for one warp: TMEM -> registers -> bias / activation / GRU blend -> global (fp32 side outputs and the
+// fp16 hi/lo planes the next convolution reads).  `valid` = this thread's pixel lies inside the image.
+__device__ __forceinline__ void epilogue_columns(const UmmaConvParams& p, uint32_t tmem_base, int warp, int q, int buf, int n0,
+                                                 int n_cnt, bool valid, size_t pix) {
+    // the two warps of a lane quarter take alternate 32-column groups
+    for (int col0 = ((warp - 2) >> 2) * 32; col0 < n_cnt; col0 += 64) {
+        uint32_t r[32];
+        tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS + col0), r);
+        const int nb = n0 + col0;
+        const bool live = valid && nb < p.cout;
+        // side inputs of the GRU epilogues: all loads of the 32-channel group are issued back to back (one
+        // dependent-load round trip per group instead of eight) while the TMEM load is still in flight
+        float4 hh[8], zz[8];
+        const bool need_h = live && ((p.epi == EPI_GRU_ZR && nb >= 128) || p.epi == EPI_GRU_Q);
+        const bool need_z = live && p.epi == EPI_GRU_Q;
+        if (need_h) {
+            const float4* hp4 = reinterpret_cast<const float4*>(p.hbuf + pix * 128 + (nb & 127));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hh[j] = hp4[j];
+        }
+        if (need_z) {
+            const float4* zp4 = reinterpret_cast<const float4*>(p.zbuf + pix * 128 + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) zz[j] = __ldg(zp4 + j);
+        }
+        float4 pre4[8];
+        if (live && p.pre) {
+            const float4* pp = reinterpret_cast<const float4*>(p.pre + pix * p.pre_pitch + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pre4[j] = __ldg(pp + j);
+        }
+        tmem_ld_wait(r);
+        if (!live) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+            v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+        }
+        if (p.pre) {                                       // contribution of the iteration-invariant input channels
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[4 * j] += pre4[j].x; v[4 * j + 1] += pre4[j].y; v[4 * j + 2] += pre4[j].z; v[4 * j + 3] += pre4[j].w;
+            }
+        }
+        // channels of this 32-group that exist: bounded by the layer (cout) and by the tile (n_tile need not be a
+        // multiple of 32, e.g. 240 for the correlation volume)
+        const int lim = min(p.cout - nb, n_cnt - col0);
+        if (p.epi == EPI_SCALE) {
+            float* d = p.out_f32 + pix * p.out_f32_pitch + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                if (j + 3 < lim) {
+                    *reinterpret_cast<float4*>(d + j) = make_float4(v[j] * p.scale, v[j + 1] * p.scale, v[j + 2] * p.scale, v[j + 3] * p.scale);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (j + t < lim) d[j + t] = v[j + t] * p.scale;
+                }
+            }
+            continue;
+        }
+        if (p.epi == EPI_GRU_ZR && nb < 128) {            // z gate, kept in fp32 for the blend
+            float* d = p.zbuf + pix * 128 + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(d + j) = make_float4(sigm(v[j]), sigm(v[j + 1]), sigm(v[j + 2]), sigm(v[j + 3]));
+            continue;
+        }
+        int oc = nb;                                       // output channel of v[0]
+        if (p.epi == EPI_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.epi == EPI_GRU_ZR) {                  // r gate -> r * h
+            oc = nb - 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[4 * j] = sigm(v[4 * j]) * hh[j].x; v[4 * j + 1] = sigm(v[4 * j + 1]) * hh[j].y;
+                v[4 * j + 2] = sigm(v[4 * j + 2]) * hh[j].z; v[4 * j + 3] = sigm(v[4 * j + 3]) * hh[j].w;
+            }
+        } else if (p.epi == EPI_GRU_Q) {                   // h <- (1-z) h + z tanh(q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[4 * j] = (1.f - zz[j].x) * hh[j].x + zz[j].x * tanhf(v[4 * j]);
+                v[4 * j + 1] = (1.f - zz[j].y) * hh[j].y + zz[j].y * tanhf(v[4 * j + 1]);
+                v[4 * j + 2] = (1.f - zz[j].z) * hh[j].z + zz[j].z * tanhf(v[4 * j + 2]);
+                v[4 * j + 3] = (1.f - zz[j].w) * hh[j].w + zz[j].w * tanhf(v[4 * j + 3]);
+            }
+            float4* hp4 = reinterpret_cast<float4*>(p.hbuf + pix * 128 + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hp4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        // fp16 hi/lo planes for the next convolution
+        __half* dh = p.out_hi + pix * p.out_h_pitch + oc;
+        __half* dl = p.out_lo + pix * p.out_h_pitch + oc;
+        const int cvalid = lim;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            __align__(16) __half hi8[8];
+            __align__(16) __half lo8[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) b2p_split_half(v[j + t], hi8[t], lo8[t]);
+            if (j + 7 < cvalid) {
+                *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(hi8);
+                *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(lo8);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (j + t < cvalid) { dh[j + t] = hi8[t]; dl[j + t] = lo8[t]; }
+            }
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
@@ -274,115 +394,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         const size_t pix = ((size_t)bimg * p.h + yy) * p.w + xx;
         mbar_wait_backoff(tmem_full_bar(buf), (tile_iter >> 1) & 1);
         tc_fence_after();
-        // the two warps of a lane quarter take alternate 32-column groups
-        for (int col0 = ((warp - 2) >> 2) * 32; col0 < n_cnt; col0 += 64) {
-            uint32_t r[32];
-            tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS + col0), r);
-            const int nb = n0 + col0;
-            const bool live = valid && nb < p.cout;
-            // side inputs of the GRU epilogues: all loads of the 32-channel group are issued back to back (one
-            // dependent-load round trip per group instead of eight) while the TMEM load is still in flight
-            float4 hh[8], zz[8];
-            const bool need_h = live && ((p.epi == EPI_GRU_ZR && nb >= 128) || p.epi == EPI_GRU_Q);
-            const bool need_z = live && p.epi == EPI_GRU_Q;
-            if (need_h) {
-                const float4* hp4 = reinterpret_cast<const float4*>(p.hbuf + pix * 128 + (nb & 127));
-#pragma unroll
-                for (int j = 0; j < 8; ++j) hh[j] = hp4[j];
-            }
-            if (need_z) {
-                const float4* zp4 = reinterpret_cast<const float4*>(p.zbuf + pix * 128 + nb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) zz[j] = __ldg(zp4 + j);
-            }
-            float4 pre4[8];
-            if (live && p.pre) {
-                const float4* pp = reinterpret_cast<const float4*>(p.pre + pix * p.pre_pitch + nb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) pre4[j] = __ldg(pp + j);
-            }
-            tmem_ld_wait(r);
-            if (!live) continue;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-                v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-                v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-            }
-            if (p.pre) {                                       // contribution of the iteration-invariant input channels
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    v[4 * j] += pre4[j].x; v[4 * j + 1] += pre4[j].y; v[4 * j + 2] += pre4[j].z; v[4 * j + 3] += pre4[j].w;
-                }
-            }
-            // channels of this 32-group that exist: bounded by the layer (cout) and by the tile (n_tile need not be a
-            // multiple of 32, e.g. 240 for the correlation volume)
-            const int lim = min(p.cout - nb, n_cnt - col0);
-            if (p.epi == EPI_SCALE) {
-                float* d = p.out_f32 + pix * p.out_f32_pitch + nb;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (j + 3 < lim) {
-                        *reinterpret_cast<float4*>(d + j) = make_float4(v[j] * p.scale, v[j + 1] * p.scale, v[j + 2] * p.scale, v[j + 3] * p.scale);
-                    } else {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t)
-                            if (j + t < lim) d[j + t] = v[j + t] * p.scale;
-                    }
-                }
-                continue;
-            }
-            if (p.epi == EPI_GRU_ZR && nb < 128) {            // z gate, kept in fp32 for the blend
-                float* d = p.zbuf + pix * 128 + nb;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(d + j) = make_float4(sigm(v[j]), sigm(v[j + 1]), sigm(v[j + 2]), sigm(v[j + 3]));
-                continue;
-            }
-            int oc = nb;                                       // output channel of v[0]
-            if (p.epi == EPI_RELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            } else if (p.epi == EPI_GRU_ZR) {                  // r gate -> r * h
-                oc = nb - 128;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    v[4 * j] = sigm(v[4 * j]) * hh[j].x; v[4 * j + 1] = sigm(v[4 * j + 1]) * hh[j].y;
-                    v[4 * j + 2] = sigm(v[4 * j + 2]) * hh[j].z; v[4 * j + 3] = sigm(v[4 * j + 3]) * hh[j].w;
-                }
-            } else if (p.epi == EPI_GRU_Q) {                   // h <- (1-z) h + z tanh(q)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    v[4 * j] = (1.f - zz[j].x) * hh[j].x + zz[j].x * tanhf(v[4 * j]);
-                    v[4 * j + 1] = (1.f - zz[j].y) * hh[j].y + zz[j].y * tanhf(v[4 * j + 1]);
-                    v[4 * j + 2] = (1.f - zz[j].z) * hh[j].z + zz[j].z * tanhf(v[4 * j + 2]);
-                    v[4 * j + 3] = (1.f - zz[j].w) * hh[j].w + zz[j].w * tanhf(v[4 * j + 3]);
-                }
-                float4* hp4 = reinterpret_cast<float4*>(p.hbuf + pix * 128 + nb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) hp4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            // fp16 hi/lo planes for the next convolution
-            __half* dh = p.out_hi + pix * p.out_h_pitch + oc;
-            __half* dl = p.out_lo + pix * p.out_h_pitch + oc;
-            const int cvalid = lim;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                __align__(16) __half hi8[8];
-                __align__(16) __half lo8[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) b2p_split_half(v[j + t], hi8[t], lo8[t]);
-                if (j + 7 < cvalid) {
-                    *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(hi8);
-                    *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(lo8);
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 8; ++t)
-                        if (j + t < cvalid) { dh[j + t] = hi8[t]; dl[j + t] = lo8[t]; }
-                }
-            }
-        }
+        epilogue_columns(p, tmem_base, warp, q, buf, n0, n_cnt, valid, pix);
         // every TMEM read of this tile has completed (tcgen05.wait::ld above): hand the buffer back to the MMA warp
         tc_fence_before();
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(buf)) : "memory");
@@ -392,6 +404,270 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------- kernel, second generation
+// The first kernel is bound by the L2 -> shared-memory feed (profiles/r1_final_summary.md: 6.9 GB per update-block pass at
+// 8-11 TB/s, the LTS cap is ~12 TB/s), not by the tensor pipe.  This one moves fewer bytes for the same MMAs:
+//  * NCTA = 2: a CTA pair (cluster of two SMs of one TPC) computes two M tiles against ONE weight tile with
+//    tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own 128 pixels and only HALF of the weight rows, the MMA reads
+//    both halves.  Weight traffic per pixel tile halves.  The leader CTA (rank 0) issues the MMAs; both CTAs run a
+//    producer and an epilogue.  Full barriers live in the leader (the peer's TMA completes on them remotely), the
+//    MMA-completion commits are multicast to the empty barriers of both CTAs.
+//  * vertical-tap reuse: for a kh x kw filter the activation box is loaded once per (kx, channel chunk) with kh-1 halo rows
+//    (16+kh-1 rows of 8 pixels = whole 1024-byte swizzle atoms); the A descriptor of vertical tap ky starts ky atoms
+//    further down.  Activation traffic of the 3x3 layers drops 9 -> 3.4 boxes, of the 5x1 layers 5 -> 1.25.
+//    Activations and weights therefore travel in two rings (one A slot serves a_taps B slots).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in the cluster's CTA `rank` (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// pair variants: destination in the executing CTA, completion on the (possibly remote) barrier `bar`
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {     // arrives on `bar`'s offset in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int NCTA>
+__global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_constant__ UmmaConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    pdl_trigger();
+    // identical offsets in both CTAs of a pair: the MMA applies one descriptor to the shared memory of both
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
+    const uint32_t a_plane = (uint32_t)p.a_rows * 1024u;                 // one fp16 plane of an activation box
+    const uint32_t a_slot = 2u * a_plane;
+    const uint32_t b_plane = (uint32_t)(p.n_tile / NCTA) * 128u;          // this CTA's share of the weight rows, one plane
+    const uint32_t b_slot = 2u * b_plane;
+    const uint32_t a_ring = smem_base, b_ring = smem_base + (uint32_t)p.ring_a * a_slot;
+    const uint32_t bars = b_ring + (uint32_t)p.ring_b * b_slot;
+    auto full_a = [&](int s) { return bars + 8u * s; };
+    auto empty_a = [&](int s) { return bars + 8u * (p.ring_a + s); };
+    const uint32_t bars_b = bars + 16u * p.ring_a;
+    auto full_b = [&](int s) { return bars_b + 8u * s; };
+    auto empty_b = [&](int s) { return bars_b + 8u * (p.ring_b + s); };
+    const uint32_t bars_t = bars_b + 16u * p.ring_b;
+    auto tmem_full_bar = [&](int b) { return bars_t + 8u * b; };
+    auto tmem_empty_bar = [&](int b) { return bars_t + 16u + 8u * b; };
+    const uint32_t tmem_slot = bars_t + 32u;
+
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    // a unit = (N tile or sub-tile) x (group of NCTA consecutive M tiles); CTA `rank` of the cluster owns M tile group*NCTA+rank.
+    // A group that runs past the last M tile repeats it and discards the result (`real` = false).
+    auto decode = [&](int u, int& bimg, int& y0, int& x0, int& n0, int& n_cnt, bool& real) {
+        int t = u, sub = 0;
+        n_cnt = p.n_tile;
+        if (u >= p.full_units) {
+            const int v = u - p.full_units;
+            t = p.full_units + v / p.split; sub = v - (v / p.split) * p.split;
+            n_cnt = p.n_sub;
+        }
+        const int n_idx = t / p.m_groups;
+        int m_idx = (t - n_idx * p.m_groups) * NCTA + (int)rank;
+        real = m_idx < p.m_tiles;
+        if (!real) m_idx = p.m_tiles - 1;
+        bimg = m_idx / tiles_per_img;
+        const int trem = m_idx - bimg * tiles_per_img;
+        y0 = (trem / p.tiles_x) * TILE_ROWS; x0 = (trem % p.tiles_x) * TILE_COLS;
+        n0 = n_idx * p.n_tile + sub * p.n_sub;
+    };
+    const int unit0 = (int)blockIdx.x / NCTA, unit_step = (int)gridDim.x / NCTA;
+    const int outer_taps = p.a_taps == p.kh ? 1 : p.kh;       // vertical taps that need an activation box of their own
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.ring_a; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
+        for (int s = 0; s < p.ring_b; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 256 * NCTA); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        if (NCTA == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    if (NCTA == 2) cluster_sync_all(); else __syncthreads();      // the peer's barriers exist before anything signals them
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer (every CTA; the leader arms the full barriers)
+            int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+            const uint32_t a_tx = (uint32_t)NCTA * a_slot;
+            for (int u = unit0; u < p.total_units; u += unit_step) {
+                int bimg, y0, x0, n0, n_cnt; bool real;
+                decode(u, bimg, y0, x0, n0, n_cnt, real);
+                const bool whole = n_cnt == p.n_tile;
+                const CUtensorMap* bh = whole ? &p.b_hi : &p.bs_hi;
+                const CUtensorMap* bl = whole ? &p.b_lo : &p.bs_lo;
+                const int b_rows = n_cnt / NCTA;
+                const uint32_t b_tx = (uint32_t)NCTA * 2u * (uint32_t)b_rows * 128u;
+                const int nb0 = n0 + (int)rank * b_rows;
+                for (int kyo = 0; kyo < outer_taps; ++kyo) {
+                    const int ys = y0 + kyo - (p.kh >> 1);
+                    for (int kx = 0; kx < p.kw; ++kx) {
+                        const int xs = x0 + kx - (p.kw >> 1);
+                        for (int a = 0; a < p.n_active; ++a) {
+                            const int cc = p.chunk_list[a];
+                            const int seg = cc >= p.seg0_chunks ? 1 : 0;
+                            const int c0 = (seg ? cc - p.seg0_chunks : cc) * BKC;
+                            const uint32_t da = a_ring + (uint32_t)sa * a_slot;
+                            mbar_wait(empty_a(sa), pha ^ 1u);
+                            if (NCTA == 2) {
+                                const uint32_t fb = mapa_rank(full_a(sa), 0);
+                                if (rank == 0) mbar_expect_tx(full_a(sa), a_tx);
+                                tma_load_4d_pair(&p.a_hi[seg], da, fb, c0, xs, ys, bimg);
+                                tma_load_4d_pair(&p.a_lo[seg], da + a_plane, fb, c0, xs, ys, bimg);
+                            } else {
+                                mbar_expect_tx(full_a(sa), a_tx);
+                                tma_load_4d(&p.a_hi[seg], da, full_a(sa), c0, xs, ys, bimg);
+                                tma_load_4d(&p.a_lo[seg], da + a_plane, full_a(sa), c0, xs, ys, bimg);
+                            }
+                            if (++sa == p.ring_a) { sa = 0; pha ^= 1u; }
+                            for (int j = 0; j < p.a_taps; ++j) {
+                                const int tap = (kyo + j) * p.kw + kx;
+                                const uint32_t db = b_ring + (uint32_t)sb * b_slot;
+                                mbar_wait(empty_b(sb), phb ^ 1u);
+                                if (NCTA == 2) {
+                                    const uint32_t fb = mapa_rank(full_b(sb), 0);
+                                    if (rank == 0) mbar_expect_tx(full_b(sb), b_tx);
+                                    tma_load_3d_pair(bh, db, fb, cc * BKC, nb0, tap);
+                                    tma_load_3d_pair(bl, db + b_plane, fb, cc * BKC, nb0, tap);
+                                } else {
+                                    mbar_expect_tx(full_b(sb), b_tx);
+                                    tma_load_3d(bh, db, full_b(sb), cc * BKC, nb0, tap);
+                                    tma_load_3d(bl, db + b_plane, full_b(sb), cc * BKC, nb0, tap);
+                                }
+                                if (++sb == p.ring_b) { sb = 0; phb ^= 1u; }
+                            }
+                        }
+                    }
+                }
+            }
+            // drain: every commit aimed at this CTA's empty barriers has landed before the CTA may exit
+            for (int i = 0; i < p.ring_a; ++i) { mbar_wait(empty_a(sa), pha ^ 1u); if (++sa == p.ring_a) { sa = 0; pha ^= 1u; } }
+            for (int i = 0; i < p.ring_b; ++i) { mbar_wait(empty_b(sb), phb ^ 1u); if (++sb == p.ring_b) { sb = 0; phb ^= 1u; } }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ------------------------------------------------ MMA issuer (leader CTA only)
+            const uint32_t m_field = ((128u * NCTA) >> 4) << 24;
+            const uint32_t idesc_whole = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | m_field;
+            const uint32_t idesc_sub = (1u << 4) | ((uint32_t)(p.n_sub >> 3) << 17) | m_field;
+            const int a_items = outer_taps * p.kw * p.n_active;
+            uint32_t tile_iter = 0;
+            int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+            for (int u = unit0; u < p.total_units; u += unit_step, ++tile_iter) {
+                const uint32_t idesc = u < p.full_units ? idesc_whole : idesc_sub;
+                const int buf = tile_iter & 1;
+                const uint32_t acc = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
+                mbar_wait(tmem_empty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // the epilogues (both CTAs) drained this buffer
+                tc_fence_after();
+                uint32_t accumulate = 0;
+                for (int ai = 0; ai < a_items; ++ai) {
+                    mbar_wait(full_a(sa), pha);
+                    tc_fence_after();
+                    const uint32_t da = a_ring + (uint32_t)sa * a_slot;
+                    for (int j = 0; j < p.a_taps; ++j) {
+                        mbar_wait(full_b(sb), phb);
+                        tc_fence_after();
+                        const uint32_t db = b_ring + (uint32_t)sb * b_slot;
+                        const uint64_t a_hi = umma_desc_sw128(da + (uint32_t)j * 1024u);
+                        const uint64_t a_lo = umma_desc_sw128(da + a_plane + (uint32_t)j * 1024u);
+                        const uint64_t b_hi = umma_desc_sw128(db), b_lo = umma_desc_sw128(db + b_plane);
+#pragma unroll
+                        for (int k = 0; k < BKC / 16; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 2);
+                            if (NCTA == 2) {
+                                tc_mma_f16_pair(acc, a_lo + adv, b_hi + adv, idesc, accumulate);
+                                tc_mma_f16_pair(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                                tc_mma_f16_pair(acc, a_hi + adv, b_hi + adv, idesc, 1u);
+                            } else {
+                                tc_mma_f16(acc, a_lo + adv, b_hi + adv, idesc, accumulate);
+                                tc_mma_f16(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                                tc_mma_f16(acc, a_hi + adv, b_hi + adv, idesc, 1u);
+                            }
+                            accumulate = 1u;
+                        }
+                        if (NCTA == 2) tc_commit_pair(empty_b(sb)); else tc_commit(empty_b(sb));
+                        if (++sb == p.ring_b) { sb = 0; phb ^= 1u; }
+                    }
+                    if (NCTA == 2) tc_commit_pair(empty_a(sa)); else tc_commit(empty_a(sa));
+                    if (++sa == p.ring_a) { sa = 0; pha ^= 1u; }
+                }
+                if (NCTA == 2) tc_commit_pair(tmem_full_bar(buf)); else tc_commit(tmem_full_bar(buf));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------- epilogue (every CTA, its own 128 accumulator lanes)
+        const int q = warp & 3;
+        const int mrow = q * 32 + lane;
+        uint32_t tile_iter = 0;
+        for (int u = unit0; u < p.total_units; u += unit_step, ++tile_iter) {
+            int bimg, y0, x0, n0, n_cnt; bool real;
+            decode(u, bimg, y0, x0, n0, n_cnt, real);
+            const int buf = tile_iter & 1;
+            const int yy = y0 + (mrow >> 3), xx = x0 + (mrow & 7);
+            const bool valid = real && yy < p.h && xx < p.w;
+            const size_t pix = ((size_t)bimg * p.h + yy) * p.w + xx;
+            mbar_wait_backoff(tmem_full_bar(buf), (tile_iter >> 1) & 1);
+            tc_fence_after();
+            epilogue_columns(p, tmem_base, warp, q, buf, n0, n_cnt, valid, pix);
+            tc_fence_before();
+            if (NCTA == 2) mbar_arrive_cluster(mapa_rank(tmem_empty_bar(buf), 0));
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(buf)) : "memory");
+        }
+    }
+    tc_fence_before();
+    // nobody leaves while the peer may still read this CTA's shared memory or signal its barriers
+    if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) {
+        if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -443,13 +719,13 @@ int cached_map(CUtensorMap* m, const MapKey& key, Make make) {
     return 0;
 }
 
-int make_act_map(CUtensorMap* m, const __half* base, int C, int pitch, int B, int h, int w) {
-    return cached_map(m, MapKey{base, {C, pitch, B, h, w, -1}}, [&](CUtensorMap* out) -> int {
+int make_act_map(CUtensorMap* m, const __half* base, int C, int pitch, int B, int h, int w, int box_rows = TILE_ROWS) {
+    return cached_map(m, MapKey{base, {C, pitch, B, h, w, -box_rows}}, [&](CUtensorMap* out) -> int {
         EncodeTiledFn enc = get_encode();
         if (!enc) return (int)cudaErrorNotSupported;
         cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
         cuuint64_t gstr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)w * pitch * 2, (cuuint64_t)h * w * pitch * 2};
-        cuuint32_t box[4] = {BKC, TILE_COLS, TILE_ROWS, 1};
+        cuuint32_t box[4] = {BKC, TILE_COLS, (cuuint32_t)box_rows, 1};
         cuuint32_t est[4] = {1, 1, 1, 1};
         CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -482,6 +758,8 @@ int device_sms() {
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
         if (cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(conv_umma2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(conv_umma2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
         sms_of[dev] = sms; done[dev] = true;
     }
     return sms_of[dev];
@@ -489,6 +767,80 @@ int device_sms() {
 
 // smallest channel count of a split unit (0 disables splitting); B200POSE_TAIL_MIN_N overrides it for experiments
 int g_tail_min_n = []() { const char* e = getenv("B200POSE_TAIL_MIN_N"); return e ? atoi(e) : 32; }();
+
+// Kernel selection, B200POSE_CONV_MODE (read at every launch so that tests can switch): bit 0 = CTA pairs
+// (tcgen05.mma.cta_group::2), bit 1 = vertical-tap reuse of the activation box; 0 = first-generation kernel; unset = default.
+constexpr int kDefaultConvMode = 0;
+int conv_mode() {
+    const char* e = getenv("B200POSE_CONV_MODE");
+    return e && *e ? atoi(e) : kDefaultConvMode;
+}
+
+template <typename... KArgs>
+cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), int grid, int cluster, size_t smem, cudaStream_t s, const UmmaConvParams& p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cluster; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = cluster > 1 ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
+// Second-generation launch (conv_umma2_kernel).  ncta = 2: units are CTA pairs.
+int launch_conv_umma2(const UmmaConvArgs& a, UmmaConvParams& p, int ncta, bool reuse_v, int sms, cudaStream_t s) {
+    int rc;
+    const int taps = a.kh * a.kw;
+    // rings: one activation slot serves a_taps weight slots; without reuse the two rings advance together
+    const int b_slot = 2 * (a.n_tile / ncta) * 128, budget = 222 * 1024;
+    p.a_taps = reuse_v ? a.kh : 1;
+    p.a_rows = TILE_ROWS + p.a_taps - 1;
+    p.ring_a = 2;
+    p.ring_b = (budget - p.ring_a * 2 * p.a_rows * 1024) / b_slot;
+    if (p.a_taps > 1 && p.ring_b < 2) { p.a_taps = 1; p.a_rows = TILE_ROWS; }     // the halo box does not fit: plain boxes
+    if (p.a_taps == 1) {
+        int st = budget / (2 * A_TILE_BYTES + b_slot);
+        p.ring_a = p.ring_b = st > 6 ? 6 : st;
+    } else if (p.ring_b > 6) {
+        p.ring_b = 6;
+    }
+    if (p.ring_a < 2 || p.ring_b < 2) return -1;
+    for (int g = 0; g < 2; ++g) {
+        if (a.seg_c[g] == 0) { p.a_hi[g] = p.a_hi[0]; p.a_lo[g] = p.a_lo[0]; continue; }
+        if ((rc = make_act_map(&p.a_hi[g], a.seg_hi[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.a_rows))) return rc;
+        if ((rc = make_act_map(&p.a_lo[g], a.seg_lo[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.a_rows))) return rc;
+    }
+    if ((rc = make_wgt_map(&p.b_hi, a.w_hi, a.cin_pad, a.cout_pad, taps, a.n_tile / ncta))) return rc;
+    if ((rc = make_wgt_map(&p.b_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, a.n_tile / ncta))) return rc;
+    const size_t smem = (size_t)p.ring_a * (2 * p.a_rows * 1024) + (size_t)p.ring_b * (2 * (a.n_tile / ncta) * 128) + 1024 +
+                        16 * (p.ring_a + p.ring_b) + 64;
+    p.m_groups = ceil_div(p.m_tiles, ncta);
+    p.total_tiles = p.m_groups * (a.cout_pad / a.n_tile);
+    const int slots = sms / ncta;                                    // clusters resident at once
+    int nclusters = p.total_tiles < slots ? p.total_tiles : slots;
+    p.full_units = p.total_tiles; p.total_units = p.total_tiles; p.split = 1; p.n_sub = a.n_tile;
+    const int tail = p.total_tiles < slots ? p.total_tiles : p.total_tiles % slots;
+    if (tail && g_tail_min_n > 0) {
+        for (int sp = a.n_tile / g_tail_min_n; sp >= 2; --sp) {
+            if (a.n_tile % sp || (a.n_tile / sp) % 32 || tail * sp > slots) continue;
+            p.split = sp; p.n_sub = a.n_tile / sp;
+            p.full_units = p.total_tiles - tail; p.total_units = p.full_units + tail * sp;
+            if (p.total_units < slots) nclusters = p.total_units;
+            break;
+        }
+    }
+    p.bs_hi = p.b_hi; p.bs_lo = p.b_lo;
+    if (p.split > 1) {
+        if ((rc = make_wgt_map(&p.bs_hi, a.w_hi, a.cin_pad, a.cout_pad, taps, p.n_sub / ncta))) return rc;
+        if ((rc = make_wgt_map(&p.bs_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, p.n_sub / ncta))) return rc;
+    }
+    if (ncta == 2) B2P_CUDA(launch_pdl_cluster(conv_umma2_kernel<2>, nclusters * 2, 2, smem, s, p));
+    else B2P_CUDA(launch_pdl_cluster(conv_umma2_kernel<1>, nclusters, 1, smem, s, p));
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
 
 }  // namespace
 
@@ -526,6 +878,14 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     p.m_tiles = a.B * p.tiles_x * p.tiles_y;
     p.total_tiles = p.m_tiles * (a.cout_pad / a.n_tile);
     p.b_batched = a.b_batched;
+    // second-generation kernel (see conv_mode): not for the batched-weight volume GEMM (a pair of M tiles may straddle two
+    // samples); CTA pairs only when the problem fills the machine (they halve the number of schedulable units)
+    const int mode = a.b_batched ? 0 : conv_mode();
+    if (mode) {
+        const bool pair = (mode & 1) && p.total_tiles >= sms && (a.n_tile % 32) == 0;
+        const bool reuse_v = (mode & 2) && a.kh > 1;
+        if (pair || reuse_v) return launch_conv_umma2(a, p, pair ? 2 : 1, reuse_v, sms, s);
+    }
     int grid = p.total_tiles < sms ? p.total_tiles : sms;            // persistent: one CTA per SM
     // split the tiles of the last partial round (see UmmaConvParams): the largest split whose units still fit one round.
     // A problem with fewer tiles than SMs (small batches) is one partial round: all of its tiles are split.

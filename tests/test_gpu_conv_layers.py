@@ -98,3 +98,36 @@ def test_corr_pyramid_tensor_core_vs_oracle(ops, shape):
         assert lv[l].shape == ref[l].shape
         err = (lv[l].cpu() - ref[l]).abs().max().item()
         assert err <= 2e-5 * ref[l].abs().max().item() + 1e-5, (l, err)
+
+
+# Second-generation tensor-core kernel (conv_umma2_kernel): B200POSE_CONV_MODE bit 0 = CTA pairs (cta_group::2, only taken
+# when the problem has at least one tile per SM), bit 1 = vertical-tap reuse of the activation box.  Shapes: few tiles
+# (every tile split), 320 M tiles (B=32 at 30x40: several persistent rounds + split tail) and an odd tile count (153: the
+# last pair has a dummy half).
+_REF_CACHE = {}
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["pair", "vreuse", "pair+vreuse"])
+@pytest.mark.parametrize("layer", sorted(LAYERS))
+@pytest.mark.parametrize("shape", [(2, 9, 12), (32, 30, 40), (51, 16, 20)], ids=["2x9x12", "32x30x40", "51x16x20"])
+def test_conv_layer_second_generation(ops, packed, layer, shape, mode, monkeypatch):
+    wts = load_update_weights()
+    keys, pad = LAYERS[layer]
+    W = torch.cat([wts[k + ".weight"] for k in keys], 0)
+    bias = torch.cat([wts[k + ".bias"] for k in keys], 0)
+    B, h, w = shape
+    cin0, cin1, cout, kh, kw = ops.conv_layer_info(layer)
+    if (layer, shape) not in _REF_CACHE:                    # the CPU reference is shared by the three kernel variants
+        x = S.hash_features((B, cin0 + cin1, h, w), 200 + layer, 1.5)
+        _REF_CACHE.clear()
+        _REF_CACHE[(layer, shape)] = (x, F.conv2d(x, W, bias, padding=pad))
+    x, ref = _REF_CACHE[(layer, shape)]
+    in0 = to_pxc(x[:, :cin0]).to(dev())
+    in1 = to_pxc(x[:, cin0:]).to(dev()) if cin1 else None
+    monkeypatch.setenv("B200POSE_CONV_MODE", str(mode))
+    out = ops.conv_layer(packed, layer, in0, in1, B, h, w, flags=1)
+    torch.cuda.synchronize()
+    got = from_pxc(out[:, :cout].contiguous(), B, h, w).cpu()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    assert err <= 4e-5 * scale + 1e-5, f"layer {layer} mode {mode}: max err {err} (scale {scale})"

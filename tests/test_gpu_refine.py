@@ -74,6 +74,19 @@ def test_refine_matches_reference_golden(ops, packed, name, flags):
             assert abs(a.item() - b.item()) / sc.diameter < 5e-5
 
 
+@pytest.mark.parametrize("conv_mode", [1, 2, 3], ids=["pair", "vreuse", "pair+vreuse"])
+def test_refine_golden_240x320_second_generation_kernels(ops, packed, conv_mode, monkeypatch):
+    """The executed reference's 240x320 4x3 result through the second-generation convolution kernel variants."""
+    monkeypatch.setenv("B200POSE_CONV_MODE", str(conv_mode))
+    g = golden("refine_240x320_4x3.npz")
+    H, W, n_iters, n_lm, seed, occl = [int(v) for v in g["meta"]]
+    mb = S.make_batch([int(i) for i in g["idxs"]], H, W, seed, bool(occl), with_images=False)
+    res = run_gpu(ops, packed, T(g["fmap1"]), T(g["fmap2"]), mb, T(g["G0"]), n_iters, n_lm, flags=1)
+    err = (torch.matmul(res["G"].cpu(), mb["T_init"]) - T(g["Ti_pred"])).abs().max().item()
+    print(f"[parity] 240x320 4x3 conv_mode={conv_mode}: max |dSE3| vs executed reference = {err:.3e}")
+    assert err < SE3_TOL
+
+
 def test_refine_batched_vs_oracle(ops, packed):
     """A native batch of 3 different scenes equals three oracle (= reference B=1) runs."""
     H, W, idxs = 128, 160, [7, 8, 9]
@@ -87,9 +100,13 @@ def test_refine_batched_vs_oracle(ops, packed):
     torch.testing.assert_close(res["flow_last"].cpu(), ref["flows"][-1], rtol=1e-3, atol=2e-2)
 
 
-def test_refine_full_size_batch_properties(ops, packed):
+@pytest.mark.parametrize("conv_mode", [None, 0, 1, 2, 3], ids=["default", "gen1", "pair", "vreuse", "pair+vreuse"])
+def test_refine_full_size_batch_properties(ops, packed, conv_mode, monkeypatch):
     """BASELINE configs[1] shape (B=32, 240x320, 4x3): per-sample results do not depend on batch position or
-    batch size (bit-exact), outputs are finite rigid transforms, and a subset agrees with the oracle."""
+    batch size (bit-exact), outputs are finite rigid transforms, and a subset agrees with the oracle.  Run for every
+    tensor-core convolution kernel variant (B200POSE_CONV_MODE, conv_umma.cu)."""
+    if conv_mode is not None:
+        monkeypatch.setenv("B200POSE_CONV_MODE", str(conv_mode))
     H, W, B = 240, 320, 32
     uniq = S.make_batch([0, 1, 2, 3], H, W, with_images=False)
     rep = {k: v.repeat(8, *([1] * (v.dim() - 1))) for k, v in uniq.items() if k != "diameter"}
@@ -106,7 +123,8 @@ def test_refine_full_size_batch_properties(ops, packed):
     # batch of 1 == slot 0 of the batch of 32
     one = {k: v[:1].contiguous() for k, v in uniq.items() if k != "diameter"}
     G1 = run_gpu(ops, packed, f1u[:1], f2u[:1], one, G0[:1], 4, 3)["G"].cpu()
-    assert torch.equal(G1[0], G[0])
+    # (the CTA-pair kernel is only taken for machine-filling problems, so B=1 and B=32 may run M=128 and M=256 MMAs)
+    assert torch.equal(G1[0], G[0]) or (conv_mode in (1, 3) and (G1[0] - G[0]).abs().max().item() < 1e-6)
     # oracle on two of the samples
     sub = {k: v[:2].contiguous() for k, v in uniq.items() if k != "diameter"}
     ref = O.refine_inner_loop(load_update_weights(), f1u[:2], f2u[:2], sub["context"], sub["geofea1"], sub["geofea2"],
