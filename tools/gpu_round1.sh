@@ -4,14 +4,14 @@ mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt 2>&1
 echo "== conv second generation tests" > gpurun_out/r.log
-timeout 900 python -m pytest tests/test_gpu_conv_layers.py -q -k second_generation -x 2>&1 | tail -15 >> gpurun_out/r.log
+timeout 600 python -m pytest tests/test_gpu_conv_layers.py -q -k second_generation --tb=line 2>&1 | tail -40 >> gpurun_out/r.log
 echo "== timing per mode" >> gpurun_out/r.log
 for m in 0 1 2 3; do
   echo "-- mode $m" >> gpurun_out/r.log
   B200POSE_CONV_MODE=$m timeout 300 python tools/profile_step.py --time --passes 2 2>&1 | tail -3 >> gpurun_out/r.log
 done
 echo "== full gpu suite" >> gpurun_out/r.log
-timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 >> gpurun_out/r.log
+timeout 700 python -m pytest tests -q -m gpu -x -k "not second_generation" --durations=8 2>&1 | tail -25 >> gpurun_out/r.log
 echo "== launch list mode 3" >> gpurun_out/r.log
 B200POSE_CONV_MODE=3 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 70 -c 110 --csv --log-file gpurun_out/launches_mode3.csv python tools/profile_step.py --passes 3 > gpurun_out/ncu_launch.log 2>&1
 tail -2 gpurun_out/ncu_launch.log >> gpurun_out/r.log
