@@ -91,11 +91,11 @@ int run_update_block(const float* wts, float* net, float* xbuf, const float* cor
     if ((rc = conv(CV_Q2, u.rhbuf, 128, 128, xbuf, 256, 256, nullptr, 0, EPI_GRU_Q, 1.f))) return rc;
     // heads (update.py:13-14, 172-176, 187)
     if ((rc = conv(CV_HEADS, net, 128, 128, nullptr, 0, 0, u.hm, 512, EPI_RELU, 1.f))) return rc;
-    if ((rc = b2p_flow_head2(u.hm, nullptr, nullptr, wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, B, h, w, s))) return rc;
+    if ((rc = b2p_flow_head2(u.hm, nullptr, nullptr, wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, u.col, B, h, w, s))) return rc;
     if ((rc = conv(CV_MASK2, u.hm + 256, 512, 256, nullptr, 0, 0, mask, 576, EPI_SCALE, 0.25f))) return rc;
     return 0;
 }
-constexpr int UPDATE_LAUNCHES = 13;
+constexpr int UPDATE_LAUNCHES = 14;     // im2col, 11 convolutions, flow-head partial + gather
 
 // ------------------------------------------------------------------------------------------------
 // tensor-core path (tcgen05, fp16 hi/lo operands).  Expects u.corr_h, u.net_h and u.x_h[:, 0:128] filled.
@@ -115,6 +115,7 @@ int run_update_block_tc(const float* wts, float* net, float* coords1, float* flo
         const B2PHalfConvDesc& d = HL.cv[id];
         UmmaConvArgs a;
         memset(&a, 0, sizeof(a));
+        a.layer_id = id;
         if (pre) { a.pre = pre; a.pre_pitch = pre_pitch; a.chunk_mask = 0x33u; }     // chunks {0,1,4,5}: h and motion
         a.seg_hi[0] = s0[0] + off0; a.seg_lo[0] = s0[1] + off0; a.seg_c[0] = c0; a.seg_pitch[0] = p0;
         if (s1) { a.seg_hi[1] = s1[0]; a.seg_lo[1] = s1[1]; a.seg_c[1] = c1n; a.seg_pitch[1] = p1; }
@@ -139,7 +140,7 @@ int run_update_block_tc(const float* wts, float* net, float* coords1, float* flo
     if ((rc = conv(CV_ZR2, u.net_h, 0, 128, 128, u.x_h, 256, 256, u.rh_h, 0, 128, EPI_GRU_ZR, 1.f, nullptr, 0, pz2, 256))) return rc;
     if ((rc = conv(CV_Q2, u.rh_h, 0, 128, 128, u.x_h, 256, 256, u.net_h, 0, 128, EPI_GRU_Q, 1.f, nullptr, 0, pq2, 128))) return rc;
     if ((rc = conv(CV_HEADS, u.net_h, 0, 128, 128, nullptr, 0, 0, u.hm_h, 0, 512, EPI_RELU, 1.f, nullptr, 0))) return rc;
-    if ((rc = b2p_flow_head2(nullptr, u.hm_h[0], u.hm_h[1], wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, B, h, w, s))) return rc;
+    if ((rc = b2p_flow_head2(nullptr, u.hm_h[0], u.hm_h[1], wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, u.col, B, h, w, s))) return rc;
     if ((rc = conv(CV_MASK2, u.hm_h, 256, 256, 512, nullptr, 0, 0, nullptr, 0, 0, EPI_SCALE, 0.25f, mask, 576))) return rc;
     return 0;
 }
@@ -162,6 +163,7 @@ int run_gru_precompute(const float* wts, int B, int h, int w, const UpdateWs& u,
         a.B = B; a.h = h; a.w = w; a.epi = EPI_SCALE; a.scale = 1.f;
         a.out_f32 = u.pre[k]; a.out_f32_pitch = d.cout;
         a.chunk_mask = 0x0Cu;                                     // chunks {2,3}: the inp channels
+        a.layer_id = ids[k];
         int rc = b2p_launch_conv_umma(a, s);
         if (rc) return rc;
     }
@@ -216,7 +218,7 @@ int run_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int h, int
     UmmaConvArgs a;
     memset(&a, 0, sizeof(a));
     a.seg_hi[0] = v.fm_h[0]; a.seg_lo[0] = v.fm_h[1]; a.seg_c[0] = 256; a.seg_pitch[0] = 256;
-    a.w_hi = v.fm_h[2]; a.w_lo = v.fm_h[3]; a.bias = v.zero_bias; a.b_batched = B;
+    a.w_hi = v.fm_h[2]; a.w_lo = v.fm_h[3]; a.bias = v.zero_bias; a.b_batched = B; a.layer_id = -1;
     a.cin_pad = 256; a.cout_pad = P; a.cout = P; a.n_tile = nt; a.kh = 1; a.kw = 1;
     a.B = B; a.h = h; a.w = w; a.epi = EPI_SCALE; a.scale = 0.0625f;     // 1/sqrt(256), exact
     a.out_f32 = level0; a.out_f32_pitch = P;
@@ -404,6 +406,7 @@ int b200pose_conv_layer(const void* packed_weights, int layer, const float* in0,
     a.w_hi = hbase + hd.hi_off; a.w_lo = hbase + hd.lo_off; a.bias = wts + d.b_off;
     a.cin_pad = hd.cin_pad; a.cout_pad = hd.cout_pad; a.cout = hd.cout; a.n_tile = hd.n_tile; a.kh = hd.kh; a.kw = hd.kw;
     a.B = B; a.h = h; a.w = w; a.epi = EPI_SCALE; a.scale = 1.f; a.out_f32 = out; a.out_f32_pitch = (cout + 3) / 4 * 4;
+    a.layer_id = layer;
     return b2p_launch_conv_umma(a, s);
 }
 

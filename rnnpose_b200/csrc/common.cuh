@@ -134,6 +134,7 @@ struct UmmaConvArgs {
     float* zbuf; float* hbuf;
     unsigned chunk_mask;       // bit cc set = visit 64-channel chunk cc of every tap (0 = all chunks)
     const float* pre; int pre_pitch;   // fp32 [P][pre_pitch] partial sums added in the epilogue (or nullptr)
+    int layer_id;              // B2PConvId of an update-block layer, or -1
     int b_batched;             // weights differ per sample: 3rd weight-map coordinate = sample index (1x1 only)
 };
 int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s);
@@ -155,7 +156,8 @@ int b2p_im2col_f1(const float* flow, int B, int h, int w, float* col /*[P][112]*
                   __half* col_hi, __half* col_lo, __half* x_hi, __half* x_lo, cudaStream_t s);
 int b2p_flow_head2(const float* hm /*[P][512] fp32, first 256 = flow-head features; or nullptr*/, const __half* hm_hi,
                    const __half* hm_lo, const float* w2, const float* b2, float* coords1 /*[P][2] in/out*/,
-                   float* flow /*[P][2] out = coords1 - coords0*/, float* dflow_out, int B, int h, int w, cudaStream_t s);
+                   float* flow /*[P][2] out = coords1 - coords0*/, float* dflow_out, float* part /*scratch [P][20]*/,
+                   int B, int h, int w, cudaStream_t s);
 int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth,
                         float sigma, int B, int C, int H, int W, float* flow_up, float* target, float* weight,
                         int lazy_background, cudaStream_t s);

@@ -776,6 +776,12 @@ int conv_mode() {
     return e && *e ? atoi(e) : kDefaultConvMode;
 }
 
+// experiment knobs (read per launch): ring budget in KB, PDL off, which layers may take the second-generation kernel
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
 template <typename... KArgs>
 cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), int grid, int cluster, size_t smem, cudaStream_t s, const UmmaConvParams& p) {
     cudaLaunchConfig_t cfg = {};
@@ -786,6 +792,10 @@ cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), int grid, int cluster, 
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = cluster; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = cluster > 1 ? 2 : 1;
+    if (env_int("B200POSE_V2_NOPDL", 0)) {            // plain stream-ordered launch
+        attr[0] = attr[1];
+        cfg.numAttrs = cluster > 1 ? 1 : 0;
+    }
     return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
@@ -794,7 +804,7 @@ int launch_conv_umma2(const UmmaConvArgs& a, UmmaConvParams& p, int ncta, bool r
     int rc;
     const int taps = a.kh * a.kw;
     // rings: one activation slot serves a_taps weight slots; without reuse the two rings advance together
-    const int b_slot = 2 * (a.n_tile / ncta) * 128, budget = 222 * 1024;
+    const int b_slot = 2 * (a.n_tile / ncta) * 128, budget = env_int("B200POSE_V2_BUDGET_KB", 222) * 1024;
     p.a_taps = reuse_v ? a.kh : 1;
     p.a_rows = TILE_ROWS + p.a_taps - 1;
     p.ring_a = 2;
@@ -880,11 +890,12 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     p.b_batched = a.b_batched;
     // second-generation kernel (see conv_mode): not for the batched-weight volume GEMM (a pair of M tiles may straddle two
     // samples); CTA pairs only when the problem fills the machine (they halve the number of schedulable units)
-    const int mode = a.b_batched ? 0 : conv_mode();
+    int mode = a.b_batched ? 0 : conv_mode();
+    if (mode && a.layer_id >= 0 && !((env_int("B200POSE_CONV_LAYERS", -1) >> a.layer_id) & 1)) mode = 0;
     if (mode) {
         const bool pair = (mode & 1) && p.total_tiles >= sms && (a.n_tile % 32) == 0;
         const bool reuse_v = (mode & 2) && a.kh > 1;
-        if (pair || reuse_v) return launch_conv_umma2(a, p, pair ? 2 : 1, reuse_v, sms, s);
+        if (pair || reuse_v || (mode & 4)) return launch_conv_umma2(a, p, pair ? 2 : 1, reuse_v, sms, s);
     }
     int grid = p.total_tiles < sms ? p.total_tiles : sms;            // persistent: one CTA per SM
     // split the tiles of the last partial round (see UmmaConvParams): the largest split whose units still fit one round.

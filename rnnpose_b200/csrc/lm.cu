@@ -336,9 +336,18 @@ __global__ void __launch_bounds__(LM_THREADS) lm_multi_kernel(
         }
         __syncthreads();
         if (tid < NACC) {
+            // same left-to-right order in every block; the loads of eight partials are in flight together
             double s = 0.0;
             const double* pp = partials + ((size_t)(step & 1) * B + b) * nb * NACC + tid;
-            for (int k = 0; k < nb; ++k) s += __ldcg(pp + (size_t)k * NACC);
+            int k = 0;
+            for (; k + 8 <= nb; k += 8) {
+                double v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __ldcg(pp + (size_t)(k + j) * NACC);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += v[j];
+            }
+            for (; k < nb; ++k) s += __ldcg(pp + (size_t)k * NACC);
             tot[tid] = s;
         }
         __syncthreads();

@@ -101,61 +101,97 @@ __global__ void __launch_bounds__(256) im2col_f1_kernel(const float* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(256) flow_head2_kernel(const float* __restrict__ hm, const __half* __restrict__ hm_hi,
-                                                         const __half* __restrict__ hm_lo, const float* __restrict__ w2,
-                                                         const float* __restrict__ b2, float* __restrict__ coords1,
-                                                         float* __restrict__ flow,
-                                                         float* __restrict__ dflow_out, int B, int h, int w) {
+// flow_head.conv2 (3x3, 256 -> 2, update.py:13-14) in two steps that read every feature vector once instead of nine times:
+//   (1) partial: for every SOURCE pixel the 18 dot products <features(src), W2[o][tap]> (4 lanes per pixel, 64 channels each,
+//       weights broadcast from shared memory), part[src][tap*2 + o];
+//   (2) gather: delta(y,x)[o] = b2[o] + sum_tap part[(y+ky-1, x+kx-1)][tap*2+o]  (zero padding = skipped taps), then
+//       coords1 += delta, flow = coords1 - coords0  (model/CFNet.py:157,166).
+constexpr int FH2_PITCH = 20;      // 18 partial sums per pixel, rows padded to 16-byte multiples
+
+__global__ void __launch_bounds__(256) flow_head2_partial_kernel(const float* __restrict__ hm, const __half* __restrict__ hm_hi,
+                                                                 const __half* __restrict__ hm_lo, const float* __restrict__ w2,
+                                                                 float* __restrict__ part, int npix) {
+    pdl_trigger();
+    __shared__ __align__(16) float ws[18][256];            // [tap*2+o][c]
+    for (int i = threadIdx.x; i < 18 * 256; i += blockDim.x) {
+        const int k = i >> 8, c = i & 255;
+        ws[k][c] = __ldg(w2 + ((k & 1) * 9 + (k >> 1)) * 256 + c);      // weights are not written by the previous kernel
+    }
+    __syncthreads();
+    pdl_wait();
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pix = gid >> 2, q = gid & 3;
+    const bool live = pix < npix;
+    float acc[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) acc[k] = 0.f;
+    if (live) {
+        const size_t so = (size_t)pix * 512;
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+            const int c = (it * 4 + q) * 8;                // the quad reads 64 contiguous bytes of each fp16 plane
+            float a[8];
+            if (hm) {
+                const float4 a0 = __ldg(reinterpret_cast<const float4*>(hm + so + c));
+                const float4 a1 = __ldg(reinterpret_cast<const float4*>(hm + so + c + 4));
+                a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            } else {
+                const uint4 uh = __ldg(reinterpret_cast<const uint4*>(hm_hi + so + c));
+                const uint4 ul = __ldg(reinterpret_cast<const uint4*>(hm_lo + so + c));
+                const __half2* hh = reinterpret_cast<const __half2*>(&uh);
+                const __half2* ll = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    a[2 * j] = __low2float(hh[j]) + __low2float(ll[j]);
+                    a[2 * j + 1] = __high2float(hh[j]) + __high2float(ll[j]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 18; ++k) {
+                const float4 u0 = *reinterpret_cast<const float4*>(&ws[k][c]);
+                const float4 u1 = *reinterpret_cast<const float4*>(&ws[k][c + 4]);
+                acc[k] += a[0] * u0.x + a[1] * u0.y + a[2] * u0.z + a[3] * u0.w + a[4] * u1.x + a[5] * u1.y + a[6] * u1.z + a[7] * u1.w;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 18; ++k) {
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
+    }
+    if (live && q == 0) {
+        float4* d = reinterpret_cast<float4*>(part + (size_t)pix * FH2_PITCH);
+        d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        d[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+        d[3] = make_float4(acc[12], acc[13], acc[14], acc[15]);
+        d[4] = make_float4(acc[16], acc[17], 0.f, 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(128) flow_head2_gather_kernel(const float* __restrict__ part, const float* __restrict__ b2,
+                                                                float* __restrict__ coords1, float* __restrict__ flow,
+                                                                float* __restrict__ dflow_out, int B, int h, int w) {
     pdl_trigger();
     pdl_wait();
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     const int hw = h * w;
-    if (warp >= B * hw) return;
-    const int b = warp / hw, r = warp - b * hw;
+    if (pix >= B * hw) return;
+    const int b = pix / hw, r = pix - b * hw;
     const int y = r / w, x = r - y * w;
-    float s0 = 0.f, s1 = 0.f;
+    float s0 = b2[0], s1 = b2[1];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
         const int sy = y + tap / 3 - 1, sx = x + tap % 3 - 1;
         if (sy < 0 || sy >= h || sx < 0 || sx >= w) continue;
-        const size_t so = ((size_t)(b * h + sy) * w + sx) * 512;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int c = half * 128 + lane * 4;
-            float4 a;
-            if (hm) {
-                a = __ldg(reinterpret_cast<const float4*>(hm + so + c));
-            } else {
-                const uint2 uh = __ldg(reinterpret_cast<const uint2*>(hm_hi + so + c));
-                const uint2 ul = __ldg(reinterpret_cast<const uint2*>(hm_lo + so + c));
-                const __half2 h0 = *reinterpret_cast<const __half2*>(&uh.x), h1 = *reinterpret_cast<const __half2*>(&uh.y);
-                const __half2 l0 = *reinterpret_cast<const __half2*>(&ul.x), l1 = *reinterpret_cast<const __half2*>(&ul.y);
-                a.x = __low2float(h0) + __low2float(l0); a.y = __high2float(h0) + __high2float(l0);
-                a.z = __low2float(h1) + __low2float(l1); a.w = __high2float(h1) + __high2float(l1);
-            }
-            const float4 u0 = __ldg(reinterpret_cast<const float4*>(w2 + (0 * 9 + tap) * 256 + c));
-            const float4 u1 = __ldg(reinterpret_cast<const float4*>(w2 + (1 * 9 + tap) * 256 + c));
-            s0 += a.x * u0.x + a.y * u0.y + a.z * u0.z + a.w * u0.w;
-            s1 += a.x * u1.x + a.y * u1.y + a.z * u1.z + a.w * u1.w;
-        }
+        const float2 v = __ldg(reinterpret_cast<const float2*>(part + ((size_t)(b * h + sy) * w + sx) * FH2_PITCH + tap * 2));
+        s0 += v.x; s1 += v.y;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    }
-    if (lane == 0) {
-        const float d0 = s0 + b2[0], d1 = s1 + b2[1];
-        if (dflow_out) { dflow_out[(size_t)warp * 2] = d0; dflow_out[(size_t)warp * 2 + 1] = d1; }
-        // coords1 = coords1 + delta ; flow_lr = coords1 - coords0  (model/CFNet.py:157,166)
-        const float c1x = coords1[(size_t)warp * 2] + d0;
-        const float c1y = coords1[(size_t)warp * 2 + 1] + d1;
-        coords1[(size_t)warp * 2] = c1x;
-        coords1[(size_t)warp * 2 + 1] = c1y;
-        flow[(size_t)warp * 2] = c1x - (float)x;
-        flow[(size_t)warp * 2 + 1] = c1y - (float)y;
-    }
+    if (dflow_out) { dflow_out[(size_t)pix * 2] = s0; dflow_out[(size_t)pix * 2 + 1] = s1; }
+    float2 c1 = *reinterpret_cast<float2*>(coords1 + (size_t)pix * 2);
+    c1.x += s0; c1.y += s1;
+    *reinterpret_cast<float2*>(coords1 + (size_t)pix * 2) = c1;
+    *reinterpret_cast<float2*>(flow + (size_t)pix * 2) = make_float2(c1.x - (float)x, c1.y - (float)y);
 }
 
 B2PWeightLayout make_layout() {
@@ -302,8 +338,12 @@ int b2p_im2col_f1(const float* flow, int B, int h, int w, float* col, float* xbu
 }
 
 int b2p_flow_head2(const float* hm, const __half* hm_hi, const __half* hm_lo, const float* w2, const float* b2,
-                   float* coords1, float* flow, float* dflow_out, int B, int h, int w, cudaStream_t s) {
-    B2P_CUDA(b2p_launch_pdl(flow_head2_kernel, dim3(ceil_div(B * h * w, 8)), dim3(256), 0, s, hm, hm_hi, hm_lo, w2, b2, coords1, flow, dflow_out, B, h, w));
+                   float* coords1, float* flow, float* dflow_out, float* part, int B, int h, int w, cudaStream_t s) {
+    const int npix = B * h * w;
+    B2P_CUDA(b2p_launch_pdl(flow_head2_partial_kernel, dim3(ceil_div(npix * 4, 256)), dim3(256), 0, s, hm, hm_hi, hm_lo, w2, part, npix));
+    B2P_LAUNCH_CHECK();
+    B2P_CUDA(b2p_launch_pdl(flow_head2_gather_kernel, dim3(ceil_div(npix, 128)), dim3(128), 0, s, (const float*)part, b2, coords1, flow,
+                            dflow_out, B, h, w));
     B2P_LAUNCH_CHECK();
     return 0;
 }
