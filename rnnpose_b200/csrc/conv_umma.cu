@@ -56,6 +56,8 @@ struct UmmaConvParams {
     int a_rows;                        // rows of the activation box = 16 + a_taps - 1
     int ring_a, ring_b;                // ring depths
     int m_groups;                      // M tiles / CTAs per cluster, rounded up (a unit = one group x one N tile)
+    int dbg_layer;                     // row of g_conv_dbg (layer id + 1)
+    int debug;                         // timing experiments only (results are garbage): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -140,7 +142,26 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
-__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+// one lane of a converged warp (the compiler keeps the surrounding loop in uniform registers and issues the tcgen05 / TMA
+// instructions directly, without the per-thread serialisation loop it emits inside an `if (lane == 0)` region)
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred;
+}
+// Branch-free gate functions of the tensor-core epilogue (ex2.approx + rcp.approx, ~3e-7 relative error).  The IEEE
+// expf / division / tanhf sequences carry a slow-path branch per element, which serialises the 32 elements of a column
+// group (~130 dependent clocks each) and made the GRU epilogues as long as their main loops.  The exact-fp32 path
+// (conv_gemm.cu) keeps the IEEE functions.
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float t = __expf(-2.0f * fabsf(x));               // in (0, 1]
+    return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+}
 
 // Epilogue of one tile for one warp: TMEM -> registers -> bias / activation / GRU blend -> global (fp32 side outputs and the
 // fp16 hi/lo planes the next convolution reads).  `valid` = this thread's pixel lies inside the image.
@@ -226,10 +247,10 @@ __device__ __forceinline__ void epilogue_columns(const UmmaConvParams& p, uint32
         } else if (p.epi == EPI_GRU_Q) {                   // h <- (1-z) h + z tanh(q)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                v[4 * j] = (1.f - zz[j].x) * hh[j].x + zz[j].x * tanhf(v[4 * j]);
-                v[4 * j + 1] = (1.f - zz[j].y) * hh[j].y + zz[j].y * tanhf(v[4 * j + 1]);
-                v[4 * j + 2] = (1.f - zz[j].z) * hh[j].z + zz[j].z * tanhf(v[4 * j + 2]);
-                v[4 * j + 3] = (1.f - zz[j].w) * hh[j].w + zz[j].w * tanhf(v[4 * j + 3]);
+                v[4 * j] = (1.f - zz[j].x) * hh[j].x + zz[j].x * tanh_fast(v[4 * j]);
+                v[4 * j + 1] = (1.f - zz[j].y) * hh[j].y + zz[j].y * tanh_fast(v[4 * j + 1]);
+                v[4 * j + 2] = (1.f - zz[j].z) * hh[j].z + zz[j].z * tanh_fast(v[4 * j + 2]);
+                v[4 * j + 3] = (1.f - zz[j].w) * hh[j].w + zz[j].w * tanh_fast(v[4 * j + 3]);
             }
             float4* hp4 = reinterpret_cast<float4*>(p.hbuf + pix * 128 + nb);
 #pragma unroll
@@ -255,6 +276,18 @@ __device__ __forceinline__ void epilogue_columns(const UmmaConvParams& p, uint32
             }
         }
     }
+}
+
+// Timing experiment (debug bit 16): per-CTA clock counters of the last launch.
+//   [0] MMA warp: clocks from first to last instruction of its loop   [1] ... spent waiting for full barriers
+//   [2] ... waiting for a drained TMEM buffer   [3] producer: waiting for empty slots   [4] epilogue warp 2: waiting for
+//   tmem_full   [5] epilogue warp 2: working   [6] tiles of this CTA   [7] stages of this CTA
+__device__ unsigned long long g_conv_dbg[12][160][8];      // [layer id + 1][CTA][counter], accumulated over launches
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, bool timed, unsigned long long& accum) {
+    if (!timed) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    accum += (unsigned long long)(clock64() - t0);
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
@@ -295,6 +328,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 256); }
+        mbar_init(tmem_slot + 16u, 1);           // scratch barrier of the commit-cost experiment (debug bit 8)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -310,63 +344,77 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     pdl_wait();                          // barriers and TMEM are set up; from here on the previous kernel's output is read
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------ TMA producer (runs ahead across tile boundaries)
-            // ring slot and phase are carried incrementally and the K loop is nested (tap, channel chunk): this thread is
-            // a single instruction stream, and the integer divisions of a flat K index cost more than a stage's MMAs
-            int s = 0; uint32_t ph = 0;
-            for (int t = blockIdx.x; t < p.total_units; t += gridDim.x) {
-                int bimg, y0, x0, n0, n_cnt;
-                decode(t, bimg, y0, x0, n0, n_cnt);
-                const bool whole = n_cnt == p.n_tile;
-                const CUtensorMap* bh = whole ? &p.b_hi : &p.bs_hi;
-                const CUtensorMap* bl = whole ? &p.b_lo : &p.bs_lo;
-                const uint32_t tx_bytes = 2u * A_TILE_BYTES + 2u * (uint32_t)n_cnt * 128u;
-                int tap = 0;
-                for (int ky = 0; ky < p.kh; ++ky) {
-                    const int ys = y0 + ky - (p.kh >> 1);
-                    for (int kx = 0; kx < p.kw; ++kx, ++tap) {
-                        const int xs = x0 + kx - (p.kw >> 1);
-                        const int b2 = p.b_batched ? bimg : tap;
-                        for (int a = 0; a < p.n_active; ++a) {
-                            const int cc = p.chunk_list[a];
-                            const int seg = cc >= p.seg0_chunks ? 1 : 0;
-                            const int c0 = (seg ? cc - p.seg0_chunks : cc) * BKC;
-                            const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-                            mbar_wait(empty_bar(s), ph ^ 1u);
-                            mbar_expect_tx(full_bar(s), tx_bytes);
-                            tma_load_4d(&p.a_hi[seg], sa, full_bar(s), c0, xs, ys, bimg);
-                            tma_load_4d(&p.a_lo[seg], sa + A_TILE_BYTES, full_bar(s), c0, xs, ys, bimg);
-                            tma_load_3d(bh, sa + 2 * A_TILE_BYTES, full_bar(s), cc * BKC, n0, b2);
-                            tma_load_3d(bl, sa + 2 * A_TILE_BYTES + b_tile_bytes, full_bar(s), cc * BKC, n0, b2);
-                            if (++s == p.stages) { s = 0; ph ^= 1u; }
+        // ------------------------------------------------ TMA producer (runs ahead across tile boundaries): warp-uniform loop,
+        // one elected lane issues.  Ring slot and phase are carried incrementally and the K loop is nested (tap, channel
+        // chunk): no integer divisions of a flat K index on the issue path.
+        int s = 0; uint32_t ph = 0;
+        const bool timed = (p.debug & 16) != 0;
+        unsigned long long w_empty = 0;
+        for (int t = blockIdx.x; t < p.total_units; t += gridDim.x) {
+            int bimg, y0, x0, n0, n_cnt;
+            decode(t, bimg, y0, x0, n0, n_cnt);
+            const bool whole = n_cnt == p.n_tile;
+            const CUtensorMap* bh = whole ? &p.b_hi : &p.bs_hi;
+            const CUtensorMap* bl = whole ? &p.b_lo : &p.bs_lo;
+            const uint32_t tx_bytes = 2u * A_TILE_BYTES + 2u * (uint32_t)n_cnt * 128u;
+            int tap = 0;
+            for (int ky = 0; ky < p.kh; ++ky) {
+                const int ys = y0 + ky - (p.kh >> 1);
+                for (int kx = 0; kx < p.kw; ++kx, ++tap) {
+                    const int xs = x0 + kx - (p.kw >> 1);
+                    const int b2 = p.b_batched ? bimg : tap;
+                    for (int a = 0; a < p.n_active; ++a) {
+                        const int cc = p.chunk_list[a];
+                        const int seg = cc >= p.seg0_chunks ? 1 : 0;
+                        const int c0 = (seg ? cc - p.seg0_chunks : cc) * BKC;
+                        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+                        mbar_wait_timed(empty_bar(s), ph ^ 1u, timed, w_empty);
+                        if (elect_one()) {
+                            if (p.debug & 1) {
+                                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_bar(s)) : "memory");
+                            } else {
+                                mbar_expect_tx(full_bar(s), tx_bytes);
+                                tma_load_4d(&p.a_hi[seg], sa, full_bar(s), c0, xs, ys, bimg);
+                                tma_load_4d(&p.a_lo[seg], sa + A_TILE_BYTES, full_bar(s), c0, xs, ys, bimg);
+                                tma_load_3d(bh, sa + 2 * A_TILE_BYTES, full_bar(s), cc * BKC, n0, b2);
+                                tma_load_3d(bl, sa + 2 * A_TILE_BYTES + b_tile_bytes, full_bar(s), cc * BKC, n0, b2);
+                            }
                         }
+                        __syncwarp();
+                        if (++s == p.stages) { s = 0; ph ^= 1u; }
                     }
                 }
             }
         }
+        if (timed && lane == 0) g_conv_dbg[p.dbg_layer][blockIdx.x][3] += w_empty;
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------ MMA issuer
-            // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=B=F16 (0), K-major both,
-            // N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc_whole = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t idesc_sub = (1u << 4) | ((uint32_t)(p.n_sub >> 3) << 17) | ((128u >> 4) << 24);
-            uint32_t tile_iter = 0;
-            int s = 0; uint32_t ph = 0;
-            for (int t = blockIdx.x; t < p.total_units; t += gridDim.x, ++tile_iter) {
-                const uint32_t idesc = t < p.full_units ? idesc_whole : idesc_sub;
-                const int buf = tile_iter & 1;
-                const uint32_t acc = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
-                mbar_wait(tmem_empty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // epilogue has drained this buffer
+        // ------------------------------------------------ MMA issuer: the whole warp walks the loop (uniform control flow and
+        // uniform-register descriptors), one elected lane issues
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=B=F16 (0), K-major both,
+        // N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc_whole = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc_sub = (1u << 4) | ((uint32_t)(p.n_sub >> 3) << 17) | ((128u >> 4) << 24);
+        uint32_t tile_iter = 0;
+        int s = 0; uint32_t ph = 0;
+        const bool timed = (p.debug & 16) != 0;
+        unsigned long long w_full = 0, w_tmem = 0, n_stage = 0;
+        const long long t_begin = clock64();
+        for (int t = blockIdx.x; t < p.total_units; t += gridDim.x, ++tile_iter) {
+            const uint32_t idesc = t < p.full_units ? idesc_whole : idesc_sub;
+            const int buf = tile_iter & 1;
+            const uint32_t acc = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
+            mbar_wait_timed(tmem_empty_bar(buf), ((tile_iter >> 1) & 1) ^ 1, timed, w_tmem);     // epilogue has drained this buffer
+            tc_fence_after();
+            for (int kc = 0; kc < nk; ++kc) {
+                mbar_wait_timed(full_bar(s), ph, timed, w_full);
+                ++n_stage;
                 tc_fence_after();
-                for (int kc = 0; kc < nk; ++kc) {
-                    mbar_wait(full_bar(s), ph);
-                    tc_fence_after();
-                    const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+                const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+                if (elect_one()) {
                     const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE_BYTES);
                     const uint64_t b_hi = umma_desc_sw128(sa + 2 * A_TILE_BYTES);
                     const uint64_t b_lo = umma_desc_sw128(sa + 2 * A_TILE_BYTES + b_tile_bytes);
+                    if (!(p.debug & 2))
 #pragma unroll
                     for (int k = 0; k < BKC / 16; ++k) {
                         const uint64_t adv = (uint64_t)(k * 2);   // 16 halves = 32 B = 2 x 16 B along K inside the swizzle atom
@@ -374,31 +422,44 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
                         tc_mma_f16(acc, a_hi + adv, b_lo + adv, idesc, 1u);
                         tc_mma_f16(acc, a_hi + adv, b_hi + adv, idesc, 1u);
                     }
+                    if (p.debug & 8) tc_commit(tmem_slot + 16u);     // experiment: cost of one more commit per stage
                     tc_commit(empty_bar(s));      // frees the smem stage when these MMAs have read it
-                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
-                tc_commit(tmem_full_bar(buf));    // accumulator of this tile complete
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
+            if (elect_one()) tc_commit(tmem_full_bar(buf));    // accumulator of this tile complete
+            __syncwarp();
+        }
+        if (timed && lane == 0) {
+            unsigned long long* d = g_conv_dbg[p.dbg_layer][blockIdx.x];
+            d[0] += (unsigned long long)(clock64() - t_begin); d[1] += w_full; d[2] += w_tmem; d[6] += tile_iter; d[7] += n_stage;
         }
     } else {
         // ---------------------------------------------------- epilogue: TMEM -> registers -> global
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
         const int mrow = q * 32 + lane;
         uint32_t tile_iter = 0;
+        const bool timed = (p.debug & 16) != 0 && warp == 2;
+        unsigned long long w_tfull = 0, busy = 0;
         for (int t = blockIdx.x; t < p.total_units; t += gridDim.x, ++tile_iter) {
         int bimg, y0, x0, n0, n_cnt;
         decode(t, bimg, y0, x0, n0, n_cnt);
         const int buf = tile_iter & 1;
+        const long long e0 = timed ? clock64() : 0;
         const int yy = y0 + (mrow >> 3), xx = x0 + (mrow & 7);
         const bool valid = yy < p.h && xx < p.w;
         const size_t pix = ((size_t)bimg * p.h + yy) * p.w + xx;
         mbar_wait_backoff(tmem_full_bar(buf), (tile_iter >> 1) & 1);
+        const long long e1 = timed ? clock64() : 0;
         tc_fence_after();
-        epilogue_columns(p, tmem_base, warp, q, buf, n0, n_cnt, valid, pix);
+        if (!(p.debug & 4)) epilogue_columns(p, tmem_base, warp, q, buf, n0, n_cnt, valid, pix);
+        if (timed) { w_tfull += (unsigned long long)(e1 - e0); busy += (unsigned long long)(clock64() - e1); }
         // every TMEM read of this tile has completed (tcgen05.wait::ld above): hand the buffer back to the MMA warp
         tc_fence_before();
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(buf)) : "memory");
         }   // tile loop
+        if (timed && lane == 0) { g_conv_dbg[p.dbg_layer][blockIdx.x][4] += w_tfull; g_conv_dbg[p.dbg_layer][blockIdx.x][5] += busy; }
     }
     tc_fence_before();
     __syncthreads();
@@ -532,30 +593,35 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
     pdl_wait();
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------ TMA producer (every CTA; the leader arms the full barriers)
-            int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
-            const uint32_t a_tx = (uint32_t)NCTA * a_slot;
-            for (int u = unit0; u < p.total_units; u += unit_step) {
-                int bimg, y0, x0, n0, n_cnt; bool real;
-                decode(u, bimg, y0, x0, n0, n_cnt, real);
-                const bool whole = n_cnt == p.n_tile;
-                const CUtensorMap* bh = whole ? &p.b_hi : &p.bs_hi;
-                const CUtensorMap* bl = whole ? &p.b_lo : &p.bs_lo;
-                const int b_rows = n_cnt / NCTA;
-                const uint32_t b_tx = (uint32_t)NCTA * 2u * (uint32_t)b_rows * 128u;
-                const int nb0 = n0 + (int)rank * b_rows;
-                for (int kyo = 0; kyo < outer_taps; ++kyo) {
-                    const int ys = y0 + kyo - (p.kh >> 1);
-                    for (int kx = 0; kx < p.kw; ++kx) {
-                        const int xs = x0 + kx - (p.kw >> 1);
-                        for (int a = 0; a < p.n_active; ++a) {
-                            const int cc = p.chunk_list[a];
-                            const int seg = cc >= p.seg0_chunks ? 1 : 0;
-                            const int c0 = (seg ? cc - p.seg0_chunks : cc) * BKC;
-                            const uint32_t da = a_ring + (uint32_t)sa * a_slot;
-                            mbar_wait(empty_a(sa), pha ^ 1u);
-                            if (NCTA == 2) {
+        // ------------------------------------------------ TMA producer (every CTA; the leader arms the full barriers).
+        // Warp-uniform loop, one elected lane issues.
+        int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+        const uint32_t a_tx = (uint32_t)NCTA * a_slot;
+        const bool timed = (p.debug & 16) != 0;
+        unsigned long long w_empty = 0;
+        for (int u = unit0; u < p.total_units; u += unit_step) {
+            int bimg, y0, x0, n0, n_cnt; bool real;
+            decode(u, bimg, y0, x0, n0, n_cnt, real);
+            const bool whole = n_cnt == p.n_tile;
+            const CUtensorMap* bh = whole ? &p.b_hi : &p.bs_hi;
+            const CUtensorMap* bl = whole ? &p.b_lo : &p.bs_lo;
+            const int b_rows = n_cnt / NCTA;
+            const uint32_t b_tx = (uint32_t)NCTA * 2u * (uint32_t)b_rows * 128u;
+            const int nb0 = n0 + (int)rank * b_rows;
+            for (int kyo = 0; kyo < outer_taps; ++kyo) {
+                const int ys = y0 + kyo - (p.kh >> 1);
+                for (int kx = 0; kx < p.kw; ++kx) {
+                    const int xs = x0 + kx - (p.kw >> 1);
+                    for (int a = 0; a < p.n_active; ++a) {
+                        const int cc = p.chunk_list[a];
+                        const int seg = cc >= p.seg0_chunks ? 1 : 0;
+                        const int c0 = (seg ? cc - p.seg0_chunks : cc) * BKC;
+                        const uint32_t da = a_ring + (uint32_t)sa * a_slot;
+                        mbar_wait_timed(empty_a(sa), pha ^ 1u, timed, w_empty);
+                        if (elect_one()) {
+                            if (p.debug & 1) {
+                                if (rank == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_a(sa)) : "memory");
+                            } else if (NCTA == 2) {
                                 const uint32_t fb = mapa_rank(full_a(sa), 0);
                                 if (rank == 0) mbar_expect_tx(full_a(sa), a_tx);
                                 tma_load_4d_pair(&p.a_hi[seg], da, fb, c0, xs, ys, bimg);
@@ -565,12 +631,17 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
                                 tma_load_4d(&p.a_hi[seg], da, full_a(sa), c0, xs, ys, bimg);
                                 tma_load_4d(&p.a_lo[seg], da + a_plane, full_a(sa), c0, xs, ys, bimg);
                             }
-                            if (++sa == p.ring_a) { sa = 0; pha ^= 1u; }
-                            for (int j = 0; j < p.a_taps; ++j) {
-                                const int tap = (kyo + j) * p.kw + kx;
-                                const uint32_t db = b_ring + (uint32_t)sb * b_slot;
-                                mbar_wait(empty_b(sb), phb ^ 1u);
-                                if (NCTA == 2) {
+                        }
+                        __syncwarp();
+                        if (++sa == p.ring_a) { sa = 0; pha ^= 1u; }
+                        for (int j = 0; j < p.a_taps; ++j) {
+                            const int tap = (kyo + j) * p.kw + kx;
+                            const uint32_t db = b_ring + (uint32_t)sb * b_slot;
+                            mbar_wait_timed(empty_b(sb), phb ^ 1u, timed, w_empty);
+                            if (elect_one()) {
+                                if (p.debug & 1) {
+                                    if (rank == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_b(sb)) : "memory");
+                                } else if (NCTA == 2) {
                                     const uint32_t fb = mapa_rank(full_b(sb), 0);
                                     if (rank == 0) mbar_expect_tx(full_b(sb), b_tx);
                                     tma_load_3d_pair(bh, db, fb, cc * BKC, nb0, tap);
@@ -580,87 +651,107 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
                                     tma_load_3d(bh, db, full_b(sb), cc * BKC, nb0, tap);
                                     tma_load_3d(bl, db + b_plane, full_b(sb), cc * BKC, nb0, tap);
                                 }
-                                if (++sb == p.ring_b) { sb = 0; phb ^= 1u; }
                             }
+                            __syncwarp();
+                            if (++sb == p.ring_b) { sb = 0; phb ^= 1u; }
                         }
                     }
                 }
             }
-            // drain: every commit aimed at this CTA's empty barriers has landed before the CTA may exit
-            for (int i = 0; i < p.ring_a; ++i) { mbar_wait(empty_a(sa), pha ^ 1u); if (++sa == p.ring_a) { sa = 0; pha ^= 1u; } }
-            for (int i = 0; i < p.ring_b; ++i) { mbar_wait(empty_b(sb), phb ^ 1u); if (++sb == p.ring_b) { sb = 0; phb ^= 1u; } }
         }
-        __syncwarp();
+        if (timed && lane == 0) g_conv_dbg[p.dbg_layer][blockIdx.x][3] += w_empty;
+        // drain: every commit aimed at this CTA's empty barriers has landed before the CTA may exit
+        for (int i = 0; i < p.ring_a; ++i) { mbar_wait(empty_a(sa), pha ^ 1u); if (++sa == p.ring_a) { sa = 0; pha ^= 1u; } }
+        for (int i = 0; i < p.ring_b; ++i) { mbar_wait(empty_b(sb), phb ^ 1u); if (++sb == p.ring_b) { sb = 0; phb ^= 1u; } }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            // ------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0) {
+            // ------------------------------------------------ MMA issuer (leader CTA only): warp-uniform loop, one elected
+            // lane issues
             const uint32_t m_field = ((128u * NCTA) >> 4) << 24;
             const uint32_t idesc_whole = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | m_field;
             const uint32_t idesc_sub = (1u << 4) | ((uint32_t)(p.n_sub >> 3) << 17) | m_field;
             const int a_items = outer_taps * p.kw * p.n_active;
             uint32_t tile_iter = 0;
             int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+            const bool timed = (p.debug & 16) != 0;
+            unsigned long long w_full = 0, w_tmem = 0, n_stage = 0;
+            const long long t_begin = clock64();
             for (int u = unit0; u < p.total_units; u += unit_step, ++tile_iter) {
                 const uint32_t idesc = u < p.full_units ? idesc_whole : idesc_sub;
                 const int buf = tile_iter & 1;
                 const uint32_t acc = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
-                mbar_wait(tmem_empty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // the epilogues (both CTAs) drained this buffer
+                mbar_wait_timed(tmem_empty_bar(buf), ((tile_iter >> 1) & 1) ^ 1, timed, w_tmem);     // the epilogues (both CTAs) drained this buffer
                 tc_fence_after();
                 uint32_t accumulate = 0;
                 for (int ai = 0; ai < a_items; ++ai) {
-                    mbar_wait(full_a(sa), pha);
-                    tc_fence_after();
+                    mbar_wait_timed(full_a(sa), pha, timed, w_full);
                     const uint32_t da = a_ring + (uint32_t)sa * a_slot;
                     for (int j = 0; j < p.a_taps; ++j) {
-                        mbar_wait(full_b(sb), phb);
+                        mbar_wait_timed(full_b(sb), phb, timed, w_full);
+                        ++n_stage;
                         tc_fence_after();
                         const uint32_t db = b_ring + (uint32_t)sb * b_slot;
-                        const uint64_t a_hi = umma_desc_sw128(da + (uint32_t)j * 1024u);
-                        const uint64_t a_lo = umma_desc_sw128(da + a_plane + (uint32_t)j * 1024u);
-                        const uint64_t b_hi = umma_desc_sw128(db), b_lo = umma_desc_sw128(db + b_plane);
+                        if (elect_one()) {
+                            const uint64_t a_hi = umma_desc_sw128(da + (uint32_t)j * 1024u);
+                            const uint64_t a_lo = umma_desc_sw128(da + a_plane + (uint32_t)j * 1024u);
+                            const uint64_t b_hi = umma_desc_sw128(db), b_lo = umma_desc_sw128(db + b_plane);
+                            if (!(p.debug & 2))
 #pragma unroll
-                        for (int k = 0; k < BKC / 16; ++k) {
-                            const uint64_t adv = (uint64_t)(k * 2);
-                            if (NCTA == 2) {
-                                tc_mma_f16_pair(acc, a_lo + adv, b_hi + adv, idesc, accumulate);
-                                tc_mma_f16_pair(acc, a_hi + adv, b_lo + adv, idesc, 1u);
-                                tc_mma_f16_pair(acc, a_hi + adv, b_hi + adv, idesc, 1u);
-                            } else {
-                                tc_mma_f16(acc, a_lo + adv, b_hi + adv, idesc, accumulate);
-                                tc_mma_f16(acc, a_hi + adv, b_lo + adv, idesc, 1u);
-                                tc_mma_f16(acc, a_hi + adv, b_hi + adv, idesc, 1u);
+                            for (int k = 0; k < BKC / 16; ++k) {
+                                const uint64_t adv = (uint64_t)(k * 2);
+                                const uint32_t acc_flag = k == 0 ? accumulate : 1u;
+                                if (NCTA == 2) {
+                                    tc_mma_f16_pair(acc, a_lo + adv, b_hi + adv, idesc, acc_flag);
+                                    tc_mma_f16_pair(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                                    tc_mma_f16_pair(acc, a_hi + adv, b_hi + adv, idesc, 1u);
+                                } else {
+                                    tc_mma_f16(acc, a_lo + adv, b_hi + adv, idesc, acc_flag);
+                                    tc_mma_f16(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                                    tc_mma_f16(acc, a_hi + adv, b_hi + adv, idesc, 1u);
+                                }
                             }
-                            accumulate = 1u;
+                            if (NCTA == 2) tc_commit_pair(empty_b(sb)); else tc_commit(empty_b(sb));
+                            if (j == p.a_taps - 1) { if (NCTA == 2) tc_commit_pair(empty_a(sa)); else tc_commit(empty_a(sa)); }
                         }
-                        if (NCTA == 2) tc_commit_pair(empty_b(sb)); else tc_commit(empty_b(sb));
+                        __syncwarp();
+                        accumulate = 1u;
                         if (++sb == p.ring_b) { sb = 0; phb ^= 1u; }
                     }
-                    if (NCTA == 2) tc_commit_pair(empty_a(sa)); else tc_commit(empty_a(sa));
                     if (++sa == p.ring_a) { sa = 0; pha ^= 1u; }
                 }
-                if (NCTA == 2) tc_commit_pair(tmem_full_bar(buf)); else tc_commit(tmem_full_bar(buf));
+                if (elect_one()) { if (NCTA == 2) tc_commit_pair(tmem_full_bar(buf)); else tc_commit(tmem_full_bar(buf)); }
+                __syncwarp();
+            }
+            if (timed && lane == 0) {
+                unsigned long long* d = g_conv_dbg[p.dbg_layer][blockIdx.x];
+                d[0] += (unsigned long long)(clock64() - t_begin); d[1] += w_full; d[2] += w_tmem; d[6] += tile_iter; d[7] += n_stage;
             }
         }
-        __syncwarp();
     } else {
         // ---------------------------------------------------- epilogue (every CTA, its own 128 accumulator lanes)
         const int q = warp & 3;
         const int mrow = q * 32 + lane;
         uint32_t tile_iter = 0;
+        const bool timed = (p.debug & 16) != 0 && warp == 2;
+        unsigned long long w_tfull = 0, busy = 0;
         for (int u = unit0; u < p.total_units; u += unit_step, ++tile_iter) {
             int bimg, y0, x0, n0, n_cnt; bool real;
             decode(u, bimg, y0, x0, n0, n_cnt, real);
             const int buf = tile_iter & 1;
+            const long long e0 = timed ? clock64() : 0;
             const int yy = y0 + (mrow >> 3), xx = x0 + (mrow & 7);
             const bool valid = real && yy < p.h && xx < p.w;
             const size_t pix = ((size_t)bimg * p.h + yy) * p.w + xx;
             mbar_wait_backoff(tmem_full_bar(buf), (tile_iter >> 1) & 1);
+            const long long e1 = timed ? clock64() : 0;
             tc_fence_after();
-            epilogue_columns(p, tmem_base, warp, q, buf, n0, n_cnt, valid, pix);
+            if (!(p.debug & 4)) epilogue_columns(p, tmem_base, warp, q, buf, n0, n_cnt, valid, pix);
+            if (timed) { w_tfull += (unsigned long long)(e1 - e0); busy += (unsigned long long)(clock64() - e1); }
             tc_fence_before();
             if (NCTA == 2) mbar_arrive_cluster(mapa_rank(tmem_empty_bar(buf), 0));
             else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(buf)) : "memory");
         }
+        if (timed && lane == 0) { g_conv_dbg[p.dbg_layer][blockIdx.x][4] += w_tfull; g_conv_dbg[p.dbg_layer][blockIdx.x][5] += busy; }
     }
     tc_fence_before();
     // nobody leaves while the peer may still read this CTA's shared memory or signal its barriers
@@ -770,7 +861,7 @@ int g_tail_min_n = []() { const char* e = getenv("B200POSE_TAIL_MIN_N"); return 
 
 // Kernel selection, B200POSE_CONV_MODE (read at every launch so that tests can switch): bit 0 = CTA pairs
 // (tcgen05.mma.cta_group::2), bit 1 = vertical-tap reuse of the activation box; 0 = first-generation kernel; unset = default.
-constexpr int kDefaultConvMode = 0;
+constexpr int kDefaultConvMode = 3;
 int conv_mode() {
     const char* e = getenv("B200POSE_CONV_MODE");
     return e && *e ? atoi(e) : kDefaultConvMode;
@@ -826,6 +917,7 @@ int launch_conv_umma2(const UmmaConvArgs& a, UmmaConvParams& p, int ncta, bool r
     if ((rc = make_wgt_map(&p.b_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, a.n_tile / ncta))) return rc;
     const size_t smem = (size_t)p.ring_a * (2 * p.a_rows * 1024) + (size_t)p.ring_b * (2 * (a.n_tile / ncta) * 128) + 1024 +
                         16 * (p.ring_a + p.ring_b) + 64;
+    p.debug = env_int("B200POSE_V2_DEBUG", 0);
     p.m_groups = ceil_div(p.m_tiles, ncta);
     p.total_tiles = p.m_groups * (a.cout_pad / a.n_tile);
     const int slots = sms / ncta;                                    // clusters resident at once
@@ -888,6 +980,8 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     p.m_tiles = a.B * p.tiles_x * p.tiles_y;
     p.total_tiles = p.m_tiles * (a.cout_pad / a.n_tile);
     p.b_batched = a.b_batched;
+    p.debug = a.b_batched ? 0 : env_int("B200POSE_V2_DEBUG", 0);
+    p.dbg_layer = a.layer_id >= 0 && a.layer_id < 11 ? a.layer_id + 1 : 0;
     // second-generation kernel (see conv_mode): not for the batched-weight volume GEMM (a pair of M tiles may straddle two
     // samples); CTA pairs only when the problem fills the machine (they halve the number of schedulable units)
     int mode = a.b_batched ? 0 : conv_mode();
@@ -895,6 +989,15 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     if (mode) {
         const bool pair = (mode & 1) && p.total_tiles >= sms && (a.n_tile % 32) == 0;
         const bool reuse_v = (mode & 2) && a.kh > 1;
+        if (pair && a.n_tile == 128 && a.cout_pad % 256 == 0 && env_int("B200POSE_PAIR_N256", 1)) {
+            // A pair holds a 256-row weight tile in the shared memory of two SMs (128 rows each): one pass over the
+            // activations instead of two, and M=256 x N=256 MMAs read half as many operand bytes per SM and flop.
+            UmmaConvArgs a2 = a;
+            a2.n_tile = 256;
+            p.n_tile = 256;
+            p.total_tiles = p.m_tiles * (a.cout_pad / 256);
+            return launch_conv_umma2(a2, p, 2, reuse_v, sms, s);
+        }
         if (pair || reuse_v || (mode & 4)) return launch_conv_umma2(a, p, pair ? 2 : 1, reuse_v, sms, s);
     }
     int grid = p.total_tiles < sms ? p.total_tiles : sms;            // persistent: one CTA per SM
@@ -918,5 +1021,18 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     }
     B2P_CUDA(b2p_launch_pdl(conv_umma_kernel, dim3(grid), dim3(UM_THREADS), smem, s, p));
     B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+// Experiment hook (not part of include/b200pose.h): per-CTA clock counters of the last gen-1 launch made with
+// B200POSE_V2_DEBUG bit 16.  host_out: 12 x 160 x 8 unsigned 64-bit values.
+extern "C" int b200pose_debug_conv_counters(unsigned long long* host_out, int reset) {
+    B2P_CUDA(cudaDeviceSynchronize());
+    if (host_out) B2P_CUDA(cudaMemcpyFromSymbol(host_out, g_conv_dbg, sizeof(unsigned long long) * 12 * 160 * 8));
+    if (reset) {
+        void* d = nullptr;
+        B2P_CUDA(cudaGetSymbolAddress(&d, g_conv_dbg));
+        B2P_CUDA(cudaMemset(d, 0, sizeof(unsigned long long) * 12 * 160 * 8));
+    }
     return 0;
 }

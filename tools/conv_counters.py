@@ -1,0 +1,50 @@
+"""Where the conv kernels' warps wait inside the real fused loop (B200POSE_V2_DEBUG=16 clock counters, accumulated per layer
+over one refine call at the bench shape).  usage: B200POSE_CONV_MODE=m python tools/conv_counters.py"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["B200POSE_V2_DEBUG"] = "16"
+from rnnpose_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+sd = torch.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "weights", "gru_update.pth"), map_location="cpu")
+packed = ops.pack_weights({k[len("update_block."):]: v.float() for k, v in sd.items()}, dev)
+H, W, B = 240, 320, 32
+f1 = torch.randn(B, 256, H // 8, W // 8, device=dev); f2 = torch.randn(B, 256, H // 8, W // 8, device=dev)
+ctx = 0.1 * torch.randn(B, 256, H, W, device=dev)
+g1 = torch.nn.functional.normalize(torch.randn(B, 32, H, W, device=dev), dim=1)
+g2 = torch.nn.functional.normalize(torch.randn(B, 32, H, W, device=dev), dim=1)
+yy, xx = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+depth = (((yy - H / 2) ** 2 / (0.35 * H) ** 2 + (xx - W / 2) ** 2 / (0.3 * W) ** 2) < 1).float()[None].repeat(B, 1, 1) * 0.9
+K = torch.tensor([[600.0, 0, W / 2], [0, 600.0, H / 2], [0, 0, 1]], device=dev)[None].repeat(B, 1, 1).contiguous()
+ws = ops.RefineWorkspace(B, H, W, dev)
+L = ops._lib.lib()
+L.b200pose_debug_conv_counters.argtypes = [C.c_void_p, C.c_int]
+buf = (C.c_ulonglong * (12 * 160 * 8))()
+
+
+def call():
+    G = torch.eye(4, device=dev)[None].repeat(B, 1, 1).contiguous()
+    ops.refine_iters(packed, f1, f2, ctx, g1, g2, depth.contiguous(), K, G, 1.0, 4, 3, workspace=ws, flags=ops.FLAG_TENSOR_CORES)
+
+
+call(); call()
+L.b200pose_debug_conv_counters(None, 1)
+call()
+L.b200pose_debug_conv_counters(buf, 0)
+v = torch.tensor(list(buf), dtype=torch.float64).view(12, 160, 8)
+names = ["(other)", "C1", "C2", "F1", "F2", "ENC", "ZR1", "Q1", "ZR2", "Q2", "HEADS", "MASK2"]
+print(f"mode {os.environ.get('B200POSE_CONV_MODE', 'default')}: clocks per launch, mean over the CTAs that issue MMAs (4 launches per layer + GRU pre-sums)")
+print("layer   units stages | MMA-loop | wait full  wait tmem | prod wait empty | epi wait full  epi busy | loop clk/stage  epi busy/unit")
+for i, n in enumerate(names):
+    x = v[i]
+    act = x[x[:, 0] > 0]
+    if act.numel() == 0:
+        continue
+    m = act.mean(0) / 4.0
+    pe = x[x[:, 5] > 0].mean(0) / 4.0
+    print(f"{n:7s} {m[6]:5.1f} {m[7]:6.1f} | {m[0]:8.0f} | {m[1]:9.0f} {m[2]:10.0f} | {pe[3]:15.0f} | {pe[4]:13.0f} {pe[5]:9.0f} | {m[0] / max(m[7], 1):14.0f} {pe[5] / max(m[6], 1e-9):14.0f}")
