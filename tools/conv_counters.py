@@ -48,3 +48,24 @@ for i, n in enumerate(names):
     m = act.mean(0) / 4.0
     pe = x[x[:, 5] > 0].mean(0) / 4.0
     print(f"{n:7s} {m[6]:5.1f} {m[7]:6.1f} | {m[0]:8.0f} | {m[1]:9.0f} {m[2]:10.0f} | {pe[3]:15.0f} | {pe[4]:13.0f} {pe[5]:9.0f} | {m[0] / max(m[7], 1):14.0f} {pe[5] / max(m[6], 1e-9):14.0f}")
+
+# timeline of CTA 0 over the last call: entry -> dependency resolved (griddepcontrol.wait returned) -> exit
+log = (C.c_ulonglong * (512 * 4))()
+L.b200pose_debug_conv_log.argtypes = [C.c_void_p]
+n = L.b200pose_debug_conv_log(log)
+ev = sorted([(log[i * 4], log[i * 4 + 1], log[i * 4 + 2], int(log[i * 4 + 3])) for i in range(n)])
+print(f"\nCTA 0 timeline of the conv launches ({n} launches), us relative to the first; one recurrent iteration shown")
+t0 = ev[0][0]
+prev_exit = None
+shown = 0
+for e in ev:
+    if shown >= 30:
+        break
+    if e[0] - t0 < 1.6e6:      # skip the per-call part (pre-sum GEMMs) and the first iteration
+        prev_exit = e[2]
+        continue
+    gap = (e[0] - prev_exit) / 1e3 if prev_exit else 0.0
+    print(f"  {names[e[3]]:6s} entry {(e[0] - t0) / 1e3:9.1f}  blocked on previous kernel {(e[1] - e[0]) / 1e3:6.1f}  run {(e[2] - e[1]) / 1e3:6.1f}  "
+          f"(entry - previous conv exit {gap:7.1f})")
+    prev_exit = e[2]
+    shown += 1
