@@ -56,10 +56,6 @@ struct UmmaConvParams {
     int a_rows;                        // rows of the activation box = 16 + a_taps - 1
     int ring_a, ring_b;                // ring depths
     int m_groups;                      // M tiles / CTAs per cluster, rounded up (a unit = one group x one N tile)
-    // transposed variant (TR): D^T[channel][pixel] = W X^T, TMEM lanes = output channels, columns = pixels.  The split
-    // units of the last round are bands of band_rows pixel rows (of the 16) instead of channel sub-tiles.
-    CUtensorMap as_hi[2], as_lo[2];    // activation maps with a (band_rows + a_taps - 1)-row box
-    int band_rows;
     int dbg_layer;                     // row of g_conv_dbg (layer id + 1)
     int debug;                         // timing experiments only (results are garbage): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue
 };
@@ -487,66 +483,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
 }
 
 
-
-// Epilogue of the transposed variant for one warp.  TMEM lane = output channel (this thread: channel c), column = pixel, so
-// every global access of a warp is one contiguous row segment of a PXC tensor (32 consecutive channels of one pixel): one
-// 128-byte line per instruction instead of the 32 lines of the pixel-per-thread layout, which made the epilogues of the
-// pixel-major kernel L1-bound (a GRU tile took as long to drain as to compute).
-// cols = live columns of this unit (pixels, patch-major: patch r occupies [r * band_px, (r + 1) * band_px)).
-struct PatchOrigin { int bimg, y0, x0; bool real; };
-template <int NCTA>
-__device__ __forceinline__ void epilogue_transposed(const UmmaConvParams& p, uint32_t tmem_base, int warp, int q, int lane, int buf,
-                                                    int c, const PatchOrigin (&po)[NCTA], int band_px) {
-    const bool c_ok = c < p.cout;
-    const float bias = c_ok ? __ldg(p.bias + c) : 0.f;
-    const bool is_z = p.epi == EPI_GRU_ZR && c < 128;
-    const int oc = (p.epi == EPI_GRU_ZR && !is_z) ? c - 128 : c;          // channel in the 128-wide GRU side buffers / output
-    const int cols = NCTA * band_px;
-    for (int col0 = ((warp - 2) >> 2) * 32; col0 < cols; col0 += 64) {
-        uint32_t r[32];
-        tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS + col0), r);
-        const int patch = col0 / band_px;                                  // band_px >= 32: a group never straddles patches
-        const PatchOrigin o = po[NCTA == 2 ? patch : 0];
-        const int m0 = col0 - patch * band_px;
-        tmem_ld_wait(r);
-        if (!c_ok || !o.real) continue;
-#pragma unroll
-        for (int j0 = 0; j0 < 32; j0 += 8) {
-            // 8 pixels = one row of the 8-wide patch: yy is uniform over the chunk
-            const int yy = o.y0 + ((m0 + j0) >> 3);
-            if (yy >= p.h) continue;
-            const size_t prow = ((size_t)o.bimg * p.h + yy) * p.w + o.x0;
-            float pre[8], hh[8], zz[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const bool ok = o.x0 + t < p.w;
-                const size_t pix = prow + t;
-                pre[t] = (ok && p.pre) ? __ldg(p.pre + pix * p.pre_pitch + c) : 0.f;
-                hh[t] = (ok && ((p.epi == EPI_GRU_ZR && !is_z) || p.epi == EPI_GRU_Q)) ? p.hbuf[pix * 128 + oc] : 0.f;
-                zz[t] = (ok && p.epi == EPI_GRU_Q) ? __ldg(p.zbuf + pix * 128 + c) : 0.f;
-            }
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                if (o.x0 + t >= p.w) continue;
-                const size_t pix = prow + t;
-                float v = __uint_as_float(r[j0 + t]) + bias + pre[t];
-                if (p.epi == EPI_SCALE) { p.out_f32[pix * p.out_f32_pitch + c] = v * p.scale; continue; }
-                if (is_z) { p.zbuf[pix * 128 + c] = sigm(v); continue; }
-                if (p.epi == EPI_RELU) v = fmaxf(v, 0.f);
-                else if (p.epi == EPI_GRU_ZR) v = sigm(v) * hh[t];
-                else if (p.epi == EPI_GRU_Q) {
-                    v = (1.f - zz[t]) * hh[t] + zz[t] * tanh_fast(v);
-                    p.hbuf[pix * 128 + c] = v;
-                }
-                __half hi, lo;
-                b2p_split_half(v, hi, lo);
-                p.out_hi[pix * p.out_h_pitch + oc] = hi;
-                p.out_lo[pix * p.out_h_pitch + oc] = lo;
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------- kernel, second generation
 // The first kernel is bound by the L2 -> shared-memory feed (profiles/r1_final_summary.md: 6.9 GB per update-block pass at
 // 8-11 TB/s, the LTS cap is ~12 TB/s), not by the tensor pipe.  This one moves fewer bytes for the same MMAs:
@@ -600,7 +536,7 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc,
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-template <int NCTA, bool TR>
+template <int NCTA>
 __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_constant__ UmmaConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     const unsigned long long t_entry = (p.debug & 16) ? gtime_ns() : 0ull;
@@ -628,26 +564,22 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     // a unit = (N tile or sub-tile) x (group of NCTA consecutive M tiles); CTA `rank` of the cluster owns M tile group*NCTA+rank.
     // A group that runs past the last M tile repeats it and discards the result (`real` = false).
-    // (TR: n_cnt stays n_tile; a split unit is a band of p.band_rows pixel rows starting at y0, px_rows tells which)
-    auto decode_rank = [&](int u, int rk, int& bimg, int& y0, int& x0, int& n0, int& n_cnt, int& px_rows, bool& real) {
+    auto decode = [&](int u, int& bimg, int& y0, int& x0, int& n0, int& n_cnt, bool& real) {
         int t = u, sub = 0;
-        n_cnt = p.n_tile; px_rows = TILE_ROWS;
+        n_cnt = p.n_tile;
         if (u >= p.full_units) {
             const int v = u - p.full_units;
             t = p.full_units + v / p.split; sub = v - (v / p.split) * p.split;
-            if (TR) px_rows = p.band_rows; else n_cnt = p.n_sub;
+            n_cnt = p.n_sub;
         }
         const int n_idx = t / p.m_groups;
-        int m_idx = (t - n_idx * p.m_groups) * NCTA + rk;
+        int m_idx = (t - n_idx * p.m_groups) * NCTA + (int)rank;
         real = m_idx < p.m_tiles;
         if (!real) m_idx = p.m_tiles - 1;
         bimg = m_idx / tiles_per_img;
         const int trem = m_idx - bimg * tiles_per_img;
-        y0 = (trem / p.tiles_x) * TILE_ROWS + (TR ? sub * p.band_rows : 0); x0 = (trem % p.tiles_x) * TILE_COLS;
-        n0 = n_idx * p.n_tile + (TR ? 0 : sub * p.n_sub);
-    };
-    auto decode = [&](int u, int& bimg, int& y0, int& x0, int& n0, int& n_cnt, int& px_rows, bool& real) {
-        decode_rank(u, (int)rank, bimg, y0, x0, n0, n_cnt, px_rows, real);
+        y0 = (trem / p.tiles_x) * TILE_ROWS; x0 = (trem % p.tiles_x) * TILE_COLS;
+        n0 = n_idx * p.n_tile + sub * p.n_sub;
     };
     const int unit0 = (int)blockIdx.x / NCTA, unit_step = (int)gridDim.x / NCTA;
     const int outer_taps = p.a_taps == p.kh ? 1 : p.kh;       // vertical taps that need an activation box of their own
@@ -680,18 +612,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
         // ------------------------------------------------ TMA producer (every CTA; the leader arms the full barriers).
         // Warp-uniform loop, one elected lane issues.
         int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+        const uint32_t a_tx = (uint32_t)NCTA * a_slot;
         const bool timed = (p.debug & 16) != 0;
         unsigned long long w_empty = 0;
         for (int u = unit0; u < p.total_units; u += unit_step) {
-            int bimg, y0, x0, n0, n_cnt, px_rows; bool real;
-            decode(u, bimg, y0, x0, n0, n_cnt, px_rows, real);
-            const bool whole = u < p.full_units;
-            const CUtensorMap* bh = (whole || TR) ? &p.b_hi : &p.bs_hi;
-            const CUtensorMap* bl = (whole || TR) ? &p.b_lo : &p.bs_lo;
-            const CUtensorMap* ah = (whole || !TR) ? p.a_hi : p.as_hi;
-            const CUtensorMap* al = (whole || !TR) ? p.a_lo : p.as_lo;
-            // bytes landing on the leader's barrier per activation box (both planes, every CTA of the cluster)
-            const uint32_t a_tx = (uint32_t)NCTA * 2u * (uint32_t)(px_rows + p.a_taps - 1) * 1024u;
+            int bimg, y0, x0, n0, n_cnt; bool real;
+            decode(u, bimg, y0, x0, n0, n_cnt, real);
+            const bool whole = n_cnt == p.n_tile;
+            const CUtensorMap* bh = whole ? &p.b_hi : &p.bs_hi;
+            const CUtensorMap* bl = whole ? &p.b_lo : &p.bs_lo;
             const int b_rows = n_cnt / NCTA;
             const uint32_t b_tx = (uint32_t)NCTA * 2u * (uint32_t)b_rows * 128u;
             const int nb0 = n0 + (int)rank * b_rows;
@@ -711,12 +640,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
                             } else if (NCTA == 2) {
                                 const uint32_t fb = mapa_rank(full_a(sa), 0);
                                 if (rank == 0) mbar_expect_tx(full_a(sa), a_tx);
-                                tma_load_4d_pair(&ah[seg], da, fb, c0, xs, ys, bimg);
-                                tma_load_4d_pair(&al[seg], da + a_plane, fb, c0, xs, ys, bimg);
+                                tma_load_4d_pair(&p.a_hi[seg], da, fb, c0, xs, ys, bimg);
+                                tma_load_4d_pair(&p.a_lo[seg], da + a_plane, fb, c0, xs, ys, bimg);
                             } else {
                                 mbar_expect_tx(full_a(sa), a_tx);
-                                tma_load_4d(&ah[seg], da, full_a(sa), c0, xs, ys, bimg);
-                                tma_load_4d(&al[seg], da + a_plane, full_a(sa), c0, xs, ys, bimg);
+                                tma_load_4d(&p.a_hi[seg], da, full_a(sa), c0, xs, ys, bimg);
+                                tma_load_4d(&p.a_lo[seg], da + a_plane, full_a(sa), c0, xs, ys, bimg);
                             }
                         }
                         __syncwarp();
@@ -755,9 +684,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
             // ------------------------------------------------ MMA issuer (leader CTA only): warp-uniform loop, one elected
             // lane issues
             const uint32_t m_field = ((128u * NCTA) >> 4) << 24;
-            // N: output channels of the unit, or (TR) its pixels = NCTA patches of 16 (band_rows) rows of 8
-            const uint32_t idesc_whole = (1u << 4) | ((uint32_t)(TR ? NCTA * TILE_ROWS : p.n_tile >> 3) << 17) | m_field;
-            const uint32_t idesc_sub = (1u << 4) | ((uint32_t)(TR ? NCTA * p.band_rows : p.n_sub >> 3) << 17) | m_field;
+            const uint32_t idesc_whole = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | m_field;
+            const uint32_t idesc_sub = (1u << 4) | ((uint32_t)(p.n_sub >> 3) << 17) | m_field;
             const int a_items = outer_taps * p.kw * p.n_active;
             uint32_t tile_iter = 0;
             int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
@@ -780,12 +708,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
                         tc_fence_after();
                         const uint32_t db = b_ring + (uint32_t)sb * b_slot;
                         if (elect_one()) {
-                            // operand roles: pixels x weights^T, or (TR) weights x pixels^T -- both tiles are K-major rows
-                            const uint64_t x_hi = umma_desc_sw128(da + (uint32_t)j * 1024u);
-                            const uint64_t x_lo = umma_desc_sw128(da + a_plane + (uint32_t)j * 1024u);
-                            const uint64_t w_hi = umma_desc_sw128(db), w_lo = umma_desc_sw128(db + b_plane);
-                            const uint64_t a_hi = TR ? w_hi : x_hi, a_lo = TR ? w_lo : x_lo;
-                            const uint64_t b_hi = TR ? x_hi : w_hi, b_lo = TR ? x_lo : w_lo;
+                            const uint64_t a_hi = umma_desc_sw128(da + (uint32_t)j * 1024u);
+                            const uint64_t a_lo = umma_desc_sw128(da + a_plane + (uint32_t)j * 1024u);
+                            const uint64_t b_hi = umma_desc_sw128(db), b_lo = umma_desc_sw128(db + b_plane);
                             if (!(p.debug & 2))
 #pragma unroll
                             for (int k = 0; k < BKC / 16; ++k) {
@@ -826,31 +751,17 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
         const bool timed = (p.debug & 16) != 0 && warp == 2;
         unsigned long long w_tfull = 0, busy = 0;
         for (int u = unit0; u < p.total_units; u += unit_step, ++tile_iter) {
-            int bimg, y0, x0, n0, n_cnt, px_rows; bool real;
-            decode(u, bimg, y0, x0, n0, n_cnt, px_rows, real);
+            int bimg, y0, x0, n0, n_cnt; bool real;
+            decode(u, bimg, y0, x0, n0, n_cnt, real);
             const int buf = tile_iter & 1;
             const long long e0 = timed ? clock64() : 0;
             const int yy = y0 + (mrow >> 3), xx = x0 + (mrow & 7);
             const bool valid = real && yy < p.h && xx < p.w;
             const size_t pix = ((size_t)bimg * p.h + yy) * p.w + xx;
-            PatchOrigin po[NCTA];
-            if (TR) {
-#pragma unroll
-                for (int rk = 0; rk < NCTA; ++rk) {
-                    int n0r, ncr, pxr;
-                    decode_rank(u, rk, po[rk].bimg, po[rk].y0, po[rk].x0, n0r, ncr, pxr, po[rk].real);
-                }
-            }
             mbar_wait_backoff(tmem_full_bar(buf), (tile_iter >> 1) & 1);
             const long long e1 = timed ? clock64() : 0;
             tc_fence_after();
-            if (p.debug & 4) {
-            } else if (TR) {
-                // this CTA's 128 accumulator lanes are the channels n0 + rank * 128 + [0, 128)
-                epilogue_transposed<NCTA>(p, tmem_base, warp, q, lane, buf, n0 + (int)rank * 128 + mrow, po, px_rows * TILE_COLS);
-            } else {
-                epilogue_columns(p, tmem_base, warp, q, buf, n0, n_cnt, valid, pix);
-            }
+            if (!(p.debug & 4)) epilogue_columns(p, tmem_base, warp, q, buf, n0, n_cnt, valid, pix);
             if (timed) { w_tfull += (unsigned long long)(e1 - e0); busy += (unsigned long long)(clock64() - e1); }
             tc_fence_before();
             if (NCTA == 2) mbar_arrive_cluster(mapa_rank(tmem_empty_bar(buf), 0));
@@ -958,10 +869,8 @@ int device_sms() {
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
         if (cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(conv_umma2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(conv_umma2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(conv_umma2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(conv_umma2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(conv_umma2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(conv_umma2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
         sms_of[dev] = sms; done[dev] = true;
     }
     return sms_of[dev];
@@ -1001,15 +910,12 @@ cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), int grid, int cluster, 
     return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
-// Second-generation launch (conv_umma2_kernel).  ncta = 2: units are CTA pairs.  tr: transposed variant (channels on the
-// TMEM lanes), a unit is 128 * ncta channels x ncta pixel tiles; a.n_tile is ignored.
-int launch_conv_umma2(const UmmaConvArgs& a, UmmaConvParams& p, int ncta, bool reuse_v, bool tr, int sms, cudaStream_t s) {
+// Second-generation launch (conv_umma2_kernel).  ncta = 2: units are CTA pairs.
+int launch_conv_umma2(const UmmaConvArgs& a, UmmaConvParams& p, int ncta, bool reuse_v, int sms, cudaStream_t s) {
     int rc;
     const int taps = a.kh * a.kw;
-    const int n_tile = tr ? 128 * ncta : a.n_tile;
-    p.n_tile = n_tile;
     // rings: one activation slot serves a_taps weight slots; without reuse the two rings advance together
-    const int b_slot = 2 * (n_tile / ncta) * 128, budget = env_int("B200POSE_V2_BUDGET_KB", 222) * 1024;
+    const int b_slot = 2 * (a.n_tile / ncta) * 128, budget = env_int("B200POSE_V2_BUDGET_KB", 222) * 1024;
     p.a_taps = reuse_v ? a.kh : 1;
     p.a_rows = TILE_ROWS + p.a_taps - 1;
     p.ring_a = 2;
@@ -1027,49 +933,33 @@ int launch_conv_umma2(const UmmaConvArgs& a, UmmaConvParams& p, int ncta, bool r
         if ((rc = make_act_map(&p.a_hi[g], a.seg_hi[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.a_rows))) return rc;
         if ((rc = make_act_map(&p.a_lo[g], a.seg_lo[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.a_rows))) return rc;
     }
-    if ((rc = make_wgt_map(&p.b_hi, a.w_hi, a.cin_pad, a.cout_pad, taps, n_tile / ncta))) return rc;
-    if ((rc = make_wgt_map(&p.b_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, n_tile / ncta))) return rc;
-    const size_t smem = (size_t)p.ring_a * (2 * p.a_rows * 1024) + (size_t)p.ring_b * (2 * (n_tile / ncta) * 128) + 1024 +
+    if ((rc = make_wgt_map(&p.b_hi, a.w_hi, a.cin_pad, a.cout_pad, taps, a.n_tile / ncta))) return rc;
+    if ((rc = make_wgt_map(&p.b_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, a.n_tile / ncta))) return rc;
+    const size_t smem = (size_t)p.ring_a * (2 * p.a_rows * 1024) + (size_t)p.ring_b * (2 * (a.n_tile / ncta) * 128) + 1024 +
                         16 * (p.ring_a + p.ring_b) + 64;
     p.debug = env_int("B200POSE_V2_DEBUG", 0);
     p.m_groups = ceil_div(p.m_tiles, ncta);
-    // channel tiles: the packed weights are padded to a.n_tile; rows past the tensor are zero-filled by TMA and their
-    // channels masked in the epilogue (c >= cout), so the transposed variant may tile by 128 * ncta regardless
-    p.total_tiles = p.m_groups * (tr ? ceil_div(a.cout, n_tile) : a.cout_pad / n_tile);
+    p.total_tiles = p.m_groups * (a.cout_pad / a.n_tile);
     const int slots = sms / ncta;                                    // clusters resident at once
     int nclusters = p.total_tiles < slots ? p.total_tiles : slots;
-    p.full_units = p.total_tiles; p.total_units = p.total_tiles; p.split = 1; p.n_sub = n_tile; p.band_rows = TILE_ROWS;
+    p.full_units = p.total_tiles; p.total_units = p.total_tiles; p.split = 1; p.n_sub = a.n_tile;
     const int tail = p.total_tiles < slots ? p.total_tiles : p.total_tiles % slots;
     if (tail && g_tail_min_n > 0) {
-        // split the units of the last partial round: channel sub-tiles, or (tr) bands of pixel rows (at least 4 rows: a
-        // 32-column epilogue group must not straddle two patches)
-        for (int sp = tr ? 4 : n_tile / g_tail_min_n; sp >= 2; --sp) {
-            if (tr ? (TILE_ROWS % sp != 0) : (n_tile % sp || (n_tile / sp) % 32)) continue;
-            if (tail * sp > slots) continue;
-            p.split = sp;
-            if (tr) p.band_rows = TILE_ROWS / sp; else p.n_sub = n_tile / sp;
+        for (int sp = a.n_tile / g_tail_min_n; sp >= 2; --sp) {
+            if (a.n_tile % sp || (a.n_tile / sp) % 32 || tail * sp > slots) continue;
+            p.split = sp; p.n_sub = a.n_tile / sp;
             p.full_units = p.total_tiles - tail; p.total_units = p.full_units + tail * sp;
             if (p.total_units < slots) nclusters = p.total_units;
             break;
         }
     }
     p.bs_hi = p.b_hi; p.bs_lo = p.b_lo;
-    for (int g = 0; g < 2; ++g) { p.as_hi[g] = p.a_hi[g]; p.as_lo[g] = p.a_lo[g]; }
-    if (p.split > 1 && !tr) {
+    if (p.split > 1) {
         if ((rc = make_wgt_map(&p.bs_hi, a.w_hi, a.cin_pad, a.cout_pad, taps, p.n_sub / ncta))) return rc;
         if ((rc = make_wgt_map(&p.bs_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, p.n_sub / ncta))) return rc;
     }
-    if (p.split > 1 && tr) {
-        for (int g = 0; g < 2; ++g) {
-            if (a.seg_c[g] == 0) { p.as_hi[g] = p.as_hi[0]; p.as_lo[g] = p.as_lo[0]; continue; }
-            if ((rc = make_act_map(&p.as_hi[g], a.seg_hi[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.band_rows + p.a_taps - 1))) return rc;
-            if ((rc = make_act_map(&p.as_lo[g], a.seg_lo[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.band_rows + p.a_taps - 1))) return rc;
-        }
-    }
-    if (ncta == 2 && tr) B2P_CUDA(launch_pdl_cluster(conv_umma2_kernel<2, true>, nclusters * 2, 2, smem, s, p));
-    else if (ncta == 2) B2P_CUDA(launch_pdl_cluster(conv_umma2_kernel<2, false>, nclusters * 2, 2, smem, s, p));
-    else if (tr) B2P_CUDA(launch_pdl_cluster(conv_umma2_kernel<1, true>, nclusters, 1, smem, s, p));
-    else B2P_CUDA(launch_pdl_cluster(conv_umma2_kernel<1, false>, nclusters, 1, smem, s, p));
+    if (ncta == 2) B2P_CUDA(launch_pdl_cluster(conv_umma2_kernel<2>, nclusters * 2, 2, smem, s, p));
+    else B2P_CUDA(launch_pdl_cluster(conv_umma2_kernel<1>, nclusters, 1, smem, s, p));
     B2P_LAUNCH_CHECK();
     return 0;
 }
@@ -1119,23 +1009,16 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     if (mode) {
         const bool pair = (mode & 1) && p.total_tiles >= sms && (a.n_tile % 32) == 0;
         const bool reuse_v = (mode & 2) && a.kh > 1;
-        // bit 3: transposed variant (coalesced epilogue) for the layers whose channel count tiles by 128 without much
-        // padding (at most 1/8): all but C2 (192) and F2 (64)
-        const int cout_t = (a.cout + 127) / 128 * 128;
-        const bool tr = (mode & 8) && (cout_t - a.cout) * 8 <= cout_t;
-        if (tr) {
-            const bool pair_t = pair && a.cout % 256 == 0;
-            return launch_conv_umma2(a, p, pair_t ? 2 : 1, reuse_v, true, sms, s);
-        }
         if (pair && a.n_tile == 128 && a.cout_pad % 256 == 0 && env_int("B200POSE_PAIR_N256", 1)) {
             // A pair holds a 256-row weight tile in the shared memory of two SMs (128 rows each): one pass over the
             // activations instead of two, and M=256 x N=256 MMAs read half as many operand bytes per SM and flop.
             UmmaConvArgs a2 = a;
             a2.n_tile = 256;
+            p.n_tile = 256;
             p.total_tiles = p.m_tiles * (a.cout_pad / 256);
-            return launch_conv_umma2(a2, p, 2, reuse_v, false, sms, s);
+            return launch_conv_umma2(a2, p, 2, reuse_v, sms, s);
         }
-        if (pair || reuse_v || (mode & 4)) return launch_conv_umma2(a, p, pair ? 2 : 1, reuse_v, false, sms, s);
+        if (pair || reuse_v || (mode & 4)) return launch_conv_umma2(a, p, pair ? 2 : 1, reuse_v, sms, s);
     }
     int grid = p.total_tiles < sms ? p.total_tiles : sms;            // persistent: one CTA per SM
     // split the tiles of the last partial round (see UmmaConvParams): the largest split whose units still fit one round.

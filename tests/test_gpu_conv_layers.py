@@ -107,7 +107,7 @@ def test_corr_pyramid_tensor_core_vs_oracle(ops, shape):
 _REF_CACHE = {}
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3, 8, 11], ids=["pair", "vreuse", "pair+vreuse", "transposed", "pair+vreuse+transposed"])
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["pair", "vreuse", "pair+vreuse"])
 @pytest.mark.parametrize("layer", sorted(LAYERS))
 @pytest.mark.parametrize("shape", [(2, 9, 12), (32, 30, 40), (51, 16, 20)], ids=["2x9x12", "32x30x40", "51x16x20"])
 def test_conv_layer_second_generation(ops, packed, layer, shape, mode, monkeypatch):

@@ -74,7 +74,7 @@ def test_refine_matches_reference_golden(ops, packed, name, flags):
             assert abs(a.item() - b.item()) / sc.diameter < 5e-5
 
 
-@pytest.mark.parametrize("conv_mode", [1, 2, 3, 8, 11], ids=["pair", "vreuse", "pair+vreuse", "transposed", "pair+vreuse+transposed"])
+@pytest.mark.parametrize("conv_mode", [1, 2, 3], ids=["pair", "vreuse", "pair+vreuse"])
 def test_refine_golden_240x320_second_generation_kernels(ops, packed, conv_mode, monkeypatch):
     """The executed reference's 240x320 4x3 result through the second-generation convolution kernel variants."""
     monkeypatch.setenv("B200POSE_CONV_MODE", str(conv_mode))
@@ -100,7 +100,7 @@ def test_refine_batched_vs_oracle(ops, packed):
     torch.testing.assert_close(res["flow_last"].cpu(), ref["flows"][-1], rtol=1e-3, atol=2e-2)
 
 
-@pytest.mark.parametrize("conv_mode", [None, 0, 1, 2, 3, 11], ids=["default", "gen1", "pair", "vreuse", "pair+vreuse", "pair+vreuse+transposed"])
+@pytest.mark.parametrize("conv_mode", [None, 0, 1, 2, 3], ids=["default", "gen1", "pair", "vreuse", "pair+vreuse"])
 def test_refine_full_size_batch_properties(ops, packed, conv_mode, monkeypatch):
     """BASELINE configs[1] shape (B=32, 240x320, 4x3): per-sample results do not depend on batch position or
     batch size (bit-exact), outputs are finite rigid transforms, and a subset agrees with the oracle.  Run for every
@@ -124,7 +124,7 @@ def test_refine_full_size_batch_properties(ops, packed, conv_mode, monkeypatch):
     one = {k: v[:1].contiguous() for k, v in uniq.items() if k != "diameter"}
     G1 = run_gpu(ops, packed, f1u[:1], f2u[:1], one, G0[:1], 4, 3)["G"].cpu()
     # (the CTA-pair kernel is only taken for machine-filling problems, so B=1 and B=32 may run M=128 and M=256 MMAs)
-    assert torch.equal(G1[0], G[0]) or (conv_mode in (None, 1, 3, 11) and (G1[0] - G[0]).abs().max().item() < 1e-6)
+    assert torch.equal(G1[0], G[0]) or (conv_mode in (None, 1, 3) and (G1[0] - G[0]).abs().max().item() < 1e-6)
     # oracle on two of the samples
     sub = {k: v[:2].contiguous() for k, v in uniq.items() if k != "diameter"}
     ref = O.refine_inner_loop(load_update_weights(), f1u[:2], f2u[:2], sub["context"], sub["geofea1"], sub["geofea2"],
