@@ -28,17 +28,18 @@ struct UpdateWs {
 
 size_t update_ws_layout(int B, int h, int w, void* ws, size_t cap, UpdateWs* out) {
     const size_t P = (size_t)B * h * w;
+    const size_t Pt = b2p_tiled_pixels(B, h, w);       // pixel slots of the tiled side buffers (z, h, pre-sums), >= P
     Carver c(ws, cap);
     UpdateWs u;
     u.col = c.take<float>(P * 112);
     u.c1 = c.take<float>(P * 256);
     u.corflo = c.take<float>(P * 256);
     u.f1o = c.take<float>(P * 128);
-    u.zbuf = c.take<float>(P * 128);
-    u.rhbuf = c.take<float>(P * 128);
+    u.zbuf = c.take<float>(Pt * 128);
+    u.rhbuf = c.take<float>(Pt * 128);             // exact path: r*h (PXC); tensor-core path: the hidden state h (tiled)
     u.hm = c.take<float>(P * 512);
-    u.pre[0] = c.take<float>(P * 256); u.pre[1] = c.take<float>(P * 128);
-    u.pre[2] = c.take<float>(P * 256); u.pre[3] = c.take<float>(P * 128);
+    u.pre[0] = c.take<float>(Pt * 256); u.pre[1] = c.take<float>(Pt * 128);
+    u.pre[2] = c.take<float>(Pt * 256); u.pre[3] = c.take<float>(Pt * 128);
     u.zero_bias = c.take<float>(1024);
     for (int k = 0; k < 2; ++k) {
         u.corr_h[k] = c.take<__half>(P * B200POSE_CORR_PITCH);
@@ -124,7 +125,7 @@ int run_update_block_tc(const float* wts, float* net, float* coords1, float* flo
         a.B = B; a.h = h; a.w = w; a.epi = epi; a.scale = scale;
         a.out_f32 = out_f32; a.out_f32_pitch = f32_pitch;
         if (dst) { a.out_hi = dst[0] + doff; a.out_lo = dst[1] + doff; a.out_h_pitch = dpitch; }
-        a.zbuf = u.zbuf; a.hbuf = net;
+        a.zbuf = u.zbuf; a.hbuf = u.rhbuf; a.side_tiled = 1;       // h: tiled fp32 copy of the hidden state (see callers)
         return b2p_launch_conv_umma(a, s);
     };
     if ((rc = b2p_im2col_f1(flow, B, h, w, nullptr, nullptr, u.col_h[0], u.col_h[1], u.x_h[0], u.x_h[1], s))) return rc;
@@ -162,6 +163,7 @@ int run_gru_precompute(const float* wts, int B, int h, int w, const UpdateWs& u,
         a.cin_pad = d.cin_pad; a.cout_pad = d.cout_pad; a.cout = d.cout; a.n_tile = d.n_tile; a.kh = d.kh; a.kw = d.kw;
         a.B = B; a.h = h; a.w = w; a.epi = EPI_SCALE; a.scale = 1.f;
         a.out_f32 = u.pre[k]; a.out_f32_pitch = d.cout;
+        a.out_tiled = 1; a.side_tiled = 1;                        // the consumers read the pre-sums as a tiled side buffer
         a.chunk_mask = 0x0Cu;                                     // chunks {2,3}: the inp channels
         a.layer_id = ids[k];
         int rc = b2p_launch_conv_umma(a, s);
@@ -352,7 +354,10 @@ int b200pose_update_block(const void* packed_weights, float* net, float* xbuf, c
     if ((rc = b2p_split_planes(corr, B200POSE_CORR_PITCH, B200POSE_CORR_PITCH, P, u.corr_h[0], u.corr_h[1], B200POSE_CORR_PITCH, s))) return rc;
     if ((rc = b2p_split_planes(net, 128, 128, P, u.net_h[0], u.net_h[1], 128, s))) return rc;
     if ((rc = b2p_split_planes(xbuf, 256, 128, P, u.x_h[0], u.x_h[1], 256, s))) return rc;
-    return run_update_block_tc(wts, net, coords1, flow, mask, dflow_out, B, h, w, u, false, s);
+    // the tensor-core epilogues keep the fp32 hidden state in the tiled side-buffer layout (u.rhbuf)
+    if ((rc = b2p_pxc_to_tiled(net, u.rhbuf, B, h, w, 128, s))) return rc;
+    if ((rc = run_update_block_tc(wts, net, coords1, flow, mask, dflow_out, B, h, w, u, false, s))) return rc;
+    return b2p_tiled_to_pxc(u.rhbuf, net, B, h, w, 128, s);
 }
 
 size_t b200pose_conv_layer_workspace_bytes(int B, int h, int w) { return (size_t)B * h * w * 384 * 2 * sizeof(__half) + 4096; }
@@ -489,6 +494,7 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
     if (tc) rc = b2p_context_init(context, B, H, W, r.net, nullptr, u.net_h[0], u.net_h[1], u.x_h[0], u.x_h[1], s);
     else rc = b2p_context_init(context, B, H, W, r.net, r.xbuf, nullptr, nullptr, nullptr, nullptr, s);
     if (rc) return rc;
+    if (tc && (rc = b2p_pxc_to_tiled(r.net, u.rhbuf, B, h, w, 128, s))) return rc;     // hidden state of the tensor-core epilogues
     if (tc && n_iters > 1 && (rc = run_gru_precompute(wts, B, h, w, u, s))) return rc;
     for (int it = 0; it < n_iters; ++it) {
         if ((rc = b2p_flow_init(depth, K, G, B, H, W, r.coords1, r.flow, s))) return rc;

@@ -110,6 +110,20 @@ __host__ __device__ __forceinline__ void b2p_split_half(float v, __half& hi, __h
 #endif
 }
 
+// Tiled layout of the fp32 buffers that only the tensor-core epilogues touch (z gate, hidden state, GRU pre-sums):
+// [pixel tile (16 rows x 8 pixels, the conv_umma M tile)][C/4][128 pixels of the tile, row-major][4 channels].
+// The 32 pixels a warp owns are then contiguous for every float4 of channels.
+constexpr int B2P_TILE_ROWS = 16, B2P_TILE_COLS = 8;
+__host__ __device__ __forceinline__ size_t b2p_tiled_index(int tile, int m, int c, int C) {
+    return (((size_t)tile * (C >> 2) + (c >> 2)) * 128 + m) * 4 + (c & 3);
+}
+static inline size_t b2p_tiled_pixels(int B, int h, int w) {       // pixel slots of a tiled buffer (>= B*h*w)
+    return (size_t)B * ((h + B2P_TILE_ROWS - 1) / B2P_TILE_ROWS) * ((w + B2P_TILE_COLS - 1) / B2P_TILE_COLS) * 128;
+}
+// fp32 [P][C] pixel-major <-> tiled
+int b2p_pxc_to_tiled(const float* src, float* dst, int B, int h, int w, int C, cudaStream_t s);
+int b2p_tiled_to_pxc(const float* src, float* dst, int B, int h, int w, int C, cudaStream_t s);
+
 // fp16 weight planes: W[tap][cout_pad][cin_pad] (cin contiguous = K-major), cin_pad multiple of 64,
 // cout_pad multiple of n_tile.
 struct B2PHalfConvDesc {
@@ -135,6 +149,8 @@ struct UmmaConvArgs {
     unsigned chunk_mask;       // bit cc set = visit 64-channel chunk cc of every tap (0 = all chunks)
     const float* pre; int pre_pitch;   // fp32 [P][pre_pitch] partial sums added in the epilogue (or nullptr)
     int layer_id;              // B2PConvId of an update-block layer, or -1
+    int side_tiled;            // zbuf / hbuf / pre use the tiled side-buffer layout (b2p_tiled_index)
+    int out_tiled;             // EPI_SCALE: out_f32 is a tiled side buffer with out_f32_pitch channels
     int b_batched;             // weights differ per sample: 3rd weight-map coordinate = sample index (1x1 only)
 };
 int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s);

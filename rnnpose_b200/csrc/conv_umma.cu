@@ -56,6 +56,8 @@ struct UmmaConvParams {
     int a_rows;                        // rows of the activation box = 16 + a_taps - 1
     int ring_a, ring_b;                // ring depths
     int m_groups;                      // M tiles / CTAs per cluster, rounded up (a unit = one group x one N tile)
+    int side_tiled;                    // z / h / pre-sum side buffers use the tiled layout (b2p_tiled_index)
+    int out_tiled;                     // EPI_SCALE output is such a side buffer (the GRU pre-sum GEMMs)
     int dbg_layer;                     // row of g_conv_dbg (layer id + 1)
     int debug;                         // timing experiments only (results are garbage): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue
 };
@@ -163,10 +165,30 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
 }
 
+// 256-bit global stores (sm_100: STG.E.256): a thread's 32-byte row segment in one instruction and one L1 wavefront
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&w)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
 // Epilogue of one tile for one warp: TMEM -> registers -> bias / activation / GRU blend -> global (fp32 side outputs and the
 // fp16 hi/lo planes the next convolution reads).  `valid` = this thread's pixel lies inside the image.
+//
+// Every global access here is one pixel row segment per thread (thread = pixel), i.e. 32 different cache lines per warp
+// instruction: the L1 takes one wavefront per line, so the epilogue cost is (instructions x 32) wavefronts and the GRU
+// epilogues (24 loads + 16 stores per 32-channel group) took as long as their main loops.  Two remedies:
+//  * the fp32 side buffers that only the epilogues touch (z gate, hidden state h, GRU pre-sums) use a TILED layout
+//    [pixel tile][C/4][128 pixels][4] (b2p_tiled_index): the 32 pixels of a warp are contiguous, 4 lines per instruction;
+//  * the PXC rows that must stay pixel-major (TMA operand planes, mask) are written with 256-bit stores.
 __device__ __forceinline__ void epilogue_columns(const UmmaConvParams& p, uint32_t tmem_base, int warp, int q, int buf, int n0,
-                                                 int n_cnt, bool valid, size_t pix) {
+                                                 int n_cnt, bool valid, size_t pix, int tile, int mrow) {
+    // float4 slot of channel c (multiple of 4) of this thread's pixel in a side buffer with C channels; step between
+    // consecutive float4 slots: 1 (PXC) or 128 (tiled)
+    const int sstep = p.side_tiled ? 128 : 1;
+    auto side4 = [&](const float* base, int C, int c) -> const float4* {
+        return reinterpret_cast<const float4*>(base) +
+               (p.side_tiled ? ((size_t)tile * (C >> 2) + (c >> 2)) * 128 + mrow : (pix * C + c) >> 2);
+    };
     // the two warps of a lane quarter take alternate 32-column groups
     for (int col0 = ((warp - 2) >> 2) * 32; col0 < n_cnt; col0 += 64) {
         uint32_t r[32];
@@ -179,20 +201,20 @@ __device__ __forceinline__ void epilogue_columns(const UmmaConvParams& p, uint32
         const bool need_h = live && ((p.epi == EPI_GRU_ZR && nb >= 128) || p.epi == EPI_GRU_Q);
         const bool need_z = live && p.epi == EPI_GRU_Q;
         if (need_h) {
-            const float4* hp4 = reinterpret_cast<const float4*>(p.hbuf + pix * 128 + (nb & 127));
+            const float4* hp4 = side4(p.hbuf, 128, nb & 127);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) hh[j] = hp4[j];
+            for (int j = 0; j < 8; ++j) hh[j] = hp4[j * sstep];
         }
         if (need_z) {
-            const float4* zp4 = reinterpret_cast<const float4*>(p.zbuf + pix * 128 + nb);
+            const float4* zp4 = side4(p.zbuf, 128, nb);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) zz[j] = __ldg(zp4 + j);
+            for (int j = 0; j < 8; ++j) zz[j] = __ldg(zp4 + j * sstep);
         }
         float4 pre4[8];
         if (live && p.pre) {
-            const float4* pp = reinterpret_cast<const float4*>(p.pre + pix * p.pre_pitch + nb);
+            const float4* pp = side4(p.pre, p.pre_pitch, nb);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) pre4[j] = __ldg(pp + j);
+            for (int j = 0; j < 8; ++j) pre4[j] = __ldg(pp + j * sstep);
         }
         tmem_ld_wait(r);
         if (!live) continue;
@@ -213,24 +235,35 @@ __device__ __forceinline__ void epilogue_columns(const UmmaConvParams& p, uint32
         // multiple of 32, e.g. 240 for the correlation volume)
         const int lim = min(p.cout - nb, n_cnt - col0);
         if (p.epi == EPI_SCALE) {
-            float* d = p.out_f32 + pix * p.out_f32_pitch + nb;
+            if (p.out_tiled) {                             // GRU pre-sums: a side buffer of out_f32_pitch channels
+                float4* d = const_cast<float4*>(side4(p.out_f32, p.out_f32_pitch, nb));
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                if (j + 3 < lim) {
-                    *reinterpret_cast<float4*>(d + j) = make_float4(v[j] * p.scale, v[j + 1] * p.scale, v[j + 2] * p.scale, v[j + 3] * p.scale);
+                for (int j = 0; j < 8; ++j)
+                    if (4 * j + 3 < lim) d[j * sstep] = make_float4(v[4 * j] * p.scale, v[4 * j + 1] * p.scale, v[4 * j + 2] * p.scale, v[4 * j + 3] * p.scale);
+                continue;
+            }
+            float* d = p.out_f32 + pix * p.out_f32_pitch + nb;
+            const bool v8 = (p.out_f32_pitch & 7) == 0;    // 32-byte aligned row segments
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                if (v8 && j + 7 < lim) {
+                    uint32_t w8[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) w8[t] = __float_as_uint(v[j + t] * p.scale);
+                    st_global_v8(d + j, w8);
                 } else {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
+                    for (int t = 0; t < 8; ++t)
                         if (j + t < lim) d[j + t] = v[j + t] * p.scale;
                 }
             }
             continue;
         }
         if (p.epi == EPI_GRU_ZR && nb < 128) {            // z gate, kept in fp32 for the blend
-            float* d = p.zbuf + pix * 128 + nb;
+            float4* d = const_cast<float4*>(side4(p.zbuf, 128, nb));
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(d + j) = make_float4(sigm(v[j]), sigm(v[j + 1]), sigm(v[j + 2]), sigm(v[j + 3]));
+            for (int j = 0; j < 8; ++j)
+                d[j * sstep] = make_float4(sigm(v[4 * j]), sigm(v[4 * j + 1]), sigm(v[4 * j + 2]), sigm(v[4 * j + 3]));
             continue;
         }
         int oc = nb;                                       // output channel of v[0]
@@ -252,27 +285,33 @@ __device__ __forceinline__ void epilogue_columns(const UmmaConvParams& p, uint32
                 v[4 * j + 2] = (1.f - zz[j].z) * hh[j].z + zz[j].z * tanh_fast(v[4 * j + 2]);
                 v[4 * j + 3] = (1.f - zz[j].w) * hh[j].w + zz[j].w * tanh_fast(v[4 * j + 3]);
             }
-            float4* hp4 = reinterpret_cast<float4*>(p.hbuf + pix * 128 + nb);
+            float4* hp4 = const_cast<float4*>(side4(p.hbuf, 128, nb));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) hp4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) hp4[j * sstep] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        // fp16 hi/lo planes for the next convolution
+        // fp16 hi/lo planes for the next convolution: 16 channels = 32 bytes per store
         __half* dh = p.out_hi + pix * p.out_h_pitch + oc;
         __half* dl = p.out_lo + pix * p.out_h_pitch + oc;
         const int cvalid = lim;
+        const bool h16 = (p.out_h_pitch & 15) == 0 && (oc & 15) == 0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            __align__(16) __half hi8[8];
-            __align__(16) __half lo8[8];
+        for (int j = 0; j < 32; j += 16) {
+            __half hi16[16], lo16[16];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) b2p_split_half(v[j + t], hi8[t], lo8[t]);
-            if (j + 7 < cvalid) {
-                *reinterpret_cast<uint4*>(dh + j) = *reinterpret_cast<const uint4*>(hi8);
-                *reinterpret_cast<uint4*>(dl + j) = *reinterpret_cast<const uint4*>(lo8);
+            for (int t = 0; t < 16; ++t) b2p_split_half(v[j + t], hi16[t], lo16[t]);
+            if (h16 && j + 15 < cvalid) {
+                uint32_t wh[8], wl[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    wh[t] = (uint32_t)__half_as_ushort(hi16[2 * t]) | ((uint32_t)__half_as_ushort(hi16[2 * t + 1]) << 16);
+                    wl[t] = (uint32_t)__half_as_ushort(lo16[2 * t]) | ((uint32_t)__half_as_ushort(lo16[2 * t + 1]) << 16);
+                }
+                st_global_v8(dh + j, wh);
+                st_global_v8(dl + j, wl);
             } else {
 #pragma unroll
-                for (int t = 0; t < 8; ++t)
-                    if (j + t < cvalid) { dh[j + t] = hi8[t]; dl[j + t] = lo8[t]; }
+                for (int t = 0; t < 16; ++t)
+                    if (j + t < cvalid) { dh[j + t] = hi16[t]; dl[j + t] = lo16[t]; }
             }
         }
     }
@@ -319,7 +358,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     // CTAs of one round share the weight tile (L2) and walk over different pixel tiles
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int nk = p.kh * p.kw * p.n_active;
-    auto decode = [&](int u, int& bimg, int& y0, int& x0, int& n0, int& n_cnt) {
+    auto decode = [&](int u, int& bimg, int& y0, int& x0, int& n0, int& n_cnt, int& m_idx) {
         int t = u, sub = 0;
         n_cnt = p.n_tile;
         if (u >= p.full_units) {
@@ -327,7 +366,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
             t = p.full_units + v / p.split; sub = v - (v / p.split) * p.split;
             n_cnt = p.n_sub;
         }
-        const int n_idx = t / p.m_tiles, m_idx = t - n_idx * p.m_tiles;
+        const int n_idx = t / p.m_tiles;
+        m_idx = t - n_idx * p.m_tiles;
         bimg = m_idx / tiles_per_img;
         const int trem = m_idx - bimg * tiles_per_img;
         y0 = (trem / p.tiles_x) * TILE_ROWS; x0 = (trem % p.tiles_x) * TILE_COLS;
@@ -361,8 +401,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         const bool timed = (p.debug & 16) != 0;
         unsigned long long w_empty = 0;
         for (int t = blockIdx.x; t < p.total_units; t += gridDim.x) {
-            int bimg, y0, x0, n0, n_cnt;
-            decode(t, bimg, y0, x0, n0, n_cnt);
+            int bimg, y0, x0, n0, n_cnt, m_idx;
+            decode(t, bimg, y0, x0, n0, n_cnt, m_idx);
             const bool whole = n_cnt == p.n_tile;
             const CUtensorMap* bh = whole ? &p.b_hi : &p.bs_hi;
             const CUtensorMap* bl = whole ? &p.b_lo : &p.bs_lo;
@@ -453,8 +493,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         const bool timed = (p.debug & 16) != 0 && warp == 2;
         unsigned long long w_tfull = 0, busy = 0;
         for (int t = blockIdx.x; t < p.total_units; t += gridDim.x, ++tile_iter) {
-        int bimg, y0, x0, n0, n_cnt;
-        decode(t, bimg, y0, x0, n0, n_cnt);
+        int bimg, y0, x0, n0, n_cnt, m_idx;
+        decode(t, bimg, y0, x0, n0, n_cnt, m_idx);
         const int buf = tile_iter & 1;
         const long long e0 = timed ? clock64() : 0;
         const int yy = y0 + (mrow >> 3), xx = x0 + (mrow & 7);
@@ -463,7 +503,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         mbar_wait_backoff(tmem_full_bar(buf), (tile_iter >> 1) & 1);
         const long long e1 = timed ? clock64() : 0;
         tc_fence_after();
-        if (!(p.debug & 4)) epilogue_columns(p, tmem_base, warp, q, buf, n0, n_cnt, valid, pix);
+        if (!(p.debug & 4)) epilogue_columns(p, tmem_base, warp, q, buf, n0, n_cnt, valid, pix, m_idx, mrow);
         if (timed) { w_tfull += (unsigned long long)(e1 - e0); busy += (unsigned long long)(clock64() - e1); }
         // every TMEM read of this tile has completed (tcgen05.wait::ld above): hand the buffer back to the MMA warp
         tc_fence_before();
@@ -564,7 +604,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     // a unit = (N tile or sub-tile) x (group of NCTA consecutive M tiles); CTA `rank` of the cluster owns M tile group*NCTA+rank.
     // A group that runs past the last M tile repeats it and discards the result (`real` = false).
-    auto decode = [&](int u, int& bimg, int& y0, int& x0, int& n0, int& n_cnt, bool& real) {
+    auto decode = [&](int u, int& bimg, int& y0, int& x0, int& n0, int& n_cnt, bool& real, int& m_idx) {
         int t = u, sub = 0;
         n_cnt = p.n_tile;
         if (u >= p.full_units) {
@@ -573,7 +613,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
             n_cnt = p.n_sub;
         }
         const int n_idx = t / p.m_groups;
-        int m_idx = (t - n_idx * p.m_groups) * NCTA + (int)rank;
+        m_idx = (t - n_idx * p.m_groups) * NCTA + (int)rank;
         real = m_idx < p.m_tiles;
         if (!real) m_idx = p.m_tiles - 1;
         bimg = m_idx / tiles_per_img;
@@ -616,8 +656,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
         const bool timed = (p.debug & 16) != 0;
         unsigned long long w_empty = 0;
         for (int u = unit0; u < p.total_units; u += unit_step) {
-            int bimg, y0, x0, n0, n_cnt; bool real;
-            decode(u, bimg, y0, x0, n0, n_cnt, real);
+            int bimg, y0, x0, n0, n_cnt, m_idx; bool real;
+            decode(u, bimg, y0, x0, n0, n_cnt, real, m_idx);
             const bool whole = n_cnt == p.n_tile;
             const CUtensorMap* bh = whole ? &p.b_hi : &p.bs_hi;
             const CUtensorMap* bl = whole ? &p.b_lo : &p.bs_lo;
@@ -751,8 +791,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
         const bool timed = (p.debug & 16) != 0 && warp == 2;
         unsigned long long w_tfull = 0, busy = 0;
         for (int u = unit0; u < p.total_units; u += unit_step, ++tile_iter) {
-            int bimg, y0, x0, n0, n_cnt; bool real;
-            decode(u, bimg, y0, x0, n0, n_cnt, real);
+            int bimg, y0, x0, n0, n_cnt, m_idx; bool real;
+            decode(u, bimg, y0, x0, n0, n_cnt, real, m_idx);
             const int buf = tile_iter & 1;
             const long long e0 = timed ? clock64() : 0;
             const int yy = y0 + (mrow >> 3), xx = x0 + (mrow & 7);
@@ -761,7 +801,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
             mbar_wait_backoff(tmem_full_bar(buf), (tile_iter >> 1) & 1);
             const long long e1 = timed ? clock64() : 0;
             tc_fence_after();
-            if (!(p.debug & 4)) epilogue_columns(p, tmem_base, warp, q, buf, n0, n_cnt, valid, pix);
+            if (!(p.debug & 4)) epilogue_columns(p, tmem_base, warp, q, buf, n0, n_cnt, valid, pix, m_idx, mrow);
             if (timed) { w_tfull += (unsigned long long)(e1 - e0); busy += (unsigned long long)(clock64() - e1); }
             tc_fence_before();
             if (NCTA == 2) mbar_arrive_cluster(mapa_rank(tmem_empty_bar(buf), 0));
@@ -994,6 +1034,7 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     p.out_f32 = a.out_f32; p.out_f32_pitch = a.out_f32_pitch;
     p.out_hi = a.out_hi; p.out_lo = a.out_lo; p.out_h_pitch = a.out_h_pitch;
     p.zbuf = a.zbuf; p.hbuf = a.hbuf;
+    p.side_tiled = a.side_tiled; p.out_tiled = a.out_tiled;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
     const int sms = device_sms();
     if (sms <= 0) return (int)cudaErrorInvalidDevice;

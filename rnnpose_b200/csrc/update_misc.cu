@@ -194,6 +194,32 @@ __global__ void __launch_bounds__(128) flow_head2_gather_kernel(const float* __r
     *reinterpret_cast<float2*>(flow + (size_t)pix * 2) = make_float2(c1.x - (float)x, c1.y - (float)y);
 }
 
+
+// fp32 [P][C] pixel-major <-> the tiled side-buffer layout (common.cuh: b2p_tiled_index); one thread per float4
+template <bool TO_TILED>
+__global__ void __launch_bounds__(256) tiled_convert_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int h,
+                                                            int w, int C) {
+    pdl_trigger();
+    pdl_wait();
+    const int tiles_x = (w + B2P_TILE_COLS - 1) / B2P_TILE_COLS, tiles_y = (h + B2P_TILE_ROWS - 1) / B2P_TILE_ROWS;
+    const size_t total = (size_t)B * tiles_x * tiles_y * (C >> 2) * 128;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int m = (int)(i & 127);
+    const size_t t2 = i >> 7;
+    const int c4 = (int)(t2 % (size_t)(C >> 2));
+    const int tile = (int)(t2 / (size_t)(C >> 2));
+    const int b = tile / (tiles_x * tiles_y), tr = tile - b * tiles_x * tiles_y;
+    const int y = (tr / tiles_x) * B2P_TILE_ROWS + (m >> 3), x = (tr % tiles_x) * B2P_TILE_COLS + (m & 7);
+    const bool in = y < h && x < w;
+    const size_t pxc = (((size_t)b * h + y) * w + x) * C + c4 * 4;
+    if (TO_TILED) {
+        reinterpret_cast<float4*>(dst)[i] = in ? *reinterpret_cast<const float4*>(src + pxc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (in) {
+        *reinterpret_cast<float4*>(dst + pxc) = reinterpret_cast<const float4*>(src)[i];
+    }
+}
+
 B2PWeightLayout make_layout() {
     B2PWeightLayout L;
     auto set = [&](int id, int kh, int kw, int cin, int cout) {
@@ -344,6 +370,20 @@ int b2p_flow_head2(const float* hm, const __half* hm_hi, const __half* hm_lo, co
     B2P_LAUNCH_CHECK();
     B2P_CUDA(b2p_launch_pdl(flow_head2_gather_kernel, dim3(ceil_div(npix, 128)), dim3(128), 0, s, (const float*)part, b2, coords1, flow,
                             dflow_out, B, h, w));
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2p_pxc_to_tiled(const float* src, float* dst, int B, int h, int w, int C, cudaStream_t s) {
+    const size_t total = b2p_tiled_pixels(B, h, w) * (size_t)(C >> 2);
+    B2P_CUDA(b2p_launch_pdl(tiled_convert_kernel<true>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, src, dst, B, h, w, C));
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2p_tiled_to_pxc(const float* src, float* dst, int B, int h, int w, int C, cudaStream_t s) {
+    const size_t total = b2p_tiled_pixels(B, h, w) * (size_t)(C >> 2);
+    B2P_CUDA(b2p_launch_pdl(tiled_convert_kernel<false>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, src, dst, B, h, w, C));
     B2P_LAUNCH_CHECK();
     return 0;
 }
