@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -54,6 +55,11 @@ size_t update_ws_layout(int B, int h, int w, void* ws, size_t cap, UpdateWs* out
     }
     if (out) *out = u;
     return align_up(c.off, 1024);
+}
+
+inline bool fg_list_enabled() {
+    const char* e = getenv("B200POSE_FG_LIST");
+    return !(e && *e == '0');
 }
 
 inline bool shape_ok(int B, int H, int W) {
@@ -230,6 +236,7 @@ int run_corr_volume_tc(const float* fmap1, const float* fmap2, int B, int h, int
 struct RefineWs {
     float *pyr, *net, *xbuf, *corr, *coords1, *flow, *mask, *target, *weight;
     void* lm;
+    void* fg;                     // foreground list of the call (b2p_fg_build)
     VolumeWs vol;
     UpdateWs u;
 };
@@ -249,6 +256,7 @@ size_t refine_ws_layout(int B, int H, int W, void* ws, size_t cap, RefineWs* out
     r.target = c.take<float>(N * 2);
     r.weight = c.take<float>(N);
     r.lm = c.take<char>(b2p_lm_ws_bytes(B, H, W));
+    r.fg = c.take<char>(b2p_fg_ws_bytes(B, H, W));
     c.off = align_up(c.off, 1024);
     c.off += volume_ws_layout(B, h, w, ws ? c.base + c.off : nullptr, 0, &r.vol);
     const size_t used = update_ws_layout(B, h, w, ws ? c.base + c.off : nullptr, cap > c.off ? cap - c.off : 0, &r.u);
@@ -462,9 +470,10 @@ size_t b200pose_refine_workspace_bytes(int B, int H, int W) { return refine_ws_l
 int b200pose_refine_launch_count(int n_iters, int n_lm) {
     // per render iteration: volume + 3 pools + context;  per recurrent iteration: flow_init, lookup,
     // update block, upsample+weight, 1 launch per LM step (+1 counter reset per call)
-    // (tensor-core path: counter reset, 2 feature-map transposes, volume GEMM, 3 pools, context = 8 per call,
-    //  + 4 GRU partial-sum GEMMs when there is more than one recurrent iteration)
-    return 8 + (n_iters > 1 ? 4 : 0) + n_iters * (2 + UPDATE_LAUNCHES + 1 + (n_lm > 1 ? 1 : n_lm));
+    // (tensor-core path: counter reset, 2 feature-map transposes, volume GEMM, 3 pools, context, hidden state to the tiled
+    //  layout = 9 per call, + 4 GRU partial-sum GEMMs when there is more than one recurrent iteration)
+    // + 3 launches that build the foreground list of the call
+    return 9 + (n_iters > 0 ? 3 : 0) + (n_iters > 1 ? 4 : 0) + n_iters * (2 + UPDATE_LAUNCHES + 1 + (n_lm > 1 ? 1 : n_lm));
 }
 
 int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const float* fmap2, const float* context,
@@ -496,6 +505,12 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
     if (rc) return rc;
     if (tc && (rc = b2p_pxc_to_tiled(r.net, u.rhbuf, B, h, w, 128, s))) return rc;     // hidden state of the tensor-core epilogues
     if (tc && n_iters > 1 && (rc = run_gru_precompute(wts, B, h, w, u, s))) return rc;
+    // The rendered depth is fixed over the recurrent iterations: compact its foreground once, and run the per-iteration
+    // full-resolution kernels (upsample + weight, LM) over the list (B200POSE_FG_LIST=0: dense kernels).
+    const bool use_fg = n_iters > 0 && fg_list_enabled();
+    if (use_fg && (rc = b2p_fg_build(depth, B, H, W, r.fg, r.target, r.weight, s))) return rc;
+    const int* fg_idx = use_fg ? b2p_fg_idx(r.fg) : nullptr;
+    const int* fg_count = use_fg ? b2p_fg_count(r.fg, B, H, W) : nullptr;
     for (int it = 0; it < n_iters; ++it) {
         if ((rc = b2p_flow_init(depth, K, G, B, H, W, r.coords1, r.flow, s))) return rc;
         if (tc) {
@@ -506,11 +521,14 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
             if ((rc = run_update_block(wts, r.net, r.xbuf, r.corr, r.coords1, r.flow, r.mask, nullptr, B, h, w, u, s))) return rc;
         }
         float* fu = (it == 0 && flow_first) ? flow_first : ((it == n_iters - 1) ? flow_last : nullptr);
-        if ((rc = b2p_upsample_weight(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, fu, r.target,
-                                      r.weight, 1, s))) return rc;
+        if (use_fg && !fu) {
+            if ((rc = b2p_upsample_weight_fg(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, r.fg, r.target, r.weight, s)))
+                return rc;
+        } else if ((rc = b2p_upsample_weight(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, fu, r.target,
+                                             r.weight, 1, s))) return rc;
         if (it == 0 && it == n_iters - 1 && flow_first && flow_last)
             B2P_CUDA(cudaMemcpyAsync(flow_last, flow_first, (size_t)B * 2 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        if ((rc = b2p_lm_steps(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, n_lm, r.lm, s))) return rc;
+        if ((rc = b2p_lm_steps(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, n_lm, r.lm, s, fg_idx, fg_count))) return rc;
     }
     if (weight_last && n_iters > 0)
         B2P_CUDA(cudaMemcpyAsync(weight_last, r.weight, (size_t)B * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -177,11 +177,20 @@ int b2p_flow_head2(const float* hm /*[P][512] fp32, first 256 = flow-head featur
 int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth,
                         float sigma, int B, int C, int H, int W, float* flow_up, float* target, float* weight,
                         int lazy_background, cudaStream_t s);
+// foreground list (depth > 0 or non-finite) of a call, built once; see upsample_weight.cu
+size_t b2p_fg_ws_bytes(int B, int H, int W);
+int b2p_fg_build(const float* depth, int B, int H, int W, void* fg_ws, float* target, float* weight, cudaStream_t s);
+const int* b2p_fg_idx(const void* fg_ws);
+const int* b2p_fg_count(const void* fg_ws, int B, int H, int W);
+int b2p_upsample_weight_fg(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth, float sigma,
+                           int B, int C, int H, int W, const void* fg_ws, float* target, float* weight, cudaStream_t s);
 int b2p_lm_step(const float* depth, const float* target, const float* weight, const float* K, float* G,
                 int B, int H, int W, float depth_add, double ep, double lm, double* H_out, double* b_out,
                 float* delta_out, void* ws, cudaStream_t s);
+// fg_idx / fg_count != nullptr: visit only the listed pixels (every other pixel must have weight 0 and finite inputs)
 int b2p_lm_steps(const float* depth, const float* target, const float* weight, const float* K, float* G,
-                 int B, int H, int W, float depth_add, double ep, double lm, int n_steps, void* ws, cudaStream_t s);
+                 int B, int H, int W, float depth_add, double ep, double lm, int n_steps, void* ws, cudaStream_t s,
+                 const int* fg_idx = nullptr, const int* fg_count = nullptr);
 size_t b2p_lm_ws_bytes(int B, int H, int W);
 int b2p_lm_reset(void* ws, int B, int H, int W, cudaStream_t s);   // once before the first b2p_lm_step on a workspace
 size_t b2p_pose_metrics_ws_bytes(int B, int n);

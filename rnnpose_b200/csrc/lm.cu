@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(LM_THREADS) lm_step_kernel(
 __global__ void __launch_bounds__(LM_THREADS) lm_multi_kernel(
     const float* __restrict__ depth, const float* __restrict__ target, const float* __restrict__ weight,
     const float* __restrict__ K, float* __restrict__ G, int B, int H, int W, float depth_add, double ep, double lm,
-    int n_steps, double* __restrict__ partials /*[2][B][nb][27]*/, unsigned* __restrict__ counters) {
+    int n_steps, double* __restrict__ partials /*[2][B][nb][27]*/, unsigned* __restrict__ counters,
+    const int* __restrict__ fg_idx, const int* __restrict__ fg_count) {
     pdl_trigger();
     pdl_wait();
     const int b = blockIdx.y, nb = gridDim.x, tid = threadIdx.x;
@@ -287,9 +288,12 @@ __global__ void __launch_bounds__(LM_THREADS) lm_multi_kernel(
     const float* dptr = depth + (size_t)b * N;
     const float2* tptr = reinterpret_cast<const float2*>(target) + (size_t)b * N;
     const float* wptr = weight + (size_t)b * N;
-    // contiguous pixel range of this block
-    const int per = (N + nb - 1) / nb;
-    const int p_begin = blockIdx.x * per, p_end = min(N, p_begin + per);
+    // contiguous range of this block: of the pixels, or of the sample's foreground list (every unlisted pixel has weight
+    // exactly 0 and finite inputs, i.e. contributes exactly 0)
+    const int* fidx = fg_idx ? fg_idx + (size_t)b * N : nullptr;
+    const int count = fg_idx ? fg_count[b] : N;
+    const int per = (count + nb - 1) / nb;
+    const int p_begin = blockIdx.x * per, p_end = min(count, p_begin + per);
     unsigned* arrive = counters + 2 * b;
     unsigned* finished = counters + 2 * b + 1;
 
@@ -303,18 +307,22 @@ __global__ void __launch_bounds__(LM_THREADS) lm_multi_kernel(
         for (int base = p_begin; base < p_end; base += LM_PX_PER_BLOCK) {
             float Zs[LM_PX_PER_THREAD], ws_[LM_PX_PER_THREAD];
             float2 tgs[LM_PX_PER_THREAD];
+            int rs[LM_PX_PER_THREAD];
 #pragma unroll
             for (int it = 0; it < LM_PX_PER_THREAD; ++it) {
                 const int px = base + it * LM_THREADS + tid;
-                const bool in = px < p_end;
-                Zs[it] = in ? __ldg(dptr + px) : 0.f;
-                tgs[it] = in ? __ldg(tptr + px) : make_float2(0.f, 0.f);
-                ws_[it] = in ? __ldg(wptr + px) : 0.f;
+                rs[it] = px < p_end ? (fidx ? __ldg(fidx + px) : px) : -1;
             }
 #pragma unroll
             for (int it = 0; it < LM_PX_PER_THREAD; ++it) {
-                const int px = base + it * LM_THREADS + tid;
-                if (px < p_end) lm_pixel(acc, px % W, px / W, Zs[it], tgs[it], ws_[it], depth_add, fx, fy, cx, cy, Gm);
+                const bool in = rs[it] >= 0;
+                Zs[it] = in ? __ldg(dptr + rs[it]) : 0.f;
+                tgs[it] = in ? tptr[rs[it]] : make_float2(0.f, 0.f);
+                ws_[it] = in ? wptr[rs[it]] : 0.f;
+            }
+#pragma unroll
+            for (int it = 0; it < LM_PX_PER_THREAD; ++it) {
+                if (rs[it] >= 0) lm_pixel(acc, rs[it] % W, rs[it] / W, Zs[it], tgs[it], ws_[it], depth_add, fx, fy, cx, cy, Gm);
             }
         }
         double mine;
@@ -413,7 +421,8 @@ int b2p_lm_step(const float* depth, const float* target, const float* weight, co
 
 // All n_steps in one launch when the blocks can be co-resident; otherwise n_steps single-step launches.
 int b2p_lm_steps(const float* depth, const float* target, const float* weight, const float* K, float* G, int B, int H,
-                 int W, float depth_add, double ep, double lm, int n_steps, void* ws, cudaStream_t s) {
+                 int W, float depth_add, double ep, double lm, int n_steps, void* ws, cudaStream_t s, const int* fg_idx,
+                 const int* fg_count) {
     if (n_steps <= 0) return 0;
     int dev = 0, sms = 0, per_sm = 0;
     B2P_CUDA(cudaGetDevice(&dev));
@@ -435,7 +444,7 @@ int b2p_lm_steps(const float* depth, const float* target, const float* weight, c
     unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + lm_partials_bytes(B, H, W));
     dim3 grid(nb, B);
     B2P_CUDA(b2p_launch_pdl(lm_multi_kernel, grid, dim3(LM_THREADS), 0, s, depth, target, weight, K, G, B, H, W, depth_add, ep, lm, n_steps,
-                            partials, counters));
+                            partials, counters, fg_idx, fg_count));
     B2P_LAUNCH_CHECK();
     return 0;
 }

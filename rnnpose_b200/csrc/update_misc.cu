@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(256) im2col_f1_kernel(const float* __restrict_
 //       coords1 += delta, flow = coords1 - coords0  (model/CFNet.py:157,166).
 constexpr int FH2_PITCH = 20;      // 18 partial sums per pixel, rows padded to 16-byte multiples
 
+constexpr int FH2_PX = 2;          // pixels per lane quad: every weight vector read from shared memory serves both
+
 __global__ void __launch_bounds__(256) flow_head2_partial_kernel(const float* __restrict__ hm, const __half* __restrict__ hm_hi,
                                                                  const __half* __restrict__ hm_lo, const float* __restrict__ w2,
                                                                  float* __restrict__ part, int npix) {
@@ -120,52 +122,66 @@ __global__ void __launch_bounds__(256) flow_head2_partial_kernel(const float* __
     __syncthreads();
     pdl_wait();
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int pix = gid >> 2, q = gid & 3;
-    const bool live = pix < npix;
-    float acc[18];
+    const int pix0 = (gid >> 2) * FH2_PX, q = gid & 3;
+    float acc[FH2_PX][18];
 #pragma unroll
-    for (int k = 0; k < 18; ++k) acc[k] = 0.f;
-    if (live) {
-        const size_t so = (size_t)pix * 512;
+    for (int u = 0; u < FH2_PX; ++u)
+#pragma unroll
+        for (int k = 0; k < 18; ++k) acc[u][k] = 0.f;
+    if (pix0 < npix) {
 #pragma unroll 2
         for (int it = 0; it < 8; ++it) {
             const int c = (it * 4 + q) * 8;                // the quad reads 64 contiguous bytes of each fp16 plane
-            float a[8];
-            if (hm) {
-                const float4 a0 = __ldg(reinterpret_cast<const float4*>(hm + so + c));
-                const float4 a1 = __ldg(reinterpret_cast<const float4*>(hm + so + c + 4));
-                a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-            } else {
-                const uint4 uh = __ldg(reinterpret_cast<const uint4*>(hm_hi + so + c));
-                const uint4 ul = __ldg(reinterpret_cast<const uint4*>(hm_lo + so + c));
-                const __half2* hh = reinterpret_cast<const __half2*>(&uh);
-                const __half2* ll = reinterpret_cast<const __half2*>(&ul);
+            float a[FH2_PX][8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    a[2 * j] = __low2float(hh[j]) + __low2float(ll[j]);
-                    a[2 * j + 1] = __high2float(hh[j]) + __high2float(ll[j]);
+            for (int u = 0; u < FH2_PX; ++u) {
+                const size_t so = (size_t)min(pix0 + u, npix - 1) * 512;
+                if (hm) {
+                    const float4 a0 = __ldg(reinterpret_cast<const float4*>(hm + so + c));
+                    const float4 a1 = __ldg(reinterpret_cast<const float4*>(hm + so + c + 4));
+                    a[u][0] = a0.x; a[u][1] = a0.y; a[u][2] = a0.z; a[u][3] = a0.w;
+                    a[u][4] = a1.x; a[u][5] = a1.y; a[u][6] = a1.z; a[u][7] = a1.w;
+                } else {
+                    const uint4 uh = __ldg(reinterpret_cast<const uint4*>(hm_hi + so + c));
+                    const uint4 ul = __ldg(reinterpret_cast<const uint4*>(hm_lo + so + c));
+                    const __half2* hh = reinterpret_cast<const __half2*>(&uh);
+                    const __half2* ll = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        a[u][2 * j] = __low2float(hh[j]) + __low2float(ll[j]);
+                        a[u][2 * j + 1] = __high2float(hh[j]) + __high2float(ll[j]);
+                    }
                 }
             }
 #pragma unroll
             for (int k = 0; k < 18; ++k) {
                 const float4 u0 = *reinterpret_cast<const float4*>(&ws[k][c]);
                 const float4 u1 = *reinterpret_cast<const float4*>(&ws[k][c + 4]);
-                acc[k] += a[0] * u0.x + a[1] * u0.y + a[2] * u0.z + a[3] * u0.w + a[4] * u1.x + a[5] * u1.y + a[6] * u1.z + a[7] * u1.w;
+#pragma unroll
+                for (int u = 0; u < FH2_PX; ++u)
+                    acc[u][k] += a[u][0] * u0.x + a[u][1] * u0.y + a[u][2] * u0.z + a[u][3] * u0.w + a[u][4] * u1.x + a[u][5] * u1.y +
+                                 a[u][6] * u1.z + a[u][7] * u1.w;
             }
         }
     }
 #pragma unroll
-    for (int k = 0; k < 18; ++k) {
-        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
-        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
-    }
-    if (live && q == 0) {
-        float4* d = reinterpret_cast<float4*>(part + (size_t)pix * FH2_PITCH);
-        d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        d[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
-        d[3] = make_float4(acc[12], acc[13], acc[14], acc[15]);
-        d[4] = make_float4(acc[16], acc[17], 0.f, 0.f);
+    for (int u = 0; u < FH2_PX; ++u)
+#pragma unroll
+        for (int k = 0; k < 18; ++k) {
+            acc[u][k] += __shfl_xor_sync(0xffffffffu, acc[u][k], 1);
+            acc[u][k] += __shfl_xor_sync(0xffffffffu, acc[u][k], 2);
+        }
+    if (q == 0) {
+#pragma unroll
+        for (int u = 0; u < FH2_PX; ++u) {
+            if (pix0 + u >= npix) continue;
+            float4* d = reinterpret_cast<float4*>(part + (size_t)(pix0 + u) * FH2_PITCH);
+            d[0] = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+            d[1] = make_float4(acc[u][4], acc[u][5], acc[u][6], acc[u][7]);
+            d[2] = make_float4(acc[u][8], acc[u][9], acc[u][10], acc[u][11]);
+            d[3] = make_float4(acc[u][12], acc[u][13], acc[u][14], acc[u][15]);
+            d[4] = make_float4(acc[u][16], acc[u][17], 0.f, 0.f);
+        }
     }
 }
 
@@ -366,7 +382,7 @@ int b2p_im2col_f1(const float* flow, int B, int h, int w, float* col, float* xbu
 int b2p_flow_head2(const float* hm, const __half* hm_hi, const __half* hm_lo, const float* w2, const float* b2,
                    float* coords1, float* flow, float* dflow_out, float* part, int B, int h, int w, cudaStream_t s) {
     const int npix = B * h * w;
-    B2P_CUDA(b2p_launch_pdl(flow_head2_partial_kernel, dim3(ceil_div(npix * 4, 256)), dim3(256), 0, s, hm, hm_hi, hm_lo, w2, part, npix));
+    B2P_CUDA(b2p_launch_pdl(flow_head2_partial_kernel, dim3(ceil_div(ceil_div(npix, FH2_PX) * 4, 256)), dim3(256), 0, s, hm, hm_hi, hm_lo, w2, part, npix));
     B2P_LAUNCH_CHECK();
     B2P_CUDA(b2p_launch_pdl(flow_head2_gather_kernel, dim3(ceil_div(npix, 128)), dim3(128), 0, s, (const float*)part, b2, coords1, flow,
                             dflow_out, B, h, w));

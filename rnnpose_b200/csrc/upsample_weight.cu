@@ -12,31 +12,18 @@
 
 namespace {
 
-__global__ void __launch_bounds__(64) upsample_weight_kernel(
-    const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1,
-    const float* __restrict__ g2, const float* __restrict__ depth, float sigma, int B, int C, int H, int W,
-    float* __restrict__ flow_up, float* __restrict__ target, float* __restrict__ weight, int lazy_background) {
-    pdl_trigger();
-    pdl_wait();
+// Everything for one full-resolution pixel (b, Y, X): convex upsampling, target, descriptor similarity weight.
+__device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ flow, const float* __restrict__ mask,
+                                                      const float* __restrict__ g1, const float* __restrict__ g2,
+                                                      const float* __restrict__ depth, float sigma, int b, int Y, int X, int C, int H,
+                                                      int W, float* __restrict__ flow_up, float* __restrict__ target,
+                                                      float* __restrict__ weight) {
     const int h = H >> 3, w = W >> 3;
     const size_t N = (size_t)H * W;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)B * N) return;
-    const int b = (int)(idx / N);
-    const int r = (int)(idx - (size_t)b * N);
-    const int Y = r / W, X = r - Y * W;
+    const int r = Y * W + X;
+    const size_t idx = (size_t)b * N + r;
     const int y = Y >> 3, i = Y & 7, x = X >> 3, j = X & 7;
     const size_t p = ((size_t)b * h + y) * w + x;
-
-    // Fused-loop shortcut: a background pixel (syn_depth <= 0) has weight exactly 0, so the LM step ignores its target
-    // (any finite value contributes 0 * finite = 0, as in the reference).  When the up-sampled flow itself is not an
-    // output of this iteration, skip the mask softmax and the descriptor warp for it.
-    if (lazy_background && !flow_up && depth[idx] <= 0.f) {
-        if (target) *reinterpret_cast<float2*>(target + idx * 2) = make_float2((float)X, (float)Y);
-        if (weight) weight[idx] = 0.f;
-        return;
-    }
-
     // softmax over the 9 taps of mask[p][k*64 + i*8 + j]
     const float* mp = mask + p * 576 + i * 8 + j;
     float mk[9];
@@ -104,6 +91,134 @@ __global__ void __launch_bounds__(64) upsample_weight_kernel(
     weight[idx] = wgt;
 }
 
+__global__ void __launch_bounds__(64) upsample_weight_kernel(
+    const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1,
+    const float* __restrict__ g2, const float* __restrict__ depth, float sigma, int B, int C, int H, int W,
+    float* __restrict__ flow_up, float* __restrict__ target, float* __restrict__ weight, int lazy_background) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t N = (size_t)H * W;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * N) return;
+    const int b = (int)(idx / N);
+    const int r = (int)(idx - (size_t)b * N);
+    const int Y = r / W, X = r - Y * W;
+    // Fused-loop shortcut: a background pixel (syn_depth <= 0) has weight exactly 0, so the LM step ignores its target
+    // (any finite value contributes 0 * finite = 0, as in the reference).  When the up-sampled flow itself is not an
+    // output of this iteration, skip the mask softmax and the descriptor warp for it.
+    if (lazy_background && !flow_up && depth[idx] <= 0.f) {
+        if (target) *reinterpret_cast<float2*>(target + idx * 2) = make_float2((float)X, (float)Y);
+        if (weight) weight[idx] = 0.f;
+        return;
+    }
+    upsample_weight_pixel(flow, mask, g1, g2, depth, sigma, b, Y, X, C, H, W, flow_up, target, weight);
+}
+
+// ------------------------------------------------------------------------------------------------ foreground list
+// The rendered depth does not change over the recurrent iterations of a call, so the set of pixels that can carry a
+// non-zero weight (depth > 0; non-finite depths are kept so that they poison the LM sums exactly as before) is compacted
+// ONCE into a per-sample index list, in raster order (deterministic).  The per-iteration kernels (upsample + weight, LM)
+// then run over the list only: dense warps, no block-launch churn over the 60 % background.
+//   row_count [B][H]  foreground pixels per image row      (fg_rows_kernel)
+//   row_start [B][H]  exclusive prefix over the rows, fg_count[B] the total   (fg_scan_kernel)
+//   fg_idx    [B][N]  pixel index Y*W+X of the k-th foreground pixel; background pixels get weight 0 and a finite
+//                     target here, once   (fg_fill_kernel)
+__device__ __forceinline__ bool is_fg(float d) { return !(d <= 0.f); }
+
+__global__ void __launch_bounds__(128) fg_rows_kernel(const float* __restrict__ depth, int H, int W, int* __restrict__ row_count) {
+    pdl_trigger();
+    pdl_wait();
+    const int row = blockIdx.x;                    // b * H + Y
+    const float* d = depth + (size_t)row * W;
+    int c = 0;
+    for (int X = threadIdx.x; X < W; X += blockDim.x) c += is_fg(d[X]) ? 1 : 0;
+    __shared__ int red[4];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) row_count[row] = red[0] + red[1] + red[2] + red[3];
+}
+
+__global__ void __launch_bounds__(256) fg_scan_kernel(const int* __restrict__ row_count, int H, int* __restrict__ row_start,
+                                                      int* __restrict__ fg_count) {
+    pdl_trigger();
+    pdl_wait();
+    // one block per sample, serial over chunks of 256 rows (H is a few hundred)
+    const int b = blockIdx.x;
+    __shared__ int sh[256];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < H; base += 256) {
+        const int Y = base + threadIdx.x;
+        const int v = Y < H ? row_count[b * H + Y] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {                      // Hillis-Steele inclusive scan
+            const int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (Y < H) row_start[b * H + Y] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry += sh[255];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) fg_count[b] = carry;
+}
+
+__global__ void __launch_bounds__(128) fg_fill_kernel(const float* __restrict__ depth, int H, int W, const int* __restrict__ row_start,
+                                                      int* __restrict__ fg_idx, float* __restrict__ target,
+                                                      float* __restrict__ weight) {
+    pdl_trigger();
+    pdl_wait();
+    const int row = blockIdx.x;                    // b * H + Y
+    const int b = row / H, Y = row - b * H;
+    const size_t N = (size_t)H * W;
+    const float* d = depth + (size_t)row * W;
+    __shared__ int wsum[4];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = row_start[row];
+    __syncthreads();
+    for (int X0 = 0; X0 < W; X0 += blockDim.x) {
+        const int X = X0 + threadIdx.x;
+        const bool fg = X < W && is_fg(d[X]);
+        const unsigned bal = __ballot_sync(0xffffffffu, fg);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) wsum[wid] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (int k = 0; k < wid; ++k) off += wsum[k];
+        const int rank = off + __popc(bal & ((1u << lane) - 1u));
+        if (fg) {
+            fg_idx[(size_t)b * N + rank] = Y * W + X;
+        } else if (X < W) {
+            const size_t idx = (size_t)b * N + (size_t)Y * W + X;
+            *reinterpret_cast<float2*>(target + idx * 2) = make_float2((float)X, (float)Y);
+            weight[idx] = 0.f;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) base += wsum[0] + wsum[1] + wsum[2] + wsum[3];
+        __syncthreads();
+    }
+}
+
+// upsample + weight over the foreground list: thread k of sample b handles pixel fg_idx[b][k]
+__global__ void __launch_bounds__(128) upsample_weight_fg_kernel(
+    const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1,
+    const float* __restrict__ g2, const float* __restrict__ depth, float sigma, int C, int H, int W,
+    const int* __restrict__ fg_idx, const int* __restrict__ fg_count, float* __restrict__ target, float* __restrict__ weight) {
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= fg_count[b]) return;
+    const int r = fg_idx[(size_t)b * H * W + k];
+    const int Y = r / W, X = r - Y * W;
+    upsample_weight_pixel(flow, mask, g1, g2, depth, sigma, b, Y, X, C, H, W, nullptr, target, weight);
+}
+
 }  // namespace
 
 int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth,
@@ -112,6 +227,45 @@ int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, c
     const size_t total = (size_t)B * H * W;
     B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel, dim3((unsigned)((total + 63) / 64)), dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B,
                             C, H, W, flow_up, target, weight, lazy_background));
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+size_t b2p_fg_ws_bytes(int B, int H, int W) {
+    return align_up((size_t)B * H * W * sizeof(int), 256) + 2 * align_up((size_t)B * H * sizeof(int), 256) + align_up((size_t)B * sizeof(int), 256);
+}
+
+static inline void fg_ws_split(void* ws, int B, int H, int W, int** fg_idx, int** row_count, int** row_start, int** fg_count) {
+    char* p = reinterpret_cast<char*>(ws);
+    *fg_idx = reinterpret_cast<int*>(p); p += align_up((size_t)B * H * W * sizeof(int), 256);
+    *row_count = reinterpret_cast<int*>(p); p += align_up((size_t)B * H * sizeof(int), 256);
+    *row_start = reinterpret_cast<int*>(p); p += align_up((size_t)B * H * sizeof(int), 256);
+    *fg_count = reinterpret_cast<int*>(p);
+}
+
+const int* b2p_fg_idx(const void* ws) { return reinterpret_cast<const int*>(ws); }
+const int* b2p_fg_count(const void* ws, int B, int H, int W) {
+    return reinterpret_cast<const int*>(reinterpret_cast<const char*>(ws) + align_up((size_t)B * H * W * sizeof(int), 256) +
+                                        2 * align_up((size_t)B * H * sizeof(int), 256));
+}
+
+// once per call: the foreground list of `depth`; background pixels of target / weight are set here (finite target, weight 0)
+int b2p_fg_build(const float* depth, int B, int H, int W, void* ws, float* target, float* weight, cudaStream_t s) {
+    int *fg_idx, *row_count, *row_start, *fg_count;
+    fg_ws_split(ws, B, H, W, &fg_idx, &row_count, &row_start, &fg_count);
+    B2P_CUDA(b2p_launch_pdl(fg_rows_kernel, dim3(B * H), dim3(128), 0, s, depth, H, W, row_count));
+    B2P_LAUNCH_CHECK();
+    B2P_CUDA(b2p_launch_pdl(fg_scan_kernel, dim3(B), dim3(256), 0, s, (const int*)row_count, H, row_start, fg_count));
+    B2P_LAUNCH_CHECK();
+    B2P_CUDA(b2p_launch_pdl(fg_fill_kernel, dim3(B * H), dim3(128), 0, s, depth, H, W, (const int*)row_start, fg_idx, target, weight));
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2p_upsample_weight_fg(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth, float sigma,
+                           int B, int C, int H, int W, const void* fg_ws, float* target, float* weight, cudaStream_t s) {
+    B2P_CUDA(b2p_launch_pdl(upsample_weight_fg_kernel, dim3((unsigned)ceil_div(H * W, 128), B), dim3(128), 0, s, flow, mask, g1, g2, depth,
+                            sigma, C, H, W, b2p_fg_idx(fg_ws), b2p_fg_count(fg_ws, B, H, W), target, weight));
     B2P_LAUNCH_CHECK();
     return 0;
 }

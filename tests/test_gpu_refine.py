@@ -196,3 +196,23 @@ def test_refine_zero_iterations_and_single_object(ops, packed):
     assert torch.equal(run_gpu(ops, packed, f, f, mb, G0, 0, 3)["G"].cpu(), G0)
     res = run_gpu(ops, packed, f, f, mb, G0, 1, 0, want_flows=True)
     assert torch.equal(res["G"].cpu(), G0) and torch.isfinite(res["flow_last"]).all()
+
+
+def test_refine_foreground_list_matches_dense_kernels(ops, packed, monkeypatch):
+    """The per-call foreground list (depth > 0 compacted once; upsample + weight and LM run over the list) against the dense
+    kernels: identical weights, poses equal up to the fp64 summation order.  Includes an object-free crop (empty list)."""
+    H, W = 128, 160
+    mb = S.make_batch([41, 42, 43], H, W, with_images=False)
+    mb["depth"][1] = 0.0                                    # sample 1: no foreground at all
+    f1 = S.hash_features((3, 256, H // 8, W // 8), 96); f2 = S.hash_features((3, 256, H // 8, W // 8), 97)
+    G0 = torch.eye(4)[None].repeat(3, 1, 1)
+    monkeypatch.setenv("B200POSE_FG_LIST", "0")
+    dense = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, want_weight=True)
+    monkeypatch.setenv("B200POSE_FG_LIST", "1")
+    fg = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, want_weight=True)
+    assert torch.equal(fg["G"][1].cpu(), G0[1]) and torch.equal(dense["G"][1].cpu(), G0[1])
+    assert (fg["G"].cpu() - dense["G"].cpu()).abs().max().item() < 1e-6
+    torch.testing.assert_close(fg["weight"].cpu(), dense["weight"].cpu(), rtol=0, atol=2e-6)
+    ref = O.refine_inner_loop(load_update_weights(), f1, f2, mb["context"], mb["geofea1"], mb["geofea2"], mb["depth"],
+                              mb["K"], G0, n_iters=3, n_lm=3)
+    assert (fg["G"].cpu() - ref["G"]).abs().max().item() < SE3_TOL
