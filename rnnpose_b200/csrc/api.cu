@@ -505,10 +505,10 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
     if (rc) return rc;
     if (tc && (rc = b2p_pxc_to_tiled(r.net, u.rhbuf, B, h, w, 128, s))) return rc;     // hidden state of the tensor-core epilogues
     if (tc && n_iters > 1 && (rc = run_gru_precompute(wts, B, h, w, u, s))) return rc;
-    // The rendered depth is fixed over the recurrent iterations: compact its foreground once, and run the per-iteration
-    // full-resolution kernels (upsample + weight, LM) over the list (B200POSE_FG_LIST=0: dense kernels).
+    // The rendered depth is fixed over the recurrent iterations: compact its foreground once and run the LM steps over
+    // the list (B200POSE_FG_LIST=0: dense LM).
     const bool use_fg = n_iters > 0 && fg_list_enabled();
-    if (use_fg && (rc = b2p_fg_build(depth, B, H, W, r.fg, r.target, r.weight, s))) return rc;
+    if (use_fg && (rc = b2p_fg_build(depth, B, H, W, r.fg, s))) return rc;
     const int* fg_idx = use_fg ? b2p_fg_idx(r.fg) : nullptr;
     const int* fg_count = use_fg ? b2p_fg_count(r.fg, B, H, W) : nullptr;
     for (int it = 0; it < n_iters; ++it) {
@@ -521,11 +521,8 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
             if ((rc = run_update_block(wts, r.net, r.xbuf, r.corr, r.coords1, r.flow, r.mask, nullptr, B, h, w, u, s))) return rc;
         }
         float* fu = (it == 0 && flow_first) ? flow_first : ((it == n_iters - 1) ? flow_last : nullptr);
-        if (use_fg && !fu) {
-            if ((rc = b2p_upsample_weight_fg(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, r.fg, r.target, r.weight, s)))
-                return rc;
-        } else if ((rc = b2p_upsample_weight(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, fu, r.target,
-                                             r.weight, 1, s))) return rc;
+        if ((rc = b2p_upsample_weight(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, fu, r.target,
+                                      r.weight, 1, s))) return rc;
         if (it == 0 && it == n_iters - 1 && flow_first && flow_last)
             B2P_CUDA(cudaMemcpyAsync(flow_last, flow_first, (size_t)B * 2 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
         if ((rc = b2p_lm_steps(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, n_lm, r.lm, s, fg_idx, fg_count))) return rc;

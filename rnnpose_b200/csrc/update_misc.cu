@@ -4,6 +4,8 @@
 // reference thirdparty/raft/update.py:13-14,83-97 ; model/CFNet.py:157.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace {
 
 // dst[tap][c][n_off + n] = src[n][c][ky][kx]     (tap = ky*kw + kx)
@@ -115,20 +117,23 @@ __global__ void __launch_bounds__(256) flow_head2_partial_kernel(const float* __
                                                                  float* __restrict__ part, int npix) {
     pdl_trigger();
     __shared__ __align__(16) float ws[18][256];            // [tap*2+o][c]
-    for (int i = threadIdx.x; i < 18 * 256; i += blockDim.x) {
-        const int k = i >> 8, c = i & 255;
-        ws[k][c] = __ldg(w2 + ((k & 1) * 9 + (k >> 1)) * 256 + c);      // weights are not written by the previous kernel
+    for (int i = threadIdx.x; i < 18 * 64; i += blockDim.x) {          // float4 copies, all independent
+        const int k = i >> 6, c4 = i & 63;
+        *reinterpret_cast<float4*>(&ws[k][c4 * 4]) =
+            __ldg(reinterpret_cast<const float4*>(w2 + ((k & 1) * 9 + (k >> 1)) * 256) + c4);      // weights: not written by the previous kernel
     }
     __syncthreads();
     pdl_wait();
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int pix0 = (gid >> 2) * FH2_PX, q = gid & 3;
+    const int q = threadIdx.x & 3;
+    // persistent blocks (the weights are staged once per block): lane quads walk the pixel pairs
+    for (int quad = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; quad * FH2_PX < npix; quad += (gridDim.x * blockDim.x) >> 2) {
+    const int pix0 = quad * FH2_PX;
     float acc[FH2_PX][18];
 #pragma unroll
     for (int u = 0; u < FH2_PX; ++u)
 #pragma unroll
         for (int k = 0; k < 18; ++k) acc[u][k] = 0.f;
-    if (pix0 < npix) {
+    {
 #pragma unroll 2
         for (int it = 0; it < 8; ++it) {
             const int c = (it * 4 + q) * 8;                // the quad reads 64 contiguous bytes of each fp16 plane
@@ -183,6 +188,7 @@ __global__ void __launch_bounds__(256) flow_head2_partial_kernel(const float* __
             d[4] = make_float4(acc[u][16], acc[u][17], 0.f, 0.f);
         }
     }
+    }   // quad loop (uniform per warp up to whole quads: the shuffles above see every lane of a live quad)
 }
 
 __global__ void __launch_bounds__(128) flow_head2_gather_kernel(const float* __restrict__ part, const float* __restrict__ b2,
@@ -382,7 +388,7 @@ int b2p_im2col_f1(const float* flow, int B, int h, int w, float* col, float* xbu
 int b2p_flow_head2(const float* hm, const __half* hm_hi, const __half* hm_lo, const float* w2, const float* b2,
                    float* coords1, float* flow, float* dflow_out, float* part, int B, int h, int w, cudaStream_t s) {
     const int npix = B * h * w;
-    B2P_CUDA(b2p_launch_pdl(flow_head2_partial_kernel, dim3(ceil_div(ceil_div(npix, FH2_PX) * 4, 256)), dim3(256), 0, s, hm, hm_hi, hm_lo, w2, part, npix));
+    B2P_CUDA(b2p_launch_pdl(flow_head2_partial_kernel, dim3(std::min(ceil_div(ceil_div(npix, FH2_PX) * 4, 256), 2 * 148)), dim3(256), 0, s, hm, hm_hi, hm_lo, w2, part, npix));
     B2P_LAUNCH_CHECK();
     B2P_CUDA(b2p_launch_pdl(flow_head2_gather_kernel, dim3(ceil_div(npix, 128)), dim3(128), 0, s, (const float*)part, b2, coords1, flow,
                             dflow_out, B, h, w));

@@ -117,12 +117,12 @@ __global__ void __launch_bounds__(64) upsample_weight_kernel(
 // ------------------------------------------------------------------------------------------------ foreground list
 // The rendered depth does not change over the recurrent iterations of a call, so the set of pixels that can carry a
 // non-zero weight (depth > 0; non-finite depths are kept so that they poison the LM sums exactly as before) is compacted
-// ONCE into a per-sample index list, in raster order (deterministic).  The per-iteration kernels (upsample + weight, LM)
-// then run over the list only: dense warps, no block-launch churn over the 60 % background.
+// ONCE into a per-sample index list, in raster order (deterministic).  The LM kernel then runs over the list only (every
+// unlisted pixel has weight exactly 0 and finite inputs: upsample_weight_kernel's background shortcut).  A list-driven
+// variant of upsample_weight_kernel was measured too: no faster than the dense kernel (173 us both; profiles/r1c_summary.md).
 //   row_count [B][H]  foreground pixels per image row      (fg_rows_kernel)
 //   row_start [B][H]  exclusive prefix over the rows, fg_count[B] the total   (fg_scan_kernel)
-//   fg_idx    [B][N]  pixel index Y*W+X of the k-th foreground pixel; background pixels get weight 0 and a finite
-//                     target here, once   (fg_fill_kernel)
+//   fg_idx    [B][N]  pixel index Y*W+X of the k-th foreground pixel   (fg_fill_kernel)
 __device__ __forceinline__ bool is_fg(float d) { return !(d <= 0.f); }
 
 __global__ void __launch_bounds__(128) fg_rows_kernel(const float* __restrict__ depth, int H, int W, int* __restrict__ row_count) {
@@ -169,8 +169,7 @@ __global__ void __launch_bounds__(256) fg_scan_kernel(const int* __restrict__ ro
 }
 
 __global__ void __launch_bounds__(128) fg_fill_kernel(const float* __restrict__ depth, int H, int W, const int* __restrict__ row_start,
-                                                      int* __restrict__ fg_idx, float* __restrict__ target,
-                                                      float* __restrict__ weight) {
+                                                      int* __restrict__ fg_idx) {
     pdl_trigger();
     pdl_wait();
     const int row = blockIdx.x;                    // b * H + Y
@@ -191,32 +190,11 @@ __global__ void __launch_bounds__(128) fg_fill_kernel(const float* __restrict__ 
         int off = base;
         for (int k = 0; k < wid; ++k) off += wsum[k];
         const int rank = off + __popc(bal & ((1u << lane) - 1u));
-        if (fg) {
-            fg_idx[(size_t)b * N + rank] = Y * W + X;
-        } else if (X < W) {
-            const size_t idx = (size_t)b * N + (size_t)Y * W + X;
-            *reinterpret_cast<float2*>(target + idx * 2) = make_float2((float)X, (float)Y);
-            weight[idx] = 0.f;
-        }
+        if (fg) fg_idx[(size_t)b * N + rank] = Y * W + X;
         __syncthreads();
         if (threadIdx.x == 0) base += wsum[0] + wsum[1] + wsum[2] + wsum[3];
         __syncthreads();
     }
-}
-
-// upsample + weight over the foreground list: thread k of sample b handles pixel fg_idx[b][k]
-__global__ void __launch_bounds__(128) upsample_weight_fg_kernel(
-    const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1,
-    const float* __restrict__ g2, const float* __restrict__ depth, float sigma, int C, int H, int W,
-    const int* __restrict__ fg_idx, const int* __restrict__ fg_count, float* __restrict__ target, float* __restrict__ weight) {
-    pdl_trigger();
-    pdl_wait();
-    const int b = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= fg_count[b]) return;
-    const int r = fg_idx[(size_t)b * H * W + k];
-    const int Y = r / W, X = r - Y * W;
-    upsample_weight_pixel(flow, mask, g1, g2, depth, sigma, b, Y, X, C, H, W, nullptr, target, weight);
 }
 
 }  // namespace
@@ -249,23 +227,15 @@ const int* b2p_fg_count(const void* ws, int B, int H, int W) {
                                         2 * align_up((size_t)B * H * sizeof(int), 256));
 }
 
-// once per call: the foreground list of `depth`; background pixels of target / weight are set here (finite target, weight 0)
-int b2p_fg_build(const float* depth, int B, int H, int W, void* ws, float* target, float* weight, cudaStream_t s) {
+// once per call: the foreground list of `depth`
+int b2p_fg_build(const float* depth, int B, int H, int W, void* ws, cudaStream_t s) {
     int *fg_idx, *row_count, *row_start, *fg_count;
     fg_ws_split(ws, B, H, W, &fg_idx, &row_count, &row_start, &fg_count);
     B2P_CUDA(b2p_launch_pdl(fg_rows_kernel, dim3(B * H), dim3(128), 0, s, depth, H, W, row_count));
     B2P_LAUNCH_CHECK();
     B2P_CUDA(b2p_launch_pdl(fg_scan_kernel, dim3(B), dim3(256), 0, s, (const int*)row_count, H, row_start, fg_count));
     B2P_LAUNCH_CHECK();
-    B2P_CUDA(b2p_launch_pdl(fg_fill_kernel, dim3(B * H), dim3(128), 0, s, depth, H, W, (const int*)row_start, fg_idx, target, weight));
-    B2P_LAUNCH_CHECK();
-    return 0;
-}
-
-int b2p_upsample_weight_fg(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth, float sigma,
-                           int B, int C, int H, int W, const void* fg_ws, float* target, float* weight, cudaStream_t s) {
-    B2P_CUDA(b2p_launch_pdl(upsample_weight_fg_kernel, dim3((unsigned)ceil_div(H * W, 128), B), dim3(128), 0, s, flow, mask, g1, g2, depth,
-                            sigma, C, H, W, b2p_fg_idx(fg_ws), b2p_fg_count(fg_ws, B, H, W), target, weight));
+    B2P_CUDA(b2p_launch_pdl(fg_fill_kernel, dim3(B * H), dim3(128), 0, s, depth, H, W, (const int*)row_start, fg_idx));
     B2P_LAUNCH_CHECK();
     return 0;
 }
