@@ -38,7 +38,7 @@ import torch  # noqa: E402
 H, W, B_PER_GPU, N_ITERS, N_LM = 240, 320, 32, 4, 3
 UNIQUE_SCENES = 8            # distinct synthetic scenes per rank, tiled to the batch
 FLOP_PER_LOWRES_PX = 6236672  # update-block convolutions, SURVEY.md Appendix A.2
-NCU_TRAFFIC_BYTES_PER_PASS = 769_000_000   # profiles/r1_final_summary.md (644 MB read + 125 MB written)
+NCU_TRAFFIC_BYTES_PER_PASS = 775_000_000   # profiles/r1c_summary.md (642 MB read + 133 MB written)
 WORKLOAD = f"synthetic {H}x{W} crops, batch {B_PER_GPU}/GPU, {N_ITERS} recurrent iters x {N_LM} LM steps"
 
 
@@ -211,7 +211,7 @@ def main():
     FLAGS = ops.FLAG_EXACT_FP32 if args.exact_fp32 else ops.FLAG_TENSOR_CORES
     dtype = ("f32 (CUDA-core FFMA convolutions; LM step f64)" if args.exact_fp32 else
              "f32-equivalent: tcgen05 kind::f16 on fp16 hi/lo split operands (22-bit), 3 MMAs, fp32 TMEM accumulate; LM step f64")
-    conv_kernel = ("conv_gemm_kernel<128|64> (FFMA)" if args.exact_fp32 else "conv_umma_kernel (tcgen05.mma + TMA + TMEM)")
+    conv_kernel = ("conv_gemm_kernel<128|64> (FFMA)" if args.exact_fp32 else "conv_umma2_kernel (tcgen05.mma cta_group::2 on CTA pairs + TMA + TMEM)")
 
     inputs = make_inputs(rank, B, UNIQUE_SCENES)
     assert args.cpu_objects <= B
@@ -312,7 +312,7 @@ def main():
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC_BYTES_PER_PASS if not args.exact_fp32 else None,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum over the 11 conv launches of one pass, "
-                                  "profiles/r1_final_conv_umma_ncu_raw.csv (B=32, 240x320; ncu flushes caches per launch)",
+                                  "profiles/r1c_conv_umma2_ncu_raw.csv (B=32, 240x320; ncu flushes caches per launch)",
                 "peak_source": f"{peak_src} (bf16 dense, sustained)",
                 "kernel": conv_kernel + ": the 11 convolution launches of one update-block pass, timed back to back "
                           "(incl. the im2col / flow-head / operand-split helper launches, <3% of the pass)",

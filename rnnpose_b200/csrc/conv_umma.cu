@@ -927,7 +927,7 @@ int conv_mode() {
     return e && *e ? atoi(e) : kDefaultConvMode;
 }
 
-// experiment knobs (read per launch): ring budget in KB, PDL off, which layers may take the second-generation kernel
+// integer environment knob, read per launch (tests switch kernels between calls)
 int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e && *e ? atoi(e) : dflt;
@@ -943,10 +943,6 @@ cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), int grid, int cluster, 
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = cluster; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = cluster > 1 ? 2 : 1;
-    if (env_int("B200POSE_V2_NOPDL", 0)) {            // plain stream-ordered launch
-        attr[0] = attr[1];
-        cfg.numAttrs = cluster > 1 ? 1 : 0;
-    }
     return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
@@ -955,7 +951,7 @@ int launch_conv_umma2(const UmmaConvArgs& a, UmmaConvParams& p, int ncta, bool r
     int rc;
     const int taps = a.kh * a.kw;
     // rings: one activation slot serves a_taps weight slots; without reuse the two rings advance together
-    const int b_slot = 2 * (a.n_tile / ncta) * 128, budget = env_int("B200POSE_V2_BUDGET_KB", 222) * 1024;
+    const int b_slot = 2 * (a.n_tile / ncta) * 128, budget = 222 * 1024;
     p.a_taps = reuse_v ? a.kh : 1;
     p.a_rows = TILE_ROWS + p.a_taps - 1;
     p.ring_a = 2;
@@ -1046,11 +1042,10 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     // second-generation kernel (see conv_mode): not for the batched-weight volume GEMM (a pair of M tiles may straddle two
     // samples); CTA pairs only when the problem fills the machine (they halve the number of schedulable units)
     int mode = a.b_batched ? 0 : conv_mode();
-    if (mode && a.layer_id >= 0 && !((env_int("B200POSE_CONV_LAYERS", -1) >> a.layer_id) & 1)) mode = 0;
     if (mode) {
         const bool pair = (mode & 1) && p.total_tiles >= sms && (a.n_tile % 32) == 0;
         const bool reuse_v = (mode & 2) && a.kh > 1;
-        if (pair && a.n_tile == 128 && a.cout_pad % 256 == 0 && env_int("B200POSE_PAIR_N256", 1)) {
+        if (pair && a.n_tile == 128 && a.cout_pad % 256 == 0) {
             // A pair holds a 256-row weight tile in the shared memory of two SMs (128 rows each): one pass over the
             // activations instead of two, and M=256 x N=256 MMAs read half as many operand bytes per SM and flop.
             UmmaConvArgs a2 = a;
