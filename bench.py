@@ -285,7 +285,10 @@ def main():
     for y in range(H // 8):
         y0 = min(int(y * sy), H - 1); rows.update((y0, min(y0 + 1, H - 1)))
     ctx_bytes = B * 256 * len(rows) * W * 4
-    h2d = sum(host[k].numel() * 4 for k in ("fmap1", "fmap2", "geofea1", "geofea2", "depth", "K", "G0")) + ctx_bytes
+    # the first descriptor map is fetched from the pinned buffer only where the rendered depth is positive
+    sparse_g1 = os.environ.get("B200POSE_SPARSE_G1", "1") != "0"
+    g1_bytes = (int((host["depth"] > 0).sum()) * host["geofea1"].shape[1] * 4) if sparse_g1 else host["geofea1"].numel() * 4
+    h2d = sum(host[k].numel() * 4 for k in ("fmap1", "fmap2", "geofea2", "depth", "K", "G0")) + g1_bytes + ctx_bytes
     d2h = Gh.numel() * 4
     agree = (Gh.to(dev) - G).abs().max().item()
     del scratch
@@ -337,7 +340,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": ke, "ms_per_step": ms_e2e / ke, "max_abs_diff_vs_device_entry": agree,
                     "host_input_bytes": sum(host[k].numel() * 4 for k in host),
-                    "note": "context map is read in place from pinned host memory (only the rows the 1/8 resample touches)"},
+                    "note": "context map is read in place from pinned host memory (only the rows the 1/8 resample touches); the first descriptor map likewise only at the pixels with depth > 0"},
             "gpu_launches": args.steps * ops.launch_count(N_ITERS, N_LM),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "parity": {"objects": int(gm.shape[0]), "mean_add_over_diameter": float((gm[:, 0] / diam_d.repeat(world)[: gm.shape[0]]).mean()),

@@ -603,6 +603,18 @@ int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_ho
         else
             (void)cudaGetLastError();
     }
+    // Likewise the first descriptor map is only read where the rendered depth is positive (upsample_weight.cu): from a
+    // pinned buffer only those pixels are fetched (B200POSE_SPARSE_G1=0: plain copy).
+    const float* g1_mapped = nullptr;
+    {
+        const char* e = getenv("B200POSE_SPARSE_G1");
+        cudaPointerAttributes attr;
+        if (!(e && *e == '0') && cudaPointerGetAttributes(&attr, geofea1_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            attr.devicePointer != nullptr)
+            g1_mapped = reinterpret_cast<const float*>(attr.devicePointer);
+        else
+            (void)cudaGetLastError();
+    }
     HostScratch hs;
     host_scratch_layout(B, C_geo, H, W, ctx_mapped == nullptr, device_scratch, device_scratch_bytes, &hs);
     const int h = H / 8, w = W / 8, bs = hs.bs;
@@ -629,9 +641,14 @@ int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_ho
         B2P_TRY(cudaMemcpyAsync(st.fmap2, fmap2_host + (size_t)b0 * 256 * h * w, (size_t)nb * 256 * h * w * f, cudaMemcpyHostToDevice, cs));
         if (!ctx_mapped)
             B2P_TRY(cudaMemcpyAsync(st.context, context_host + (size_t)b0 * 256 * H * W, (size_t)nb * 256 * H * W * f, cudaMemcpyHostToDevice, cs));
-        B2P_TRY(cudaMemcpyAsync(st.geo1, geofea1_host + (size_t)b0 * C_geo * H * W, (size_t)nb * C_geo * H * W * f, cudaMemcpyHostToDevice, cs));
-        B2P_TRY(cudaMemcpyAsync(st.geo2, geofea2_host + (size_t)b0 * C_geo * H * W, (size_t)nb * C_geo * H * W * f, cudaMemcpyHostToDevice, cs));
         B2P_TRY(cudaMemcpyAsync(st.depth, depth_host + (size_t)b0 * H * W, (size_t)nb * H * W * f, cudaMemcpyHostToDevice, cs));
+        if (g1_mapped) {
+            rc = b2p_gather_fg_planes(st.depth, g1_mapped + (size_t)b0 * C_geo * H * W, st.geo1, nb, C_geo, H, W, cs);
+            if (rc) goto cleanup;
+        } else {
+            B2P_TRY(cudaMemcpyAsync(st.geo1, geofea1_host + (size_t)b0 * C_geo * H * W, (size_t)nb * C_geo * H * W * f, cudaMemcpyHostToDevice, cs));
+        }
+        B2P_TRY(cudaMemcpyAsync(st.geo2, geofea2_host + (size_t)b0 * C_geo * H * W, (size_t)nb * C_geo * H * W * f, cudaMemcpyHostToDevice, cs));
         B2P_TRY(cudaMemcpyAsync(st.K, K_host + (size_t)b0 * 9, (size_t)nb * 9 * f, cudaMemcpyHostToDevice, cs));
         B2P_TRY(cudaMemcpyAsync(st.G, G_host + (size_t)b0 * 16, (size_t)nb * 16 * f, cudaMemcpyHostToDevice, cs));
         B2P_TRY(cudaEventRecord(ev_copy[k & 1], cs));

@@ -182,6 +182,8 @@ size_t b2p_fg_ws_bytes(int B, int H, int W);
 int b2p_fg_build(const float* depth, int B, int H, int W, void* fg_ws, cudaStream_t s);
 const int* b2p_fg_idx(const void* fg_ws);
 const int* b2p_fg_count(const void* fg_ws, int B, int H, int W);
+// dst[b][c][r] = src[b][c][r] for the pixels with depth[b][r] > 0 (src may be a mapped host pointer)
+int b2p_gather_fg_planes(const float* depth_dev, const float* src_mapped, float* dst_dev, int B, int C, int H, int W, cudaStream_t s);
 int b2p_lm_step(const float* depth, const float* target, const float* weight, const float* K, float* G,
                 int B, int H, int W, float depth_add, double ep, double lm, double* H_out, double* b_out,
                 float* delta_out, void* ws, cudaStream_t s);

@@ -197,6 +197,23 @@ __global__ void __launch_bounds__(128) fg_fill_kernel(const float* __restrict__ 
     }
 }
 
+// Host-entry helper: upload of the first descriptor map.  upsample_weight_pixel reads geofea1 only where depth > 0, so when
+// the caller's buffer is pinned (device-accessible) only those pixels are fetched over PCIe: src is the mapped HOST pointer,
+// depth / dst are device memory.  Grid (pixel chunks, channel groups of 8, samples); 8 independent loads per thread.
+__global__ void __launch_bounds__(256) gather_fg_planes_kernel(const float* __restrict__ depth, const float* __restrict__ src,
+                                                               float* __restrict__ dst, int C, int N) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.z, c0 = blockIdx.y * 8;
+    if (r >= N || !(depth[(size_t)b * N + r] > 0.f)) return;
+    const size_t base = ((size_t)b * C + c0) * N + r;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = c0 + k < C ? src[base + (size_t)k * N] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (c0 + k < C) dst[base + (size_t)k * N] = v[k];
+}
+
 }  // namespace
 
 int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth,
@@ -236,6 +253,13 @@ int b2p_fg_build(const float* depth, int B, int H, int W, void* ws, cudaStream_t
     B2P_CUDA(b2p_launch_pdl(fg_scan_kernel, dim3(B), dim3(256), 0, s, (const int*)row_count, H, row_start, fg_count));
     B2P_LAUNCH_CHECK();
     B2P_CUDA(b2p_launch_pdl(fg_fill_kernel, dim3(B * H), dim3(128), 0, s, depth, H, W, (const int*)row_start, fg_idx));
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2p_gather_fg_planes(const float* depth_dev, const float* src_mapped, float* dst_dev, int B, int C, int H, int W, cudaStream_t s) {
+    const int N = H * W;
+    gather_fg_planes_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)ceil_div(C, 8), (unsigned)B), 256, 0, s>>>(depth_dev, src_mapped, dst_dev, C, N);
     B2P_LAUNCH_CHECK();
     return 0;
 }
