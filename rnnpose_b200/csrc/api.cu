@@ -62,6 +62,11 @@ inline bool fg_list_enabled() {
     return !(e && *e == '0');
 }
 
+inline bool fg_upsample_enabled() {           // B200POSE_FG_UPSAMPLE=1: persistent list-driven upsample + weight kernel (opt-in)
+    const char* e = getenv("B200POSE_FG_UPSAMPLE");
+    return e && *e == '1';
+}
+
 inline bool shape_ok(int B, int H, int W) {
     return B >= 1 && H >= 128 && W >= 128 && (H % 8) == 0 && (W % 8) == 0;   // (H/8)>>3 >= 2: the reference's
 }                                                                             // sampler divides by (w_l - 1)
@@ -505,10 +510,11 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
     if (rc) return rc;
     if (tc && (rc = b2p_pxc_to_tiled(r.net, u.rhbuf, B, h, w, 128, s))) return rc;     // hidden state of the tensor-core epilogues
     if (tc && n_iters > 1 && (rc = run_gru_precompute(wts, B, h, w, u, s))) return rc;
-    // The rendered depth is fixed over the recurrent iterations: compact its foreground once and run the LM steps over
-    // the list (B200POSE_FG_LIST=0: dense LM).
+    // The rendered depth is fixed over the recurrent iterations: compact its foreground once and run the LM steps and the
+    // upsample + weight kernel over the list (B200POSE_FG_LIST=0: dense kernels).
     const bool use_fg = n_iters > 0 && fg_list_enabled();
-    if (use_fg && (rc = b2p_fg_build(depth, B, H, W, r.fg, s))) return rc;
+    const bool fg_up = use_fg && fg_upsample_enabled();
+    if (use_fg && (rc = b2p_fg_build(depth, B, H, W, r.fg, fg_up ? r.target : nullptr, fg_up ? r.weight : nullptr, s))) return rc;
     const int* fg_idx = use_fg ? b2p_fg_idx(r.fg) : nullptr;
     const int* fg_count = use_fg ? b2p_fg_count(r.fg, B, H, W) : nullptr;
     for (int it = 0; it < n_iters; ++it) {
@@ -521,8 +527,11 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
             if ((rc = run_update_block(wts, r.net, r.xbuf, r.corr, r.coords1, r.flow, r.mask, nullptr, B, h, w, u, s))) return rc;
         }
         float* fu = (it == 0 && flow_first) ? flow_first : ((it == n_iters - 1) ? flow_last : nullptr);
-        if ((rc = b2p_upsample_weight(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, fu, r.target,
-                                      r.weight, 1, s))) return rc;
+        if (fg_up && !fu) {      // persistent kernel over the foreground list (the up-sampled flow is not an output here)
+            if ((rc = b2p_upsample_weight_fg(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, r.fg, r.target, r.weight, s)))
+                return rc;
+        } else if ((rc = b2p_upsample_weight(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, fu, r.target,
+                                             r.weight, 1, s))) return rc;
         if (it == 0 && it == n_iters - 1 && flow_first && flow_last)
             B2P_CUDA(cudaMemcpyAsync(flow_last, flow_first, (size_t)B * 2 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
         if ((rc = b2p_lm_steps(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, n_lm, r.lm, s, fg_idx, fg_count))) return rc;

@@ -179,7 +179,9 @@ int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, c
                         int lazy_background, cudaStream_t s);
 // foreground list (depth > 0 or non-finite) of a call, built once; see upsample_weight.cu
 size_t b2p_fg_ws_bytes(int B, int H, int W);
-int b2p_fg_build(const float* depth, int B, int H, int W, void* fg_ws, cudaStream_t s);
+int b2p_fg_build(const float* depth, int B, int H, int W, void* fg_ws, float* target, float* weight, cudaStream_t s);
+int b2p_upsample_weight_fg(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth, float sigma,
+                           int B, int C, int H, int W, const void* fg_ws, float* target, float* weight, cudaStream_t s);
 const int* b2p_fg_idx(const void* fg_ws);
 const int* b2p_fg_count(const void* fg_ws, int B, int H, int W);
 // dst[b][c][r] = src[b][c][r] for the pixels with depth[b][r] > 0 (src may be a mapped host pointer)

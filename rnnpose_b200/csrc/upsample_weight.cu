@@ -10,6 +10,8 @@
 // frees its slot as soon as its own warps finish, which roughly doubles the resident foreground warps.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 // Everything for one full-resolution pixel (b, Y, X): convex upsampling, target, descriptor similarity weight.
@@ -169,7 +171,8 @@ __global__ void __launch_bounds__(256) fg_scan_kernel(const int* __restrict__ ro
 }
 
 __global__ void __launch_bounds__(128) fg_fill_kernel(const float* __restrict__ depth, int H, int W, const int* __restrict__ row_start,
-                                                      int* __restrict__ fg_idx) {
+                                                      int* __restrict__ fg_idx, float* __restrict__ target,
+                                                      float* __restrict__ weight) {
     pdl_trigger();
     pdl_wait();
     const int row = blockIdx.x;                    // b * H + Y
@@ -190,10 +193,37 @@ __global__ void __launch_bounds__(128) fg_fill_kernel(const float* __restrict__ 
         int off = base;
         for (int k = 0; k < wid; ++k) off += wsum[k];
         const int rank = off + __popc(bal & ((1u << lane) - 1u));
-        if (fg) fg_idx[(size_t)b * N + rank] = Y * W + X;
+        if (fg) {
+            fg_idx[(size_t)b * N + rank] = Y * W + X;
+        } else if (X < W && weight) {                   // background: weight 0 and a finite target, once per call
+            const size_t idx = (size_t)b * N + (size_t)Y * W + X;
+            *reinterpret_cast<float2*>(target + idx * 2) = make_float2((float)X, (float)Y);
+            weight[idx] = 0.f;
+        }
         __syncthreads();
         if (threadIdx.x == 0) base += wsum[0] + wsum[1] + wsum[2] + wsum[3];
         __syncthreads();
+    }
+}
+
+// upsample + weight over the foreground list, PERSISTENT: gridDim.x blocks per sample stride over that sample's list.
+// The dense kernel launches 38 400 two-warp blocks of which 60 % exit at once; ncu shows it latency-bound at 27 % of
+// HBM peak with half the warp slots idle, and a list-driven kernel with the same block count ran no faster: the block
+// launch rate (~260 blocks per SM) bounds both.  Here every resident warp works on foreground pixels until the list ends.
+template <int BLOCKS_PER_SM>
+__global__ void __launch_bounds__(128, BLOCKS_PER_SM) upsample_weight_fg_kernel(
+    const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1,
+    const float* __restrict__ g2, const float* __restrict__ depth, float sigma, int C, int H, int W,
+    const int* __restrict__ fg_idx, const int* __restrict__ fg_count, float* __restrict__ target, float* __restrict__ weight) {
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.y;
+    const int count = fg_count[b];
+    const int* idx = fg_idx + (size_t)b * H * W;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const int r = __ldg(idx + k);
+        const int Y = r / W, X = r - Y * W;
+        upsample_weight_pixel(flow, mask, g1, g2, depth, sigma, b, Y, X, C, H, W, nullptr, target, weight);
     }
 }
 
@@ -244,15 +274,40 @@ const int* b2p_fg_count(const void* ws, int B, int H, int W) {
                                         2 * align_up((size_t)B * H * sizeof(int), 256));
 }
 
-// once per call: the foreground list of `depth`
-int b2p_fg_build(const float* depth, int B, int H, int W, void* ws, cudaStream_t s) {
+// once per call: the foreground list of `depth`; target / weight (optional): their background pixels are set here
+// (finite target, weight 0) for the list-driven upsample + weight kernel, which never touches them
+int b2p_fg_build(const float* depth, int B, int H, int W, void* ws, float* target, float* weight, cudaStream_t s) {
     int *fg_idx, *row_count, *row_start, *fg_count;
     fg_ws_split(ws, B, H, W, &fg_idx, &row_count, &row_start, &fg_count);
     B2P_CUDA(b2p_launch_pdl(fg_rows_kernel, dim3(B * H), dim3(128), 0, s, depth, H, W, row_count));
     B2P_LAUNCH_CHECK();
     B2P_CUDA(b2p_launch_pdl(fg_scan_kernel, dim3(B), dim3(256), 0, s, (const int*)row_count, H, row_start, fg_count));
     B2P_LAUNCH_CHECK();
-    B2P_CUDA(b2p_launch_pdl(fg_fill_kernel, dim3(B * H), dim3(128), 0, s, depth, H, W, (const int*)row_start, fg_idx));
+    B2P_CUDA(b2p_launch_pdl(fg_fill_kernel, dim3(B * H), dim3(128), 0, s, depth, H, W, (const int*)row_start, fg_idx, target, weight));
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2p_upsample_weight_fg(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth, float sigma,
+                           int B, int C, int H, int W, const void* fg_ws, float* target, float* weight, cudaStream_t s) {
+    int dev = 0, sms = 0;
+    B2P_CUDA(cudaGetDevice(&dev));
+    B2P_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // all blocks resident; B200POSE_FG_BLOCKS picks the register / occupancy point (8 blocks of 128 threads per SM at 64
+    // registers, or 6 at 80)
+    const char* e = getenv("B200POSE_FG_BLOCKS");
+    const int bps = (e && atoi(e) == 6) ? 6 : 8;
+    int per_sample = (sms * bps) / B;
+    const int useful = ceil_div(H * W, 128);
+    if (per_sample > useful) per_sample = useful;
+    if (per_sample < 1) per_sample = 1;
+    const dim3 grid((unsigned)per_sample, (unsigned)B);
+    if (bps == 6)
+        B2P_CUDA(b2p_launch_pdl(upsample_weight_fg_kernel<6>, grid, dim3(128), 0, s, flow, mask, g1, g2, depth, sigma, C, H, W,
+                                b2p_fg_idx(fg_ws), b2p_fg_count(fg_ws, B, H, W), target, weight));
+    else
+        B2P_CUDA(b2p_launch_pdl(upsample_weight_fg_kernel<8>, grid, dim3(128), 0, s, flow, mask, g1, g2, depth, sigma, C, H, W,
+                                b2p_fg_idx(fg_ws), b2p_fg_count(fg_ws, B, H, W), target, weight));
     B2P_LAUNCH_CHECK();
     return 0;
 }
