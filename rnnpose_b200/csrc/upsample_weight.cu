@@ -36,15 +36,22 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
 #pragma unroll
     for (int k = 0; k < 9; ++k) { mk[k] = expf(mk[k] - mx); den += mk[k]; }
     float ux = 0.f, uy = 0.f;
+    // (loads are unconditional from clamped addresses and the out-of-image taps are zeroed by a select: a load behind a
+    //  branch cannot be hoisted, and the kernel was serialising on one memory round trip per tap)
+    float2 fl[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         const int ny = y + k / 3 - 1, nx = x + k % 3 - 1;
-        float2 f = make_float2(0.f, 0.f);
-        if (ny >= 0 && ny < h && nx >= 0 && nx < w)
-            f = __ldg(reinterpret_cast<const float2*>(flow + (((size_t)b * h + ny) * w + nx) * 2));
+        const int cy = min(max(ny, 0), h - 1), cx = min(max(nx, 0), w - 1);
+        const float2 f = __ldg(reinterpret_cast<const float2*>(flow + (((size_t)b * h + cy) * w + cx) * 2));
+        const bool in = ny >= 0 && ny < h && nx >= 0 && nx < w;
+        fl[k] = in ? f : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
         const float sm = mk[k] / den;
-        ux += sm * (8.f * f.x);
-        uy += sm * (8.f * f.y);
+        ux += sm * (8.f * fl[k].x);
+        uy += sm * (8.f * fl[k].y);
     }
     if (flow_up) {
         flow_up[((size_t)b * 2 + 0) * N + r] = ux;
@@ -72,21 +79,28 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
         const bool ya = y0 >= 0 && y0 < H, yb = y0 + 1 >= 0 && y0 + 1 < H;
         // ix may be NaN/inf for degenerate flow: all comparisons false -> zero sample, like grid_sample
         const bool fin = isfinite(ix) && isfinite(iy);
-        const size_t o00 = (size_t)y0 * W + x0;
+        // Branch-free gather: every corner is loaded from an in-image (clamped) address and discarded by a select when
+        // the reference would not sample it (outside the image, or non-finite coordinates -> all four).  Same arithmetic
+        // and order as the conditional form; the 5 x C loads of a pixel are independent and can all be in flight.
+        const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
+        const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
+        const int o00 = yc0 * W + xc0, o01 = yc0 * W + xc1, o10 = yc1 * W + xc0, o11 = yc1 * W + xc1;
+        const bool k00 = fin && ya && xa, k01 = fin && ya && xb, k10 = fin && yb && xa, k11 = fin && yb && xb;
+        const float w00 = k00 ? wnw : 0.f, w01 = k01 ? wne : 0.f, w10 = k10 ? wsw : 0.f, w11 = k11 ? wse : 0.f;
         float s = 0.f;
         const float* g1p = g1 + (size_t)b * C * N + r;
         const float* g2p = g2 + (size_t)b * C * N;
 #pragma unroll 8
         for (int c = 0; c < C; ++c) {
             const float* pl = g2p + (size_t)c * N;
+            const float t00 = __ldg(pl + o00), t01 = __ldg(pl + o01), t10 = __ldg(pl + o10), t11 = __ldg(pl + o11);
+            const float a = __ldg(g1p + (size_t)c * N);
             float v = 0.f;
-            if (fin) {
-                if (ya && xa) v += __ldg(pl + o00) * wnw;
-                if (ya && xb) v += __ldg(pl + o00 + 1) * wne;
-                if (yb && xa) v += __ldg(pl + o00 + W) * wsw;
-                if (yb && xb) v += __ldg(pl + o00 + W + 1) * wse;
-            }
-            s += __ldg(g1p + (size_t)c * N) * v;
+            v += (k00 ? t00 : 0.f) * w00;
+            v += (k01 ? t01 : 0.f) * w01;
+            v += (k10 ? t10 : 0.f) * w10;
+            v += (k11 ? t11 : 0.f) * w11;
+            s += a * v;
         }
         wgt = expf(-fabsf(1.f - s) / sigma);
     }
