@@ -1,6 +1,12 @@
 // Tensor-core implicit-GEMM convolution for the update block: tcgen05.mma (kind::f16) with fp32 accumulators
 // in TMEM, operands staged by TMA into 128B-swizzled shared memory, warp-specialised
-// (warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2-5 = epilogue).
+// (warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2-9 = epilogue).
+// Two kernels: conv_umma_kernel (one smem ring, single CTA; correlation volume and small problems) and
+// conv_umma2_kernel<NCTA> (separate activation / weight rings, vertical-tap reuse, CTA pairs with
+// tcgen05.mma.cta_group::2; the default for the update block, B200POSE_CONV_MODE).  DESIGN.md section 6.
+// Diagnostics compiled in (off unless B200POSE_V2_DEBUG is set): bits 1/2/4 drop the TMA loads / MMAs / epilogue for
+// timing experiments (results garbage), bit 16 records per-CTA clock counters and a launch timeline
+// (b200pose_debug_conv_counters / b200pose_debug_conv_log, read by tools/conv_counters.py).
 //
 // Precision scheme ("fp16x3"): every fp32 operand x is carried as two fp16 planes hi = fp16(x),
 // lo = fp16(x - hi) (22 significant bits together); a product is accumulated as
