@@ -213,6 +213,11 @@ def test_refine_foreground_list_matches_dense_kernels(ops, packed, monkeypatch):
     assert torch.equal(fg["G"][1].cpu(), G0[1]) and torch.equal(dense["G"][1].cpu(), G0[1])
     assert (fg["G"].cpu() - dense["G"].cpu()).abs().max().item() < 1e-6
     torch.testing.assert_close(fg["weight"].cpu(), dense["weight"].cpu(), rtol=0, atol=2e-6)
+    # opt-in: the persistent list-driven upsample + weight kernel (same per-pixel function, background set once per call)
+    monkeypatch.setenv("B200POSE_FG_UPSAMPLE", "1")
+    fgu = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, want_weight=True)
+    assert (fgu["G"].cpu() - dense["G"].cpu()).abs().max().item() < 1e-6
+    torch.testing.assert_close(fgu["weight"].cpu(), dense["weight"].cpu(), rtol=0, atol=2e-6)
     ref = O.refine_inner_loop(load_update_weights(), f1, f2, mb["context"], mb["geofea1"], mb["geofea2"], mb["depth"],
                               mb["K"], G0, n_iters=3, n_lm=3)
     assert (fg["G"].cpu() - ref["G"]).abs().max().item() < SE3_TOL
