@@ -115,8 +115,16 @@ constexpr int UPDATE_LAUNCHES = 14;     // im2col, 11 convolutions, flow-head pa
 // use_pre: the `inp` channels (chunks 2,3 of the 384-wide GRU input [h | inp | motion]) do not change between the
 // recurrent iterations of one render iteration (CFNet.py:124-133 computes inp once): their contribution to the six GRU
 // convolutions is computed once (run_gru_precompute) and added in the epilogue, so the per-iteration GEMMs skip 1/3 of K.
+int run_update_block_tc_chain(const float* wts, float* net, float* coords1, float* flow, float* mask, float* dflow_out,
+                              int B, int h, int w, const UpdateWs& u, bool use_pre, cudaStream_t s);
+
 int run_update_block_tc(const float* wts, float* net, float* coords1, float* flow, float* mask, float* dflow_out,
                         int B, int h, int w, const UpdateWs& u, bool use_pre, cudaStream_t s) {
+    if (b2p_conv_chain_enabled() && B * ceil_div(h, B2P_TILE_ROWS) * ceil_div(w, B2P_TILE_COLS) >= 296) {
+        // experimental single-launch variant; -1 = not applicable, fall through to the layer-by-layer pass
+        const int rcc = run_update_block_tc_chain(wts, net, coords1, flow, mask, dflow_out, B, h, w, u, use_pre, s);
+        if (rcc != -1) return rcc;
+    }
     const B2PWeightLayout& L = b2p_weight_layout();
     const B2PHalfLayout& HL = b2p_half_layout();
     const __half* hbase = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(wts) + b2p_half_section_offset_bytes());
@@ -155,6 +163,59 @@ int run_update_block_tc(const float* wts, float* net, float* coords1, float* flo
     if ((rc = b2p_flow_head2(nullptr, u.hm_h[0], u.hm_h[1], wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, u.col, B, h, w, s))) return rc;
     if ((rc = conv(CV_MASK2, u.hm_h, 256, 256, 512, nullptr, 0, 0, nullptr, 0, 0, EPI_SCALE, 0.25f, mask, 576))) return rc;
     return 0;
+}
+
+// EXPERIMENTAL (B200POSE_CONV_MODE bit 4, not yet run on hardware): the same pass with the eleven convolutions in one
+// persistent launch (conv_chain_kernel).  Returns -1 when the chain cannot take this problem; the caller then runs the
+// layer-by-layer version above.
+int run_update_block_tc_chain(const float* wts, float* net, float* coords1, float* flow, float* mask, float* dflow_out,
+                              int B, int h, int w, const UpdateWs& u, bool use_pre, cudaStream_t s) {
+    (void)net;
+    const B2PWeightLayout& L = b2p_weight_layout();
+    const B2PHalfLayout& HL = b2p_half_layout();
+    const __half* hbase = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(wts) + b2p_half_section_offset_bytes());
+    UmmaConvArgs args[11];
+    int n = 0;
+    auto add = [&](int id, __half* const* s0, int off0, int c0, int p0, __half* const* s1, int c1n, int p1,
+                   __half* const* dst, int doff, int dpitch, int epi, float scale, float* out_f32, int f32_pitch,
+                   const float* pre = nullptr, int pre_pitch = 0) {
+        const B2PHalfConvDesc& d = HL.cv[id];
+        UmmaConvArgs& a = args[n++];
+        memset(&a, 0, sizeof(a));
+        a.layer_id = id;
+        if (pre) { a.pre = pre; a.pre_pitch = pre_pitch; a.chunk_mask = 0x33u; }
+        a.seg_hi[0] = s0[0] + off0; a.seg_lo[0] = s0[1] + off0; a.seg_c[0] = c0; a.seg_pitch[0] = p0;
+        if (s1) { a.seg_hi[1] = s1[0]; a.seg_lo[1] = s1[1]; a.seg_c[1] = c1n; a.seg_pitch[1] = p1; }
+        a.w_hi = hbase + d.hi_off; a.w_lo = hbase + d.lo_off; a.bias = wts + L.cv[id].b_off;
+        a.cin_pad = d.cin_pad; a.cout_pad = d.cout_pad; a.cout = d.cout; a.n_tile = d.n_tile; a.kh = d.kh; a.kw = d.kw;
+        a.B = B; a.h = h; a.w = w; a.epi = epi; a.scale = scale;
+        a.out_f32 = out_f32; a.out_f32_pitch = f32_pitch;
+        if (dst) { a.out_hi = dst[0] + doff; a.out_lo = dst[1] + doff; a.out_h_pitch = dpitch; }
+        a.zbuf = u.zbuf; a.hbuf = u.rhbuf; a.side_tiled = 1;
+    };
+    const float* pz1 = use_pre ? u.pre[0] : nullptr; const float* pq1 = use_pre ? u.pre[1] : nullptr;
+    const float* pz2 = use_pre ? u.pre[2] : nullptr; const float* pq2 = use_pre ? u.pre[3] : nullptr;
+    //  0 C1   1 C2   2 F1   3 F2   4 ENC   5 ZR1   6 Q1   7 ZR2   8 Q2   9 HEADS   10 MASK2
+    add(CV_C1, u.corr_h, 0, B200POSE_CORR_PITCH, B200POSE_CORR_PITCH, nullptr, 0, 0, u.c1_h, 0, 256, EPI_RELU, 1.f, nullptr, 0);
+    add(CV_C2, u.c1_h, 0, 256, 256, nullptr, 0, 0, u.corflo_h, 0, 256, EPI_RELU, 1.f, nullptr, 0);
+    add(CV_F1, u.col_h, 0, 112, 112, nullptr, 0, 0, u.f1o_h, 0, 128, EPI_RELU, 1.f, nullptr, 0);
+    add(CV_F2, u.f1o_h, 0, 128, 128, nullptr, 0, 0, u.corflo_h, 192, 256, EPI_RELU, 1.f, nullptr, 0);
+    add(CV_ENC, u.corflo_h, 0, 256, 256, nullptr, 0, 0, u.x_h, 128, 256, EPI_RELU, 1.f, nullptr, 0);
+    add(CV_ZR1, u.net_h, 0, 128, 128, u.x_h, 256, 256, u.rh_h, 0, 128, EPI_GRU_ZR, 1.f, nullptr, 0, pz1, 256);
+    add(CV_Q1, u.rh_h, 0, 128, 128, u.x_h, 256, 256, u.net_h, 0, 128, EPI_GRU_Q, 1.f, nullptr, 0, pq1, 128);
+    add(CV_ZR2, u.net_h, 0, 128, 128, u.x_h, 256, 256, u.rh_h, 0, 128, EPI_GRU_ZR, 1.f, nullptr, 0, pz2, 256);
+    add(CV_Q2, u.rh_h, 0, 128, 128, u.x_h, 256, 256, u.net_h, 0, 128, EPI_GRU_Q, 1.f, nullptr, 0, pq2, 128);
+    add(CV_HEADS, u.net_h, 0, 128, 128, nullptr, 0, 0, u.hm_h, 0, 512, EPI_RELU, 1.f, nullptr, 0);
+    add(CV_MASK2, u.hm_h, 256, 256, 512, nullptr, 0, 0, nullptr, 0, 0, EPI_SCALE, 0.25f, mask, 576);
+    // which earlier layers each layer reads (also the layers whose readers it must not overtake, see conv_chain_kernel)
+    const int n_src[11] = {0, 1, 0, 1, 2, 1, 1, 1, 1, 1, 1};
+    const int src[11][2] = {{0, 0}, {0, 0}, {0, 0}, {2, 0}, {1, 3}, {4, 0}, {5, 0}, {6, 0}, {7, 0}, {8, 0}, {9, 0}};
+    const int halo[11] = {0, 1, 0, 1, 1, 1, 1, 1, 1, 1, 0};
+    int rc;
+    if ((rc = b2p_im2col_f1(flow, B, h, w, nullptr, nullptr, u.col_h[0], u.col_h[1], u.x_h[0], u.x_h[1], s))) return rc;
+    // completion counters: the fp32 scratch of the exact path (unused here), well past the flow-head partial sums in u.col
+    if ((rc = b2p_launch_conv_chain(args, n, n_src, src, halo, reinterpret_cast<int*>(u.c1), s))) return rc;
+    return b2p_flow_head2(nullptr, u.hm_h[0], u.hm_h[1], wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, u.col, B, h, w, s);
 }
 
 // GRU partial sums over the `inp` channels only (chunks 2,3), no bias, no activation: pre[k][P][cout] fp32.

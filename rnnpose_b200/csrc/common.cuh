@@ -154,6 +154,10 @@ struct UmmaConvArgs {
     int b_batched;             // weights differ per sample: 3rd weight-map coordinate = sample index (1x1 only)
 };
 int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s);
+// EXPERIMENTAL: several layers in one persistent launch with tile-level dependencies (conv_chain_kernel, conv_umma.cu)
+bool b2p_conv_chain_enabled();
+int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const int* n_src, const int (*src)[2], const int* halo, int* done_ws,
+                          cudaStream_t s);
 // fp32 [P][pitch_in] -> fp16 hi/lo planes [P][pitch_out] (first C channels); used by the per-operator entry
 int b2p_split_planes(const float* src, int pitch_in, int C, size_t P, __half* hi, __half* lo, int pitch_out, cudaStream_t s);
 

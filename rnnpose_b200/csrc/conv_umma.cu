@@ -186,6 +186,9 @@ __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&w)[8]) 
 //  * the fp32 side buffers that only the epilogues touch (z gate, hidden state h, GRU pre-sums) use a TILED layout
 //    [pixel tile][C/4][128 pixels][4] (b2p_tiled_index): the 32 pixels of a warp are contiguous, 4 lines per instruction;
 //  * the PXC rows that must stay pixel-major (TMA operand planes, mask) are written with 256-bit stores.
+// COHERENT: the side buffers may have been written by another SM earlier in the SAME launch (conv_chain_kernel): read them
+// through L2 (ld.global.cg) instead of the L1 / non-coherent path.
+template <bool COHERENT = false>
 __device__ __forceinline__ void epilogue_columns(const UmmaConvParams& p, uint32_t tmem_base, int warp, int q, int buf, int n0,
                                                  int n_cnt, bool valid, size_t pix, int tile, int mrow) {
     // float4 slot of channel c (multiple of 4) of this thread's pixel in a side buffer with C channels; step between
@@ -209,12 +212,12 @@ __device__ __forceinline__ void epilogue_columns(const UmmaConvParams& p, uint32
         if (need_h) {
             const float4* hp4 = side4(p.hbuf, 128, nb & 127);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) hh[j] = hp4[j * sstep];
+            for (int j = 0; j < 8; ++j) hh[j] = COHERENT ? __ldcg(hp4 + j * sstep) : hp4[j * sstep];
         }
         if (need_z) {
             const float4* zp4 = side4(p.zbuf, 128, nb);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) zz[j] = __ldg(zp4 + j * sstep);
+            for (int j = 0; j < 8; ++j) zz[j] = COHERENT ? __ldcg(zp4 + j * sstep) : __ldg(zp4 + j * sstep);
         }
         float4 pre4[8];
         if (live && p.pre) {
@@ -828,6 +831,254 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------- kernel, chained layers
+// EXPERIMENTAL (opt-in: B200POSE_CONV_MODE bit 4; written at the end of round 1, NOT yet run on hardware).
+// The eleven convolutions of an update-block pass in ONE persistent launch of CTA pairs.  Each separate launch spends
+// 15-20 us outside its MMA loop (pipeline fill, the last unit's epilogue, the grid-wide griddepcontrol.wait; see
+// profiles/r1c_conv_counters_timeline.txt), although a tile of layer L+1 only needs its 3x3 tile neighbourhood of layer L.
+// Here the units of all layers form one list in topological order (layer by layer); clusters take them round-robin; the
+// epilogue bumps done[layer][tile] once per warp (release), and before the first activation load of a unit the producer warp
+// polls the counters of the tile neighbourhood in the unit's source layers (acquire), then fences the async proxy (the TMA
+// reads what other SMs wrote with ordinary stores).  The same neighbourhood wait also covers every write-after-read hazard of
+// the pass (net_h, rh_h, zbuf are rewritten by later layers): a layer that rewrites tile T waits for exactly the units that
+// read T.  Every cluster processes its units in list order and only waits for earlier units, so with all clusters
+// co-resident there is no deadlock.  Side buffers written earlier in the same launch are read through L2
+// (epilogue_columns<true>).  Shared memory: fixed-size ring slots for the largest layer.
+constexpr int CH_MAX_LAYERS = 11;
+constexpr int CH_RING_A = 2, CH_RING_B = 4;
+constexpr uint32_t CH_A_SLOT = 2u * 20u * 1024u;          // hi + lo planes of a 20-row activation box (5x1 with halo)
+constexpr uint32_t CH_B_SLOT = 2u * 128u * 128u;          // hi + lo planes of 128 weight rows per CTA (256-channel tiles)
+
+struct ChainDep {
+    int n_src, src[2], need[2];       // source layers and the counter value that marks one of their tiles complete
+    int halo;                          // 1: wait for the 3x3 tile neighbourhood, 0: the same tile only (1x1 layers)
+};
+struct ChainParams {
+    int n_layers, m_tiles;
+    int unit_start[CH_MAX_LAYERS + 1];     // prefix sums of the layers' unit counts
+    int* done;                              // [n_layers][m_tiles], zeroed before the launch
+    ChainDep dep[CH_MAX_LAYERS];
+    UmmaConvParams L[CH_MAX_LAYERS];
+};
+static_assert(sizeof(ChainParams) <= 32000, "kernel parameters are limited to 32764 bytes (CUDA >= 12.1, sm_70+)");
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_constant__ ChainParams cp) {
+    extern __shared__ uint8_t smem_raw[];
+    pdl_trigger();
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t a_ring = smem_base, b_ring = smem_base + CH_RING_A * CH_A_SLOT;
+    const uint32_t bars = b_ring + CH_RING_B * CH_B_SLOT;
+    auto full_a = [&](int s) { return bars + 8u * s; };
+    auto empty_a = [&](int s) { return bars + 8u * (CH_RING_A + s); };
+    const uint32_t bars_b = bars + 16u * CH_RING_A;
+    auto full_b = [&](int s) { return bars_b + 8u * s; };
+    auto empty_b = [&](int s) { return bars_b + 8u * (CH_RING_B + s); };
+    const uint32_t bars_t = bars_b + 16u * CH_RING_B;
+    auto tmem_full_bar = [&](int b) { return bars_t + 8u * b; };
+    auto tmem_empty_bar = [&](int b) { return bars_t + 16u + 8u * b; };
+    const uint32_t tmem_slot = bars_t + 32u;
+
+    // unit g of the chain -> layer l (g is monotonic per role, so l only ever advances) and the unit inside the layer;
+    // a unit = one N tile x two consecutive M tiles, CTA `rank` owns M tile 2 * group + rank (a missing second tile is
+    // replaced by the last tile and its result discarded)
+    const int total_units = cp.unit_start[cp.n_layers];
+    const int unit0 = (int)blockIdx.x >> 1, unit_step = (int)gridDim.x >> 1;
+    auto decode = [&](const UmmaConvParams& p, int u, int& bimg, int& y0, int& x0, int& n0, bool& real, int& m_idx) {
+        const int n_idx = u / p.m_groups;
+        m_idx = (u - n_idx * p.m_groups) * 2 + (int)rank;
+        real = m_idx < p.m_tiles;
+        if (!real) m_idx = p.m_tiles - 1;
+        const int tiles_per_img = p.tiles_x * p.tiles_y;
+        bimg = m_idx / tiles_per_img;
+        const int trem = m_idx - bimg * tiles_per_img;
+        y0 = (trem / p.tiles_x) * TILE_ROWS; x0 = (trem % p.tiles_x) * TILE_COLS;
+        n0 = n_idx * p.n_tile;
+    };
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < CH_RING_A; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
+        for (int s = 0; s < CH_RING_B; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 512); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer (both CTAs)
+        int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+        int l = 0;
+        for (int g = unit0; g < total_units; g += unit_step) {
+            while (g >= cp.unit_start[l + 1]) ++l;
+            const UmmaConvParams& p = cp.L[l];
+            int bimg, y0, x0, n0, m_idx; bool real;
+            decode(p, g - cp.unit_start[l], bimg, y0, x0, n0, real, m_idx);
+            // ---- dependencies: lanes 0..8 each watch one tile of the 3x3 neighbourhood (lane 4 = the tile itself)
+            const ChainDep& d = cp.dep[l];
+            if (d.n_src > 0 && lane < 9 && (d.halo || lane == 4)) {
+                const int tiles_per_img = p.tiles_x * p.tiles_y;
+                const int trem = m_idx - bimg * tiles_per_img;
+                const int ty = trem / p.tiles_x + lane / 3 - 1, tx = trem % p.tiles_x + lane % 3 - 1;
+                if (ty >= 0 && ty < p.tiles_y && tx >= 0 && tx < p.tiles_x) {
+                    const int t = bimg * tiles_per_img + ty * p.tiles_x + tx;
+                    for (int k = 0; k < d.n_src; ++k) {
+                        const int* c = cp.done + (size_t)d.src[k] * cp.m_tiles + t;
+                        uint32_t spins = 0;
+                        while (ld_acquire_gpu(c) < d.need[k]) {
+                            __nanosleep(64);
+                            if (++spins > (1u << 24)) __trap();          // a scheduling bug must fail the launch, never hang
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            asm volatile("fence.proxy.async.global;" ::: "memory");        // what those stores wrote, as seen by the TMA unit
+            const uint32_t a_plane = (uint32_t)p.a_rows * 1024u;
+            const int b_rows = p.n_tile >> 1;
+            const uint32_t b_plane = (uint32_t)b_rows * 128u;
+            const uint32_t a_tx = 2u * 2u * a_plane, b_tx = 2u * 2u * b_plane;
+            const int nb0 = n0 + (int)rank * b_rows;
+            const int outer_taps = p.a_taps == p.kh ? 1 : p.kh;
+            for (int kyo = 0; kyo < outer_taps; ++kyo) {
+                const int ys = y0 + kyo - (p.kh >> 1);
+                for (int kx = 0; kx < p.kw; ++kx) {
+                    const int xs = x0 + kx - (p.kw >> 1);
+                    for (int a = 0; a < p.n_active; ++a) {
+                        const int cc = p.chunk_list[a];
+                        const int seg = cc >= p.seg0_chunks ? 1 : 0;
+                        const int c0 = (seg ? cc - p.seg0_chunks : cc) * BKC;
+                        const uint32_t da = a_ring + (uint32_t)sa * CH_A_SLOT;
+                        mbar_wait(empty_a(sa), pha ^ 1u);
+                        if (elect_one()) {
+                            const uint32_t fb = mapa_rank(full_a(sa), 0);
+                            if (rank == 0) mbar_expect_tx(full_a(sa), a_tx);
+                            tma_load_4d_pair(&p.a_hi[seg], da, fb, c0, xs, ys, bimg);
+                            tma_load_4d_pair(&p.a_lo[seg], da + a_plane, fb, c0, xs, ys, bimg);
+                        }
+                        __syncwarp();
+                        if (++sa == CH_RING_A) { sa = 0; pha ^= 1u; }
+                        for (int j = 0; j < p.a_taps; ++j) {
+                            const int tap = (kyo + j) * p.kw + kx;
+                            const uint32_t db = b_ring + (uint32_t)sb * CH_B_SLOT;
+                            mbar_wait(empty_b(sb), phb ^ 1u);
+                            if (elect_one()) {
+                                const uint32_t fb = mapa_rank(full_b(sb), 0);
+                                if (rank == 0) mbar_expect_tx(full_b(sb), b_tx);
+                                tma_load_3d_pair(&p.b_hi, db, fb, cc * BKC, nb0, tap);
+                                tma_load_3d_pair(&p.b_lo, db + b_plane, fb, cc * BKC, nb0, tap);
+                            }
+                            __syncwarp();
+                            if (++sb == CH_RING_B) { sb = 0; phb ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+        // drain: every commit aimed at this CTA's empty barriers has landed before the CTA may exit
+        for (int i = 0; i < CH_RING_A; ++i) { mbar_wait(empty_a(sa), pha ^ 1u); if (++sa == CH_RING_A) { sa = 0; pha ^= 1u; } }
+        for (int i = 0; i < CH_RING_B; ++i) { mbar_wait(empty_b(sb), phb ^ 1u); if (++sb == CH_RING_B) { sb = 0; phb ^= 1u; } }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ------------------------------------------------ MMA issuer (leader CTA)
+            uint32_t tile_iter = 0;
+            int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+            int l = 0;
+            for (int g = unit0; g < total_units; g += unit_step, ++tile_iter) {
+                while (g >= cp.unit_start[l + 1]) ++l;
+                const UmmaConvParams& p = cp.L[l];
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((256u >> 4) << 24);
+                const uint32_t a_plane = (uint32_t)p.a_rows * 1024u, b_plane = (uint32_t)(p.n_tile >> 1) * 128u;
+                const int outer_taps = p.a_taps == p.kh ? 1 : p.kh;
+                const int a_items = outer_taps * p.kw * p.n_active;
+                const int buf = tile_iter & 1;
+                const uint32_t acc = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
+                mbar_wait(tmem_empty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);
+                tc_fence_after();
+                uint32_t accumulate = 0;
+                for (int ai = 0; ai < a_items; ++ai) {
+                    mbar_wait(full_a(sa), pha);
+                    const uint32_t da = a_ring + (uint32_t)sa * CH_A_SLOT;
+                    for (int j = 0; j < p.a_taps; ++j) {
+                        mbar_wait(full_b(sb), phb);
+                        tc_fence_after();
+                        const uint32_t db = b_ring + (uint32_t)sb * CH_B_SLOT;
+                        if (elect_one()) {
+                            const uint64_t a_hi = umma_desc_sw128(da + (uint32_t)j * 1024u);
+                            const uint64_t a_lo = umma_desc_sw128(da + a_plane + (uint32_t)j * 1024u);
+                            const uint64_t b_hi = umma_desc_sw128(db), b_lo = umma_desc_sw128(db + b_plane);
+#pragma unroll
+                            for (int k = 0; k < BKC / 16; ++k) {
+                                const uint64_t adv = (uint64_t)(k * 2);
+                                tc_mma_f16_pair(acc, a_lo + adv, b_hi + adv, idesc, k == 0 ? accumulate : 1u);
+                                tc_mma_f16_pair(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                                tc_mma_f16_pair(acc, a_hi + adv, b_hi + adv, idesc, 1u);
+                            }
+                            tc_commit_pair(empty_b(sb));
+                            if (j == p.a_taps - 1) tc_commit_pair(empty_a(sa));
+                        }
+                        __syncwarp();
+                        accumulate = 1u;
+                        if (++sb == CH_RING_B) { sb = 0; phb ^= 1u; }
+                    }
+                    if (++sa == CH_RING_A) { sa = 0; pha ^= 1u; }
+                }
+                if (elect_one()) tc_commit_pair(tmem_full_bar(buf));
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---------------------------------------------------- epilogue (both CTAs), then the completion signal of the tile
+        const int q = warp & 3;
+        const int mrow = q * 32 + lane;
+        uint32_t tile_iter = 0;
+        int l = 0;
+        for (int g = unit0; g < total_units; g += unit_step, ++tile_iter) {
+            while (g >= cp.unit_start[l + 1]) ++l;
+            const UmmaConvParams& p = cp.L[l];
+            int bimg, y0, x0, n0, m_idx; bool real;
+            decode(p, g - cp.unit_start[l], bimg, y0, x0, n0, real, m_idx);
+            const int buf = tile_iter & 1;
+            const int yy = y0 + (mrow >> 3), xx = x0 + (mrow & 7);
+            const bool valid = real && yy < p.h && xx < p.w;
+            const size_t pix = ((size_t)bimg * p.h + yy) * p.w + xx;
+            mbar_wait_backoff(tmem_full_bar(buf), (tile_iter >> 1) & 1);
+            tc_fence_after();
+            epilogue_columns<true>(p, tmem_base, warp, q, buf, n0, p.n_tile, valid, pix, m_idx, mrow);
+            tc_fence_before();
+            mbar_arrive_cluster(mapa_rank(tmem_empty_bar(buf), 0));
+            // publish this warp's share of the tile: its stores become visible device-wide (and to the async proxy of the
+            // SMs that will TMA-load them) before the counter moves
+            __threadfence();
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && real)
+                asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(cp.done + (size_t)l * cp.m_tiles + m_idx) : "memory");
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -917,6 +1168,7 @@ int device_sms() {
         if (cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
         if (cudaFuncSetAttribute(conv_umma2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
         if (cudaFuncSetAttribute(conv_umma2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
         sms_of[dev] = sms; done[dev] = true;
     }
     return sms_of[dev];
@@ -1003,6 +1255,45 @@ int launch_conv_umma2(const UmmaConvArgs& a, UmmaConvParams& p, int ncta, bool r
     if (ncta == 2) B2P_CUDA(launch_pdl_cluster(conv_umma2_kernel<2>, nclusters * 2, 2, smem, s, p));
     else B2P_CUDA(launch_pdl_cluster(conv_umma2_kernel<1>, nclusters, 1, smem, s, p));
     B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+
+// One layer of a chained launch: the same planning as launch_conv_umma2 for a CTA pair with vertical-tap reuse, without
+// rings (fixed) and without tail splitting (the next layer's units fill the tail).
+int fill_chain_layer(const UmmaConvArgs& a, UmmaConvParams& p) {
+    memset(&p, 0, sizeof(p));
+    int rc;
+    const int taps = a.kh * a.kw;
+    const int n_tile = (a.n_tile == 128 && a.cout_pad % 256 == 0) ? 256 : a.n_tile;
+    if (a.b_batched || n_tile % 32 || n_tile / 2 > 128 || a.kh > 5 || a.cout_pad % n_tile) return -1;
+    p.a_taps = a.kh;
+    p.a_rows = TILE_ROWS + a.kh - 1;
+    for (int g = 0; g < 2; ++g) {
+        if (a.seg_c[g] == 0) { p.a_hi[g] = p.a_hi[0]; p.a_lo[g] = p.a_lo[0]; continue; }
+        if ((rc = make_act_map(&p.a_hi[g], a.seg_hi[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.a_rows))) return rc;
+        if ((rc = make_act_map(&p.a_lo[g], a.seg_lo[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.a_rows))) return rc;
+    }
+    if ((rc = make_wgt_map(&p.b_hi, a.w_hi, a.cin_pad, a.cout_pad, taps, n_tile / 2))) return rc;
+    if ((rc = make_wgt_map(&p.b_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, n_tile / 2))) return rc;
+    p.bs_hi = p.b_hi; p.bs_lo = p.b_lo;
+    p.seg0_chunks = (a.seg_c[0] + BKC - 1) / BKC;
+    p.chunks_per_tap = a.cin_pad / BKC;
+    for (int cc = 0; cc < p.chunks_per_tap && cc < 8; ++cc)
+        if (a.chunk_mask == 0 || ((a.chunk_mask >> cc) & 1u)) p.chunk_list[p.n_active++] = cc;
+    p.pre = a.pre; p.pre_pitch = a.pre_pitch;
+    p.kh = a.kh; p.kw = a.kw; p.B = a.B; p.h = a.h; p.w = a.w;
+    p.tiles_x = ceil_div(a.w, TILE_COLS); p.tiles_y = ceil_div(a.h, TILE_ROWS);
+    p.n_tile = n_tile; p.cout = a.cout;
+    p.bias = a.bias; p.epi = a.epi; p.scale = a.scale;
+    p.out_f32 = a.out_f32; p.out_f32_pitch = a.out_f32_pitch;
+    p.out_hi = a.out_hi; p.out_lo = a.out_lo; p.out_h_pitch = a.out_h_pitch;
+    p.zbuf = a.zbuf; p.hbuf = a.hbuf;
+    p.side_tiled = a.side_tiled; p.out_tiled = a.out_tiled;
+    p.m_tiles = a.B * p.tiles_x * p.tiles_y;
+    p.m_groups = ceil_div(p.m_tiles, 2);
+    p.total_tiles = p.m_groups * (a.cout_pad / n_tile);
+    p.full_units = p.total_units = p.total_tiles; p.split = 1; p.n_sub = n_tile;
     return 0;
 }
 
@@ -1107,4 +1398,52 @@ extern "C" int b200pose_debug_conv_log(unsigned long long* host_out) {
     B2P_CUDA(cudaMemcpyFromSymbol(&n, g_conv_log_n, sizeof(n)));
     B2P_CUDA(cudaMemcpyFromSymbol(host_out, g_conv_log, sizeof(unsigned long long) * 512 * 4));
     return (int)(n > 512 ? 512 : n);
+}
+
+// EXPERIMENTAL chained launch (conv_chain_kernel): n layers in list order; src[l][k] (k < n_src[l]) are the indices of the
+// layers whose output layer l reads, halo[l] = 0 for 1x1 layers.  done_ws: n * m_tiles ints of device scratch.
+// Returns -1 when the layer set does not fit the fixed ring geometry (the caller then launches the layers one by one).
+bool b2p_conv_chain_enabled() { return (conv_mode() & 16) != 0; }
+
+int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const int* n_src, const int (*src)[2], const int* halo, int* done_ws,
+                          cudaStream_t s) {
+    if (n < 1 || n > CH_MAX_LAYERS) return -1;
+    const int sms = device_sms();
+    if (sms <= 0) return (int)cudaErrorInvalidDevice;
+    static ChainParams cp;                       // large: keep it off the stack; filled and consumed under the lock
+    static std::mutex cp_mutex;
+    std::lock_guard<std::mutex> lk(cp_mutex);
+    memset(&cp, 0, sizeof(cp));
+    cp.n_layers = n;
+    int rc;
+    for (int l = 0; l < n; ++l) {
+        if ((rc = fill_chain_layer(args[l], cp.L[l]))) return rc;
+        cp.unit_start[l + 1] = cp.unit_start[l] + cp.L[l].total_units;
+        if (cp.L[l].m_tiles != cp.L[0].m_tiles) return -1;
+    }
+    cp.m_tiles = cp.L[0].m_tiles;
+    for (int l = 0; l < n; ++l) {
+        cp.dep[l].n_src = n_src[l]; cp.dep[l].halo = halo[l];
+        for (int k = 0; k < n_src[l]; ++k) {
+            const int sl = src[l][k];
+            if (sl < 0 || sl >= l) return -1;                       // topological order
+            cp.dep[l].src[k] = sl;
+            cp.dep[l].need[k] = (args[sl].cout_pad / cp.L[sl].n_tile) * 8;      // units per tile x epilogue warps
+        }
+    }
+    cp.done = done_ws;
+    B2P_CUDA(cudaMemsetAsync(done_ws, 0, (size_t)n * cp.m_tiles * sizeof(int), s));
+    const int nclusters = sms / 2;
+    const size_t smem = (size_t)CH_RING_A * CH_A_SLOT + (size_t)CH_RING_B * CH_B_SLOT + 1024 + 16 * (CH_RING_A + CH_RING_B) + 64;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nclusters * 2); cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    B2P_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel, cp));
+    B2P_LAUNCH_CHECK();
+    return 0;
 }

@@ -1,6 +1,8 @@
 """End-to-end parity of the fused inner loop (b200pose_refine_iters through the C-ABI) with
 (1) the golden outputs of the executed reference, (2) the oracle on batched inputs, and size-independent
 properties at the BASELINE.json sizes.  Tolerance (north_star): final SE3 within 1e-4 abs."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -221,3 +223,23 @@ def test_refine_foreground_list_matches_dense_kernels(ops, packed, monkeypatch):
     ref = O.refine_inner_loop(load_update_weights(), f1, f2, mb["context"], mb["geofea1"], mb["geofea2"], mb["depth"],
                               mb["K"], G0, n_iters=3, n_lm=3)
     assert (fg["G"].cpu() - ref["G"]).abs().max().item() < SE3_TOL
+
+
+@pytest.mark.skipif(os.environ.get("B200POSE_TEST_EXPERIMENTAL") != "1",
+                    reason="conv_chain_kernel (B200POSE_CONV_MODE bit 4) has not been run on hardware yet; opt in with "
+                           "B200POSE_TEST_EXPERIMENTAL=1")
+def test_refine_chained_convolutions_experimental(ops, packed, monkeypatch):
+    """The eleven convolutions of a pass in one persistent launch with tile-level dependencies (mode 19) against the
+    layer-by-layer default at the bench shape (the chain needs a machine-filling batch)."""
+    H, W, B = 240, 320, 32
+    uniq = S.make_batch([0, 1, 2, 3], H, W, with_images=False)
+    rep = {k: v.repeat(8, *([1] * (v.dim() - 1))) for k, v in uniq.items() if k != "diameter"}
+    f1 = S.hash_features((4, 256, H // 8, W // 8), 71).repeat(8, 1, 1, 1); f2 = S.hash_features((4, 256, H // 8, W // 8), 72).repeat(8, 1, 1, 1)
+    G0 = torch.eye(4)[None].repeat(B, 1, 1)
+    ref = run_gpu(ops, packed, f1, f2, rep, G0, 4, 3)["G"].cpu()
+    monkeypatch.setenv("B200POSE_CONV_MODE", "19")
+    got = run_gpu(ops, packed, f1, f2, rep, G0, 4, 3)["G"].cpu()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() < 1e-6
+    for k in range(4, B):
+        assert torch.equal(got[k], got[k % 4])
