@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200POSE_VERSION 1
+#define B200POSE_VERSION 2
 
 /* error codes (negative); positive return values are cudaError_t */
 #define B200POSE_OK            0
@@ -153,14 +153,26 @@ int b200pose_lm_solve(const float* depth, const float* target, const float* weig
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- f3: per-object pose metrics ----------------------------------------------------------------
- * Replaces the evaluator's per-object arithmetic: utils/eval_metric.py:161-192 (add_metric with the brute-force
- * nearest neighbour of thirdparty/nn/src/nearest_neighborhood.cu:48-117 for symmetric objects, cm_degree_5_metric)
- * and utils/geometric.py:36-40 (rotation_angle).  T_pred,T_gt: [B,4,4] row-major; pts: [B,n_pts,3] model points;
- * diameter: [B].  out: [B,8] = {ADD, ADD-S, rotation error (deg), translation error (same unit as pts),
- * ADD < 0.1 d, ADD-S < 0.1 d, (trans*100 < 5 and deg < 5), 0}.  workspace: b200pose_pose_metrics_workspace_bytes.   */
+ * Replaces the evaluator's per-object arithmetic (utils/eval_metric.py:306-339 evaluate_rnnpose): add_metric /
+ * add2_metric / add5_metric (:120-179) with the brute-force nearest neighbour of thirdparty/nn (nn_utils.py:6-22,
+ * src/nearest_neighborhood.cu:48-80) for symmetric objects, projection_2d (:102-110, :23-35), cm_degree_5_metric
+ * (:181-192) and utils/geometric.py:36-40 (rotation_angle).  T_pred,T_gt: [B,4,4] row-major; pts: [B,n_pts,3] model
+ * points; diameter: [B] (same unit as pts); K: [B,3,3] projection intrinsics (the reference uses linemod_K).
+ * out: [B,B200POSE_METRIC_COLS] =
+ *   0 ADD            mean_x |T_pred x - T_gt x|
+ *   1 ADD-S          mean over the GROUND-TRUTH points of the distance to the nearest PREDICTED point (the reference's
+ *                    direction: find_nearest_point_idx(model_pred, model_targets), eval_metric.py:167-171)
+ *   2 rotation error, chordal form 2 asin(|R_gt - R_pred|_F / sqrt 8), degrees     3 translation error |t_pred - t_gt|
+ *   4 mean 2-D projection error (pixels)     5 rotation error from the trace, acos((tr(R_pred R_gt^T) - 1) / 2), degrees
+ *   6 ADD < 0.1 d   7 ADD-S < 0.1 d   8 ADD < 0.02 d   9 ADD-S < 0.02 d   10 ADD < 0.05 d   11 ADD-S < 0.05 d
+ *   12 projection error < 5 px     13 translation * 100 < 5 and trace angle < 5 (5 cm 5 deg, pts in metres)
+ *   14 0 (slot for the caller's object index)     15 d
+ * workspace: b200pose_pose_metrics_workspace_bytes.                                                              */
+#define B200POSE_METRIC_COLS 16
 size_t b200pose_pose_metrics_workspace_bytes(int B, int n_pts);
 int b200pose_pose_metrics(const float* T_pred, const float* T_gt, const float* pts, const float* diameter,
-                          int B, int n_pts, float* out, void* workspace, size_t workspace_bytes, void* stream);
+                          const float* K, int B, int n_pts, float* out, void* workspace, size_t workspace_bytes,
+                          void* stream);
 
 /* ---- a14: the fused inner loop ----------------------------------------------------------------
  * Replaces the body of `for i in range(cfg.ITER_COUNT)` in PoseRefiner.forward

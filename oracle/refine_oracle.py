@@ -407,15 +407,37 @@ def refine_inner_loop(wts: Dict[str, torch.Tensor], fmap1, fmap2, context_fea, g
 
 # ----------------------------------------------------------------------------- metrics (A.8)
 def add_metric(R_p, t_p, R_g, t_g, pts, symmetric: bool = False) -> torch.Tensor:
-    """ADD / ADD-S mean distance, utils/eval_metric.py:161-179 (ADD-S: nearest neighbour, the
-    job of thirdparty/nn/src/nearest_neighborhood.cu).  R [B,3,3], t [B,3], pts [N,3] -> [B]."""
+    """ADD / ADD-S mean distance, utils/eval_metric.py:161-179.  R [B,3,3], t [B,3], pts [N,3] -> [B].
+    ADD-S (syn=True, :167-171): idxs = find_nearest_point_idx(model_pred, model_targets) -- ref = the PREDICTED points,
+    que = the GROUND-TRUTH points (thirdparty/nn/nn_utils.py:6-22), each query takes the first nearest reference point
+    (thirdparty/nn/src/nearest_neighborhood.cu:48-80) -- then mean ||model_pred[idxs] - model_targets|| over the
+    ground-truth points.  Pinned by tests/golden/metrics.npz (the reference's evaluator executed)."""
     pp = torch.einsum("bij,nj->bni", R_p, pts) + t_p[:, None]
     pg = torch.einsum("bij,nj->bni", R_g, pts) + t_g[:, None]
     if symmetric:
-        d = torch.cdist(pp, pg, compute_mode="donot_use_mm_for_euclid_dist").min(dim=2).values
+        d2 = ((pp[:, :, None, :] - pg[:, None, :, :]) ** 2).sum(-1)            # [B, pred, gt]
+        idx = d2.argmin(dim=1)                                                  # nearest predicted point of each gt point
+        d = (torch.gather(pp, 1, idx[..., None].expand(-1, -1, 3)) - pg).norm(dim=-1)
     else:
         d = (pp - pg).norm(dim=-1)
     return d.mean(dim=1)
+
+
+def projection_2d(R_p, t_p, R_g, t_g, pts, K) -> torch.Tensor:
+    """Mean pixel distance of the model projected with both poses, utils/eval_metric.py:23-35,102-110.  K [3,3]."""
+    def proj(R, t):
+        x = torch.einsum("bij,nj->bni", R, pts) + t[:, None]
+        x = torch.einsum("ij,bnj->bni", K.to(x), x)
+        return x[..., :2] / x[..., 2:]
+    return (proj(R_p, t_p) - proj(R_g, t_g)).norm(dim=-1).mean(dim=1)
+
+
+def cm_degree_5(R_p, t_p, R_g, t_g):
+    """utils/eval_metric.py:181-192: (translation distance * 100, angle from the trace in degrees, flag)."""
+    trans = (t_p - t_g).norm(dim=1) * 100
+    trace = torch.clamp((R_p * R_g).sum(dim=(1, 2)), max=3.0)
+    ang = torch.rad2deg(torch.acos((trace - 1.0) / 2.0))
+    return trans, ang, (trans < 5) & (ang < 5)
 
 
 def rotation_angle_deg(R_p, R_g) -> torch.Tensor:

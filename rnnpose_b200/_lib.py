@@ -32,7 +32,7 @@ SIGNATURES = {
     "b200pose_conv_layer": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "b200pose_upsample_weight": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "b200pose_pose_metrics_workspace_bytes": (_sz, [_i, _i]),
-    "b200pose_pose_metrics": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "b200pose_pose_metrics": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "b200pose_lm_workspace_bytes": (_sz, [_i, _i, _i]),
     "b200pose_lm_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _d, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200pose_refine_workspace_bytes": (_sz, [_i, _i, _i]),

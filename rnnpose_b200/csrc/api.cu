@@ -501,12 +501,12 @@ int b200pose_upsample_weight(const float* flow, const float* mask, const float* 
 
 size_t b200pose_pose_metrics_workspace_bytes(int B, int n_pts) { return b2p_pose_metrics_ws_bytes(B, n_pts); }
 
-int b200pose_pose_metrics(const float* T_pred, const float* T_gt, const float* pts, const float* diameter, int B, int n_pts,
-                          float* out, void* workspace, size_t workspace_bytes, void* stream) {
-    if (!T_pred || !T_gt || !pts || !diameter || !out || !workspace) return B200POSE_E_NULL;
+int b200pose_pose_metrics(const float* T_pred, const float* T_gt, const float* pts, const float* diameter, const float* K,
+                          int B, int n_pts, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!T_pred || !T_gt || !pts || !diameter || !K || !out || !workspace) return B200POSE_E_NULL;
     if (B < 1 || B > 65535 || n_pts < 1) return B200POSE_E_SHAPE;
     if (((uintptr_t)workspace & 255) || workspace_bytes < b2p_pose_metrics_ws_bytes(B, n_pts)) return B200POSE_E_WORKSPACE;
-    return b2p_pose_metrics(T_pred, T_gt, pts, diameter, B, n_pts, out, workspace, (cudaStream_t)stream);
+    return b2p_pose_metrics(T_pred, T_gt, pts, diameter, K, B, n_pts, out, workspace, (cudaStream_t)stream);
 }
 
 size_t b200pose_lm_workspace_bytes(int B, int H, int W) { return b2p_lm_ws_bytes(B, H, W); }

@@ -200,6 +200,6 @@ int b2p_lm_steps(const float* depth, const float* target, const float* weight, c
 size_t b2p_lm_ws_bytes(int B, int H, int W);
 int b2p_lm_reset(void* ws, int B, int H, int W, cudaStream_t s);   // once before the first b2p_lm_step on a workspace
 size_t b2p_pose_metrics_ws_bytes(int B, int n);
-int b2p_pose_metrics(const float* T_pred, const float* T_gt, const float* pts, const float* diameter, int B, int n, float* out,
-                     void* ws, cudaStream_t s);
+int b2p_pose_metrics(const float* T_pred, const float* T_gt, const float* pts, const float* diameter, const float* K, int B,
+                     int n, float* out, void* ws, cudaStream_t s);
 int b2p_pack_weights(const float* const* t, float* packed, cudaStream_t s);   // fp32 section + fp16 hi/lo section

@@ -221,21 +221,33 @@ def lm_solve(depth: torch.Tensor, target: torch.Tensor, weight: torch.Tensor, K:
     return (G, Ho, bo, do) if taps else G
 
 
-def pose_metrics(T_pred: torch.Tensor, T_gt: torch.Tensor, pts: torch.Tensor, diameter: torch.Tensor) -> torch.Tensor:
-    """[B,8] = ADD, ADD-S, rotation error (deg), translation error, ADD < 0.1 d, ADD-S < 0.1 d, 5cm5deg, 0.
-    Replaces utils/eval_metric.py:161-192 + thirdparty/nn (brute-force nearest neighbour) + geometric.py:36-40."""
+METRIC_COLS = 16
+LINEMOD_K = ((572.4114, 0.0, 325.2611), (0.0, 573.57043, 242.04899), (0.0, 0.0, 1.0))   # data/linemod/linemod_config.py:23-25
+
+
+def pose_metrics(T_pred: torch.Tensor, T_gt: torch.Tensor, pts: torch.Tensor, diameter: torch.Tensor,
+                 K: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B,16] per-object metric row of include/b200pose.h (ADD, ADD-S, angles, translation, 2-D projection, flags).
+    Replaces utils/eval_metric.py:102-192 + thirdparty/nn (brute-force nearest neighbour) + geometric.py:36-40.
+    K [B,3,3] or [3,3]; default linemod_K, which is what the reference's evaluator projects with (eval_metric.py:338)."""
     L = _lib.lib()
     T_pred, T_gt, pts, diameter = (t.contiguous().float() for t in (T_pred, T_gt, pts, diameter))
-    for t, n in ((T_pred, "T_pred"), (T_gt, "T_gt"), (pts, "pts"), (diameter, "diameter")):
-        _chk(t, n)
     B, n_pts = pts.shape[0], pts.shape[1]
-    if T_pred.shape != (B, 4, 4) or T_gt.shape != (B, 4, 4) or pts.shape[2] != 3 or diameter.shape != (B,):
-        raise ValueError("pose_metrics: T [B,4,4], pts [B,n,3], diameter [B]")
-    out = torch.empty(B, 8, dtype=torch.float32, device=pts.device)
+    if K is None:
+        K = torch.tensor(LINEMOD_K, dtype=torch.float32, device=pts.device)
+    K = K.to(device=pts.device, dtype=torch.float32)
+    if K.dim() == 2:
+        K = K[None].expand(B, 3, 3)
+    K = K.contiguous()
+    for t, n in ((T_pred, "T_pred"), (T_gt, "T_gt"), (pts, "pts"), (diameter, "diameter"), (K, "K")):
+        _chk(t, n)
+    if T_pred.shape != (B, 4, 4) or T_gt.shape != (B, 4, 4) or pts.shape[2] != 3 or diameter.shape != (B,) or K.shape != (B, 3, 3):
+        raise ValueError("pose_metrics: T [B,4,4], pts [B,n,3], diameter [B], K [B,3,3]")
+    out = torch.empty(B, METRIC_COLS, dtype=torch.float32, device=pts.device)
     nb = L.b200pose_pose_metrics_workspace_bytes(B, n_pts)
     ws = _ws(nb, pts.device)
-    _lib.check(L.b200pose_pose_metrics(T_pred.data_ptr(), T_gt.data_ptr(), pts.data_ptr(), diameter.data_ptr(), B, n_pts,
-                                       out.data_ptr(), ws.data_ptr(), nb, _stream()), "b200pose_pose_metrics")
+    _lib.check(L.b200pose_pose_metrics(T_pred.data_ptr(), T_gt.data_ptr(), pts.data_ptr(), diameter.data_ptr(), K.data_ptr(),
+                                       B, n_pts, out.data_ptr(), ws.data_ptr(), nb, _stream()), "b200pose_pose_metrics")
     return out
 
 

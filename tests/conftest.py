@@ -16,33 +16,3 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
-
-
-# One full-suite run on the GPU pool (out of about ten on the same build; the test was green three times in isolation right
-# after) failed tests/test_gpu_ops.py::test_context_init, a self-contained, deterministic kernel-vs-oracle comparison.  The
-# cause was not found (nothing else runs on the device during that test).  GPU tests are therefore retried ONCE when their call
-# phase fails: a test that fails twice is reported as failed, and every retried test is named in the terminal summary so
-# that a recurring one does not go unnoticed.
-_RETRIED = []
-
-
-def pytest_runtest_protocol(item, nextitem):
-    if item.get_closest_marker("gpu") is None:
-        return None                                   # default protocol
-    from _pytest.runner import runtestprotocol
-    item.ihook.pytest_runtest_logstart(nodeid=item.nodeid, location=item.location)
-    reports = runtestprotocol(item, nextitem=nextitem, log=False)
-    if any(r.when == "call" and r.failed for r in reports):
-        _RETRIED.append(item.nodeid)
-        if hasattr(item, "_request") and hasattr(item, "_initrequest"):
-            item._initrequest()                       # fresh fixture request for the second attempt
-        reports = runtestprotocol(item, nextitem=nextitem, log=False)
-    for r in reports:
-        item.ihook.pytest_runtest_logreport(report=r)
-    item.ihook.pytest_runtest_logfinish(nodeid=item.nodeid, location=item.location)
-    return True
-
-
-def pytest_terminal_summary(terminalreporter):
-    if _RETRIED:
-        terminalreporter.write_line("GPU tests retried once after a failed first attempt: " + ", ".join(_RETRIED))

@@ -81,3 +81,82 @@ def build_reference_refiner(renderer, H, W, **cfgkw):
     net = PoseRefiner(motion_cfg(**cfgkw), renderer=renderer)
     net.eval()
     return net
+
+
+def install_eval_stubs():
+    """Extra in-memory stubs so that the reference's evaluator (utils/eval_metric.py) imports unmodified:
+    plyfile / open3d / matplotlib (not installed; unused by the metric methods), a namespace `data` package (its
+    __init__ pulls the whole dataset stack), and thirdparty.nn._ext -- the compiled CUDA extension -- whose one entry
+    point is restated in numpy from thirdparty/nn/src/nearest_neighborhood.cu:48-80 (float32 squared distances summed
+    x, y, z; strict '<' so the FIRST minimum wins).  thirdparty/nn/nn_utils.py itself runs unmodified on top of it."""
+    install_stubs()
+    import ctypes
+    import numpy as np
+
+    def mod(name, **attrs):
+        if name in sys.modules:
+            m = sys.modules[name]
+        else:
+            m = types.ModuleType(name)
+            sys.modules[name] = m
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        return m
+
+    mod("plyfile", PlyData=object)
+    mod("open3d")
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        mpl = mod("matplotlib")
+        mpl.cm = mod("matplotlib.cm", get_cmap=lambda *a, **k: None)
+        mpl.pyplot = mod("matplotlib.pyplot")
+        mpl.patches = mod("matplotlib.patches")
+    try:
+        import scipy.misc  # noqa: F401
+    except ImportError:
+        import scipy
+        scipy.misc = mod("scipy.misc")
+    q = sys.modules["transforms3d.quaternions"]
+    for n in ("mat2quat", "quat2mat", "qmult"):
+        if not hasattr(q, n):
+            setattr(q, n, None)
+    if "data" not in sys.modules:
+        d = mod("data")
+        d.__path__ = [os.path.join(REF, "data")]
+
+    class _FFI:
+        @staticmethod
+        def cast(ctype, addr):
+            return (ctype, int(addr))
+
+    class _Lib:
+        @staticmethod
+        def findNearestPointIdxLauncher(ref_ptr, que_ptr, idx_ptr, b, pn1, pn2, dim, exclude_self):
+            assert b == 1 and not exclude_self
+            ref = np.ctypeslib.as_array(ctypes.cast(ref_ptr[1], ctypes.POINTER(ctypes.c_float)), shape=(pn1, dim))
+            que = np.ctypeslib.as_array(ctypes.cast(que_ptr[1], ctypes.POINTER(ctypes.c_float)), shape=(pn2, dim))
+            idx = np.ctypeslib.as_array(ctypes.cast(idx_ptr[1], ctypes.POINTER(ctypes.c_int32)), shape=(pn2,))
+            for i in range(pn2):
+                d = np.zeros(pn1, np.float32)
+                for k in range(dim):                       # (x1-x2)^2 + (y1-y2)^2 + (z1-z2)^2 in float32, in this order
+                    diff = ref[:, k] - que[i, k]
+                    d = d + diff * diff
+                idx[i] = int(np.argmin(d))                  # first minimum, as the strict '<' scan
+
+    mod("thirdparty.nn._ext", lib=_Lib, ffi=_FFI)
+
+
+def reference_evaluator(model_pts, diameter_m):
+    """utils.eval_metric.LineMODEvaluator with its metric methods untouched; the constructor (which reads a .ply from
+    EXPDATA, absent here) is bypassed and the attributes it would set are filled from the arguments."""
+    install_eval_stubs()
+    import numpy as np
+    import utils.eval_metric as EM
+    ev = EM.LineMODEvaluator.__new__(EM.LineMODEvaluator)
+    ev.class_name = "synthetic"
+    ev.model = np.asarray(model_pts, np.float32)
+    ev.diameter = float(diameter_m)
+    for name in ("proj2d", "add", "adds", "add2", "add5", "cmd5", "icp_proj2d", "icp_add", "icp_cmd5", "mask_ap", "pose_preds"):
+        setattr(ev, name, [])
+    return ev, EM

@@ -19,7 +19,8 @@ def header_functions():
 def test_library_builds_and_loads():
     if not os.path.exists(_lib.LIB_PATH):
         _lib.build()
-    assert _lib.lib().b200pose_version() == 1
+    hdr = open(os.path.join(ROOT, "include", "b200pose.h")).read()
+    assert _lib.lib().b200pose_version() == int(re.search(r"#define B200POSE_VERSION (\d+)", hdr).group(1))
 
 
 def test_every_declared_symbol_is_exported_and_bound():

@@ -232,7 +232,50 @@ def test_lm_vs_oracle_random(ops):
     torch.testing.assert_close(Gd.cpu(), Gr, rtol=0, atol=5e-6)
 
 
-# ----------------------------------------------------------------------------- f3: pose metrics (ADD / ADD-S kernel)
+# ----------------------------------------------------------------------------- f3: pose metrics kernel
+def _metric_cases():
+    """tests/golden/metrics.npz: the reference's LineMODEvaluator executed (make_golden_metrics.py)."""
+    g = golden("metrics.npz")
+    rows = g["rows"]
+    by_set = {}
+    for r in rows:
+        by_set.setdefault(int(r[0]), []).append(r)
+    return g, by_set
+
+
+def test_pose_metrics_reference_golden(ops):
+    """ADD, ADD-S (ground-truth query -> nearest predicted point, eval_metric.py:167-171), ADD2/ADD5, 2-D projection and
+    5cm5deg against the executed reference: distances within 1e-6 d, every flag identical (the golden holds pairs 0.5 %
+    either side of each threshold)."""
+    from rnnpose_b200 import metrics as M
+    g, by_set = _metric_cases()
+    K = T(g["K"]).float()
+    for si, rows in by_set.items():
+        pts = T(g[f"pts{si}"]).float()
+        n = len(rows)
+        Tp = torch.eye(4).repeat(n, 1, 1); Tg = torch.eye(4).repeat(n, 1, 1)
+        for k, r in enumerate(rows):
+            Tp[k, :3] = T(g[f"pose_pred_{si}_{int(r[1])}"]); Tg[k, :3] = T(g[f"pose_gt_{si}_{int(r[1])}"])
+        R = torch.from_numpy(np.asarray(rows))
+        d = R[:, 2]
+        out = M.pose_metrics(Tp.to(dev()), Tg.to(dev()), pts[None].repeat(n, 1, 1).to(dev()), d.float().to(dev()),
+                             torch.arange(n).to(dev()), K.to(dev())).cpu().double()
+        assert out.shape == (n, 16)
+        assert ((out[:, 0] - R[:, 3]).abs() / d).max() < 1e-6, "ADD"
+        assert ((out[:, 1] - R[:, 4]).abs() / d).max() < 1e-6, "ADD-S"
+        torch.testing.assert_close(out[:, 4], R[:, 5], rtol=2e-5, atol=2e-4)          # projection error, pixels
+        fin = torch.isfinite(R[:, 6]) & (R[:, 6] > 0.5) & (R[:, 6] < 179.5)
+        torch.testing.assert_close(out[fin, 5], R[fin, 6], rtol=1e-4, atol=3e-2)      # acos near 0 / 180 deg is ill-conditioned
+        ok = R[:, 7] < 170                                                             # asin at 1 is ill-conditioned
+        torch.testing.assert_close(out[ok, 2], R[ok, 7], rtol=1e-4, atol=2e-3)
+        torch.testing.assert_close(out[~ok, 2], R[~ok, 7], rtol=0, atol=0.1)
+        torch.testing.assert_close(out[:, 3], R[:, 8], rtol=1e-5, atol=1e-7)
+        for col, gcol in ((6, 9), (7, 10), (8, 11), (9, 12), (10, 13), (11, 14), (12, 15), (13, 16)):
+            assert torch.equal(out[:, col], R[:, gcol]), f"flag column {col} (set {si})"
+        assert out[:, 14].tolist() == [float(i) for i in range(n)]
+        torch.testing.assert_close(out[:, 15], d, rtol=1e-6, atol=0)
+
+
 @pytest.mark.parametrize("n_pts", [1, 50, 256, 300, 2500])
 def test_pose_metrics_vs_oracle(ops, n_pts):
     from rnnpose_b200 import metrics as M
@@ -241,29 +284,32 @@ def test_pose_metrics_vs_oracle(ops, n_pts):
     xi = torch.randn(B, 6, generator=g) * 0.1
     Tp = O.se3_exp(xi); Tg = O.se3_exp(xi + 0.02 * torch.randn(B, 6, generator=g))
     Tg[0] = Tp[0]                                                      # an exact pose: every metric 0, every flag 1
+    Tp[:, 2, 3] += 0.8; Tg[:, 2, 3] += 0.8                             # in front of the camera (projection)
     pts = torch.randn(n_pts, 3, generator=g) * 0.05
     diam = torch.tensor([0.15, 0.15, 0.01, 0.15, 0.3])
     out = ops.pose_metrics(Tp.cuda(), Tg.cuda(), pts[None].repeat(B, 1, 1).cuda(), diam.cuda()).cpu()
-    add = O.add_metric(Tp[:, :3, :3], Tp[:, :3, 3], Tg[:, :3, :3], Tg[:, :3, 3], pts, False)
-    adds = O.add_metric(Tp[:, :3, :3], Tp[:, :3, 3], Tg[:, :3, :3], Tg[:, :3, 3], pts, True)
-    torch.testing.assert_close(out[:, 0], add, rtol=1e-5, atol=1e-7)
-    torch.testing.assert_close(out[:, 1], adds, rtol=1e-5, atol=1e-7)
-    torch.testing.assert_close(out[:, 2], O.rotation_angle_deg(Tp[:, :3, :3], Tg[:, :3, :3]), rtol=1e-4, atol=2e-3)
-    torch.testing.assert_close(out[:, 3], (Tp[:, :3, 3] - Tg[:, :3, 3]).norm(dim=1), rtol=1e-5, atol=1e-7)
-    assert out[0, :4].abs().max() < 1e-6 and out[0, 4:7].tolist() == [1.0, 1.0, 1.0]
+    Rp, tp, Rg, tg = Tp[:, :3, :3], Tp[:, :3, 3], Tg[:, :3, :3], Tg[:, :3, 3]
+    torch.testing.assert_close(out[:, 0], O.add_metric(Rp, tp, Rg, tg, pts, False), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(out[:, 1], O.add_metric(Rp, tp, Rg, tg, pts, True), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(out[:, 2], O.rotation_angle_deg(Rp, Rg), rtol=1e-4, atol=2e-3)
+    torch.testing.assert_close(out[:, 3], (tp - tg).norm(dim=1), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(out[:, 4], O.projection_2d(Rp, tp, Rg, tg, pts, torch.tensor(ops.LINEMOD_K)), rtol=1e-4, atol=1e-3)
+    assert out[0, :5].abs().max() < 1e-4 and out[0, 6:14].tolist() == [1.0] * 8
     ref = M.pose_metrics_torch(Tp, Tg, pts[None].repeat(B, 1, 1), diam, torch.zeros(B))
-    margin = (ref[:, 0] - 0.1 * diam).abs() > 1e-6                     # flags can only differ on a threshold tie
-    assert torch.equal(out[margin, 4], ref[margin, 4])
-    assert torch.equal(out[:, 5][(ref[:, 1] - 0.1 * diam).abs() > 1e-6], ref[:, 5][(ref[:, 1] - 0.1 * diam).abs() > 1e-6])
-    assert torch.equal(out[:, 6], ref[:, 6])
+    for col, val, frac in ((6, 0, 0.1), (7, 1, 0.1), (8, 0, 0.02), (9, 1, 0.02), (10, 0, 0.05), (11, 1, 0.05)):
+        margin = (ref[:, val] - frac * diam).abs() > 1e-6              # flags can only differ on a threshold tie
+        assert torch.equal(out[margin, col], ref[margin, col])
+    assert torch.equal(out[:, 13], ref[:, 13])
     full = M.pose_metrics(Tp.cuda(), Tg.cuda(), pts[None].repeat(B, 1, 1).cuda(), diam.cuda(), torch.arange(B).cuda()).cpu()
-    assert full[:, 7].tolist() == [0.0, 1.0, 2.0, 3.0, 4.0] and torch.equal(full[:, :7], out[:, :7])
+    assert full[:, 14].tolist() == [0.0, 1.0, 2.0, 3.0, 4.0] and torch.equal(full[:, :14], out[:, :14])
 
 
 def test_pose_metrics_error_codes(ops):
     from rnnpose_b200 import _lib
     L = _lib.lib()
     t = torch.zeros(64, device="cuda")
-    assert L.b200pose_pose_metrics(0, t.data_ptr(), t.data_ptr(), t.data_ptr(), 1, 4, t.data_ptr(), t.data_ptr(), 1024, 0) == -1
-    assert L.b200pose_pose_metrics(t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), 0, 4, t.data_ptr(), t.data_ptr(), 1024, 0) == -2
-    assert L.b200pose_pose_metrics(t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), 1, 4, t.data_ptr(), t.data_ptr(), 0, 0) == -3
+    p = t.data_ptr()
+    assert L.b200pose_pose_metrics(0, p, p, p, p, 1, 4, p, p, 1024, 0) == -1
+    assert L.b200pose_pose_metrics(p, p, p, p, 0, 1, 4, p, p, 1024, 0) == -1      # K is required
+    assert L.b200pose_pose_metrics(p, p, p, p, p, 0, 4, p, p, 1024, 0) == -2
+    assert L.b200pose_pose_metrics(p, p, p, p, p, 1, 4, p, p, 0, 0) == -3

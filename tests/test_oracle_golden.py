@@ -160,3 +160,37 @@ def test_aten_sequence_variant_matches_reference_and_restatement():
     Ti = torch.matmul(a["G"], mb["T_init"])
     assert (Ti - T(g["Ti_pred"])[:1]).abs().max().item() < 2e-5
     assert (a["G"] - b["G"]).abs().max().item() < 2e-5
+
+
+def test_g10_metrics_reference_evaluator():
+    """oracle ADD / ADD-S / 2-D projection / 5cm5deg and the torch formulation of rnnpose_b200.metrics against the
+    reference's LineMODEvaluator executed by tests/golden/make_golden_metrics.py (ADD-S: ground-truth query, nearest
+    predicted point; utils/eval_metric.py:167-171)."""
+    from rnnpose_b200 import metrics as M
+    g = golden("metrics.npz")
+    rows = g["rows"]
+    K = T(g["K"])
+    worst_dir = 0.0
+    for r in rows:
+        si, pi, d = int(r[0]), int(r[1]), float(r[2])
+        pts = T(g[f"pts{si}"]).double()
+        pp = T(g[f"pose_pred_{si}_{pi}"]).double()[None]; pg = T(g[f"pose_gt_{si}_{pi}"]).double()[None]
+        Rp, tp, Rg, tg = pp[:, :, :3], pp[:, :, 3], pg[:, :, :3], pg[:, :, 3]
+        add = O.add_metric(Rp, tp, Rg, tg, pts, False).item()
+        adds = O.add_metric(Rp, tp, Rg, tg, pts, True).item()
+        assert abs(add - r[3]) / d < 1e-6 and abs(adds - r[4]) / d < 1e-6
+        # the opposite direction (mean over predicted points of the distance to the nearest gt point) is a different number
+        pred = torch.einsum("ij,nj->ni", Rp[0], pts) + tp[0]; gt = torch.einsum("ij,nj->ni", Rg[0], pts) + tg[0]
+        worst_dir = max(worst_dir, abs(torch.cdist(pred, gt).min(dim=1).values.mean().item() - r[4]) / d)
+        assert abs(O.projection_2d(Rp, tp, Rg, tg, pts, K).item() - r[5]) < 1e-4 * max(1.0, r[5])
+        trans_cm, ang, flag = O.cm_degree_5(Rp, tp, Rg, tg)
+        if np.isfinite(r[6]) and 0.5 < r[6] < 179.5:      # acos at +-1 is ill-conditioned (a 1-ulp trace decides 180 vs NaN)
+            assert abs(ang.item() - r[6]) < 3e-2
+        assert bool(flag.item()) == bool(r[16])
+        assert abs(O.rotation_angle_deg(Rp, Rg).item() - r[7]) < (2e-3 if r[7] < 170 else 0.1)     # asin at 1: ill-conditioned
+        T4p = torch.eye(4, dtype=torch.float64)[None].clone(); T4p[:, :3] = pp
+        T4g = torch.eye(4, dtype=torch.float64)[None].clone(); T4g[:, :3] = pg
+        m = M.pose_metrics_torch(T4p.float(), T4g.float(), pts.float()[None], torch.tensor([d]), torch.zeros(1), K.float())[0].double()
+        assert abs(m[0] - r[3]) / d < 2e-6 and abs(m[1] - r[4]) / d < 2e-6 and abs(m[4] - r[5]) < 2e-4 * max(1.0, r[5])
+        assert m[6:14].tolist() == [float(v) for v in r[9:17]]
+    assert worst_dir > 1e-3          # the fixture does separate the two ADD-S directions
