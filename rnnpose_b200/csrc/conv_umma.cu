@@ -1433,7 +1433,7 @@ int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const int* n_src, con
     }
     cp.done = done_ws;
     B2P_CUDA(cudaMemsetAsync(done_ws, 0, (size_t)n * cp.m_tiles * sizeof(int), s));
-    const int nclusters = sms / 2;
+    int nclusters = sms / 2;
     const size_t smem = (size_t)CH_RING_A * CH_A_SLOT + (size_t)CH_RING_B * CH_B_SLOT + 1024 + 16 * (CH_RING_A + CH_RING_B) + 64;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nclusters * 2); cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -1443,6 +1443,22 @@ int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const int* n_src, con
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 2;
+    // The units wait for each other, so every cluster of the grid must be resident at once: ask the driver how many CTA
+    // pairs it can co-schedule (an SM without a free partner holds none) and launch no more than that.
+    {
+        static int max_clusters[64];
+        int dev = 0;
+        B2P_CUDA(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && max_clusters[dev] == 0) {
+            int n = 0;
+            B2P_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_chain_kernel, &cfg));
+            max_clusters[dev] = n > 0 ? n : -1;
+        }
+        const int cap = (dev >= 0 && dev < 64) ? max_clusters[dev] : -1;
+        if (cap < 1) return -1;
+        if (nclusters > cap) nclusters = cap;
+        cfg.gridDim = dim3(nclusters * 2);
+    }
     B2P_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel, cp));
     B2P_LAUNCH_CHECK();
     return 0;
