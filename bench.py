@@ -343,8 +343,9 @@ def main():
                     "note": "context map is read in place from pinned host memory (only the rows the 1/8 resample touches); the first descriptor map likewise only at the pixels with depth > 0"},
             "gpu_launches": args.steps * ops.launch_count(N_ITERS, N_LM),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "parity": {"objects": int(gm.shape[0]), "mean_add_over_diameter": float((gm[:, 0] / diam_d.repeat(world)[: gm.shape[0]]).mean()),
-                       "add_0.1d_recall": float(gm[:, 4].mean()), "adds_0.1d_recall": float(gm[:, 5].mean())},
+            "accuracy_vs_gt": {"objects": int(gm.shape[0]), "mean_add_over_diameter": float((gm[:, 0] / gm[:, 15]).mean()),
+                               "add_0.1d_recall": float(gm[:, 6].mean()), "adds_0.1d_recall": float(gm[:, 7].mean()),
+                               "proj2d_5px_recall": float(gm[:, 12].mean()), "cm5deg5_recall": float(gm[:, 13].mean())},
         }
         print(json.dumps(line), flush=True)
     if torch.distributed.is_available() and torch.distributed.is_initialized():
