@@ -286,7 +286,7 @@ def main():
         y0 = min(int(y * sy), H - 1); rows.update((y0, min(y0 + 1, H - 1)))
     ctx_bytes = B * 256 * len(rows) * W * 4
     # the first descriptor map is fetched from the pinned buffer only where the rendered depth is positive
-    sparse_g1 = os.environ.get("B200POSE_SPARSE_G1", "1") != "0"
+    sparse_g1 = ops.get_option("sparse_g1") != 0
     g1_bytes = (int((host["depth"] > 0).sum()) * host["geofea1"].shape[1] * 4) if sparse_g1 else host["geofea1"].numel() * 4
     h2d = sum(host[k].numel() * 4 for k in ("fmap1", "fmap2", "geofea2", "depth", "K", "G0")) + g1_bytes + ctx_bytes
     d2h = Gh.numel() * 4

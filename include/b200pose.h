@@ -13,7 +13,10 @@
  *   - work is enqueued on the caller's stream (cudaStream_t passed as void*), no device-wide sync,
  *     graph-capturable (except where noted); scratch memory comes from the caller
  *     (b200pose_workspace_bytes);
- *   - the library keeps no global state.
+ *   - process-wide state is limited to (1) the kernel-selection OPTIONS below (read once from B200POSE_* environment
+ *     variables at the first call, then changed only by b200pose_set_option), (2) a bounded cache of encoded TMA
+ *     descriptors keyed by (device address, extents, box) -- a descriptor depends on nothing else, so a hit is always
+ *     valid -- and (3) per-device attributes queried once (SM count, shared-memory opt-in).  No data, no handles.
  *
  * Internal activation layout ("PXC"): pixel-major, channels contiguous: [B*h*w][C] float32, where
  * h = H/8, w = W/8 is the 1/8-resolution grid.  Boundary tensors keep the reference's NCHW layout.
@@ -52,6 +55,21 @@ extern "C" {
 
 int b200pose_version(void);
 const char* b200pose_error_string(int code);
+
+/* ---- options ------------------------------------------------------------------------------------
+ * Integer options that select between kernel variants (all variants meet the parity bar; they exist for A/B timing and
+ * for the tests, which run every variant).  Names (initial value <- environment variable, read once):
+ *   conv_mode (B200POSE_CONV_MODE, 3)  tensor-core convolution: bit0 CTA pairs, bit1 vertical-tap reuse, bit2 force the
+ *                                      second-generation kernel, bit4 chained single-launch update block; 0 = first generation
+ *   fg_list (B200POSE_FG_LIST, 1)      LM steps over the per-call foreground list
+ *   fg_pipeline (B200POSE_FG_PIPELINE, 1)  compact channels-last upsample+weight kernel + cluster LM kernel
+ *   fg_upsample, fg_blocks, sparse_g1, tail_min_n, lookup_mode, lm_mode, pool_mode, conv_debug, lm_debug: see csrc/options.cu
+ * Returns 0, B200POSE_E_NULL or B200POSE_E_ARG (unknown name).  Not synchronised against launches in flight on other
+ * threads.                                                                                         */
+int b200pose_set_option(const char* name, int value);
+int b200pose_get_option(const char* name, int* value);
+int b200pose_option_count(void);
+const char* b200pose_option_name(int index);
 
 /* ---- weights ----------------------------------------------------------------------------------
  * Replaces: nn.Conv2d parameter storage of BasicUpdateBlock (reference thirdparty/raft/update.py:

@@ -16,6 +16,10 @@ _vp, _i, _f, _d, _sz = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t
 SIGNATURES = {
     "b200pose_version": (_i, []),
     "b200pose_error_string": (C.c_char_p, [_i]),
+    "b200pose_set_option": (_i, [C.c_char_p, _i]),
+    "b200pose_get_option": (_i, [C.c_char_p, C.POINTER(_i)]),
+    "b200pose_option_count": (_i, []),
+    "b200pose_option_name": (C.c_char_p, [_i]),
     "b200pose_packed_weights_bytes": (_sz, []),
     "b200pose_pack_weights": (_i, [C.POINTER(_vp), _vp, _vp]),
     "b200pose_pyramid_floats": (_sz, [_i, _i, _i]),

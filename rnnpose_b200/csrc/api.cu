@@ -57,15 +57,8 @@ size_t update_ws_layout(int B, int h, int w, void* ws, size_t cap, UpdateWs* out
     return align_up(c.off, 1024);
 }
 
-inline bool fg_list_enabled() {
-    const char* e = getenv("B200POSE_FG_LIST");
-    return !(e && *e == '0');
-}
-
-inline bool fg_upsample_enabled() {           // B200POSE_FG_UPSAMPLE=1: persistent list-driven upsample + weight kernel (opt-in)
-    const char* e = getenv("B200POSE_FG_UPSAMPLE");
-    return e && *e == '1';
-}
+inline bool fg_list_enabled() { return b2p_options().fg_list != 0; }
+inline bool fg_upsample_enabled() { return b2p_options().fg_upsample == 1; }   // round-1 list-driven upsample + weight kernel (opt-in)
 
 inline bool shape_ok(int B, int H, int W) {
     return B >= 1 && H >= 128 && W >= 128 && (H % 8) == 0 && (W % 8) == 0;   // (H/8)>>3 >= 2: the reference's
@@ -677,9 +670,8 @@ int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_ho
     // pinned buffer only those pixels are fetched (B200POSE_SPARSE_G1=0: plain copy).
     const float* g1_mapped = nullptr;
     {
-        const char* e = getenv("B200POSE_SPARSE_G1");
         cudaPointerAttributes attr;
-        if (!(e && *e == '0') && cudaPointerGetAttributes(&attr, geofea1_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+        if (b2p_options().sparse_g1 != 0 && cudaPointerGetAttributes(&attr, geofea1_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
             attr.devicePointer != nullptr)
             g1_mapped = reinterpret_cast<const float*>(attr.devicePointer);
         else

@@ -38,6 +38,14 @@ inline cudaError_t b2p_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
         if (e__ != cudaSuccess) return (int)e__;             \
     } while (0)
 
+// Process-wide kernel-selection options (options.cu): read once from B200POSE_* environment variables at the first call
+// into the library, changed afterwards only through b200pose_set_option.
+struct B2POptions {
+    int conv_mode, fg_list, fg_pipeline, fg_upsample, sparse_g1, fg_blocks, tail_min_n, conv_debug, lookup_mode, lm_mode,
+        pool_mode, lm_debug;
+};
+B2POptions& b2p_options();
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

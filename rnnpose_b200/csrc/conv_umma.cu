@@ -1174,22 +1174,10 @@ int device_sms() {
     return sms_of[dev];
 }
 
-// smallest channel count of a split unit (0 disables splitting); B200POSE_TAIL_MIN_N overrides it for experiments
-int g_tail_min_n = []() { const char* e = getenv("B200POSE_TAIL_MIN_N"); return e ? atoi(e) : 32; }();
-
-// Kernel selection, B200POSE_CONV_MODE (read at every launch so that tests can switch): bit 0 = CTA pairs
-// (tcgen05.mma.cta_group::2), bit 1 = vertical-tap reuse of the activation box; 0 = first-generation kernel; unset = default.
-constexpr int kDefaultConvMode = 3;
-int conv_mode() {
-    const char* e = getenv("B200POSE_CONV_MODE");
-    return e && *e ? atoi(e) : kDefaultConvMode;
-}
-
-// integer environment knob, read per launch (tests switch kernels between calls)
-int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e && *e ? atoi(e) : dflt;
-}
+// Kernel selection: option "conv_mode" (options.cu; initial value from B200POSE_CONV_MODE, read once): bit 0 = CTA pairs
+// (tcgen05.mma.cta_group::2), bit 1 = vertical-tap reuse of the activation box; 0 = first-generation kernel.
+// "tail_min_n": smallest channel count of a split unit (0 disables splitting).
+int conv_mode() { return b2p_options().conv_mode; }
 
 template <typename... KArgs>
 cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), int grid, int cluster, size_t smem, cudaStream_t s, const UmmaConvParams& p) {
@@ -1231,15 +1219,16 @@ int launch_conv_umma2(const UmmaConvArgs& a, UmmaConvParams& p, int ncta, bool r
     if ((rc = make_wgt_map(&p.b_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, a.n_tile / ncta))) return rc;
     const size_t smem = (size_t)p.ring_a * (2 * p.a_rows * 1024) + (size_t)p.ring_b * (2 * (a.n_tile / ncta) * 128) + 1024 +
                         16 * (p.ring_a + p.ring_b) + 64;
-    p.debug = env_int("B200POSE_V2_DEBUG", 0);
+    p.debug = b2p_options().conv_debug;
     p.m_groups = ceil_div(p.m_tiles, ncta);
     p.total_tiles = p.m_groups * (a.cout_pad / a.n_tile);
     const int slots = sms / ncta;                                    // clusters resident at once
     int nclusters = p.total_tiles < slots ? p.total_tiles : slots;
     p.full_units = p.total_tiles; p.total_units = p.total_tiles; p.split = 1; p.n_sub = a.n_tile;
     const int tail = p.total_tiles < slots ? p.total_tiles : p.total_tiles % slots;
-    if (tail && g_tail_min_n > 0) {
-        for (int sp = a.n_tile / g_tail_min_n; sp >= 2; --sp) {
+    const int tail_min_n = b2p_options().tail_min_n;
+    if (tail && tail_min_n > 0) {
+        for (int sp = a.n_tile / tail_min_n; sp >= 2; --sp) {
             if (a.n_tile % sp || (a.n_tile / sp) % 32 || tail * sp > slots) continue;
             p.split = sp; p.n_sub = a.n_tile / sp;
             p.full_units = p.total_tiles - tail; p.total_units = p.full_units + tail * sp;
@@ -1334,7 +1323,7 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     p.m_tiles = a.B * p.tiles_x * p.tiles_y;
     p.total_tiles = p.m_tiles * (a.cout_pad / a.n_tile);
     p.b_batched = a.b_batched;
-    p.debug = a.b_batched ? 0 : env_int("B200POSE_V2_DEBUG", 0);
+    p.debug = a.b_batched ? 0 : b2p_options().conv_debug;
     p.dbg_layer = a.layer_id >= 0 && a.layer_id < 11 ? a.layer_id + 1 : 0;
     // second-generation kernel (see conv_mode): not for the batched-weight volume GEMM (a pair of M tiles may straddle two
     // samples); CTA pairs only when the problem fills the machine (they halve the number of schedulable units)
@@ -1358,8 +1347,9 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     // A problem with fewer tiles than SMs (small batches) is one partial round: all of its tiles are split.
     p.full_units = p.total_tiles; p.total_units = p.total_tiles; p.split = 1; p.n_sub = a.n_tile;
     const int tail = p.total_tiles < sms ? p.total_tiles : p.total_tiles % sms;
-    if (tail && g_tail_min_n > 0) {
-        for (int sp = a.n_tile / g_tail_min_n; sp >= 2; --sp) {
+    const int tail_min_n = b2p_options().tail_min_n;
+    if (tail && tail_min_n > 0) {
+        for (int sp = a.n_tile / tail_min_n; sp >= 2; --sp) {
             if (a.n_tile % sp || (a.n_tile / sp) % 32 || tail * sp > sms) continue;
             p.split = sp; p.n_sub = a.n_tile / sp;
             p.full_units = p.total_tiles - tail; p.total_units = p.full_units + tail * sp;

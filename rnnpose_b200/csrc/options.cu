@@ -1,0 +1,72 @@
+// Process-wide kernel-selection options of libb200pose.so.
+// They used to be getenv() calls on the launch path (several per launch; an inherited variable could silently change which
+// kernels -- and therefore which rounding -- a run used).  Now: read ONCE, at the first call into the library, from the
+// B200POSE_* environment variables below; afterwards only b200pose_set_option changes them.  Setting an option while
+// another thread is inside a launch is not synchronised (the caller's problem, like changing a stream's priority).
+#include "common.cuh"
+
+#include <mutex>
+#include <stdlib.h>
+
+namespace {
+
+struct OptDesc { const char* name; const char* env; int B2POptions::*field; int dflt; };
+
+const OptDesc kOpts[] = {
+    // tensor-core convolution kernel: bit 0 CTA pairs (cta_group::2), bit 1 vertical-tap reuse, bit 2 force the
+    // second-generation kernel, bit 4 the chained single-launch update block; 0 = first-generation kernel
+    {"conv_mode", "B200POSE_CONV_MODE", &B2POptions::conv_mode, 3},
+    {"fg_list", "B200POSE_FG_LIST", &B2POptions::fg_list, 1},               // LM over the per-call foreground list
+    {"fg_pipeline", "B200POSE_FG_PIPELINE", &B2POptions::fg_pipeline, 1},   // compact channels-last upsample+weight + cluster LM
+    {"fg_upsample", "B200POSE_FG_UPSAMPLE", &B2POptions::fg_upsample, 0},   // round-1 list-driven upsample kernel (NCHW planes)
+    {"sparse_g1", "B200POSE_SPARSE_G1", &B2POptions::sparse_g1, 1},         // host entry: fetch geofea1 only where depth > 0
+    {"fg_blocks", "B200POSE_FG_BLOCKS", &B2POptions::fg_blocks, 8},
+    {"tail_min_n", "B200POSE_TAIL_MIN_N", &B2POptions::tail_min_n, 32},     // smallest channel count of a split tail unit
+    {"conv_debug", "B200POSE_V2_DEBUG", &B2POptions::conv_debug, 0},        // timing experiments (results garbage unless 0 / 16)
+    {"lookup_mode", "B200POSE_LOOKUP_MODE", &B2POptions::lookup_mode, 1},   // 1 = shared-memory window lookup, 0 = round-1 kernel
+    {"lm_mode", "B200POSE_LM_MODE", &B2POptions::lm_mode, 1},               // 1 = cluster LM kernel, 0 = round-1 spin-barrier kernel
+    {"pool_mode", "B200POSE_POOL_MODE", &B2POptions::pool_mode, 1},         // 1 = three pyramid levels in one pass
+    {"lm_debug", "B200POSE_LM_DEBUG", &B2POptions::lm_debug, 0},            // 1 = drop the fp64 contraction (timing A/B only)
+};
+constexpr int kNumOpts = (int)(sizeof(kOpts) / sizeof(kOpts[0]));
+
+B2POptions g_opts;
+std::once_flag g_once;
+
+void init_opts() {
+    for (int i = 0; i < kNumOpts; ++i) {
+        const char* e = getenv(kOpts[i].env);
+        g_opts.*(kOpts[i].field) = (e && *e) ? atoi(e) : kOpts[i].dflt;
+    }
+}
+
+}  // namespace
+
+B2POptions& b2p_options() {
+    std::call_once(g_once, init_opts);
+    return g_opts;
+}
+
+extern "C" {
+
+int b200pose_set_option(const char* name, int value) {
+    if (!name) return B200POSE_E_NULL;
+    B2POptions& o = b2p_options();
+    for (int i = 0; i < kNumOpts; ++i)
+        if (!strcmp(name, kOpts[i].name)) { o.*(kOpts[i].field) = value; return 0; }
+    return B200POSE_E_ARG;
+}
+
+int b200pose_get_option(const char* name, int* value) {
+    if (!name || !value) return B200POSE_E_NULL;
+    B2POptions& o = b2p_options();
+    for (int i = 0; i < kNumOpts; ++i)
+        if (!strcmp(name, kOpts[i].name)) { *value = o.*(kOpts[i].field); return 0; }
+    return B200POSE_E_ARG;
+}
+
+int b200pose_option_count(void) { return kNumOpts; }
+
+const char* b200pose_option_name(int index) { return index >= 0 && index < kNumOpts ? kOpts[index].name : nullptr; }
+
+}  // extern "C"

@@ -309,8 +309,7 @@ int b2p_upsample_weight_fg(const float* flow, const float* mask, const float* g1
     B2P_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     // all blocks resident; B200POSE_FG_BLOCKS picks the register / occupancy point (8 blocks of 128 threads per SM at 64
     // registers, or 6 at 80)
-    const char* e = getenv("B200POSE_FG_BLOCKS");
-    const int bps = (e && atoi(e) == 6) ? 6 : 8;
+    const int bps = b2p_options().fg_blocks == 6 ? 6 : 8;
     int per_sample = (sms * bps) / B;
     const int useful = ceil_div(H * W, 128);
     if (per_sample > useful) per_sample = useful;

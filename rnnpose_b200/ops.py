@@ -50,6 +50,40 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return t[off:off + max(int(nbytes), 256)]
 
 
+def set_option(name: str, value: int) -> None:
+    """Kernel-selection option of the library (include/b200pose.h "options")."""
+    _lib.check(_lib.lib().b200pose_set_option(name.encode(), int(value)), f"b200pose_set_option({name})")
+
+
+def get_option(name: str) -> int:
+    v = C.c_int()
+    _lib.check(_lib.lib().b200pose_get_option(name.encode(), C.byref(v)), f"b200pose_get_option({name})")
+    return v.value
+
+
+def option_names() -> List[str]:
+    L = _lib.lib()
+    return [L.b200pose_option_name(i).decode() for i in range(L.b200pose_option_count())]
+
+
+class options:
+    """Context manager: ``with ops.options(conv_mode=1): ...`` sets options and restores the previous values."""
+
+    def __init__(self, **kw):
+        self.kw, self.old = kw, {}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.old[k] = get_option(k)
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, v)
+        return False
+
+
 def pack_weights(state: Dict[str, torch.Tensor], device="cuda") -> torch.Tensor:
     """state: ``cf_net.update_block`` state dict (keys 'encoder.convc1.weight', ...).  Returns the packed
     device blob consumed by update_block / refine_iters."""

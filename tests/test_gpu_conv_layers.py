@@ -110,7 +110,7 @@ _REF_CACHE = {}
 @pytest.mark.parametrize("mode", [1, 2, 3], ids=["pair", "vreuse", "pair+vreuse"])
 @pytest.mark.parametrize("layer", sorted(LAYERS))
 @pytest.mark.parametrize("shape", [(2, 9, 12), (32, 30, 40), (51, 16, 20)], ids=["2x9x12", "32x30x40", "51x16x20"])
-def test_conv_layer_second_generation(ops, packed, layer, shape, mode, monkeypatch):
+def test_conv_layer_second_generation(ops, packed, layer, shape, mode):
     wts = load_update_weights()
     keys, pad = LAYERS[layer]
     W = torch.cat([wts[k + ".weight"] for k in keys], 0)
@@ -124,9 +124,9 @@ def test_conv_layer_second_generation(ops, packed, layer, shape, mode, monkeypat
     x, ref = _REF_CACHE[(layer, shape)]
     in0 = to_pxc(x[:, :cin0]).to(dev())
     in1 = to_pxc(x[:, cin0:]).to(dev()) if cin1 else None
-    monkeypatch.setenv("B200POSE_CONV_MODE", str(mode))
-    out = ops.conv_layer(packed, layer, in0, in1, B, h, w, flags=1)
-    torch.cuda.synchronize()
+    with ops.options(conv_mode=mode):
+        out = ops.conv_layer(packed, layer, in0, in1, B, h, w, flags=1)
+        torch.cuda.synchronize()
     got = from_pxc(out[:, :cout].contiguous(), B, h, w).cpu()
     scale = ref.abs().max().item()
     err = (got - ref).abs().max().item()

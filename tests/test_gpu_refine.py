@@ -79,9 +79,9 @@ def test_refine_matches_reference_golden(ops, packed, name, flags):
 
 
 @pytest.mark.parametrize("conv_mode", [1, 2, 3], ids=["pair", "vreuse", "pair+vreuse"])
-def test_refine_golden_240x320_second_generation_kernels(ops, packed, conv_mode, monkeypatch):
+def test_refine_golden_240x320_second_generation_kernels(ops, packed, conv_mode, libopt):
     """The executed reference's 240x320 4x3 result through the second-generation convolution kernel variants."""
-    monkeypatch.setenv("B200POSE_CONV_MODE", str(conv_mode))
+    libopt("conv_mode", conv_mode)
     g = golden("refine_240x320_4x3.npz")
     H, W, n_iters, n_lm, seed, occl = [int(v) for v in g["meta"]]
     mb = S.make_batch([int(i) for i in g["idxs"]], H, W, seed, bool(occl), with_images=False)
@@ -105,12 +105,12 @@ def test_refine_batched_vs_oracle(ops, packed):
 
 
 @pytest.mark.parametrize("conv_mode", [None, 0, 1, 2, 3], ids=["default", "gen1", "pair", "vreuse", "pair+vreuse"])
-def test_refine_full_size_batch_properties(ops, packed, conv_mode, monkeypatch):
+def test_refine_full_size_batch_properties(ops, packed, conv_mode, libopt):
     """BASELINE configs[1] shape (B=32, 240x320, 4x3): per-sample results do not depend on batch position or
     batch size (bit-exact), outputs are finite rigid transforms, and a subset agrees with the oracle.  Run for every
     tensor-core convolution kernel variant (B200POSE_CONV_MODE, conv_umma.cu)."""
     if conv_mode is not None:
-        monkeypatch.setenv("B200POSE_CONV_MODE", str(conv_mode))
+        libopt("conv_mode", conv_mode)
     H, W, B = 240, 320, 32
     uniq = S.make_batch([0, 1, 2, 3], H, W, with_images=False)
     rep = {k: v.repeat(8, *([1] * (v.dim() - 1))) for k, v in uniq.items() if k != "diameter"}
@@ -202,7 +202,7 @@ def test_refine_zero_iterations_and_single_object(ops, packed):
     assert torch.equal(res["G"].cpu(), G0) and torch.isfinite(res["flow_last"]).all()
 
 
-def test_refine_foreground_list_matches_dense_kernels(ops, packed, monkeypatch):
+def test_refine_foreground_list_matches_dense_kernels(ops, packed, libopt):
     """The per-call foreground list (depth > 0 compacted once; upsample + weight and LM run over the list) against the dense
     kernels: identical weights, poses equal up to the fp64 summation order.  Includes an object-free crop (empty list)."""
     H, W = 128, 160
@@ -210,15 +210,15 @@ def test_refine_foreground_list_matches_dense_kernels(ops, packed, monkeypatch):
     mb["depth"][1] = 0.0                                    # sample 1: no foreground at all
     f1 = S.hash_features((3, 256, H // 8, W // 8), 96); f2 = S.hash_features((3, 256, H // 8, W // 8), 97)
     G0 = torch.eye(4)[None].repeat(3, 1, 1)
-    monkeypatch.setenv("B200POSE_FG_LIST", "0")
+    libopt("fg_list", 0)
     dense = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, want_weight=True)
-    monkeypatch.setenv("B200POSE_FG_LIST", "1")
+    libopt("fg_list", 1)
     fg = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, want_weight=True)
     assert torch.equal(fg["G"][1].cpu(), G0[1]) and torch.equal(dense["G"][1].cpu(), G0[1])
     assert (fg["G"].cpu() - dense["G"].cpu()).abs().max().item() < 1e-6
     torch.testing.assert_close(fg["weight"].cpu(), dense["weight"].cpu(), rtol=0, atol=2e-6)
     # opt-in: the persistent list-driven upsample + weight kernel (same per-pixel function, background set once per call)
-    monkeypatch.setenv("B200POSE_FG_UPSAMPLE", "1")
+    libopt("fg_upsample", 1)
     fgu = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, want_weight=True)
     assert (fgu["G"].cpu() - dense["G"].cpu()).abs().max().item() < 1e-6
     torch.testing.assert_close(fgu["weight"].cpu(), dense["weight"].cpu(), rtol=0, atol=2e-6)
@@ -230,7 +230,7 @@ def test_refine_foreground_list_matches_dense_kernels(ops, packed, monkeypatch):
 @pytest.mark.skipif(os.environ.get("B200POSE_TEST_EXPERIMENTAL") != "1",
                     reason="conv_chain_kernel (B200POSE_CONV_MODE bit 4) has not been run on hardware yet; opt in with "
                            "B200POSE_TEST_EXPERIMENTAL=1")
-def test_refine_chained_convolutions_experimental(ops, packed, monkeypatch):
+def test_refine_chained_convolutions_experimental(ops, packed, libopt):
     """The eleven convolutions of a pass in one persistent launch with tile-level dependencies (mode 19) against the
     layer-by-layer default at the bench shape (the chain needs a machine-filling batch)."""
     H, W, B = 240, 320, 32
@@ -239,7 +239,7 @@ def test_refine_chained_convolutions_experimental(ops, packed, monkeypatch):
     f1 = S.hash_features((4, 256, H // 8, W // 8), 71).repeat(8, 1, 1, 1); f2 = S.hash_features((4, 256, H // 8, W // 8), 72).repeat(8, 1, 1, 1)
     G0 = torch.eye(4)[None].repeat(B, 1, 1)
     ref = run_gpu(ops, packed, f1, f2, rep, G0, 4, 3)["G"].cpu()
-    monkeypatch.setenv("B200POSE_CONV_MODE", "19")
+    libopt("conv_mode", 19)
     got = run_gpu(ops, packed, f1, f2, rep, G0, 4, 3)["G"].cpu()
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max().item() < 1e-6

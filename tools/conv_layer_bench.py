@@ -34,7 +34,7 @@ for layer in [int(x) for x in a.layers.split(",")]:
     ws = ops._ws(nb, dev)
     line = f"{names.get(layer, layer):6s}"
     for m in modes:
-        os.environ["B200POSE_CONV_MODE"] = str(m)
+        ops.set_option("conv_mode", m)
         for _ in range(3):
             ops.conv_layer(packed, layer, in0, in1, B, h, w, flags=1, workspace=ws, out=out)
         torch.cuda.synchronize()

@@ -28,7 +28,7 @@ ops.refine_iters(packed, f1.to(dev), f2.to(dev), ctx.to(dev), g1.to(dev), g2.to(
 torch.cuda.synchronize()
 scratch = None
 for mode in ("0", "1"):
-    os.environ["B200POSE_SPARSE_G1"] = mode
+    ops.set_option("sparse_g1", int(mode))
     res = []
     for i in range(6):
         Gh.copy_(G0)
