@@ -52,6 +52,9 @@ extern "C" {
 #define B200POSE_FLAG_EXACT_FP32    0   /* CUDA-core FFMA convolutions, fp32 throughout (LM step fp64) */
 #define B200POSE_FLAG_TENSOR_CORES  1   /* tcgen05 convolutions, fp16 hi/lo split operands (x ~= hi+lo, 3 MMAs,
                                            fp32 TMEM accumulate): fp32-level accuracy, see DESIGN.md section 5 */
+#define B200POSE_FLAG_GEO2_CHANNELS_LAST 2 /* b200pose_refine_iters only: geofea2 is [B,H*W,32] (pixel-major, the layout
+                                           b200pose_zoom_crop writes) instead of NCHW; needs C_geo == 32 and the
+                                           foreground pipeline (options fg_list, fg_pipeline), else B200POSE_E_ARG */
 
 int b200pose_version(void);
 const char* b200pose_error_string(int code);
@@ -63,7 +66,7 @@ const char* b200pose_error_string(int code);
  *                                      second-generation kernel, bit4 chained single-launch update block; 0 = first generation
  *   fg_list (B200POSE_FG_LIST, 1)      LM steps over the per-call foreground list
  *   fg_pipeline (B200POSE_FG_PIPELINE, 1)  compact channels-last upsample+weight kernel + cluster LM kernel
- *   fg_upsample, fg_blocks, sparse_g1, tail_min_n, lookup_mode, lm_mode, pool_mode, conv_debug, lm_debug: see csrc/options.cu
+ *   fg_upsample, fg_blocks, sparse_g1, tail_min_n, lookup_mode, pool_mode, conv_debug, lm_debug: see csrc/options.cu
  * Returns 0, B200POSE_E_NULL or B200POSE_E_ARG (unknown name).  Not synchronised against launches in flight on other
  * threads.                                                                                         */
 int b200pose_set_option(const char* name, int value);
@@ -169,6 +172,15 @@ int b200pose_lm_solve(const float* depth, const float* target, const float* weig
                       float* G, int B, int H, int W, float depth_offset, int n_steps, double ep_lmbda, double lm_lmbda,
                       double* H_out, double* b_out, float* delta_out,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a11, a12 in isolation (the LM kernels above run them inline; these entries let a caller -- and the tests -- reach
+ * the two small pieces directly) -------------------------------------------------------------------
+ * b200pose_cholesky_solve: geometry/cholesky.py:32-50 `solve` for 6x6 systems: x = H^-1 b by Cholesky in fp64, NaN -> 0,
+ *   clamp to [-1, 1], cast to fp32.  H [B,6,6] fp64 symmetric (no damping is added), b [B,6] fp64, x [B,6] fp32.
+ * b200pose_se3_retract: SE3.increment (geometry/transformation.py:110-115): G <- exp(delta) G with the fp32 exponential of
+ *   geometry/se3.py:228-306 (Taylor branch below theta = 1e-4); delta [B,6] = (upsilon, omega), G [B,4,4] in place.   */
+int b200pose_cholesky_solve(const double* H, const double* b, float* x, int B, void* stream);
+int b200pose_se3_retract(const float* delta, float* G, int B, void* stream);
 
 /* ---- f3: per-object pose metrics ----------------------------------------------------------------
  * Replaces the evaluator's per-object arithmetic (utils/eval_metric.py:306-339 evaluate_rnnpose): add_metric /

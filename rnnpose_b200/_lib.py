@@ -39,6 +39,8 @@ SIGNATURES = {
     "b200pose_pose_metrics": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "b200pose_lm_workspace_bytes": (_sz, [_i, _i, _i]),
     "b200pose_lm_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _d, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200pose_cholesky_solve": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "b200pose_se3_retract": (_i, [_vp, _vp, _i, _vp]),
     "b200pose_refine_workspace_bytes": (_sz, [_i, _i, _i]),
     "b200pose_refine_iters": (_i, [_vp] * 9 + [_f, _i, _i, _i, _i, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200pose_refine_host_scratch_bytes": (_sz, [_i, _i, _i, _i]),

@@ -240,6 +240,10 @@ int run_gru_precompute(const float* wts, int B, int h, int w, const UpdateWs& u,
 // levels 1..3 of the pyramid from level 0 (2x2 floor average pooling, corr.py:32-34)
 int pool_pyramid(float* pyramid, int B, int h, int w, cudaStream_t s) {
     const int P = h * w;
+    {
+        const int rc3 = b2p_corr_pool3(pyramid, B, h, w, s);       // one pass over level 0 when an image fits shared memory
+        if (rc3 != -1) return rc3;
+    }
     float* src = pyramid;
     int hl = h, wl = w, rc;
     for (int l = 1; l < B200POSE_CORR_LEVELS; ++l) {
@@ -296,6 +300,7 @@ struct RefineWs {
     float *pyr, *net, *xbuf, *corr, *coords1, *flow, *mask, *target, *weight;
     void* lm;
     void* fg;                     // foreground list of the call (b2p_fg_build)
+    void* fgp;                    // foreground pipeline: channels-last descriptors + per-pixel records (fg_pipeline.cu)
     VolumeWs vol;
     UpdateWs u;
 };
@@ -316,6 +321,7 @@ size_t refine_ws_layout(int B, int H, int W, void* ws, size_t cap, RefineWs* out
     r.weight = c.take<float>(N);
     r.lm = c.take<char>(b2p_lm_ws_bytes(B, H, W));
     r.fg = c.take<char>(b2p_fg_ws_bytes(B, H, W));
+    r.fgp = c.take<char>(b2p_fgpipe_ws_bytes(B, H, W));
     c.off = align_up(c.off, 1024);
     c.off += volume_ws_layout(B, h, w, ws ? c.base + c.off : nullptr, 0, &r.vol);
     const size_t used = update_ws_layout(B, h, w, ws ? c.base + c.off : nullptr, cap > c.off ? cap - c.off : 0, &r.u);
@@ -524,15 +530,28 @@ int b200pose_lm_solve(const float* depth, const float* target, const float* weig
     return 0;
 }
 
+int b200pose_cholesky_solve(const double* H, const double* b, float* x, int B, void* stream) {
+    if (!H || !b || !x) return B200POSE_E_NULL;
+    if (B < 1) return B200POSE_E_SHAPE;
+    return b2p_chol_solve(H, b, x, B, (cudaStream_t)stream);
+}
+
+int b200pose_se3_retract(const float* delta, float* G, int B, void* stream) {
+    if (!delta || !G) return B200POSE_E_NULL;
+    if (B < 1) return B200POSE_E_SHAPE;
+    return b2p_se3_retract(delta, G, B, (cudaStream_t)stream);
+}
+
 size_t b200pose_refine_workspace_bytes(int B, int H, int W) { return refine_ws_layout(B, H, W, nullptr, 0, nullptr); }
 
 int b200pose_refine_launch_count(int n_iters, int n_lm) {
-    // per render iteration: volume + 3 pools + context;  per recurrent iteration: flow_init, lookup,
-    // update block, upsample+weight, 1 launch per LM step (+1 counter reset per call)
-    // (tensor-core path: counter reset, 2 feature-map transposes, volume GEMM, 3 pools, context, hidden state to the tiled
-    //  layout = 9 per call, + 4 GRU partial-sum GEMMs when there is more than one recurrent iteration)
-    // + 3 launches that build the foreground list of the call
-    return 9 + (n_iters > 0 ? 3 : 0) + (n_iters > 1 ? 4 : 0) + n_iters * (2 + UPDATE_LAUNCHES + 1 + (n_lm > 1 ? 1 : n_lm));
+    // Kernels b200pose_refine_iters enqueues with the default options (tensor-core path, foreground pipeline, C_geo = 32, a
+    // level-0 correlation image that fits the one-pass pooling):
+    //   per call: LM counter reset, 2 feature-map transposes, volume GEMM, pooling, context init, hidden state to the tiled
+    //   layout = 7; with n_iters > 0: 3 for the foreground list + 2 for the channels-last descriptors; with n_iters > 1: the
+    //   4 GRU partial-sum GEMMs;  per recurrent iteration: flow_init, lookup, the update block (im2col, 11 convolutions,
+    //   flow-head partial + gather), upsample + weight, and one launch for all LM steps
+    return 7 + (n_iters > 0 ? 5 : 0) + (n_iters > 1 ? 4 : 0) + n_iters * (2 + UPDATE_LAUNCHES + 1 + (n_lm > 0 ? 1 : 0));
 }
 
 int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const float* fmap2, const float* context,
@@ -565,10 +584,15 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
     if (tc && (rc = b2p_pxc_to_tiled(r.net, u.rhbuf, B, h, w, 128, s))) return rc;     // hidden state of the tensor-core epilogues
     if (tc && n_iters > 1 && (rc = run_gru_precompute(wts, B, h, w, u, s))) return rc;
     // The rendered depth is fixed over the recurrent iterations: compact its foreground once and run the LM steps and the
-    // upsample + weight kernel over the list (B200POSE_FG_LIST=0: dense kernels).
+    // upsample + weight kernel over the list (option fg_list = 0: dense kernels).
     const bool use_fg = n_iters > 0 && fg_list_enabled();
-    const bool fg_up = use_fg && fg_upsample_enabled();
+    const bool g2_cl = (flags & B200POSE_FLAG_GEO2_CHANNELS_LAST) != 0;
+    // foreground pipeline (fg_pipeline.cu + lm_cluster_kernel): channels-last descriptors, one record per listed pixel
+    const bool use_pipe = use_fg && C_geo == 32 && b2p_options().fg_pipeline != 0;
+    if (g2_cl && !use_pipe) return B200POSE_E_ARG;          // only the pipeline reads channels-last descriptors
+    const bool fg_up = use_fg && !use_pipe && fg_upsample_enabled();
     if (use_fg && (rc = b2p_fg_build(depth, B, H, W, r.fg, fg_up ? r.target : nullptr, fg_up ? r.weight : nullptr, s))) return rc;
+    if (use_pipe && (rc = b2p_fgpipe_prepare(geofea1, geofea2, g2_cl ? 1 : 0, B, H, W, r.fg, r.fgp, s))) return rc;
     const int* fg_idx = use_fg ? b2p_fg_idx(r.fg) : nullptr;
     const int* fg_count = use_fg ? b2p_fg_count(r.fg, B, H, W) : nullptr;
     for (int it = 0; it < n_iters; ++it) {
@@ -581,15 +605,28 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
             if ((rc = run_update_block(wts, r.net, r.xbuf, r.corr, r.coords1, r.flow, r.mask, nullptr, B, h, w, u, s))) return rc;
         }
         float* fu = (it == 0 && flow_first) ? flow_first : ((it == n_iters - 1) ? flow_last : nullptr);
-        if (fg_up && !fu) {      // persistent kernel over the foreground list (the up-sampled flow is not an output here)
+        if (use_pipe) {
+            // dense outputs on request: the up-sampled flow of every pixel from the dense kernel (no descriptors involved),
+            // the weight map as a scatter of the records' weights over a zeroed map
+            if (fu && (rc = b2p_upsample_weight(r.flow, r.mask, nullptr, nullptr, nullptr, sigma, B, C_geo, H, W, fu, nullptr, nullptr, 0, s)))
+                return rc;
+            float* wd = (weight_last && it == n_iters - 1) ? weight_last : nullptr;
+            if (wd) B2P_CUDA(cudaMemsetAsync(wd, 0, (size_t)B * H * W * sizeof(float), s));
+            if ((rc = b2p_fgpipe_upsample_weight(r.flow, r.mask, g2_cl ? geofea2 : nullptr, depth, sigma, B, H, W, r.fg, r.fgp, wd, s)))
+                return rc;
+        } else if (fg_up && !fu) {      // persistent kernel over the foreground list (the up-sampled flow is not an output here)
             if ((rc = b2p_upsample_weight_fg(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, r.fg, r.target, r.weight, s)))
                 return rc;
         } else if ((rc = b2p_upsample_weight(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, fu, r.target,
                                              r.weight, 1, s))) return rc;
         if (it == 0 && it == n_iters - 1 && flow_first && flow_last)
             B2P_CUDA(cudaMemcpyAsync(flow_last, flow_first, (size_t)B * 2 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        if ((rc = b2p_lm_steps(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, n_lm, r.lm, s, fg_idx, fg_count))) return rc;
+        if (use_pipe) {
+            if ((rc = b2p_lm_cluster(b2p_fgpipe_records(r.fgp, B, H, W), fg_idx, fg_count, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, n_lm, s)))
+                return rc;
+        } else if ((rc = b2p_lm_steps(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, n_lm, r.lm, s, fg_idx, fg_count))) return rc;
     }
+    if (use_pipe) return 0;                                 // weight_last was written by the last iteration's scatter
     if (weight_last && n_iters > 0)
         B2P_CUDA(cudaMemcpyAsync(weight_last, r.weight, (size_t)B * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return 0;

@@ -41,8 +41,8 @@ inline cudaError_t b2p_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 // Process-wide kernel-selection options (options.cu): read once from B200POSE_* environment variables at the first call
 // into the library, changed afterwards only through b200pose_set_option.
 struct B2POptions {
-    int conv_mode, fg_list, fg_pipeline, fg_upsample, sparse_g1, fg_blocks, tail_min_n, conv_debug, lookup_mode, lm_mode,
-        pool_mode, lm_debug;
+    int conv_mode, fg_list, fg_pipeline, fg_upsample, sparse_g1, fg_blocks, tail_min_n, conv_debug, lookup_mode, pool_mode,
+        lm_debug;
 };
 B2POptions& b2p_options();
 
@@ -172,6 +172,7 @@ int b2p_split_planes(const float* src, int pitch_in, int C, size_t P, __half* hi
 // kernels implemented across the .cu files (host launchers; all return 0 / cudaError_t)
 int b2p_corr_volume(const float* f1, const float* f2, int B, int D, int P, float* level0, cudaStream_t s);
 int b2p_corr_pool(const float* src, int NP, int hs, int ws, float* dst, cudaStream_t s);
+int b2p_corr_pool3(float* pyramid, int B, int h, int w, cudaStream_t s);   // levels 1..3 in one pass, or -1 (not applicable)
 int b2p_fmap_to_pxc_half(const float* f, int B, int D, int P, __half* hi, __half* lo, cudaStream_t s);
 // hi/lo != nullptr: additionally (or instead, when out == nullptr) write fp16 hi/lo planes with the same pitch
 int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, __half* out_hi,
@@ -206,7 +207,17 @@ int b2p_lm_steps(const float* depth, const float* target, const float* weight, c
                  int B, int H, int W, float depth_add, double ep, double lm, int n_steps, void* ws, cudaStream_t s,
                  const int* fg_idx = nullptr, const int* fg_count = nullptr);
 size_t b2p_lm_ws_bytes(int B, int H, int W);
+int b2p_se3_retract(const float* delta, float* G, int B, cudaStream_t s);
+int b2p_chol_solve(const double* H, const double* b, float* x, int B, cudaStream_t s);
 int b2p_lm_reset(void* ws, int B, int H, int W, cudaStream_t s);   // once before the first b2p_lm_step on a workspace
+int b2p_lm_cluster(const float4* rec, const int* fg_idx, const int* fg_count, const float* K, float* G, int B, int H, int W,
+                   float depth_add, double ep, double lm, int n_steps, cudaStream_t s);
+// foreground pipeline (fg_pipeline.cu): channels-last descriptors, float4 records per listed pixel
+size_t b2p_fgpipe_ws_bytes(int B, int H, int W);
+const float4* b2p_fgpipe_records(const void* ws, int B, int H, int W);
+int b2p_fgpipe_prepare(const float* g1, const float* g2, int g2_is_cl, int B, int H, int W, const void* fg_ws, void* ws, cudaStream_t s);
+int b2p_fgpipe_upsample_weight(const float* flow, const float* mask, const float* g2_cl_or_null, const float* depth, float sigma, int B,
+                               int H, int W, const void* fg_ws, void* ws, float* weight_dense, cudaStream_t s);
 size_t b2p_pose_metrics_ws_bytes(int B, int n);
 int b2p_pose_metrics(const float* T_pred, const float* T_gt, const float* pts, const float* diameter, const float* K, int B,
                      int n, float* out, void* ws, cudaStream_t s);

@@ -871,6 +871,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 
 __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_constant__ ChainParams cp) {
     extern __shared__ uint8_t smem_raw[];
+    const unsigned long long t_entry = (cp.L[0].debug & 16) ? gtime_ns() : 0ull;
     pdl_trigger();
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -921,11 +922,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     pdl_wait();
+    const unsigned long long t_dep = (cp.L[0].debug & 16) ? gtime_ns() : 0ull;
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer (both CTAs)
         int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
         int l = 0;
+        const bool timed = (cp.L[0].debug & 16) != 0;
         for (int g = unit0; g < total_units; g += unit_step) {
             while (g >= cp.unit_start[l + 1]) ++l;
             const UmmaConvParams& p = cp.L[l];
@@ -933,6 +936,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
             decode(p, g - cp.unit_start[l], bimg, y0, x0, n0, real, m_idx);
             // ---- dependencies: lanes 0..8 each watch one tile of the 3x3 neighbourhood (lane 4 = the tile itself)
             const ChainDep& d = cp.dep[l];
+            const long long td0 = timed ? clock64() : 0;
             if (d.n_src > 0 && lane < 9 && (d.halo || lane == 4)) {
                 const int tiles_per_img = p.tiles_x * p.tiles_y;
                 const int trem = m_idx - bimg * tiles_per_img;
@@ -951,6 +955,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
             }
             __syncwarp();
             asm volatile("fence.proxy.async.global;" ::: "memory");        // what those stores wrote, as seen by the TMA unit
+            if (timed && lane == 0) atomicAdd(&g_conv_dbg[l + 1][blockIdx.x][7], (unsigned long long)(clock64() - td0));
+            unsigned long long w_empty = 0;
             const uint32_t a_plane = (uint32_t)p.a_rows * 1024u;
             const int b_rows = p.n_tile >> 1;
             const uint32_t b_plane = (uint32_t)b_rows * 128u;
@@ -966,7 +972,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
                         const int seg = cc >= p.seg0_chunks ? 1 : 0;
                         const int c0 = (seg ? cc - p.seg0_chunks : cc) * BKC;
                         const uint32_t da = a_ring + (uint32_t)sa * CH_A_SLOT;
-                        mbar_wait(empty_a(sa), pha ^ 1u);
+                        mbar_wait_timed(empty_a(sa), pha ^ 1u, timed, w_empty);
                         if (elect_one()) {
                             const uint32_t fb = mapa_rank(full_a(sa), 0);
                             if (rank == 0) mbar_expect_tx(full_a(sa), a_tx);
@@ -978,7 +984,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
                         for (int j = 0; j < p.a_taps; ++j) {
                             const int tap = (kyo + j) * p.kw + kx;
                             const uint32_t db = b_ring + (uint32_t)sb * CH_B_SLOT;
-                            mbar_wait(empty_b(sb), phb ^ 1u);
+                            mbar_wait_timed(empty_b(sb), phb ^ 1u, timed, w_empty);
                             if (elect_one()) {
                                 const uint32_t fb = mapa_rank(full_b(sb), 0);
                                 if (rank == 0) mbar_expect_tx(full_b(sb), b_tx);
@@ -991,6 +997,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
                     }
                 }
             }
+            if (timed && lane == 0) atomicAdd(&g_conv_dbg[l + 1][blockIdx.x][3], w_empty);
         }
         // drain: every commit aimed at this CTA's empty barriers has landed before the CTA may exit
         for (int i = 0; i < CH_RING_A; ++i) { mbar_wait(empty_a(sa), pha ^ 1u); if (++sa == CH_RING_A) { sa = 0; pha ^= 1u; } }
@@ -1001,8 +1008,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
             uint32_t tile_iter = 0;
             int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
             int l = 0;
+            const bool timed = (cp.L[0].debug & 16) != 0;
             for (int g = unit0; g < total_units; g += unit_step, ++tile_iter) {
                 while (g >= cp.unit_start[l + 1]) ++l;
+                unsigned long long w_full = 0, w_tmem = 0;
+                const long long t_begin = timed ? clock64() : 0;
                 const UmmaConvParams& p = cp.L[l];
                 const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((256u >> 4) << 24);
                 const uint32_t a_plane = (uint32_t)p.a_rows * 1024u, b_plane = (uint32_t)(p.n_tile >> 1) * 128u;
@@ -1010,14 +1020,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
                 const int a_items = outer_taps * p.kw * p.n_active;
                 const int buf = tile_iter & 1;
                 const uint32_t acc = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
-                mbar_wait(tmem_empty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);
+                mbar_wait_timed(tmem_empty_bar(buf), ((tile_iter >> 1) & 1) ^ 1, timed, w_tmem);
                 tc_fence_after();
                 uint32_t accumulate = 0;
                 for (int ai = 0; ai < a_items; ++ai) {
-                    mbar_wait(full_a(sa), pha);
+                    mbar_wait_timed(full_a(sa), pha, timed, w_full);
                     const uint32_t da = a_ring + (uint32_t)sa * CH_A_SLOT;
                     for (int j = 0; j < p.a_taps; ++j) {
-                        mbar_wait(full_b(sb), phb);
+                        mbar_wait_timed(full_b(sb), phb, timed, w_full);
                         tc_fence_after();
                         const uint32_t db = b_ring + (uint32_t)sb * CH_B_SLOT;
                         if (elect_one()) {
@@ -1042,6 +1052,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
                 }
                 if (elect_one()) tc_commit_pair(tmem_full_bar(buf));
                 __syncwarp();
+                if (timed && lane == 0) {
+                    unsigned long long* dd = g_conv_dbg[l + 1][blockIdx.x];
+                    atomicAdd(&dd[0], (unsigned long long)(clock64() - t_begin)); atomicAdd(&dd[1], w_full); atomicAdd(&dd[2], w_tmem);
+                    atomicAdd(&dd[6], 1ull);
+                }
             }
         }
     } else {
@@ -1050,6 +1065,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
         const int mrow = q * 32 + lane;
         uint32_t tile_iter = 0;
         int l = 0;
+        const bool timed = (cp.L[0].debug & 16) != 0 && warp == 2;
         for (int g = unit0; g < total_units; g += unit_step, ++tile_iter) {
             while (g >= cp.unit_start[l + 1]) ++l;
             const UmmaConvParams& p = cp.L[l];
@@ -1059,11 +1075,17 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
             const int yy = y0 + (mrow >> 3), xx = x0 + (mrow & 7);
             const bool valid = real && yy < p.h && xx < p.w;
             const size_t pix = ((size_t)bimg * p.h + yy) * p.w + xx;
+            const long long e0 = timed ? clock64() : 0;
             mbar_wait_backoff(tmem_full_bar(buf), (tile_iter >> 1) & 1);
+            const long long e1 = timed ? clock64() : 0;
             tc_fence_after();
             epilogue_columns<true>(p, tmem_base, warp, q, buf, n0, p.n_tile, valid, pix, m_idx, mrow);
             tc_fence_before();
             mbar_arrive_cluster(mapa_rank(tmem_empty_bar(buf), 0));
+            if (timed && lane == 0) {
+                atomicAdd(&g_conv_dbg[l + 1][blockIdx.x][4], (unsigned long long)(e1 - e0));
+                atomicAdd(&g_conv_dbg[l + 1][blockIdx.x][5], (unsigned long long)(clock64() - e1));
+            }
             // publish this warp's share of the tile: its stores become visible device-wide (and to the async proxy of the
             // SMs that will TMA-load them) before the counter moves
             __threadfence();
@@ -1077,6 +1099,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
     cluster_sync_all();
     if (warp == 1)
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if ((cp.L[0].debug & 16) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned i = atomicAdd(&g_conv_log_n, 1u) & 511u;
+        g_conv_log[i][0] = t_entry; g_conv_log[i][1] = t_dep; g_conv_log[i][2] = gtime_ns(); g_conv_log[i][3] = 0ull;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -1279,6 +1305,7 @@ int fill_chain_layer(const UmmaConvArgs& a, UmmaConvParams& p) {
     p.out_hi = a.out_hi; p.out_lo = a.out_lo; p.out_h_pitch = a.out_h_pitch;
     p.zbuf = a.zbuf; p.hbuf = a.hbuf;
     p.side_tiled = a.side_tiled; p.out_tiled = a.out_tiled;
+    p.debug = b2p_options().conv_debug & 16;             // clock counters only; the drop-a-stage experiments are gen-2 only
     p.m_tiles = a.B * p.tiles_x * p.tiles_y;
     p.m_groups = ceil_div(p.m_tiles, 2);
     p.total_tiles = p.m_groups * (a.cout_pad / n_tile);

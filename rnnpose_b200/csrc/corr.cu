@@ -95,6 +95,139 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------ lookup, second version
+// The 81 samples of one level share ONE fractional offset (the window offsets are integers), so they are the four-corner
+// blend of a 10 x 10 texel window with constant weights.  One warp per low-resolution pixel:
+//   1. the four windows (4 x 100 texels) are staged into shared memory with branch-free loads (clamped address + select:
+//      zeros outside the level, utils/utils.py:57-65 grid_sample zero padding), 400 loads instead of 1296;
+//   2. every lane blends its samples from shared memory (same products and order as the first kernel) into a 328-wide
+//      staging row; 3. the row leaves as 128-bit stores: fp32 (float4) and/or the fp16 hi / lo operand planes (8 halves).
+// Channel order: l*81 + i*9 + j samples (x + i - 4, y + j - 4): the slow window index moves x (corr.py:44-50).
+constexpr int LK_WARPS = 8;
+constexpr int LK_WIN = 104;                     // 100 texels per level window, padded
+
+__global__ void __launch_bounds__(LK_WARPS * 32) corr_lookup_win_kernel(const float* __restrict__ pyr, const float* __restrict__ coords,
+                                                                         int B, int h, int w, float* __restrict__ out,
+                                                                         __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+    __shared__ __align__(16) float win[LK_WARPS][B200POSE_CORR_LEVELS][LK_WIN];
+    __shared__ __align__(16) float row[LK_WARPS][B200POSE_CORR_PITCH];
+    pdl_trigger();
+    pdl_wait();
+    const int P = h * w;
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * LK_WARPS + wib;
+    if (warp >= B * P) return;                                   // warp-uniform; no block-wide barrier below
+    const int b = warp / P, p = warp - b * P;
+    const float cx = coords[(size_t)warp * 2 + 0];
+    const float cy = coords[(size_t)warp * 2 + 1];
+    float fxs[B200POSE_CORR_LEVELS], fys[B200POSE_CORR_LEVELS];
+    size_t lvl_off = 0;
+    int hl = h, wl = w;
+    float inv = 1.0f;
+#pragma unroll
+    for (int l = 0; l < B200POSE_CORR_LEVELS; ++l) {
+        const float* img = pyr + lvl_off + ((size_t)b * P + p) * (size_t)(hl * wl);
+        // sample (i, j) sits at (x0c + i - 4, y0c + j - 4); floor(x0c + k) == floor(x0c) + k exactly unless |x0c| is so
+        // large that the window lies outside every level anyway (then the integer conversion saturates and all texels
+        // fail the bounds test: zeros, like the reference)
+        const float x0c = cx * inv, y0c = cy * inv;              // cx / 2^l (exact: power of two)
+        const float xb = floorf(x0c - 4.0f), yb = floorf(y0c - 4.0f);
+        fxs[l] = (x0c - 4.0f) - xb; fys[l] = (y0c - 4.0f) - yb;
+        const bool fin = isfinite(x0c) && isfinite(y0c);
+        const int xi0 = fin ? (int)fmaxf(fminf(xb, 1e6f), -1e6f) : -1000000;
+        const int yi0 = fin ? (int)fmaxf(fminf(yb, 1e6f), -1e6f) : -1000000;
+#pragma unroll
+        for (int t = lane; t < 100; t += 32) {
+            const int ry = t / 10, rx = t - ry * 10;
+            const int yy = yi0 + ry, xx = xi0 + rx;
+            const bool ok = yy >= 0 && yy < hl && xx >= 0 && xx < wl;
+            const int yc = min(max(yy, 0), hl - 1), xc = min(max(xx, 0), wl - 1);
+            const float v = __ldg(img + yc * wl + xc);
+            win[wib][l][t] = ok ? v : 0.f;
+        }
+        lvl_off += (size_t)B * P * (size_t)(hl * wl);
+        hl >>= 1; wl >>= 1; inv *= 0.5f;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int l = 0; l < B200POSE_CORR_LEVELS; ++l) {
+        const float fx = fxs[l], fy = fys[l];
+        // the first kernel evaluates floor() per sample: xs = x0c + (i - 4), fx = xs - floor(xs).  For |x0c| < 2^22 both
+        // give the same fraction up to the rounding of the addition; keep its weights' form (1-fx)(1-fy) etc.
+        const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
+        for (int k = lane; k < 81; k += 32) {
+            const int i = k / 9, j = k - i * 9;                  // i moves x, j moves y
+            const float* wp = &win[wib][l][j * 10 + i];
+            row[wib][l * 81 + k] = wp[0] * w00 + wp[1] * w01 + wp[10] * w10 + wp[11] * w11;
+        }
+    }
+    if (lane < B200POSE_CORR_PITCH - B200POSE_CORR_CH) row[wib][B200POSE_CORR_CH + lane] = 0.f;
+    __syncwarp();
+    if (out) {
+        float4* o4 = reinterpret_cast<float4*>(out + (size_t)warp * B200POSE_CORR_PITCH);
+        const float4* r4 = reinterpret_cast<const float4*>(row[wib]);
+        for (int c = lane; c < B200POSE_CORR_PITCH / 4; c += 32) o4[c] = r4[c];
+    }
+    if (out_hi) {
+        uint4* oh = reinterpret_cast<uint4*>(out_hi + (size_t)warp * B200POSE_CORR_PITCH);
+        uint4* ol = reinterpret_cast<uint4*>(out_lo + (size_t)warp * B200POSE_CORR_PITCH);
+        for (int c = lane; c < B200POSE_CORR_PITCH / 8; c += 32) {
+            uint32_t wh[4], wlw[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                __half h0, l0, h1, l1;
+                b2p_split_half(row[wib][c * 8 + 2 * t], h0, l0);
+                b2p_split_half(row[wib][c * 8 + 2 * t + 1], h1, l1);
+                wh[t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                wlw[t] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            oh[c] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+            ol[c] = make_uint4(wlw[0], wlw[1], wlw[2], wlw[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pyramid levels 1..3 in one pass
+// One block per (sample, source pixel) image of level 0 (hs x ws floats): the image is read once into shared memory and the
+// three 2x2 floor poolings are chained there (corr.py:32-34; the first kernel reads level l to write level l+1: 3 passes).
+// Summation order as corr_pool_kernel: ((a + b) + c) + d, then * 0.25.
+__global__ void __launch_bounds__(128) corr_pool3_kernel(const float* __restrict__ l0, int hs, int ws, float* __restrict__ l1,
+                                                         float* __restrict__ l2, float* __restrict__ l3) {
+    extern __shared__ float sm[];
+    const size_t n = blockIdx.x;
+    const int n0 = hs * ws, h1 = hs >> 1, w1 = ws >> 1, h2 = h1 >> 1, w2 = w1 >> 1, h3 = h2 >> 1, w3 = w2 >> 1;
+    float* s0 = sm; float* s1 = s0 + n0; float* s2 = s1 + h1 * w1;
+    const float* src = l0 + n * n0;
+    if ((n0 & 3) == 0) {
+        for (int i = threadIdx.x; i < n0 / 4; i += blockDim.x) reinterpret_cast<float4*>(s0)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    } else {
+        for (int i = threadIdx.x; i < n0; i += blockDim.x) s0[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < h1 * w1; i += blockDim.x) {
+        const int y = i / w1, x = i - y * w1;
+        const float* s = s0 + (2 * y) * ws + 2 * x;
+        float sum = s[0]; sum += s[1]; sum += s[ws]; sum += s[ws + 1];
+        const float v = sum * 0.25f;
+        s1[i] = v; l1[n * (size_t)(h1 * w1) + i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < h2 * w2; i += blockDim.x) {
+        const int y = i / w2, x = i - y * w2;
+        const float* s = s1 + (2 * y) * w1 + 2 * x;
+        float sum = s[0]; sum += s[1]; sum += s[w1]; sum += s[w1 + 1];
+        const float v = sum * 0.25f;
+        s2[i] = v; l2[n * (size_t)(h2 * w2) + i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < h3 * w3; i += blockDim.x) {
+        const int y = i / w3, x = i - y * w3;
+        const float* s = s2 + (2 * y) * w2 + 2 * x;
+        float sum = s[0]; sum += s[1]; sum += s[w2]; sum += s[w2 + 1];
+        l3[n * (size_t)(h3 * w3) + i] = sum * 0.25f;
+    }
+}
+
 // context [B,256,H,W] --(1/8 bilinear, align_corners=True)--> net = tanh(ch 0..127) [P][128],
 // xbuf[:, 0:128] = relu(ch 128..255).   32 low-res pixels x 32 channels per block, smem transpose.
 __global__ void __launch_bounds__(256) context_init_kernel(const float* __restrict__ ctx, int B, int H, int W, int h, int w,
@@ -214,9 +347,28 @@ int b2p_corr_pool(const float* src, int NP, int hs, int ws, float* dst, cudaStre
     return 0;
 }
 
+// levels 1..3 from level 0 in one pass; -1 if the level-0 image does not fit the shared-memory budget (caller falls back)
+int b2p_corr_pool3(float* pyramid, int B, int h, int w, cudaStream_t s) {
+    const int P = h * w;
+    const size_t n0 = (size_t)h * w, n1 = (size_t)(h >> 1) * (w >> 1), n2 = (size_t)(h >> 2) * (w >> 2), n3 = (size_t)(h >> 3) * (w >> 3);
+    const size_t smem = (n0 + n1 + n2) * sizeof(float);
+    if (smem > 40 * 1024 || b2p_options().pool_mode != 1) return -1;
+    float* l0 = pyramid; float* l1 = l0 + (size_t)B * P * n0; float* l2 = l1 + (size_t)B * P * n1; float* l3 = l2 + (size_t)B * P * n2;
+    (void)n3;
+    corr_pool3_kernel<<<(unsigned)((size_t)B * P), 128, smem, s>>>(l0, h, w, l1, l2, l3);
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
 int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, __half* out_hi,
                     __half* out_lo, cudaStream_t s) {
     const int warps = B * h * w;
+    if (b2p_options().lookup_mode == 1) {
+        B2P_CUDA(b2p_launch_pdl(corr_lookup_win_kernel, dim3(ceil_div(warps, LK_WARPS)), dim3(LK_WARPS * 32), 0, s, pyramid, coords, B, h, w,
+                                out, out_hi, out_lo));
+        B2P_LAUNCH_CHECK();
+        return 0;
+    }
     B2P_CUDA(b2p_launch_pdl(corr_lookup_kernel, dim3(ceil_div(warps, 8)), dim3(256), 0, s, pyramid, coords, B, h, w, out, out_hi, out_lo));
     B2P_LAUNCH_CHECK();
     return 0;

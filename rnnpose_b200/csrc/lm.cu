@@ -132,23 +132,9 @@ __device__ __forceinline__ void lm_block_reduce(double (&acc)[NACC], double (*re
     }
 }
 
-// Damping, Cholesky solve, NaN -> 0, clamp, exp, retraction.  tot = 21 H entries + 6 b entries (un-damped).
-__device__ void lm_solve_retract(const double* tot, const float (&Gm)[12], float (&Gn)[12], double ep, double lm,
-                                 double* H_out, double* b_out, float* delta_out) {
-    double Hm[6][6], bv[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        bv[i] = tot[21 + i];
-#pragma unroll
-        for (int j = i; j < 6; ++j) { Hm[i][j] = tot[tri_idx(i, j)]; Hm[j][i] = Hm[i][j]; }
-    }
-    if (H_out)
-        for (int i = 0; i < 36; ++i) H_out[i] = Hm[i / 6][i % 6];
-    if (b_out)
-        for (int i = 0; i < 6; ++i) b_out[i] = bv[i];
-    // damping: H += ep*I + lm*H*I   (transformation.py:300)
-#pragma unroll
-    for (int i = 0; i < 6; ++i) Hm[i][i] = Hm[i][i] + (ep + lm * Hm[i][i]);
+// 6x6 Cholesky solve in fp64, then NaN -> 0 and clamp to +-1 as fp32: geometry/cholesky.py:11-16,32-50
+// (torch.cholesky + cholesky_solve; max_update = 1.0).  Hm is symmetric positive definite (or poisoned by NaN).
+__device__ void chol_solve6(const double (&Hm)[6][6], const double (&bv)[6], float (&xi)[6]) {
     double L[6][6];
     for (int j = 0; j < 6; ++j) {
         double s = Hm[j][j];
@@ -172,13 +158,33 @@ __device__ void lm_solve_retract(const double* tot, const float (&Gm)[12], float
         for (int k = i + 1; k < 6; ++k) t -= L[k][i] * xv[k];
         xv[i] = t / L[i][i];
     }
-    float xi[6];
     for (int i = 0; i < 6; ++i) {
         double x = xv[i];
         if (x != x) x = 0.0;                       // NaN -> 0 (cholesky.py:42-43)
         x = fmin(fmax(x, -1.0), 1.0);               // clamp to +-max_update (cholesky.py:45)
         xi[i] = (float)x;
     }
+}
+
+// Damping, Cholesky solve, NaN -> 0, clamp, exp, retraction.  tot = 21 H entries + 6 b entries (un-damped).
+__device__ void lm_solve_retract(const double* tot, const float (&Gm)[12], float (&Gn)[12], double ep, double lm,
+                                 double* H_out, double* b_out, float* delta_out) {
+    double Hm[6][6], bv[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        bv[i] = tot[21 + i];
+#pragma unroll
+        for (int j = i; j < 6; ++j) { Hm[i][j] = tot[tri_idx(i, j)]; Hm[j][i] = Hm[i][j]; }
+    }
+    if (H_out)
+        for (int i = 0; i < 36; ++i) H_out[i] = Hm[i / 6][i % 6];
+    if (b_out)
+        for (int i = 0; i < 6; ++i) b_out[i] = bv[i];
+    // damping: H += ep*I + lm*H*I   (transformation.py:300)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Hm[i][i] = Hm[i][i] + (ep + lm * Hm[i][i]);
+    float xi[6];
+    chol_solve6(Hm, bv, xi);
     if (delta_out)
         for (int i = 0; i < 6; ++i) delta_out[i] = xi[i];
     float dG[12];
@@ -380,6 +386,155 @@ __global__ void __launch_bounds__(LM_THREADS) lm_multi_kernel(
     }
 }
 
+// ------------------------------------------------------------------------------------------------ n steps, one CLUSTER per sample
+// Third kernel, used by the foreground pipeline (fg_pipeline.cu): the pixels arrive as float4 records (target x, target y,
+// weight, depth) in list order, so the loads are a stream.  One thread-block cluster of LMC_CTAS CTAs per sample replaces
+// the global spin barrier of lm_multi_kernel:
+//   * the hardware co-schedules the CTAs of a cluster (no residency estimate, nothing to trap on);
+//   * after each step every CTA writes its 27 partial sums into CTA 0's shared memory (distributed shared memory), one
+//     barrier.cluster, then every CTA sums the LMC_CTAS partials in rank order and solves redundantly (bit-identical), so
+//     nothing is broadcast; the partial slots are double-buffered by step parity, which makes one barrier per step enough;
+//   * the reduction structure depends only on the sample's own list (not on the batch size): results are independent of
+//     the batch position and of B.
+// NOACC (option lm_debug = 1) drops the fp64 contraction (H, b stay ~0): a timing experiment that shows what a
+// tensor-core J^T W J could save at most (profiles/r2_summary.md); results are meaningless with it.
+constexpr int LMC_CTAS = 8;
+
+__device__ __forceinline__ uint32_t lm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lm_mapa(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void lm_st_cluster_f64(uint32_t addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ double lm_ld_cluster_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lm_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t lm_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+template <bool NOACC>
+__global__ void __launch_bounds__(LM_THREADS) lm_cluster_kernel(
+    const float4* __restrict__ rec, const int* __restrict__ fg_idx, const int* __restrict__ fg_count, const float* __restrict__ K,
+    float* __restrict__ G, int N, int W, float depth_add, double ep, double lm, int n_steps) {
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.x / LMC_CTAS, tid = threadIdx.x;
+    const uint32_t rank = lm_cluster_rank();
+    __shared__ double red[LM_THREADS / 32][NACC];
+    __shared__ double slots[2][LMC_CTAS][NACC];            // CTA 0's copy collects the cluster's partials
+    __shared__ double tot[NACC];
+    __shared__ float Gs[12];
+    const float* Kb = K + b * 9;
+    const float fx = Kb[0], fy = Kb[4], cx = Kb[2], cy = Kb[5];
+    if (tid < 12) Gs[tid] = G[b * 16 + tid];
+    __syncthreads();
+    const int count = fg_count[b];
+    const float4* rb = rec + (size_t)b * N;
+    const int* ib = fg_idx + (size_t)b * N;
+    const int first = (int)rank * LM_THREADS + tid, stride = LMC_CTAS * LM_THREADS;
+    const uint32_t slot0 = lm_mapa(lm_smem_u32(&slots[0][0][0]), 0);      // slots[][][] of CTA 0, cluster address space
+
+    for (int step = 0; step < n_steps; ++step) {
+        float Gm[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) Gm[i] = Gs[i];
+        double acc[NACC];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+        for (int k = first; k < count; k += 4 * stride) {
+            int rs[4]; float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int kk = k + u * stride;
+                rs[u] = kk < count ? __ldg(ib + kk) : -1;
+                v[u] = kk < count ? rb[kk] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (rs[u] < 0) continue;
+                if (NOACC) {
+                    double dummy[NACC];
+#pragma unroll
+                    for (int i = 0; i < NACC; ++i) dummy[i] = 0.0;
+                    lm_pixel(dummy, rs[u] % W, rs[u] / W, v[u].w, make_float2(v[u].x, v[u].y), v[u].z, depth_add, fx, fy, cx, cy, Gm);
+                    acc[0] += dummy[0];                     // keeps the loads and the Jacobian, drops 26 of the 27 sums
+                } else {
+                    lm_pixel(acc, rs[u] % W, rs[u] / W, v[u].w, make_float2(v[u].x, v[u].y), v[u].z, depth_add, fx, fy, cx, cy, Gm);
+                }
+            }
+        }
+        double mine;
+        lm_block_reduce(acc, red, tid, mine);
+        const uint32_t par = (uint32_t)(step & 1);
+        if (tid < NACC) lm_st_cluster_f64(slot0 + ((par * LMC_CTAS + rank) * NACC + tid) * 8u, mine);
+        lm_cluster_sync();                                  // every CTA's partials of this step are in CTA 0's slots
+        if (tid < NACC) {
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < LMC_CTAS; ++r) s += lm_ld_cluster_f64(slot0 + ((par * LMC_CTAS + r) * NACC + tid) * 8u);
+            tot[tid] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float Gn[12];
+            lm_solve_retract(tot, Gm, Gn, ep, lm, nullptr, nullptr, nullptr);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) Gs[i] = Gn[i];
+        }
+        __syncthreads();                                    // also orders red[] / tot[] reuse in the next step
+    }
+    if (rank == 0 && tid == 0) {
+        float Gn[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) Gn[i] = Gs[i];
+        store_G(G + b * 16, Gn);
+    }
+    lm_cluster_sync();                                      // CTA 0's shared memory stays alive until every CTA has read it
+}
+
+// Per-operator entries of the two small pieces of an LM step (tests pin their branches directly):
+//   G <- exp(delta) G  (SE3.increment, geometry/transformation.py:110-115; se3.py:228-306 incl. the Taylor branch)
+__global__ void se3_retract_kernel(const float* __restrict__ delta, float* __restrict__ G, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float xi[6], dG[12], Gm[12], Gn[12];
+    for (int i = 0; i < 6; ++i) xi[i] = delta[b * 6 + i];
+    for (int i = 0; i < 12; ++i) Gm[i] = G[b * 16 + i];
+    se3_exp_f32(xi, dG);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float s = dG[i * 4 + 0] * Gm[0 * 4 + j] + dG[i * 4 + 1] * Gm[1 * 4 + j] + dG[i * 4 + 2] * Gm[2 * 4 + j];
+            if (j == 3) s += dG[i * 4 + 3];
+            Gn[i * 4 + j] = s;
+        }
+    store_G(G + b * 16, Gn);
+}
+//   x = clamp(nan_to_zero(H^-1 b))  (geometry/cholesky.py:32-50), H [B,6,6] fp64 (no damping added here)
+__global__ void chol_solve_kernel(const double* __restrict__ H, const double* __restrict__ bvec, float* __restrict__ x, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double Hm[6][6], bv[6];
+    for (int i = 0; i < 6; ++i) {
+        bv[i] = bvec[b * 6 + i];
+        for (int j = 0; j < 6; ++j) Hm[i][j] = H[(size_t)b * 36 + i * 6 + j];
+    }
+    float xi[6];
+    chol_solve6(Hm, bv, xi);
+    for (int i = 0; i < 6; ++i) x[b * 6 + i] = xi[i];
+}
+
 __global__ void zero_u32_kernel(unsigned* p, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0u;
@@ -445,6 +600,39 @@ int b2p_lm_steps(const float* depth, const float* target, const float* weight, c
     dim3 grid(nb, B);
     B2P_CUDA(b2p_launch_pdl(lm_multi_kernel, grid, dim3(LM_THREADS), 0, s, depth, target, weight, K, G, B, H, W, depth_add, ep, lm, n_steps,
                             partials, counters, fg_idx, fg_count));
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+// All n_steps of one recurrent iteration over the foreground records (fg_pipeline.cu), one cluster per sample.
+int b2p_lm_cluster(const float4* rec, const int* fg_idx, const int* fg_count, const float* K, float* G, int B, int H, int W,
+                   float depth_add, double ep, double lm, int n_steps, cudaStream_t s) {
+    if (n_steps <= 0) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * LMC_CTAS)); cfg.blockDim = dim3(LM_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = LMC_CTAS; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    const int N = H * W;
+    if (b2p_options().lm_debug == 1)
+        B2P_CUDA(cudaLaunchKernelEx(&cfg, lm_cluster_kernel<true>, rec, fg_idx, fg_count, K, G, N, W, depth_add, ep, lm, n_steps));
+    else
+        B2P_CUDA(cudaLaunchKernelEx(&cfg, lm_cluster_kernel<false>, rec, fg_idx, fg_count, K, G, N, W, depth_add, ep, lm, n_steps));
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2p_se3_retract(const float* delta, float* G, int B, cudaStream_t s) {
+    se3_retract_kernel<<<ceil_div(B, 64), 64, 0, s>>>(delta, G, B);
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+int b2p_chol_solve(const double* H, const double* b, float* x, int B, cudaStream_t s) {
+    chol_solve_kernel<<<ceil_div(B, 64), 64, 0, s>>>(H, b, x, B);
     B2P_LAUNCH_CHECK();
     return 0;
 }

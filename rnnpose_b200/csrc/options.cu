@@ -24,7 +24,6 @@ const OptDesc kOpts[] = {
     {"tail_min_n", "B200POSE_TAIL_MIN_N", &B2POptions::tail_min_n, 32},     // smallest channel count of a split tail unit
     {"conv_debug", "B200POSE_V2_DEBUG", &B2POptions::conv_debug, 0},        // timing experiments (results garbage unless 0 / 16)
     {"lookup_mode", "B200POSE_LOOKUP_MODE", &B2POptions::lookup_mode, 1},   // 1 = shared-memory window lookup, 0 = round-1 kernel
-    {"lm_mode", "B200POSE_LM_MODE", &B2POptions::lm_mode, 1},               // 1 = cluster LM kernel, 0 = round-1 spin-barrier kernel
     {"pool_mode", "B200POSE_POOL_MODE", &B2POptions::pool_mode, 1},         // 1 = three pyramid levels in one pass
     {"lm_debug", "B200POSE_LM_DEBUG", &B2POptions::lm_debug, 0},            // 1 = drop the fp64 contraction (timing A/B only)
 };

@@ -255,6 +255,26 @@ def lm_solve(depth: torch.Tensor, target: torch.Tensor, weight: torch.Tensor, K:
     return (G, Ho, bo, do) if taps else G
 
 
+def cholesky_solve(H: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """geometry/cholesky.py `solve` for 6x6 fp64 systems: H [B,6,6], b [B,6] -> x [B,6] fp32 (NaN -> 0, clamp +-1)."""
+    L = _lib.lib()
+    _chk(H, "H", torch.float64); _chk(b, "b", torch.float64)
+    B = H.shape[0]
+    if H.shape != (B, 6, 6) or b.shape != (B, 6):
+        raise ValueError("cholesky_solve: H [B,6,6], b [B,6]")
+    x = torch.empty(B, 6, dtype=torch.float32, device=H.device)
+    _lib.check(L.b200pose_cholesky_solve(H.data_ptr(), b.data_ptr(), x.data_ptr(), B, _stream()), "b200pose_cholesky_solve")
+    return x
+
+
+def se3_retract(delta: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
+    """G <- exp(delta) G in place (SE3.increment); delta [B,6], G [B,4,4]."""
+    L = _lib.lib()
+    _chk(delta, "delta"); _chk(G, "G")
+    _lib.check(L.b200pose_se3_retract(delta.data_ptr(), G.data_ptr(), G.shape[0], _stream()), "b200pose_se3_retract")
+    return G
+
+
 METRIC_COLS = 16
 LINEMOD_K = ((572.4114, 0.0, 325.2611), (0.0, 573.57043, 242.04899), (0.0, 0.0, 1.0))   # data/linemod/linemod_config.py:23-25
 

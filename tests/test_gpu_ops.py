@@ -40,7 +40,9 @@ def packed(ops):
     return ops.pack_weights(load_update_weights(), dev())
 
 
-def test_corr_pyramid_and_lookup_golden(ops):
+@pytest.mark.parametrize("variant", [(1, 1), (0, 0)], ids=["window-lookup+pool3", "round1-kernels"])
+def test_corr_pyramid_and_lookup_golden(ops, libopt, variant):
+    libopt("lookup_mode", variant[0]); libopt("pool_mode", variant[1])
     g = golden("corr_lookup.npz")
     B, D, h, w, s1, s2 = [int(v) for v in g["meta"]]
     f1 = S.hash_features((B, D, h, w), s1).to(dev()); f2 = S.hash_features((B, D, h, w), s2).to(dev())
@@ -57,6 +59,34 @@ def test_corr_pyramid_and_lookup_golden(ops):
     assert out.shape == (B * h * w, 328)
     assert torch.all(out[:, 324:] == 0)
     torch.testing.assert_close(from_pxc(out[:, :324].contiguous(), B, h, w).cpu(), T(g["out"]), rtol=1e-5, atol=5e-6)
+
+
+def test_corr_lookup_window_kernel_edge_coordinates(ops):
+    """The shared-memory window lookup against the round-1 per-sample kernel and the oracle on coordinates that stress the
+    window logic: integers, just below integers, far outside the map on every side, huge and non-finite values."""
+    B, D, h, w = 1, 64, 16, 20
+    f1 = S.hash_features((B, D, h, w), 61).to(dev()); f2 = S.hash_features((B, D, h, w), 62).to(dev())
+    pyr = ops.corr_pyramid(f1, f2)
+    P = h * w
+    base = S.hash_features((B, 2, h, w), 63, 12.0) + torch.tensor([10.0, 8.0]).view(1, 2, 1, 1)
+    c = to_pxc(base).clone()
+    c[0] = torch.tensor([3.0, 5.0]); c[1] = torch.tensor([2.9999998, 4.9999995]); c[2] = torch.tensor([-30.0, 7.0])
+    c[3] = torch.tensor([7.0, 400.0]); c[4] = torch.tensor([1e9, -1e9]); c[5] = torch.tensor([19.0, 15.0])
+    c[6] = torch.tensor([-4.5, -4.5]); c[7] = torch.tensor([23.5, 19.5]); c[8] = torch.tensor([0.0, 0.0])
+    cd = c.to(dev())
+    with ops.options(lookup_mode=0):
+        old = ops.corr_lookup(pyr, cd, B, h, w).cpu()
+    with ops.options(lookup_mode=1):
+        new = ops.corr_lookup(pyr, cd, B, h, w).cpu()
+    assert torch.all(new[:, 324:] == 0)
+    torch.testing.assert_close(new, old, rtol=1e-5, atol=5e-6)
+    ref = O.corr_lookup(O.corr_pyramid(f1.cpu(), f2.cpu()), from_pxc(c, B, h, w))
+    torch.testing.assert_close(from_pxc(new[:, :324].contiguous(), B, h, w), ref, rtol=1e-5, atol=5e-6)
+    # non-finite coordinates: the reference's grid_sample yields zeros there; both kernels must agree and stay finite
+    c2 = c.clone(); c2[9] = torch.tensor([float("nan"), 3.0]); c2[10] = torch.tensor([float("inf"), 3.0])
+    with ops.options(lookup_mode=1):
+        nf = ops.corr_lookup(pyr, c2.to(dev()), B, h, w).cpu()
+    assert torch.all(nf[9:11] == 0) and torch.isfinite(nf).all()
 
 
 def test_corr_pyramid_full_size_vs_oracle(ops):
@@ -230,6 +260,62 @@ def test_lm_vs_oracle_random(ops):
     Gd = ops.lm_solve(depth.to(dev()), tgt.to(dev()), wgt.to(dev()), mb["K"].to(dev()), G.clone().to(dev()), 3,
                       depth_offset=1e-5)
     torch.testing.assert_close(Gd.cpu(), Gr, rtol=0, atol=5e-6)
+
+
+# ----------------------------------------------------------------------------- GPU pins of the small branches
+def test_se3_retract_golden_both_branches(ops):
+    """geometry/se3.py _se3_matrix_expm executed (expm.npz): Taylor branch (theta < 1e-4), Rodrigues branch, the threshold."""
+    g = golden("expm.npz")
+    xi = T(g["xi"]).float()
+    G = torch.eye(4)[None].repeat(xi.shape[0], 1, 1).contiguous().to(dev())
+    out = ops.se3_retract(xi.to(dev()), G).cpu()
+    torch.testing.assert_close(out, T(g["G"]), rtol=1e-6, atol=1e-7)
+    # composition: exp(d) G0 against the oracle
+    G0 = O.se3_exp(torch.tensor([[0.2, -0.1, 0.3, 0.5, 0.1, -0.4]])).repeat(xi.shape[0], 1, 1)
+    out2 = ops.se3_retract(xi.to(dev()), G0.clone().to(dev())).cpu()
+    torch.testing.assert_close(out2, torch.matmul(O.se3_exp(xi), G0), rtol=1e-6, atol=2e-7)
+
+
+def test_cholesky_solve_golden(ops):
+    """geometry/cholesky.py solve executed (cholesky.npz): the module's own 3x3 test system (embedded in a 6x6 block
+    system; its answer hits the +-1 clamp), eight random 6x6 systems, and NaN -> 0."""
+    g = golden("cholesky.npz")
+    H3 = torch.eye(6, dtype=torch.float64); H3[:3, :3] = T(g["H3"])
+    b3 = torch.zeros(6, dtype=torch.float64); b3[:3] = T(g["b3"])
+    x3 = ops.cholesky_solve(H3[None].contiguous().to(dev()), b3[None].contiguous().to(dev())).cpu()[0]
+    torch.testing.assert_close(x3[:3], T(g["x3"]).float(), rtol=1e-6, atol=1e-7)
+    assert x3[0] == -1.0 and x3[1] == 1.0 and torch.all(x3[3:] == 0)
+    x6 = ops.cholesky_solve(T(g["H6"]).contiguous().to(dev()), T(g["b6"]).contiguous().to(dev())).cpu()
+    torch.testing.assert_close(x6, T(g["x6"]).float(), rtol=1e-6, atol=1e-7)
+    Hn = T(g["H6"]).clone(); Hn[0, 2, 2] = float("nan")
+    xn = ops.cholesky_solve(Hn.contiguous().to(dev()), T(g["b6"]).contiguous().to(dev())).cpu()
+    assert torch.all(xn[0] == 0) and torch.equal(xn[1:], x6[1:])
+
+
+def test_cfnet_sequence_state_carry_golden(ops, packed):
+    """Three consecutive GRU_CFUpdator.forward calls of the executed reference (cfnet_seq.npz; update_corr_fn only on the
+    first): the hidden state and the context features must carry over between the per-operator calls on the GPU."""
+    g = golden("cfnet_seq.npz")
+    B, H, W, s1, s2, s3, s4 = [int(v) for v in g["meta"]]
+    h, w = H // 8, W // 8
+    f1 = S.hash_features((B, 256, h, w), s1).to(dev()); f2 = S.hash_features((B, 256, h, w), s2).to(dev())
+    ctx = S.hash_features((B, 256, H, W), s3, 0.1).to(dev())
+    u, v = O.pixel_grid(h, w)
+    grid = to_pxc(torch.stack([u, v])[None].expand(B, 2, h, w)).to(dev())
+    for flags in (0, 1):
+        pyr = ops.corr_pyramid(f1, f2)                               # update_corr_fn == True part (CFNet.py:115-133)
+        net, xbuf = ops.context_init(ctx)
+        for it in range(3):
+            fi = S.hash_features((B, 2, H, W), s4 + it, 6.0)
+            fl_lr = O.downsample_align_corners(fi / 8.0, 8)            # CFNet.py:138-142 (input preparation)
+            flow = to_pxc(fl_lr).to(dev()).contiguous()
+            coords1 = (grid + flow).contiguous()
+            corr = ops.corr_lookup(pyr, coords1, B, h, w)
+            mask, _ = ops.update_block(packed, net, xbuf, corr, coords1, flow, B, h, w, flags=flags)
+            fu, _, _ = ops.upsample_weight(flow, mask, None, None, None, 1.0, B, H, W)
+            tol = 1.0 if flags == 0 else 4.0
+            torch.testing.assert_close(fu.cpu(), T(g["flow_up"][it]), rtol=1e-4, atol=2e-4 * tol)
+            torch.testing.assert_close(from_pxc(net, B, h, w).cpu(), T(g["net"][it]), rtol=1e-4, atol=2e-5 * tol * 2)
 
 
 # ----------------------------------------------------------------------------- f3: pose metrics kernel

@@ -148,6 +148,40 @@ def test_refine_host_entry_matches_device_entry(ops, packed):
     assert torch.equal(Gh, Gd)
 
 
+def test_refine_iters_cuda_graph_capture(ops, packed):
+    """b200pose_refine_iters is stream-ordered and allocation-free: captured into a CUDA graph (PDL and cluster launches
+    included) and replayed, it reproduces the eager result bit for bit, also after the inputs change in place."""
+    H, W, idxs = 128, 160, [21, 22]
+    mb = S.make_batch(idxs, H, W, with_images=False)
+    d = torch.device("cuda:0")
+    f1 = S.hash_features((2, 256, H // 8, W // 8), 83).to(d); f2 = S.hash_features((2, 256, H // 8, W // 8), 84).to(d)
+    t = {k: mb[k].to(d).contiguous() for k in ("context", "geofea1", "geofea2", "K")}
+    depth = mb["depth"][:, 0].contiguous().to(d)
+    G0 = torch.eye(4, device=d)[None].repeat(2, 1, 1).contiguous()
+    ws = ops.RefineWorkspace(2, H, W, d)
+
+    def call(G):
+        ops.refine_iters(packed, f1, f2, t["context"], t["geofea1"], t["geofea2"], depth, t["K"], G, 1.0, 3, 3, workspace=ws)
+
+    Ge = G0.clone(); call(Ge); torch.cuda.synchronize()              # eager (also initialises the library's lazy statics)
+    Gs = G0.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            call(Gs)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(2):
+        Gs.copy_(G0); graph.replay(); torch.cuda.synchronize()
+        assert torch.equal(Gs, Ge)
+    # new inputs in the same buffers: the graph reads them at replay time
+    G1 = O.se3_exp(torch.tensor([[0.01, 0.0, -0.01, 0.02, 0.01, 0.0], [0.0, 0.02, 0.01, -0.01, 0.0, 0.02]])).to(d)
+    Ge2 = G1.clone(); call(Ge2); torch.cuda.synchronize()
+    Gs.copy_(G1); graph.replay(); torch.cuda.synchronize()
+    assert torch.equal(Gs, Ge2) and not torch.equal(Ge2, Ge)
+
+
 def test_error_codes(ops, packed):
     from rnnpose_b200 import _lib
     L = _lib.lib()
@@ -211,9 +245,24 @@ def test_refine_foreground_list_matches_dense_kernels(ops, packed, libopt):
     f1 = S.hash_features((3, 256, H // 8, W // 8), 96); f2 = S.hash_features((3, 256, H // 8, W // 8), 97)
     G0 = torch.eye(4)[None].repeat(3, 1, 1)
     libopt("fg_list", 0)
-    dense = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, want_weight=True)
-    libopt("fg_list", 1)
+    dense = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, want_weight=True, want_flows=True)
+    libopt("fg_list", 1); libopt("fg_pipeline", 0)
     fg = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, want_weight=True)
+    # default: the foreground pipeline (channels-last descriptors, float4 records, cluster LM kernel), with and without the
+    # dense outputs requested, tensor-core and exact-fp32 convolutions
+    libopt("fg_pipeline", 1)
+    for kw in (dict(want_weight=True, want_flows=True), dict()):
+        pipe = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, **kw)
+        assert torch.equal(pipe["G"][1].cpu(), G0[1])
+        assert (pipe["G"].cpu() - dense["G"].cpu()).abs().max().item() < 1e-6
+        if kw:
+            torch.testing.assert_close(pipe["weight"].cpu(), dense["weight"].cpu(), rtol=0, atol=2e-6)
+            assert torch.equal(pipe["flow_first"].cpu(), dense["flow_first"].cpu())
+            assert torch.equal(pipe["flow_last"].cpu(), dense["flow_last"].cpu())
+    libopt("fg_pipeline", 0); d32 = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, flags=0)
+    libopt("fg_pipeline", 1); p32 = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, flags=0)
+    assert (p32["G"].cpu() - d32["G"].cpu()).abs().max().item() < 1e-6
+    libopt("fg_pipeline", 0)
     assert torch.equal(fg["G"][1].cpu(), G0[1]) and torch.equal(dense["G"][1].cpu(), G0[1])
     assert (fg["G"].cpu() - dense["G"].cpu()).abs().max().item() < 1e-6
     torch.testing.assert_close(fg["weight"].cpu(), dense["weight"].cpu(), rtol=0, atol=2e-6)

@@ -1,5 +1,5 @@
 """Where the conv kernels' warps wait inside the real fused loop (B200POSE_V2_DEBUG=16 clock counters, accumulated per layer
-over one refine call at the bench shape).  usage: B200POSE_CONV_MODE=m python tools/conv_counters.py"""
+over one refine call at the bench shape).  usage: B200POSE_CONV_MODE=m python tools/conv_counters.py   (m with bit 4 set: the chained launch, per-layer counters)"""
 import ctypes as C
 import os
 import sys
@@ -7,8 +7,10 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["B200POSE_V2_DEBUG"] = "16"
 from rnnpose_b200 import ops  # noqa: E402
+
+ops.set_option("conv_debug", 16)
+CHAIN = (ops.get_option("conv_mode") & 16) != 0
 
 dev = torch.device("cuda:0")
 sd = torch.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "weights", "gru_update.pth"), map_location="cpu")
@@ -38,7 +40,26 @@ call()
 L.b200pose_debug_conv_counters(buf, 0)
 v = torch.tensor(list(buf), dtype=torch.float64).view(12, 160, 8)
 names = ["(other)", "C1", "C2", "F1", "F2", "ENC", "ZR1", "Q1", "ZR2", "Q2", "HEADS", "MASK2"]
-print(f"mode {os.environ.get('B200POSE_CONV_MODE', 'default')}: clocks per launch, mean over the CTAs that issue MMAs (4 launches per layer + GRU pre-sums)")
+if CHAIN:
+    # conv_chain_kernel: one launch per recurrent iteration; counters per layer, summed over the units of a cluster
+    print(f"conv_mode {ops.get_option('conv_mode')} (chained launch): clocks per launch and cluster (leader CTA), mean over clusters")
+    print("layer   units | MMA loop  per unit | wait full  wait tmem | prod wait empty  dep wait | epi wait full  epi busy  busy/unit")
+    tot = torch.zeros(8, dtype=torch.float64)
+    for i, n in enumerate(names):
+        x = v[i]
+        act = x[x[:, 6] > 0]
+        if act.numel() == 0:
+            continue
+        m = act.mean(0) / 4.0
+        pe = x[x[:, 5] > 0].mean(0) / 4.0
+        pp = x[(x[:, 3] > 0) | (x[:, 7] > 0)]
+        pw = (pp.mean(0) / 4.0) if pp.numel() else torch.zeros(8, dtype=torch.float64)
+        tot += torch.stack([m[0], m[1], m[2], pw[3], pe[4], pe[5], m[6], pw[7]])
+        print(f"{n:7s} {m[6]:5.2f} | {m[0]:8.0f} {m[0] / max(m[6], 1e-9):9.0f} | {m[1]:9.0f} {m[2]:10.0f} | {pw[3]:15.0f} {pw[7]:9.0f} | "
+              f"{pe[4]:13.0f} {pe[5]:9.0f} {pe[5] / max(m[6], 1e-9):10.0f}")
+    print(f"sum     {tot[6]:5.1f} | {tot[0]:8.0f}           | {tot[1]:9.0f} {tot[2]:10.0f} | {tot[3]:15.0f} {tot[7]:9.0f} | {tot[4]:13.0f} {tot[5]:9.0f}")
+    print(f"  (1 us = 1965 clocks; MMA-loop sum = {tot[0] / 1965:.0f} us per launch)")
+print(f"mode {ops.get_option('conv_mode')}: clocks per launch, mean over the CTAs that issue MMAs (4 launches per layer + GRU pre-sums)")
 print("layer   units stages | MMA-loop | wait full  wait tmem | prod wait empty | epi wait full  epi busy | loop clk/stage  epi busy/unit")
 for i, n in enumerate(names):
     x = v[i]
