@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(LK_WARPS * 32) corr_lookup_win_kernel(const fl
         // fail the bounds test: zeros, like the reference)
         const float x0c = cx * inv, y0c = cy * inv;              // cx / 2^l (exact: power of two)
         const float xb = floorf(x0c - 4.0f), yb = floorf(y0c - 4.0f);
-        fxs[l] = (x0c - 4.0f) - xb; fys[l] = (y0c - 4.0f) - yb;
         const bool fin = isfinite(x0c) && isfinite(y0c);
+        fxs[l] = fin ? (x0c - 4.0f) - xb : 0.f; fys[l] = fin ? (y0c - 4.0f) - yb : 0.f;     // non-finite centre: exact zeros
         const int xi0 = fin ? (int)fmaxf(fminf(xb, 1e6f), -1e6f) : -1000000;
         const int yi0 = fin ? (int)fmaxf(fminf(yb, 1e6f), -1e6f) : -1000000;
 #pragma unroll
