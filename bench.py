@@ -4,9 +4,14 @@
 Contract (driver):  python bench.py --gpus N --steps K --warmup W [--impl reference]
 (N>1: launched under torch.distributed.run, one rank per GPU).  One JSON line on rank 0.
 
-A "step" = one pass of the hot path (b200pose_refine_iters: ITER_COUNT=4 recurrent iterations x
-OPTIM_ITER_COUNT=3 LM steps) over one batch of 32 synthetic 240x320 crop pairs per GPU
-(BASELINE.json configs[1]; at N=8 this is configs[2], 256 objects sharded 32/GPU, weak scaling).
+A "step" = one pass of the hot path (b200pose_refine_iters: ITER_COUNT recurrent iterations x OPTIM_ITER_COUNT LM steps)
+over one batch of synthetic crop pairs per GPU.  Workloads (BASELINE.json configs):
+  --config cfg1  (default)  32 objects/GPU, 240x320, 4 x 3            configs[1]; at --gpus 8 this is configs[2] (256 objects)
+  --config cfg3             32 objects/GPU, 240x320, 8 x 3, occluded scenes, sample_poses-style perturbed initial poses
+                            (configs[3]: 128 objects on 4 GPUs)
+  --config cfg4             480x640, 4 x 3; --global-batch B (8..512) or --sweep for the whole batch-size sweep (configs[4])
+  --global-batch B          total objects over all ranks (e.g. --config cfg1 --global-batch 256 at N=1: the strong-scaling point)
+Batches larger than --chunk objects per GPU are processed in chunks (every chunk is real work on resident inputs).
   value : poses/s with the loop's inputs resident in HBM (CUDA events, max over ranks)
   e2e   : poses/s through the host-buffer C-ABI entry (pinned host inputs -> H2D -> loop -> D2H of the poses)
   roofline / cpu_baseline : see DESIGN.md section "Measurement"
@@ -14,6 +19,7 @@ OPTIM_ITER_COUNT=3 LM steps) over one batch of 32 synthetic 240x320 crop pairs p
 does not exist on the GPU box) timed on the host cores on a bounded sample of the same workload.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -35,31 +41,47 @@ if os.environ.get("OMP_NUM_THREADS") == "1":
 
 import torch  # noqa: E402
 
-H, W, B_PER_GPU, N_ITERS, N_LM = 240, 320, 32, 4, 3
 UNIQUE_SCENES = 8            # distinct synthetic scenes per rank, tiled to the batch
 FLOP_PER_LOWRES_PX = 6236672  # update-block convolutions, SURVEY.md Appendix A.2
-NCU_TRAFFIC_BYTES_PER_PASS = 775_000_000   # profiles/r1c_summary.md (642 MB read + 133 MB written)
-WORKLOAD = f"synthetic {H}x{W} crops, batch {B_PER_GPU}/GPU, {N_ITERS} recurrent iters x {N_LM} LM steps"
+# dram__bytes_read.sum + dram__bytes_write.sum of the convolution launch(es) of one update-block pass at B=32, 240x320, from
+# the committed `ncu --set full` capture named in TRAFFIC_SOURCE (ncu flushes caches per launch: an upper bound)
+NCU_TRAFFIC_BYTES_PER_PASS = 775_000_000
+TRAFFIC_SOURCE = "profiles/r1c_conv_umma2_ncu_raw.csv (11 conv launches of one pass, B=32, 240x320)"
+
+CONFIGS = {
+    #        H    W   iters lm  objects/GPU occluded  chunk
+    "cfg1": (240, 320, 4, 3, 32, False, 64),
+    "cfg3": (240, 320, 8, 3, 32, True, 64),
+    "cfg4": (480, 640, 4, 3, 8, False, 16),
+}
+SWEEP_BATCHES = (8, 16, 32, 64, 128, 256, 512)
+
+
+def workload_name(cfg, per_gpu):
+    H, W, it, lm, _, occ, _ = CONFIGS[cfg]
+    return (f"synthetic {H}x{W} crops, batch {per_gpu}/GPU, {it} recurrent iters x {lm} LM steps" +
+            (", occluded targets, perturbed initial poses" if occ else ""))
 
 
 def load_weights():
-    sd = torch.load(os.path.join(ROOT, "tests", "golden", "weights", "gru_update.pth"), map_location="cpu")
-    return {k[len("update_block."):]: v.float() for k, v in sd.items()}
+    from rnnpose_b200.assets import load_update_weights
+    return load_update_weights()
 
 
-def make_inputs(rank: int, batch: int, unique: int):
+def make_inputs(rank: int, batch: int, unique: int, H: int, W: int, occlude: bool = False):
     """CPU float32 inputs of the inner loop for `batch` objects (unique scenes tiled)."""
     from rnnpose_b200 import synthetic as S
+    unique = min(unique, batch)
     idx = [rank * unique + i for i in range(unique)]
-    mb = S.make_batch(idx, H, W, with_images=False)
-    rep = batch // unique
-    out = {k: v.repeat(rep, *([1] * (v.dim() - 1))).contiguous() for k, v in mb.items()}
+    mb = S.make_batch(idx, H, W, occlude=occlude, with_images=False)
+    rep = (batch + unique - 1) // unique
+    out = {k: v.repeat(rep, *([1] * (v.dim() - 1)))[:batch].contiguous() for k, v in mb.items()}
     h, w = H // 8, W // 8
-    out["fmap1"] = S.hash_features((unique, 256, h, w), 9000 + rank).repeat(rep, 1, 1, 1).contiguous()
-    out["fmap2"] = S.hash_features((unique, 256, h, w), 9500 + rank).repeat(rep, 1, 1, 1).contiguous()
+    out["fmap1"] = S.hash_features((unique, 256, h, w), 9000 + rank).repeat(rep, 1, 1, 1)[:batch].contiguous()
+    out["fmap2"] = S.hash_features((unique, 256, h, w), 9500 + rank).repeat(rep, 1, 1, 1)[:batch].contiguous()
     out["depth"] = out["depth"][:, 0].contiguous()
     out["G0"] = torch.eye(4)[None].repeat(batch, 1, 1).contiguous()
-    out["scene_idx"] = torch.tensor(idx).repeat(rep)
+    out["scene_idx"] = torch.tensor(idx).repeat(rep)[:batch]
     return out
 
 
@@ -108,6 +130,48 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def bind_numa(dev_index: int):
+    """Bind this rank's CPU threads and its future host allocations (the pinned e2e buffers) to the NUMA node of its GPU,
+    BEFORE anything is pinned: at N=8 every rank otherwise allocates on the node it happens to start on and half of the
+    H2D traffic crosses the socket interconnect (round-1 SCALE run: e2e efficiency 0.49 with all ranks on node 0).
+    Best effort: reports what it could do."""
+    info = {"gpu_numa_node": None, "cpus_bound": None, "mempolicy": "unchanged"}
+    try:
+        pr = torch.cuda.get_device_properties(dev_index)
+        bdf = None
+        if hasattr(pr, "pci_bus_id") and hasattr(pr, "pci_device_id"):
+            bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        else:
+            q = subprocess.run(["nvidia-smi", "--query-gpu=uuid,pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True).stdout
+            uuid = str(getattr(pr, "uuid", ""))
+            for line in q.splitlines():
+                u, b = [x.strip() for x in line.split(",")]
+                if uuid and uuid in u:
+                    bdf = b[-12:].lower()
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read()) if bdf else -1
+        info["gpu_numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus_bound"] = len(allowed)
+        else:
+            info["cpus_bound"] = 0                      # the node's cores are outside this container's cpuset
+        libc = ctypes.CDLL("libc.so.6", use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        MPOL_PREFERRED, NR_set_mempolicy = 1, 238
+        rc = libc.syscall(NR_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))
+        info["mempolicy"] = f"preferred node {node}" if rc == 0 else f"set_mempolicy failed (errno {ctypes.get_errno()})"
+    except Exception as e:  # noqa: BLE001
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
+
+
 _THREADS = None
 
 
@@ -143,98 +207,139 @@ def pick_cpu_threads(wts) -> int:
     return best
 
 
-def cpu_oracle_rate(inputs, n_objects: int, wts):
+def cpu_oracle_rate(inputs, n_objects: int, wts, n_iters: int, n_lm: int):
     """Oracle port on the host cores: `n_objects` objects, one reference-style B=1 call each."""
     from oracle import refine_oracle as O
     pick_cpu_threads(wts)
     t0 = time.time()
+    outs = []
     with torch.no_grad():
         for i in range(n_objects):
             sl = slice(i, i + 1)
             # the variant that issues the reference's own ATen op sequence (grid_sample, interpolate, einsum f64, ...)
-            O.refine_inner_loop_aten(wts, inputs["fmap1"][sl], inputs["fmap2"][sl], inputs["context"][sl],
-                                     inputs["geofea1"][sl], inputs["geofea2"][sl], inputs["depth"][sl][:, None],
-                                     inputs["K"][sl], inputs["G0"][sl], sigma=1.0, n_iters=N_ITERS, n_lm=N_LM)
+            r = O.refine_inner_loop_aten(wts, inputs["fmap1"][sl], inputs["fmap2"][sl], inputs["context"][sl],
+                                         inputs["geofea1"][sl], inputs["geofea2"][sl], inputs["depth"][sl][:, None],
+                                         inputs["K"][sl], inputs["G0"][sl], sigma=1.0, n_iters=n_iters, n_lm=n_lm)
+            outs.append(r["G"])
     dt = time.time() - t0
-    return n_objects / dt, dt
+    return n_objects / dt, dt, torch.cat(outs)
+
+
+def metric_name(cfg):
+    H, W, it, lm = CONFIGS[cfg][:4]
+    return f"refined poses/sec ({it} recur iters x {lm} LM steps, {H}x{W})"
 
 
 def run_reference(args):
     """--impl reference: CPU oracle port, all host threads, bounded sample per step."""
-    rank, _, world = int(os.environ.get("RANK", 0)), 0, int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    per_step = 4
-    inputs = make_inputs(0, per_step, per_step)
+    H, W, n_iters, n_lm, per_gpu, occl, _ = CONFIGS[args.config]
+    per_step = 4 if H * W <= 240 * 320 else 1
+    inputs = make_inputs(0, per_step, per_step, H, W, occl)
     wts = load_weights()
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_oracle_rate(inputs, 1, wts)
+        cpu_oracle_rate(inputs, 1, wts, n_iters, n_lm)
     t0 = time.time()
     n = 0
     for _ in range(args.steps):
-        cpu_oracle_rate(inputs, per_step, wts); n += per_step
+        cpu_oracle_rate(inputs, per_step, wts, n_iters, n_lm); n += per_step
     dt = time.time() - t0
     v = n / dt
     cores = torch.get_num_threads()
-    line = {"impl": "reference", "metric": "refined poses/sec (4 recur iters x 3 LM steps, 240x320)", "value": v,
+    per = args.global_batch // max(1, args.gpus) if args.global_batch else per_gpu
+    line = {"impl": "reference", "metric": metric_name(args.config), "value": v,
             "unit": "poses/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (LM step f64)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"{per_step} objects per step, one B=1 call each"},
+            "config": {"workload": workload_name(args.config, per), "sample": f"{per_step} objects per step, one B=1 call each"},
             "cpu_baseline": {"value": v, "unit": "poses/s", "cores": cores, "kind": "port",
-                             "sample": f"{n} objects x ({N_ITERS}x{N_LM}) at {H}x{W}, oracle/refine_oracle.py::refine_inner_loop_aten, torch CPU fp32"},
+                             "sample": f"{n} objects x ({n_iters}x{n_lm}) at {H}x{W}, oracle/refine_oracle.py::refine_inner_loop_aten, torch CPU fp32"},
             "e2e": {"value": v, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--e2e-steps", type=int, default=None)
-    ap.add_argument("--cpu-objects", type=int, default=8)
-    ap.add_argument("--exact-fp32", action="store_true", help="CUDA-core fp32 convolutions instead of the tcgen05 path")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    args.warmup = max(3, args.warmup)
+def conv_pass_roofline(ops, packed, Bc, H, W, FLAGS, peaks, peak_src, exact, ms_step, n_iters, passes_per_step):
+    """Roofline of the dominant kernel family -- the convolutions of one update-block pass -- timed live, back to back, at
+    the chunk batch size.  The pass is timed ALONE (not inside the long step), so the denominator is the BURST dense-bf16
+    peak of MEASURED_PEAKS.json; the sustained-peak fraction is reported next to it."""
+    dev = packed.device
+    h, w = H // 8, W // 8
+    P = Bc * h * w
+    net = torch.tanh(torch.randn(P, 128, device=dev)); xbuf = torch.relu(torch.randn(P, 256, device=dev))
+    corr = torch.randn(P, 328, device=dev); c1 = torch.randn(P, 2, device=dev); fl = torch.randn(P, 2, device=dev)
+    for _ in range(3):
+        ops.update_block(packed, net, xbuf, corr, c1, fl, Bc, h, w, flags=FLAGS)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    torch.cuda.synchronize()
+    r0.record()
+    for _ in range(reps):
+        ops.update_block(packed, net, xbuf, corr, c1, fl, Bc, h, w, flags=FLAGS)
+    r1.record(); torch.cuda.synchronize()
+    ub_ms = r0.elapsed_time(r1) / reps
+    flops = FLOP_PER_LOWRES_PX * P
+    achieved = flops / (ub_ms * 1e-3) / 1e12
+    burst = float(peaks.get("bf16_tflops"))
+    sustained = float(peaks.get("bf16_tflops_sustained", burst))
+    chain = (ops.get_option("conv_mode") & 16) != 0
+    kern = ("conv_gemm_kernel<128|64> (FFMA)" if exact else
+            ("conv_chain_kernel (the 11 convolutions of a pass in one persistent launch of CTA pairs, tcgen05.mma cta_group::2 + TMA + TMEM)"
+             if chain else "conv_umma2_kernel (tcgen05.mma cta_group::2 on CTA pairs + TMA + TMEM), 11 launches"))
+    same_shape = (Bc, H, W) == (32, 240, 320) and not exact and not chain
+    return {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+            "frac_of_sustained_peak": achieved / sustained,
+            "traffic": NCU_TRAFFIC_BYTES_PER_PASS if same_shape else None,
+            "traffic_source": TRAFFIC_SOURCE if same_shape else None,
+            "peak_source": f"{peak_src}: dense bf16 burst (the pass is timed alone); sustained {sustained:.1f}",
+            "kernel": kern + "; one update-block pass timed back to back incl. its helper launches (im2col, flow head, operand split)",
+            "algorithmic_flops_per_pass": flops, "ms_per_pass": ub_ms, "batch": Bc,
+            "share_of_step": (ub_ms * n_iters * passes_per_step) / ms_step}
 
+
+def run_workload(args, cfg, per_gpu, rank, local_rank, world, dev, numa, want_cpu=True, want_e2e=True):
+    """One workload on this rank's GPU; returns the JSON line (rank 0) or None."""
     from rnnpose_b200 import dist as D, metrics as M, ops, synthetic as S
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
-    rank, local_rank, world = D.init_from_env("nccl")
-    assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    B = B_PER_GPU
+    H, W, N_ITERS, N_LM, _, occl, chunk_cap = CONFIGS[cfg]
+    chunk = min(per_gpu, args.chunk or chunk_cap)
+    n_chunks = (per_gpu + chunk - 1) // chunk
+    assert per_gpu % chunk == 0, f"--global-batch per GPU ({per_gpu}) must be a multiple of the chunk ({chunk})"
     FLAGS = ops.FLAG_EXACT_FP32 if args.exact_fp32 else ops.FLAG_TENSOR_CORES
     dtype = ("f32 (CUDA-core FFMA convolutions; LM step f64)" if args.exact_fp32 else
              "f32-equivalent: tcgen05 kind::f16 on fp16 hi/lo split operands (22-bit), 3 MMAs, fp32 TMEM accumulate; LM step f64")
-    conv_kernel = ("conv_gemm_kernel<128|64> (FFMA)" if args.exact_fp32 else "conv_umma2_kernel (tcgen05.mma cta_group::2 on CTA pairs + TMA + TMEM)")
 
-    inputs = make_inputs(rank, B, UNIQUE_SCENES)
-    assert args.cpu_objects <= B
-    host = {k: inputs[k].pin_memory() for k in ("fmap1", "fmap2", "context", "geofea1", "geofea2", "depth", "K", "G0")}
-    d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    # resident inputs: one chunk's worth per distinct chunk (up to 4 distinct chunks; more chunks re-use them round robin --
+    # every chunk is still far larger than the 126 MB L2)
+    n_res = min(n_chunks, 4 if H * W <= 240 * 320 else 1)
+    inputs = [make_inputs(rank * n_res + c, chunk, UNIQUE_SCENES, H, W, occl) for c in range(n_res)]
+    keys = ("fmap1", "fmap2", "context", "geofea1", "geofea2", "depth", "K", "G0")
+    host = {k: inputs[0][k].pin_memory() for k in keys}                       # e2e: chunk 0's buffers, pinned after bind_numa
+    d = [{k: (host[k] if c == 0 else inputs[c][k]).to(dev, non_blocking=True) for k in keys} for c in range(n_res)]
     wts = load_weights()
     packed = ops.pack_weights(wts, dev)
-    ws = ops.RefineWorkspace(B, H, W, dev)
-    G = d["G0"].clone()
+    ws = ops.RefineWorkspace(chunk, H, W, dev)
+    Gs = [d[c % n_res]["G0"].clone() for c in range(n_chunks)]
 
     def step():
-        G.copy_(d["G0"])
-        ops.refine_iters(packed, d["fmap1"], d["fmap2"], d["context"], d["geofea1"], d["geofea2"], d["depth"], d["K"], G,
-                         1.0, N_ITERS, N_LM, workspace=ws, flags=FLAGS)
+        for c in range(n_chunks):
+            t = d[c % n_res]
+            Gs[c].copy_(t["G0"])
+            ops.refine_iters(packed, t["fmap1"], t["fmap2"], t["context"], t["geofea1"], t["geofea2"], t["depth"], t["K"], Gs[c],
+                             1.0, N_ITERS, N_LM, workspace=ws, flags=FLAGS)
 
     # everything the closing metric gather needs is resident before the timed region
-    T_init_d, T_gt_d = inputs["T_init"].to(dev), inputs["T_gt"].to(dev)
-    diam_d, sidx_d = inputs["diameter"].to(dev), inputs["scene_idx"].to(dev)
-    pts = torch.stack([torch.from_numpy(S.model_points(S.make_scene(int(i), H, W))) for i in inputs["scene_idx"]]).to(dev)
+    T_init_d = torch.cat([inputs[c % n_res]["T_init"] for c in range(n_chunks)]).to(dev)
+    T_gt_d = torch.cat([inputs[c % n_res]["T_gt"] for c in range(n_chunks)]).to(dev)
+    diam_d = torch.cat([inputs[c % n_res]["diameter"] for c in range(n_chunks)]).to(dev)
+    sidx = torch.cat([inputs[c % n_res]["scene_idx"] for c in range(n_chunks)])
+    sidx_d = sidx.to(dev)
+    scene_pts = {int(i): torch.from_numpy(S.model_points(S.make_scene(int(i), H, W, occlude=occl))) for i in sidx.unique()}
+    pts = torch.stack([scene_pts[int(i)] for i in sidx]).to(dev)
 
     def gather_metrics():
         """per-object metrics + the single all-gather that closes the job (reference tools/train.py:724-741)"""
-        met = M.pose_metrics(torch.matmul(G, T_init_d), T_gt_d, pts, diam_d, sidx_d)
+        met = M.pose_metrics(torch.matmul(torch.cat(Gs), T_init_d), T_gt_d, pts, diam_d, sidx_d)
         return D.all_gather_metrics(met)
 
     for _ in range(args.warmup):
@@ -255,98 +360,140 @@ def main():
     t_wall1 = time.time()
     ms = D.max_over_ranks(ev0.elapsed_time(ev1), dev)
     clocks = sampler.stop(t_wall0, t_wall1)
-    value = world * B * args.steps / (ms * 1e-3)
+    value = world * per_gpu * args.steps / (ms * 1e-3)
+    G_dev0 = Gs[0].clone()
 
-    # ---- e2e: host buffers through the C-ABI host entry (H2D + loop + D2H inside the timed region)
-    ke = args.e2e_steps or max(3, min(args.steps, 10))
-    Gh = host["G0"].clone().pin_memory()
-    scratch = None
-    def e2e_step():
-        nonlocal scratch
-        Gh.copy_(host["G0"])
-        _, scratch = ops.refine_iters_host(packed, host["fmap1"], host["fmap2"], host["context"], host["geofea1"],
-                                           host["geofea2"], host["depth"], host["K"], Gh, 1.0, N_ITERS, N_LM, scratch=scratch,
-                                           flags=FLAGS)
-    del ws
-    e2e_step()
-    torch.cuda.synchronize(); D.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(ke):
+    # ---- e2e: host buffers through the C-ABI host entry (H2D + loop + D2H inside the timed region), chunk by chunk
+    e2e = None
+    if want_e2e:
+        ke = args.e2e_steps or max(3, min(args.steps, 10))
+        Gh = host["G0"].clone().pin_memory()
+        scratch = None
+
+        def e2e_step():
+            nonlocal scratch
+            for _c in range(n_chunks):
+                Gh.copy_(host["G0"])
+                _, scratch = ops.refine_iters_host(packed, host["fmap1"], host["fmap2"], host["context"], host["geofea1"],
+                                                   host["geofea2"], host["depth"], host["K"], Gh, 1.0, N_ITERS, N_LM,
+                                                   scratch=scratch, flags=FLAGS)
+        del ws
         e2e_step()
-    e1.record()
-    torch.cuda.synchronize(); D.barrier()
-    ms_e2e = D.max_over_ranks(e0.elapsed_time(e1), dev)
-    e2e_value = world * B * ke / (ms_e2e * 1e-3)
-    # bytes that cross PCIe per step: cudaMemcpy of every input except the context map, plus the context rows the
-    # context-init kernel reads directly from the pinned host buffer (rows floor(y*s) and +1 of each 1/8-res row)
-    sy = (H - 1) / (H // 8 - 1)
-    rows = set()
-    for y in range(H // 8):
-        y0 = min(int(y * sy), H - 1); rows.update((y0, min(y0 + 1, H - 1)))
-    ctx_bytes = B * 256 * len(rows) * W * 4
-    # the first descriptor map is fetched from the pinned buffer only where the rendered depth is positive
-    sparse_g1 = ops.get_option("sparse_g1") != 0
-    g1_bytes = (int((host["depth"] > 0).sum()) * host["geofea1"].shape[1] * 4) if sparse_g1 else host["geofea1"].numel() * 4
-    h2d = sum(host[k].numel() * 4 for k in ("fmap1", "fmap2", "geofea2", "depth", "K", "G0")) + g1_bytes + ctx_bytes
-    d2h = Gh.numel() * 4
-    agree = (Gh.to(dev) - G).abs().max().item()
-    del scratch
+        torch.cuda.synchronize(); D.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(ke):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize(); D.barrier()
+        my_ms = e0.elapsed_time(e1)
+        ms_e2e = D.max_over_ranks(my_ms, dev)
+        e2e_value = world * per_gpu * ke / (ms_e2e * 1e-3)
+        # bytes that cross PCIe per chunk: cudaMemcpy of every input except the context map, plus the context rows the
+        # context-init kernel reads directly from the pinned host buffer (rows floor(y*s) and +1 of each 1/8-res row)
+        sy = (H - 1) / (H // 8 - 1)
+        rows = set()
+        for y in range(H // 8):
+            y0 = min(int(y * sy), H - 1); rows.update((y0, min(y0 + 1, H - 1)))
+        ctx_bytes = chunk * 256 * len(rows) * W * 4
+        sparse_g1 = ops.get_option("sparse_g1") != 0
+        g1_bytes = (int((host["depth"] > 0).sum()) * host["geofea1"].shape[1] * 4) if sparse_g1 else host["geofea1"].numel() * 4
+        h2d = n_chunks * (sum(host[k].numel() * 4 for k in ("fmap1", "fmap2", "geofea2", "depth", "K", "G0")) + g1_bytes + ctx_bytes)
+        d2h = n_chunks * Gh.numel() * 4
+        agree = (Gh.to(dev) - G_dev0).abs().max().item()
+        e2e = {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": ke, "ms_per_step": ms_e2e / ke, "max_abs_diff_vs_device_entry": agree,
+               "h2d_gbs_this_rank": h2d * ke / (my_ms * 1e-3) / 1e9,
+               "host_input_bytes": n_chunks * sum(host[k].numel() * 4 for k in host), "numa": numa,
+               "note": "context map is read in place from pinned host memory (only the rows the 1/8 resample touches); the first descriptor map likewise only at the pixels with depth > 0"}
+        del scratch
+    else:
+        del ws
 
-    # ---- roofline of the dominant kernel family: the update-block convolutions (conv_gemm_kernel), timed live
     peaks, peak_src = measured_peaks()
-    h, w = H // 8, W // 8
-    P = B * h * w
-    net = torch.tanh(torch.randn(P, 128, device=dev)); xbuf = torch.relu(torch.randn(P, 256, device=dev))
-    corr = torch.randn(P, 328, device=dev); c1 = torch.randn(P, 2, device=dev); fl = torch.randn(P, 2, device=dev)
-    for _ in range(3):
-        ops.update_block(packed, net, xbuf, corr, c1, fl, B, h, w, flags=FLAGS)
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    torch.cuda.synchronize()
-    r0.record()
-    for _ in range(reps):
-        ops.update_block(packed, net, xbuf, corr, c1, fl, B, h, w, flags=FLAGS)
-    r1.record(); torch.cuda.synchronize()
-    ub_ms = r0.elapsed_time(r1) / reps
-    flops = FLOP_PER_LOWRES_PX * P
-    achieved = flops / (ub_ms * 1e-3) / 1e12
-    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES_PER_PASS if not args.exact_fp32 else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum over the 11 conv launches of one pass, "
-                                  "profiles/r1c_conv_umma2_ncu_raw.csv (B=32, 240x320; ncu flushes caches per launch)",
-                "peak_source": f"{peak_src} (bf16 dense, sustained)",
-                "kernel": conv_kernel + ": the 11 convolution launches of one update-block pass, timed back to back "
-                          "(incl. the im2col / flow-head / operand-split helper launches, <3% of the pass)",
-                "algorithmic_flops_per_pass": flops, "ms_per_pass": ub_ms,
-                "share_of_step": (ub_ms * N_ITERS) / (ms / args.steps)}
+    roofline = conv_pass_roofline(ops, packed, chunk, H, W, FLAGS, peaks, peak_src, args.exact_fp32, ms / args.steps, N_ITERS, n_chunks)
 
     line = None
     if rank == 0:
         cpu = None
-        if world == 1:
-            n_cpu = max(1, args.cpu_objects)
-            rate, dt = cpu_oracle_rate(inputs, n_cpu, wts)
+        oracle_check = None
+        if world == 1 and want_cpu:
+            n_cpu = max(1, min(args.cpu_objects, chunk)) if H * W <= 240 * 320 else 1
+            rate, dt, G_cpu = cpu_oracle_rate(inputs[0], n_cpu, wts, N_ITERS, N_LM)
             cpu = {"value": rate, "unit": "poses/s", "cores": torch.get_num_threads(), "kind": "port",
                    "sample": f"{n_cpu} objects x ({N_ITERS}x{N_LM}) at {H}x{W} in {dt:.1f}s, oracle/refine_oracle.py::refine_inner_loop_aten (reference ATen op sequence, torch CPU fp32, LM fp64)"}
+            k = min(2, n_cpu)
+            oracle_check = {"objects": k, "max_abs_dSE3_vs_oracle": float((G_dev0[:k].cpu() - G_cpu[:k]).abs().max())}
+        opts = {n: ops.get_option(n) for n in ops.option_names()}
         line = {
-            "metric": "refined poses/sec (4 recur iters x 3 LM steps, 240x320)", "value": value, "unit": "poses/s",
+            "metric": metric_name(cfg), "value": value, "unit": "poses/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
-            "data": f"synthetic (seeded ellipsoid scenes, {UNIQUE_SCENES} unique per GPU tiled to {B}; hash-noise feature maps; shipped gru_update weights)",
-            "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world} (objects sharded, one all-gather of metrics)",
-                       "l2": "inputs per step (3.2 GB/GPU) exceed the 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": ke, "ms_per_step": ms_e2e / ke, "max_abs_diff_vs_device_entry": agree,
-                    "host_input_bytes": sum(host[k].numel() * 4 for k in host),
-                    "note": "context map is read in place from pinned host memory (only the rows the 1/8 resample touches); the first descriptor map likewise only at the pixels with depth > 0"},
-            "gpu_launches": args.steps * ops.launch_count(N_ITERS, N_LM),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "data": f"synthetic (seeded ellipsoid scenes, {UNIQUE_SCENES} unique per chunk tiled to {chunk}; hash-noise feature maps; shipped gru_update weights)",
+            "config": {"workload": workload_name(cfg, per_gpu), "name": cfg, "global_batch": world * per_gpu,
+                       "chunk": chunk, "chunks_per_step": n_chunks,
+                       "parallelism": f"dp{world} (objects sharded, one all-gather of metrics)",
+                       "l2": f"resident inputs per chunk ({sum(d[0][k].numel() * 4 for k in keys) / 1e9:.1f} GB) exceed the 126 MB L2; no explicit flush"},
+            "e2e": e2e,
+            "gpu_launches": args.steps * n_chunks * ops.launch_count(N_ITERS, N_LM) + 2,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "options": opts,
             "accuracy_vs_gt": {"objects": int(gm.shape[0]), "mean_add_over_diameter": float((gm[:, 0] / gm[:, 15]).mean()),
                                "add_0.1d_recall": float(gm[:, 6].mean()), "adds_0.1d_recall": float(gm[:, 7].mean()),
-                               "proj2d_5px_recall": float(gm[:, 12].mean()), "cm5deg5_recall": float(gm[:, 13].mean())},
+                               "proj2d_5px_recall": float(gm[:, 12].mean()), "cm5deg5_recall": float(gm[:, 13].mean()),
+                               "note": "pose vs ground truth after refinement on synthetic scenes; a sanity number, not parity"},
+            "oracle_check": oracle_check,
         }
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default="cfg1", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--global-batch", type=int, default=None, help="total objects over all ranks (default: 32 per GPU; cfg4: 8 per GPU)")
+    ap.add_argument("--chunk", type=int, default=None, help="objects per b200pose_refine_iters call (default: up to 64 at 240x320, 16 at 480x640)")
+    ap.add_argument("--sweep", action="store_true", help="cfg4: batch-size sweep 8..512, one JSON line with a `sweep` list")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--cpu-objects", type=int, default=8)
+    ap.add_argument("--exact-fp32", action="store_true", help="CUDA-core fp32 convolutions instead of the tcgen05 path")
+    args = ap.parse_args()
+    if args.config == "cfg2":
+        args.config = "cfg1"                      # configs[2] is configs[1]'s per-GPU workload on 8 GPUs
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(3, args.warmup)
+
+    from rnnpose_b200 import dist as D
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    rank, local_rank, world = D.init_from_env("nccl")
+    assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    numa = bind_numa(local_rank)                  # before any pinned allocation
+
+    if args.sweep:
+        assert args.config == "cfg4", "--sweep is the configs[4] batch-size sweep"
+        rows = []
+        for gb in SWEEP_BATCHES:
+            if gb % world:
+                continue
+            ln = run_workload(args, "cfg4", gb // world, rank, local_rank, world, dev, numa, want_cpu=False, want_e2e=False)
+            if ln:
+                rows.append({"global_batch": gb, "value": ln["value"], "ms_per_step": ln["ms_per_step"], "chunk": ln["config"]["chunk"],
+                             "roofline_frac": ln["roofline"]["frac"], "conv_tflops": ln["roofline"]["achieved"],
+                             "ms_per_conv_pass": ln["roofline"]["ms_per_pass"]})
+            torch.cuda.empty_cache()
+        line = run_workload(args, "cfg4", max(1, 8 // world) if world <= 8 else 1, rank, local_rank, world, dev, numa)
+        if line:
+            line["sweep"] = rows
+    else:
+        per_gpu = (args.global_batch // world) if args.global_batch else CONFIGS[args.config][4]
+        assert per_gpu >= 1 and (not args.global_batch or args.global_batch % world == 0)
+        line = run_workload(args, args.config, per_gpu, rank, local_rank, world, dev, numa)
+    if line:
         print(json.dumps(line), flush=True)
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()

@@ -62,11 +62,12 @@ const char* b200pose_error_string(int code);
 /* ---- options ------------------------------------------------------------------------------------
  * Integer options that select between kernel variants (all variants meet the parity bar; they exist for A/B timing and
  * for the tests, which run every variant).  Names (initial value <- environment variable, read once):
- *   conv_mode (B200POSE_CONV_MODE, 3)  tensor-core convolution: bit0 CTA pairs, bit1 vertical-tap reuse, bit2 force the
- *                                      second-generation kernel, bit4 chained single-launch update block; 0 = first generation
+ *   conv_mode (B200POSE_CONV_MODE, 19) tensor-core convolution: bit0 CTA pairs, bit1 vertical-tap reuse, bit2 force the
+ *                                      second-generation kernel, bit4 the eleven convolutions of an update-block pass in one
+ *                                      persistent launch (machine-filling batches; else layer by layer); 0 = first generation
  *   fg_list (B200POSE_FG_LIST, 1)      LM steps over the per-call foreground list
  *   fg_pipeline (B200POSE_FG_PIPELINE, 1)  compact channels-last upsample+weight kernel + cluster LM kernel
- *   fg_upsample, fg_blocks, sparse_g1, tail_min_n, lookup_mode, pool_mode, conv_debug, lm_debug: see csrc/options.cu
+ *   fg_upsample, fg_blocks, sparse_g1, tail_min_n, lookup_mode, pool_mode, chain_rings, conv_debug, lm_debug: see csrc/options.cu
  * Returns 0, B200POSE_E_NULL or B200POSE_E_ARG (unknown name).  Not synchronised against launches in flight on other
  * threads.                                                                                         */
 int b200pose_set_option(const char* name, int value);
@@ -203,6 +204,23 @@ size_t b200pose_pose_metrics_workspace_bytes(int B, int n_pts);
 int b200pose_pose_metrics(const float* T_pred, const float* T_gt, const float* pts, const float* diameter,
                           const float* K, int B, int n_pts, float* out, void* workspace, size_t workspace_bytes,
                           void* stream);
+
+/* ---- f1: online zoom-crop -------------------------------------------------------------------------
+ * Replaces, per render iteration, PoseRefiner.gen_zoom_crop_grids / get_affine_transformation (model/PoseRefiner.py:145-218:
+ * numpy nonzero + cv2.getAffineTransform on the host, per sample) and the two F.grid_sample crops of :287 and :292.
+ * pc_depth [B,H,W]: rendered point-cloud depth (foreground = depth > 0, :259-263); K [B,3,3] full-image intrinsics;
+ * T [B,4,4] current pose (the crop is centred on the projection of its translation, :204-205); image [B,Ci,H,W] and
+ * geofea [B,Cg,H,W] are the maps to crop (either may be NULL with its output).  margin_ratio: 0.4 in the reference.
+ * Outputs: image_crop [B,Ci,Hc,Wc]; geofea_crop [B,Cg,Hc,Wc], or with B200POSE_ZOOM_GEO_CHANNELS_LAST in `flags` (needs
+ * Cg == 32) [B,Hc*Wc,32] = what b200pose_refine_iters takes with B200POSE_FLAG_GEO2_CHANNELS_LAST; K_crop [B,3,3] (:211);
+ * theta [B,2,3] (optional, the F.affine_grid matrix).  Bilinear, zeros outside, align_corners=False (torch defaults, as the
+ * reference).  An empty foreground yields the reference's zero box.  workspace: b200pose_zoom_crop_workspace_bytes(B).   */
+#define B200POSE_ZOOM_GEO_CHANNELS_LAST 1
+size_t b200pose_zoom_crop_workspace_bytes(int B);
+int b200pose_zoom_crop(const float* pc_depth, const float* K, const float* T, const float* image, const float* geofea,
+                       int B, int Ci, int Cg, int H, int W, int Hc, int Wc, float margin_ratio, int flags,
+                       float* image_crop, float* geofea_crop, float* K_crop, float* theta,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a14: the fused inner loop ----------------------------------------------------------------
  * Replaces the body of `for i in range(cfg.ITER_COUNT)` in PoseRefiner.forward

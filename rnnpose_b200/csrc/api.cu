@@ -158,8 +158,7 @@ int run_update_block_tc(const float* wts, float* net, float* coords1, float* flo
     return 0;
 }
 
-// EXPERIMENTAL (B200POSE_CONV_MODE bit 4, not yet run on hardware): the same pass with the eleven convolutions in one
-// persistent launch (conv_chain_kernel).  Returns -1 when the chain cannot take this problem; the caller then runs the
+// conv_mode bit 4: the same pass with the eleven convolutions in one persistent launch (conv_chain_kernel).  Returns -1 when the chain cannot take this problem; the caller then runs the
 // layer-by-layer version above.
 int run_update_block_tc_chain(const float* wts, float* net, float* coords1, float* flow, float* mask, float* dflow_out,
                               int B, int h, int w, const UpdateWs& u, bool use_pre, cudaStream_t s) {
@@ -188,10 +187,12 @@ int run_update_block_tc_chain(const float* wts, float* net, float* coords1, floa
     };
     const float* pz1 = use_pre ? u.pre[0] : nullptr; const float* pq1 = use_pre ? u.pre[1] : nullptr;
     const float* pz2 = use_pre ? u.pre[2] : nullptr; const float* pq2 = use_pre ? u.pre[3] : nullptr;
-    //  0 C1   1 C2   2 F1   3 F2   4 ENC   5 ZR1   6 Q1   7 ZR2   8 Q2   9 HEADS   10 MASK2
+    // List order: a layer's units follow its sources' units by at least one whole layer where the graph allows it (F1 before
+    // C2 so that F2 does not wait on the F1 units issued just before it; the mask half of HEADS first, see n_reverse).
+    //  0 C1   1 F1   2 C2   3 F2   4 ENC   5 ZR1   6 Q1   7 ZR2   8 Q2   9 HEADS   10 MASK2
     add(CV_C1, u.corr_h, 0, B200POSE_CORR_PITCH, B200POSE_CORR_PITCH, nullptr, 0, 0, u.c1_h, 0, 256, EPI_RELU, 1.f, nullptr, 0);
-    add(CV_C2, u.c1_h, 0, 256, 256, nullptr, 0, 0, u.corflo_h, 0, 256, EPI_RELU, 1.f, nullptr, 0);
     add(CV_F1, u.col_h, 0, 112, 112, nullptr, 0, 0, u.f1o_h, 0, 128, EPI_RELU, 1.f, nullptr, 0);
+    add(CV_C2, u.c1_h, 0, 256, 256, nullptr, 0, 0, u.corflo_h, 0, 256, EPI_RELU, 1.f, nullptr, 0);
     add(CV_F2, u.f1o_h, 0, 128, 128, nullptr, 0, 0, u.corflo_h, 192, 256, EPI_RELU, 1.f, nullptr, 0);
     add(CV_ENC, u.corflo_h, 0, 256, 256, nullptr, 0, 0, u.x_h, 128, 256, EPI_RELU, 1.f, nullptr, 0);
     add(CV_ZR1, u.net_h, 0, 128, 128, u.x_h, 256, 256, u.rh_h, 0, 128, EPI_GRU_ZR, 1.f, nullptr, 0, pz1, 256);
@@ -200,14 +201,24 @@ int run_update_block_tc_chain(const float* wts, float* net, float* coords1, floa
     add(CV_Q2, u.rh_h, 0, 128, 128, u.x_h, 256, 256, u.net_h, 0, 128, EPI_GRU_Q, 1.f, nullptr, 0, pq2, 128);
     add(CV_HEADS, u.net_h, 0, 128, 128, nullptr, 0, 0, u.hm_h, 0, 512, EPI_RELU, 1.f, nullptr, 0);
     add(CV_MASK2, u.hm_h, 256, 256, 512, nullptr, 0, 0, nullptr, 0, 0, EPI_SCALE, 0.25f, mask, 576);
-    // which earlier layers each layer reads (also the layers whose readers it must not overtake, see conv_chain_kernel)
-    const int n_src[11] = {0, 1, 0, 1, 2, 1, 1, 1, 1, 1, 1};
-    const int src[11][2] = {{0, 0}, {0, 0}, {0, 0}, {2, 0}, {1, 3}, {4, 0}, {5, 0}, {6, 0}, {7, 0}, {8, 0}, {9, 0}};
-    const int halo[11] = {0, 1, 0, 1, 1, 1, 1, 1, 1, 1, 0};
+    // which earlier layers each layer reads (also the layers whose readers it must not overtake, see conv_chain_kernel).
+    // MASK2 reads channels 256..511 of HEADS = its N unit 1 only (chained N tile 256); HEADS lists that unit first.
+    B2PChainDep deps[11];
+    memset(deps, 0, sizeof(deps));
+    auto dep = [&](int l, int halo, int s0, int s1 = -1) {
+        deps[l].halo = halo; deps[l].n_src = s0 < 0 ? 0 : (s1 < 0 ? 1 : 2);
+        deps[l].src[0] = s0 < 0 ? 0 : s0; deps[l].src[1] = s1 < 0 ? 0 : s1;
+    };
+    dep(0, 0, -1); dep(1, 0, -1); dep(2, 1, 0); dep(3, 1, 1); dep(4, 1, 2, 3); dep(5, 1, 4); dep(6, 1, 5); dep(7, 1, 6);
+    dep(8, 1, 7); dep(9, 1, 8); dep(10, 0, 9);
+    deps[10].n_first[0] = 1; deps[10].n_cnt[0] = 1;
+    int n_reverse[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
     int rc;
     if ((rc = b2p_im2col_f1(flow, B, h, w, nullptr, nullptr, u.col_h[0], u.col_h[1], u.x_h[0], u.x_h[1], s))) return rc;
     // completion counters: the fp32 scratch of the exact path (unused here), well past the flow-head partial sums in u.col
-    if ((rc = b2p_launch_conv_chain(args, n, n_src, src, halo, reinterpret_cast<int*>(u.c1), s))) return rc;
+    const int m_tiles = B * ceil_div(h, B2P_TILE_ROWS) * ceil_div(w, B2P_TILE_COLS);
+    if (b2p_conv_chain_done_ints(n, m_tiles) * sizeof(int) > (size_t)B * h * w * 256 * sizeof(float)) return -1;
+    if ((rc = b2p_launch_conv_chain(args, n, deps, n_reverse, reinterpret_cast<int*>(u.c1), s))) return rc;
     return b2p_flow_head2(nullptr, u.hm_h[0], u.hm_h[1], wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, u.col, B, h, w, s);
 }
 
@@ -498,6 +509,22 @@ int b200pose_upsample_weight(const float* flow, const float* mask, const float* 
                                (cudaStream_t)stream);
 }
 
+size_t b200pose_zoom_crop_workspace_bytes(int B) { return b2p_zoom_crop_ws_bytes(B); }
+
+int b200pose_zoom_crop(const float* pc_depth, const float* K, const float* T, const float* image, const float* geofea, int B, int Ci,
+                       int Cg, int H, int W, int Hc, int Wc, float margin_ratio, int flags, float* image_crop, float* geofea_crop,
+                       float* K_crop, float* theta, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!pc_depth || !K || !T || !workspace) return B200POSE_E_NULL;
+    if ((image != nullptr) != (image_crop != nullptr) || (geofea != nullptr) != (geofea_crop != nullptr)) return B200POSE_E_NULL;
+    if (B < 1 || H < 2 || W < 2 || Hc < 2 || Wc < 2 || (image && Ci < 1) || (geofea && Cg < 1)) return B200POSE_E_SHAPE;
+    const int cl = (flags & B200POSE_ZOOM_GEO_CHANNELS_LAST) ? 1 : 0;
+    if (cl && geofea && Cg != 32) return B200POSE_E_SHAPE;
+    if (!(margin_ratio >= 0.f)) return B200POSE_E_ARG;
+    if (((uintptr_t)workspace & 255) || workspace_bytes < b2p_zoom_crop_ws_bytes(B)) return B200POSE_E_WORKSPACE;
+    return b2p_zoom_crop(pc_depth, K, T, image, geofea, B, Ci, Cg, H, W, Hc, Wc, margin_ratio, cl, image_crop, geofea_crop, K_crop,
+                         theta, workspace, (cudaStream_t)stream);
+}
+
 size_t b200pose_pose_metrics_workspace_bytes(int B, int n_pts) { return b2p_pose_metrics_ws_bytes(B, n_pts); }
 
 int b200pose_pose_metrics(const float* T_pred, const float* T_gt, const float* pts, const float* diameter, const float* K,
@@ -550,8 +577,8 @@ int b200pose_refine_launch_count(int n_iters, int n_lm) {
     //   per call: LM counter reset, 2 feature-map transposes, volume GEMM, pooling, context init, hidden state to the tiled
     //   layout = 7; with n_iters > 0: 3 for the foreground list + 2 for the channels-last descriptors; with n_iters > 1: the
     //   4 GRU partial-sum GEMMs;  per recurrent iteration: flow_init, lookup, the update block (im2col, 11 convolutions,
-    //   flow-head partial + gather), upsample + weight, and one launch for all LM steps
-    return 7 + (n_iters > 0 ? 5 : 0) + (n_iters > 1 ? 4 : 0) + n_iters * (2 + UPDATE_LAUNCHES + 1 + (n_lm > 0 ? 1 : 0));
+    //   flow-head partial + gather), target + weight (2), and one launch for all LM steps
+    return 7 + (n_iters > 0 ? 5 : 0) + (n_iters > 1 ? 4 : 0) + n_iters * (2 + UPDATE_LAUNCHES + 2 + (n_lm > 0 ? 1 : 0));
 }
 
 int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const float* fmap2, const float* context,

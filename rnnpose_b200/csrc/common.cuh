@@ -42,7 +42,7 @@ inline cudaError_t b2p_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 // into the library, changed afterwards only through b200pose_set_option.
 struct B2POptions {
     int conv_mode, fg_list, fg_pipeline, fg_upsample, sparse_g1, fg_blocks, tail_min_n, conv_debug, lookup_mode, pool_mode,
-        lm_debug;
+        lm_debug, chain_rings;
 };
 B2POptions& b2p_options();
 
@@ -162,10 +162,15 @@ struct UmmaConvArgs {
     int b_batched;             // weights differ per sample: 3rd weight-map coordinate = sample index (1x1 only)
 };
 int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s);
-// EXPERIMENTAL: several layers in one persistent launch with tile-level dependencies (conv_chain_kernel, conv_umma.cu)
+// several layers in one persistent launch with tile-level dependencies (conv_chain_kernel, conv_umma.cu)
+struct B2PChainDep {
+    int n_src, src[2];                 // indices (in list order) of the layers whose output this layer reads
+    int n_first[2], n_cnt[2];          // N units of the source that are read (n_cnt = 0: all of them)
+    int halo;                          // 1: 3x3 tile neighbourhood, 0: the same tile only
+};
 bool b2p_conv_chain_enabled();
-int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const int* n_src, const int (*src)[2], const int* halo, int* done_ws,
-                          cudaStream_t s);
+int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const B2PChainDep* deps, const int* n_reverse, int* done_ws, cudaStream_t s);
+size_t b2p_conv_chain_done_ints(int n, int m_tiles);
 // fp32 [P][pitch_in] -> fp16 hi/lo planes [P][pitch_out] (first C channels); used by the per-operator entry
 int b2p_split_planes(const float* src, int pitch_in, int C, size_t P, __half* hi, __half* lo, int pitch_out, cudaStream_t s);
 
@@ -218,6 +223,10 @@ const float4* b2p_fgpipe_records(const void* ws, int B, int H, int W);
 int b2p_fgpipe_prepare(const float* g1, const float* g2, int g2_is_cl, int B, int H, int W, const void* fg_ws, void* ws, cudaStream_t s);
 int b2p_fgpipe_upsample_weight(const float* flow, const float* mask, const float* g2_cl_or_null, const float* depth, float sigma, int B,
                                int H, int W, const void* fg_ws, void* ws, float* weight_dense, cudaStream_t s);
+size_t b2p_zoom_crop_ws_bytes(int B);
+int b2p_zoom_crop(const float* pc_depth, const float* K, const float* T, const float* image, const float* geo, int B, int Ci, int Cg,
+                  int H, int W, int Hc, int Wc, float margin_ratio, int geo_channels_last, float* image_crop, float* geo_crop,
+                  float* K_crop, float* theta, void* ws, cudaStream_t s);
 size_t b2p_pose_metrics_ws_bytes(int B, int n);
 int b2p_pose_metrics(const float* T_pred, const float* T_gt, const float* pts, const float* diameter, const float* K, int B,
                      int n, float* out, void* ws, cudaStream_t s);

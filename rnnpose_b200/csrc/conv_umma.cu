@@ -65,6 +65,7 @@ struct UmmaConvParams {
     int side_tiled;                    // z / h / pre-sum side buffers use the tiled layout (b2p_tiled_index)
     int out_tiled;                     // EPI_SCALE output is such a side buffer (the GRU pre-sum GEMMs)
     int dbg_layer;                     // row of g_conv_dbg (layer id + 1)
+    int n_reverse;                     // conv_chain_kernel: list the layer's N tiles last-to-first
     int debug;                         // timing experiments only (results are garbage): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue
 };
 
@@ -833,7 +834,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
 
 
 // ---------------------------------------------------------------------------------------------- kernel, chained layers
-// EXPERIMENTAL (opt-in: B200POSE_CONV_MODE bit 4; written at the end of round 1, NOT yet run on hardware).
+// (conv_mode bit 4; first run on hardware in round 2: profiles/r2a, r2b.)
 // The eleven convolutions of an update-block pass in ONE persistent launch of CTA pairs.  Each separate launch spends
 // 15-20 us outside its MMA loop (pipeline fill, the last unit's epilogue, the grid-wide griddepcontrol.wait; see
 // profiles/r1c_conv_counters_timeline.txt), although a tile of layer L+1 only needs its 3x3 tile neighbourhood of layer L.
@@ -846,18 +847,20 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
 // co-resident there is no deadlock.  Side buffers written earlier in the same launch are read through L2
 // (epilogue_columns<true>).  Shared memory: fixed-size ring slots for the largest layer.
 constexpr int CH_MAX_LAYERS = 11;
-constexpr int CH_RING_A = 2, CH_RING_B = 4;
+constexpr int CH_MAX_NSUB = 3;                            // N units per tile of a layer (MASK2: 576 = 3 x 192)
 constexpr uint32_t CH_A_SLOT = 2u * 20u * 1024u;          // hi + lo planes of a 20-row activation box (5x1 with halo)
 constexpr uint32_t CH_B_SLOT = 2u * 128u * 128u;          // hi + lo planes of 128 weight rows per CTA (256-channel tiles)
 
 struct ChainDep {
-    int n_src, src[2], need[2];       // source layers and the counter value that marks one of their tiles complete
+    int n_src, src[2];                 // source layers
+    int n_first[2], n_cnt[2];          // which N units of the source this layer reads (HEADS -> MASK2: the mask half only)
     int halo;                          // 1: wait for the 3x3 tile neighbourhood, 0: the same tile only (1x1 layers)
 };
 struct ChainParams {
     int n_layers, m_tiles;
+    int ring_a, ring_b;                     // ring depths (option chain_rings)
     int unit_start[CH_MAX_LAYERS + 1];     // prefix sums of the layers' unit counts
-    int* done;                              // [n_layers][m_tiles], zeroed before the launch
+    int* done;                              // [n_layers][CH_MAX_NSUB][m_tiles] epilogue-warp arrivals, zeroed before the launch
     ChainDep dep[CH_MAX_LAYERS];
     UmmaConvParams L[CH_MAX_LAYERS];
 };
@@ -876,14 +879,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const uint32_t a_ring = smem_base, b_ring = smem_base + CH_RING_A * CH_A_SLOT;
-    const uint32_t bars = b_ring + CH_RING_B * CH_B_SLOT;
+    const int RA = cp.ring_a, RB = cp.ring_b;
+    const uint32_t a_ring = smem_base, b_ring = smem_base + (uint32_t)RA * CH_A_SLOT;
+    const uint32_t bars = b_ring + (uint32_t)RB * CH_B_SLOT;
     auto full_a = [&](int s) { return bars + 8u * s; };
-    auto empty_a = [&](int s) { return bars + 8u * (CH_RING_A + s); };
-    const uint32_t bars_b = bars + 16u * CH_RING_A;
+    auto empty_a = [&](int s) { return bars + 8u * (RA + s); };
+    const uint32_t bars_b = bars + 16u * RA;
     auto full_b = [&](int s) { return bars_b + 8u * s; };
-    auto empty_b = [&](int s) { return bars_b + 8u * (CH_RING_B + s); };
-    const uint32_t bars_t = bars_b + 16u * CH_RING_B;
+    auto empty_b = [&](int s) { return bars_b + 8u * (RB + s); };
+    const uint32_t bars_t = bars_b + 16u * RB;
     auto tmem_full_bar = [&](int b) { return bars_t + 8u * b; };
     auto tmem_empty_bar = [&](int b) { return bars_t + 16u + 8u * b; };
     const uint32_t tmem_slot = bars_t + 32u;
@@ -894,20 +898,21 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
     const int total_units = cp.unit_start[cp.n_layers];
     const int unit0 = (int)blockIdx.x >> 1, unit_step = (int)gridDim.x >> 1;
     auto decode = [&](const UmmaConvParams& p, int u, int& bimg, int& y0, int& x0, int& n0, bool& real, int& m_idx) {
-        const int n_idx = u / p.m_groups;
-        m_idx = (u - n_idx * p.m_groups) * 2 + (int)rank;
+        const int n_ord = u / p.m_groups;                       // position of the unit's N tile in the list order
+        m_idx = (u - n_ord * p.m_groups) * 2 + (int)rank;
         real = m_idx < p.m_tiles;
         if (!real) m_idx = p.m_tiles - 1;
         const int tiles_per_img = p.tiles_x * p.tiles_y;
         bimg = m_idx / tiles_per_img;
         const int trem = m_idx - bimg * tiles_per_img;
         y0 = (trem / p.tiles_x) * TILE_ROWS; x0 = (trem % p.tiles_x) * TILE_COLS;
-        n0 = n_idx * p.n_tile;
+        // n_reverse: the layer's N tiles are listed last-to-first (HEADS: the mask half, which MASK2 waits for, goes first)
+        n0 = (p.n_reverse ? (p.total_tiles / p.m_groups - 1 - n_ord) : n_ord) * p.n_tile;
     };
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < CH_RING_A; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
-        for (int s = 0; s < CH_RING_B; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+        for (int s = 0; s < RA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
+        for (int s = 0; s < RB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 512); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -944,18 +949,20 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
                 if (ty >= 0 && ty < p.tiles_y && tx >= 0 && tx < p.tiles_x) {
                     const int t = bimg * tiles_per_img + ty * p.tiles_x + tx;
                     for (int k = 0; k < d.n_src; ++k) {
-                        const int* c = cp.done + (size_t)d.src[k] * cp.m_tiles + t;
-                        uint32_t spins = 0;
-                        while (ld_acquire_gpu(c) < d.need[k]) {
-                            __nanosleep(64);
-                            if (++spins > (1u << 24)) __trap();          // a scheduling bug must fail the launch, never hang
+                        for (int n = d.n_first[k]; n < d.n_first[k] + d.n_cnt[k]; ++n) {
+                            const int* c = cp.done + ((size_t)d.src[k] * CH_MAX_NSUB + n) * cp.m_tiles + t;
+                            uint32_t spins = 0;
+                            while (ld_acquire_gpu(c) < 8) {                // the 8 epilogue warps of the CTA that owned the tile
+                                __nanosleep(64);
+                                if (++spins > (1u << 24)) __trap();      // a scheduling bug must fail the launch, never hang
+                            }
                         }
                     }
                 }
             }
             __syncwarp();
             asm volatile("fence.proxy.async.global;" ::: "memory");        // what those stores wrote, as seen by the TMA unit
-            if (timed && lane == 0) atomicAdd(&g_conv_dbg[l + 1][blockIdx.x][7], (unsigned long long)(clock64() - td0));
+            if (timed && lane == 0) atomicAdd(&g_conv_dbg[p.dbg_layer][blockIdx.x][7], (unsigned long long)(clock64() - td0));
             unsigned long long w_empty = 0;
             const uint32_t a_plane = (uint32_t)p.a_rows * 1024u;
             const int b_rows = p.n_tile >> 1;
@@ -980,7 +987,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
                             tma_load_4d_pair(&p.a_lo[seg], da + a_plane, fb, c0, xs, ys, bimg);
                         }
                         __syncwarp();
-                        if (++sa == CH_RING_A) { sa = 0; pha ^= 1u; }
+                        if (++sa == RA) { sa = 0; pha ^= 1u; }
                         for (int j = 0; j < p.a_taps; ++j) {
                             const int tap = (kyo + j) * p.kw + kx;
                             const uint32_t db = b_ring + (uint32_t)sb * CH_B_SLOT;
@@ -992,16 +999,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
                                 tma_load_3d_pair(&p.b_lo, db + b_plane, fb, cc * BKC, nb0, tap);
                             }
                             __syncwarp();
-                            if (++sb == CH_RING_B) { sb = 0; phb ^= 1u; }
+                            if (++sb == RB) { sb = 0; phb ^= 1u; }
                         }
                     }
                 }
             }
-            if (timed && lane == 0) atomicAdd(&g_conv_dbg[l + 1][blockIdx.x][3], w_empty);
+            if (timed && lane == 0) atomicAdd(&g_conv_dbg[p.dbg_layer][blockIdx.x][3], w_empty);
         }
         // drain: every commit aimed at this CTA's empty barriers has landed before the CTA may exit
-        for (int i = 0; i < CH_RING_A; ++i) { mbar_wait(empty_a(sa), pha ^ 1u); if (++sa == CH_RING_A) { sa = 0; pha ^= 1u; } }
-        for (int i = 0; i < CH_RING_B; ++i) { mbar_wait(empty_b(sb), phb ^ 1u); if (++sb == CH_RING_B) { sb = 0; phb ^= 1u; } }
+        for (int i = 0; i < RA; ++i) { mbar_wait(empty_a(sa), pha ^ 1u); if (++sa == RA) { sa = 0; pha ^= 1u; } }
+        for (int i = 0; i < RB; ++i) { mbar_wait(empty_b(sb), phb ^ 1u); if (++sb == RB) { sb = 0; phb ^= 1u; } }
     } else if (warp == 1) {
         if (rank == 0) {
             // ------------------------------------------------ MMA issuer (leader CTA)
@@ -1046,14 +1053,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
                         }
                         __syncwarp();
                         accumulate = 1u;
-                        if (++sb == CH_RING_B) { sb = 0; phb ^= 1u; }
+                        if (++sb == RB) { sb = 0; phb ^= 1u; }
                     }
-                    if (++sa == CH_RING_A) { sa = 0; pha ^= 1u; }
+                    if (++sa == RA) { sa = 0; pha ^= 1u; }
                 }
                 if (elect_one()) tc_commit_pair(tmem_full_bar(buf));
                 __syncwarp();
                 if (timed && lane == 0) {
-                    unsigned long long* dd = g_conv_dbg[l + 1][blockIdx.x];
+                    unsigned long long* dd = g_conv_dbg[p.dbg_layer][blockIdx.x];
                     atomicAdd(&dd[0], (unsigned long long)(clock64() - t_begin)); atomicAdd(&dd[1], w_full); atomicAdd(&dd[2], w_tmem);
                     atomicAdd(&dd[6], 1ull);
                 }
@@ -1083,8 +1090,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
             tc_fence_before();
             mbar_arrive_cluster(mapa_rank(tmem_empty_bar(buf), 0));
             if (timed && lane == 0) {
-                atomicAdd(&g_conv_dbg[l + 1][blockIdx.x][4], (unsigned long long)(e1 - e0));
-                atomicAdd(&g_conv_dbg[l + 1][blockIdx.x][5], (unsigned long long)(clock64() - e1));
+                atomicAdd(&g_conv_dbg[p.dbg_layer][blockIdx.x][4], (unsigned long long)(e1 - e0));
+                atomicAdd(&g_conv_dbg[p.dbg_layer][blockIdx.x][5], (unsigned long long)(clock64() - e1));
             }
             // publish this warp's share of the tile: its stores become visible device-wide (and to the async proxy of the
             // SMs that will TMA-load them) before the counter moves
@@ -1092,7 +1099,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
             asm volatile("fence.proxy.async.global;" ::: "memory");
             __syncwarp();
             if (lane == 0 && real)
-                asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(cp.done + (size_t)l * cp.m_tiles + m_idx) : "memory");
+                asm volatile("red.release.gpu.global.add.s32 [%0], 1;"
+                             ::"l"(cp.done + ((size_t)l * CH_MAX_NSUB + n0 / p.n_tile) * cp.m_tiles + m_idx) : "memory");
         }
     }
     tc_fence_before();
@@ -1306,6 +1314,7 @@ int fill_chain_layer(const UmmaConvArgs& a, UmmaConvParams& p) {
     p.zbuf = a.zbuf; p.hbuf = a.hbuf;
     p.side_tiled = a.side_tiled; p.out_tiled = a.out_tiled;
     p.debug = b2p_options().conv_debug & 16;             // clock counters only; the drop-a-stage experiments are gen-2 only
+    p.dbg_layer = a.layer_id >= 0 && a.layer_id < 11 ? a.layer_id + 1 : 0;
     p.m_tiles = a.B * p.tiles_x * p.tiles_y;
     p.m_groups = ceil_div(p.m_tiles, 2);
     p.total_tiles = p.m_groups * (a.cout_pad / n_tile);
@@ -1417,13 +1426,13 @@ extern "C" int b200pose_debug_conv_log(unsigned long long* host_out) {
     return (int)(n > 512 ? 512 : n);
 }
 
-// EXPERIMENTAL chained launch (conv_chain_kernel): n layers in list order; src[l][k] (k < n_src[l]) are the indices of the
-// layers whose output layer l reads, halo[l] = 0 for 1x1 layers.  done_ws: n * m_tiles ints of device scratch.
+// Chained launch (conv_chain_kernel): n layers in list order; deps[l] names the layers whose output layer l reads (and which
+// of their N units), halo = 0 for 1x1 layers; n_reverse[l]: list layer l's N tiles last-to-first.  done_ws:
+// b2p_conv_chain_done_ints() ints of device scratch.
 // Returns -1 when the layer set does not fit the fixed ring geometry (the caller then launches the layers one by one).
 bool b2p_conv_chain_enabled() { return (conv_mode() & 16) != 0; }
 
-int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const int* n_src, const int (*src)[2], const int* halo, int* done_ws,
-                          cudaStream_t s) {
+int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const B2PChainDep* deps, const int* n_reverse, int* done_ws, cudaStream_t s) {
     if (n < 1 || n > CH_MAX_LAYERS) return -1;
     const int sms = device_sms();
     if (sms <= 0) return (int)cudaErrorInvalidDevice;
@@ -1432,26 +1441,35 @@ int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const int* n_src, con
     std::lock_guard<std::mutex> lk(cp_mutex);
     memset(&cp, 0, sizeof(cp));
     cp.n_layers = n;
+    // ring depths: option chain_rings = 10 * A + B (activation slots of 40 KB, weight slots of 32 KB; A * 40 + B * 32 <= 222)
+    const int rings = b2p_options().chain_rings;
+    cp.ring_a = rings / 10; cp.ring_b = rings % 10;
+    if (cp.ring_a < 2 || cp.ring_b < 2 || cp.ring_a * 40 + cp.ring_b * 32 > 222) { cp.ring_a = 2; cp.ring_b = 4; }
     int rc;
     for (int l = 0; l < n; ++l) {
         if ((rc = fill_chain_layer(args[l], cp.L[l]))) return rc;
+        cp.L[l].n_reverse = n_reverse ? n_reverse[l] : 0;
         cp.unit_start[l + 1] = cp.unit_start[l] + cp.L[l].total_units;
         if (cp.L[l].m_tiles != cp.L[0].m_tiles) return -1;
+        if (cp.L[l].total_tiles / cp.L[l].m_groups > CH_MAX_NSUB) return -1;
     }
     cp.m_tiles = cp.L[0].m_tiles;
     for (int l = 0; l < n; ++l) {
-        cp.dep[l].n_src = n_src[l]; cp.dep[l].halo = halo[l];
-        for (int k = 0; k < n_src[l]; ++k) {
-            const int sl = src[l][k];
+        cp.dep[l].n_src = deps[l].n_src; cp.dep[l].halo = deps[l].halo;
+        for (int k = 0; k < deps[l].n_src; ++k) {
+            const int sl = deps[l].src[k];
             if (sl < 0 || sl >= l) return -1;                       // topological order
+            const int units = cp.L[sl].total_tiles / cp.L[sl].m_groups;      // N units per tile of the source layer
             cp.dep[l].src[k] = sl;
-            cp.dep[l].need[k] = (args[sl].cout_pad / cp.L[sl].n_tile) * 8;      // units per tile x epilogue warps
+            cp.dep[l].n_first[k] = deps[l].n_cnt[k] > 0 ? deps[l].n_first[k] : 0;
+            cp.dep[l].n_cnt[k] = deps[l].n_cnt[k] > 0 ? deps[l].n_cnt[k] : units;
+            if (cp.dep[l].n_first[k] < 0 || cp.dep[l].n_first[k] + cp.dep[l].n_cnt[k] > units) return -1;
         }
     }
     cp.done = done_ws;
-    B2P_CUDA(cudaMemsetAsync(done_ws, 0, (size_t)n * cp.m_tiles * sizeof(int), s));
+    B2P_CUDA(cudaMemsetAsync(done_ws, 0, (size_t)n * CH_MAX_NSUB * cp.m_tiles * sizeof(int), s));
     int nclusters = sms / 2;
-    const size_t smem = (size_t)CH_RING_A * CH_A_SLOT + (size_t)CH_RING_B * CH_B_SLOT + 1024 + 16 * (CH_RING_A + CH_RING_B) + 64;
+    const size_t smem = (size_t)cp.ring_a * CH_A_SLOT + (size_t)cp.ring_b * CH_B_SLOT + 1024 + 16 * (cp.ring_a + cp.ring_b) + 64;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nclusters * 2); cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[2];
@@ -1463,15 +1481,16 @@ int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const int* n_src, con
     // The units wait for each other, so every cluster of the grid must be resident at once: ask the driver how many CTA
     // pairs it can co-schedule (an SM without a free partner holds none) and launch no more than that.
     {
-        static int max_clusters[64];
+        static int max_clusters[64][10][10];
         int dev = 0;
         B2P_CUDA(cudaGetDevice(&dev));
-        if (dev >= 0 && dev < 64 && max_clusters[dev] == 0) {
-            int n = 0;
-            B2P_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_chain_kernel, &cfg));
-            max_clusters[dev] = n > 0 ? n : -1;
+        if (dev < 0 || dev >= 64) return -1;
+        int& cap = max_clusters[dev][cp.ring_a][cp.ring_b];
+        if (cap == 0) {
+            int nmax = 0;
+            B2P_CUDA(cudaOccupancyMaxActiveClusters(&nmax, conv_chain_kernel, &cfg));
+            cap = nmax > 0 ? nmax : -1;
         }
-        const int cap = (dev >= 0 && dev < 64) ? max_clusters[dev] : -1;
         if (cap < 1) return -1;
         if (nclusters > cap) nclusters = cap;
         cfg.gridDim = dim3(nclusters * 2);
@@ -1480,3 +1499,6 @@ int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const int* n_src, con
     B2P_LAUNCH_CHECK();
     return 0;
 }
+
+// ints of device scratch b2p_launch_conv_chain needs for n layers over m_tiles pixel tiles
+size_t b2p_conv_chain_done_ints(int n, int m_tiles) { return (size_t)n * CH_MAX_NSUB * m_tiles; }

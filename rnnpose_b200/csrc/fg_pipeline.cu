@@ -57,40 +57,28 @@ __global__ void __launch_bounds__(256) geo_to_cl_kernel(const float* __restrict_
     }
 }
 
-// One lane group (8 lanes) per listed pixel, 4 pixels per warp; blocks stride over the sample's list.
-//   rec[b][k] = (target x, target y, weight, depth) of the k-th foreground pixel.
-__global__ void __launch_bounds__(256, 4) upsample_weight_cl_kernel(
-    const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1c, const float* __restrict__ g2cl,
-    const float* __restrict__ depth, float sigma, int H, int W, const int* __restrict__ fg_idx, const int* __restrict__ fg_count,
-    float4* __restrict__ rec, float* __restrict__ weight_dense /* optional [B][H*W]: scatter of the weights (background untouched) */) {
+// Two kernels per recurrent iteration (one fused kernel was measured first: 175 us at B=32 -- 8 lanes per pixel leave only
+// 4 pixels in flight per warp behind a three-deep dependent chain index -> mask/flow -> descriptor gather; profiles/r2b):
+//
+// (A) fg_target_kernel: one THREAD per listed pixel.  Convex upsampling (CFNet.py:95-106) and target = flow + grid
+//     (PoseRefiner.py:335-338); needs only the mask and the low-resolution flow (both L2-resident, just written by the update
+//     block).  rec[b][k] = (target x, target y, 0, depth).
+__global__ void __launch_bounds__(256) fg_target_kernel(const float* __restrict__ flow, const float* __restrict__ mask,
+                                                        const float* __restrict__ depth, int H, int W, const int* __restrict__ fg_idx,
+                                                        const int* __restrict__ fg_count, float4* __restrict__ rec) {
     pdl_trigger();
     pdl_wait();
     const int b = blockIdx.y;
     const int count = fg_count[b];
     const int h = H >> 3, w = W >> 3, N = H * W;
-    const int grp = threadIdx.x >> 3, cg = threadIdx.x & 7;            // 32 groups per block
     const int* idx = fg_idx + (size_t)b * N;
-    const float* g2b = g2cl + (size_t)b * N * GC;
-    const float* dep = depth + (size_t)b * N;
-    // warp-uniform trip count (the shuffles below need all 32 lanes): a group past the end repeats the last entry and
-    // does not store.  The next entry's pixel index is fetched one trip ahead.
-    const int stride = gridDim.x * 32;
-    const int k_first = blockIdx.x * 32 + (grp & ~3);                  // first entry of this warp's four groups
-    int r_next = (count > 0) ? __ldg(idx + min(k_first + (grp & 3), count - 1)) : 0;
-    for (int k0 = k_first; k0 < count; k0 += stride) {
-        const int k = k0 + (grp & 3);
-        const bool live = k < count;
-        const int kk = live ? k : count - 1;
-        const int r = r_next;
-        if (k0 + stride < count) r_next = __ldg(idx + min(k + stride, count - 1));
-        // descriptor of the rendered view at this pixel: independent of everything below, issued first
-        const float4 a = __ldg(reinterpret_cast<const float4*>(g1c + ((size_t)b * N + kk) * GC) + cg);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const int r = __ldg(idx + k);
         const int Y = r / W, X = r - Y * W;
         const int y = Y >> 3, i = Y & 7, x = X >> 3, j = X & 7;
         const size_t p = ((size_t)b * h + y) * w + x;
-        const float dz = __ldg(dep + r);
-        // convex upsampling (CFNet.py:95-106): softmax over the 9 taps of mask[p][k*64 + i*8 + j]; the 8 lanes of the group
-        // compute it redundantly (same addresses: one request), in the order of upsample_weight_kernel
+        const float dz = __ldg(depth + (size_t)b * N + r);
+        // softmax over the 9 taps of mask[p][t*64 + i*8 + j], in the order of upsample_weight_kernel
         const float* mp = mask + p * 576 + i * 8 + j;
         float mk[9];
         float mx = -INFINITY;
@@ -115,53 +103,95 @@ __global__ void __launch_bounds__(256, 4) upsample_weight_cl_kernel(
             ux += sm * (8.f * fl[t].x);
             uy += sm * (8.f * fl[t].y);
         }
-        const float tx = ux + (float)X, ty = uy + (float)Y;
-        // normalize_coords_grid then grid_sample's align_corners=False un-normalisation (PoseRefiner.py:343)
-        const float gx = 2.f * tx / (float)(W - 1) - 1.f;
-        const float gy = 2.f * ty / (float)(H - 1) - 1.f;
-        const float ix = ((gx + 1.f) * (float)W - 1.f) / 2.f;
-        const float iy = ((gy + 1.f) * (float)H - 1.f) / 2.f;
-        const float fx0 = floorf(ix), fy0 = floorf(iy);
-        const int x0 = (int)fx0, y0 = (int)fy0;
-        const float wnw = (fx0 + 1.f - ix) * (fy0 + 1.f - iy);
-        const float wne = (ix - fx0) * (fy0 + 1.f - iy);
-        const float wsw = (fx0 + 1.f - ix) * (iy - fy0);
-        const float wse = (ix - fx0) * (iy - fy0);
-        const bool xa = x0 >= 0 && x0 < W, xb = x0 + 1 >= 0 && x0 + 1 < W;
-        const bool ya = y0 >= 0 && y0 < H, yb = y0 + 1 >= 0 && y0 + 1 < H;
-        const bool fin = isfinite(ix) && isfinite(iy);
-        const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
-        const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
-        const bool k00 = fin && ya && xa, k01 = fin && ya && xb, k10 = fin && yb && xa, k11 = fin && yb && xb;
-        const float w00 = k00 ? wnw : 0.f, w01 = k01 ? wne : 0.f, w10 = k10 ? wsw : 0.f, w11 = k11 ? wse : 0.f;
-        // four corners: one 128-byte line each, this lane's 4 channels
-        const float4 t00 = __ldg(reinterpret_cast<const float4*>(g2b + (size_t)(yc0 * W + xc0) * GC) + cg);
-        const float4 t01 = __ldg(reinterpret_cast<const float4*>(g2b + (size_t)(yc0 * W + xc1) * GC) + cg);
-        const float4 t10 = __ldg(reinterpret_cast<const float4*>(g2b + (size_t)(yc1 * W + xc0) * GC) + cg);
-        const float4 t11 = __ldg(reinterpret_cast<const float4*>(g2b + (size_t)(yc1 * W + xc1) * GC) + cg);
-        // per channel: v = ((t00 w00 + t01 w01) + t10 w10) + t11 w11 as in upsample_weight_kernel (a discarded corner's
-        // value is replaced by 0 so that a non-finite texel outside the sampled set cannot leak in)
-        auto blend = [&](float c00, float c01, float c10, float c11) {
-            float v = 0.f;
-            v += (k00 ? c00 : 0.f) * w00;
-            v += (k01 ? c01 : 0.f) * w01;
-            v += (k10 ? c10 : 0.f) * w10;
-            v += (k11 ? c11 : 0.f) * w11;
-            return v;
-        };
-        float s = 0.f;
-        s += a.x * blend(t00.x, t01.x, t10.x, t11.x);
-        s += a.y * blend(t00.y, t01.y, t10.y, t11.y);
-        s += a.z * blend(t00.z, t01.z, t10.z, t11.z);
-        s += a.w * blend(t00.w, t01.w, t10.w, t11.w);
-        // the 8 lanes of a group are consecutive lanes: xor 1, 2, 4 stay inside it
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        const float wgt = dz > 0.f ? expf(-fabsf(1.f - s) / sigma) : 0.f;
-        if (cg == 0 && live) {
-            rec[(size_t)b * N + k] = make_float4(tx, ty, wgt, dz);
-            if (weight_dense) weight_dense[(size_t)b * N + r] = wgt;
+        rec[(size_t)b * N + k] = make_float4(ux + (float)X, uy + (float)Y, 0.f, dz);
+    }
+}
+
+// (B) fg_weight_kernel: one lane GROUP (8 lanes, 4 channels each) per listed pixel, FGW_U pixels per group and trip so that a
+//     warp keeps 4 * FGW_U pixels x 5 lines in flight.  Descriptor warp at the target (normalize_coords_grid + grid_sample with
+//     align_corners=False, zeros; PoseRefiner.py:343, projective_ops.py:11-23), similarity and weight exp(-|1 - s| / sigma)
+//     (:344-345).  Writes rec[b][k].z and, on request, scatters the weight into a dense [B][H*W] map.
+constexpr int FGW_U = 2;
+
+__global__ void __launch_bounds__(256, 5) fg_weight_kernel(const float* __restrict__ g1c, const float* __restrict__ g2cl, float sigma, int H,
+                                                           int W, const int* __restrict__ fg_idx, const int* __restrict__ fg_count,
+                                                           float4* __restrict__ rec, float* __restrict__ weight_dense) {
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.y;
+    const int count = fg_count[b];
+    const int N = H * W;
+    const int grp = threadIdx.x >> 3, cg = threadIdx.x & 7;            // 32 groups per block
+    const float* g2b = g2cl + (size_t)b * N * GC;
+    float4* recb = rec + (size_t)b * N;
+    // warp-uniform trip count (the shuffles below need all 32 lanes): a group past the end repeats the last entry and does
+    // not store.  Per trip a block covers 32 * FGW_U consecutive entries.
+    const int stride = gridDim.x * 32 * FGW_U;
+    for (int k0 = blockIdx.x * 32 * FGW_U + (grp & ~3) * FGW_U; k0 < count; k0 += stride) {
+        int kk[FGW_U]; bool live[FGW_U];
+        float4 t[FGW_U], a[FGW_U];
+#pragma unroll
+        for (int u = 0; u < FGW_U; ++u) {
+            const int k = k0 + (grp & 3) * FGW_U + u;
+            live[u] = k < count;
+            kk[u] = live[u] ? k : count - 1;
+            t[u] = recb[kk[u]];                                         // written by fg_target_kernel in the previous launch
+            a[u] = __ldg(reinterpret_cast<const float4*>(g1c + ((size_t)b * N + kk[u]) * GC) + cg);
+        }
+        float4 c00[FGW_U], c01[FGW_U], c10[FGW_U], c11[FGW_U];
+        float w00[FGW_U], w01[FGW_U], w10[FGW_U], w11[FGW_U];
+        bool k00[FGW_U], k01[FGW_U], k10[FGW_U], k11[FGW_U];
+#pragma unroll
+        for (int u = 0; u < FGW_U; ++u) {
+            const float tx = t[u].x, ty = t[u].y;
+            const float gx = 2.f * tx / (float)(W - 1) - 1.f;
+            const float gy = 2.f * ty / (float)(H - 1) - 1.f;
+            const float ix = ((gx + 1.f) * (float)W - 1.f) / 2.f;
+            const float iy = ((gy + 1.f) * (float)H - 1.f) / 2.f;
+            const float fx0 = floorf(ix), fy0 = floorf(iy);
+            // ix may be NaN / inf for a degenerate flow: every comparison false -> zero sample, like grid_sample
+            const bool fin = isfinite(ix) && isfinite(iy);
+            const int x0 = fin ? (int)fmaxf(fminf(fx0, 1e7f), -1e7f) : -100, y0 = fin ? (int)fmaxf(fminf(fy0, 1e7f), -1e7f) : -100;
+            const float wnw = (fx0 + 1.f - ix) * (fy0 + 1.f - iy), wne = (ix - fx0) * (fy0 + 1.f - iy);
+            const float wsw = (fx0 + 1.f - ix) * (iy - fy0), wse = (ix - fx0) * (iy - fy0);
+            const bool xa = x0 >= 0 && x0 < W, xb = x0 + 1 >= 0 && x0 + 1 < W;
+            const bool ya = y0 >= 0 && y0 < H, yb = y0 + 1 >= 0 && y0 + 1 < H;
+            const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
+            const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
+            k00[u] = fin && ya && xa; k01[u] = fin && ya && xb; k10[u] = fin && yb && xa; k11[u] = fin && yb && xb;
+            w00[u] = k00[u] ? wnw : 0.f; w01[u] = k01[u] ? wne : 0.f; w10[u] = k10[u] ? wsw : 0.f; w11[u] = k11[u] ? wse : 0.f;
+            // four corners: one 128-byte line each, this lane's 4 channels
+            c00[u] = __ldg(reinterpret_cast<const float4*>(g2b + (size_t)(yc0 * W + xc0) * GC) + cg);
+            c01[u] = __ldg(reinterpret_cast<const float4*>(g2b + (size_t)(yc0 * W + xc1) * GC) + cg);
+            c10[u] = __ldg(reinterpret_cast<const float4*>(g2b + (size_t)(yc1 * W + xc0) * GC) + cg);
+            c11[u] = __ldg(reinterpret_cast<const float4*>(g2b + (size_t)(yc1 * W + xc1) * GC) + cg);
+        }
+#pragma unroll
+        for (int u = 0; u < FGW_U; ++u) {
+            // per channel: v = ((t00 w00 + t01 w01) + t10 w10) + t11 w11 as in upsample_weight_kernel (a discarded corner's
+            // value is replaced by 0 so that a non-finite texel outside the sampled set cannot leak in)
+            auto blend = [&](float q00, float q01, float q10, float q11) {
+                float v = 0.f;
+                v += (k00[u] ? q00 : 0.f) * w00[u];
+                v += (k01[u] ? q01 : 0.f) * w01[u];
+                v += (k10[u] ? q10 : 0.f) * w10[u];
+                v += (k11[u] ? q11 : 0.f) * w11[u];
+                return v;
+            };
+            float s = 0.f;
+            s += a[u].x * blend(c00[u].x, c01[u].x, c10[u].x, c11[u].x);
+            s += a[u].y * blend(c00[u].y, c01[u].y, c10[u].y, c11[u].y);
+            s += a[u].z * blend(c00[u].z, c01[u].z, c10[u].z, c11[u].z);
+            s += a[u].w * blend(c00[u].w, c01[u].w, c10[u].w, c11[u].w);
+            // the 8 lanes of a group are consecutive lanes: xor 1, 2, 4 stay inside it
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            const float wgt = t[u].w > 0.f ? expf(-fabsf(1.f - s) / sigma) : 0.f;
+            if (cg == 0 && live[u]) {
+                reinterpret_cast<float*>(recb + kk[u])[2] = wgt;
+                if (weight_dense) weight_dense[(size_t)b * N + __ldg(fg_idx + (size_t)b * N + kk[u])] = wgt;
+            }
         }
     }
 }
@@ -210,14 +240,19 @@ int b2p_fgpipe_upsample_weight(const float* flow, const float* mask, const float
     int dev = 0, sms = 0;
     B2P_CUDA(cudaGetDevice(&dev));
     B2P_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    // resident blocks only (each strides over its sample's list): 4 blocks of 256 threads per SM shared by the samples
-    int per_sample = (sms * 4) / B;
-    const int useful = ceil_div(H * W, 32);
-    if (per_sample > useful) per_sample = useful;
-    if (per_sample < 1) per_sample = 1;
-    B2P_CUDA(b2p_launch_pdl(upsample_weight_cl_kernel, dim3((unsigned)per_sample, (unsigned)B), dim3(256), 0, s, flow, mask, (const float*)g1c,
-                            g2_cl_or_null ? g2_cl_or_null : (const float*)g2cl, depth, sigma, H, W, b2p_fg_idx(fg_ws),
-                            b2p_fg_count(fg_ws, B, H, W), rec, weight_dense));
+    const int* fg_idx = b2p_fg_idx(fg_ws);
+    const int* fg_count = b2p_fg_count(fg_ws, B, H, W);
+    // resident blocks only (each strides over its sample's list), shared by the samples
+    int nA = (sms * 6) / B;
+    const int usefulA = ceil_div(H * W, 256);
+    nA = nA > usefulA ? usefulA : (nA < 1 ? 1 : nA);
+    B2P_CUDA(b2p_launch_pdl(fg_target_kernel, dim3((unsigned)nA, (unsigned)B), dim3(256), 0, s, flow, mask, depth, H, W, fg_idx, fg_count, rec));
+    B2P_LAUNCH_CHECK();
+    int nB = (sms * 5) / B;
+    const int usefulB = ceil_div(H * W, 32 * FGW_U);
+    nB = nB > usefulB ? usefulB : (nB < 1 ? 1 : nB);
+    B2P_CUDA(b2p_launch_pdl(fg_weight_kernel, dim3((unsigned)nB, (unsigned)B), dim3(256), 0, s, (const float*)g1c,
+                            g2_cl_or_null ? g2_cl_or_null : (const float*)g2cl, sigma, H, W, fg_idx, fg_count, rec, weight_dense));
     B2P_LAUNCH_CHECK();
     return 0;
 }

@@ -15,7 +15,7 @@ struct OptDesc { const char* name; const char* env; int B2POptions::*field; int 
 const OptDesc kOpts[] = {
     // tensor-core convolution kernel: bit 0 CTA pairs (cta_group::2), bit 1 vertical-tap reuse, bit 2 force the
     // second-generation kernel, bit 4 the chained single-launch update block; 0 = first-generation kernel
-    {"conv_mode", "B200POSE_CONV_MODE", &B2POptions::conv_mode, 3},
+    {"conv_mode", "B200POSE_CONV_MODE", &B2POptions::conv_mode, 19},
     {"fg_list", "B200POSE_FG_LIST", &B2POptions::fg_list, 1},               // LM over the per-call foreground list
     {"fg_pipeline", "B200POSE_FG_PIPELINE", &B2POptions::fg_pipeline, 1},   // compact channels-last upsample+weight + cluster LM
     {"fg_upsample", "B200POSE_FG_UPSAMPLE", &B2POptions::fg_upsample, 0},   // round-1 list-driven upsample kernel (NCHW planes)
@@ -26,6 +26,7 @@ const OptDesc kOpts[] = {
     {"lookup_mode", "B200POSE_LOOKUP_MODE", &B2POptions::lookup_mode, 1},   // 1 = shared-memory window lookup, 0 = round-1 kernel
     {"pool_mode", "B200POSE_POOL_MODE", &B2POptions::pool_mode, 1},         // 1 = three pyramid levels in one pass
     {"lm_debug", "B200POSE_LM_DEBUG", &B2POptions::lm_debug, 0},            // 1 = drop the fp64 contraction (timing A/B only)
+    {"chain_rings", "B200POSE_CHAIN_RINGS", &B2POptions::chain_rings, 24},  // chained launch: 10 * activation slots + weight slots
 };
 constexpr int kNumOpts = (int)(sizeof(kOpts) / sizeof(kOpts[0]));
 

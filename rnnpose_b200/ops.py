@@ -18,6 +18,7 @@ WEIGHT_KEYS: List[str] = [
 ]
 FLAG_EXACT_FP32 = 0      # CUDA-core fp32 convolutions
 FLAG_TENSOR_CORES = 1    # tcgen05 convolutions on fp16 hi/lo split operands (fp32-level accuracy)
+FLAG_GEO2_CHANNELS_LAST = 2   # refine_iters: geofea2 is [B, H*W, 32] (what zoom_crop(channels_last=True) writes)
 DEFAULT_FLAGS = FLAG_TENSOR_CORES
 LM_LMBDA = 1e-4   # reference config/default.py:54
 EP_LMBDA = 100.0  # reference config/default.py:55
@@ -253,6 +254,36 @@ def lm_solve(depth: torch.Tensor, target: torch.Tensor, weight: torch.Tensor, K:
                                    B, H, W, float(depth_offset), n_steps, float(ep_lmbda), float(lm_lmbda), _p(Ho), _p(bo), _p(do),
                                    ws.data_ptr(), nb, _stream()), "b200pose_lm_solve")
     return (G, Ho, bo, do) if taps else G
+
+
+def zoom_crop(pc_depth: torch.Tensor, K: torch.Tensor, T: torch.Tensor, image: Optional[torch.Tensor],
+              geofea: Optional[torch.Tensor], out_hw, margin_ratio: float = 0.4, channels_last: bool = False,
+              want_theta: bool = False):
+    """Device-side PoseRefiner.gen_zoom_crop_grids + the two grid_sample crops (b200pose_zoom_crop).  pc_depth [B,H,W]
+    (foreground = > 0), K [B,3,3], T [B,4,4], image [B,Ci,H,W], geofea [B,Cg,H,W].  Returns dict(image_crop, geofea_crop
+    ([B,Cg,Hc,Wc] or, channels_last, [B,Hc*Wc,32]), K_crop, theta)."""
+    _need_cuda()
+    L = _lib.lib()
+    _chk(pc_depth, "pc_depth"); _chk(K, "K"); _chk(T, "T")
+    B, H, W = pc_depth.shape
+    Hc, Wc = int(out_hw[0]), int(out_hw[1])
+    dev = pc_depth.device
+    Ci = Cg = 0
+    ic = gc = None
+    if image is not None:
+        _chk(image, "image"); Ci = image.shape[1]
+        ic = torch.empty(B, Ci, Hc, Wc, dtype=torch.float32, device=dev)
+    if geofea is not None:
+        _chk(geofea, "geofea"); Cg = geofea.shape[1]
+        gc = torch.empty((B, Hc * Wc, Cg) if channels_last else (B, Cg, Hc, Wc), dtype=torch.float32, device=dev)
+    Kc = torch.empty(B, 3, 3, dtype=torch.float32, device=dev)
+    th = torch.empty(B, 2, 3, dtype=torch.float32, device=dev) if want_theta else None
+    nb = L.b200pose_zoom_crop_workspace_bytes(B)
+    ws = _ws(nb, dev)
+    _lib.check(L.b200pose_zoom_crop(pc_depth.data_ptr(), K.data_ptr(), T.data_ptr(), _p(image), _p(geofea), B, Ci, Cg, H, W, Hc, Wc,
+                                    float(margin_ratio), 1 if channels_last else 0, _p(ic), _p(gc), Kc.data_ptr(), _p(th),
+                                    ws.data_ptr(), nb, _stream()), "b200pose_zoom_crop")
+    return dict(image_crop=ic, geofea_crop=gc, K_crop=Kc, theta=th)
 
 
 def cholesky_solve(H: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

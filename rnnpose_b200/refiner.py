@@ -8,9 +8,10 @@ geofea_3d, geofea_2d)`` and the same return dict (reference model/PoseRefiner.py
 What runs where:
   * the OUTER render loop (reference PoseRefiner.py:239-313) stays PyTorch: it calls the injected renderer and the
     injected feature encoder (both out of scope) and builds the zoom-crop.  The crop geometry of
-    ``gen_zoom_crop_grids`` / ``get_affine_transformation`` (reference :145-213) is restated with device-side torch
-    ops (bounding box by reductions, closed-form axis-aligned affine), removing the reference's numpy/cv2 host
-    round-trip (SURVEY section 8(f)-1);
+    ``gen_zoom_crop_grids`` / ``get_affine_transformation`` (reference :145-213) and the two grid_sample crops run in the
+    library's zoom-crop kernels (``ops.zoom_crop``: bounding box by atomics, closed-form axis-aligned affine, fused
+    resample), removing the reference's numpy/cv2 host round-trip; ``zoom_crop_params`` below is
+    the same geometry in torch ops, kept as a checker;
   * the INNER loop (reference :315-362) is one call into libb200pose.so (``ops.refine_iters``), natively batched
     (the reference only supports batch size 1, SURVEY finding 1).
 Inference only (the reference's training loss is out of scope).
@@ -142,6 +143,14 @@ class PoseRefiner(nn.Module):
         b = get_cfg("BASIC")
         return tuple(b.render_image_size), tuple(b.zoom_crop_size)
 
+    def _sigma_value(self) -> float:
+        """sigma as a host scalar, read back from the device only when the parameter changes (no sync per render iteration)."""
+        p = self.sigma[0]
+        key = (p.data_ptr(), p._version)
+        if getattr(self, "_sigma_key", None) != key:
+            self._sigma_cache, self._sigma_key = float(p.detach()), key
+        return self._sigma_cache
+
     def packed_weights(self) -> torch.Tensor:
         sd = self.cf_net.update_block.state_dict()
         key = tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in sd.items())
@@ -172,17 +181,19 @@ class PoseRefiner(nn.Module):
             Tij = Ti * Ti.inv()                                           # legacy "identity" (:243-244)
             T_mat = Ti.matrix().detach().squeeze(1)
             pc_depth = self.renderer.render_pointcloud(obj_cls, T=T_mat, K=intrinsics.detach(), render_image_size=render_size)
-            B, C = pc_depth.shape[:2]
-            theta, K_crop = zoom_crop_params(pc_depth > 0, intrinsics.detach(), T_mat, (Hc, Wc))
-            grids = F.affine_grid(theta, torch.Size([B, C, Hc, Wc]))
+            B = pc_depth.shape[0]
+            # zoom-crop on device (reference :145-218,:287,:292): foreground box, crop intrinsics and both crops in one
+            # entry; the descriptors leave channels-last, which is what the loop's foreground pipeline reads
+            cl = geofea_2d.shape[1] == 32 and ops.get_option("fg_list") != 0 and ops.get_option("fg_pipeline") != 0
+            zc = ops.zoom_crop(pc_depth[:, 0].contiguous().float(), intrinsics.detach().float().contiguous(), T_mat.float().contiguous(),
+                               image.float().contiguous(), geofea_2d.float().contiguous(), (Hc, Wc), channels_last=cl)
+            K_crop, image_crop, geofea2_crop = zc["K_crop"], zc["image_crop"], zc["geofea_crop"]
             attr = torch.cat([fea_3d, geofea_3d], dim=-1)
             color, depth = self.renderer(obj_cls, attr, T=T_mat, K=K_crop.detach(), render_image_size=(Hc, Wc), near=0.1,
                                          far=6, render_tex=True)
             depth = depth.clone(); depth[depth == -1] = 0                  # (:138)
             syn_img, cfea, geofea1 = torch.split(color, [3, fea_3d.shape[-1], geofea_3d.shape[-1]], dim=1)
             cfea = cfea * 0.1                                              # (:283)
-            image_crop = F.grid_sample(image, grids)
-            geofea2_crop = F.grid_sample(geofea_2d, grids)
             syn_depth = self.renderer.render_depth(obj_cls, T=T_mat, K=K_crop.detach(), render_image_size=(Hc, Wc),
                                                    near=0.1, far=6)         # legacy second render (:296-304)
             syn_imgs += [syn_img, image_crop]
@@ -191,9 +202,10 @@ class PoseRefiner(nn.Module):
             if self._ws is None or self._ws.key != (B, Hc, Wc):
                 self._ws = ops.RefineWorkspace(B, Hc, Wc, G.device)
             res = ops.refine_iters(packed, feats1.float().contiguous(), feats2.float().contiguous(), cfea.contiguous(),
-                                   geofea1.contiguous(), geofea2_crop.contiguous(), syn_depth[:, 0].contiguous(),
-                                   K_crop.contiguous(), G, float(self.sigma[0]), n_iters, n_lm, workspace=self._ws,
-                                   want_flows=True, want_weight=True, flags=self.flags)
+                                   geofea1.contiguous(), geofea2_crop, syn_depth[:, 0].contiguous(),
+                                   K_crop, G, self._sigma_value(), n_iters, n_lm, workspace=self._ws,
+                                   want_flows=True, want_weight=True,
+                                   flags=self.flags | (ops.FLAG_GEO2_CHANNELS_LAST if cl else 0))
             Tij = SE3Sequence(matrix=G[:, None])
             if first_flow is None:
                 first_flow = [res["flow_first"]]
@@ -206,6 +218,7 @@ class PoseRefiner(nn.Module):
         return {
             "Tij": Tij, "Ti_pred": Ti, "intrinsics": intrinsics, "flow": first_flow, "vmask": syn_depth > 0,
             "weight": weight[:, None, None], "syn_depth": syn_depths,
-            "syn_img": syn_imgs + [image_crop, cfea[:, :3] * 10, geofea1[:, :3], geofea2_crop[:, :3]],
+            "syn_img": syn_imgs + [image_crop, cfea[:, :3] * 10, geofea1[:, :3],
+                        (geofea2_crop.view(B, Hc, Wc, -1).permute(0, 3, 1, 2) if cl else geofea2_crop)[:, :3]],
             "Tij_gt": Tij_gt,
         }

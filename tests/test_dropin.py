@@ -91,3 +91,48 @@ def test_pose_refiner_dropin_matches_reference(flags):
         assert err < 1e-4
         assert out["weight"].shape == (1, 1, 1, *CROP_HW) and out["flow"][0].shape == (1, 2, *CROP_HW)
         assert len(out["syn_depth"]) == n_render * n_iters and len(out["Tij_gt"]) == n_render * n_iters
+
+
+@pytest.mark.gpu
+def test_zoom_crop_kernel_matches_reference_cv2_path():
+    """b200pose_zoom_crop (bounding box + crop intrinsics + both resampled crops on device) against the crop parameters the
+    executed reference computed with numpy + cv2 (dropin_2x2x1.npz) and against F.affine_grid + F.grid_sample on the same
+    theta; NCHW and channels-last descriptor outputs; natively batched; an empty foreground gives the reference's zero box."""
+    from rnnpose_b200 import ops
+    g = golden("dropin_2x2x1.npz")
+    dev = torch.device("cuda:0")
+    idxs = [int(i) for i in g["idxs"]]
+    scs = [scene(i) for i in idxs]
+    ins = [inputs(sc) for sc in scs]
+    image = torch.cat([i[0] for i in ins]).to(dev); geo2 = torch.cat([i[1] for i in ins]).to(dev)
+    K = torch.cat([i[2] for i in ins]).to(dev); T0 = torch.cat([i[3][:, 0] for i in ins]).to(dev)
+    pcs = torch.cat([S.AnalyticRenderer([sc]).render_pointcloud(None, T=i[3][:, 0], K=i[2], render_image_size=IMG_HW) for sc, i in zip(scs, ins)])
+    pc = pcs[:, 0].contiguous().to(dev)
+    out = ops.zoom_crop(pc, K, T0, image, geo2, CROP_HW, want_theta=True)
+    for k in range(len(idxs)):
+        torch.testing.assert_close(out["K_crop"][k].cpu(), torch.from_numpy(g["K_crop"][k, 0]), rtol=1e-5, atol=1e-3)
+    grid = F.affine_grid(out["theta"], torch.Size([len(idxs), 1, *CROP_HW]), align_corners=False)
+    corners = grid[:, [0, 0, -1], [0, -1, 0]].cpu()
+    torch.testing.assert_close(corners, torch.from_numpy(g["theta"][:, 0]), rtol=1e-5, atol=1e-5)
+    # geometry also equals the torch restatement used as checker
+    theta_t, Kc_t = zoom_crop_params(pc[:, None] > 0, K, T0, CROP_HW)
+    torch.testing.assert_close(out["theta"], theta_t, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out["K_crop"], Kc_t, rtol=1e-5, atol=1e-3)
+    # the resampled crops
+    ref_img = F.grid_sample(image, grid, align_corners=False); ref_geo = F.grid_sample(geo2, grid, align_corners=False)
+    torch.testing.assert_close(out["image_crop"], ref_img, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(out["geofea_crop"], ref_geo, rtol=1e-4, atol=2e-5)
+    cl = ops.zoom_crop(pc, K, T0, image, geo2, CROP_HW, channels_last=True)
+    B = len(idxs)
+    assert cl["geofea_crop"].shape == (B, CROP_HW[0] * CROP_HW[1], 32)
+    assert torch.equal(cl["geofea_crop"].view(B, *CROP_HW, 32).permute(0, 3, 1, 2), out["geofea_crop"])
+    assert torch.equal(cl["image_crop"], out["image_crop"]) and torch.equal(cl["K_crop"], out["K_crop"])
+    # an output size that is not a multiple of the 64-pixel block, and an empty foreground in sample 1
+    pc2 = pc.clone(); pc2[1] = 0
+    odd = ops.zoom_crop(pc2, K, T0, image, geo2, (50, 70), want_theta=True, channels_last=True)
+    th2, Kc2 = zoom_crop_params(pc2[:, None] > 0, K, T0, (50, 70))
+    torch.testing.assert_close(odd["theta"], th2, rtol=1e-5, atol=1e-6)
+    assert torch.isfinite(odd["K_crop"][0]).all()
+    grid2 = F.affine_grid(odd["theta"][:1], torch.Size([1, 1, 50, 70]), align_corners=False)
+    torch.testing.assert_close(odd["geofea_crop"][0].view(50, 70, 32).permute(2, 0, 1), F.grid_sample(geo2[:1], grid2, align_corners=False)[0],
+                               rtol=1e-4, atol=2e-5)

@@ -256,7 +256,8 @@ def test_refine_foreground_list_matches_dense_kernels(ops, packed, libopt):
         assert torch.equal(pipe["G"][1].cpu(), G0[1])
         assert (pipe["G"].cpu() - dense["G"].cpu()).abs().max().item() < 1e-6
         if kw:
-            torch.testing.assert_close(pipe["weight"].cpu(), dense["weight"].cpu(), rtol=0, atol=2e-6)
+            # (the weights of the LAST iteration sit behind two LM rounds whose poses differ by ~1e-7 between the variants)
+            torch.testing.assert_close(pipe["weight"].cpu(), dense["weight"].cpu(), rtol=0, atol=2e-5)
             assert torch.equal(pipe["flow_first"].cpu(), dense["flow_first"].cpu())
             torch.testing.assert_close(pipe["flow_last"].cpu(), dense["flow_last"].cpu(), rtol=0, atol=1e-4)   # poses differ ~1e-7
     libopt("fg_pipeline", 0); d32 = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, flags=0)
@@ -276,21 +277,33 @@ def test_refine_foreground_list_matches_dense_kernels(ops, packed, libopt):
     assert (fg["G"].cpu() - ref["G"]).abs().max().item() < SE3_TOL
 
 
-@pytest.mark.skipif(os.environ.get("B200POSE_TEST_EXPERIMENTAL") != "1",
-                    reason="conv_chain_kernel (B200POSE_CONV_MODE bit 4) has not been run on hardware yet; opt in with "
-                           "B200POSE_TEST_EXPERIMENTAL=1")
-def test_refine_chained_convolutions_experimental(ops, packed, libopt):
-    """The eleven convolutions of a pass in one persistent launch with tile-level dependencies (mode 19) against the
-    layer-by-layer default at the bench shape (the chain needs a machine-filling batch)."""
+@pytest.mark.parametrize("rings", [24, 33], ids=["rings2+4", "rings3+3"])
+def test_refine_chained_convolutions(ops, packed, libopt, rings):
+    """The eleven convolutions of a pass in one persistent launch with tile-level dependencies (conv_mode 19, the default)
+    against the layer-by-layer launches (conv_mode 3) at the bench shape (the chain needs a machine-filling batch), for both
+    shared-memory ring geometries."""
     H, W, B = 240, 320, 32
     uniq = S.make_batch([0, 1, 2, 3], H, W, with_images=False)
     rep = {k: v.repeat(8, *([1] * (v.dim() - 1))) for k, v in uniq.items() if k != "diameter"}
     f1 = S.hash_features((4, 256, H // 8, W // 8), 71).repeat(8, 1, 1, 1); f2 = S.hash_features((4, 256, H // 8, W // 8), 72).repeat(8, 1, 1, 1)
     G0 = torch.eye(4)[None].repeat(B, 1, 1)
+    libopt("conv_mode", 3)
     ref = run_gpu(ops, packed, f1, f2, rep, G0, 4, 3)["G"].cpu()
-    libopt("conv_mode", 19)
+    libopt("conv_mode", 19); libopt("chain_rings", rings)
     got = run_gpu(ops, packed, f1, f2, rep, G0, 4, 3)["G"].cpu()
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max().item() < 1e-6
     for k in range(4, B):
         assert torch.equal(got[k], got[k % 4])
+    # an odd number of pixel tiles (99 x 3 = 297: the last CTA pair has a dummy half) and a 480x640 batch
+    for (Bo, Ho, Wo) in ((99, 128, 160), (10, 480, 640)):
+        u2 = S.make_batch([0, 1], Ho, Wo, with_images=False)
+        r2 = {k: v.repeat((Bo + 1) // 2, *([1] * (v.dim() - 1)))[:Bo].contiguous() for k, v in u2.items() if k != "diameter"}
+        g1 = S.hash_features((2, 256, Ho // 8, Wo // 8), 73).repeat((Bo + 1) // 2, 1, 1, 1)[:Bo].contiguous()
+        g2 = S.hash_features((2, 256, Ho // 8, Wo // 8), 74).repeat((Bo + 1) // 2, 1, 1, 1)[:Bo].contiguous()
+        Go = torch.eye(4)[None].repeat(Bo, 1, 1)
+        libopt("conv_mode", 3)
+        a = run_gpu(ops, packed, g1, g2, r2, Go, 2, 2)["G"].cpu()
+        libopt("conv_mode", 19)
+        b = run_gpu(ops, packed, g1, g2, r2, Go, 2, 2)["G"].cpu()
+        assert (a - b).abs().max().item() < 1e-6 and torch.equal(b[0], b[2])

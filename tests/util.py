@@ -12,7 +12,7 @@ def golden(name):
 
 
 def load_update_weights():
-    """Shipped RAFT update-block weights (reference weights/gru_update.pth, a data file consumed by the
-    kernels) with the ``update_block.`` prefix stripped."""
-    sd = torch.load(os.path.join(GOLDEN, "weights", "gru_update.pth"), map_location="cpu")
-    return {k[len("update_block."):]: v.float() for k, v in sd.items()}
+    """Shipped RAFT update-block weights (rnnpose_b200/weights/gru_update.pth = reference weights/gru_update.pth, a data
+    file consumed by the kernels) with the ``update_block.`` prefix stripped."""
+    from rnnpose_b200.assets import load_update_weights as _l
+    return _l()

@@ -13,7 +13,7 @@ ops.set_option("conv_debug", 16)
 CHAIN = (ops.get_option("conv_mode") & 16) != 0
 
 dev = torch.device("cuda:0")
-sd = torch.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "weights", "gru_update.pth"), map_location="cpu")
+sd = torch.load(os.path.join(os.path.dirname(__file__), "..", "rnnpose_b200", "weights", "gru_update.pth"), map_location="cpu")
 packed = ops.pack_weights({k[len("update_block."):]: v.float() for k, v in sd.items()}, dev)
 H, W, B = 240, 320, 32
 f1 = torch.randn(B, 256, H // 8, W // 8, device=dev); f2 = torch.randn(B, 256, H // 8, W // 8, device=dev)

@@ -18,7 +18,7 @@ ap.add_argument("--layers", default="0,1,3,4,5,6,7,8,9,10")
 ap.add_argument("--reps", type=int, default=20)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-sd = torch.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "weights", "gru_update.pth"), map_location="cpu")
+sd = torch.load(os.path.join(os.path.dirname(__file__), "..", "rnnpose_b200", "weights", "gru_update.pth"), map_location="cpu")
 packed = ops.pack_weights({k[len("update_block."):]: v.float() for k, v in sd.items()}, dev)
 B, h, w = a.batch, 30, 40
 P = B * h * w

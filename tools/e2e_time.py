@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rnnpose_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")
-sd = torch.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "weights", "gru_update.pth"), map_location="cpu")
+sd = torch.load(os.path.join(os.path.dirname(__file__), "..", "rnnpose_b200", "weights", "gru_update.pth"), map_location="cpu")
 packed = ops.pack_weights({k[len("update_block."):]: v.float() for k, v in sd.items()}, dev)
 H, W, B = 240, 320, 32
 g = torch.Generator().manual_seed(0)

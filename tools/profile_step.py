@@ -18,7 +18,7 @@ a = ap.parse_args()
 H, W, B = 240, 320, a.batch
 dev = torch.device("cuda:0")
 g = torch.Generator(device="cpu").manual_seed(0)
-sd = torch.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "weights", "gru_update.pth"), map_location="cpu")
+sd = torch.load(os.path.join(os.path.dirname(__file__), "..", "rnnpose_b200", "weights", "gru_update.pth"), map_location="cpu")
 packed = ops.pack_weights({k[len("update_block."):]: v.float() for k, v in sd.items()}, dev)
 f1 = torch.randn(B, 256, H // 8, W // 8, device=dev); f2 = torch.randn(B, 256, H // 8, W // 8, device=dev)
 ctx = 0.1 * torch.randn(B, 256, H, W, device=dev)
