@@ -222,6 +222,22 @@ int b200pose_zoom_crop(const float* pc_depth, const float* K, const float* T, co
                        float* image_crop, float* geofea_crop, float* K_crop, float* theta,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- f2: RAFT feature encoder ---------------------------------------------------------------------
+ * Replaces ImageFeaEncoder.forward (model/CFNet.py:26-49) = BasicEncoder(output_dim 256, norm_fn 'instance') of
+ * thirdparty/raft/extractor.py:118-232 on both images at once: 7x7 s2 stem, six residual blocks with InstanceNorm + ReLU
+ * (two of them stride 2 with a 1x1 down-sampling branch), 1x1 output convolution; inputs are normalised as
+ * 2 (x / 255) - 1 inside (CFNet.py:42-43).  fp32-equivalent arithmetic (the stem in fp32 FFMA, the other fifteen
+ * convolutions on tcgen05 with fp16 hi/lo split operands).
+ * `tensors` = 32 device pointers in state-dict order of weights/img_fea_enc.pth (fnet.conv1, fnet.layer1.0.conv1,
+ * .conv2, fnet.layer1.1.*, fnet.layer2.0.conv1, .conv2, .downsample.0, fnet.layer2.1.*, fnet.layer3.0.*, fnet.layer3.1.*,
+ * fnet.conv2; each weight then bias).  image1, image2: [B,3,H,W] (H, W multiples of 8, >= 16); fmap1, fmap2: [B,256,H/8,W/8].  */
+#define B200POSE_NUM_ENCODER_TENSORS 32
+size_t b200pose_encoder_packed_weights_bytes(void);
+int b200pose_encoder_pack_weights(const float* const* tensors_host, void* packed, void* stream);
+size_t b200pose_encoder_workspace_bytes(int B, int H, int W);
+int b200pose_image_encoder(const void* packed_weights, const float* image1, const float* image2, int B, int H, int W,
+                           float* fmap1, float* fmap2, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a14: the fused inner loop ----------------------------------------------------------------
  * Replaces the body of `for i in range(cfg.ITER_COUNT)` in PoseRefiner.forward
  * (model/PoseRefiner.py:315-362) for one render iteration, natively batched.

@@ -35,6 +35,10 @@ SIGNATURES = {
     "b200pose_conv_layer_info": (_i, [_i] + [C.POINTER(_i)] * 5),
     "b200pose_conv_layer": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "b200pose_upsample_weight": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "b200pose_encoder_packed_weights_bytes": (_sz, []),
+    "b200pose_encoder_pack_weights": (_i, [C.POINTER(_vp), _vp, _vp]),
+    "b200pose_encoder_workspace_bytes": (_sz, [_i, _i, _i]),
+    "b200pose_image_encoder": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200pose_zoom_crop_workspace_bytes": (_sz, [_i]),
     "b200pose_zoom_crop": (_i, [_vp] * 5 + [_i] * 7 + [_f, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200pose_pose_metrics_workspace_bytes": (_sz, [_i, _i]),

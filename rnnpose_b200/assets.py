@@ -15,3 +15,9 @@ def load_update_weights() -> Dict[str, torch.Tensor]:
     """cf_net.update_block state dict with the ``update_block.`` prefix stripped (keys 'encoder.convc1.weight', ...)."""
     sd = torch.load(os.path.join(WEIGHTS_DIR, "gru_update.pth"), map_location="cpu")
     return {k[len("update_block."):]: v.float() for k, v in sd.items()}
+
+
+def load_encoder_weights() -> Dict[str, torch.Tensor]:
+    """ImageFeaEncoder state dict (keys 'fnet.conv1.weight', ...), reference weights/img_fea_enc.pth."""
+    sd = torch.load(os.path.join(WEIGHTS_DIR, "img_fea_enc.pth"), map_location="cpu")
+    return {k: v.float() for k, v in sd.items()}

@@ -509,6 +509,26 @@ int b200pose_upsample_weight(const float* flow, const float* mask, const float* 
                                (cudaStream_t)stream);
 }
 
+size_t b200pose_encoder_packed_weights_bytes(void) { return b2p_encoder_packed_bytes(); }
+
+int b200pose_encoder_pack_weights(const float* const* tensors_host, void* packed, void* stream) {
+    if (!tensors_host || !packed) return B200POSE_E_NULL;
+    if ((uintptr_t)packed & 1023) return B200POSE_E_WORKSPACE;
+    for (int i = 0; i < B200POSE_NUM_ENCODER_TENSORS; ++i)
+        if (!tensors_host[i]) return B200POSE_E_NULL;
+    return b2p_encoder_pack(tensors_host, packed, (cudaStream_t)stream);
+}
+
+size_t b200pose_encoder_workspace_bytes(int B, int H, int W) { return b2p_encoder_ws_bytes(B, H, W); }
+
+int b200pose_image_encoder(const void* packed_weights, const float* image1, const float* image2, int B, int H, int W, float* fmap1,
+                           float* fmap2, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!packed_weights || !image1 || !image2 || !fmap1 || !fmap2 || !workspace) return B200POSE_E_NULL;
+    if (B < 1 || H < 16 || W < 16 || (H % 8) || (W % 8)) return B200POSE_E_SHAPE;
+    if (((uintptr_t)workspace & 1023) || workspace_bytes < b2p_encoder_ws_bytes(B, H, W)) return B200POSE_E_WORKSPACE;
+    return b2p_image_encoder(packed_weights, image1, image2, B, H, W, fmap1, fmap2, workspace, (cudaStream_t)stream);
+}
+
 size_t b200pose_zoom_crop_workspace_bytes(int B) { return b2p_zoom_crop_ws_bytes(B); }
 
 int b200pose_zoom_crop(const float* pc_depth, const float* K, const float* T, const float* image, const float* geofea, int B, int Ci,

@@ -160,6 +160,7 @@ struct UmmaConvArgs {
     int side_tiled;            // zbuf / hbuf / pre use the tiled side-buffer layout (b2p_tiled_index)
     int out_tiled;             // EPI_SCALE: out_f32 is a tiled side buffer with out_f32_pitch channels
     int b_batched;             // weights differ per sample: 3rd weight-map coordinate = sample index (1x1 only)
+    int stride, in_h, in_w;    // stride 2 (encoder): h, w are the OUTPUT dimensions, in_h x in_w the input map (0: same as h, w)
 };
 int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s);
 // several layers in one persistent launch with tile-level dependencies (conv_chain_kernel, conv_umma.cu)
@@ -223,6 +224,11 @@ const float4* b2p_fgpipe_records(const void* ws, int B, int H, int W);
 int b2p_fgpipe_prepare(const float* g1, const float* g2, int g2_is_cl, int B, int H, int W, const void* fg_ws, void* ws, cudaStream_t s);
 int b2p_fgpipe_upsample_weight(const float* flow, const float* mask, const float* g2_cl_or_null, const float* depth, float sigma, int B,
                                int H, int W, const void* fg_ws, void* ws, float* weight_dense, cudaStream_t s);
+size_t b2p_encoder_packed_bytes();
+int b2p_encoder_pack(const float* const* t, void* packed, cudaStream_t s);
+size_t b2p_encoder_ws_bytes(int B, int H, int W);
+int b2p_image_encoder(const void* packed, const float* image1, const float* image2, int B, int H, int W, float* fmap1, float* fmap2,
+                      void* ws, cudaStream_t s);
 size_t b2p_zoom_crop_ws_bytes(int B);
 int b2p_zoom_crop(const float* pc_depth, const float* K, const float* T, const float* image, const float* geo, int B, int Ci, int Cg,
                   int H, int W, int Hc, int Wc, float margin_ratio, int geo_channels_last, float* image_crop, float* geo_crop,

@@ -66,6 +66,7 @@ struct UmmaConvParams {
     int out_tiled;                     // EPI_SCALE output is such a side buffer (the GRU pre-sum GEMMs)
     int dbg_layer;                     // row of g_conv_dbg (layer id + 1)
     int n_reverse;                     // conv_chain_kernel: list the layer's N tiles last-to-first
+    int stride;                        // convolution stride (1, or 2 for the encoder's down-sampling layers; gen-1 / gen-2 without tap reuse)
     int debug;                         // timing experiments only (results are garbage): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue
 };
 
@@ -419,9 +420,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
             const uint32_t tx_bytes = 2u * A_TILE_BYTES + 2u * (uint32_t)n_cnt * 128u;
             int tap = 0;
             for (int ky = 0; ky < p.kh; ++ky) {
-                const int ys = y0 + ky - (p.kh >> 1);
+                const int ys = y0 * p.stride + ky - (p.kh >> 1);
                 for (int kx = 0; kx < p.kw; ++kx, ++tap) {
-                    const int xs = x0 + kx - (p.kw >> 1);
+                    const int xs = x0 * p.stride + kx - (p.kw >> 1);
                     const int b2 = p.b_batched ? bimg : tap;
                     for (int a = 0; a < p.n_active; ++a) {
                         const int cc = p.chunk_list[a];
@@ -675,9 +676,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
             const uint32_t b_tx = (uint32_t)NCTA * 2u * (uint32_t)b_rows * 128u;
             const int nb0 = n0 + (int)rank * b_rows;
             for (int kyo = 0; kyo < outer_taps; ++kyo) {
-                const int ys = y0 + kyo - (p.kh >> 1);
+                const int ys = y0 * p.stride + kyo - (p.kh >> 1);
                 for (int kx = 0; kx < p.kw; ++kx) {
-                    const int xs = x0 + kx - (p.kw >> 1);
+                    const int xs = x0 * p.stride + kx - (p.kw >> 1);
                     for (int a = 0; a < p.n_active; ++a) {
                         const int cc = p.chunk_list[a];
                         const int seg = cc >= p.seg0_chunks ? 1 : 0;
@@ -1161,14 +1162,16 @@ int cached_map(CUtensorMap* m, const MapKey& key, Make make) {
     return 0;
 }
 
-int make_act_map(CUtensorMap* m, const __half* base, int C, int pitch, int B, int h, int w, int box_rows = TILE_ROWS) {
-    return cached_map(m, MapKey{base, {C, pitch, B, h, w, -box_rows}}, [&](CUtensorMap* out) -> int {
+// h, w: dimensions of the INPUT map; stride > 1: the box covers stride x as many input pixels per dimension and TMA keeps
+// every stride-th one (elementStrides), so the tile in shared memory is always box_rows x 8 pixels.
+int make_act_map(CUtensorMap* m, const __half* base, int C, int pitch, int B, int h, int w, int box_rows = TILE_ROWS, int stride = 1) {
+    return cached_map(m, MapKey{base, {C, pitch, B, h, w, -box_rows - 1000 * (stride - 1)}}, [&](CUtensorMap* out) -> int {
         EncodeTiledFn enc = get_encode();
         if (!enc) return (int)cudaErrorNotSupported;
         cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
         cuuint64_t gstr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)w * pitch * 2, (cuuint64_t)h * w * pitch * 2};
-        cuuint32_t box[4] = {BKC, TILE_COLS, (cuuint32_t)box_rows, 1};
-        cuuint32_t est[4] = {1, 1, 1, 1};
+        cuuint32_t box[4] = {BKC, (cuuint32_t)(TILE_COLS * stride), (cuuint32_t)(box_rows * stride), 1};
+        cuuint32_t est[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
@@ -1232,6 +1235,10 @@ int launch_conv_umma2(const UmmaConvArgs& a, UmmaConvParams& p, int ncta, bool r
     const int taps = a.kh * a.kw;
     // rings: one activation slot serves a_taps weight slots; without reuse the two rings advance together
     const int b_slot = 2 * (a.n_tile / ncta) * 128, budget = 222 * 1024;
+    const int st = a.stride > 1 ? a.stride : 1;
+    const int in_h = a.in_h > 0 ? a.in_h : a.h, in_w = a.in_w > 0 ? a.in_w : a.w;
+    p.stride = st;
+    if (st > 1) reuse_v = false;                       // the halo-box trick needs consecutive input rows
     p.a_taps = reuse_v ? a.kh : 1;
     p.a_rows = TILE_ROWS + p.a_taps - 1;
     p.ring_a = 2;
@@ -1246,8 +1253,8 @@ int launch_conv_umma2(const UmmaConvArgs& a, UmmaConvParams& p, int ncta, bool r
     if (p.ring_a < 2 || p.ring_b < 2) return -1;
     for (int g = 0; g < 2; ++g) {
         if (a.seg_c[g] == 0) { p.a_hi[g] = p.a_hi[0]; p.a_lo[g] = p.a_lo[0]; continue; }
-        if ((rc = make_act_map(&p.a_hi[g], a.seg_hi[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.a_rows))) return rc;
-        if ((rc = make_act_map(&p.a_lo[g], a.seg_lo[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.a_rows))) return rc;
+        if ((rc = make_act_map(&p.a_hi[g], a.seg_hi[g], a.seg_c[g], a.seg_pitch[g], a.B, in_h, in_w, p.a_rows, st))) return rc;
+        if ((rc = make_act_map(&p.a_lo[g], a.seg_lo[g], a.seg_c[g], a.seg_pitch[g], a.B, in_h, in_w, p.a_rows, st))) return rc;
     }
     if ((rc = make_wgt_map(&p.b_hi, a.w_hi, a.cin_pad, a.cout_pad, taps, a.n_tile / ncta))) return rc;
     if ((rc = make_wgt_map(&p.b_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, a.n_tile / ncta))) return rc;
@@ -1313,6 +1320,7 @@ int fill_chain_layer(const UmmaConvArgs& a, UmmaConvParams& p) {
     p.out_hi = a.out_hi; p.out_lo = a.out_lo; p.out_h_pitch = a.out_h_pitch;
     p.zbuf = a.zbuf; p.hbuf = a.hbuf;
     p.side_tiled = a.side_tiled; p.out_tiled = a.out_tiled;
+    p.stride = 1;
     p.debug = b2p_options().conv_debug & 16;             // clock counters only; the drop-a-stage experiments are gen-2 only
     p.dbg_layer = a.layer_id >= 0 && a.layer_id < 11 ? a.layer_id + 1 : 0;
     p.m_tiles = a.B * p.tiles_x * p.tiles_y;
@@ -1328,11 +1336,14 @@ int b2p_launch_conv_umma(const UmmaConvArgs& a, cudaStream_t s) {
     UmmaConvParams p;
     memset(&p, 0, sizeof(p));
     int rc;
+    const int st = a.stride > 1 ? a.stride : 1;
+    const int in_h = a.in_h > 0 ? a.in_h : a.h, in_w = a.in_w > 0 ? a.in_w : a.w;
     for (int g = 0; g < 2; ++g) {
         if (a.seg_c[g] == 0) { p.a_hi[g] = p.a_hi[0]; p.a_lo[g] = p.a_lo[0]; continue; }
-        if ((rc = make_act_map(&p.a_hi[g], a.seg_hi[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w))) return rc;
-        if ((rc = make_act_map(&p.a_lo[g], a.seg_lo[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w))) return rc;
+        if ((rc = make_act_map(&p.a_hi[g], a.seg_hi[g], a.seg_c[g], a.seg_pitch[g], a.B, in_h, in_w, TILE_ROWS, st))) return rc;
+        if ((rc = make_act_map(&p.a_lo[g], a.seg_lo[g], a.seg_c[g], a.seg_pitch[g], a.B, in_h, in_w, TILE_ROWS, st))) return rc;
     }
+    p.stride = st;
     const int taps = a.b_batched ? a.b_batched : a.kh * a.kw;     // 3rd weight-map dimension: tap, or sample
     if ((rc = make_wgt_map(&p.b_hi, a.w_hi, a.cin_pad, a.cout_pad, taps, a.n_tile))) return rc;
     if ((rc = make_wgt_map(&p.b_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, a.n_tile))) return rc;

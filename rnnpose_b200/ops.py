@@ -256,6 +256,47 @@ def lm_solve(depth: torch.Tensor, target: torch.Tensor, weight: torch.Tensor, K:
     return (G, Ho, bo, do) if taps else G
 
 
+ENCODER_KEYS: List[str] = (["fnet.conv1"] + [f"fnet.layer1.{b}.conv{c}" for b in (0, 1) for c in (1, 2)] +
+                           ["fnet.layer2.0.conv1", "fnet.layer2.0.conv2", "fnet.layer2.0.downsample.0", "fnet.layer2.1.conv1", "fnet.layer2.1.conv2",
+                            "fnet.layer3.0.conv1", "fnet.layer3.0.conv2", "fnet.layer3.0.downsample.0", "fnet.layer3.1.conv1", "fnet.layer3.1.conv2",
+                            "fnet.conv2"])
+
+
+def encoder_pack_weights(state: Dict[str, torch.Tensor], device="cuda") -> torch.Tensor:
+    """state: ImageFeaEncoder state dict (keys 'fnet.conv1.weight', ...; weights/img_fea_enc.pth).  Returns the packed blob."""
+    _need_cuda()
+    L = _lib.lib()
+    tens = []
+    for k in ENCODER_KEYS:
+        for sfx in (".weight", ".bias"):
+            tens.append(state[k + sfx].detach().to(device=device, dtype=torch.float32).contiguous())
+    arr = (C.c_void_p * len(tens))(*[t.data_ptr() for t in tens])
+    blob = _ws(L.b200pose_encoder_packed_weights_bytes(), device)
+    _lib.check(L.b200pose_encoder_pack_weights(arr, blob.data_ptr(), _stream()), "b200pose_encoder_pack_weights")
+    torch.cuda.current_stream().synchronize()      # `tens` must outlive the packing kernels
+    return blob
+
+
+def image_encoder(packed: torch.Tensor, image1: torch.Tensor, image2: torch.Tensor, workspace: Optional[torch.Tensor] = None):
+    """ImageFeaEncoder.forward(image1, image2) (reference model/CFNet.py:39-49) in the library's kernels: [B,3,H,W] x 2 ->
+    (fmap1, fmap2) [B,256,H/8,W/8]."""
+    _need_cuda()
+    L = _lib.lib()
+    _chk(image1, "image1"); _chk(image2, "image2")
+    B, Ci, H, W = image1.shape
+    if Ci != 3 or image2.shape != image1.shape:
+        raise ValueError("image_encoder: two [B,3,H,W] images")
+    dev = image1.device
+    f1 = torch.empty(B, 256, H // 8, W // 8, dtype=torch.float32, device=dev)
+    f2 = torch.empty(B, 256, H // 8, W // 8, dtype=torch.float32, device=dev)
+    nb = L.b200pose_encoder_workspace_bytes(B, H, W)
+    if workspace is None or workspace.numel() < nb:
+        workspace = _ws(nb, dev)
+    _lib.check(L.b200pose_image_encoder(packed.data_ptr(), image1.data_ptr(), image2.data_ptr(), B, H, W, f1.data_ptr(), f2.data_ptr(),
+                                        workspace.data_ptr(), workspace.numel(), _stream()), "b200pose_image_encoder")
+    return f1, f2
+
+
 def zoom_crop(pc_depth: torch.Tensor, K: torch.Tensor, T: torch.Tensor, image: Optional[torch.Tensor],
               geofea: Optional[torch.Tensor], out_hw, margin_ratio: float = 0.4, channels_last: bool = False,
               want_theta: bool = False):

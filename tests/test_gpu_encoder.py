@@ -1,0 +1,113 @@
+"""f2: the RAFT BasicEncoder kernels (csrc/encoder.cu through b200pose_image_encoder) against the executed reference
+(tests/golden/encoder.npz) and the CPU oracle.  Run on the B200 box:  python -m pytest tests -m gpu"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoder_oracle as E
+from rnnpose_b200 import synthetic as S
+from rnnpose_b200.assets import load_encoder_weights
+from tests.util import golden
+
+pytestmark = pytest.mark.gpu
+# the reference's own GPU path runs this network under fp16 autocast; the bar here is the fp32 CPU result
+RTOL, ATOL = 2e-4, 2e-4
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def enc():
+    from rnnpose_b200 import ops
+    assert torch.cuda.is_available()
+    return ops, ops.encoder_pack_weights(load_encoder_weights(), torch.device("cuda:0"))
+
+
+def _close(a, b, what):
+    scale = b.abs().max().item()
+    err = (a - b).abs().max().item()
+    print(f"[encoder] {what}: max abs err {err:.3e} (scale {scale:.2f})")
+    torch.testing.assert_close(a, b, rtol=RTOL, atol=ATOL * max(1.0, scale))
+
+
+def test_encoder_matches_reference_golden(enc):
+    ops, packed = enc
+    g = golden("encoder.npz")
+    d = torch.device("cuda:0")
+    f1, f2 = ops.image_encoder(packed, T(g["a_img1"]).to(d), T(g["a_img2"]).to(d))
+    assert f1.shape == (2, 256, 8, 12)
+    _close(f1.cpu(), T(g["a_f1"]), "64x96 fmap1"); _close(f2.cpu(), T(g["a_f2"]), "64x96 fmap2")
+    f1, f2 = ops.image_encoder(packed, T(g["c_img1"]).to(d), T(g["c_img2"]).to(d))
+    _close(f1.cpu(), T(g["c_f1"]), "72x104 fmap1"); _close(f2.cpu(), T(g["c_f2"]), "72x104 fmap2")
+    idx, H, W = [int(v) for v in g["b_meta"]]
+    mb = S.make_batch([idx], H, W, with_images=True)
+    f1, f2 = ops.image_encoder(packed, mb["syn_img"].to(d), mb["obs_img"].to(d))
+    # images in [0,1] normalised as if in [0,255]: nearly constant input, InstanceNorm amplifies rounding;
+    # the CPU oracle itself is 4e-4 from the executed reference on this case (tests/test_oracle_golden.py)
+    torch.testing.assert_close(f1.cpu(), T(g["b_f1"]), rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(f2.cpu(), T(g["b_f2"]), rtol=2e-3, atol=2e-3)
+
+
+def test_encoder_batched_vs_oracle_and_batch_invariance(enc):
+    """A machine-filling batch (CTA-pair kernels, several persistent rounds) against the oracle on a subset; a sample's maps do
+    not depend on its position in the batch or on the batch size."""
+    ops, packed = enc
+    d = torch.device("cuda:0")
+    mb = S.make_batch([3, 4], 240, 320, with_images=True)
+    a = mb["syn_img"].repeat(8, 1, 1, 1).contiguous(); b = mb["obs_img"].repeat(8, 1, 1, 1).contiguous()
+    f1, f2 = ops.image_encoder(packed, a.to(d), b.to(d))
+    f1, f2 = f1.cpu(), f2.cpu()
+    assert torch.isfinite(f1).all() and torch.isfinite(f2).all()
+    for k in range(2, 16):
+        assert torch.equal(f1[k], f1[k % 2]) and torch.equal(f2[k], f2[k % 2])
+    with torch.no_grad():
+        r1, r2 = E.image_encoder(load_encoder_weights(), mb["syn_img"], mb["obs_img"])
+    torch.testing.assert_close(f1[:2], r1, rtol=2e-3, atol=2e-3); torch.testing.assert_close(f2[:2], r2, rtol=2e-3, atol=2e-3)
+    g1, g2 = ops.image_encoder(packed, mb["syn_img"][:1].to(d).contiguous(), mb["obs_img"][:1].to(d).contiguous())
+    # (small batches run M=128 tiles, the large one CTA pairs with M=256: same products, possibly another summation grouping)
+    torch.testing.assert_close(g1.cpu(), f1[:1], rtol=2e-3, atol=2e-3); torch.testing.assert_close(g2.cpu(), f2[:1], rtol=2e-3, atol=2e-3)
+
+
+def test_encoder_module_mirror_and_error_codes(enc):
+    ops, packed = enc
+    from rnnpose_b200 import _lib
+    from rnnpose_b200.encoder import ImageFeaEncoder
+    net = ImageFeaEncoder().to("cuda:0")
+    assert len(net.state_dict()) == 32
+    net.load_state_dict(load_encoder_weights(), strict=True)
+    g = golden("encoder.npz")
+    f1, f2 = net(T(g["a_img1"]).cuda(), T(g["a_img2"]).cuda())
+    _close(f1.cpu(), T(g["a_f1"]), "module fmap1")
+    L = _lib.lib()
+    t = torch.zeros(1024, device="cuda")
+    p = t.data_ptr()
+    assert L.b200pose_image_encoder(0, p, p, 1, 64, 96, p, p, p, 1 << 30, 0) == -1
+    assert L.b200pose_image_encoder(p, p, p, 1, 60, 96, p, p, p, 1 << 30, 0) == -2
+    assert L.b200pose_image_encoder(packed.data_ptr(), p, p, 1, 64, 96, p, p, packed.data_ptr(), 16, 0) == -3
+
+
+def test_refine_on_encoder_features(enc):
+    """Encoder -> inner loop end to end on the GPU against encoder-oracle -> refine-oracle on the CPU."""
+    from oracle import refine_oracle as O
+    from tests.util import load_update_weights
+    ops, packed = enc
+    d = torch.device("cuda:0")
+    H, W = 128, 160
+    mb = S.make_batch([7, 8], H, W, with_images=True)
+    f1, f2 = ops.image_encoder(packed, mb["syn_img"].to(d), mb["obs_img"].to(d))
+    wts = load_update_weights()
+    pk = ops.pack_weights(wts, d)
+    G0 = torch.eye(4)[None].repeat(2, 1, 1)
+    G = G0.clone().to(d)
+    ops.refine_iters(pk, f1, f2, mb["context"].to(d), mb["geofea1"].to(d), mb["geofea2"].to(d), mb["depth"][:, 0].contiguous().to(d),
+                     mb["K"].to(d), G, 1.0, 4, 3)
+    with torch.no_grad():
+        r1, r2 = E.image_encoder(load_encoder_weights(), mb["syn_img"], mb["obs_img"])
+        ref = O.refine_inner_loop(wts, r1, r2, mb["context"], mb["geofea1"], mb["geofea2"], mb["depth"], mb["K"], G0, n_iters=4, n_lm=3)
+    err = (G.cpu() - ref["G"]).abs().max().item()
+    print(f"[encoder+refine] max |dSE3| vs oracle chain = {err:.3e}")
+    # the 1e-4 bar is defined for the loop on IDENTICAL feature maps (tests/test_gpu_refine.py); here the two encoders' maps
+    # already differ at the 1e-3 level on these [0,1] images (ill-conditioned InstanceNorm, see above), so the bound is looser
+    assert err < 1e-3

@@ -194,3 +194,25 @@ def test_g10_metrics_reference_evaluator():
         assert abs(m[0] - r[3]) / d < 2e-6 and abs(m[1] - r[4]) / d < 2e-6 and abs(m[4] - r[5]) < 2e-4 * max(1.0, r[5])
         assert m[6:14].tolist() == [float(v) for v in r[9:17]]
     assert worst_dir > 1e-3          # the fixture does separate the two ADD-S directions
+
+
+def test_g11_image_encoder_oracle():
+    """oracle/encoder_oracle.py (explicit conv + InstanceNorm restatement) against the executed reference ImageFeaEncoder
+    (tests/golden/encoder.npz): random 64x96 pairs, the synthetic 240x320 crop pair, a 72x104 pair."""
+    from oracle import encoder_oracle as E
+    from rnnpose_b200.assets import load_encoder_weights
+    w = load_encoder_weights()
+    g = golden("encoder.npz")
+    with torch.no_grad():
+        f1, f2 = E.image_encoder(w, T(g["a_img1"]), T(g["a_img2"]))
+        torch.testing.assert_close(f1, T(g["a_f1"]), rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(f2, T(g["a_f2"]), rtol=1e-4, atol=2e-5)
+        f1, f2 = E.image_encoder(w, T(g["c_img1"]), T(g["c_img2"]))
+        torch.testing.assert_close(f1, T(g["c_f1"]), rtol=1e-4, atol=2e-5)
+        idx, H, W = [int(v) for v in g["b_meta"]]
+        mb = S.make_batch([idx], H, W, with_images=True)
+        f1, f2 = E.image_encoder(w, mb["syn_img"], mb["obs_img"])
+        # (these images are in [0,1] and the encoder normalises them as if in [0,255] -- SURVEY Appendix D8: a nearly constant
+        #  input, whose InstanceNorm amplifies fp32 rounding; two fp32 evaluations of the same network differ by ~4e-4 here)
+        torch.testing.assert_close(f1, T(g["b_f1"]), rtol=1e-3, atol=1e-3)
+        torch.testing.assert_close(f2, T(g["b_f2"]), rtol=1e-3, atol=1e-3)
