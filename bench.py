@@ -45,8 +45,9 @@ UNIQUE_SCENES = 8            # distinct synthetic scenes per rank, tiled to the 
 FLOP_PER_LOWRES_PX = 6236672  # update-block convolutions, SURVEY.md Appendix A.2
 # dram__bytes_read.sum + dram__bytes_write.sum of the convolution launch(es) of one update-block pass at B=32, 240x320, from
 # the committed `ncu --set full` capture named in TRAFFIC_SOURCE (ncu flushes caches per launch: an upper bound)
-NCU_TRAFFIC_BYTES_PER_PASS = 775_000_000
-TRAFFIC_SOURCE = "profiles/r1c_conv_umma2_ncu_raw.csv (11 conv launches of one pass, B=32, 240x320)"
+NCU_TRAFFIC_BYTES_PER_PASS = {"chain": 818_810_112, "layers": 775_000_000}
+TRAFFIC_SOURCE = {"chain": "profiles/r2c/chain_ncu_raw.csv (conv_chain_kernel, one launch, B=32, 240x320)",
+                  "layers": "profiles/r1c_conv_umma2_ncu_raw.csv (11 conv launches of one pass, B=32, 240x320)"}
 
 CONFIGS = {
     #        H    W   iters lm  objects/GPU occluded  chunk
@@ -261,9 +262,10 @@ def run_reference(args):
 
 
 def conv_pass_roofline(ops, packed, Bc, H, W, FLAGS, peaks, peak_src, exact, ms_step, n_iters, passes_per_step):
-    """Roofline of the dominant kernel family -- the convolutions of one update-block pass -- timed live, back to back, at
-    the chunk batch size.  The pass is timed ALONE (not inside the long step), so the denominator is the BURST dense-bf16
-    peak of MEASURED_PEAKS.json; the sustained-peak fraction is reported next to it."""
+    from rnnpose_b200 import _lib
+    """Roofline of the dominant kernel -- the convolutions of one update-block pass (one chained launch by default) -- timed
+    live at the chunk batch size with CUDA events around the launch.  The passes run ALONE (not inside the long step), so the
+    denominator is the BURST dense-bf16 peak of MEASURED_PEAKS.json; the sustained-peak fraction is reported next to it."""
     dev = packed.device
     h, w = H // 8, W // 8
     P = Bc * h * w
@@ -271,31 +273,42 @@ def conv_pass_roofline(ops, packed, Bc, H, W, FLAGS, peaks, peak_src, exact, ms_
     corr = torch.randn(P, 328, device=dev); c1 = torch.randn(P, 2, device=dev); fl = torch.randn(P, 2, device=dev)
     for _ in range(3):
         ops.update_block(packed, net, xbuf, corr, c1, fl, Bc, h, w, flags=FLAGS)
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 10
+    # (1) the convolution launch(es) alone: CUDA events recorded by the library on its stream immediately around them
+    #     (b200pose_debug_set_conv_events); (2) the whole pass incl. its helper launches, for the share of the step
+    L = _lib.lib()
+    pairs = []
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     r0.record()
     for _ in range(reps):
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(); k1.record()                       # creates the handles; the library re-records them
+        if not exact:
+            L.b200pose_debug_set_conv_events(k0.cuda_event, k1.cuda_event)
         ops.update_block(packed, net, xbuf, corr, c1, fl, Bc, h, w, flags=FLAGS)
+        pairs.append((k0, k1))
     r1.record(); torch.cuda.synchronize()
     ub_ms = r0.elapsed_time(r1) / reps
+    conv_ms = ub_ms if exact else sum(a.elapsed_time(b) for a, b in pairs) / reps
     flops = FLOP_PER_LOWRES_PX * P
-    achieved = flops / (ub_ms * 1e-3) / 1e12
+    achieved = flops / (conv_ms * 1e-3) / 1e12
     burst = float(peaks.get("bf16_tflops"))
     sustained = float(peaks.get("bf16_tflops_sustained", burst))
     chain = (ops.get_option("conv_mode") & 16) != 0
     kern = ("conv_gemm_kernel<128|64> (FFMA)" if exact else
             ("conv_chain_kernel (the 11 convolutions of a pass in one persistent launch of CTA pairs, tcgen05.mma cta_group::2 + TMA + TMEM)"
              if chain else "conv_umma2_kernel (tcgen05.mma cta_group::2 on CTA pairs + TMA + TMEM), 11 launches"))
-    same_shape = (Bc, H, W) == (32, 240, 320) and not exact and not chain
+    same_shape = (Bc, H, W) == (32, 240, 320) and not exact
+    tkey = "chain" if chain else "layers"
     return {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
             "frac_of_sustained_peak": achieved / sustained,
-            "traffic": NCU_TRAFFIC_BYTES_PER_PASS if same_shape else None,
-            "traffic_source": TRAFFIC_SOURCE if same_shape else None,
+            "traffic": NCU_TRAFFIC_BYTES_PER_PASS[tkey] if same_shape else None,
+            "traffic_source": TRAFFIC_SOURCE[tkey] if same_shape else None,
             "peak_source": f"{peak_src}: dense bf16 burst (the pass is timed alone); sustained {sustained:.1f}",
-            "kernel": kern + "; one update-block pass timed back to back incl. its helper launches (im2col, flow head, operand split)",
-            "algorithmic_flops_per_pass": flops, "ms_per_pass": ub_ms, "batch": Bc,
-            "share_of_step": (ub_ms * n_iters * passes_per_step) / ms_step}
+            "kernel": kern + "; CUDA events recorded by the library on its stream immediately before / after the convolution launch(es) of a pass",
+            "algorithmic_flops_per_pass": flops, "ms_per_launch": conv_ms, "ms_per_pass_with_helpers": ub_ms, "batch": Bc,
+            "share_of_step": (conv_ms * n_iters * passes_per_step) / ms_step}
 
 
 def run_workload(args, cfg, per_gpu, rank, local_rank, world, dev, numa, want_cpu=True, want_e2e=True):
@@ -484,7 +497,7 @@ def main():
             if ln:
                 rows.append({"global_batch": gb, "value": ln["value"], "ms_per_step": ln["ms_per_step"], "chunk": ln["config"]["chunk"],
                              "roofline_frac": ln["roofline"]["frac"], "conv_tflops": ln["roofline"]["achieved"],
-                             "ms_per_conv_pass": ln["roofline"]["ms_per_pass"]})
+                             "ms_per_conv_launch": ln["roofline"]["ms_per_launch"]})
             torch.cuda.empty_cache()
         line = run_workload(args, "cfg4", max(1, 8 // world) if world <= 8 else 1, rank, local_rank, world, dev, numa)
         if line:

@@ -268,6 +268,11 @@ int b200pose_refine_iters_host(const void* packed_weights,
                                double ep_lmbda, double lm_lmbda, int flags,
                                void* device_scratch, size_t device_scratch_bytes, void* stream);
 
+/* Measurement hook (bench.py "roofline"): the NEXT tensor-core update-block pass (b200pose_update_block or an iteration of
+ * b200pose_refine_iters) records the two cudaEvent_t on its stream immediately before and after its convolution launch(es)
+ * -- the chained launch, or the eleven layer launches -- and forgets them.  Not thread-safe.                        */
+int b200pose_debug_set_conv_events(void* ev_start, void* ev_stop);
+
 /* number of kernel launches b200pose_refine_iters enqueues (for bench.py's gpu_launches) */
 int b200pose_refine_launch_count(int n_iters, int n_lm);
 

@@ -111,6 +111,10 @@ constexpr int UPDATE_LAUNCHES = 14;     // im2col, 11 convolutions, flow-head pa
 int run_update_block_tc_chain(const float* wts, float* net, float* coords1, float* flow, float* mask, float* dflow_out,
                               int B, int h, int w, const UpdateWs& u, bool use_pre, cudaStream_t s);
 
+// Timing hook (b200pose_debug_set_conv_events): the next tensor-core update-block pass records these two events on its stream
+// immediately before the first and after the last convolution launch (the chained launch, or the eleven layer launches).
+cudaEvent_t g_conv_ev[2] = {nullptr, nullptr};
+
 int run_update_block_tc(const float* wts, float* net, float* coords1, float* flow, float* mask, float* dflow_out,
                         int B, int h, int w, const UpdateWs& u, bool use_pre, cudaStream_t s) {
     if (b2p_conv_chain_enabled() && B * ceil_div(h, B2P_TILE_ROWS) * ceil_div(w, B2P_TILE_COLS) >= 296) {
@@ -141,6 +145,7 @@ int run_update_block_tc(const float* wts, float* net, float* coords1, float* flo
         return b2p_launch_conv_umma(a, s);
     };
     if ((rc = b2p_im2col_f1(flow, B, h, w, nullptr, nullptr, u.col_h[0], u.col_h[1], u.x_h[0], u.x_h[1], s))) return rc;
+    if (g_conv_ev[0]) B2P_CUDA(cudaEventRecord(g_conv_ev[0], s));
     if ((rc = conv(CV_C1, u.corr_h, 0, B200POSE_CORR_PITCH, B200POSE_CORR_PITCH, nullptr, 0, 0, u.c1_h, 0, 256, EPI_RELU, 1.f, nullptr, 0))) return rc;
     if ((rc = conv(CV_C2, u.c1_h, 0, 256, 256, nullptr, 0, 0, u.corflo_h, 0, 256, EPI_RELU, 1.f, nullptr, 0))) return rc;
     if ((rc = conv(CV_F1, u.col_h, 0, 112, 112, nullptr, 0, 0, u.f1o_h, 0, 128, EPI_RELU, 1.f, nullptr, 0))) return rc;
@@ -153,8 +158,9 @@ int run_update_block_tc(const float* wts, float* net, float* coords1, float* flo
     if ((rc = conv(CV_ZR2, u.net_h, 0, 128, 128, u.x_h, 256, 256, u.rh_h, 0, 128, EPI_GRU_ZR, 1.f, nullptr, 0, pz2, 256))) return rc;
     if ((rc = conv(CV_Q2, u.rh_h, 0, 128, 128, u.x_h, 256, 256, u.net_h, 0, 128, EPI_GRU_Q, 1.f, nullptr, 0, pq2, 128))) return rc;
     if ((rc = conv(CV_HEADS, u.net_h, 0, 128, 128, nullptr, 0, 0, u.hm_h, 0, 512, EPI_RELU, 1.f, nullptr, 0))) return rc;
-    if ((rc = b2p_flow_head2(nullptr, u.hm_h[0], u.hm_h[1], wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, u.col, B, h, w, s))) return rc;
     if ((rc = conv(CV_MASK2, u.hm_h, 256, 256, 512, nullptr, 0, 0, nullptr, 0, 0, EPI_SCALE, 0.25f, mask, 576))) return rc;
+    if (g_conv_ev[1]) { B2P_CUDA(cudaEventRecord(g_conv_ev[1], s)); g_conv_ev[0] = g_conv_ev[1] = nullptr; }
+    if ((rc = b2p_flow_head2(nullptr, u.hm_h[0], u.hm_h[1], wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, u.col, B, h, w, s))) return rc;
     return 0;
 }
 
@@ -218,7 +224,9 @@ int run_update_block_tc_chain(const float* wts, float* net, float* coords1, floa
     // completion counters: the fp32 scratch of the exact path (unused here), well past the flow-head partial sums in u.col
     const int m_tiles = B * ceil_div(h, B2P_TILE_ROWS) * ceil_div(w, B2P_TILE_COLS);
     if (b2p_conv_chain_done_ints(n, m_tiles) * sizeof(int) > (size_t)B * h * w * 256 * sizeof(float)) return -1;
+    if (g_conv_ev[0]) B2P_CUDA(cudaEventRecord(g_conv_ev[0], s));
     if ((rc = b2p_launch_conv_chain(args, n, deps, n_reverse, reinterpret_cast<int*>(u.c1), s))) return rc;
+    if (g_conv_ev[1]) { B2P_CUDA(cudaEventRecord(g_conv_ev[1], s)); g_conv_ev[0] = g_conv_ev[1] = nullptr; }
     return b2p_flow_head2(nullptr, u.hm_h[0], u.hm_h[1], wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, u.col, B, h, w, s);
 }
 
@@ -574,6 +582,11 @@ int b200pose_lm_solve(const float* depth, const float* target, const float* weig
                              delta_out ? delta_out + (size_t)i * B * 6 : nullptr, workspace, (cudaStream_t)stream);
         if (rc) return rc;
     }
+    return 0;
+}
+
+int b200pose_debug_set_conv_events(void* ev_start, void* ev_stop) {
+    g_conv_ev[0] = (cudaEvent_t)ev_start; g_conv_ev[1] = (cudaEvent_t)ev_stop;
     return 0;
 }
 

@@ -14,6 +14,7 @@ ap.add_argument("--fp32", action="store_true")
 ap.add_argument("--passes", type=int, default=2)
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--time", action="store_true")
+ap.add_argument("--iters", type=int, default=4)
 a = ap.parse_args()
 H, W, B = 240, 320, a.batch
 dev = torch.device("cuda:0")
@@ -31,14 +32,14 @@ ws = ops.RefineWorkspace(B, H, W, dev)
 flags = ops.FLAG_EXACT_FP32 if a.fp32 else ops.FLAG_TENSOR_CORES
 for i in range(a.passes):
     G = torch.eye(4, device=dev)[None].repeat(B, 1, 1).contiguous()
-    ops.refine_iters(packed, f1, f2, ctx, g1, g2, depth.contiguous(), K, G, 1.0, 4, 3, workspace=ws, flags=flags)
+    ops.refine_iters(packed, f1, f2, ctx, g1, g2, depth.contiguous(), K, G, 1.0, a.iters, 3, workspace=ws, flags=flags)
 torch.cuda.synchronize()
 if a.time:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(10):
         G = torch.eye(4, device=dev)[None].repeat(B, 1, 1).contiguous()
-        ops.refine_iters(packed, f1, f2, ctx, g1, g2, depth.contiguous(), K, G, 1.0, 4, 3, workspace=ws, flags=flags)
+        ops.refine_iters(packed, f1, f2, ctx, g1, g2, depth.contiguous(), K, G, 1.0, a.iters, 3, workspace=ws, flags=flags)
     e1.record(); torch.cuda.synchronize()
     print(f"ms per pass: {e0.elapsed_time(e1) / 10:.3f}  poses/s: {B * 10 / (e0.elapsed_time(e1) * 1e-3):.0f}")
 print("ok", torch.isfinite(G).all().item())
