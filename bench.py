@@ -448,7 +448,7 @@ def run_workload(args, cfg, per_gpu, rank, local_rank, world, dev, numa, want_cp
                        "parallelism": f"dp{world} (objects sharded, one all-gather of metrics)",
                        "l2": f"resident inputs per chunk ({sum(d[0][k].numel() * 4 for k in keys) / 1e9:.1f} GB) exceed the 126 MB L2; no explicit flush"},
             "e2e": e2e,
-            "gpu_launches": args.steps * n_chunks * ops.launch_count(N_ITERS, N_LM) + 2,
+            "gpu_launches": args.steps * n_chunks * ops.launch_count(chunk, H, W, N_ITERS, N_LM) + 2,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "options": opts,
             "accuracy_vs_gt": {"objects": int(gm.shape[0]), "mean_add_over_diameter": float((gm[:, 0] / gm[:, 15]).mean()),
                                "add_0.1d_recall": float(gm[:, 6].mean()), "adds_0.1d_recall": float(gm[:, 7].mean()),

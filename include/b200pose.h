@@ -66,8 +66,9 @@ const char* b200pose_error_string(int code);
  *                                      second-generation kernel, bit4 the eleven convolutions of an update-block pass in one
  *                                      persistent launch (machine-filling batches; else layer by layer); 0 = first generation
  *   fg_list (B200POSE_FG_LIST, 1)      LM steps over the per-call foreground list
- *   fg_pipeline (B200POSE_FG_PIPELINE, 1)  compact channels-last upsample+weight kernel + cluster LM kernel
- *   fg_upsample, fg_blocks, sparse_g1, tail_min_n, lookup_mode, pool_mode, chain_rings, conv_debug, lm_debug: see csrc/options.cu
+ *   fg_pipeline (B200POSE_FG_PIPELINE, 2)  channels-last target / weight kernels + cluster LM kernel: 0 off, 1 on, 2 only when
+ *                                      geofea2 arrives channels-last (B200POSE_FLAG_GEO2_CHANNELS_LAST)
+ *   fg_upsample, fg_blocks, sparse_g1, tail_min_n, lookup_mode, pool_mode, chain_rings, chain_dynamic, conv_debug, lm_debug: see csrc/options.cu
  * Returns 0, B200POSE_E_NULL or B200POSE_E_ARG (unknown name).  Not synchronised against launches in flight on other
  * threads.                                                                                         */
 int b200pose_set_option(const char* name, int value);
@@ -273,8 +274,9 @@ int b200pose_refine_iters_host(const void* packed_weights,
  * -- the chained launch, or the eleven layer launches -- and forgets them.  Not thread-safe.                        */
 int b200pose_debug_set_conv_events(void* ev_start, void* ev_stop);
 
-/* number of kernel launches b200pose_refine_iters enqueues (for bench.py's gpu_launches) */
-int b200pose_refine_launch_count(int n_iters, int n_lm);
+/* number of kernel launches b200pose_refine_iters enqueues for this shape with the tensor-core flag, C_geo = 32 and the
+ * current options (for bench.py's gpu_launches); 0 for an unsupported shape */
+int b200pose_refine_launch_count(int B, int H, int W, int n_iters, int n_lm);
 
 #ifdef __cplusplus
 }

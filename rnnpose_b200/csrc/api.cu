@@ -100,7 +100,6 @@ int run_update_block(const float* wts, float* net, float* xbuf, const float* cor
     if ((rc = conv(CV_MASK2, u.hm + 256, 512, 256, nullptr, 0, 0, mask, 576, EPI_SCALE, 0.25f))) return rc;
     return 0;
 }
-constexpr int UPDATE_LAUNCHES = 14;     // im2col, 11 convolutions, flow-head partial + gather
 
 // ------------------------------------------------------------------------------------------------
 // tensor-core path (tcgen05, fp16 hi/lo operands).  Expects u.corr_h, u.net_h and u.x_h[:, 0:128] filled.
@@ -117,7 +116,7 @@ cudaEvent_t g_conv_ev[2] = {nullptr, nullptr};
 
 int run_update_block_tc(const float* wts, float* net, float* coords1, float* flow, float* mask, float* dflow_out,
                         int B, int h, int w, const UpdateWs& u, bool use_pre, cudaStream_t s) {
-    if (b2p_conv_chain_enabled() && B * ceil_div(h, B2P_TILE_ROWS) * ceil_div(w, B2P_TILE_COLS) >= 296) {
+    if (b2p_conv_chain_enabled() && B * ceil_div(h, B2P_TILE_ROWS) * ceil_div(w, B2P_TILE_COLS) >= 296) {     // (also in b200pose_refine_launch_count)
         // experimental single-launch variant; -1 = not applicable, fall through to the layer-by-layer pass
         const int rcc = run_update_block_tc_chain(wts, net, coords1, flow, mask, dflow_out, B, h, w, u, use_pre, s);
         if (rcc != -1) return rcc;
@@ -172,7 +171,7 @@ int run_update_block_tc_chain(const float* wts, float* net, float* coords1, floa
     const B2PWeightLayout& L = b2p_weight_layout();
     const B2PHalfLayout& HL = b2p_half_layout();
     const __half* hbase = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(wts) + b2p_half_section_offset_bytes());
-    UmmaConvArgs args[11];
+    UmmaConvArgs args[12];
     int n = 0;
     auto add = [&](int id, __half* const* s0, int off0, int c0, int p0, __half* const* s1, int c1n, int p1,
                    __half* const* dst, int doff, int dpitch, int epi, float scale, float* out_f32, int f32_pitch,
@@ -207,27 +206,40 @@ int run_update_block_tc_chain(const float* wts, float* net, float* coords1, floa
     add(CV_Q2, u.rh_h, 0, 128, 128, u.x_h, 256, 256, u.net_h, 0, 128, EPI_GRU_Q, 1.f, nullptr, 0, pq2, 128);
     add(CV_HEADS, u.net_h, 0, 128, 128, nullptr, 0, 0, u.hm_h, 0, 512, EPI_RELU, 1.f, nullptr, 0);
     add(CV_MASK2, u.hm_h, 256, 256, 512, nullptr, 0, 0, nullptr, 0, 0, EPI_SCALE, 0.25f, mask, 576);
+    {   // 11 FH2: flow_head.conv2 (3x3, 256 -> 2, padded to 32 columns) on the flow half of HEADS; its epilogue applies
+        // coords1 += delta and flow = coords1 - coords0 (the two flow_head2 FFMA launches of the layer-by-layer path)
+        const B2PHalfConvDesc& d = HL.fh2;
+        UmmaConvArgs& a = args[n++];
+        memset(&a, 0, sizeof(a));
+        a.layer_id = -1;
+        a.seg_hi[0] = u.hm_h[0]; a.seg_lo[0] = u.hm_h[1]; a.seg_c[0] = 256; a.seg_pitch[0] = 512;
+        a.w_hi = hbase + d.hi_off; a.w_lo = hbase + d.lo_off; a.bias = wts + L.fh2_b_off;       // 2 biases followed by zeros
+        a.cin_pad = d.cin_pad; a.cout_pad = d.cout_pad; a.cout = d.cout; a.n_tile = d.n_tile; a.kh = 3; a.kw = 3;
+        a.B = B; a.h = h; a.w = w; a.epi = EPI_FLOW; a.scale = 1.f;
+        a.fl_coords1 = coords1; a.fl_flow = flow; a.fl_dflow = dflow_out;
+    }
     // which earlier layers each layer reads (also the layers whose readers it must not overtake, see conv_chain_kernel).
-    // MASK2 reads channels 256..511 of HEADS = its N unit 1 only (chained N tile 256); HEADS lists that unit first.
-    B2PChainDep deps[11];
+    // HEADS lists its N unit 1 (channels 256..511, the mask half) first: MASK2 reads only that unit, FH2 only unit 0.
+    B2PChainDep deps[12];
     memset(deps, 0, sizeof(deps));
     auto dep = [&](int l, int halo, int s0, int s1 = -1) {
         deps[l].halo = halo; deps[l].n_src = s0 < 0 ? 0 : (s1 < 0 ? 1 : 2);
         deps[l].src[0] = s0 < 0 ? 0 : s0; deps[l].src[1] = s1 < 0 ? 0 : s1;
     };
     dep(0, 0, -1); dep(1, 0, -1); dep(2, 1, 0); dep(3, 1, 1); dep(4, 1, 2, 3); dep(5, 1, 4); dep(6, 1, 5); dep(7, 1, 6);
-    dep(8, 1, 7); dep(9, 1, 8); dep(10, 0, 9);
+    dep(8, 1, 7); dep(9, 1, 8); dep(10, 0, 9); dep(11, 1, 9);
     deps[10].n_first[0] = 1; deps[10].n_cnt[0] = 1;
-    int n_reverse[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
+    deps[11].n_first[0] = 0; deps[11].n_cnt[0] = 1;
+    int n_reverse[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0};
     int rc;
     if ((rc = b2p_im2col_f1(flow, B, h, w, nullptr, nullptr, u.col_h[0], u.col_h[1], u.x_h[0], u.x_h[1], s))) return rc;
-    // completion counters: the fp32 scratch of the exact path (unused here), well past the flow-head partial sums in u.col
+    // completion counters: the fp32 scratch of the exact path (unused here)
     const int m_tiles = B * ceil_div(h, B2P_TILE_ROWS) * ceil_div(w, B2P_TILE_COLS);
     if (b2p_conv_chain_done_ints(n, m_tiles) * sizeof(int) > (size_t)B * h * w * 256 * sizeof(float)) return -1;
     if (g_conv_ev[0]) B2P_CUDA(cudaEventRecord(g_conv_ev[0], s));
     if ((rc = b2p_launch_conv_chain(args, n, deps, n_reverse, reinterpret_cast<int*>(u.c1), s))) return rc;
     if (g_conv_ev[1]) { B2P_CUDA(cudaEventRecord(g_conv_ev[1], s)); g_conv_ev[0] = g_conv_ev[1] = nullptr; }
-    return b2p_flow_head2(nullptr, u.hm_h[0], u.hm_h[1], wts + L.fh2_w_off, wts + L.fh2_b_off, coords1, flow, dflow_out, u.col, B, h, w, s);
+    return 0;
 }
 
 // GRU partial sums over the `inp` channels only (chunks 2,3), no bias, no activation: pre[k][P][cout] fp32.
@@ -236,9 +248,10 @@ int run_gru_precompute(const float* wts, int B, int h, int w, const UpdateWs& u,
     const __half* hbase = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(wts) + b2p_half_section_offset_bytes());
     B2P_CUDA(cudaMemsetAsync(u.zero_bias, 0, 1024 * sizeof(float), s));
     const int ids[4] = {CV_ZR1, CV_Q1, CV_ZR2, CV_Q2};
+    UmmaConvArgs args[4];
     for (int k = 0; k < 4; ++k) {
         const B2PHalfConvDesc& d = HL.cv[ids[k]];
-        UmmaConvArgs a;
+        UmmaConvArgs& a = args[k];
         memset(&a, 0, sizeof(a));
         // segment 0 is only a placeholder here (its chunks 0,1 are masked out); segment 1 = x = [inp | motion]
         a.seg_hi[0] = u.net_h[0]; a.seg_lo[0] = u.net_h[1]; a.seg_c[0] = 128; a.seg_pitch[0] = 128;
@@ -250,7 +263,18 @@ int run_gru_precompute(const float* wts, int B, int h, int w, const UpdateWs& u,
         a.out_tiled = 1; a.side_tiled = 1;                        // the consumers read the pre-sums as a tiled side buffer
         a.chunk_mask = 0x0Cu;                                     // chunks {2,3}: the inp channels
         a.layer_id = ids[k];
-        int rc = b2p_launch_conv_umma(a, s);
+    }
+    // the four GEMMs are independent: one chained launch (no dependencies) when the batch fills the machine
+    const int m_tiles = B * ceil_div(h, B2P_TILE_ROWS) * ceil_div(w, B2P_TILE_COLS);
+    if (b2p_conv_chain_enabled() && m_tiles >= 296 &&
+        b2p_conv_chain_done_ints(4, m_tiles) * sizeof(int) <= (size_t)B * h * w * 256 * sizeof(float)) {
+        B2PChainDep deps[4];
+        memset(deps, 0, sizeof(deps));
+        const int rcc = b2p_launch_conv_chain(args, 4, deps, nullptr, reinterpret_cast<int*>(u.c1), s);
+        if (rcc != -1) return rcc;
+    }
+    for (int k = 0; k < 4; ++k) {
+        int rc = b2p_launch_conv_umma(args[k], s);
         if (rc) return rc;
     }
     return 0;
@@ -604,14 +628,22 @@ int b200pose_se3_retract(const float* delta, float* G, int B, void* stream) {
 
 size_t b200pose_refine_workspace_bytes(int B, int H, int W) { return refine_ws_layout(B, H, W, nullptr, 0, nullptr); }
 
-int b200pose_refine_launch_count(int n_iters, int n_lm) {
-    // Kernels b200pose_refine_iters enqueues with the default options (tensor-core path, foreground pipeline, C_geo = 32, a
-    // level-0 correlation image that fits the one-pass pooling):
-    //   per call: LM counter reset, 2 feature-map transposes, volume GEMM, pooling, context init, hidden state to the tiled
-    //   layout = 7; with n_iters > 0: 3 for the foreground list + 2 for the channels-last descriptors; with n_iters > 1: the
-    //   4 GRU partial-sum GEMMs;  per recurrent iteration: flow_init, lookup, the update block (im2col, 11 convolutions,
-    //   flow-head partial + gather), target + weight (2), and one launch for all LM steps
-    return 7 + (n_iters > 0 ? 5 : 0) + (n_iters > 1 ? 4 : 0) + n_iters * (2 + UPDATE_LAUNCHES + 2 + (n_lm > 0 ? 1 : 0));
+int b200pose_refine_launch_count(int B, int H, int W, int n_iters, int n_lm) {
+    // Kernels b200pose_refine_iters enqueues on the tensor-core path with C_geo = 32 and the current options:
+    //   per call: LM counter reset, 2 feature-map transposes, volume GEMM, pooling (1 pass, or 3), context init, hidden state to
+    //   the tiled layout; with n_iters > 0: 3 for the foreground list (+ 2 for the pipeline's channels-last descriptors);
+    //   with n_iters > 1: the 4 GRU partial-sum GEMMs (1 chained launch, or 4);  per recurrent iteration: flow_init, lookup, im2col, the convolutions
+    //   (1 chained launch incl. the flow head, or 11 + 2), upsample/target/weight (2 with the pipeline, else 1), one launch
+    //   for all LM steps
+    if (!shape_ok(B, H, W)) return 0;
+    const int h = H / 8, w = W / 8;
+    const B2POptions& o = b2p_options();
+    const bool chain = (o.conv_mode & 16) && B * ceil_div(h, B2P_TILE_ROWS) * ceil_div(w, B2P_TILE_COLS) >= 296;
+    const bool pool3 = o.pool_mode == 1 && (size_t)(h * w + (h >> 1) * (w >> 1) + (h >> 2) * (w >> 2)) * sizeof(float) <= 40 * 1024;
+    const bool pipe = o.fg_list != 0 && o.fg_pipeline == 1;      // (2 = only with channels-last geofea2, which this count does not assume)
+    const int per_call = 4 + (pool3 ? 1 : 3) + 2 + (n_iters > 0 && o.fg_list ? 3 + (pipe ? 2 : 0) : 0) + (n_iters > 1 ? (chain ? 1 : 4) : 0);
+    const int per_iter = 2 + 1 + (chain ? 1 : 13) + (pipe ? 2 : 1) + (n_lm > 0 ? 1 : 0);
+    return per_call + n_iters * per_iter;
 }
 
 int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const float* fmap2, const float* context,
@@ -648,7 +680,10 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
     const bool use_fg = n_iters > 0 && fg_list_enabled();
     const bool g2_cl = (flags & B200POSE_FLAG_GEO2_CHANNELS_LAST) != 0;
     // foreground pipeline (fg_pipeline.cu + lm_cluster_kernel): channels-last descriptors, one record per listed pixel
-    const bool use_pipe = use_fg && C_geo == 32 && b2p_options().fg_pipeline != 0;
+    // option fg_pipeline: 0 off, 1 on, 2 (default) only when geofea2 arrives channels-last (zoom-crop output): with NCHW input the
+    // two transposes (140 us per call at B=32) outweigh the 16 us per iteration the pipeline saves (profiles/r2d)
+    const int pipe_opt = b2p_options().fg_pipeline;
+    const bool use_pipe = use_fg && C_geo == 32 && (pipe_opt == 1 || (pipe_opt == 2 && g2_cl));
     if (g2_cl && !use_pipe) return B200POSE_E_ARG;          // only the pipeline reads channels-last descriptors
     const bool fg_up = use_fg && !use_pipe && fg_upsample_enabled();
     if (use_fg && (rc = b2p_fg_build(depth, B, H, W, r.fg, fg_up ? r.target : nullptr, fg_up ? r.weight : nullptr, s))) return rc;

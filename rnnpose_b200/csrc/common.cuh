@@ -42,7 +42,7 @@ inline cudaError_t b2p_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 // into the library, changed afterwards only through b200pose_set_option.
 struct B2POptions {
     int conv_mode, fg_list, fg_pipeline, fg_upsample, sparse_g1, fg_blocks, tail_min_n, conv_debug, lookup_mode, pool_mode,
-        lm_debug, chain_rings;
+        lm_debug, chain_rings, chain_dynamic;
 };
 B2POptions& b2p_options();
 
@@ -84,7 +84,7 @@ struct B2PWeightLayout {
 const B2PWeightLayout& b2p_weight_layout();
 
 // conv epilogues
-enum { EPI_NONE = 0, EPI_RELU = 1, EPI_SCALE = 2, EPI_GRU_ZR = 3, EPI_GRU_Q = 4 };
+enum { EPI_NONE = 0, EPI_RELU = 1, EPI_SCALE = 2, EPI_GRU_ZR = 3, EPI_GRU_Q = 4, EPI_FLOW = 5 };
 
 struct ConvParams {
     const float* src0; int pitch0; int c0;   // input segment 0 (PXC): pointer at first channel, pixel pitch, channels
@@ -140,6 +140,7 @@ struct B2PHalfConvDesc {
 };
 struct B2PHalfLayout {
     B2PHalfConvDesc cv[CV_COUNT];
+    B2PHalfConvDesc fh2;       // flow_head.conv2 (3x3, 256 -> 2) padded to 32 output channels: the last layer of the chained launch
     size_t total_halves;
 };
 const B2PHalfLayout& b2p_half_layout();
@@ -154,6 +155,7 @@ struct UmmaConvArgs {
     float* out_f32; int out_f32_pitch;
     __half* out_hi; __half* out_lo; int out_h_pitch;
     float* zbuf; float* hbuf;
+    float* fl_coords1; float* fl_flow; float* fl_dflow;   // EPI_FLOW: coords1 [P][2] in/out, flow [P][2] out, delta [P][2] out or nullptr
     unsigned chunk_mask;       // bit cc set = visit 64-channel chunk cc of every tap (0 = all chunks)
     const float* pre; int pre_pitch;   // fp32 [P][pre_pitch] partial sums added in the epilogue (or nullptr)
     int layer_id;              // B2PConvId of an update-block layer, or -1

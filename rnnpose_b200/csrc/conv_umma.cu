@@ -57,6 +57,7 @@ struct UmmaConvParams {
     float* out_f32; int out_f32_pitch;
     __half* out_hi; __half* out_lo; int out_h_pitch;
     float* zbuf; float* hbuf;         // GRU side buffers, fp32 [P][128]
+    float* fl_coords1; float* fl_flow; float* fl_dflow;   // EPI_FLOW (flow head conv2, chained launch only)
     // conv_umma2_kernel only (separate activation / weight rings, optional CTA pair):
     int a_taps;                        // vertical taps served by one activation box (kh when the box carries the halo rows, else 1)
     int a_rows;                        // rows of the activation box = 16 + a_taps - 1
@@ -245,6 +246,17 @@ __device__ __forceinline__ void epilogue_columns(const UmmaConvParams& p, uint32
         // channels of this 32-group that exist: bounded by the layer (cout) and by the tile (n_tile need not be a
         // multiple of 32, e.g. 240 for the correlation volume)
         const int lim = min(p.cout - nb, n_cnt - col0);
+        if (p.epi == EPI_FLOW) {
+            // flow head conv2 (update.py:13-14) fused with coords1 += delta_flow; flow = coords1 - coords0 (CFNet.py:157,166):
+            // this thread's pixel, output channels 0 (x) and 1 (y)
+            const int px = (int)(pix % (size_t)p.w), py = (int)((pix / (size_t)p.w) % (size_t)p.h);
+            if (p.fl_dflow) *reinterpret_cast<float2*>(p.fl_dflow + pix * 2) = make_float2(v[0], v[1]);
+            float2 c1 = *reinterpret_cast<const float2*>(p.fl_coords1 + pix * 2);
+            c1.x += v[0]; c1.y += v[1];
+            *reinterpret_cast<float2*>(p.fl_coords1 + pix * 2) = c1;
+            *reinterpret_cast<float2*>(p.fl_flow + pix * 2) = make_float2(c1.x - (float)px, c1.y - (float)py);
+            continue;
+        }
         if (p.epi == EPI_SCALE) {
             if (p.out_tiled) {                             // GRU pre-sums: a side buffer of out_f32_pitch channels
                 float4* d = const_cast<float4*>(side4(p.out_f32, p.out_f32_pitch, nb));
@@ -847,7 +859,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
 // read T.  Every cluster processes its units in list order and only waits for earlier units, so with all clusters
 // co-resident there is no deadlock.  Side buffers written earlier in the same launch are read through L2
 // (epilogue_columns<true>).  Shared memory: fixed-size ring slots for the largest layer.
-constexpr int CH_MAX_LAYERS = 11;
+constexpr int CH_MAX_LAYERS = 12;
 constexpr int CH_MAX_NSUB = 3;                            // N units per tile of a layer (MASK2: 576 = 3 x 192)
 constexpr uint32_t CH_A_SLOT = 2u * 20u * 1024u;          // hi + lo planes of a 20-row activation box (5x1 with halo)
 constexpr uint32_t CH_B_SLOT = 2u * 128u * 128u;          // hi + lo planes of 128 weight rows per CTA (256-channel tiles)
@@ -862,10 +874,39 @@ struct ChainParams {
     int ring_a, ring_b;                     // ring depths (option chain_rings)
     int unit_start[CH_MAX_LAYERS + 1];     // prefix sums of the layers' unit counts
     int* done;                              // [n_layers][CH_MAX_NSUB][m_tiles] epilogue-warp arrivals, zeroed before the launch
+    int* next_unit;                         // the unit queue's head (dynamic scheduling), zeroed before the launch
+    int dynamic;                            // 1: clusters take units from the queue as they become free; 0: static round robin
     ChainDep dep[CH_MAX_LAYERS];
     UmmaConvParams L[CH_MAX_LAYERS];
 };
 static_assert(sizeof(ChainParams) <= 32000, "kernel parameters are limited to 32764 bytes (CUDA >= 12.1, sm_70+)");
+
+// cluster-scope barrier operations for the unit queue (the leader CTA hands unit numbers to its peer through distributed
+// shared memory: the peer must see the number the remote store wrote once it has seen the remote arrival)
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+constexpr int CH_SCHED = 3;                               // unit-queue slots per cluster (producer runs <= 2 units ahead of the epilogue)
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
@@ -892,6 +933,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
     auto tmem_full_bar = [&](int b) { return bars_t + 8u * b; };
     auto tmem_empty_bar = [&](int b) { return bars_t + 16u + 8u * b; };
     const uint32_t tmem_slot = bars_t + 32u;
+    // unit queue: sched_full[s] in every CTA (1 arrival: the leader's producer), sched_empty[s] in the leader (18 arrivals: its
+    // MMA warp + 8 epilogue warps, the peer's producer + 8 epilogue warps), sched_id[s] in every CTA
+    auto sched_full = [&](int s) { return bars_t + 64u + 8u * s; };
+    auto sched_empty = [&](int s) { return bars_t + 64u + 8u * (CH_SCHED + s); };
+    auto sched_id = [&](int s) { return bars_t + 64u + 16u * CH_SCHED + 4u * s; };
 
     // unit g of the chain -> layer l (g is monotonic per role, so l only ever advances) and the unit inside the layer;
     // a unit = one N tile x two consecutive M tiles, CTA `rank` owns M tile 2 * group + rank (a missing second tile is
@@ -915,6 +961,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
         for (int s = 0; s < RA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
         for (int s = 0; s < RB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tmem_full_bar(b), 1); mbar_init(tmem_empty_bar(b), 512); }
+        for (int s = 0; s < CH_SCHED; ++s) { mbar_init(sched_full(s), 1); mbar_init(sched_empty(s), 18); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -930,12 +977,48 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
     pdl_wait();
     const unsigned long long t_dep = (cp.L[0].debug & 16) ? gtime_ns() : 0ull;
 
+    // Unit sequence of this cluster.  Static: unit0, unit0 + unit_step, ...  Dynamic: the leader's producer warp takes the
+    // next unit of the list from a global counter when it is ready to load it and publishes the number to both CTAs; every
+    // other role reads it from its CTA's queue slot.  Units are handed out in list order, and a unit only ever waits for
+    // units EARLIER in the list, each of which is already held by a resident cluster: no deadlock.
+    int q_slot = 0; uint32_t q_phase = 0; int g_static = unit0;
+    auto q_advance = [&]() { if (++q_slot == CH_SCHED) { q_slot = 0; q_phase ^= 1u; } };
+    // consumer side (whole warp calls it): next unit or -1
+    auto next_unit_consumer = [&]() -> int {
+        if (!cp.dynamic) { const int g = g_static; g_static += unit_step; return g < total_units ? g : -1; }
+        mbar_wait_acquire_cluster(sched_full(q_slot), q_phase);
+        const int g = (int)ld_shared_u32(sched_id(q_slot));
+        __syncwarp();
+        if (lane == 0) mbar_arrive_release_cluster(mapa_rank(sched_empty(q_slot), 0));
+        q_advance();
+        return g;
+    };
+
     if (warp == 0) {
         // ------------------------------------------------ TMA producer (both CTAs)
         int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
         int l = 0;
         const bool timed = (cp.L[0].debug & 16) != 0;
-        for (int g = unit0; g < total_units; g += unit_step) {
+        while (true) {
+            int g;
+            if (cp.dynamic && rank == 0) {
+                // scheduler: wait until every reader has taken the number that occupied this slot, take the next unit
+                mbar_wait(sched_empty(q_slot), q_phase ^ 1u);
+                int gq = 0;
+                if (lane == 0) {
+                    gq = atomicAdd(cp.next_unit, 1);
+                    if (gq >= total_units) gq = -1;
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sched_id(q_slot)), "r"((uint32_t)gq) : "memory");
+                    st_cluster_u32(mapa_rank(sched_id(q_slot), 1), (uint32_t)gq);
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sched_full(q_slot)) : "memory");
+                    mbar_arrive_release_cluster(mapa_rank(sched_full(q_slot), 1));
+                }
+                g = __shfl_sync(0xffffffffu, gq, 0);
+                q_advance();
+            } else {
+                g = next_unit_consumer();
+            }
+            if (g < 0) break;
             while (g >= cp.unit_start[l + 1]) ++l;
             const UmmaConvParams& p = cp.L[l];
             int bimg, y0, x0, n0, m_idx; bool real;
@@ -1017,7 +1100,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
             int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
             int l = 0;
             const bool timed = (cp.L[0].debug & 16) != 0;
-            for (int g = unit0; g < total_units; g += unit_step, ++tile_iter) {
+            for (;; ++tile_iter) {
+                const int g = next_unit_consumer();
+                if (g < 0) break;
                 while (g >= cp.unit_start[l + 1]) ++l;
                 unsigned long long w_full = 0, w_tmem = 0;
                 const long long t_begin = timed ? clock64() : 0;
@@ -1074,7 +1159,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
         uint32_t tile_iter = 0;
         int l = 0;
         const bool timed = (cp.L[0].debug & 16) != 0 && warp == 2;
-        for (int g = unit0; g < total_units; g += unit_step, ++tile_iter) {
+        for (;; ++tile_iter) {
+            const int g = next_unit_consumer();
+            if (g < 0) break;
             while (g >= cp.unit_start[l + 1]) ++l;
             const UmmaConvParams& p = cp.L[l];
             int bimg, y0, x0, n0, m_idx; bool real;
@@ -1319,6 +1406,7 @@ int fill_chain_layer(const UmmaConvArgs& a, UmmaConvParams& p) {
     p.out_f32 = a.out_f32; p.out_f32_pitch = a.out_f32_pitch;
     p.out_hi = a.out_hi; p.out_lo = a.out_lo; p.out_h_pitch = a.out_h_pitch;
     p.zbuf = a.zbuf; p.hbuf = a.hbuf;
+    p.fl_coords1 = a.fl_coords1; p.fl_flow = a.fl_flow; p.fl_dflow = a.fl_dflow;
     p.side_tiled = a.side_tiled; p.out_tiled = a.out_tiled;
     p.stride = 1;
     p.debug = b2p_options().conv_debug & 16;             // clock counters only; the drop-a-stage experiments are gen-2 only
@@ -1478,9 +1566,11 @@ int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const B2PChainDep* de
         }
     }
     cp.done = done_ws;
-    B2P_CUDA(cudaMemsetAsync(done_ws, 0, (size_t)n * CH_MAX_NSUB * cp.m_tiles * sizeof(int), s));
+    cp.next_unit = done_ws + (size_t)n * CH_MAX_NSUB * cp.m_tiles;
+    cp.dynamic = b2p_options().chain_dynamic != 0;
+    B2P_CUDA(cudaMemsetAsync(done_ws, 0, ((size_t)n * CH_MAX_NSUB * cp.m_tiles + 1) * sizeof(int), s));
     int nclusters = sms / 2;
-    const size_t smem = (size_t)cp.ring_a * CH_A_SLOT + (size_t)cp.ring_b * CH_B_SLOT + 1024 + 16 * (cp.ring_a + cp.ring_b) + 64;
+    const size_t smem = (size_t)cp.ring_a * CH_A_SLOT + (size_t)cp.ring_b * CH_B_SLOT + 1024 + 16 * (cp.ring_a + cp.ring_b) + 64 + 256;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nclusters * 2); cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[2];
@@ -1512,4 +1602,4 @@ int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const B2PChainDep* de
 }
 
 // ints of device scratch b2p_launch_conv_chain needs for n layers over m_tiles pixel tiles
-size_t b2p_conv_chain_done_ints(int n, int m_tiles) { return (size_t)n * CH_MAX_NSUB * m_tiles; }
+size_t b2p_conv_chain_done_ints(int n, int m_tiles) { return (size_t)n * CH_MAX_NSUB * m_tiles + 1; }

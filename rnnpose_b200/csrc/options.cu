@@ -17,7 +17,7 @@ const OptDesc kOpts[] = {
     // second-generation kernel, bit 4 the chained single-launch update block; 0 = first-generation kernel
     {"conv_mode", "B200POSE_CONV_MODE", &B2POptions::conv_mode, 19},
     {"fg_list", "B200POSE_FG_LIST", &B2POptions::fg_list, 1},               // LM over the per-call foreground list
-    {"fg_pipeline", "B200POSE_FG_PIPELINE", &B2POptions::fg_pipeline, 1},   // compact channels-last upsample+weight + cluster LM
+    {"fg_pipeline", "B200POSE_FG_PIPELINE", &B2POptions::fg_pipeline, 2},   // channels-last target/weight kernels + cluster LM: 0 off, 1 on, 2 when geofea2 is channels-last
     {"fg_upsample", "B200POSE_FG_UPSAMPLE", &B2POptions::fg_upsample, 0},   // round-1 list-driven upsample kernel (NCHW planes)
     {"sparse_g1", "B200POSE_SPARSE_G1", &B2POptions::sparse_g1, 1},         // host entry: fetch geofea1 only where depth > 0
     {"fg_blocks", "B200POSE_FG_BLOCKS", &B2POptions::fg_blocks, 8},
@@ -27,6 +27,7 @@ const OptDesc kOpts[] = {
     {"pool_mode", "B200POSE_POOL_MODE", &B2POptions::pool_mode, 1},         // 1 = three pyramid levels in one pass
     {"lm_debug", "B200POSE_LM_DEBUG", &B2POptions::lm_debug, 0},            // 1 = drop the fp64 contraction (timing A/B only)
     {"chain_rings", "B200POSE_CHAIN_RINGS", &B2POptions::chain_rings, 24},  // chained launch: 10 * activation slots + weight slots
+    {"chain_dynamic", "B200POSE_CHAIN_DYNAMIC", &B2POptions::chain_dynamic, 1},   // chained launch: units from a global queue (1) or static round robin (0)
 };
 constexpr int kNumOpts = (int)(sizeof(kOpts) / sizeof(kOpts[0]));
 

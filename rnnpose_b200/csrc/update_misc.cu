@@ -342,6 +342,12 @@ int b2p_pack_weights(const float* const* t, float* packed, cudaStream_t s) {
     if ((rc = packh(CV_HEADS, t[22], 256, 128, 3, 3, 0, 0))) return rc;
     if ((rc = packh(CV_HEADS, t[26], 256, 128, 3, 3, 256, 0))) return rc;
     if ((rc = packh(CV_MASK2, t[28], 576, 256, 1, 1, 0, 0))) return rc;
+    {   // flow_head.conv2 for the chained launch: rows 2..31 of every tap stay zero
+        const B2PHalfConvDesc& d = HL.fh2;
+        pack_conv_half_kernel<<<(unsigned)((2 * 256 * 9 + 255) / 256), 256, 0, s>>>(t[24], 2, 256, 3, 3, hbase + d.hi_off, hbase + d.lo_off,
+                                                                                  d.cin_pad, d.cout_pad, 0, 0);
+        B2P_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -358,6 +364,14 @@ const B2PHalfLayout& b2p_half_layout() {
             d.cin_pad = (d.cin + 63) / 64 * 64;
             d.cout_pad = (d.cout + d.n_tile - 1) / d.n_tile * d.n_tile;
             const size_t n = (size_t)d.kh * d.kw * d.cout_pad * d.cin_pad;
+            d.hi_off = off; off += n;
+            d.lo_off = off; off += n;
+            off = (off + 127) / 128 * 128;
+        }
+        {
+            B2PHalfConvDesc& d = H.fh2;
+            d.kh = d.kw = 3; d.cin = 256; d.cout = 2; d.n_tile = 32; d.cin_pad = 256; d.cout_pad = 32;
+            const size_t n = (size_t)9 * d.cout_pad * d.cin_pad;
             d.hi_off = off; off += n;
             d.lo_off = off; off += n;
             off = (off + 127) / 128 * 128;

@@ -436,5 +436,5 @@ def refine_iters_host(packed: torch.Tensor, fmap1, fmap2, context, geofea1, geof
     return G, scratch
 
 
-def launch_count(n_iters: int, n_lm: int) -> int:
-    return _lib.lib().b200pose_refine_launch_count(n_iters, n_lm)
+def launch_count(B: int, H: int, W: int, n_iters: int, n_lm: int) -> int:
+    return _lib.lib().b200pose_refine_launch_count(B, H, W, n_iters, n_lm)

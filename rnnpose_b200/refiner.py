@@ -184,7 +184,7 @@ class PoseRefiner(nn.Module):
             B = pc_depth.shape[0]
             # zoom-crop on device (reference :145-218,:287,:292): foreground box, crop intrinsics and both crops in one
             # entry; the descriptors leave channels-last, which is what the loop's foreground pipeline reads
-            cl = geofea_2d.shape[1] == 32 and ops.get_option("fg_list") != 0 and ops.get_option("fg_pipeline") != 0
+            cl = geofea_2d.shape[1] == 32 and ops.get_option("fg_list") != 0 and ops.get_option("fg_pipeline") != 0   # (0 = dense kernels: NCHW)
             zc = ops.zoom_crop(pc_depth[:, 0].contiguous().float(), intrinsics.detach().float().contiguous(), T_mat.float().contiguous(),
                                image.float().contiguous(), geofea_2d.float().contiguous(), (Hc, Wc), channels_last=cl)
             K_crop, image_crop, geofea2_crop = zc["K_crop"], zc["image_crop"], zc["geofea_crop"]
