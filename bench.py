@@ -69,21 +69,46 @@ def load_weights():
     return load_update_weights()
 
 
-def make_inputs(rank: int, batch: int, unique: int, H: int, W: int, occlude: bool = False):
-    """CPU float32 inputs of the inner loop for `batch` objects (unique scenes tiled)."""
+def make_inputs(rank: int, batch: int, unique: int, H: int, W: int, occlude: bool = False, fmap_fn=None):
+    """CPU float32 inputs of the inner loop for `batch` objects (unique scenes tiled).  fmap_fn(syn_img, obs_img) -> (fmap1,
+    fmap2) supplies the feature maps (the library's encoder on the GPU); without it they are hash noise."""
     from rnnpose_b200 import synthetic as S
     unique = min(unique, batch)
     idx = [rank * unique + i for i in range(unique)]
-    mb = S.make_batch(idx, H, W, occlude=occlude, with_images=False)
+    mb = S.make_batch(idx, H, W, occlude=occlude, with_images=fmap_fn is not None)
+    h, w = H // 8, W // 8
+    if fmap_fn is not None:
+        f1, f2 = fmap_fn(mb.pop("syn_img"), mb.pop("obs_img"))
+    else:
+        f1, f2 = S.hash_features((unique, 256, h, w), 9000 + rank), S.hash_features((unique, 256, h, w), 9500 + rank)
     rep = (batch + unique - 1) // unique
     out = {k: v.repeat(rep, *([1] * (v.dim() - 1)))[:batch].contiguous() for k, v in mb.items()}
-    h, w = H // 8, W // 8
-    out["fmap1"] = S.hash_features((unique, 256, h, w), 9000 + rank).repeat(rep, 1, 1, 1)[:batch].contiguous()
-    out["fmap2"] = S.hash_features((unique, 256, h, w), 9500 + rank).repeat(rep, 1, 1, 1)[:batch].contiguous()
+    out["fmap1"] = f1.repeat(rep, 1, 1, 1)[:batch].contiguous()
+    out["fmap2"] = f2.repeat(rep, 1, 1, 1)[:batch].contiguous()
     out["depth"] = out["depth"][:, 0].contiguous()
     out["G0"] = torch.eye(4)[None].repeat(batch, 1, 1).contiguous()
     out["scene_idx"] = torch.tensor(idx).repeat(rep)[:batch]
     return out
+
+
+def encoder_fmap_fn(dev):
+    """Feature maps from the library's own RAFT encoder kernels (csrc/encoder.cu, shipped img_fea_enc weights) on the synthetic
+    crop pair, computed once before the timed region (the metric starts from resident feature maps).  Returns
+    (fn, description); falls back to hash-noise maps if the encoder cannot run."""
+    try:
+        from rnnpose_b200 import ops
+        from rnnpose_b200.assets import load_encoder_weights
+        packed = ops.encoder_pack_weights(load_encoder_weights(), dev)
+
+        def fn(a, b):
+            f1, f2 = ops.image_encoder(packed, a.to(dev).contiguous(), b.to(dev).contiguous())
+            torch.cuda.synchronize()
+            if not (torch.isfinite(f1).all() and torch.isfinite(f2).all()):
+                raise RuntimeError("non-finite encoder output")
+            return f1.cpu(), f2.cpu()
+        return fn, "feature maps from the library's RAFT encoder kernels on the synthetic crops (shipped img_fea_enc weights)"
+    except Exception as e:  # noqa: BLE001
+        return None, f"hash-noise feature maps (encoder unavailable: {type(e).__name__})"
 
 
 class ClockSampler:
@@ -325,7 +350,12 @@ def run_workload(args, cfg, per_gpu, rank, local_rank, world, dev, numa, want_cp
     # resident inputs: one chunk's worth per distinct chunk (up to 4 distinct chunks; more chunks re-use them round robin --
     # every chunk is still far larger than the 126 MB L2)
     n_res = min(n_chunks, 4 if H * W <= 240 * 320 else 1)
-    inputs = [make_inputs(rank * n_res + c, chunk, UNIQUE_SCENES, H, W, occl) for c in range(n_res)]
+    fmap_fn, fmap_desc = (None, "hash-noise feature maps") if args.fmaps == "hash" else encoder_fmap_fn(dev)
+    try:
+        inputs = [make_inputs(rank * n_res + c, chunk, UNIQUE_SCENES, H, W, occl, fmap_fn) for c in range(n_res)]
+    except Exception as e:  # noqa: BLE001  (the benchmark of the loop must not depend on the encoder row)
+        fmap_desc = f"hash-noise feature maps (encoder failed: {type(e).__name__})"
+        inputs = [make_inputs(rank * n_res + c, chunk, UNIQUE_SCENES, H, W, occl) for c in range(n_res)]
     keys = ("fmap1", "fmap2", "context", "geofea1", "geofea2", "depth", "K", "G0")
     host = {k: inputs[0][k].pin_memory() for k in keys}                       # e2e: chunk 0's buffers, pinned after bind_numa
     d = [{k: (host[k] if c == 0 else inputs[c][k]).to(dev, non_blocking=True) for k in keys} for c in range(n_res)]
@@ -442,7 +472,7 @@ def run_workload(args, cfg, per_gpu, rank, local_rank, world, dev, numa, want_cp
             "metric": metric_name(cfg), "value": value, "unit": "poses/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
-            "data": f"synthetic (seeded ellipsoid scenes, {UNIQUE_SCENES} unique per chunk tiled to {chunk}; hash-noise feature maps; shipped gru_update weights)",
+            "data": f"synthetic (seeded ellipsoid scenes, {UNIQUE_SCENES} unique per chunk tiled to {chunk}; {fmap_desc}; shipped gru_update weights)",
             "config": {"workload": workload_name(cfg, per_gpu), "name": cfg, "global_batch": world * per_gpu,
                        "chunk": chunk, "chunks_per_step": n_chunks,
                        "parallelism": f"dp{world} (objects sharded, one all-gather of metrics)",
@@ -469,6 +499,7 @@ def main():
     ap.add_argument("--global-batch", type=int, default=None, help="total objects over all ranks (default: 32 per GPU; cfg4: 8 per GPU)")
     ap.add_argument("--chunk", type=int, default=None, help="objects per b200pose_refine_iters call (default: up to 64 at 240x320, 16 at 480x640)")
     ap.add_argument("--sweep", action="store_true", help="cfg4: batch-size sweep 8..512, one JSON line with a `sweep` list")
+    ap.add_argument("--fmaps", default="encoder", choices=["encoder", "hash"], help="feature maps: the library's encoder on the synthetic crops, or hash noise")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--cpu-objects", type=int, default=8)
     ap.add_argument("--exact-fp32", action="store_true", help="CUDA-core fp32 convolutions instead of the tcgen05 path")

@@ -999,19 +999,23 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
         int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
         int l = 0;
         const bool timed = (cp.L[0].debug & 16) != 0;
+        int sched_prefetched = 0;
+        if (cp.dynamic && rank == 0 && lane == 0) sched_prefetched = atomicAdd(cp.next_unit, 1);
         while (true) {
             int g;
             if (cp.dynamic && rank == 0) {
-                // scheduler: wait until every reader has taken the number that occupied this slot, take the next unit
+                // scheduler: wait until every reader has taken the number that occupied this slot, publish the unit fetched
+                // one trip ago, and fetch the following one now (the atomic's round trip hides behind this unit's loads)
                 mbar_wait(sched_empty(q_slot), q_phase ^ 1u);
                 int gq = 0;
                 if (lane == 0) {
-                    gq = atomicAdd(cp.next_unit, 1);
+                    gq = sched_prefetched;                                   // first trip: fetched before the loop
                     if (gq >= total_units) gq = -1;
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(sched_id(q_slot)), "r"((uint32_t)gq) : "memory");
                     st_cluster_u32(mapa_rank(sched_id(q_slot), 1), (uint32_t)gq);
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sched_full(q_slot)) : "memory");
                     mbar_arrive_release_cluster(mapa_rank(sched_full(q_slot), 1));
+                    if (gq >= 0) sched_prefetched = atomicAdd(cp.next_unit, 1);
                 }
                 g = __shfl_sync(0xffffffffu, gq, 0);
                 q_advance();

@@ -1,13 +1,14 @@
 """Drop-in replacement of the reference's ``model.PoseRefiner.PoseRefiner``.
 
 Same constructor signature, same parameter names/shapes (``sigma.0``, ``cf_net.update_block.*``; plus
-``image_fea_enc.*`` when the reference's encoder is attached) so that the reference's shape-matched checkpoint
+``image_fea_enc.fnet.*``: the encoder mirror of ``rnnpose_b200.encoder``) so that the reference's shape-matched checkpoint
 loader (reference tools/eval.py:386-408) fills them, same ``forward(image, Ts, intrinsics, fea_3d, Tj_gt, obj_cls,
 geofea_3d, geofea_2d)`` and the same return dict (reference model/PoseRefiner.py:366-376).
 
 What runs where:
-  * the OUTER render loop (reference PoseRefiner.py:239-313) stays PyTorch: it calls the injected renderer and the
-    injected feature encoder (both out of scope) and builds the zoom-crop.  The crop geometry of
+  * the OUTER render loop (reference PoseRefiner.py:239-313) stays PyTorch: it calls the injected renderer (out of scope,
+    SURVEY section 2) and the feature encoder (by default the library's own RAFT encoder kernels behind
+    ``rnnpose_b200.encoder.ImageFeaEncoder``).  The crop geometry of
     ``gen_zoom_crop_grids`` / ``get_affine_transformation`` (reference :145-213) and the two grid_sample crops run in the
     library's zoom-crop kernels (``ops.zoom_crop``: bounding box by atomics, closed-form axis-aligned affine, fused
     resample), removing the reference's numpy/cv2 host round-trip; ``zoom_crop_params`` below is
@@ -115,11 +116,11 @@ class PoseRefiner(nn.Module):
         if self._cfg("FLOW_NET", "raft") != "raft":
             raise NotImplementedError
         if image_fea_enc is None:
-            try:                                   # inside the reference tree: use its encoder (stays PyTorch)
-                from model.CFNet import ImageFeaEncoder          # type: ignore
-                image_fea_enc = ImageFeaEncoder()
-            except Exception:
-                image_fea_enc = None
+            # the library's own encoder kernels behind the reference's module layout (state-dict keys image_fea_enc.fnet.*,
+            # shipped img_fea_enc weights loaded as the reference's constructor does, model/CFNet.py:33-37); any nn.Module with
+            # forward(image1, image2) -> (fmap1, fmap2) -- e.g. the reference's ImageFeaEncoder -- can be passed instead
+            from .encoder import ImageFeaEncoder
+            image_fea_enc = ImageFeaEncoder()
         self.image_fea_enc = image_fea_enc
         self.cf_net = _CFNetParams()
         self.renderer = renderer

@@ -136,3 +136,44 @@ def test_zoom_crop_kernel_matches_reference_cv2_path():
     grid2 = F.affine_grid(odd["theta"][:1], torch.Size([1, 1, 50, 70]), align_corners=False)
     torch.testing.assert_close(odd["geofea_crop"][0].view(50, 70, 32).permute(2, 0, 1), F.grid_sample(geo2[:1], grid2, align_corners=False)[0],
                                rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.gpu
+def test_pose_refiner_standalone_with_library_encoder():
+    """The drop-in with its default encoder (the library's RAFT encoder kernels; nothing from the reference tree): two render
+    iterations end to end on the GPU, checked against the CPU oracles chained the same way (encoder oracle -> refine oracle on
+    the crops the zoom-crop kernel produced)."""
+    from oracle import encoder_oracle as E, refine_oracle as O
+    from rnnpose_b200 import ops
+    from rnnpose_b200.assets import load_encoder_weights
+    dev = torch.device("cuda:0")
+    sc = scene(0)
+    image, geo2, K, T0, Tgt = inputs(sc)
+    cfg = {"FLOW_NET": "raft", "IS_CALIBRATED": True, "ITER_COUNT": 2, "RENDER_ITER_COUNT": 1, "OPTIM_ITER_COUNT": 2}
+    net = PoseRefiner(cfg, renderer=S.AnalyticRenderer([sc]), render_image_size=IMG_HW, zoom_crop_size=CROP_HW)
+    sd = net.state_dict()
+    assert any(k.startswith("image_fea_enc.fnet.conv1") for k in sd) and len([k for k in sd if k.startswith("image_fea_enc.")]) == 32
+    net.cf_net.load_state_dict({"update_block." + kk: v for kk, v in load_update_weights().items()}, strict=True)
+    net = net.to(dev)
+    # images in [0,255] as a well-conditioned encoder input (the reference pipeline feeds [0,1], SURVEY Appendix D8)
+    img255 = (image * 255.0).to(dev)
+    out = net(img255, SE3Sequence(matrix=T0.to(dev)), K.to(dev), fea_3d=torch.zeros(1, 4, 256, device=dev),
+              Tj_gt=SE3Sequence(matrix=Tgt.to(dev)), obj_cls=None, geofea_3d=torch.zeros(1, 4, 32, device=dev), geofea_2d=geo2.to(dev))
+    G = out["Ti_pred"].G[0, 0].cpu()
+    assert torch.isfinite(G).all() and out["flow"][0].shape == (1, 2, *CROP_HW)
+    # CPU chain on the same crops
+    ren = S.AnalyticRenderer([sc])
+    pc = ren.render_pointcloud(None, T=T0[:, 0], K=K, render_image_size=IMG_HW)
+    zc = ops.zoom_crop(pc[:, 0].contiguous().to(dev), K.to(dev), T0[:, 0].contiguous().to(dev), img255, geo2.to(dev), CROP_HW)
+    Kc = zc["K_crop"].cpu()
+    color, depth = ren(None, torch.zeros(1, 4, 288), T=T0[:, 0], K=Kc, render_image_size=CROP_HW, render_tex=True)
+    syn_img, cfea, geo1 = torch.split(color, [3, 256, 32], dim=1)
+    syn_depth = ren.render_depth(None, T=T0[:, 0], K=Kc, render_image_size=CROP_HW)
+    with torch.no_grad():
+        f1, f2 = E.image_encoder(load_encoder_weights(), syn_img, zc["image_crop"].cpu())
+        ref = O.refine_inner_loop(load_update_weights(), f1, f2, cfea * 0.1, geo1, zc["geofea_crop"].cpu(), syn_depth, Kc,
+                                  torch.eye(4)[None], n_iters=2, n_lm=2)
+    Ti_ref = torch.matmul(ref["G"][0], T0[0, 0])
+    err = (G - Ti_ref).abs().max().item()
+    print(f"[dropin standalone] max |dSE3| vs CPU oracle chain = {err:.3e}")
+    assert err < 1e-3        # syn_img is in [0,1] here (renderer output): the encoder is ill-conditioned on it, see test_gpu_encoder.py

@@ -53,22 +53,27 @@ def test_encoder_matches_reference_golden(enc):
 
 def test_encoder_batched_vs_oracle_and_batch_invariance(enc):
     """A machine-filling batch (CTA-pair kernels, several persistent rounds) against the oracle on a subset; a sample's maps do
-    not depend on its position in the batch or on the batch size."""
+    not depend on its position in the batch.  The synthetic images are scaled to [0,255] (what the network's normalisation
+    expects): on [0,1] input the InstanceNorm layers amplify rounding and no tight bound exists."""
     ops, packed = enc
     d = torch.device("cuda:0")
     mb = S.make_batch([3, 4], 240, 320, with_images=True)
-    a = mb["syn_img"].repeat(8, 1, 1, 1).contiguous(); b = mb["obs_img"].repeat(8, 1, 1, 1).contiguous()
+    syn, obs = mb["syn_img"] * 255.0, mb["obs_img"] * 255.0
+    a = syn.repeat(8, 1, 1, 1).contiguous(); b = obs.repeat(8, 1, 1, 1).contiguous()
     f1, f2 = ops.image_encoder(packed, a.to(d), b.to(d))
     f1, f2 = f1.cpu(), f2.cpu()
     assert torch.isfinite(f1).all() and torch.isfinite(f2).all()
     for k in range(2, 16):
         assert torch.equal(f1[k], f1[k % 2]) and torch.equal(f2[k], f2[k % 2])
     with torch.no_grad():
-        r1, r2 = E.image_encoder(load_encoder_weights(), mb["syn_img"], mb["obs_img"])
-    torch.testing.assert_close(f1[:2], r1, rtol=5e-3, atol=5e-3); torch.testing.assert_close(f2[:2], r2, rtol=5e-3, atol=5e-3)
-    g1, g2 = ops.image_encoder(packed, mb["syn_img"][:1].to(d).contiguous(), mb["obs_img"][:1].to(d).contiguous())
+        r1, r2 = E.image_encoder(load_encoder_weights(), syn, obs)
+    _close(f1[:2], r1, "batched 240x320 fmap1"); _close(f2[:2], r2, "batched 240x320 fmap2")
+    g1, g2 = ops.image_encoder(packed, syn[:1].to(d).contiguous(), obs[:1].to(d).contiguous())
     # (small batches run M=128 tiles, the large one CTA pairs with M=256: same products, possibly another summation grouping)
-    torch.testing.assert_close(g1.cpu(), f1[:1], rtol=5e-3, atol=5e-3); torch.testing.assert_close(g2.cpu(), f2[:1], rtol=5e-3, atol=5e-3)
+    _close(g1.cpu(), f1[:1], "B=1 vs B=16"); _close(g2.cpu(), f2[:1], "B=1 vs B=16")
+    # the ill-conditioned [0,1] case stays finite and batch-invariant
+    h1, h2 = ops.image_encoder(packed, mb["syn_img"].repeat(8, 1, 1, 1).contiguous().to(d), mb["obs_img"].repeat(8, 1, 1, 1).contiguous().to(d))
+    assert torch.isfinite(h1).all() and torch.equal(h1[2], h1[0]) and torch.equal(h2[3], h2[1])
 
 
 def test_encoder_module_mirror_and_error_codes(enc):
@@ -97,6 +102,7 @@ def test_refine_on_encoder_features(enc):
     d = torch.device("cuda:0")
     H, W = 128, 160
     mb = S.make_batch([7, 8], H, W, with_images=True)
+    mb["syn_img"] = mb["syn_img"] * 255.0; mb["obs_img"] = mb["obs_img"] * 255.0      # well-conditioned encoder input
     f1, f2 = ops.image_encoder(packed, mb["syn_img"].to(d), mb["obs_img"].to(d))
     wts = load_update_weights()
     pk = ops.pack_weights(wts, d)
@@ -110,5 +116,5 @@ def test_refine_on_encoder_features(enc):
     err = (G.cpu() - ref["G"]).abs().max().item()
     print(f"[encoder+refine] max |dSE3| vs oracle chain = {err:.3e}")
     # the 1e-4 bar is defined for the loop on IDENTICAL feature maps (tests/test_gpu_refine.py); here the two encoders' maps
-    # already differ at the 1e-3 level on these [0,1] images (ill-conditioned InstanceNorm, see above), so the bound is looser
-    assert err < 1e-3
+    # differ at the 1e-5 level, which the correlation / GRU chain may amplify
+    assert err < 5e-4

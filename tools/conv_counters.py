@@ -59,6 +59,11 @@ if CHAIN:
               f"{pe[4]:13.0f} {pe[5]:9.0f} {pe[5] / max(m[6], 1e-9):10.0f}")
     print(f"sum     {tot[6]:5.1f} | {tot[0]:8.0f}           | {tot[1]:9.0f} {tot[2]:10.0f} | {tot[3]:15.0f} {tot[7]:9.0f} | {tot[4]:13.0f} {tot[5]:9.0f}")
     print(f"  (1 us = 1965 clocks; MMA-loop sum = {tot[0] / 1965:.0f} us per launch)")
+    per_cta = v[:, :, 0].sum(0) / 4.0                       # MMA-loop clocks per leader CTA, summed over layers (and pre-sums)
+    act = per_cta[per_cta > 0]
+    units = (v[:, :, 6].sum(0) / 4.0)[per_cta > 0]
+    print(f"  per-cluster MMA-loop total: min {act.min() / 1965:.0f}  mean {act.mean() / 1965:.0f}  max {act.max() / 1965:.0f} us; "
+          f"units per cluster: min {units.min():.1f} mean {units.mean():.1f} max {units.max():.1f}")
 print(f"mode {ops.get_option('conv_mode')}: clocks per launch, mean over the CTAs that issue MMAs (4 launches per layer + GRU pre-sums)")
 print("layer   units stages | MMA-loop | wait full  wait tmem | prod wait empty | epi wait full  epi busy | loop clk/stage  epi busy/unit")
 for i, n in enumerate(names):
