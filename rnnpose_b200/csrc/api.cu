@@ -22,6 +22,7 @@ struct Carver {
 // ([0] = hi, [1] = lo) serve the tensor-core path.
 struct UpdateWs {
     float *col, *c1, *corflo, *f1o, *zbuf, *rhbuf, *hm;
+    float* hbuf_x;            // tensor-core path: the hidden state's second tiled copy, x-major tile order (chained launch)
     float* pre[4];            // GRU partial sums of the iteration-invariant `inp` channels: zr1 [P][256], q1 [P][128], zr2, q2
     float* zero_bias;         // 1024 zeros
     __half *corr_h[2], *col_h[2], *c1_h[2], *corflo_h[2], *f1o_h[2], *x_h[2], *net_h[2], *rh_h[2], *hm_h[2];
@@ -39,6 +40,7 @@ size_t update_ws_layout(int B, int h, int w, void* ws, size_t cap, UpdateWs* out
     u.zbuf = c.take<float>(Pt * 128);
     u.rhbuf = c.take<float>(Pt * 128);             // exact path: r*h (PXC); tensor-core path: the hidden state h (tiled)
     u.hm = c.take<float>(P * 512);
+    u.hbuf_x = c.take<float>(Pt * 128);
     u.pre[0] = c.take<float>(Pt * 256); u.pre[1] = c.take<float>(Pt * 128);
     u.pre[2] = c.take<float>(Pt * 256); u.pre[3] = c.take<float>(Pt * 128);
     u.zero_bias = c.take<float>(1024);
@@ -188,7 +190,7 @@ int run_update_block_tc_chain(const float* wts, float* net, float* coords1, floa
         a.B = B; a.h = h; a.w = w; a.epi = epi; a.scale = scale;
         a.out_f32 = out_f32; a.out_f32_pitch = f32_pitch;
         if (dst) { a.out_hi = dst[0] + doff; a.out_lo = dst[1] + doff; a.out_h_pitch = dpitch; }
-        a.zbuf = u.zbuf; a.hbuf = u.rhbuf; a.side_tiled = 1;
+        a.zbuf = u.zbuf; a.hbuf = u.rhbuf; a.hbuf_x = u.hbuf_x; a.side_tiled = 1;
     };
     const float* pz1 = use_pre ? u.pre[0] : nullptr; const float* pq1 = use_pre ? u.pre[1] : nullptr;
     const float* pz2 = use_pre ? u.pre[2] : nullptr; const float* pq2 = use_pre ? u.pre[3] : nullptr;
@@ -472,6 +474,7 @@ int b200pose_update_block(const void* packed_weights, float* net, float* xbuf, c
     if ((rc = b2p_split_planes(xbuf, 256, 128, P, u.x_h[0], u.x_h[1], 256, s))) return rc;
     // the tensor-core epilogues keep the fp32 hidden state in the tiled side-buffer layout (u.rhbuf)
     if ((rc = b2p_pxc_to_tiled(net, u.rhbuf, B, h, w, 128, s))) return rc;
+    if ((rc = b2p_pxc_to_tiled(net, u.hbuf_x, B, h, w, 128, s, 1))) return rc;
     if ((rc = run_update_block_tc(wts, net, coords1, flow, mask, dflow_out, B, h, w, u, false, s))) return rc;
     return b2p_tiled_to_pxc(u.rhbuf, net, B, h, w, 128, s);
 }
@@ -631,7 +634,7 @@ size_t b200pose_refine_workspace_bytes(int B, int H, int W) { return refine_ws_l
 int b200pose_refine_launch_count(int B, int H, int W, int n_iters, int n_lm) {
     // Kernels b200pose_refine_iters enqueues on the tensor-core path with C_geo = 32 and the current options:
     //   per call: LM counter reset, 2 feature-map transposes, volume GEMM, pooling (1 pass, or 3), context init, hidden state to
-    //   the tiled layout; with n_iters > 0: 3 for the foreground list (+ 2 for the pipeline's channels-last descriptors);
+    //   the two tiled layouts; with n_iters > 0: 3 for the foreground list (+ 2 for the pipeline's channels-last descriptors);
     //   with n_iters > 1: the 4 GRU partial-sum GEMMs (1 chained launch, or 4);  per recurrent iteration: flow_init, lookup, im2col, the convolutions
     //   (1 chained launch incl. the flow head, or 11 + 2), upsample/target/weight (2 with the pipeline, else 1), one launch
     //   for all LM steps
@@ -641,7 +644,7 @@ int b200pose_refine_launch_count(int B, int H, int W, int n_iters, int n_lm) {
     const bool chain = (o.conv_mode & 16) && B * ceil_div(h, B2P_TILE_ROWS) * ceil_div(w, B2P_TILE_COLS) >= 296;
     const bool pool3 = o.pool_mode == 1 && (size_t)(h * w + (h >> 1) * (w >> 1) + (h >> 2) * (w >> 2)) * sizeof(float) <= 40 * 1024;
     const bool pipe = o.fg_list != 0 && o.fg_pipeline == 1;      // (2 = only with channels-last geofea2, which this count does not assume)
-    const int per_call = 4 + (pool3 ? 1 : 3) + 2 + (n_iters > 0 && o.fg_list ? 3 + (pipe ? 2 : 0) : 0) + (n_iters > 1 ? (chain ? 1 : 4) : 0);
+    const int per_call = 4 + (pool3 ? 1 : 3) + 3 + (n_iters > 0 && o.fg_list ? 3 + (pipe ? 2 : 0) : 0) + (n_iters > 1 ? (chain ? 1 : 4) : 0);
     const int per_iter = 2 + 1 + (chain ? 1 : 13) + (pipe ? 2 : 1) + (n_lm > 0 ? 1 : 0);
     return per_call + n_iters * per_iter;
 }
@@ -674,6 +677,7 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
     else rc = b2p_context_init(context, B, H, W, r.net, r.xbuf, nullptr, nullptr, nullptr, nullptr, s);
     if (rc) return rc;
     if (tc && (rc = b2p_pxc_to_tiled(r.net, u.rhbuf, B, h, w, 128, s))) return rc;     // hidden state of the tensor-core epilogues
+    if (tc && (rc = b2p_pxc_to_tiled(r.net, u.hbuf_x, B, h, w, 128, s, 1))) return rc;  // ... and its x-major copy (chained launch)
     if (tc && n_iters > 1 && (rc = run_gru_precompute(wts, B, h, w, u, s))) return rc;
     // The rendered depth is fixed over the recurrent iterations: compact its foreground once and run the LM steps and the
     // upsample + weight kernel over the list (option fg_list = 0: dense kernels).

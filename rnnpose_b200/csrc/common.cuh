@@ -42,7 +42,7 @@ inline cudaError_t b2p_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 // into the library, changed afterwards only through b200pose_set_option.
 struct B2POptions {
     int conv_mode, fg_list, fg_pipeline, fg_upsample, sparse_g1, fg_blocks, tail_min_n, conv_debug, lookup_mode, pool_mode,
-        lm_debug, chain_rings, chain_dynamic;
+        lm_debug, chain_rings, chain_dynamic, chain_xmajor;
 };
 B2POptions& b2p_options();
 
@@ -129,7 +129,7 @@ static inline size_t b2p_tiled_pixels(int B, int h, int w) {       // pixel slot
     return (size_t)B * ((h + B2P_TILE_ROWS - 1) / B2P_TILE_ROWS) * ((w + B2P_TILE_COLS - 1) / B2P_TILE_COLS) * 128;
 }
 // fp32 [P][C] pixel-major <-> tiled
-int b2p_pxc_to_tiled(const float* src, float* dst, int B, int h, int w, int C, cudaStream_t s);
+int b2p_pxc_to_tiled(const float* src, float* dst, int B, int h, int w, int C, cudaStream_t s, int xmajor = 0);
 int b2p_tiled_to_pxc(const float* src, float* dst, int B, int h, int w, int C, cudaStream_t s);
 
 // fp16 weight planes: W[tap][cout_pad][cin_pad] (cin contiguous = K-major), cin_pad multiple of 64,
@@ -155,6 +155,7 @@ struct UmmaConvArgs {
     float* out_f32; int out_f32_pitch;
     __half* out_hi; __half* out_lo; int out_h_pitch;
     float* zbuf; float* hbuf;
+    float* hbuf_x;             // chained launch with x-major 1 x kw layers: the hidden state's copy in x-major tile order (or nullptr)
     float* fl_coords1; float* fl_flow; float* fl_dflow;   // EPI_FLOW: coords1 [P][2] in/out, flow [P][2] out, delta [P][2] out or nullptr
     unsigned chunk_mask;       // bit cc set = visit 64-channel chunk cc of every tap (0 = all chunks)
     const float* pre; int pre_pitch;   // fp32 [P][pre_pitch] partial sums added in the epilogue (or nullptr)

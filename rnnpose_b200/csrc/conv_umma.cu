@@ -68,6 +68,11 @@ struct UmmaConvParams {
     int dbg_layer;                     // row of g_conv_dbg (layer id + 1)
     int n_reverse;                     // conv_chain_kernel: list the layer's N tiles last-to-first
     int stride;                        // convolution stride (1, or 2 for the encoder's down-sampling layers; gen-1 / gen-2 without tap reuse)
+    // conv_chain_kernel, 1 x kw layers with horizontal-tap reuse: the activation box is ordered [x][y][C] (16 rows x 8+kw-1
+    // columns, x slow), one box serves all kw taps (tap kx = the same box 16 pixels = 2 swizzle atoms further on), and the
+    // accumulator row of a pixel is m = x * 16 + y instead of y * 8 + x
+    int xmajor;
+    float* hbuf_alt;                   // EPI_GRU_Q: second copy of the hidden state, kept in the OTHER pixel order (see api.cu)
     int debug;                         // timing experiments only (results are garbage): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue
 };
 
@@ -193,7 +198,7 @@ __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&w)[8]) 
 // through L2 (ld.global.cg) instead of the L1 / non-coherent path.
 template <bool COHERENT = false>
 __device__ __forceinline__ void epilogue_columns(const UmmaConvParams& p, uint32_t tmem_base, int warp, int q, int buf, int n0,
-                                                 int n_cnt, bool valid, size_t pix, int tile, int mrow) {
+                                                 int n_cnt, bool valid, size_t pix, int tile, int mrow, int mrow_alt = -1) {
     // float4 slot of channel c (multiple of 4) of this thread's pixel in a side buffer with C channels; step between
     // consecutive float4 slots: 1 (PXC) or 128 (tiled)
     const int sstep = p.side_tiled ? 128 : 1;
@@ -311,6 +316,11 @@ __device__ __forceinline__ void epilogue_columns(const UmmaConvParams& p, uint32
             float4* hp4 = const_cast<float4*>(side4(p.hbuf, 128, nb));
 #pragma unroll
             for (int j = 0; j < 8; ++j) hp4[j * sstep] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (p.hbuf_alt && mrow_alt >= 0) {             // the copy in the other pixel order (tiled buffers only)
+                float4* ha = reinterpret_cast<float4*>(p.hbuf_alt) + ((size_t)tile * 32 + (nb >> 2)) * 128 + mrow_alt;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ha[j * 128] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
         }
         // fp16 hi/lo planes for the next convolution: 16 channels = 32 bytes per store
         __half* dh = p.out_hi + pix * p.out_h_pitch + oc;
@@ -861,7 +871,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma2_kernel(const __grid_
 // (epilogue_columns<true>).  Shared memory: fixed-size ring slots for the largest layer.
 constexpr int CH_MAX_LAYERS = 12;
 constexpr int CH_MAX_NSUB = 3;                            // N units per tile of a layer (MASK2: 576 = 3 x 192)
-constexpr uint32_t CH_A_SLOT = 2u * 20u * 1024u;          // hi + lo planes of a 20-row activation box (5x1 with halo)
+// activation slot: hi + lo planes of the largest box of the launch -- 20 atoms (5x1 with halo rows) or 24 (1x5 with halo
+// columns, x-major) of 1024 bytes each; ChainParams::a_slot
 constexpr uint32_t CH_B_SLOT = 2u * 128u * 128u;          // hi + lo planes of 128 weight rows per CTA (256-channel tiles)
 
 struct ChainDep {
@@ -872,6 +883,7 @@ struct ChainDep {
 struct ChainParams {
     int n_layers, m_tiles;
     int ring_a, ring_b;                     // ring depths (option chain_rings)
+    uint32_t a_slot;                        // bytes of one activation ring slot
     int unit_start[CH_MAX_LAYERS + 1];     // prefix sums of the layers' unit counts
     int* done;                              // [n_layers][CH_MAX_NSUB][m_tiles] epilogue-warp arrivals, zeroed before the launch
     int* next_unit;                         // the unit queue's head (dynamic scheduling), zeroed before the launch
@@ -922,6 +934,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int RA = cp.ring_a, RB = cp.ring_b;
+    const uint32_t CH_A_SLOT = cp.a_slot;
     const uint32_t a_ring = smem_base, b_ring = smem_base + (uint32_t)RA * CH_A_SLOT;
     const uint32_t bars = b_ring + (uint32_t)RB * CH_B_SLOT;
     auto full_a = [&](int s) { return bars + 8u * s; };
@@ -1057,10 +1070,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
             const uint32_t b_plane = (uint32_t)b_rows * 128u;
             const uint32_t a_tx = 2u * 2u * a_plane, b_tx = 2u * 2u * b_plane;
             const int nb0 = n0 + (int)rank * b_rows;
-            const int outer_taps = p.a_taps == p.kh ? 1 : p.kh;
+            const int outer_taps = (p.xmajor || p.a_taps == p.kh) ? 1 : p.kh;
+            const int kxn = p.xmajor ? 1 : p.kw;                 // x-major: one box serves every horizontal tap
             for (int kyo = 0; kyo < outer_taps; ++kyo) {
                 const int ys = y0 + kyo - (p.kh >> 1);
-                for (int kx = 0; kx < p.kw; ++kx) {
+                for (int kx = 0; kx < kxn; ++kx) {
                     const int xs = x0 + kx - (p.kw >> 1);
                     for (int a = 0; a < p.n_active; ++a) {
                         const int cc = p.chunk_list[a];
@@ -1071,13 +1085,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
                         if (elect_one()) {
                             const uint32_t fb = mapa_rank(full_a(sa), 0);
                             if (rank == 0) mbar_expect_tx(full_a(sa), a_tx);
-                            tma_load_4d_pair(&p.a_hi[seg], da, fb, c0, xs, ys, bimg);
-                            tma_load_4d_pair(&p.a_lo[seg], da + a_plane, fb, c0, xs, ys, bimg);
+                            // tensor-map dimension order: (C, x, y, B), or (C, y, x, B) for the x-major boxes
+                            const int d1 = p.xmajor ? ys : xs, d2 = p.xmajor ? xs : ys;
+                            tma_load_4d_pair(&p.a_hi[seg], da, fb, c0, d1, d2, bimg);
+                            tma_load_4d_pair(&p.a_lo[seg], da + a_plane, fb, c0, d1, d2, bimg);
                         }
                         __syncwarp();
                         if (++sa == RA) { sa = 0; pha ^= 1u; }
                         for (int j = 0; j < p.a_taps; ++j) {
-                            const int tap = (kyo + j) * p.kw + kx;
+                            const int tap = p.xmajor ? j : (kyo + j) * p.kw + kx;
                             const uint32_t db = b_ring + (uint32_t)sb * CH_B_SLOT;
                             mbar_wait_timed(empty_b(sb), phb ^ 1u, timed, w_empty);
                             if (elect_one()) {
@@ -1113,8 +1129,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
                 const UmmaConvParams& p = cp.L[l];
                 const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((256u >> 4) << 24);
                 const uint32_t a_plane = (uint32_t)p.a_rows * 1024u, b_plane = (uint32_t)(p.n_tile >> 1) * 128u;
-                const int outer_taps = p.a_taps == p.kh ? 1 : p.kh;
-                const int a_items = outer_taps * p.kw * p.n_active;
+                const int outer_taps = (p.xmajor || p.a_taps == p.kh) ? 1 : p.kh;
+                const int a_items = outer_taps * (p.xmajor ? 1 : p.kw) * p.n_active;
+                const uint32_t tap_step = p.xmajor ? 2048u : 1024u;        // bytes between the A views of consecutive taps
                 const int buf = tile_iter & 1;
                 const uint32_t acc = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
                 mbar_wait_timed(tmem_empty_bar(buf), ((tile_iter >> 1) & 1) ^ 1, timed, w_tmem);
@@ -1128,8 +1145,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
                         tc_fence_after();
                         const uint32_t db = b_ring + (uint32_t)sb * CH_B_SLOT;
                         if (elect_one()) {
-                            const uint64_t a_hi = umma_desc_sw128(da + (uint32_t)j * 1024u);
-                            const uint64_t a_lo = umma_desc_sw128(da + a_plane + (uint32_t)j * 1024u);
+                            const uint64_t a_hi = umma_desc_sw128(da + (uint32_t)j * tap_step);
+                            const uint64_t a_lo = umma_desc_sw128(da + a_plane + (uint32_t)j * tap_step);
                             const uint64_t b_hi = umma_desc_sw128(db), b_lo = umma_desc_sw128(db + b_plane);
 #pragma unroll
                             for (int k = 0; k < BKC / 16; ++k) {
@@ -1171,14 +1188,17 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
             int bimg, y0, x0, n0, m_idx; bool real;
             decode(p, g - cp.unit_start[l], bimg, y0, x0, n0, real, m_idx);
             const int buf = tile_iter & 1;
-            const int yy = y0 + (mrow >> 3), xx = x0 + (mrow & 7);
+            // accumulator row -> pixel of the tile: y * 8 + x, or x * 16 + y for the x-major layers
+            const int ty = p.xmajor ? (mrow & 15) : (mrow >> 3), tx = p.xmajor ? (mrow >> 4) : (mrow & 7);
+            const int mrow_alt = p.xmajor ? (ty * 8 + tx) : (tx * 16 + ty);       // the same pixel's row in the other order
+            const int yy = y0 + ty, xx = x0 + tx;
             const bool valid = real && yy < p.h && xx < p.w;
             const size_t pix = ((size_t)bimg * p.h + yy) * p.w + xx;
             const long long e0 = timed ? clock64() : 0;
             mbar_wait_backoff(tmem_full_bar(buf), (tile_iter >> 1) & 1);
             const long long e1 = timed ? clock64() : 0;
             tc_fence_after();
-            epilogue_columns<true>(p, tmem_base, warp, q, buf, n0, p.n_tile, valid, pix, m_idx, mrow);
+            epilogue_columns<true>(p, tmem_base, warp, q, buf, n0, p.n_tile, valid, pix, m_idx, mrow, mrow_alt);
             tc_fence_before();
             mbar_arrive_cluster(mapa_rank(tmem_empty_bar(buf), 0));
             if (timed && lane == 0) {
@@ -1263,6 +1283,22 @@ int make_act_map(CUtensorMap* m, const __half* base, int C, int pitch, int B, in
         cuuint64_t gstr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)w * pitch * 2, (cuuint64_t)h * w * pitch * 2};
         cuuint32_t box[4] = {BKC, (cuuint32_t)(TILE_COLS * stride), (cuuint32_t)(box_rows * stride), 1};
         cuuint32_t est[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+    });
+}
+
+// x-major activation box for the 1 x kw layers of the chained launch: dimensions ordered (C, y, x, B) so that shared memory
+// receives [x][y][C]; box = 16 rows x box_cols columns.
+int make_act_map_x(CUtensorMap* m, const __half* base, int C, int pitch, int B, int h, int w, int box_cols) {
+    return cached_map(m, MapKey{base, {C, pitch, B, h, w, -5000 - box_cols}}, [&](CUtensorMap* out) -> int {
+        EncodeTiledFn enc = get_encode();
+        if (!enc) return (int)cudaErrorNotSupported;
+        cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)h, (cuuint64_t)w, (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)w * pitch * 2, (cuuint64_t)pitch * 2, (cuuint64_t)h * w * pitch * 2};
+        cuuint32_t box[4] = {BKC, TILE_ROWS, (cuuint32_t)box_cols, 1};
+        cuuint32_t est[4] = {1, 1, 1, 1};
         CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
@@ -1388,12 +1424,25 @@ int fill_chain_layer(const UmmaConvArgs& a, UmmaConvParams& p) {
     const int taps = a.kh * a.kw;
     const int n_tile = (a.n_tile == 128 && a.cout_pad % 256 == 0) ? 256 : a.n_tile;
     if (a.b_batched || n_tile % 32 || n_tile / 2 > 128 || a.kh > 5 || a.cout_pad % n_tile) return -1;
-    p.a_taps = a.kh;
-    p.a_rows = TILE_ROWS + a.kh - 1;
-    for (int g = 0; g < 2; ++g) {
-        if (a.seg_c[g] == 0) { p.a_hi[g] = p.a_hi[0]; p.a_lo[g] = p.a_lo[0]; continue; }
-        if ((rc = make_act_map(&p.a_hi[g], a.seg_hi[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.a_rows))) return rc;
-        if ((rc = make_act_map(&p.a_lo[g], a.seg_lo[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.a_rows))) return rc;
+    // horizontal-tap reuse for the 1 x kw layers (option chain_xmajor): x-major boxes, see UmmaConvParams::xmajor
+    p.xmajor = (b2p_options().chain_xmajor != 0 && a.kh == 1 && a.kw > 1 && a.kw <= 5) ? 1 : 0;
+    if (p.xmajor) {
+        const int box_cols = TILE_COLS + a.kw - 1;
+        p.a_taps = a.kw;
+        p.a_rows = 2 * box_cols;                       // 1024-byte atoms of one plane: box_cols columns x 16 rows x 128 B
+        for (int g = 0; g < 2; ++g) {
+            if (a.seg_c[g] == 0) { p.a_hi[g] = p.a_hi[0]; p.a_lo[g] = p.a_lo[0]; continue; }
+            if ((rc = make_act_map_x(&p.a_hi[g], a.seg_hi[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, box_cols))) return rc;
+            if ((rc = make_act_map_x(&p.a_lo[g], a.seg_lo[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, box_cols))) return rc;
+        }
+    } else {
+        p.a_taps = a.kh;
+        p.a_rows = TILE_ROWS + a.kh - 1;
+        for (int g = 0; g < 2; ++g) {
+            if (a.seg_c[g] == 0) { p.a_hi[g] = p.a_hi[0]; p.a_lo[g] = p.a_lo[0]; continue; }
+            if ((rc = make_act_map(&p.a_hi[g], a.seg_hi[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.a_rows))) return rc;
+            if ((rc = make_act_map(&p.a_lo[g], a.seg_lo[g], a.seg_c[g], a.seg_pitch[g], a.B, a.h, a.w, p.a_rows))) return rc;
+        }
     }
     if ((rc = make_wgt_map(&p.b_hi, a.w_hi, a.cin_pad, a.cout_pad, taps, n_tile / 2))) return rc;
     if ((rc = make_wgt_map(&p.b_lo, a.w_lo, a.cin_pad, a.cout_pad, taps, n_tile / 2))) return rc;
@@ -1410,6 +1459,8 @@ int fill_chain_layer(const UmmaConvArgs& a, UmmaConvParams& p) {
     p.out_f32 = a.out_f32; p.out_f32_pitch = a.out_f32_pitch;
     p.out_hi = a.out_hi; p.out_lo = a.out_lo; p.out_h_pitch = a.out_h_pitch;
     p.zbuf = a.zbuf; p.hbuf = a.hbuf;
+    // (two hidden-state copies, one per pixel order: an x-major layer reads / writes the x-major copy as its own)
+    if (p.xmajor && a.hbuf_x) { p.hbuf = a.hbuf_x; p.hbuf_alt = a.hbuf; } else { p.hbuf_alt = a.hbuf_x; }
     p.fl_coords1 = a.fl_coords1; p.fl_flow = a.fl_flow; p.fl_dflow = a.fl_dflow;
     p.side_tiled = a.side_tiled; p.out_tiled = a.out_tiled;
     p.stride = 1;
@@ -1547,16 +1598,21 @@ int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const B2PChainDep* de
     // ring depths: option chain_rings = 10 * A + B (activation slots of 40 KB, weight slots of 32 KB; A * 40 + B * 32 <= 222)
     const int rings = b2p_options().chain_rings;
     cp.ring_a = rings / 10; cp.ring_b = rings % 10;
-    if (cp.ring_a < 2 || cp.ring_b < 2 || cp.ring_a * 40 + cp.ring_b * 32 > 222) { cp.ring_a = 2; cp.ring_b = 4; }
     int rc;
+    int max_atoms = TILE_ROWS;
     for (int l = 0; l < n; ++l) {
         if ((rc = fill_chain_layer(args[l], cp.L[l]))) return rc;
+        if (cp.L[l].a_rows > max_atoms) max_atoms = cp.L[l].a_rows;
         cp.L[l].n_reverse = n_reverse ? n_reverse[l] : 0;
         cp.unit_start[l + 1] = cp.unit_start[l] + cp.L[l].total_units;
         if (cp.L[l].m_tiles != cp.L[0].m_tiles) return -1;
         if (cp.L[l].total_tiles / cp.L[l].m_groups > CH_MAX_NSUB) return -1;
     }
     cp.m_tiles = cp.L[0].m_tiles;
+    cp.a_slot = 2u * (uint32_t)max_atoms * 1024u;
+    auto ring_bytes = [&](int ra, int rb) { return (size_t)ra * cp.a_slot + (size_t)rb * CH_B_SLOT + 1024 + 16 * (ra + rb) + 64 + 256; };
+    if (cp.ring_a < 2 || cp.ring_b < 2 || cp.ring_a > 9 || cp.ring_b > 9 || ring_bytes(cp.ring_a, cp.ring_b) > 227 * 1024) { cp.ring_a = 2; cp.ring_b = 4; }
+    if (ring_bytes(cp.ring_a, cp.ring_b) > 227 * 1024) return -1;
     for (int l = 0; l < n; ++l) {
         cp.dep[l].n_src = deps[l].n_src; cp.dep[l].halo = deps[l].halo;
         for (int k = 0; k < deps[l].n_src; ++k) {
@@ -1574,7 +1630,7 @@ int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const B2PChainDep* de
     cp.dynamic = b2p_options().chain_dynamic != 0;
     B2P_CUDA(cudaMemsetAsync(done_ws, 0, ((size_t)n * CH_MAX_NSUB * cp.m_tiles + 1) * sizeof(int), s));
     int nclusters = sms / 2;
-    const size_t smem = (size_t)cp.ring_a * CH_A_SLOT + (size_t)cp.ring_b * CH_B_SLOT + 1024 + 16 * (cp.ring_a + cp.ring_b) + 64 + 256;
+    const size_t smem = ring_bytes(cp.ring_a, cp.ring_b);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nclusters * 2); cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[2];
@@ -1586,11 +1642,11 @@ int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const B2PChainDep* de
     // The units wait for each other, so every cluster of the grid must be resident at once: ask the driver how many CTA
     // pairs it can co-schedule (an SM without a free partner holds none) and launch no more than that.
     {
-        static int max_clusters[64][10][10];
+        static int max_clusters[64][10][10][2];
         int dev = 0;
         B2P_CUDA(cudaGetDevice(&dev));
         if (dev < 0 || dev >= 64) return -1;
-        int& cap = max_clusters[dev][cp.ring_a][cp.ring_b];
+        int& cap = max_clusters[dev][cp.ring_a][cp.ring_b][cp.a_slot > 40960u ? 1 : 0];
         if (cap == 0) {
             int nmax = 0;
             B2P_CUDA(cudaOccupancyMaxActiveClusters(&nmax, conv_chain_kernel, &cfg));

@@ -218,9 +218,10 @@ __global__ void __launch_bounds__(128) flow_head2_gather_kernel(const float* __r
 
 
 // fp32 [P][C] pixel-major <-> the tiled side-buffer layout (common.cuh: b2p_tiled_index); one thread per float4
+// xmajor: the 128 pixel slots of a tile are ordered x * 16 + y (the x-major layers of the chained launch) instead of y * 8 + x
 template <bool TO_TILED>
 __global__ void __launch_bounds__(256) tiled_convert_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int h,
-                                                            int w, int C) {
+                                                            int w, int C, int xmajor) {
     pdl_trigger();
     pdl_wait();
     const int tiles_x = (w + B2P_TILE_COLS - 1) / B2P_TILE_COLS, tiles_y = (h + B2P_TILE_ROWS - 1) / B2P_TILE_ROWS;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256) tiled_convert_kernel(const float* __restr
     const int c4 = (int)(t2 % (size_t)(C >> 2));
     const int tile = (int)(t2 / (size_t)(C >> 2));
     const int b = tile / (tiles_x * tiles_y), tr = tile - b * tiles_x * tiles_y;
-    const int y = (tr / tiles_x) * B2P_TILE_ROWS + (m >> 3), x = (tr % tiles_x) * B2P_TILE_COLS + (m & 7);
+    const int y = (tr / tiles_x) * B2P_TILE_ROWS + (xmajor ? (m & 15) : (m >> 3)), x = (tr % tiles_x) * B2P_TILE_COLS + (xmajor ? (m >> 4) : (m & 7));
     const bool in = y < h && x < w;
     const size_t pxc = (((size_t)b * h + y) * w + x) * C + c4 * 4;
     if (TO_TILED) {
@@ -410,16 +411,16 @@ int b2p_flow_head2(const float* hm, const __half* hm_hi, const __half* hm_lo, co
     return 0;
 }
 
-int b2p_pxc_to_tiled(const float* src, float* dst, int B, int h, int w, int C, cudaStream_t s) {
+int b2p_pxc_to_tiled(const float* src, float* dst, int B, int h, int w, int C, cudaStream_t s, int xmajor) {
     const size_t total = b2p_tiled_pixels(B, h, w) * (size_t)(C >> 2);
-    B2P_CUDA(b2p_launch_pdl(tiled_convert_kernel<true>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, src, dst, B, h, w, C));
+    B2P_CUDA(b2p_launch_pdl(tiled_convert_kernel<true>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, src, dst, B, h, w, C, xmajor));
     B2P_LAUNCH_CHECK();
     return 0;
 }
 
 int b2p_tiled_to_pxc(const float* src, float* dst, int B, int h, int w, int C, cudaStream_t s) {
     const size_t total = b2p_tiled_pixels(B, h, w) * (size_t)(C >> 2);
-    B2P_CUDA(b2p_launch_pdl(tiled_convert_kernel<false>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, src, dst, B, h, w, C));
+    B2P_CUDA(b2p_launch_pdl(tiled_convert_kernel<false>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, src, dst, B, h, w, C, 0));
     B2P_LAUNCH_CHECK();
     return 0;
 }

@@ -40,8 +40,8 @@ def test_host_side_size_queries():
     assert L.b200pose_pyramid_floats(B, h, w) == B * 1200 * (1200 + 300 + 70 + 15)
     assert L.b200pose_refine_workspace_bytes(1, 240, 320) < L.b200pose_refine_workspace_bytes(2, 240, 320)
     # B=32 at 240x320 fills the machine: chained convolutions (1 launch); B=1 runs the layers one by one (11 + flow head 2)
-    assert L.b200pose_refine_launch_count(32, 240, 320, 4, 3) == 11 + 4 * (3 + 1 + 1 + 1)
-    assert L.b200pose_refine_launch_count(1, 240, 320, 4, 3) == 14 + 4 * (3 + 13 + 1 + 1)
+    assert L.b200pose_refine_launch_count(32, 240, 320, 4, 3) == 12 + 4 * (3 + 1 + 1 + 1)
+    assert L.b200pose_refine_launch_count(1, 240, 320, 4, 3) == 15 + 4 * (3 + 13 + 1 + 1)
     assert L.b200pose_refine_launch_count(1, 100, 320, 4, 3) == 0
     assert b"workspace" in L.b200pose_error_string(-3)
 
