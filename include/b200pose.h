@@ -175,6 +175,18 @@ int b200pose_lm_solve(const float* depth, const float* target, const float* weig
                       double* H_out, double* b_out, float* delta_out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- f4: backward of one LM step ------------------------------------------------------------------
+ * What autograd computes in the reference for SE3Sequence.reprojction_optim(num_iters = 1) (geometry/transformation.py:
+ * 265-316; the shipped OPTIM_ITER_COUNT is 1) through the custom Cholesky backward of geometry/cholesky.py:19-28: given
+ * grad_delta [B,6] = dL/d(delta) of the step's clamped fp32 update, the gradients with respect to target [B,H,W,2] and
+ * weight [B,H,W].  G [B,4,4] is the pose ENTERING the step (a constant of the step: PoseRefiner.py:320 detaches it);
+ * depth / depth_offset / K / ep_lmbda / lm_lmbda as in b200pose_lm_solve.  The gradient through NaN -> 0 and the +-1 clamp is
+ * zero for the affected components, as torch.where / torch.clamp.  workspace: b200pose_lm_backward_workspace_bytes.      */
+size_t b200pose_lm_backward_workspace_bytes(int B, int H, int W);
+int b200pose_lm_backward(const float* depth, const float* target, const float* weight, const float* K, const float* G,
+                         const float* grad_delta, int B, int H, int W, float depth_offset, double ep_lmbda, double lm_lmbda,
+                         float* grad_target, float* grad_weight, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a11, a12 in isolation (the LM kernels above run them inline; these entries let a caller -- and the tests -- reach
  * the two small pieces directly) -------------------------------------------------------------------
  * b200pose_cholesky_solve: geometry/cholesky.py:32-50 `solve` for 6x6 systems: x = H^-1 b by Cholesky in fp64, NaN -> 0,

@@ -299,11 +299,10 @@ def cholesky_solve6(H: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- a10: LM normal equations
-def lm_normal_equations(depth_eps: torch.Tensor, target: torch.Tensor, weight: torch.Tensor,
-                        K: torch.Tensor, G: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """H = sum v w J^T J, b = sum v w J^T r in fp64 from fp32 geometry.
-    geometry/transformation.py:284-297, jac_local_perturb :27-46, project(jacobian=True)
-    projective_ops.py:116-131.  depth_eps/weight [B,H,W], target [B,H,W,2].  Un-damped."""
+def lm_jacobian_residual(depth_eps: torch.Tensor, target: torch.Tensor, K: torch.Tensor, G: torch.Tensor):
+    """Per-pixel 2x6 Jacobian J (fp64 from fp32 geometry), residual r = target - x1 and validity v.
+    geometry/transformation.py:284-292, jac_local_perturb :27-46, project(jacobian=True) projective_ops.py:116-131.
+    depth_eps [B,H,W], target [B,H,W,2] -> J [B,H,W,2,6], r [B,H,W,2], v [B,H,W]."""
     X0 = backproject(depth_eps, K)                       # fp32, as the reference
     X1 = se3_apply(G, X0)
     fx, fy, cx, cy = _intr(K)
@@ -323,8 +322,16 @@ def lm_normal_equations(depth_eps: torch.Tensor, target: torch.Tensor, weight: t
                         dim=-1)                                                               # [B,H,W,3,6]
     J = torch.matmul(jproj.double(), jtran.double())                                          # [B,H,W,2,6]
     v = ((X0[..., 2] > MIN_DEPTH_VALID) & (Zr > MIN_DEPTH_VALID)).double()
-    vw = (v * weight.double())[..., None, None]
     r = target.double() - x1.double()                                                         # fp64 - fp32->fp64
+    return J, r, v
+
+
+def lm_normal_equations(depth_eps: torch.Tensor, target: torch.Tensor, weight: torch.Tensor,
+                        K: torch.Tensor, G: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """H = sum v w J^T J, b = sum v w J^T r in fp64 from fp32 geometry (transformation.py:294-297).
+    depth_eps/weight [B,H,W], target [B,H,W,2].  Un-damped."""
+    J, r, v = lm_jacobian_residual(depth_eps, target, K, G)
+    vw = (v * weight.double())[..., None, None]
     Hm = torch.einsum("bhwri,bhwrj->bij", vw * J, J)
     bv = torch.einsum("bhwri,bhwr->bi", vw * J, r)
     return Hm, bv
@@ -338,6 +345,32 @@ def lm_step(depth_eps, target, weight, K, G, lm_lmbda=LM_LMBDA, ep_lmbda=EP_LMBD
     delta = cholesky_solve6(Hd, bv)
     Gn = torch.matmul(se3_exp(delta), G)
     return Gn, delta, Hm, bv
+
+
+def lm_step_backward(depth_eps, target, weight, K, G, grad_delta, lm_lmbda=LM_LMBDA, ep_lmbda=EP_LMBDA):
+    """Gradients of one LM step with respect to target [B,H,W,2] and weight [B,H,W] given dL/d(delta) [B,6], written out by
+    hand (no autograd): geometry/cholesky.py:19-28 (z = H_d^-1 dx, dH_d = -x z^T, db = z, x the raw solution; dx is zero where
+    the NaN -> 0 / clamp of :42-45 blocks it), transformation.py:300 (dH = dH_d + lm diag(dH_d)), :294-297 (H, b linear in w;
+    b linear in target).  Pinned by tests/golden/lm_backward.npz (the reference's autograd executed)."""
+    B, H, W = depth_eps.shape
+    J, r, v = lm_jacobian_residual(depth_eps, target, K, G)                       # [B,H,W,2,6], [B,H,W,2], [B,H,W] in fp64
+    wv = (v * weight.double())[..., None, None]
+    Hm = torch.einsum("bhwri,bhwrj->bij", wv * J, J)
+    bv = torch.einsum("bhwri,bhwr->bi", wv * J, r)
+    eye = torch.eye(6, dtype=torch.float64)
+    Hd = Hm + ep_lmbda * eye + lm_lmbda * Hm * eye
+    Lc = torch.linalg.cholesky(Hd)
+    x = torch.cholesky_solve(bv[..., None], Lc)[..., 0]
+    ok = (~torch.isnan(x)) & (x >= -1.0) & (x <= 1.0)
+    dx = torch.where(ok, grad_delta.double(), torch.zeros_like(x))
+    z = torch.cholesky_solve(dx[..., None], Lc)[..., 0]
+    dHd = -torch.einsum("bi,bj->bij", x, z)
+    dH = dHd + lm_lmbda * dHd * eye
+    jb = torch.einsum("bhwri,bi->bhwr", J, z)                                     # J_row . dL/db
+    q = torch.einsum("bhwri,bij,bhwrj->bhwr", J, dH, J)
+    grad_w = v * (q + jb * r).sum(-1)
+    grad_t = (v * weight.double())[..., None] * jb
+    return grad_t.float(), grad_w.float()
 
 
 # ----------------------------------------------------------------------------- a13

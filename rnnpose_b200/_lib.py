@@ -45,6 +45,8 @@ SIGNATURES = {
     "b200pose_pose_metrics": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "b200pose_lm_workspace_bytes": (_sz, [_i, _i, _i]),
     "b200pose_lm_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _d, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200pose_lm_backward_workspace_bytes": (_sz, [_i, _i, _i]),
+    "b200pose_lm_backward": (_i, [_vp] * 6 + [_i, _i, _i, _f, _d, _d, _vp, _vp, _vp, _sz, _vp]),
     "b200pose_cholesky_solve": (_i, [_vp, _vp, _vp, _i, _vp]),
     "b200pose_se3_retract": (_i, [_vp, _vp, _i, _vp]),
     "b200pose_refine_workspace_bytes": (_sz, [_i, _i, _i]),

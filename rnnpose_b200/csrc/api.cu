@@ -612,6 +612,18 @@ int b200pose_lm_solve(const float* depth, const float* target, const float* weig
     return 0;
 }
 
+size_t b200pose_lm_backward_workspace_bytes(int B, int H, int W) { return b2p_lm_bwd_ws_bytes(B, H, W); }
+
+int b200pose_lm_backward(const float* depth, const float* target, const float* weight, const float* K, const float* G,
+                         const float* grad_delta, int B, int H, int W, float depth_offset, double ep_lmbda, double lm_lmbda,
+                         float* grad_target, float* grad_weight, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!depth || !target || !weight || !K || !G || !grad_delta || !grad_target || !grad_weight || !workspace) return B200POSE_E_NULL;
+    if (B < 1 || H < 1 || W < 1) return B200POSE_E_SHAPE;
+    if (((uintptr_t)workspace & 255) || workspace_bytes < b2p_lm_bwd_ws_bytes(B, H, W)) return B200POSE_E_WORKSPACE;
+    return b2p_lm_backward(depth, target, weight, K, G, grad_delta, B, H, W, depth_offset, ep_lmbda, lm_lmbda, grad_target, grad_weight,
+                           workspace, (cudaStream_t)stream);
+}
+
 int b200pose_debug_set_conv_events(void* ev_start, void* ev_stop) {
     g_conv_ev[0] = (cudaEvent_t)ev_start; g_conv_ev[1] = (cudaEvent_t)ev_stop;
     return 0;

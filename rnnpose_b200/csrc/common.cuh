@@ -216,6 +216,10 @@ int b2p_lm_steps(const float* depth, const float* target, const float* weight, c
                  int B, int H, int W, float depth_add, double ep, double lm, int n_steps, void* ws, cudaStream_t s,
                  const int* fg_idx = nullptr, const int* fg_count = nullptr);
 size_t b2p_lm_ws_bytes(int B, int H, int W);
+size_t b2p_lm_bwd_ws_bytes(int B, int H, int W);
+int b2p_lm_backward(const float* depth, const float* target, const float* weight, const float* K, const float* G, const float* grad_delta,
+                    int B, int H, int W, float depth_add, double ep, double lm, float* grad_target, float* grad_weight, void* ws,
+                    cudaStream_t s);
 int b2p_se3_retract(const float* delta, float* G, int B, cudaStream_t s);
 int b2p_chol_solve(const double* H, const double* b, float* x, int B, cudaStream_t s);
 int b2p_lm_reset(void* ws, int B, int H, int W, cudaStream_t s);   // once before the first b2p_lm_step on a workspace

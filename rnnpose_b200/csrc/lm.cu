@@ -538,6 +538,118 @@ __global__ void chol_solve_kernel(const double* __restrict__ H, const double* __
     for (int i = 0; i < 6; ++i) x[b * 6 + i] = xi[i];
 }
 
+// ------------------------------------------------------------------------------------------------ backward of one LM step (f4)
+// Gradient of a loss with respect to the correspondence target and weight through ONE damped Gauss-Newton step, i.e. what
+// autograd computes in the reference for reprojction_optim(num_iters = 1) (the shipped OPTIM_ITER_COUNT,
+// config/linemod/template_fw0.5.yml:81) given dL/d(delta):
+//   geometry/cholesky.py:19-28  (OptNet backward of the solve): z = H_d^-1 dx, dL/dH_d = -x z^T, dL/db = z, with x the RAW
+//     solution (before NaN -> 0 and the clamp, whose backward zeroes dx where x is NaN or outside [-1, 1], cholesky.py:42-45);
+//   geometry/transformation.py:300: H_d = H + ep I + lm H (.) I  =>  dL/dH = dL/dH_d + lm diag(dL/dH_d);
+//   :294-297: H = sum v w J^T J, b = sum v w J^T (target - x1)  =>  per pixel
+//     dL/dw      = v sum_rows [ J_row dL/dH J_row^T + (J_row . dL/db) r_row ],   dL/dtarget_row = v w (J_row . dL/db).
+// The pose entering the step is a constant here (PoseRefiner.py:320 detaches it: Tij.copy(stop_gradients=True)).
+__global__ void lm_bwd_solve_kernel(const double* __restrict__ Hs, const double* __restrict__ bs, const float* __restrict__ grad_delta,
+                                    double ep, double lm, int B, double* __restrict__ dHb /*[B][42]: dL/dH (36), dL/db (6)*/) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double Hm[6][6], bv[6];
+    for (int i = 0; i < 6; ++i) {
+        bv[i] = bs[b * 6 + i];
+        for (int j = 0; j < 6; ++j) Hm[i][j] = Hs[(size_t)b * 36 + i * 6 + j];
+    }
+    for (int i = 0; i < 6; ++i) Hm[i][i] = Hm[i][i] + (ep + lm * Hm[i][i]);
+    double L[6][6];
+    for (int j = 0; j < 6; ++j) {
+        double s = Hm[j][j];
+        for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+        const double d = sqrt(s);
+        L[j][j] = d;
+        for (int i = j + 1; i < 6; ++i) {
+            double t = Hm[i][j];
+            for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+            L[i][j] = t / d;
+        }
+    }
+    auto solve = [&](const double* rhs, double* out) {
+        double y[6];
+        for (int i = 0; i < 6; ++i) { double t = rhs[i]; for (int k = 0; k < i; ++k) t -= L[i][k] * y[k]; y[i] = t / L[i][i]; }
+        for (int i = 5; i >= 0; --i) { double t = y[i]; for (int k = i + 1; k < 6; ++k) t -= L[k][i] * out[k]; out[i] = t / L[i][i]; }
+    };
+    double x[6], dx[6], z[6];
+    solve(bv, x);
+    for (int i = 0; i < 6; ++i) {
+        const bool pass = (x[i] == x[i]) && x[i] >= -1.0 && x[i] <= 1.0;       // where() and clamp() backward
+        dx[i] = pass ? (double)grad_delta[b * 6 + i] : 0.0;
+    }
+    solve(dx, z);
+    double* o = dHb + (size_t)b * 42;
+    for (int i = 0; i < 6; ++i) {
+        for (int j = 0; j < 6; ++j) {
+            double g = -x[i] * z[j];
+            if (i == j) g += lm * g;                 // d(H_d)/dH has (1 + lm) on the diagonal
+            o[i * 6 + j] = g;
+        }
+        o[36 + i] = z[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) lm_bwd_pixel_kernel(const float* __restrict__ depth, const float* __restrict__ target,
+                                                           const float* __restrict__ weight, const float* __restrict__ K,
+                                                           const float* __restrict__ G, const double* __restrict__ dHb, int H, int W,
+                                                           float depth_add, float* __restrict__ grad_target,
+                                                           float* __restrict__ grad_weight) {
+    const int b = blockIdx.y, N = H * W;
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double sH[36], sb[6];
+    if (threadIdx.x < 42) (threadIdx.x < 36 ? sH[threadIdx.x] : sb[threadIdx.x - 36]) = dHb[(size_t)b * 42 + threadIdx.x];
+    __syncthreads();
+    if (px >= N) return;
+    const float* Kb = K + b * 9;
+    const float fx = Kb[0], fy = Kb[4], cx = Kb[2], cy = Kb[5];
+    float Gm[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Gm[i] = G[b * 16 + i];
+    const size_t idx = (size_t)b * N + px;
+    const int u = px % W, v = px / W;
+    const float Z = depth[idx] + depth_add;
+    const float2 tg = reinterpret_cast<const float2*>(target)[idx];
+    const float wv = weight[idx];
+    // same geometry as lm_pixel (projective_ops.py:107-124, transformation.py:29-45,289)
+    const float X = Z * ((float)u - cx) / fx, Y = Z * ((float)v - cy) / fy;
+    const float X1 = Gm[0] * X + Gm[1] * Y + Gm[2] * Z + Gm[3];
+    const float Y1 = Gm[4] * X + Gm[5] * Y + Gm[6] * Z + Gm[7];
+    const float Z1 = Gm[8] * X + Gm[9] * Y + Gm[10] * Z + Gm[11];
+    const double valid = (Z > 0.1f && Z1 > 0.1f) ? 1.0 : 0.0;
+    const float Zc = fmaxf(Z1, 0.01f);
+    const float x1 = fx * (X1 / Zc) + cx, y1 = fy * (Y1 / Zc) + cy;
+    const bool cut = Zc <= 0.02f;
+    const float zi1 = cut ? 0.f : 1.0f / Zc, zi2 = cut ? 0.f : 1.0f / (Zc * Zc);
+    const double A = (double)(fx * zi1), C = (double)((-fx * X1) * zi2);
+    const double Bq = (double)(fy * zi1), D = (double)((-fy * Y1) * zi2);
+    const double dX = (double)X1, dY = (double)Y1, dZ = (double)Z1;
+    double J[2][6];
+    J[0][0] = A;   J[0][1] = 0.0; J[0][2] = C; J[0][3] = C * dY;              J[0][4] = A * dZ + C * (-dX); J[0][5] = A * (-dY);
+    J[1][0] = 0.0; J[1][1] = Bq;  J[1][2] = D; J[1][3] = Bq * (-dZ) + D * dY; J[1][4] = D * (-dX);          J[1][5] = Bq * dX;
+    const double r[2] = {(double)tg.x - (double)x1, (double)tg.y - (double)y1};
+    double gw = 0.0, gt[2];
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+        double jb = 0.0, q = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            jb += J[row][i] * sb[i];
+            double t = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) t += sH[i * 6 + j] * J[row][j];
+            q += J[row][i] * t;
+        }
+        gw += q + jb * r[row];
+        gt[row] = valid * (double)wv * jb;
+    }
+    grad_weight[idx] = (float)(valid * gw);
+    reinterpret_cast<float2*>(grad_target)[idx] = make_float2((float)gt[0], (float)gt[1]);
+}
+
 __global__ void zero_u32_kernel(unsigned* p, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0u;
@@ -636,6 +748,32 @@ int b2p_se3_retract(const float* delta, float* G, int B, cudaStream_t s) {
 
 int b2p_chol_solve(const double* H, const double* b, float* x, int B, cudaStream_t s) {
     chol_solve_kernel<<<ceil_div(B, 64), 64, 0, s>>>(H, b, x, B);
+    B2P_LAUNCH_CHECK();
+    return 0;
+}
+
+// f4: gradients of one LM step with respect to target and weight.  ws: b2p_lm_bwd_ws_bytes.
+size_t b2p_lm_bwd_ws_bytes(int B, int H, int W) {
+    return b2p_lm_ws_bytes(B, H, W) + align_up((size_t)B * (36 + 6 + 42) * sizeof(double), 256) + align_up((size_t)B * (16 + 6) * sizeof(float), 256);
+}
+
+int b2p_lm_backward(const float* depth, const float* target, const float* weight, const float* K, const float* G, const float* grad_delta,
+                    int B, int H, int W, float depth_add, double ep, double lm, float* grad_target, float* grad_weight, void* ws,
+                    cudaStream_t s) {
+    char* p = reinterpret_cast<char*>(ws);
+    void* lm_ws = p; p += b2p_lm_ws_bytes(B, H, W);
+    double* Hs = reinterpret_cast<double*>(p); double* bs = Hs + (size_t)B * 36; double* dHb = bs + (size_t)B * 6;
+    p += align_up((size_t)B * (36 + 6 + 42) * sizeof(double), 256);
+    float* Gtmp = reinterpret_cast<float*>(p); float* dtmp = Gtmp + (size_t)B * 16;
+    int rc;
+    // forward normal equations of the step (un-damped H, b) on a scratch copy of the pose
+    B2P_CUDA(cudaMemcpyAsync(Gtmp, G, (size_t)B * 16 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if ((rc = b2p_lm_reset(lm_ws, B, H, W, s))) return rc;
+    if ((rc = b2p_lm_step(depth, target, weight, K, Gtmp, B, H, W, depth_add, ep, lm, Hs, bs, dtmp, lm_ws, s))) return rc;
+    lm_bwd_solve_kernel<<<ceil_div(B, 64), 64, 0, s>>>(Hs, bs, grad_delta, ep, lm, B, dHb);
+    B2P_LAUNCH_CHECK();
+    lm_bwd_pixel_kernel<<<dim3((unsigned)ceil_div(H * W, 256), (unsigned)B), 256, 0, s>>>(depth, target, weight, K, G, dHb, H, W, depth_add,
+                                                                                         grad_target, grad_weight);
     B2P_LAUNCH_CHECK();
     return 0;
 }

@@ -327,6 +327,45 @@ def zoom_crop(pc_depth: torch.Tensor, K: torch.Tensor, T: torch.Tensor, image: O
     return dict(image_crop=ic, geofea_crop=gc, K_crop=Kc, theta=th)
 
 
+def lm_backward(depth: torch.Tensor, target: torch.Tensor, weight: torch.Tensor, K: torch.Tensor, G: torch.Tensor,
+                grad_delta: torch.Tensor, ep_lmbda: float = EP_LMBDA, lm_lmbda: float = LM_LMBDA, depth_offset: float = 0.0):
+    """Gradients of ONE LM step with respect to target [B,H,W,2] and weight [B,H,W] given dL/d(delta) [B,6]
+    (b200pose_lm_backward; reference autograd through geometry/cholesky.py:19-28).  G is the pose entering the step."""
+    L = _lib.lib()
+    for t, n in ((depth, "depth"), (target, "target"), (weight, "weight"), (K, "K"), (G, "G"), (grad_delta, "grad_delta")):
+        _chk(t, n)
+    B, H, W = depth.shape
+    gt = torch.empty(B, H, W, 2, dtype=torch.float32, device=depth.device)
+    gw = torch.empty(B, H, W, dtype=torch.float32, device=depth.device)
+    nb = L.b200pose_lm_backward_workspace_bytes(B, H, W)
+    ws = _ws(nb, depth.device)
+    _lib.check(L.b200pose_lm_backward(depth.data_ptr(), target.data_ptr(), weight.data_ptr(), K.data_ptr(), G.data_ptr(),
+                                      grad_delta.data_ptr(), B, H, W, float(depth_offset), float(ep_lmbda), float(lm_lmbda),
+                                      gt.data_ptr(), gw.data_ptr(), ws.data_ptr(), nb, _stream()), "b200pose_lm_backward")
+    return gt, gw
+
+
+class LMStep(torch.autograd.Function):
+    """One differentiable LM step on the library's kernels: forward = b200pose_lm_solve(n_steps = 1) returning the clamped
+    update delta [B,6] (and updating a copy of G); backward = b200pose_lm_backward.  Mirrors the autograd path of the
+    reference's reprojction_optim(num_iters = 1) for target and weight (depth, K and the entering pose are constants)."""
+
+    @staticmethod
+    def forward(ctx, depth, target, weight, K, G, ep_lmbda=EP_LMBDA, lm_lmbda=LM_LMBDA):
+        Gc = G.clone()
+        _, _, _, delta = lm_solve(depth, target.contiguous(), weight.contiguous(), K, Gc, 1, ep_lmbda, lm_lmbda, taps=True)
+        ctx.save_for_backward(depth, target, weight, K, G)
+        ctx.lmb = (ep_lmbda, lm_lmbda)
+        ctx.mark_non_differentiable(Gc)
+        return delta[0], Gc
+
+    @staticmethod
+    def backward(ctx, grad_delta, _grad_G):
+        depth, target, weight, K, G = ctx.saved_tensors
+        gt, gw = lm_backward(depth, target.contiguous(), weight.contiguous(), K, G, grad_delta.contiguous().float(), *ctx.lmb)
+        return None, gt, gw, None, None, None, None
+
+
 def cholesky_solve(H: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """geometry/cholesky.py `solve` for 6x6 fp64 systems: H [B,6,6], b [B,6] -> x [B,6] fp32 (NaN -> 0, clamp +-1)."""
     L = _lib.lib()

@@ -262,6 +262,44 @@ def test_lm_vs_oracle_random(ops):
     torch.testing.assert_close(Gd.cpu(), Gr, rtol=0, atol=5e-6)
 
 
+# ----------------------------------------------------------------------------- f4: backward of one LM step
+@pytest.mark.parametrize("case", ["plain", "clamp"])
+def test_lm_backward_reference_autograd_golden(ops, case):
+    """b200pose_lm_backward against the reference's autograd through reprojction_optim(num_iters=1) (lm_backward.npz): plain
+    damping, and a case whose raw update leaves [-1, 1] so that the clamp blocks part of the gradient."""
+    g = golden("lm.npz"); gb = golden("lm_backward.npz")
+    d = dev()
+    target = (T(g["target"]) + float(gb[f"{case}_shift"])).contiguous()
+    ep = float(gb[f"{case}_ep"])
+    gt, gw = ops.lm_backward(T(g["depth"]).to(d), target.to(d), T(g["weight"]).contiguous().to(d), T(g["K"]).to(d), T(g["G_in"]).contiguous().to(d),
+                             T(gb[f"{case}_grad_delta"]).contiguous().to(d), ep_lmbda=ep)
+    rt, rw = T(gb[f"{case}_grad_target"]), T(gb[f"{case}_grad_weight"])
+    torch.testing.assert_close(gt.cpu(), rt, rtol=1e-4, atol=2e-6 * rt.abs().max().item())
+    torch.testing.assert_close(gw.cpu(), rw, rtol=1e-4, atol=2e-6 * rw.abs().max().item())
+    # the forward the gradient belongs to: delta of the same step
+    G = T(g["G_in"]).contiguous().to(d).clone()
+    _, _, _, delta = ops.lm_solve(T(g["depth"]).to(d), target.to(d), T(g["weight"]).contiguous().to(d), T(g["K"]).to(d), G, 1, ep_lmbda=ep, taps=True)
+    torch.testing.assert_close(delta[0].cpu(), T(gb[f"{case}_delta"]), rtol=1e-5, atol=1e-6)
+
+
+def test_lm_step_autograd_function(ops):
+    """ops.LMStep (forward = one LM step, backward = b200pose_lm_backward) under torch autograd against the oracle's
+    hand-written gradient for a loss on delta."""
+    g = golden("lm.npz")
+    d = dev()
+    depth, K, G = T(g["depth"]).to(d), T(g["K"]).to(d), T(g["G_in"]).contiguous().to(d)
+    target = T(g["target"]).contiguous().to(d).requires_grad_(True)
+    weight = T(g["weight"]).contiguous().to(d).requires_grad_(True)
+    delta, Gn = ops.LMStep.apply(depth, target, weight, K, G)
+    coef = torch.tensor([[1.0, -2.0, 0.5, 3.0, -1.0, 2.0], [0.3, 0.1, -0.7, 1.5, 2.5, -0.2]], device=d)
+    (delta * coef).sum().backward()
+    rt, rw = O.lm_step_backward(T(g["depth"]), T(g["target"]), T(g["weight"]), T(g["K"]), T(g["G_in"]), coef.cpu())
+    torch.testing.assert_close(target.grad.cpu(), rt, rtol=1e-4, atol=2e-6 * rt.abs().max().item())
+    torch.testing.assert_close(weight.grad.cpu(), rw, rtol=1e-4, atol=2e-6 * rw.abs().max().item())
+    Gr, dr, _, _ = O.lm_step(T(g["depth"]), T(g["target"]), T(g["weight"]), T(g["K"]), T(g["G_in"]))
+    torch.testing.assert_close(Gn.cpu(), Gr, rtol=0, atol=2e-6)
+
+
 # ----------------------------------------------------------------------------- GPU pins of the small branches
 def test_se3_retract_golden_both_branches(ops):
     """geometry/se3.py _se3_matrix_expm executed (expm.npz): Taylor branch (theta < 1e-4), Rodrigues branch, the threshold."""

@@ -216,3 +216,18 @@ def test_g11_image_encoder_oracle():
         #  input, whose InstanceNorm amplifies fp32 rounding; two fp32 evaluations of the same network differ by ~4e-4 here)
         torch.testing.assert_close(f1, T(g["b_f1"]), rtol=1e-3, atol=1e-3)
         torch.testing.assert_close(f2, T(g["b_f2"]), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("case", ["plain", "clamp"])
+def test_g12_lm_step_backward(case):
+    """oracle.lm_step_backward (hand-written gradient of one LM step) against the reference's autograd through
+    reprojction_optim(num_iters=1) executed by tests/golden/make_golden_lm_backward.py."""
+    g = golden("lm.npz"); gb = golden("lm_backward.npz")
+    target = T(g["target"]) + float(gb[f"{case}_shift"])
+    gt, gw = O.lm_step_backward(T(g["depth"]), target, T(g["weight"]), T(g["K"]), T(g["G_in"]), T(gb[f"{case}_grad_delta"]),
+                                ep_lmbda=float(gb[f"{case}_ep"]))
+    rt, rw = T(gb[f"{case}_grad_target"]), T(gb[f"{case}_grad_weight"])
+    torch.testing.assert_close(gt, rt, rtol=1e-4, atol=1e-6 * rt.abs().max().item())
+    torch.testing.assert_close(gw, rw, rtol=1e-4, atol=1e-6 * rw.abs().max().item())
+    if case == "clamp":
+        assert (T(gb["clamp_delta"]).abs() == 1.0).any()          # the fixture does hit the clamp
