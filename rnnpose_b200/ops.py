@@ -351,7 +351,7 @@ class LMStep(torch.autograd.Function):
     reference's reprojction_optim(num_iters = 1) for target and weight (depth, K and the entering pose are constants)."""
 
     @staticmethod
-    def forward(ctx, depth, target, weight, K, G, ep_lmbda=EP_LMBDA, lm_lmbda=LM_LMBDA):
+    def forward(ctx, depth, target, weight, K, G, ep_lmbda, lm_lmbda):
         Gc = G.clone()
         _, _, _, delta = lm_solve(depth, target.contiguous(), weight.contiguous(), K, Gc, 1, ep_lmbda, lm_lmbda, taps=True)
         ctx.save_for_backward(depth, target, weight, K, G)
@@ -364,6 +364,11 @@ class LMStep(torch.autograd.Function):
         depth, target, weight, K, G = ctx.saved_tensors
         gt, gw = lm_backward(depth, target.contiguous(), weight.contiguous(), K, G, grad_delta.contiguous().float(), *ctx.lmb)
         return None, gt, gw, None, None, None, None
+
+
+def lm_step_autograd(depth, target, weight, K, G, ep_lmbda: float = EP_LMBDA, lm_lmbda: float = LM_LMBDA):
+    """Differentiable single LM step: returns (delta [B,6], G_new [B,4,4]); gradients flow to target and weight."""
+    return LMStep.apply(depth, target, weight, K, G, float(ep_lmbda), float(lm_lmbda))
 
 
 def cholesky_solve(H: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

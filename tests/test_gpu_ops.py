@@ -283,14 +283,14 @@ def test_lm_backward_reference_autograd_golden(ops, case):
 
 
 def test_lm_step_autograd_function(ops):
-    """ops.LMStep (forward = one LM step, backward = b200pose_lm_backward) under torch autograd against the oracle's
+    """ops.lm_step_autograd / ops.LMStep (forward = one LM step, backward = b200pose_lm_backward) under torch autograd against the oracle's
     hand-written gradient for a loss on delta."""
     g = golden("lm.npz")
     d = dev()
     depth, K, G = T(g["depth"]).to(d), T(g["K"]).to(d), T(g["G_in"]).contiguous().to(d)
     target = T(g["target"]).contiguous().to(d).requires_grad_(True)
     weight = T(g["weight"]).contiguous().to(d).requires_grad_(True)
-    delta, Gn = ops.LMStep.apply(depth, target, weight, K, G)
+    delta, Gn = ops.lm_step_autograd(depth, target, weight, K, G)
     coef = torch.tensor([[1.0, -2.0, 0.5, 3.0, -1.0, 2.0], [0.3, 0.1, -0.7, 1.5, 2.5, -0.2]], device=d)
     (delta * coef).sum().backward()
     rt, rw = O.lm_step_backward(T(g["depth"]), T(g["target"]), T(g["weight"]), T(g["K"]), T(g["G_in"]), coef.cpu())
