@@ -156,7 +156,7 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def bind_numa(dev_index: int):
+def bind_numa(dev_index: int, world: int = 1):
     """Bind this rank's CPU threads and its future host allocations (the pinned e2e buffers) to the NUMA node of its GPU,
     BEFORE anything is pinned: at N=8 every rank otherwise allocates on the node it happens to start on and half of the
     H2D traffic crosses the socket interconnect (round-1 SCALE run: e2e efficiency 0.49 with all ranks on node 0).
@@ -177,7 +177,13 @@ def bind_numa(dev_index: int):
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read()) if bdf else -1
         info["gpu_numa_node"] = node
         if node < 0:
-            return info
+            # the box does not say which node the GPU hangs off: spread the ranks over the visible nodes in device order (GPUs
+            # 0..n/2-1 on socket 0 is the usual board layout) so that at least the host DRAM bandwidth of every socket is used
+            nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+            if len(nodes) < 2 or world < 2:
+                return info
+            node = nodes[min(len(nodes) - 1, dev_index * len(nodes) // world)]
+            info["guessed_node"] = node
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
@@ -516,7 +522,7 @@ def main():
     assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    numa = bind_numa(local_rank)                  # before any pinned allocation
+    numa = bind_numa(local_rank, world)           # before any pinned allocation
 
     if args.sweep:
         assert args.config == "cfg4", "--sweep is the configs[4] batch-size sweep"

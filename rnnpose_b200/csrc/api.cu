@@ -733,7 +733,7 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
         if (it == 0 && it == n_iters - 1 && flow_first && flow_last)
             B2P_CUDA(cudaMemcpyAsync(flow_last, flow_first, (size_t)B * 2 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
         if (use_pipe) {
-            if ((rc = b2p_lm_cluster(b2p_fgpipe_records(r.fgp, B, H, W), fg_idx, fg_count, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, n_lm, s)))
+            if ((rc = b2p_lm_cluster(b2p_fgpipe_records(r.fgp, B, H, W), nullptr, nullptr, nullptr, fg_idx, fg_count, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, n_lm, s)))
                 return rc;
         } else if ((rc = b2p_lm_steps(depth, r.target, r.weight, K, G, B, H, W, 1e-5f, ep_lmbda, lm_lmbda, n_lm, r.lm, s, fg_idx, fg_count))) return rc;
     }

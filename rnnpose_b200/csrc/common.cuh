@@ -42,7 +42,7 @@ inline cudaError_t b2p_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 // into the library, changed afterwards only through b200pose_set_option.
 struct B2POptions {
     int conv_mode, fg_list, fg_pipeline, fg_upsample, sparse_g1, fg_blocks, tail_min_n, conv_debug, lookup_mode, pool_mode,
-        lm_debug, chain_rings, chain_dynamic, chain_xmajor;
+        lm_debug, chain_rings, chain_dynamic, chain_xmajor, lm_cluster;
 };
 B2POptions& b2p_options();
 
@@ -223,8 +223,8 @@ int b2p_lm_backward(const float* depth, const float* target, const float* weight
 int b2p_se3_retract(const float* delta, float* G, int B, cudaStream_t s);
 int b2p_chol_solve(const double* H, const double* b, float* x, int B, cudaStream_t s);
 int b2p_lm_reset(void* ws, int B, int H, int W, cudaStream_t s);   // once before the first b2p_lm_step on a workspace
-int b2p_lm_cluster(const float4* rec, const int* fg_idx, const int* fg_count, const float* K, float* G, int B, int H, int W,
-                   float depth_add, double ep, double lm, int n_steps, cudaStream_t s);
+int b2p_lm_cluster(const float4* rec, const float* depth, const float* target, const float* weight, const int* fg_idx, const int* fg_count,
+                   const float* K, float* G, int B, int H, int W, float depth_add, double ep, double lm, int n_steps, cudaStream_t s);
 // foreground pipeline (fg_pipeline.cu): channels-last descriptors, float4 records per listed pixel
 size_t b2p_fgpipe_ws_bytes(int B, int H, int W);
 const float4* b2p_fgpipe_records(const void* ws, int B, int H, int W);

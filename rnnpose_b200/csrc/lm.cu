@@ -427,9 +427,12 @@ __device__ __forceinline__ uint32_t lm_cluster_rank() {
     return r;
 }
 
-template <bool NOACC>
+// RECORDS: the pixels' (target, weight, depth) come as float4 records in list order (foreground pipeline); otherwise they are
+// gathered from the dense depth / target / weight maps through the list (the default NCHW path).
+template <bool NOACC, bool RECORDS>
 __global__ void __launch_bounds__(LM_THREADS) lm_cluster_kernel(
-    const float4* __restrict__ rec, const int* __restrict__ fg_idx, const int* __restrict__ fg_count, const float* __restrict__ K,
+    const float4* __restrict__ rec, const float* __restrict__ depth, const float* __restrict__ target, const float* __restrict__ weight,
+    const int* __restrict__ fg_idx, const int* __restrict__ fg_count, const float* __restrict__ K,
     float* __restrict__ G, int N, int W, float depth_add, double ep, double lm, int n_steps) {
     pdl_trigger();
     pdl_wait();
@@ -444,7 +447,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_cluster_kernel(
     if (tid < 12) Gs[tid] = G[b * 16 + tid];
     __syncthreads();
     const int count = fg_count[b];
-    const float4* rb = rec + (size_t)b * N;
+    const float4* rb = RECORDS ? rec + (size_t)b * N : nullptr;
     const int* ib = fg_idx + (size_t)b * N;
     const int first = (int)rank * LM_THREADS + tid, stride = LMC_CTAS * LM_THREADS;
     const uint32_t slot0 = lm_mapa(lm_smem_u32(&slots[0][0][0]), 0);      // slots[][][] of CTA 0, cluster address space
@@ -462,7 +465,16 @@ __global__ void __launch_bounds__(LM_THREADS) lm_cluster_kernel(
             for (int u = 0; u < 4; ++u) {
                 const int kk = k + u * stride;
                 rs[u] = kk < count ? __ldg(ib + kk) : -1;
-                v[u] = kk < count ? rb[kk] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (RECORDS) v[u] = kk < count ? rb[kk] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (!RECORDS) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool in = rs[u] >= 0;
+                    const size_t o = (size_t)b * N + (in ? rs[u] : 0);
+                    const float2 tg = in ? reinterpret_cast<const float2*>(target)[o] : make_float2(0.f, 0.f);
+                    v[u] = make_float4(tg.x, tg.y, in ? weight[o] : 0.f, in ? __ldg(depth + o) : 0.f);
+                }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -694,6 +706,10 @@ int b2p_lm_steps(const float* depth, const float* target, const float* weight, c
                  int W, float depth_add, double ep, double lm, int n_steps, void* ws, cudaStream_t s, const int* fg_idx,
                  const int* fg_count) {
     if (n_steps <= 0) return 0;
+    // with a foreground list: the cluster kernel (hardware co-scheduled CTAs, barrier.cluster) instead of the grid-wide spin
+    // barrier of lm_multi_kernel below (option lm_cluster = 0 keeps the latter)
+    if (fg_idx && fg_count && b2p_options().lm_cluster != 0)
+        return b2p_lm_cluster(nullptr, depth, target, weight, fg_idx, fg_count, K, G, B, H, W, depth_add, ep, lm, n_steps, s);
     int dev = 0, sms = 0, per_sm = 0;
     B2P_CUDA(cudaGetDevice(&dev));
     B2P_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -719,9 +735,10 @@ int b2p_lm_steps(const float* depth, const float* target, const float* weight, c
     return 0;
 }
 
-// All n_steps of one recurrent iteration over the foreground records (fg_pipeline.cu), one cluster per sample.
-int b2p_lm_cluster(const float4* rec, const int* fg_idx, const int* fg_count, const float* K, float* G, int B, int H, int W,
-                   float depth_add, double ep, double lm, int n_steps, cudaStream_t s) {
+// All n_steps of one recurrent iteration over the foreground list, one cluster per sample: on the records of the foreground
+// pipeline (rec != nullptr), or gathering from the dense maps.
+int b2p_lm_cluster(const float4* rec, const float* depth, const float* target, const float* weight, const int* fg_idx, const int* fg_count,
+                   const float* K, float* G, int B, int H, int W, float depth_add, double ep, double lm, int n_steps, cudaStream_t s) {
     if (n_steps <= 0) return 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * LMC_CTAS)); cfg.blockDim = dim3(LM_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
@@ -732,10 +749,14 @@ int b2p_lm_cluster(const float4* rec, const int* fg_idx, const int* fg_count, co
     attr[1].val.clusterDim.x = LMC_CTAS; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 2;
     const int N = H * W;
-    if (b2p_options().lm_debug == 1)
-        B2P_CUDA(cudaLaunchKernelEx(&cfg, lm_cluster_kernel<true>, rec, fg_idx, fg_count, K, G, N, W, depth_add, ep, lm, n_steps));
-    else
-        B2P_CUDA(cudaLaunchKernelEx(&cfg, lm_cluster_kernel<false>, rec, fg_idx, fg_count, K, G, N, W, depth_add, ep, lm, n_steps));
+    const bool noacc = b2p_options().lm_debug == 1;
+    if (rec) {
+        if (noacc) B2P_CUDA(cudaLaunchKernelEx(&cfg, lm_cluster_kernel<true, true>, rec, depth, target, weight, fg_idx, fg_count, K, G, N, W, depth_add, ep, lm, n_steps));
+        else B2P_CUDA(cudaLaunchKernelEx(&cfg, lm_cluster_kernel<false, true>, rec, depth, target, weight, fg_idx, fg_count, K, G, N, W, depth_add, ep, lm, n_steps));
+    } else {
+        if (noacc) B2P_CUDA(cudaLaunchKernelEx(&cfg, lm_cluster_kernel<true, false>, rec, depth, target, weight, fg_idx, fg_count, K, G, N, W, depth_add, ep, lm, n_steps));
+        else B2P_CUDA(cudaLaunchKernelEx(&cfg, lm_cluster_kernel<false, false>, rec, depth, target, weight, fg_idx, fg_count, K, G, N, W, depth_add, ep, lm, n_steps));
+    }
     B2P_LAUNCH_CHECK();
     return 0;
 }

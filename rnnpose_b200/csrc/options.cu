@@ -25,6 +25,7 @@ const OptDesc kOpts[] = {
     {"conv_debug", "B200POSE_V2_DEBUG", &B2POptions::conv_debug, 0},        // timing experiments (results garbage unless 0 / 16)
     {"lookup_mode", "B200POSE_LOOKUP_MODE", &B2POptions::lookup_mode, 1},   // 1 = shared-memory window lookup, 0 = round-1 kernel
     {"pool_mode", "B200POSE_POOL_MODE", &B2POptions::pool_mode, 1},         // 1 = three pyramid levels in one pass
+    {"lm_cluster", "B200POSE_LM_CLUSTER", &B2POptions::lm_cluster, 1},      // LM over the list: cluster kernel (1) or spin-barrier kernel (0)
     {"lm_debug", "B200POSE_LM_DEBUG", &B2POptions::lm_debug, 0},            // 1 = drop the fp64 contraction (timing A/B only)
     {"chain_rings", "B200POSE_CHAIN_RINGS", &B2POptions::chain_rings, 24},  // chained launch: 10 * activation slots + weight slots
     {"chain_xmajor", "B200POSE_CHAIN_XMAJOR", &B2POptions::chain_xmajor, 1},   // chained launch: horizontal-tap reuse for the 1x5 layers

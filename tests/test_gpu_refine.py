@@ -246,7 +246,10 @@ def test_refine_foreground_list_matches_dense_kernels(ops, packed, libopt):
     G0 = torch.eye(4)[None].repeat(3, 1, 1)
     libopt("fg_list", 0)
     dense = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, want_weight=True, want_flows=True)
-    libopt("fg_list", 1); libopt("fg_pipeline", 0)
+    libopt("fg_list", 1); libopt("fg_pipeline", 0); libopt("lm_cluster", 0)     # list + the spin-barrier LM kernel
+    fg0 = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, want_weight=True)
+    assert (fg0["G"].cpu() - dense["G"].cpu()).abs().max().item() < 1e-6
+    libopt("lm_cluster", 1)                                                      # list + the cluster LM kernel (default)
     fg = run_gpu(ops, packed, f1, f2, mb, G0, 3, 3, want_weight=True)
     # default: the foreground pipeline (channels-last descriptors, float4 records, cluster LM kernel), with and without the
     # dense outputs requested, tensor-core and exact-fp32 convolutions
