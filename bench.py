@@ -45,8 +45,8 @@ UNIQUE_SCENES = 8            # distinct synthetic scenes per rank, tiled to the 
 FLOP_PER_LOWRES_PX = 6236672  # update-block convolutions, SURVEY.md Appendix A.2
 # dram__bytes_read.sum + dram__bytes_write.sum of the convolution launch(es) of one update-block pass at B=32, 240x320, from
 # the committed `ncu --set full` capture named in TRAFFIC_SOURCE (ncu flushes caches per launch: an upper bound)
-NCU_TRAFFIC_BYTES_PER_PASS = {"chain": 818_810_112, "layers": 775_000_000}
-TRAFFIC_SOURCE = {"chain": "profiles/r2c/chain_ncu_raw.csv (conv_chain_kernel, one launch, B=32, 240x320)",
+NCU_TRAFFIC_BYTES_PER_PASS = {"chain": 939_701_248, "layers": 775_000_000}
+TRAFFIC_SOURCE = {"chain": "profiles/r2h/chain_ncu_raw.csv (conv_chain_kernel incl. the flow head, one launch, B=32, 240x320; ncu flushes caches per launch)",
                   "layers": "profiles/r1c_conv_umma2_ncu_raw.csv (11 conv launches of one pass, B=32, 240x320)"}
 
 CONFIGS = {
@@ -89,6 +89,41 @@ def make_inputs(rank: int, batch: int, unique: int, H: int, W: int, occlude: boo
     out["G0"] = torch.eye(4)[None].repeat(batch, 1, 1).contiguous()
     out["scene_idx"] = torch.tensor(idx).repeat(rep)[:batch]
     return out
+
+
+def encoder_flops_per_image(H, W):
+    """Algorithmic FLOPs of BasicEncoder on one H x W image (thirdparty/raft/extractor.py:118-232 layer shapes)."""
+    d = lambda v: (v - 1) // 2 + 1
+    H1, W1 = d(H), d(W); H2, W2 = d(H1), d(W1); H3, W3 = d(H2), d(W2)
+    f = H1 * W1 * (147 * 64 + 4 * 9 * 64 * 64)
+    f += H2 * W2 * (9 * 64 * 96 + 3 * 9 * 96 * 96 + 64 * 96)
+    f += H3 * W3 * (9 * 96 * 128 + 3 * 9 * 128 * 128 + 96 * 128 + 128 * 256)
+    return 2 * f
+
+
+def time_encoder(ops, dev, batch, H, W, peaks):
+    """The f2 row's bench leg: ImageFeaEncoder on `batch` crop pairs (2 x batch images), CUDA events, inputs resident."""
+    try:
+        from rnnpose_b200.assets import load_encoder_weights
+        packed = ops.encoder_pack_weights(load_encoder_weights(), dev)
+        a = torch.rand(batch, 3, H, W, device=dev) * 255; b = torch.rand(batch, 3, H, W, device=dev) * 255
+        nb = ops._lib.lib().b200pose_encoder_workspace_bytes(batch, H, W)
+        ws = ops._ws(nb, dev)
+        for _ in range(2):
+            ops.image_encoder(packed, a, b, workspace=ws)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        reps = 5
+        for _ in range(reps):
+            ops.image_encoder(packed, a, b, workspace=ws)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        tf = 2 * batch * encoder_flops_per_image(H, W) / (ms * 1e-3) / 1e12
+        return {"ms_per_batch": ms, "pairs_per_s": batch / (ms * 1e-3), "algorithmic_tflops": tf,
+                "frac_of_burst_bf16_peak": tf / float(peaks.get("bf16_tflops")), "batch_pairs": batch,
+                "note": "b200pose_image_encoder (f2): fp32 stem + 15 tcgen05 convolutions (fp16x3 split) + InstanceNorm passes; not part of `value`"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def encoder_fmap_fn(dev):
@@ -460,6 +495,7 @@ def run_workload(args, cfg, per_gpu, rank, local_rank, world, dev, numa, want_cp
         del ws
 
     peaks, peak_src = measured_peaks()
+    enc_leg = time_encoder(ops, dev, chunk, H, W, peaks) if (rank == 0 and want_cpu and args.fmaps != "hash") else None
     roofline = conv_pass_roofline(ops, packed, chunk, H, W, FLAGS, peaks, peak_src, args.exact_fp32, ms / args.steps, N_ITERS, n_chunks)
 
     line = None
@@ -485,7 +521,7 @@ def run_workload(args, cfg, per_gpu, rank, local_rank, world, dev, numa, want_cp
                        "l2": f"resident inputs per chunk ({sum(d[0][k].numel() * 4 for k in keys) / 1e9:.1f} GB) exceed the 126 MB L2; no explicit flush"},
             "e2e": e2e,
             "gpu_launches": args.steps * n_chunks * ops.launch_count(chunk, H, W, N_ITERS, N_LM) + 2,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "options": opts,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "encoder": enc_leg, "options": opts,
             "accuracy_vs_gt": {"objects": int(gm.shape[0]), "mean_add_over_diameter": float((gm[:, 0] / gm[:, 15]).mean()),
                                "add_0.1d_recall": float(gm[:, 6].mean()), "adds_0.1d_recall": float(gm[:, 7].mean()),
                                "proj2d_5px_recall": float(gm[:, 12].mean()), "cm5deg5_recall": float(gm[:, 13].mean()),

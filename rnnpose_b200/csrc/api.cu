@@ -233,13 +233,16 @@ int run_update_block_tc_chain(const float* wts, float* net, float* coords1, floa
     deps[10].n_first[0] = 1; deps[10].n_cnt[0] = 1;
     deps[11].n_first[0] = 0; deps[11].n_cnt[0] = 1;
     int n_reverse[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0};
+    // interleaved pairs: C1 | F1 (F1's unit is all epilogue, C1's waits for operands) and MASK2 | flow head (MASK2 is
+    // epilogue-bound, the 32-column flow head MMA-bound)
+    const int merge_next[12] = {1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
     int rc;
     if ((rc = b2p_im2col_f1(flow, B, h, w, nullptr, nullptr, u.col_h[0], u.col_h[1], u.x_h[0], u.x_h[1], s))) return rc;
     // completion counters: the fp32 scratch of the exact path (unused here)
     const int m_tiles = B * ceil_div(h, B2P_TILE_ROWS) * ceil_div(w, B2P_TILE_COLS);
     if (b2p_conv_chain_done_ints(n, m_tiles) * sizeof(int) > (size_t)B * h * w * 256 * sizeof(float)) return -1;
     if (g_conv_ev[0]) B2P_CUDA(cudaEventRecord(g_conv_ev[0], s));
-    if ((rc = b2p_launch_conv_chain(args, n, deps, n_reverse, reinterpret_cast<int*>(u.c1), s))) return rc;
+    if ((rc = b2p_launch_conv_chain(args, n, deps, n_reverse, merge_next, reinterpret_cast<int*>(u.c1), s))) return rc;
     if (g_conv_ev[1]) { B2P_CUDA(cudaEventRecord(g_conv_ev[1], s)); g_conv_ev[0] = g_conv_ev[1] = nullptr; }
     return 0;
 }
@@ -272,7 +275,7 @@ int run_gru_precompute(const float* wts, int B, int h, int w, const UpdateWs& u,
         b2p_conv_chain_done_ints(4, m_tiles) * sizeof(int) <= (size_t)B * h * w * 256 * sizeof(float)) {
         B2PChainDep deps[4];
         memset(deps, 0, sizeof(deps));
-        const int rcc = b2p_launch_conv_chain(args, 4, deps, nullptr, reinterpret_cast<int*>(u.c1), s);
+        const int rcc = b2p_launch_conv_chain(args, 4, deps, nullptr, nullptr, reinterpret_cast<int*>(u.c1), s);
         if (rcc != -1) return rcc;
     }
     for (int k = 0; k < 4; ++k) {

@@ -42,7 +42,7 @@ inline cudaError_t b2p_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 // into the library, changed afterwards only through b200pose_set_option.
 struct B2POptions {
     int conv_mode, fg_list, fg_pipeline, fg_upsample, sparse_g1, fg_blocks, tail_min_n, conv_debug, lookup_mode, pool_mode,
-        lm_debug, chain_rings, chain_dynamic, chain_xmajor, lm_cluster;
+        lm_debug, chain_rings, chain_dynamic, chain_xmajor, lm_cluster, chain_merge;
 };
 B2POptions& b2p_options();
 
@@ -173,7 +173,8 @@ struct B2PChainDep {
     int halo;                          // 1: 3x3 tile neighbourhood, 0: the same tile only
 };
 bool b2p_conv_chain_enabled();
-int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const B2PChainDep* deps, const int* n_reverse, int* done_ws, cudaStream_t s);
+int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const B2PChainDep* deps, const int* n_reverse, const int* merge_next,
+                          int* done_ws, cudaStream_t s);
 size_t b2p_conv_chain_done_ints(int n, int m_tiles);
 // fp32 [P][pitch_in] -> fp16 hi/lo planes [P][pitch_out] (first C channels); used by the per-operator entry
 int b2p_split_planes(const float* src, int pitch_in, int C, size_t P, __half* hi, __half* lo, int pitch_out, cudaStream_t s);

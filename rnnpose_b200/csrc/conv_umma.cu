@@ -884,7 +884,14 @@ struct ChainParams {
     int n_layers, m_tiles;
     int ring_a, ring_b;                     // ring depths (option chain_rings)
     uint32_t a_slot;                        // bytes of one activation ring slot
-    int unit_start[CH_MAX_LAYERS + 1];     // prefix sums of the layers' unit counts
+    // The unit list is a sequence of SEGMENTS.  A segment is one layer (its units N-major: all pixel tiles of N tile 0, then of
+    // N tile 1, ...) or two layers interleaved per pixel-tile pair: for M group m, c0 units of layer A (its N tiles) followed by
+    // c1 units of layer B.  Interleaving lets an epilogue-bound layer (MASK2, F1) and an MMA-bound one (flow head, C1) run
+    // concurrently in the two halves of the pipeline instead of one after the other.
+    int n_seg;
+    int seg_start[CH_MAX_LAYERS + 1];      // prefix sums of the segments' unit counts
+    int seg_layer[CH_MAX_LAYERS][2];       // layer indices (second = -1 for a plain segment)
+    int seg_cnt[CH_MAX_LAYERS][2];         // units per M group of each of the two layers (plain segment: {0, 0})
     int* done;                              // [n_layers][CH_MAX_NSUB][m_tiles] epilogue-warp arrivals, zeroed before the launch
     int* next_unit;                         // the unit queue's head (dynamic scheduling), zeroed before the launch
     int dynamic;                            // 1: clusters take units from the queue as they become free; 0: static round robin
@@ -955,7 +962,19 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
     // unit g of the chain -> layer l (g is monotonic per role, so l only ever advances) and the unit inside the layer;
     // a unit = one N tile x two consecutive M tiles, CTA `rank` owns M tile 2 * group + rank (a missing second tile is
     // replaced by the last tile and its result discarded)
-    const int total_units = cp.unit_start[cp.n_layers];
+    const int total_units = cp.seg_start[cp.n_seg];
+    // unit g -> (layer l, unit u inside the layer in N-major numbering); `sidx` only ever advances
+    auto locate = [&](int g, int& sidx, int& l, int& u) {
+        while (g >= cp.seg_start[sidx + 1]) ++sidx;
+        const int off = g - cp.seg_start[sidx];
+        const int c0 = cp.seg_cnt[sidx][0], c1 = cp.seg_cnt[sidx][1];
+        if (c1 == 0) { l = cp.seg_layer[sidx][0]; u = off; return; }
+        // position j of M group mg holds item (j + mg) mod P: the rotation makes the static round-robin (stride = number of
+        // clusters, which shares factors with small P) hand every cluster a mix of both layers
+        const int P = c0 + c1, mg = off / P, j = (off - mg * P + mg) % P;
+        if (j < c0) { l = cp.seg_layer[sidx][0]; u = j * cp.L[l].m_groups + mg; }
+        else { l = cp.seg_layer[sidx][1]; u = (j - c0) * cp.L[l].m_groups + mg; }
+    };
     const int unit0 = (int)blockIdx.x >> 1, unit_step = (int)gridDim.x >> 1;
     auto decode = [&](const UmmaConvParams& p, int u, int& bimg, int& y0, int& x0, int& n0, bool& real, int& m_idx) {
         const int n_ord = u / p.m_groups;                       // position of the unit's N tile in the list order
@@ -1010,7 +1029,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
     if (warp == 0) {
         // ------------------------------------------------ TMA producer (both CTAs)
         int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
-        int l = 0;
+        int l = 0, sidx = 0;
         const bool timed = (cp.L[0].debug & 16) != 0;
         int sched_prefetched = 0;
         if (cp.dynamic && rank == 0 && lane == 0) sched_prefetched = atomicAdd(cp.next_unit, 1);
@@ -1036,10 +1055,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
                 g = next_unit_consumer();
             }
             if (g < 0) break;
-            while (g >= cp.unit_start[l + 1]) ++l;
+            int u_in;
+            locate(g, sidx, l, u_in);
             const UmmaConvParams& p = cp.L[l];
             int bimg, y0, x0, n0, m_idx; bool real;
-            decode(p, g - cp.unit_start[l], bimg, y0, x0, n0, real, m_idx);
+            decode(p, u_in, bimg, y0, x0, n0, real, m_idx);
             // ---- dependencies: lanes 0..8 each watch one tile of the 3x3 neighbourhood (lane 4 = the tile itself)
             const ChainDep& d = cp.dep[l];
             const long long td0 = timed ? clock64() : 0;
@@ -1118,12 +1138,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
             // ------------------------------------------------ MMA issuer (leader CTA)
             uint32_t tile_iter = 0;
             int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
-            int l = 0;
+            int l = 0, sidx = 0;
             const bool timed = (cp.L[0].debug & 16) != 0;
             for (;; ++tile_iter) {
                 const int g = next_unit_consumer();
                 if (g < 0) break;
-                while (g >= cp.unit_start[l + 1]) ++l;
+                int u_in;
+                locate(g, sidx, l, u_in);
                 unsigned long long w_full = 0, w_tmem = 0;
                 const long long t_begin = timed ? clock64() : 0;
                 const UmmaConvParams& p = cp.L[l];
@@ -1178,15 +1199,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_chain_kernel(const __grid_
         const int q = warp & 3;
         const int mrow = q * 32 + lane;
         uint32_t tile_iter = 0;
-        int l = 0;
+        int l = 0, sidx = 0;
         const bool timed = (cp.L[0].debug & 16) != 0 && warp == 2;
         for (;; ++tile_iter) {
             const int g = next_unit_consumer();
             if (g < 0) break;
-            while (g >= cp.unit_start[l + 1]) ++l;
+            int u_in;
+            locate(g, sidx, l, u_in);
             const UmmaConvParams& p = cp.L[l];
             int bimg, y0, x0, n0, m_idx; bool real;
-            decode(p, g - cp.unit_start[l], bimg, y0, x0, n0, real, m_idx);
+            decode(p, u_in, bimg, y0, x0, n0, real, m_idx);
             const int buf = tile_iter & 1;
             // accumulator row -> pixel of the tile: y * 8 + x, or x * 16 + y for the x-major layers
             const int ty = p.xmajor ? (mrow & 15) : (mrow >> 3), tx = p.xmajor ? (mrow >> 4) : (mrow & 7);
@@ -1586,7 +1608,8 @@ extern "C" int b200pose_debug_conv_log(unsigned long long* host_out) {
 // Returns -1 when the layer set does not fit the fixed ring geometry (the caller then launches the layers one by one).
 bool b2p_conv_chain_enabled() { return (conv_mode() & 16) != 0; }
 
-int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const B2PChainDep* deps, const int* n_reverse, int* done_ws, cudaStream_t s) {
+int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const B2PChainDep* deps, const int* n_reverse, const int* merge_next,
+                          int* done_ws, cudaStream_t s) {
     if (n < 1 || n > CH_MAX_LAYERS) return -1;
     const int sms = device_sms();
     if (sms <= 0) return (int)cudaErrorInvalidDevice;
@@ -1604,11 +1627,21 @@ int b2p_launch_conv_chain(const UmmaConvArgs* args, int n, const B2PChainDep* de
         if ((rc = fill_chain_layer(args[l], cp.L[l]))) return rc;
         if (cp.L[l].a_rows > max_atoms) max_atoms = cp.L[l].a_rows;
         cp.L[l].n_reverse = n_reverse ? n_reverse[l] : 0;
-        cp.unit_start[l + 1] = cp.unit_start[l] + cp.L[l].total_units;
         if (cp.L[l].m_tiles != cp.L[0].m_tiles) return -1;
         if (cp.L[l].total_tiles / cp.L[l].m_groups > CH_MAX_NSUB) return -1;
     }
     cp.m_tiles = cp.L[0].m_tiles;
+    // segments: layer l alone, or interleaved with layer l + 1 (merge_next[l], option chain_merge)
+    for (int l = 0; l < n;) {
+        const int sg = cp.n_seg++;
+        const bool merge = merge_next && merge_next[l] && l + 1 < n && b2p_options().chain_merge != 0 &&
+                           cp.L[l].m_groups == cp.L[l + 1].m_groups;
+        cp.seg_layer[sg][0] = l; cp.seg_layer[sg][1] = merge ? l + 1 : -1;
+        cp.seg_cnt[sg][0] = merge ? cp.L[l].total_units / cp.L[l].m_groups : 0;
+        cp.seg_cnt[sg][1] = merge ? cp.L[l + 1].total_units / cp.L[l + 1].m_groups : 0;
+        cp.seg_start[sg + 1] = cp.seg_start[sg] + cp.L[l].total_units + (merge ? cp.L[l + 1].total_units : 0);
+        l += merge ? 2 : 1;
+    }
     cp.a_slot = 2u * (uint32_t)max_atoms * 1024u;
     auto ring_bytes = [&](int ra, int rb) { return (size_t)ra * cp.a_slot + (size_t)rb * CH_B_SLOT + 1024 + 16 * (ra + rb) + 64 + 256; };
     if (cp.ring_a < 2 || cp.ring_b < 2 || cp.ring_a > 9 || cp.ring_b > 9 || ring_bytes(cp.ring_a, cp.ring_b) > 227 * 1024) { cp.ring_a = 2; cp.ring_b = 4; }

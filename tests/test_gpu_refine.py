@@ -280,9 +280,9 @@ def test_refine_foreground_list_matches_dense_kernels(ops, packed, libopt):
     assert (fg["G"].cpu() - ref["G"]).abs().max().item() < SE3_TOL
 
 
-@pytest.mark.parametrize("rings,dynamic,xmajor", [(24, 0, 1), (24, 1, 1), (33, 0, 0), (24, 1, 0)],
-                         ids=["default", "unit-queue", "rings3+3-ymajor", "unit-queue-ymajor"])
-def test_refine_chained_convolutions(ops, packed, libopt, rings, dynamic, xmajor):
+@pytest.mark.parametrize("rings,dynamic,xmajor,merge", [(24, 0, 1, 1), (24, 1, 1, 1), (33, 0, 0, 0), (24, 1, 0, 1), (24, 0, 1, 0)],
+                         ids=["default", "unit-queue", "rings3+3-ymajor-plain", "unit-queue-ymajor", "no-interleave"])
+def test_refine_chained_convolutions(ops, packed, libopt, rings, dynamic, xmajor, merge):
     """The eleven convolutions of a pass in one persistent launch with tile-level dependencies (conv_mode 19, the default)
     against the layer-by-layer launches (conv_mode 3) at the bench shape (the chain needs a machine-filling batch), for both
     shared-memory ring geometries."""
@@ -293,7 +293,7 @@ def test_refine_chained_convolutions(ops, packed, libopt, rings, dynamic, xmajor
     G0 = torch.eye(4)[None].repeat(B, 1, 1)
     libopt("conv_mode", 3)
     ref = run_gpu(ops, packed, f1, f2, rep, G0, 4, 3)["G"].cpu()
-    libopt("conv_mode", 19); libopt("chain_rings", rings); libopt("chain_dynamic", dynamic); libopt("chain_xmajor", xmajor)
+    libopt("conv_mode", 19); libopt("chain_rings", rings); libopt("chain_dynamic", dynamic); libopt("chain_xmajor", xmajor); libopt("chain_merge", merge)
     got = run_gpu(ops, packed, f1, f2, rep, G0, 4, 3)["G"].cpu()
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max().item() < 1e-6
