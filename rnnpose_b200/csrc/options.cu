@@ -29,7 +29,7 @@ const OptDesc kOpts[] = {
     {"lm_debug", "B200POSE_LM_DEBUG", &B2POptions::lm_debug, 0},            // 1 = drop the fp64 contraction (timing A/B only)
     {"chain_rings", "B200POSE_CHAIN_RINGS", &B2POptions::chain_rings, 24},  // chained launch: 10 * activation slots + weight slots
     {"chain_xmajor", "B200POSE_CHAIN_XMAJOR", &B2POptions::chain_xmajor, 1},   // chained launch: horizontal-tap reuse for the 1x5 layers
-    {"chain_merge", "B200POSE_CHAIN_MERGE", &B2POptions::chain_merge, 1},     // chained launch: interleave C1|F1 and MASK2|flow head units
+    {"chain_merge", "B200POSE_CHAIN_MERGE", &B2POptions::chain_merge, 0},     // chained launch: interleave C1|F1 and MASK2|flow head units (measured: no gain)
     {"chain_dynamic", "B200POSE_CHAIN_DYNAMIC", &B2POptions::chain_dynamic, 0},   // chained launch: units from a global queue (1) or static round robin (0)
 };
 constexpr int kNumOpts = (int)(sizeof(kOpts) / sizeof(kOpts[0]));

@@ -280,8 +280,8 @@ def test_refine_foreground_list_matches_dense_kernels(ops, packed, libopt):
     assert (fg["G"].cpu() - ref["G"]).abs().max().item() < SE3_TOL
 
 
-@pytest.mark.parametrize("rings,dynamic,xmajor,merge", [(24, 0, 1, 1), (24, 1, 1, 1), (33, 0, 0, 0), (24, 1, 0, 1), (24, 0, 1, 0)],
-                         ids=["default", "unit-queue", "rings3+3-ymajor-plain", "unit-queue-ymajor", "no-interleave"])
+@pytest.mark.parametrize("rings,dynamic,xmajor,merge", [(24, 0, 1, 0), (24, 1, 1, 1), (33, 0, 0, 0), (24, 1, 0, 1), (24, 0, 1, 1)],
+                         ids=["default", "unit-queue-interleaved", "rings3+3-ymajor", "unit-queue-ymajor-interleaved", "interleaved"])
 def test_refine_chained_convolutions(ops, packed, libopt, rings, dynamic, xmajor, merge):
     """The eleven convolutions of a pass in one persistent launch with tile-level dependencies (conv_mode 19, the default)
     against the layer-by-layer launches (conv_mode 3) at the bench shape (the chain needs a machine-filling batch), for both
