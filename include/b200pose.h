@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B200POSE_VERSION 2
+#define B200POSE_VERSION 3
 
 /* error codes (negative); positive return values are cudaError_t */
 #define B200POSE_OK            0
@@ -55,6 +55,11 @@ extern "C" {
 #define B200POSE_FLAG_GEO2_CHANNELS_LAST 2 /* b200pose_refine_iters only: geofea2 is [B,H*W,32] (pixel-major, the layout
                                            b200pose_zoom_crop writes) instead of NCHW; needs C_geo == 32 and the
                                            foreground pipeline (options fg_list, fg_pipeline), else B200POSE_E_ARG */
+#define B200POSE_FLAG_CONTEXT_TEXELS 4  /* b200pose_refine_iters only: `context` holds, instead of the [B,256,H,W] map, only the
+                                           four texels F.interpolate(scale 1/8, align_corners=True) (CFNet.py:129) reads per
+                                           low-resolution sample: [B,256,(H/8)*(W/8),4] = (v00, v01, v10, v11) with rows
+                                           y0 = min(int(y*(H-1)/(H/8-1)), H-1), y1 = min(y0+1, H-1), columns likewise (float
+                                           arithmetic).  1/16 of the bytes; what b200pose_refine_iters_host2 sends over PCIe */
 
 int b200pose_version(void);
 const char* b200pose_error_string(int code);
@@ -280,6 +285,24 @@ int b200pose_refine_iters_host(const void* packed_weights,
                                int B, int C_geo, int H, int W, int n_iters, int n_lm,
                                double ep_lmbda, double lm_lmbda, int flags,
                                void* device_scratch, size_t device_scratch_bytes, void* stream);
+
+/* The same, with the context map gathered on the host: n_host_threads worker threads (<= 0: half of the CPUs the process
+ * may run on, at most 8; they live for the call) copy the texels the 1/8 resample reads (B200POSE_FLAG_CONTEXT_TEXELS layout,
+ * 1/16 of the map) into host_staging, one sub-batch ahead of the transfers, and only those cross PCIe.  host_staging: 16-byte
+ * aligned, b200pose_refine_host_staging_bytes(B,H,W) bytes, pinned for full copy speed; NULL = exactly
+ * b200pose_refine_iters_host.  Results are bit-identical to the device-buffer entry.                  */
+size_t b200pose_refine_host_staging_bytes(int B, int H, int W);
+/* Host-only helper (no CUDA call): the gather by itself, context_host [B,256,H,W] -> texels_host [B,256,(H/8)*(W/8),4]
+ * (16-byte aligned), for callers that upload the texels themselves and pass B200POSE_FLAG_CONTEXT_TEXELS. */
+int b200pose_context_gather_texels(const float* context_host, int B, int H, int W, float* texels_host, int n_host_threads);
+int b200pose_refine_iters_host2(const void* packed_weights,
+                                const float* fmap1_host, const float* fmap2_host, const float* context_host,
+                                const float* geofea1_host, const float* geofea2_host, const float* depth_host,
+                                const float* K_host, float* G_host, float sigma,
+                                int B, int C_geo, int H, int W, int n_iters, int n_lm,
+                                double ep_lmbda, double lm_lmbda, int flags,
+                                void* device_scratch, size_t device_scratch_bytes,
+                                void* host_staging, size_t host_staging_bytes, int n_host_threads, void* stream);
 
 /* Measurement hook (bench.py "roofline"): the NEXT tensor-core update-block pass (b200pose_update_block or an iteration of
  * b200pose_refine_iters) records the two cudaEvent_t on its stream immediately before and after its convolution launch(es)

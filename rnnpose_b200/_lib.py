@@ -53,6 +53,9 @@ SIGNATURES = {
     "b200pose_refine_iters": (_i, [_vp] * 9 + [_f, _i, _i, _i, _i, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200pose_refine_host_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "b200pose_refine_iters_host": (_i, [_vp] * 9 + [_f, _i, _i, _i, _i, _i, _i, _d, _d, _i, _vp, _sz, _vp]),
+    "b200pose_refine_host_staging_bytes": (_sz, [_i, _i, _i]),
+    "b200pose_context_gather_texels": (_i, [_vp, _i, _i, _i, _vp, _i]),
+    "b200pose_refine_iters_host2": (_i, [_vp] * 9 + [_f, _i, _i, _i, _i, _i, _i, _d, _d, _i, _vp, _sz, _vp, _sz, _i, _vp]),
     "b200pose_debug_set_conv_events": (_i, [_vp, _vp]),
     "b200pose_refine_launch_count": (_i, [_i, _i, _i, _i, _i]),
 }

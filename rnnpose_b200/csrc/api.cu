@@ -4,6 +4,12 @@
 
 #include <stdio.h>
 #include <stdlib.h>
+#include <sched.h>
+#include <xmmintrin.h>
+#include <atomic>
+#include <memory>
+#include <thread>
+#include <vector>
 
 namespace {
 
@@ -688,8 +694,9 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
         if ((rc = run_corr_volume_tc(fmap1, fmap2, B, h, w, r.pyr, r.vol, s))) return rc;
         if ((rc = pool_pyramid(r.pyr, B, h, w, s))) return rc;
     } else if ((rc = b200pose_corr_pyramid(fmap1, fmap2, B, 256, h, w, r.pyr, stream))) return rc;
-    if (tc) rc = b2p_context_init(context, B, H, W, r.net, nullptr, u.net_h[0], u.net_h[1], u.x_h[0], u.x_h[1], s);
-    else rc = b2p_context_init(context, B, H, W, r.net, r.xbuf, nullptr, nullptr, nullptr, nullptr, s);
+    const bool ctx_packed = (flags & B200POSE_FLAG_CONTEXT_TEXELS) != 0;
+    if (tc) rc = b2p_context_init(context, B, H, W, r.net, nullptr, u.net_h[0], u.net_h[1], u.x_h[0], u.x_h[1], s, ctx_packed);
+    else rc = b2p_context_init(context, B, H, W, r.net, r.xbuf, nullptr, nullptr, nullptr, nullptr, s, ctx_packed);
     if (rc) return rc;
     if (tc && (rc = b2p_pxc_to_tiled(r.net, u.rhbuf, B, h, w, 128, s))) return rc;     // hidden state of the tensor-core epilogues
     if (tc && (rc = b2p_pxc_to_tiled(r.net, u.hbuf_x, B, h, w, 128, s, 1))) return rc;  // ... and its x-major copy (chained launch)
@@ -760,9 +767,63 @@ struct HostScratch {
     void* ws; size_t ws_bytes;
     int bs;                   // samples per sub-batch
 };
+// Host-side gather of the context texels the 1/8 resample reads (4 of every 64 floats), by a few worker threads that live
+// for one call.  Pure data movement: the interpolation itself stays in context_init_kernel<PACKED>.  Sub-batch k's texels
+// are complete when done[k] == T; the workers never wait (the staging buffer holds the whole batch).
+struct TexelGather {
+    const float* ctx = nullptr; float* out = nullptr;
+    int B = 0, H = 0, W = 0, h = 0, w = 0, bs = 0, nsub = 0, T = 0;
+    std::vector<int> x0, x1, y0, y1;
+    std::unique_ptr<std::atomic<int>[]> done;
+    std::vector<std::thread> workers;
+
+    void start(const float* ctx_, float* out_, int B_, int H_, int W_, int bs_, int nsub_, int threads) {
+        ctx = ctx_; out = out_; B = B_; H = H_; W = W_; h = H / 8; w = W / 8; bs = bs_; nsub = nsub_;
+        if (threads <= 0) {                          // auto: half of the CPUs this process may run on, at most 8
+            cpu_set_t set; CPU_ZERO(&set);
+            int n = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+            threads = n / 2;
+        }
+        T = threads < 1 ? 1 : (threads > 16 ? 16 : threads);
+        x0.resize(w); x1.resize(w); y0.resize(h); y1.resize(h);
+        b2p_context_sample_taps(W, w, x0.data(), x1.data());
+        b2p_context_sample_taps(H, h, y0.data(), y1.data());
+        done.reset(new std::atomic<int>[nsub]);
+        for (int k = 0; k < nsub; ++k) done[k].store(0, std::memory_order_relaxed);
+        for (int t = 0; t < T; ++t) workers.emplace_back([this, t] { run(t); });
+    }
+    void run(int t) const {
+        const size_t P = (size_t)h * w;
+        for (int k = 0; k < nsub; ++k) {
+            const int b0 = k * bs, nb = (B - b0 < bs) ? (B - b0) : bs;
+            const long planes = (long)nb * 256, lo = planes * t / T, hi = planes * (t + 1) / T;
+            for (long pl = lo; pl < hi; ++pl) {
+                const float* src = ctx + ((size_t)b0 * 256 + pl) * (size_t)H * W;
+                float* dst = out + ((size_t)b0 * 256 + pl) * P * 4;
+                for (int y = 0; y < h; ++y) {
+                    const float* r0 = src + (size_t)y0[y] * W;
+                    const float* r1 = src + (size_t)y1[y] * W;
+                    for (int x = 0; x < w; ++x, dst += 4)          // streaming store: the CPU never reads the texels back
+                        _mm_stream_ps(dst, _mm_set_ps(r1[x1[x]], r1[x0[x]], r0[x1[x]], r0[x0[x]]));
+                }
+            }
+            _mm_sfence();
+            done[k].fetch_add(1, std::memory_order_release);
+        }
+    }
+    void wait(int k) const {
+        while (done[k].load(std::memory_order_acquire) < T) std::this_thread::yield();
+    }
+    void join() {
+        for (auto& th : workers) th.join();
+        workers.clear();
+    }
+};
+
 inline int host_sub_batch(int B) { return B >= 8 ? (B + 3) / 4 : (B >= 2 ? (B + 1) / 2 : 1); }
 
-size_t host_scratch_layout(int B, int C, int H, int W, bool stage_context, void* p, size_t cap, HostScratch* out) {
+// stage_context: 0 = read in place from mapped host memory, 1 = full map, 2 = the four texels per low-res sample
+size_t host_scratch_layout(int B, int C, int H, int W, int stage_context, void* p, size_t cap, HostScratch* out) {
     const int h = H / 8, w = W / 8;
     const int bs = host_sub_batch(B);
     Carver c(p, cap);
@@ -772,7 +833,8 @@ size_t host_scratch_layout(int B, int C, int H, int W, bool stage_context, void*
         HostStage& st = hs.st[k];
         st.fmap1 = c.take<float>((size_t)bs * 256 * h * w);
         st.fmap2 = c.take<float>((size_t)bs * 256 * h * w);
-        st.context = stage_context ? c.take<float>((size_t)bs * 256 * H * W) : nullptr;
+        st.context = stage_context == 1 ? c.take<float>((size_t)bs * 256 * H * W)
+                   : stage_context == 2 ? c.take<float>((size_t)bs * 256 * h * w * 4) : nullptr;
         st.geo1 = c.take<float>((size_t)bs * C * H * W);
         st.geo2 = c.take<float>((size_t)bs * C * H * W);
         st.depth = c.take<float>((size_t)bs * H * W);
@@ -789,7 +851,22 @@ size_t host_scratch_layout(int B, int C, int H, int W, bool stage_context, void*
 extern "C" {
 
 size_t b200pose_refine_host_scratch_bytes(int B, int C_geo, int H, int W) {
-    return host_scratch_layout(B, C_geo, H, W, true, nullptr, 0, nullptr);     // worst case: context staged too
+    return host_scratch_layout(B, C_geo, H, W, 1, nullptr, 0, nullptr);     // worst case: context staged too
+}
+
+size_t b200pose_refine_host_staging_bytes(int B, int H, int W) {
+    if (B < 1 || H < 8 || W < 8) return 0;
+    return (size_t)B * 256 * (H / 8) * (W / 8) * 4 * sizeof(float);
+}
+
+int b200pose_context_gather_texels(const float* context_host, int B, int H, int W, float* texels_host, int n_host_threads) {
+    if (!context_host || !texels_host) return B200POSE_E_NULL;
+    if (B < 1 || H < 16 || W < 16 || ((uintptr_t)texels_host & 15)) return B200POSE_E_SHAPE;
+    TexelGather tg;
+    tg.start(context_host, texels_host, B, H, W, B, 1, n_host_threads);
+    tg.wait(0);
+    tg.join();
+    return 0;
 }
 
 int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_host, const float* fmap2_host,
@@ -797,19 +874,37 @@ int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_ho
                                const float* depth_host, const float* K_host, float* G_host, float sigma, int B,
                                int C_geo, int H, int W, int n_iters, int n_lm, double ep_lmbda, double lm_lmbda,
                                int flags, void* device_scratch, size_t device_scratch_bytes, void* stream) {
+    return b200pose_refine_iters_host2(packed_weights, fmap1_host, fmap2_host, context_host, geofea1_host, geofea2_host,
+                                       depth_host, K_host, G_host, sigma, B, C_geo, H, W, n_iters, n_lm, ep_lmbda, lm_lmbda,
+                                       flags, device_scratch, device_scratch_bytes, nullptr, 0, 0, stream);
+}
+
+int b200pose_refine_iters_host2(const void* packed_weights, const float* fmap1_host, const float* fmap2_host,
+                                const float* context_host, const float* geofea1_host, const float* geofea2_host,
+                                const float* depth_host, const float* K_host, float* G_host, float sigma, int B,
+                                int C_geo, int H, int W, int n_iters, int n_lm, double ep_lmbda, double lm_lmbda,
+                                int flags, void* device_scratch, size_t device_scratch_bytes, void* host_staging,
+                                size_t host_staging_bytes, int n_host_threads, void* stream) {
     if (!packed_weights || !fmap1_host || !fmap2_host || !context_host || !geofea1_host || !geofea2_host ||
         !depth_host || !K_host || !G_host || !device_scratch)
         return B200POSE_E_NULL;
     if (!shape_ok(B, H, W) || C_geo < 1) return B200POSE_E_SHAPE;
+    if (flags & B200POSE_FLAG_CONTEXT_TEXELS) return B200POSE_E_SHAPE;          // the host entry takes the full map
     if (((uintptr_t)device_scratch & 1023) || device_scratch_bytes < b200pose_refine_host_scratch_bytes(B, C_geo, H, W))
+        return B200POSE_E_WORKSPACE;
+    const bool gather = host_staging != nullptr;
+    if (gather && (((uintptr_t)host_staging & 15) || host_staging_bytes < b200pose_refine_host_staging_bytes(B, H, W)))
         return B200POSE_E_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
 
-    // The loop only ever touches the context map at the 4 texels around each 1/8-resolution sample (CFNet.py:129), i.e.
-    // ~2 of every 8 rows.  When the caller's buffer is pinned (device-accessible through UVA) the context-init kernel
-    // reads those rows straight from host memory over PCIe instead of first copying all B*256*H*W floats.
+    // The loop only ever touches the context map at the 4 texels around each 1/8-resolution sample (CFNet.py:129): 1/16 of
+    // its floats, 2 of every 8 rows.  Two ways not to copy all B*256*H*W floats:
+    //  * host_staging given: worker threads gather those texels into the caller's (pinned) staging buffer, one sub-batch
+    //    ahead of the copies, and only the texels cross PCIe (B200POSE_FLAG_CONTEXT_TEXELS layout);
+    //  * else, when context_host is pinned (device-accessible through UVA), the context-init kernel reads the rows straight
+    //    from host memory (every 32-byte sector of 2 rows in 8 is touched: 1/4 of the bytes).
     const float* ctx_mapped = nullptr;
-    {
+    if (!gather) {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, context_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
             attr.devicePointer != nullptr)
@@ -829,10 +924,14 @@ int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_ho
             (void)cudaGetLastError();
     }
     HostScratch hs;
-    host_scratch_layout(B, C_geo, H, W, ctx_mapped == nullptr, device_scratch, device_scratch_bytes, &hs);
+    host_scratch_layout(B, C_geo, H, W, gather ? 2 : (ctx_mapped == nullptr ? 1 : 0), device_scratch, device_scratch_bytes, &hs);
     const int h = H / 8, w = W / 8, bs = hs.bs;
     const int nsub = (B + bs - 1) / bs;
     const size_t f = sizeof(float);
+    const int loop_flags = gather ? (flags | B200POSE_FLAG_CONTEXT_TEXELS) : flags;
+
+    TexelGather tg;
+    if (gather) tg.start(context_host, reinterpret_cast<float*>(host_staging), B, H, W, bs, nsub, n_host_threads);
 
     cudaStream_t cs = nullptr;                     // internal copy stream + events, created and destroyed per call
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_start = nullptr;
@@ -852,7 +951,7 @@ int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_ho
         if (k >= 2) B2P_TRY(cudaStreamWaitEvent(cs, ev_done[k & 1], 0));        // staging buffer free again
         B2P_TRY(cudaMemcpyAsync(st.fmap1, fmap1_host + (size_t)b0 * 256 * h * w, (size_t)nb * 256 * h * w * f, cudaMemcpyHostToDevice, cs));
         B2P_TRY(cudaMemcpyAsync(st.fmap2, fmap2_host + (size_t)b0 * 256 * h * w, (size_t)nb * 256 * h * w * f, cudaMemcpyHostToDevice, cs));
-        if (!ctx_mapped)
+        if (!ctx_mapped && !gather)
             B2P_TRY(cudaMemcpyAsync(st.context, context_host + (size_t)b0 * 256 * H * W, (size_t)nb * 256 * H * W * f, cudaMemcpyHostToDevice, cs));
         B2P_TRY(cudaMemcpyAsync(st.depth, depth_host + (size_t)b0 * H * W, (size_t)nb * H * W * f, cudaMemcpyHostToDevice, cs));
         if (g1_mapped) {
@@ -864,11 +963,16 @@ int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_ho
         B2P_TRY(cudaMemcpyAsync(st.geo2, geofea2_host + (size_t)b0 * C_geo * H * W, (size_t)nb * C_geo * H * W * f, cudaMemcpyHostToDevice, cs));
         B2P_TRY(cudaMemcpyAsync(st.K, K_host + (size_t)b0 * 9, (size_t)nb * 9 * f, cudaMemcpyHostToDevice, cs));
         B2P_TRY(cudaMemcpyAsync(st.G, G_host + (size_t)b0 * 16, (size_t)nb * 16 * f, cudaMemcpyHostToDevice, cs));
+        if (gather) {                               // the workers ran ahead while the copies above were queued / in flight
+            tg.wait(k);
+            const size_t per = (size_t)256 * h * w * 4;
+            B2P_TRY(cudaMemcpyAsync(st.context, reinterpret_cast<const float*>(host_staging) + (size_t)b0 * per, (size_t)nb * per * f, cudaMemcpyHostToDevice, cs));
+        }
         B2P_TRY(cudaEventRecord(ev_copy[k & 1], cs));
         B2P_TRY(cudaStreamWaitEvent(s, ev_copy[k & 1], 0));
         const float* ctx = ctx_mapped ? ctx_mapped + (size_t)b0 * 256 * H * W : st.context;
         rc = b200pose_refine_iters(packed_weights, st.fmap1, st.fmap2, ctx, st.geo1, st.geo2, st.depth, st.K, st.G, sigma, nb,
-                                   C_geo, H, W, n_iters, n_lm, ep_lmbda, lm_lmbda, flags, nullptr, nullptr, nullptr, hs.ws,
+                                   C_geo, H, W, n_iters, n_lm, ep_lmbda, lm_lmbda, loop_flags, nullptr, nullptr, nullptr, hs.ws,
                                    hs.ws_bytes, stream);
         if (rc) goto cleanup;
         B2P_TRY(cudaMemcpyAsync(G_host + (size_t)b0 * 16, st.G, (size_t)nb * 16 * f, cudaMemcpyDeviceToHost, s));
@@ -877,6 +981,7 @@ int b200pose_refine_iters_host(const void* packed_weights, const float* fmap1_ho
     B2P_TRY(cudaStreamSynchronize(s));
 cleanup:
 #undef B2P_TRY
+    tg.join();
     if (rc) { if (cs) cudaStreamSynchronize(cs); cudaStreamSynchronize(s); }
     for (int k = 0; k < 2; ++k) { if (ev_copy[k]) cudaEventDestroy(ev_copy[k]); if (ev_done[k]) cudaEventDestroy(ev_done[k]); }
     if (ev_start) cudaEventDestroy(ev_start);

@@ -188,7 +188,8 @@ int b2p_fmap_to_pxc_half(const float* f, int B, int D, int P, __half* hi, __half
 int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, __half* out_hi,
                     __half* out_lo, cudaStream_t s);
 int b2p_context_init(const float* ctx, int B, int H, int W, float* net, float* xbuf, __half* net_hi, __half* net_lo,
-                     __half* x_hi, __half* x_lo, cudaStream_t s);
+                     __half* x_hi, __half* x_lo, cudaStream_t s, bool packed = false);
+void b2p_context_sample_taps(int in, int out, int* i0, int* i1);
 int b2p_flow_init(const float* depth, const float* K, const float* G, int B, int H, int W,
                   float* coords1, float* flow, cudaStream_t s);
 int b2p_im2col_f1(const float* flow, int B, int h, int w, float* col /*[P][112]*/, float* xbuf /*[P][256] ch 254,255*/,

@@ -230,6 +230,9 @@ __global__ void __launch_bounds__(128) corr_pool3_kernel(const float* __restrict
 
 // context [B,256,H,W] --(1/8 bilinear, align_corners=True)--> net = tanh(ch 0..127) [P][128],
 // xbuf[:, 0:128] = relu(ch 128..255).   32 low-res pixels x 32 channels per block, smem transpose.
+// PACKED: ctx holds only the four texels of each low-res sample, [B,256,P] float4 = (v00, v01, v10, v11), as gathered on the
+// host by b200pose_refine_iters_host2 (api.cu: gather_context_texels) -- same arithmetic, 1/16 of the bytes.
+template <bool PACKED>
 __global__ void __launch_bounds__(256) context_init_kernel(const float* __restrict__ ctx, int B, int H, int W, int h, int w,
                                                            float sy, float sx, float* __restrict__ net,
                                                            float* __restrict__ xbuf, __half* __restrict__ net_hi,
@@ -251,9 +254,15 @@ __global__ void __launch_bounds__(256) context_init_kernel(const float* __restri
         const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
         const float ly = fy - (float)y0, lx = fxx - (float)x0;
         for (int cc = tyy; cc < 32; cc += 8) {
-            const float* pl = ctx + ((size_t)b * 256 + c0 + cc) * (size_t)H * W;
-            const float v00 = __ldg(pl + (size_t)y0 * W + x0), v01 = __ldg(pl + (size_t)y0 * W + x1);
-            const float v10 = __ldg(pl + (size_t)y1 * W + x0), v11 = __ldg(pl + (size_t)y1 * W + x1);
+            float v00, v01, v10, v11;
+            if (PACKED) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(ctx) + ((size_t)b * 256 + c0 + cc) * (size_t)P + p);
+                v00 = t.x; v01 = t.y; v10 = t.z; v11 = t.w;
+            } else {
+                const float* pl = ctx + ((size_t)b * 256 + c0 + cc) * (size_t)H * W;
+                v00 = __ldg(pl + (size_t)y0 * W + x0); v01 = __ldg(pl + (size_t)y0 * W + x1);
+                v10 = __ldg(pl + (size_t)y1 * W + x0); v11 = __ldg(pl + (size_t)y1 * W + x1);
+            }
             const float top = v00 * (1.f - lx) + v01 * lx;
             const float bot = v10 * (1.f - lx) + v11 * lx;
             tile[cc][tx] = top * (1.f - ly) + bot * ly;
@@ -377,13 +386,30 @@ int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int
 static inline float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
 
 int b2p_context_init(const float* ctx, int B, int H, int W, float* net, float* xbuf, __half* net_hi, __half* net_lo,
-                     __half* x_hi, __half* x_lo, cudaStream_t s) {
+                     __half* x_hi, __half* x_lo, cudaStream_t s, bool packed) {
     const int h = H / 8, w = W / 8;
     dim3 grid(ceil_div(h * w, 32), 8, B);
-    context_init_kernel<<<grid, 256, 0, s>>>(ctx, B, H, W, h, w, ac_scale(H, h), ac_scale(W, w), net, xbuf, net_hi,
-                                               net_lo, x_hi, x_lo);
+    if (packed)
+        context_init_kernel<true><<<grid, 256, 0, s>>>(ctx, B, H, W, h, w, ac_scale(H, h), ac_scale(W, w), net, xbuf, net_hi,
+                                                         net_lo, x_hi, x_lo);
+    else
+        context_init_kernel<false><<<grid, 256, 0, s>>>(ctx, B, H, W, h, w, ac_scale(H, h), ac_scale(W, w), net, xbuf, net_hi,
+                                                          net_lo, x_hi, x_lo);
     B2P_LAUNCH_CHECK();
     return 0;
+}
+
+// The sample positions of the 1/8 resample (F.interpolate(align_corners=True), CFNet.py:129) exactly as context_init_kernel
+// computes them; used by the host-side texel gather so that both sides pick the same texels.
+void b2p_context_sample_taps(int in, int out, int* i0, int* i1) {
+    const float sc = ac_scale(in, out);
+    for (int o = 0; o < out; ++o) {
+        const float f = sc * (float)o;
+        int a = (int)f;
+        a = a < in - 1 ? a : in - 1;
+        i0[o] = a;
+        i1[o] = a + 1 < in - 1 ? a + 1 : in - 1;
+    }
 }
 
 int b2p_flow_init(const float* depth, const float* K, const float* G, int B, int H, int W, float* coords1, float* flow,

@@ -15,13 +15,16 @@
 namespace {
 
 // Everything for one full-resolution pixel (b, Y, X): convex upsampling, target, descriptor similarity weight.
+// NPLANE: H*W when known at compile time (the plane stride of the descriptor loads becomes an immediate offset: 5 loads per
+// channel with no address arithmetic), 0 = run-time size.
+template <int NPLANE = 0>
 __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ flow, const float* __restrict__ mask,
                                                       const float* __restrict__ g1, const float* __restrict__ g2,
                                                       const float* __restrict__ depth, float sigma, int b, int Y, int X, int C, int H,
                                                       int W, float* __restrict__ flow_up, float* __restrict__ target,
                                                       float* __restrict__ weight) {
     const int h = H >> 3, w = W >> 3;
-    const size_t N = (size_t)H * W;
+    const size_t N = NPLANE ? (size_t)NPLANE : (size_t)H * W;
     const int r = Y * W + X;
     const size_t idx = (size_t)b * N + r;
     const int y = Y >> 3, i = Y & 7, x = X >> 3, j = X & 7;
@@ -107,13 +110,14 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
     weight[idx] = wgt;
 }
 
+template <int NPLANE>
 __global__ void __launch_bounds__(64) upsample_weight_kernel(
     const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1,
     const float* __restrict__ g2, const float* __restrict__ depth, float sigma, int B, int C, int H, int W,
     float* __restrict__ flow_up, float* __restrict__ target, float* __restrict__ weight, int lazy_background) {
     pdl_trigger();
     pdl_wait();
-    const size_t N = (size_t)H * W;
+    const size_t N = NPLANE ? (size_t)NPLANE : (size_t)H * W;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)B * N) return;
     const int b = (int)(idx / N);
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(64) upsample_weight_kernel(
         if (weight) weight[idx] = 0.f;
         return;
     }
-    upsample_weight_pixel(flow, mask, g1, g2, depth, sigma, b, Y, X, C, H, W, flow_up, target, weight);
+    upsample_weight_pixel<NPLANE>(flow, mask, g1, g2, depth, sigma, b, Y, X, C, H, W, flow_up, target, weight);
 }
 
 // ------------------------------------------------------------------------------------------------ foreground list
@@ -264,8 +268,14 @@ int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, c
                         float sigma, int B, int C, int H, int W, float* flow_up, float* target, float* weight,
                         int lazy_background, cudaStream_t s) {
     const size_t total = (size_t)B * H * W;
-    B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel, dim3((unsigned)((total + 63) / 64)), dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B,
-                            C, H, W, flow_up, target, weight, lazy_background));
+    const dim3 grid((unsigned)((total + 63) / 64));
+    // the reference's crop size (ZOOM_CROP_SIZE 240x320, config/default.py) and its double get the immediate-offset build
+    if (H * W == 240 * 320)
+        B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel<240 * 320>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up,
+                                target, weight, lazy_background));
+    else
+        B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel<0>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up,
+                                target, weight, lazy_background));
     B2P_LAUNCH_CHECK();
     return 0;
 }

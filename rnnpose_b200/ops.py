@@ -19,6 +19,7 @@ WEIGHT_KEYS: List[str] = [
 FLAG_EXACT_FP32 = 0      # CUDA-core fp32 convolutions
 FLAG_TENSOR_CORES = 1    # tcgen05 convolutions on fp16 hi/lo split operands (fp32-level accuracy)
 FLAG_GEO2_CHANNELS_LAST = 2   # refine_iters: geofea2 is [B, H*W, 32] (what zoom_crop(channels_last=True) writes)
+FLAG_CONTEXT_TEXELS = 4       # refine_iters: context is [B,256,(H/8)*(W/8),4], the texels of the 1/8 resample (context_gather_texels)
 DEFAULT_FLAGS = FLAG_TENSOR_CORES
 LM_LMBDA = 1e-4   # reference config/default.py:54
 EP_LMBDA = 100.0  # reference config/default.py:55
@@ -457,11 +458,32 @@ def refine_iters(packed: torch.Tensor, fmap1, fmap2, context, geofea1, geofea2, 
     return dict(G=G, flow_first=ff, flow_last=fl, weight=wl, workspace=workspace)
 
 
+def host_staging(B: int, H: int, W: int) -> torch.Tensor:
+    """Pinned staging buffer for refine_iters_host(..., staging=...): b200pose_refine_host_staging_bytes(B, H, W)."""
+    n = _lib.lib().b200pose_refine_host_staging_bytes(B, H, W)
+    return torch.empty(n // 4, dtype=torch.float32).pin_memory()
+
+
+def context_gather_texels(context: torch.Tensor, threads: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Host-only (no CUDA): context [B,256,H,W] CPU float32 -> the texels the 1/8 resample reads, [B,256,(H/8)*(W/8),4]
+    (b200pose_context_gather_texels; the layout FLAG_CONTEXT_TEXELS names)."""
+    if context.is_cuda or context.dtype != torch.float32 or not context.is_contiguous() or context.dim() != 4 or context.shape[1] != 256:
+        raise ValueError("context_gather_texels expects a contiguous CPU float32 [B,256,H,W] tensor")
+    B, _, H, W = context.shape
+    if out is None:
+        out = torch.empty(B, 256, (H // 8) * (W // 8), 4, dtype=torch.float32)
+    _lib.check(_lib.lib().b200pose_context_gather_texels(context.data_ptr(), B, H, W, out.data_ptr(), int(threads)),
+               "b200pose_context_gather_texels")
+    return out
+
+
 def refine_iters_host(packed: torch.Tensor, fmap1, fmap2, context, geofea1, geofea2, depth, K, G, sigma: float,
                       n_iters: int, n_lm: int, ep_lmbda: float = EP_LMBDA, lm_lmbda: float = LM_LMBDA,
-                      scratch: Optional[torch.Tensor] = None, flags: int = DEFAULT_FLAGS):
-    """Host-buffer entry point (b200pose_refine_iters_host): all tensors are CPU float32 (pinned for full
-    copy speed); G [B,4,4] is overwritten on the host.  Synchronises the stream before returning."""
+                      scratch: Optional[torch.Tensor] = None, flags: int = DEFAULT_FLAGS,
+                      staging: Optional[torch.Tensor] = None, threads: int = 0):
+    """Host-buffer entry point (b200pose_refine_iters_host[2]): all tensors are CPU float32 (pinned for full
+    copy speed); G [B,4,4] is overwritten on the host.  Synchronises the stream before returning.
+    staging (host_staging(B,H,W), pinned) switches on the host-side gather of the context texels by `threads` workers."""
     _need_cuda()
     L = _lib.lib()
     for t in (fmap1, fmap2, context, geofea1, geofea2, depth, K, G):
@@ -472,11 +494,14 @@ def refine_iters_host(packed: torch.Tensor, fmap1, fmap2, context, geofea1, geof
     nb = L.b200pose_refine_host_scratch_bytes(B, Cg, H, W)
     if scratch is None or scratch.numel() < nb:
         scratch = _ws(nb, packed.device)
-    _lib.check(L.b200pose_refine_iters_host(packed.data_ptr(), fmap1.data_ptr(), fmap2.data_ptr(), context.data_ptr(),
-                                            geofea1.data_ptr(), geofea2.data_ptr(), depth.data_ptr(), K.data_ptr(),
-                                            G.data_ptr(), float(sigma), B, Cg, H, W, n_iters, n_lm, float(ep_lmbda),
-                                            float(lm_lmbda), int(flags), scratch.data_ptr(), scratch.numel(), _stream()),
-               "b200pose_refine_iters_host")
+    _lib.check(L.b200pose_refine_iters_host2(packed.data_ptr(), fmap1.data_ptr(), fmap2.data_ptr(), context.data_ptr(),
+                                             geofea1.data_ptr(), geofea2.data_ptr(), depth.data_ptr(), K.data_ptr(),
+                                             G.data_ptr(), float(sigma), B, Cg, H, W, n_iters, n_lm, float(ep_lmbda),
+                                             float(lm_lmbda), int(flags), scratch.data_ptr(), scratch.numel(),
+                                             staging.data_ptr() if staging is not None else None,
+                                             staging.numel() * staging.element_size() if staging is not None else 0,
+                                             int(threads), _stream()),
+               "b200pose_refine_iters_host2")
     return G, scratch
 
 

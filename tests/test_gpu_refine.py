@@ -148,6 +148,31 @@ def test_refine_host_entry_matches_device_entry(ops, packed):
     assert torch.equal(Gh, Gd)
 
 
+@pytest.mark.parametrize("threads", [1, 3])
+@pytest.mark.parametrize("B", [2, 9])
+def test_refine_host_entry_with_gathered_context_texels(ops, packed, B, threads):
+    """b200pose_refine_iters_host2: host threads gather the texels of the 1/8 resample, only those cross PCIe; and the device
+    entry with B200POSE_FLAG_CONTEXT_TEXELS fed by b200pose_context_gather_texels.  Both bit-identical to the plain call
+    (B = 9: three sub-batches, the last one ragged; more planes than threads and vice versa)."""
+    H, W = 128, 160
+    idxs = list(range(30, 30 + B))
+    mb = S.make_batch(idxs, H, W, with_images=False)
+    f1 = S.hash_features((B, 256, H // 8, W // 8), 85); f2 = S.hash_features((B, 256, H // 8, W // 8), 86)
+    G0 = torch.eye(4)[None].repeat(B, 1, 1)
+    Gd = run_gpu(ops, packed, f1, f2, mb, G0, 2, 2)["G"].cpu()
+    Gh = G0.clone()
+    staging = ops.host_staging(B, H, W)
+    staging.fill_(float("nan"))
+    ops.refine_iters_host(packed, f1, f2, mb["context"], mb["geofea1"], mb["geofea2"], mb["depth"][:, 0].contiguous(),
+                          mb["K"], Gh, 1.0, 2, 2, staging=staging, threads=threads)
+    assert torch.equal(Gh, Gd)
+    tex = ops.context_gather_texels(mb["context"], threads=threads)
+    assert torch.equal(tex.flatten(), staging[:tex.numel()])
+    mt = dict(mb); mt["context"] = tex
+    Gt = run_gpu(ops, packed, f1, f2, mt, G0, 2, 2, flags=ops.DEFAULT_FLAGS | ops.FLAG_CONTEXT_TEXELS)["G"].cpu()
+    assert torch.equal(Gt, Gd)
+
+
 def test_refine_iters_cuda_graph_capture(ops, packed):
     """b200pose_refine_iters is stream-ordered and allocation-free: captured into a CUDA graph (PDL and cluster launches
     included) and replayed, it reproduces the eager result bit for bit, also after the inputs change in place."""
