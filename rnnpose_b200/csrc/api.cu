@@ -772,13 +772,14 @@ struct HostScratch {
 // are complete when done[k] == T; the workers never wait (the staging buffer holds the whole batch).
 struct TexelGather {
     const float* ctx = nullptr; float* out = nullptr;
-    int B = 0, H = 0, W = 0, h = 0, w = 0, bs = 0, nsub = 0, T = 0;
+    int B = 0, H = 0, W = 0, h = 0, w = 0, bs = 0, nsub = 0, T = 0, mode = 0;
     std::vector<int> x0, x1, y0, y1;
     std::unique_ptr<std::atomic<int>[]> done;
     std::vector<std::thread> workers;
 
     void start(const float* ctx_, float* out_, int B_, int H_, int W_, int bs_, int nsub_, int threads) {
         ctx = ctx_; out = out_; B = B_; H = H_; W = W_; h = H / 8; w = W / 8; bs = bs_; nsub = nsub_;
+        mode = b2p_options().host_gather;
         if (threads <= 0) {                          // auto: half of the CPUs this process may run on, at most 8
             cpu_set_t set; CPU_ZERO(&set);
             int n = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
@@ -803,8 +804,17 @@ struct TexelGather {
                 for (int y = 0; y < h; ++y) {
                     const float* r0 = src + (size_t)y0[y] * W;
                     const float* r1 = src + (size_t)y1[y] * W;
-                    for (int x = 0; x < w; ++x, dst += 4)          // streaming store: the CPU never reads the texels back
-                        _mm_stream_ps(dst, _mm_set_ps(r1[x1[x]], r1[x0[x]], r0[x1[x]], r0[x0[x]]));
+                    if ((mode & 1) && (y + 1 < h || pl + 1 < hi)) {   // the two source rows of the next output row (or of the next plane)
+                        const float* n0 = y + 1 < h ? src + (size_t)y0[y + 1] * W : src + (size_t)H * W + (size_t)y0[0] * W;
+                        const float* n1 = y + 1 < h ? src + (size_t)y1[y + 1] * W : src + (size_t)H * W + (size_t)y1[0] * W;
+                        for (int x = 0; x < W; x += 16) { _mm_prefetch((const char*)(n0 + x), _MM_HINT_T0); _mm_prefetch((const char*)(n1 + x), _MM_HINT_T0); }
+                    }
+                    if (mode & 2)
+                        for (int x = 0; x < w; ++x, dst += 4)
+                            _mm_store_ps(dst, _mm_set_ps(r1[x1[x]], r1[x0[x]], r0[x1[x]], r0[x0[x]]));
+                    else
+                        for (int x = 0; x < w; ++x, dst += 4)          // streaming store: the CPU never reads the texels back
+                            _mm_stream_ps(dst, _mm_set_ps(r1[x1[x]], r1[x0[x]], r0[x1[x]], r0[x0[x]]));
                 }
             }
             _mm_sfence();

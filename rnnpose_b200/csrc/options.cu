@@ -30,6 +30,8 @@ const OptDesc kOpts[] = {
     {"chain_rings", "B200POSE_CHAIN_RINGS", &B2POptions::chain_rings, 24},  // chained launch: 10 * activation slots + weight slots
     {"chain_xmajor", "B200POSE_CHAIN_XMAJOR", &B2POptions::chain_xmajor, 1},   // chained launch: horizontal-tap reuse for the 1x5 layers
     {"chain_merge", "B200POSE_CHAIN_MERGE", &B2POptions::chain_merge, 0},     // chained launch: interleave C1|F1 and MASK2|flow head units (measured: no gain)
+    {"upsample_variant", "B200POSE_UPSAMPLE_VARIANT", &B2POptions::upsample_variant, 3},   // dense upsample+weight kernel build, see b2p_upsample_weight
+    {"host_gather", "B200POSE_HOST_GATHER", &B2POptions::host_gather, 1},     // host texel gather: bit 0 software prefetch of the next rows, bit 1 plain (not streaming) stores
     {"chain_dynamic", "B200POSE_CHAIN_DYNAMIC", &B2POptions::chain_dynamic, 0},   // chained launch: units from a global queue (1) or static round robin (0)
 };
 constexpr int kNumOpts = (int)(sizeof(kOpts) / sizeof(kOpts[0]));

@@ -14,10 +14,20 @@
 
 namespace {
 
+// A read-only load the compiler may not reorder against its siblings or sink to its use (volatile asm): the staged variants
+// below want all loads of a channel batch issued back to back.
+__device__ __forceinline__ float ldg_ordered(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // Everything for one full-resolution pixel (b, Y, X): convex upsampling, target, descriptor similarity weight.
 // NPLANE: H*W when known at compile time (the plane stride of the descriptor loads becomes an immediate offset: 5 loads per
 // channel with no address arithmetic), 0 = run-time size.
-template <int NPLANE = 0>
+// BATCH: 0 = one loop over the channels (the compiler picks the load schedule), 8 / 16 = channels are loaded BATCH at a time into
+// registers before any of them is used (5 * BATCH independent loads in flight per thread).
+template <int NPLANE = 0, int BATCH = 0>
 __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ flow, const float* __restrict__ mask,
                                                       const float* __restrict__ g1, const float* __restrict__ g2,
                                                       const float* __restrict__ depth, float sigma, int b, int Y, int X, int C, int H,
@@ -93,8 +103,30 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
         float s = 0.f;
         const float* g1p = g1 + (size_t)b * C * N + r;
         const float* g2p = g2 + (size_t)b * C * N;
+        int c = 0;
+        if (BATCH > 0) {
+            constexpr int NB = BATCH > 0 ? BATCH : 1;
+            for (; c + NB <= C; c += NB) {
+                float t[NB][4], a[NB];
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+                    const float* pl = g2p + (size_t)(c + k) * N;
+                    t[k][0] = ldg_ordered(pl + o00); t[k][1] = ldg_ordered(pl + o01); t[k][2] = ldg_ordered(pl + o10); t[k][3] = ldg_ordered(pl + o11);
+                    a[k] = ldg_ordered(g1p + (size_t)(c + k) * N);
+                }
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+                    float v = 0.f;
+                    v += (k00 ? t[k][0] : 0.f) * w00;
+                    v += (k01 ? t[k][1] : 0.f) * w01;
+                    v += (k10 ? t[k][2] : 0.f) * w10;
+                    v += (k11 ? t[k][3] : 0.f) * w11;
+                    s += a[k] * v;
+                }
+            }
+        }
 #pragma unroll 8
-        for (int c = 0; c < C; ++c) {
+        for (; c < C; ++c) {
             const float* pl = g2p + (size_t)c * N;
             const float t00 = __ldg(pl + o00), t01 = __ldg(pl + o01), t10 = __ldg(pl + o10), t11 = __ldg(pl + o11);
             const float a = __ldg(g1p + (size_t)c * N);
@@ -110,7 +142,7 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
     weight[idx] = wgt;
 }
 
-template <int NPLANE>
+template <int NPLANE, int BATCH>
 __global__ void __launch_bounds__(64) upsample_weight_kernel(
     const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1,
     const float* __restrict__ g2, const float* __restrict__ depth, float sigma, int B, int C, int H, int W,
@@ -131,7 +163,7 @@ __global__ void __launch_bounds__(64) upsample_weight_kernel(
         if (weight) weight[idx] = 0.f;
         return;
     }
-    upsample_weight_pixel<NPLANE>(flow, mask, g1, g2, depth, sigma, b, Y, X, C, H, W, flow_up, target, weight);
+    upsample_weight_pixel<NPLANE, BATCH>(flow, mask, g1, g2, depth, sigma, b, Y, X, C, H, W, flow_up, target, weight);
 }
 
 // ------------------------------------------------------------------------------------------------ foreground list
@@ -269,13 +301,21 @@ int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, c
                         int lazy_background, cudaStream_t s) {
     const size_t total = (size_t)B * H * W;
     const dim3 grid((unsigned)((total + 63) / 64));
-    // the reference's crop size (ZOOM_CROP_SIZE 240x320, config/default.py) and its double get the immediate-offset build
-    if (H * W == 240 * 320)
-        B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel<240 * 320>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up,
-                                target, weight, lazy_background));
-    else
-        B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel<0>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up,
-                                target, weight, lazy_background));
+    // upsample_variant (A/B): 0 run-time plane size, compiler-scheduled loads; 1 / 2 / 3 the reference's crop size (ZOOM_CROP_SIZE
+    // 240x320, config/default.py) as a compile-time plane stride (immediate load offsets) with the plain loop / 8 / 16 channels
+    // staged (5: 32); 4 / 6 run-time size, 8 / 16 staged.  Measured (profiles/r2l): 97 / 124 / 120 / 88 / 97 us -> default 3;
+    // other crop sizes run variant 0
+    const int var = b2p_options().upsample_variant;
+    const bool cs = H * W == 240 * 320;
+#define UPW_LAUNCH(NP, BT) B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel<NP, BT>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up, target, weight, lazy_background))
+    if (var == 1 && cs) UPW_LAUNCH(240 * 320, 0);
+    else if (var == 2 && cs) UPW_LAUNCH(240 * 320, 8);
+    else if (var == 3 && cs) UPW_LAUNCH(240 * 320, 16);
+    else if (var == 5 && cs) UPW_LAUNCH(240 * 320, 32);
+    else if (var == 6) UPW_LAUNCH(0, 16);
+    else if (var == 4) UPW_LAUNCH(0, 8);
+    else UPW_LAUNCH(0, 0);
+#undef UPW_LAUNCH
     B2P_LAUNCH_CHECK();
     return 0;
 }

@@ -192,6 +192,29 @@ def test_upsample_weight_vs_oracle(ops):
     assert torch.all(wgt.cpu()[depth == 0] == 0)
 
 
+def test_upsample_weight_kernel_builds_agree(ops, libopt):
+    """The dense kernel's builds (option upsample_variant: compile-time plane stride, staged channel batches) are the same
+    arithmetic in the same order: bit-identical outputs at the crop size the specialised builds exist for, and against the
+    oracle there."""
+    B, C, H, W = 2, 32, 240, 320
+    h, w = H // 8, W // 8
+    fl = S.hash_features((B, 2, h, w), 141, 2.5); mk = S.hash_features((B, 576, h, w), 142, 2.0)
+    g1 = S.hash_features((B, C, H, W), 143); g1 = g1 / g1.norm(dim=1, keepdim=True)
+    g2 = S.hash_features((B, C, H, W), 144); g2 = g2 / g2.norm(dim=1, keepdim=True)
+    depth = (S.hash_features((B, H, W), 145) > 0.2).float() * 0.9
+    args = (to_pxc(fl).to(dev()), to_pxc(mk).to(dev()), g1.to(dev()), g2.to(dev()), depth.to(dev()), 0.7, B, H, W)
+    libopt("upsample_variant", 0)
+    fu0, tgt0, wgt0 = [t.clone() for t in ops.upsample_weight(*args)]
+    rfu = O.convex_upsample(fl, mk)
+    u, v = O.pixel_grid(H, W)
+    rw = O.corr_weight(g1, g2, torch.stack([rfu[:, 0] + u, rfu[:, 1] + v], -1), depth, 0.7)
+    torch.testing.assert_close(wgt0.cpu(), rw, rtol=1e-4, atol=2e-5)
+    for var in range(1, 7):
+        libopt("upsample_variant", var)
+        fu, tgt, wgt = ops.upsample_weight(*args)
+        assert torch.equal(fu, fu0) and torch.equal(tgt, tgt0) and torch.equal(wgt, wgt0), f"variant {var}"
+
+
 def test_weight_golden_via_identity_mask(ops):
     """G5 fixture: drive the fused kernel with a mask that selects the centre tap (softmax -> one-hot) so
     that target = grid + 8*flow, then compare the weight with the executed reference."""
