@@ -86,16 +86,20 @@ __global__ void enc_pack_conv_kernel(const float* __restrict__ w, const float* _
 }
 
 // ---------------------------------------------------------------------------------------------- stem: 7x7 stride 2, 3 -> 64, fp32
-// Block = 8 x 16 output pixels x 64 channels (256 threads: pixel = tid & 127, channel half = tid >> 7).  The input patch
-// (21 x 37 x 3, normalised 2 (x / 255) - 1, zero outside the image: the convolution pads the NORMALISED image) and all weights
-// live in shared memory; a warp shares one channel half, so every weight read is a broadcast.
-constexpr int ST_TH = 8, ST_TW = 16, ST_PH = ST_TH * 2 + 5, ST_PW = ST_TW * 2 + 5;
+// Block = 16 x 16 output pixels x 64 channels (256 threads: pixel pair = tid & 127 -> rows ty and ty + 8, channel half = tid >> 7).
+// The input patch (37 x 37 x 3, normalised 2 (x / 255) - 1, zero outside the image: the convolution pads the NORMALISED image)
+// and all weights live in shared memory; a warp shares one channel half, so every weight read is a broadcast, and each
+// 128-bit weight read feeds 8 FFMAs (two pixels): 10 shared-memory instructions per 64 FFMAs (round 2 first version: one
+// pixel per thread, 9 per 32, 856 us for 64 images; profiles/r2m).
+constexpr int ST_TH = 16, ST_TW = 16, ST_PH = ST_TH * 2 + 5, ST_PW = ST_TW * 2 + 5;
+constexpr size_t ST_SMEM_BYTES = (147 * 64 + 3 * ST_PH * (ST_PW + 1)) * sizeof(float);
 
 __global__ void __launch_bounds__(256) enc_stem_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int B, int H, int W,
                                                        int H1, int W1, const float* __restrict__ wk /*[147][64]*/,
                                                        const float* __restrict__ bias, float* __restrict__ out /*[NI*H1*W1][64]*/) {
-    __shared__ __align__(16) float ws[147 * 64];
-    __shared__ float patch[3][ST_PH][ST_PW + 1];
+    extern __shared__ __align__(16) float st_smem[];               // ST_SMEM_BYTES (dynamic: more than the 48 KB static limit)
+    float* ws = st_smem;
+    float (*patch)[ST_PH][ST_PW + 1] = reinterpret_cast<float (*)[ST_PH][ST_PW + 1]>(st_smem + 147 * 64);
     const int n = blockIdx.z;
     const float* img = (n < B ? img1 + (size_t)n * 3 * H * W : img2 + (size_t)(n - B) * 3 * H * W);
     const int oy0 = blockIdx.y * ST_TH, ox0 = blockIdx.x * ST_TW;
@@ -110,35 +114,48 @@ __global__ void __launch_bounds__(256) enc_stem_kernel(const float* __restrict__
     }
     __syncthreads();
     const int pix = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const int ty = pix / ST_TW, tx = pix - ty * ST_TW;
-    float acc[32];
+    const int ty = pix / ST_TW, tx = pix - ty * ST_TW;          // ty 0..7; the second pixel is 8 rows below
+    float acc0[32], acc1[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = __ldg(bias + half * 32 + j);
+    for (int j = 0; j < 32; ++j) acc0[j] = acc1[j] = __ldg(bias + half * 32 + j);
     for (int c = 0; c < 3; ++c)
         for (int ky = 0; ky < 7; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 7; ++kx) {
-                const float v = patch[c][ty * 2 + ky][tx * 2 + kx];
+                const float v0 = patch[c][ty * 2 + ky][tx * 2 + kx];
+                const float v1 = patch[c][ty * 2 + 16 + ky][tx * 2 + kx];
                 const float4* w4 = reinterpret_cast<const float4*>(ws + ((c * 7 + ky) * 7 + kx) * 64 + half * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 q = w4[j];
-                    acc[4 * j] += v * q.x; acc[4 * j + 1] += v * q.y; acc[4 * j + 2] += v * q.z; acc[4 * j + 3] += v * q.w;
+                    acc0[4 * j] += v0 * q.x; acc0[4 * j + 1] += v0 * q.y; acc0[4 * j + 2] += v0 * q.z; acc0[4 * j + 3] += v0 * q.w;
+                    acc1[4 * j] += v1 * q.x; acc1[4 * j + 1] += v1 * q.y; acc1[4 * j + 2] += v1 * q.z; acc1[4 * j + 3] += v1 * q.w;
                 }
             }
-    const int oy = oy0 + ty, ox = ox0 + tx;
-    if (oy < H1 && ox < W1) {
-        float4* o = reinterpret_cast<float4*>(out + (((size_t)n * H1 + oy) * W1 + ox) * 64 + half * 32);
+    const int ox = ox0 + tx;
+    if (ox < W1) {
+        const int oya = oy0 + ty, oyb = oya + 8;
+        if (oya < H1) {
+            float4* o = reinterpret_cast<float4*>(out + (((size_t)n * H1 + oya) * W1 + ox) * 64 + half * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(acc0[4 * j], acc0[4 * j + 1], acc0[4 * j + 2], acc0[4 * j + 3]);
+        }
+        if (oyb < H1) {
+            float4* o = reinterpret_cast<float4*>(out + (((size_t)n * H1 + oyb) * W1 + ox) * 64 + half * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(acc1[4 * j], acc1[4 * j + 1], acc1[4 * j + 2], acc1[4 * j + 3]);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------- InstanceNorm statistics
-// x: [NI][P][C] fp32.  Stage 1: grid (chunks, NI); a thread owns 4 channels of every (256 / (C/4))-th pixel of its chunk and
+// x: [NI][P][C] fp32.  Grid (chunks, NI); a thread owns 4 channels of every (256 / (C/4))-th pixel of its chunk and
 // accumulates sum / sum of squares in fp64; the pixel lanes of the block are then summed in a fixed order.
+// The block that finishes an image last (ticket counter, reset for the next use) folds the partials in chunk order -- the same
+// sums whichever block that is -- into mean and 1 / sqrt(var + eps): biased variance, eps = 1e-5 (nn.InstanceNorm2d defaults).
 __global__ void __launch_bounds__(256) in_stats1_kernel(const float* __restrict__ x, int P, int C, int chunk_px,
-                                                        double* __restrict__ part /*[NI][chunks][C][2]*/) {
+                                                        double* part /*[NI][chunks][C][2]*/, int* counter /*[NI], zero*/,
+                                                        float2* __restrict__ stats /*[NI][C]*/) {
     extern __shared__ double sm[];                 // [lanes][C][2]
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int c4n = C >> 2, lanes = 256 / c4n;
@@ -162,14 +179,24 @@ __global__ void __launch_bounds__(256) in_stats1_kernel(const float* __restrict_
         double* o = part + (((size_t)n * gridDim.x + chunk) * C + c) * 2;
         o[0] = a; o[1] = b;
     }
-}
-
-// Stage 2: mean and 1 / sqrt(var + eps) per (image, channel); biased variance, eps = 1e-5 (nn.InstanceNorm2d defaults)
-__global__ void in_stats2_kernel(const double* __restrict__ part, int chunks, int P, int C, float2* __restrict__ stats /*[NI][C]*/) {
-    const int n = blockIdx.x;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(counter + n, 1);
+        is_last = (t == (int)gridDim.x - 1);
+        if (is_last) counter[n] = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int chunks = gridDim.x;
+    for (int c = threadIdx.x; c < C; c += 256) {
         double a = 0, b = 0;
-        for (int k = 0; k < chunks; ++k) { const double* o = part + (((size_t)n * chunks + k) * C + c) * 2; a += o[0]; b += o[1]; }
+        for (int k = 0; k < chunks; ++k) {
+            const double* o = part + (((size_t)n * chunks + k) * C + c) * 2;
+            a += __ldcg(o); b += __ldcg(o + 1);
+        }
         const double mean = a / P, var = fmax(b / P - mean * mean, 0.0);
         stats[(size_t)n * C + c] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
     }
@@ -238,7 +265,7 @@ __global__ void __launch_bounds__(256) enc_out_nchw_kernel(const float* __restri
 struct EncWs {
     float *r, *y, *d;            // fp32 maps: block input / residual, raw convolution output, raw down-sampling branch
     __half *xh[2], *yh[2];       // operand planes of the block input and of relu(norm1(conv1 x))
-    double* part; float2 *st_y, *st_d;
+    double* part; float2 *st_y, *st_d; int* counter;
     float* zero_bias_unused;
 };
 constexpr int IN_CHUNKS = 32;
@@ -257,6 +284,7 @@ size_t enc_ws_layout(int NI, int H, int W, void* ws, EncWs* out) {
     w.part = (double*)take((size_t)NI * IN_CHUNKS * 256 * 2 * sizeof(double));
     w.st_y = (float2*)take((size_t)NI * 256 * sizeof(float2));
     w.st_d = (float2*)take((size_t)NI * 256 * sizeof(float2));
+    w.counter = (int*)take((size_t)NI * sizeof(int));
     w.zero_bias_unused = nullptr;
     if (out) *out = w;
     return align_up(off, 1024);
@@ -266,9 +294,8 @@ int in_stats(const float* x, int NI, int P, int C, const EncWs& w, float2* stats
     const int chunk_px = ceil_div(P, IN_CHUNKS);
     const int chunks = ceil_div(P, chunk_px);
     const int lanes = 256 / (C / 4);
-    in_stats1_kernel<<<dim3((unsigned)chunks, (unsigned)NI), 256, (size_t)lanes * C * 2 * sizeof(double), s>>>(x, P, C, chunk_px, w.part);
-    B2P_LAUNCH_CHECK();
-    in_stats2_kernel<<<NI, 128, 0, s>>>(w.part, chunks, P, C, stats);
+    in_stats1_kernel<<<dim3((unsigned)chunks, (unsigned)NI), 256, (size_t)lanes * C * 2 * sizeof(double), s>>>(x, P, C, chunk_px, w.part,
+                                                                                                                 w.counter, stats);
     B2P_LAUNCH_CHECK();
     return 0;
 }
@@ -331,7 +358,10 @@ int b2p_image_encoder(const void* packed_v, const float* image1, const float* im
     const int H1 = down2(H), W1 = down2(W), H2 = down2(H1), W2 = down2(W1), H3 = down2(H2), W3 = down2(W2);
     const int P1 = H1 * W1, P2 = H2 * W2, P3 = H3 * W3;
     // conv1 + norm1 + relu (extractor.py:200-202)
-    enc_stem_kernel<<<dim3((unsigned)ceil_div(W1, ST_TW), (unsigned)ceil_div(H1, ST_TH), (unsigned)NI), 256, 0, s>>>(
+    B2P_CUDA(cudaMemsetAsync(w.counter, 0, (size_t)NI * sizeof(int), s));       // ticket counters of the statistics kernel
+    static const cudaError_t st_attr = cudaFuncSetAttribute(enc_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES);
+    B2P_CUDA(st_attr);
+    enc_stem_kernel<<<dim3((unsigned)ceil_div(W1, ST_TW), (unsigned)ceil_div(H1, ST_TH), (unsigned)NI), 256, ST_SMEM_BYTES, s>>>(
         image1, image2, B, H, W, H1, W1, packed + L.stem_w, packed + L.stem_b, w.y);
     B2P_LAUNCH_CHECK();
     if ((rc = in_stats(w.y, NI, P1, 64, w, w.st_y, s))) return rc;

@@ -22,6 +22,17 @@ __device__ __forceinline__ float ldg_ordered(const float* p) {
     return v;
 }
 
+// One channel of the descriptor similarity: s + a * (bilinear sample).  The operation sequence is pinned with intrinsics so that
+// every build of the kernel (and the list-driven one) rounds identically, whatever the compiler would contract or reorder.
+__device__ __forceinline__ float corner_dot(float s, float a, float t00, float t01, float t10, float t11, float w00, float w01,
+                                            float w10, float w11) {
+    float v = __fmul_rn(t00, w00);
+    v = __fmaf_rn(t01, w01, v);
+    v = __fmaf_rn(t10, w10, v);
+    v = __fmaf_rn(t11, w11, v);
+    return __fmaf_rn(a, v, s);
+}
+
 // Everything for one full-resolution pixel (b, Y, X): convex upsampling, target, descriptor similarity weight.
 // NPLANE: H*W when known at compile time (the plane stride of the descriptor loads becomes an immediate offset: 5 loads per
 // channel with no address arithmetic), 0 = run-time size.
@@ -115,14 +126,8 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
                     a[k] = ldg_ordered(g1p + (size_t)(c + k) * N);
                 }
 #pragma unroll
-                for (int k = 0; k < NB; ++k) {
-                    float v = 0.f;
-                    v += (k00 ? t[k][0] : 0.f) * w00;
-                    v += (k01 ? t[k][1] : 0.f) * w01;
-                    v += (k10 ? t[k][2] : 0.f) * w10;
-                    v += (k11 ? t[k][3] : 0.f) * w11;
-                    s += a[k] * v;
-                }
+                for (int k = 0; k < NB; ++k)
+                    s = corner_dot(s, a[k], k00 ? t[k][0] : 0.f, k01 ? t[k][1] : 0.f, k10 ? t[k][2] : 0.f, k11 ? t[k][3] : 0.f, w00, w01, w10, w11);
             }
         }
 #pragma unroll 8
@@ -130,12 +135,7 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
             const float* pl = g2p + (size_t)c * N;
             const float t00 = __ldg(pl + o00), t01 = __ldg(pl + o01), t10 = __ldg(pl + o10), t11 = __ldg(pl + o11);
             const float a = __ldg(g1p + (size_t)c * N);
-            float v = 0.f;
-            v += (k00 ? t00 : 0.f) * w00;
-            v += (k01 ? t01 : 0.f) * w01;
-            v += (k10 ? t10 : 0.f) * w10;
-            v += (k11 ? t11 : 0.f) * w11;
-            s += a * v;
+            s = corner_dot(s, a, k00 ? t00 : 0.f, k01 ? t01 : 0.f, k10 ? t10 : 0.f, k11 ? t11 : 0.f, w00, w01, w10, w11);
         }
         wgt = expf(-fabsf(1.f - s) / sigma);
     }
