@@ -520,7 +520,19 @@ def run_workload(args, cfg, per_gpu, rank, local_rank, world, dev, numa, want_cp
             y0 = min(int(y * sy), H - 1); rows.update((y0, min(y0 + 1, H - 1)))
         sparse_g1 = ops.get_option("sparse_g1") != 0
         g1_bytes = (int((host["depth"] > 0).sum()) * host["geofea1"].shape[1] * 4) if sparse_g1 else host["geofea1"].numel() * 4
-        other = sum(host[k].numel() * 4 for k in ("fmap1", "fmap2", "geofea2", "depth", "K", "G0")) + g1_bytes
+        g2_bytes = host["geofea2"].numel() * 4
+        if ops.get_option("sparse_g2") != 0:       # second descriptor map: only the foreground box + margin is copied (api.cu geo2_window)
+            mg = max(0, ops.get_option("g2_margin"))
+            g2_bytes = 0
+            fgm = host["depth"] > 0
+            for b in range(fgm.shape[0]):
+                ys = torch.nonzero(fgm[b].any(dim=1)).flatten(); xs = torch.nonzero(fgm[b].any(dim=0)).flatten()
+                if ys.numel() == 0:
+                    continue
+                y0, y1 = max(0, int(ys[0]) - mg), min(H, int(ys[-1]) + 1 + mg)
+                x0, x1 = max(0, int(xs[0]) - mg) & ~7, min(W, (min(W, int(xs[-1]) + 1 + mg) + 7) & ~7)
+                g2_bytes += (y1 - y0) * (x1 - x0) * host["geofea2"].shape[1] * 4
+        other = sum(host[k].numel() * 4 for k in ("fmap1", "fmap2", "depth", "K", "G0")) + g1_bytes + g2_bytes
         d2h = n_chunks * Gh.numel() * 4
         runs = []
         for threads in variants:
@@ -546,7 +558,7 @@ def run_workload(args, cfg, per_gpu, rank, local_rank, world, dev, numa, want_cp
                "steps": ke, "ms_per_step": best["ms_per_step"], "max_abs_diff_vs_device_entry": max(r["max_abs_diff_vs_device_entry"] for r in runs),
                "h2d_gbs_this_rank": best["h2d_gbs_this_rank"], "context": best["context"], "variants": runs, "host_cpus": cores,
                "host_input_bytes": n_chunks * sum(host[k].numel() * 4 for k in host), "numa": numa,
-               "note": "the context map [B,256,H,W] is never copied whole: either its needed rows are read in place from pinned host memory by the kernel, or host threads gather the 4 texels per low-res sample into a pinned staging buffer (b200pose_refine_iters_host2); the first descriptor map is read only at the pixels with depth > 0"}
+               "note": "the context map [B,256,H,W] is never copied whole: either its needed rows are read in place from pinned host memory by the kernel, or host threads gather the 4 texels per low-res sample into a pinned staging buffer (b200pose_refine_iters_host2); the first descriptor map is read only at the pixels with depth > 0, the second one is copied only inside the foreground box + margin (samples outside it are read in place; outside-window traffic is not counted)"}
         del scratch
     else:
         del ws

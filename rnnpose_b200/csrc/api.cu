@@ -670,11 +670,35 @@ int b200pose_refine_launch_count(int B, int H, int W, int n_iters, int n_lm) {
     return per_call + n_iters * per_iter;
 }
 
+}  // extern "C"
+
+// g2_far / g2_window (host entry only): geofea2 holds valid data only inside the per-sample window [B][4] = (y0, y1, x0, x1);
+// samples outside it are read from g2_far, the same map in mapped host memory (upsample_weight_pixel<WINDOW>).
+static int refine_iters_impl(const void* packed_weights, const float* fmap1, const float* fmap2, const float* context,
+                             const float* geofea1, const float* geofea2, const float* depth, const float* K, float* G,
+                             float sigma, int B, int C_geo, int H, int W, int n_iters, int n_lm, double ep_lmbda,
+                             double lm_lmbda, int flags, float* flow_first, float* flow_last, float* weight_last,
+                             void* workspace, size_t workspace_bytes, void* stream, const float* g2_far, const int* g2_window);
+
+extern "C" {
+
 int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const float* fmap2, const float* context,
                           const float* geofea1, const float* geofea2, const float* depth, const float* K, float* G,
                           float sigma, int B, int C_geo, int H, int W, int n_iters, int n_lm, double ep_lmbda,
                           double lm_lmbda, int flags, float* flow_first, float* flow_last, float* weight_last,
                           void* workspace, size_t workspace_bytes, void* stream) {
+    return refine_iters_impl(packed_weights, fmap1, fmap2, context, geofea1, geofea2, depth, K, G, sigma, B, C_geo, H, W, n_iters,
+                             n_lm, ep_lmbda, lm_lmbda, flags, flow_first, flow_last, weight_last, workspace, workspace_bytes, stream,
+                             nullptr, nullptr);
+}
+
+}  // extern "C"
+
+static int refine_iters_impl(const void* packed_weights, const float* fmap1, const float* fmap2, const float* context,
+                             const float* geofea1, const float* geofea2, const float* depth, const float* K, float* G,
+                             float sigma, int B, int C_geo, int H, int W, int n_iters, int n_lm, double ep_lmbda,
+                             double lm_lmbda, int flags, float* flow_first, float* flow_last, float* weight_last,
+                             void* workspace, size_t workspace_bytes, void* stream, const float* g2_far, const int* g2_window) {
     if (!packed_weights || !fmap1 || !fmap2 || !context || !geofea1 || !geofea2 || !depth || !K || !G || !workspace)
         return B200POSE_E_NULL;
     if (!shape_ok(B, H, W) || C_geo < 1) return B200POSE_E_SHAPE;
@@ -709,9 +733,11 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
     // option fg_pipeline: 0 off, 1 on, 2 (default) only when geofea2 arrives channels-last (zoom-crop output): with NCHW input the
     // two transposes (140 us per call at B=32) outweigh the 16 us per iteration the pipeline saves (profiles/r2d)
     const int pipe_opt = b2p_options().fg_pipeline;
-    const bool use_pipe = use_fg && C_geo == 32 && (pipe_opt == 1 || (pipe_opt == 2 && g2_cl));
+    const bool windowed = g2_far != nullptr && g2_window != nullptr;      // only the dense kernel knows the window
+    if (windowed && g2_cl) return B200POSE_E_ARG;
+    const bool use_pipe = !windowed && use_fg && C_geo == 32 && (pipe_opt == 1 || (pipe_opt == 2 && g2_cl));
     if (g2_cl && !use_pipe) return B200POSE_E_ARG;          // only the pipeline reads channels-last descriptors
-    const bool fg_up = use_fg && !use_pipe && fg_upsample_enabled();
+    const bool fg_up = !windowed && use_fg && !use_pipe && fg_upsample_enabled();
     if (use_fg && (rc = b2p_fg_build(depth, B, H, W, r.fg, fg_up ? r.target : nullptr, fg_up ? r.weight : nullptr, s))) return rc;
     if (use_pipe && (rc = b2p_fgpipe_prepare(geofea1, geofea2, g2_cl ? 1 : 0, B, H, W, r.fg, r.fgp, s))) return rc;
     const int* fg_idx = use_fg ? b2p_fg_idx(r.fg) : nullptr;
@@ -739,7 +765,7 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
             if ((rc = b2p_upsample_weight_fg(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, r.fg, r.target, r.weight, s)))
                 return rc;
         } else if ((rc = b2p_upsample_weight(r.flow, r.mask, geofea1, geofea2, depth, sigma, B, C_geo, H, W, fu, r.target,
-                                             r.weight, 1, s))) return rc;
+                                             r.weight, 1, s, g2_far, g2_window))) return rc;
         if (it == 0 && it == n_iters - 1 && flow_first && flow_last)
             B2P_CUDA(cudaMemcpyAsync(flow_last, flow_first, (size_t)B * 2 * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
         if (use_pipe) {
@@ -753,14 +779,13 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
     return 0;
 }
 
-}  // extern "C"
-
 namespace {
 // Device staging of the host entry.  The batch is processed in sub-batches so that the PCIe transfer of sub-batch
 // k+1 (on an internal copy stream) overlaps the kernels of sub-batch k (on the caller's stream); per-sample results
 // do not depend on how the batch is split (tests/test_gpu_refine.py checks this bit for bit).
 struct HostStage {
     float *fmap1, *fmap2, *context, *geo1, *geo2, *depth, *K, *G;
+    int* win;                 // [bs][4] geofea2 window per sample (y0, y1, x0, x1)
 };
 struct HostScratch {
     HostStage st[2];          // ping-pong input staging for sub-batches
@@ -830,6 +855,29 @@ struct TexelGather {
     }
 };
 
+// The second descriptor map is only sampled at flow targets of foreground pixels: the box of depth > 0 plus a margin, columns
+// rounded to 32-byte groups.  Anything sampled outside is fetched from the mapped host buffer by the kernel, so the margin is a
+// performance knob, not a correctness one.
+void geo2_window(const float* depth, int H, int W, int margin, int* win /*y0,y1,x0,x1*/) {
+    std::vector<float> colmax((size_t)W, 0.f);
+    int y0 = H, y1 = -1;
+    for (int y = 0; y < H; ++y) {
+        const float* row = depth + (size_t)y * W;
+        float m = 0.f;
+        for (int x = 0; x < W; ++x) { const float v = row[x]; m = v > m ? v : m; colmax[x] = v > colmax[x] ? v : colmax[x]; }
+        if (m > 0.f) { if (y < y0) y0 = y; y1 = y; }
+    }
+    if (y1 < 0) { win[0] = win[1] = win[2] = win[3] = 0; return; }
+    int x0 = 0, x1 = W - 1;
+    while (x0 < W && !(colmax[x0] > 0.f)) ++x0;
+    while (x1 > x0 && !(colmax[x1] > 0.f)) --x1;
+    win[0] = y0 - margin > 0 ? y0 - margin : 0;
+    win[1] = y1 + 1 + margin < H ? y1 + 1 + margin : H;
+    const int a = x0 - margin > 0 ? x0 - margin : 0, b = x1 + 1 + margin < W ? x1 + 1 + margin : W;
+    win[2] = a & ~7;
+    win[3] = ((b + 7) & ~7) < W ? ((b + 7) & ~7) : W;
+}
+
 inline int host_sub_batch(int B) { return B >= 8 ? (B + 3) / 4 : (B >= 2 ? (B + 1) / 2 : 1); }
 
 // stage_context: 0 = read in place from mapped host memory, 1 = full map, 2 = the four texels per low-res sample
@@ -850,6 +898,7 @@ size_t host_scratch_layout(int B, int C, int H, int W, int stage_context, void* 
         st.depth = c.take<float>((size_t)bs * H * W);
         st.K = c.take<float>((size_t)bs * 9);
         st.G = c.take<float>((size_t)bs * 16);
+        st.win = c.take<int>((size_t)bs * 4);
     }
     hs.ws_bytes = refine_ws_layout(bs, H, W, nullptr, 0, nullptr);
     hs.ws = c.take<char>(hs.ws_bytes);
@@ -933,6 +982,19 @@ int b200pose_refine_iters_host2(const void* packed_weights, const float* fmap1_h
         else
             (void)cudaGetLastError();
     }
+    // ... and the second one only inside the box its samples can fall into (geo2_window); the rest stays reachable through
+    // the mapped pointer (option sparse_g2 = 0, or a pageable buffer: plain copy).
+    const float* g2_mapped = nullptr;
+    {
+        cudaPointerAttributes attr;
+        if (b2p_options().sparse_g2 != 0 && cudaPointerGetAttributes(&attr, geofea2_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            attr.devicePointer != nullptr)
+            g2_mapped = reinterpret_cast<const float*>(attr.devicePointer);
+        else
+            (void)cudaGetLastError();
+    }
+    std::vector<int> win_host(g2_mapped ? (size_t)B * 4 : 0);
+    const int g2_margin = b2p_options().g2_margin < 0 ? 0 : b2p_options().g2_margin;
     HostScratch hs;
     host_scratch_layout(B, C_geo, H, W, gather ? 2 : (ctx_mapped == nullptr ? 1 : 0), device_scratch, device_scratch_bytes, &hs);
     const int h = H / 8, w = W / 8, bs = hs.bs;
@@ -970,7 +1032,24 @@ int b200pose_refine_iters_host2(const void* packed_weights, const float* fmap1_h
         } else {
             B2P_TRY(cudaMemcpyAsync(st.geo1, geofea1_host + (size_t)b0 * C_geo * H * W, (size_t)nb * C_geo * H * W * f, cudaMemcpyHostToDevice, cs));
         }
-        B2P_TRY(cudaMemcpyAsync(st.geo2, geofea2_host + (size_t)b0 * C_geo * H * W, (size_t)nb * C_geo * H * W * f, cudaMemcpyHostToDevice, cs));
+        if (g2_mapped) {
+            for (int i = 0; i < nb; ++i) {
+                int* wn = &win_host[(size_t)(b0 + i) * 4];
+                geo2_window(depth_host + (size_t)(b0 + i) * H * W, H, W, g2_margin, wn);
+                if (wn[1] <= wn[0] || wn[3] <= wn[2]) continue;
+                cudaMemcpy3DParms cp;
+                memset(&cp, 0, sizeof(cp));
+                cp.srcPtr = make_cudaPitchedPtr(const_cast<float*>(geofea2_host + (size_t)(b0 + i) * C_geo * H * W), (size_t)W * f, W, H);
+                cp.dstPtr = make_cudaPitchedPtr(st.geo2 + (size_t)i * C_geo * H * W, (size_t)W * f, W, H);
+                cp.srcPos = cp.dstPos = make_cudaPos((size_t)wn[2] * f, wn[0], 0);
+                cp.extent = make_cudaExtent((size_t)(wn[3] - wn[2]) * f, wn[1] - wn[0], C_geo);
+                cp.kind = cudaMemcpyHostToDevice;
+                B2P_TRY(cudaMemcpy3DAsync(&cp, cs));
+            }
+            B2P_TRY(cudaMemcpyAsync(st.win, &win_host[(size_t)b0 * 4], (size_t)nb * 4 * sizeof(int), cudaMemcpyHostToDevice, cs));
+        } else {
+            B2P_TRY(cudaMemcpyAsync(st.geo2, geofea2_host + (size_t)b0 * C_geo * H * W, (size_t)nb * C_geo * H * W * f, cudaMemcpyHostToDevice, cs));
+        }
         B2P_TRY(cudaMemcpyAsync(st.K, K_host + (size_t)b0 * 9, (size_t)nb * 9 * f, cudaMemcpyHostToDevice, cs));
         B2P_TRY(cudaMemcpyAsync(st.G, G_host + (size_t)b0 * 16, (size_t)nb * 16 * f, cudaMemcpyHostToDevice, cs));
         if (gather) {                               // the workers ran ahead while the copies above were queued / in flight
@@ -981,9 +1060,10 @@ int b200pose_refine_iters_host2(const void* packed_weights, const float* fmap1_h
         B2P_TRY(cudaEventRecord(ev_copy[k & 1], cs));
         B2P_TRY(cudaStreamWaitEvent(s, ev_copy[k & 1], 0));
         const float* ctx = ctx_mapped ? ctx_mapped + (size_t)b0 * 256 * H * W : st.context;
-        rc = b200pose_refine_iters(packed_weights, st.fmap1, st.fmap2, ctx, st.geo1, st.geo2, st.depth, st.K, st.G, sigma, nb,
-                                   C_geo, H, W, n_iters, n_lm, ep_lmbda, lm_lmbda, loop_flags, nullptr, nullptr, nullptr, hs.ws,
-                                   hs.ws_bytes, stream);
+        rc = refine_iters_impl(packed_weights, st.fmap1, st.fmap2, ctx, st.geo1, st.geo2, st.depth, st.K, st.G, sigma, nb,
+                               C_geo, H, W, n_iters, n_lm, ep_lmbda, lm_lmbda, loop_flags, nullptr, nullptr, nullptr, hs.ws,
+                               hs.ws_bytes, stream, g2_mapped ? g2_mapped + (size_t)b0 * C_geo * H * W : nullptr,
+                               g2_mapped ? st.win : nullptr);
         if (rc) goto cleanup;
         B2P_TRY(cudaMemcpyAsync(G_host + (size_t)b0 * 16, st.G, (size_t)nb * 16 * f, cudaMemcpyDeviceToHost, s));
         B2P_TRY(cudaEventRecord(ev_done[k & 1], s));

@@ -42,7 +42,7 @@ inline cudaError_t b2p_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 // into the library, changed afterwards only through b200pose_set_option.
 struct B2POptions {
     int conv_mode, fg_list, fg_pipeline, fg_upsample, sparse_g1, fg_blocks, tail_min_n, conv_debug, lookup_mode, pool_mode,
-        lm_debug, chain_rings, chain_dynamic, chain_xmajor, lm_cluster, chain_merge, upsample_variant, host_gather;
+        lm_debug, chain_rings, chain_dynamic, chain_xmajor, lm_cluster, chain_merge, upsample_variant, host_gather, sparse_g2, g2_margin;
 };
 B2POptions& b2p_options();
 
@@ -200,7 +200,7 @@ int b2p_flow_head2(const float* hm /*[P][512] fp32, first 256 = flow-head featur
                    int B, int h, int w, cudaStream_t s);
 int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth,
                         float sigma, int B, int C, int H, int W, float* flow_up, float* target, float* weight,
-                        int lazy_background, cudaStream_t s);
+                        int lazy_background, cudaStream_t s, const float* g2_far = nullptr, const int* g2_window = nullptr);
 // foreground list (depth > 0 or non-finite) of a call, built once; see upsample_weight.cu
 size_t b2p_fg_ws_bytes(int B, int H, int W);
 int b2p_fg_build(const float* depth, int B, int H, int W, void* fg_ws, float* target, float* weight, cudaStream_t s);

@@ -32,6 +32,11 @@ const OptDesc kOpts[] = {
     {"chain_merge", "B200POSE_CHAIN_MERGE", &B2POptions::chain_merge, 0},     // chained launch: interleave C1|F1 and MASK2|flow head units (measured: no gain)
     {"upsample_variant", "B200POSE_UPSAMPLE_VARIANT", &B2POptions::upsample_variant, 3},   // dense upsample+weight kernel build, see b2p_upsample_weight
     {"host_gather", "B200POSE_HOST_GATHER", &B2POptions::host_gather, 1},     // host texel gather: bit 0 software prefetch of the next rows, bit 1 plain (not streaming) stores
+    // host entry: copy geofea2 only inside the foreground box + g2_margin, the rest is read from mapped host memory on demand.
+    // Measured (profiles/r2r): +12 % end to end when the flows stay inside the margin, neutral on the bench scenes (their flows
+    // do not); off by default because a diverged refinement would pull more over PCIe sector by sector than the copy it saves.
+    {"sparse_g2", "B200POSE_SPARSE_G2", &B2POptions::sparse_g2, 0},
+    {"g2_margin", "B200POSE_G2_MARGIN", &B2POptions::g2_margin, 24},
     {"chain_dynamic", "B200POSE_CHAIN_DYNAMIC", &B2POptions::chain_dynamic, 0},   // chained launch: units from a global queue (1) or static round robin (0)
 };
 constexpr int kNumOpts = (int)(sizeof(kOpts) / sizeof(kOpts[0]));

@@ -38,12 +38,15 @@ __device__ __forceinline__ float corner_dot(float s, float a, float t00, float t
 // channel with no address arithmetic), 0 = run-time size.
 // BATCH: 0 = one loop over the channels (the compiler picks the load schedule), 8 / 16 = channels are loaded BATCH at a time into
 // registers before any of them is used (5 * BATCH independent loads in flight per thread).
-template <int NPLANE = 0, int BATCH = 0>
+// WINDOW: g2 holds valid data only inside the per-sample window win[b] = (y0, y1, x0, x1) (what the host entry copied over PCIe:
+// the foreground box plus a margin); a corner that is sampled outside it is read from g2_far, the same map in mapped host memory.
+template <int NPLANE = 0, int BATCH = 0, bool WINDOW = false>
 __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ flow, const float* __restrict__ mask,
                                                       const float* __restrict__ g1, const float* __restrict__ g2,
                                                       const float* __restrict__ depth, float sigma, int b, int Y, int X, int C, int H,
                                                       int W, float* __restrict__ flow_up, float* __restrict__ target,
-                                                      float* __restrict__ weight) {
+                                                      float* __restrict__ weight, const float* __restrict__ g2_far = nullptr,
+                                                      const int* __restrict__ win = nullptr) {
     const int h = H >> 3, w = W >> 3;
     const size_t N = NPLANE ? (size_t)NPLANE : (size_t)H * W;
     const int r = Y * W + X;
@@ -114,6 +117,19 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
         float s = 0.f;
         const float* g1p = g1 + (size_t)b * C * N + r;
         const float* g2p = g2 + (size_t)b * C * N;
+        // per-corner plane-0 addresses; the channel loop only adds c * N
+        const float *q00 = g2p + o00, *q01 = g2p + o01, *q10 = g2p + o10, *q11 = g2p + o11;
+        if (WINDOW) {
+            const int4 wn = __ldg(reinterpret_cast<const int4*>(win) + b);
+            const float* far = g2_far + (size_t)b * C * N;
+            const bool ra = yc0 >= wn.x && yc0 < wn.y, rb = yc1 >= wn.x && yc1 < wn.y;
+            const bool ca = xc0 >= wn.z && xc0 < wn.w, cb = xc1 >= wn.z && xc1 < wn.w;
+            // a corner the reference would not sample is discarded by a select below: leave it on the device buffer
+            if (k00 && !(ra && ca)) q00 = far + o00;
+            if (k01 && !(ra && cb)) q01 = far + o01;
+            if (k10 && !(rb && ca)) q10 = far + o10;
+            if (k11 && !(rb && cb)) q11 = far + o11;
+        }
         int c = 0;
         if (BATCH > 0) {
             constexpr int NB = BATCH > 0 ? BATCH : 1;
@@ -121,9 +137,9 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
                 float t[NB][4], a[NB];
 #pragma unroll
                 for (int k = 0; k < NB; ++k) {
-                    const float* pl = g2p + (size_t)(c + k) * N;
-                    t[k][0] = ldg_ordered(pl + o00); t[k][1] = ldg_ordered(pl + o01); t[k][2] = ldg_ordered(pl + o10); t[k][3] = ldg_ordered(pl + o11);
-                    a[k] = ldg_ordered(g1p + (size_t)(c + k) * N);
+                    const size_t co = (size_t)(c + k) * N;
+                    t[k][0] = ldg_ordered(q00 + co); t[k][1] = ldg_ordered(q01 + co); t[k][2] = ldg_ordered(q10 + co); t[k][3] = ldg_ordered(q11 + co);
+                    a[k] = ldg_ordered(g1p + co);
                 }
 #pragma unroll
                 for (int k = 0; k < NB; ++k)
@@ -132,9 +148,9 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
         }
 #pragma unroll 8
         for (; c < C; ++c) {
-            const float* pl = g2p + (size_t)c * N;
-            const float t00 = __ldg(pl + o00), t01 = __ldg(pl + o01), t10 = __ldg(pl + o10), t11 = __ldg(pl + o11);
-            const float a = __ldg(g1p + (size_t)c * N);
+            const size_t co = (size_t)c * N;
+            const float t00 = __ldg(q00 + co), t01 = __ldg(q01 + co), t10 = __ldg(q10 + co), t11 = __ldg(q11 + co);
+            const float a = __ldg(g1p + co);
             s = corner_dot(s, a, k00 ? t00 : 0.f, k01 ? t01 : 0.f, k10 ? t10 : 0.f, k11 ? t11 : 0.f, w00, w01, w10, w11);
         }
         wgt = expf(-fabsf(1.f - s) / sigma);
@@ -142,11 +158,12 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
     weight[idx] = wgt;
 }
 
-template <int NPLANE, int BATCH>
+template <int NPLANE, int BATCH, bool WINDOW = false>
 __global__ void __launch_bounds__(64) upsample_weight_kernel(
     const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1,
     const float* __restrict__ g2, const float* __restrict__ depth, float sigma, int B, int C, int H, int W,
-    float* __restrict__ flow_up, float* __restrict__ target, float* __restrict__ weight, int lazy_background) {
+    float* __restrict__ flow_up, float* __restrict__ target, float* __restrict__ weight, int lazy_background,
+    const float* __restrict__ g2_far, const int* __restrict__ win) {
     pdl_trigger();
     pdl_wait();
     const size_t N = NPLANE ? (size_t)NPLANE : (size_t)H * W;
@@ -163,7 +180,7 @@ __global__ void __launch_bounds__(64) upsample_weight_kernel(
         if (weight) weight[idx] = 0.f;
         return;
     }
-    upsample_weight_pixel<NPLANE, BATCH>(flow, mask, g1, g2, depth, sigma, b, Y, X, C, H, W, flow_up, target, weight);
+    upsample_weight_pixel<NPLANE, BATCH, WINDOW>(flow, mask, g1, g2, depth, sigma, b, Y, X, C, H, W, flow_up, target, weight, g2_far, win);
 }
 
 // ------------------------------------------------------------------------------------------------ foreground list
@@ -298,7 +315,7 @@ __global__ void __launch_bounds__(256) gather_fg_planes_kernel(const float* __re
 
 int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, const float* g2, const float* depth,
                         float sigma, int B, int C, int H, int W, float* flow_up, float* target, float* weight,
-                        int lazy_background, cudaStream_t s) {
+                        int lazy_background, cudaStream_t s, const float* g2_far, const int* g2_window) {
     const size_t total = (size_t)B * H * W;
     const dim3 grid((unsigned)((total + 63) / 64));
     // upsample_variant (A/B): 0 run-time plane size, compiler-scheduled loads; 1 / 2 / 3 the reference's crop size (ZOOM_CROP_SIZE
@@ -307,8 +324,12 @@ int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, c
     // other crop sizes run variant 0
     const int var = b2p_options().upsample_variant;
     const bool cs = H * W == 240 * 320;
-#define UPW_LAUNCH(NP, BT) B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel<NP, BT>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up, target, weight, lazy_background))
-    if (var == 1 && cs) UPW_LAUNCH(240 * 320, 0);
+#define UPW_LAUNCH(NP, BT) B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel<NP, BT>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up, target, weight, lazy_background, (const float*)nullptr, (const int*)nullptr))
+#define UPW_LAUNCH_WIN(NP, BT) B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel<NP, BT, true>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up, target, weight, lazy_background, g2_far, g2_window))
+    if (g2_far && g2_window && g2) {            // host entry: geofea2 is only valid inside a per-sample window
+        if (var != 0 && cs) UPW_LAUNCH_WIN(240 * 320, 16);
+        else UPW_LAUNCH_WIN(0, 0);
+    } else if (var == 1 && cs) UPW_LAUNCH(240 * 320, 0);
     else if (var == 2 && cs) UPW_LAUNCH(240 * 320, 8);
     else if (var == 3 && cs) UPW_LAUNCH(240 * 320, 16);
     else if (var == 5 && cs) UPW_LAUNCH(240 * 320, 32);
@@ -316,6 +337,7 @@ int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, c
     else if (var == 4) UPW_LAUNCH(0, 8);
     else UPW_LAUNCH(0, 0);
 #undef UPW_LAUNCH
+#undef UPW_LAUNCH_WIN
     B2P_LAUNCH_CHECK();
     return 0;
 }

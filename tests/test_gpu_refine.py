@@ -173,6 +173,37 @@ def test_refine_host_entry_with_gathered_context_texels(ops, packed, B, threads)
     assert torch.equal(Gt, Gd)
 
 
+@pytest.mark.parametrize("margin", [0, 8, 24])
+def test_refine_host_entry_windowed_second_descriptor_map(ops, packed, libopt, margin):
+    """Pinned host buffers: the second descriptor map is copied only inside the foreground box + margin; samples outside it come
+    from the mapped host buffer (upsample_weight_pixel<WINDOW>).  Margin 0 with a perturbed initial pose sends many samples
+    outside the copied box.  Bit-identical to the device entry, and to the plain copy (sparse_g2 = 0)."""
+    H, W, B = 128, 160, 5
+    idxs = list(range(40, 40 + B))
+    mb = S.make_batch(idxs, H, W, with_images=False)
+    f1 = S.hash_features((B, 256, H // 8, W // 8), 87); f2 = S.hash_features((B, 256, H // 8, W // 8), 88)
+    G0 = torch.eye(4)[None].repeat(B, 1, 1)
+    G0[:, 0, 3] = 0.03; G0[:, 1, 3] = -0.02                               # a few centimetres: flows of tens of pixels
+    Gd = run_gpu(ops, packed, f1, f2, mb, G0, 3, 2)["G"].cpu()
+    pin = {k: mb[k].contiguous().pin_memory() for k in ("context", "geofea1", "geofea2", "K")}
+    depth = mb["depth"][:, 0].contiguous().pin_memory()
+    f1p, f2p = f1.pin_memory(), f2.pin_memory()
+    staging = ops.host_staging(B, H, W)
+    libopt("g2_margin", margin)
+    for sparse in (1, 0):
+        libopt("sparse_g2", sparse)
+        Gh = G0.clone().pin_memory()
+        _, scratch = ops.refine_iters_host(packed, f1p, f2p, pin["context"], pin["geofea1"], pin["geofea2"], depth, pin["K"], Gh, 1.0, 3, 2,
+                                           staging=staging, threads=2)
+        assert torch.equal(Gh, Gd), f"sparse_g2={sparse}"
+        # poison the device staging area: whatever the next call does not copy must not be read
+        scratch.fill_(255)
+        Gh2 = G0.clone().pin_memory()
+        ops.refine_iters_host(packed, f1p, f2p, pin["context"], pin["geofea1"], pin["geofea2"], depth, pin["K"], Gh2, 1.0, 3, 2,
+                              scratch=scratch, staging=staging, threads=2)
+        assert torch.equal(Gh2, Gd), f"sparse_g2={sparse} after poisoning the staging buffers"
+
+
 def test_refine_iters_cuda_graph_capture(ops, packed):
     """b200pose_refine_iters is stream-ordered and allocation-free: captured into a CUDA graph (PDL and cluster launches
     included) and replayed, it reproduces the eager result bit for bit, also after the inputs change in place."""
