@@ -42,7 +42,7 @@ inline cudaError_t b2p_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 // into the library, changed afterwards only through b200pose_set_option.
 struct B2POptions {
     int conv_mode, fg_list, fg_pipeline, fg_upsample, sparse_g1, fg_blocks, tail_min_n, conv_debug, lookup_mode, pool_mode,
-        lm_debug, chain_rings, chain_dynamic, chain_xmajor, lm_cluster, chain_merge, upsample_variant, host_gather, sparse_g2, g2_margin;
+        lm_debug, chain_rings, chain_dynamic, chain_xmajor, lm_cluster, chain_merge, upsample_variant, host_gather, sparse_g2, g2_margin, enc_chunk, enc_stem;
 };
 B2POptions& b2p_options();
 

@@ -6,7 +6,7 @@
 //   ResidualBlock: y = relu(norm1(conv1 x)); y = relu(norm2(conv2 y)); x = downsample(x) if any; out = relu(x + y).
 //   InstanceNorm2d defaults: no affine parameters, biased variance, eps = 1e-5.
 // The reference runs this under fp16 autocast on its GPU path and in fp32 on CPU; the oracle is the CPU fp32 result (SURVEY
-// Appendix D10).  Here: the 7x7 stem as an exact fp32 FFMA kernel (Cin = 3 does not fill a tensor-core K chunk), the fifteen
+// Appendix D10).  Here: the 7x7 stem re-indexed into a 4x1 convolution of gathered channels (enc_stem_im2col_kernel; or an exact fp32 FFMA kernel), the fifteen
 // other convolutions on tcgen05 with fp16 hi/lo split operands (conv_umma.cu; stride 2 through the TMA box's element strides),
 // InstanceNorm as a deterministic two-stage fp64 reduction + one fused normalise / ReLU / residual / operand-split pass.
 #include "common.cuh"
@@ -43,6 +43,10 @@ const EncLayout& enc_layout() {
         l.stem_w = off; off += 147 * 64;
         l.stem_b = off; off += 64;
         size_t h = 0;
+        // the stem as a tensor-core layer (enc_stem_im2col_kernel): 4 vertical taps x 64 (48 used) gathered channels -> 64
+        l.cin_pad[0] = 64; l.n_tile[0] = 64; l.cout_pad[0] = 64; l.bias[0] = l.stem_b;
+        l.hi[0] = h; h += 4 * 64 * 64;
+        l.lo[0] = h; h += 4 * 64 * 64;
         for (int i = 1; i < EC_COUNT; ++i) {
             l.cin_pad[i] = (kEnc[i].cin + 63) / 64 * 64;
             l.n_tile[i] = kEnc[i].cout == 256 ? 128 : kEnc[i].cout;       // 64, 96, 128 (pairs load 256-row tiles for conv2)
@@ -68,6 +72,93 @@ __global__ void enc_pack_stem_kernel(const float* __restrict__ w /*[64][3][7][7]
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 64 * 147) { const int n = i / 147, k = i - n * 147; dw[k * 64 + n] = w[i]; }
     if (i < 64) db[i] = b[i];
+}
+
+// The stem on the tensor cores.  A 7x7 stride-2 convolution of 3 channels is a 4x4 stride-1 convolution of the 2x2 pixel-unshuffled
+// image (12 channels; input row 2 oy + ky - 3 = 2 (oy + t - 2) + py with t = 0..3, py = 0,1, ky = 2 t - 1 + py, and ky = -1 gets a
+// zero weight).  The four horizontal taps are gathered into the channel dimension by enc_stem_im2col_kernel, so the engine sees a
+// 4x1 convolution of 64 (48 used) channels: channel = j*12 + py*6 + px*3 + c, j = horizontal tap.  K = 256 instead of 147.
+__device__ __forceinline__ void stem_channel(int ch, int& j, int& py, int& px, int& c) {
+    j = ch / 12; const int r = ch - j * 12; py = r / 6; px = (r - py * 6) / 3; c = r % 3;
+}
+
+__global__ void enc_pack_stem_tc_kernel(const float* __restrict__ w /*[64][3][7][7]*/, __half* __restrict__ hi, __half* __restrict__ lo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // [tap t][n][ch]
+    if (i >= 4 * 64 * 64) return;
+    const int ch = i & 63, n = (i >> 6) & 63, t = i >> 12;
+    float v = 0.f;
+    if (ch < 48) {
+        int j, py, px, c;
+        stem_channel(ch, j, py, px, c);
+        const int ky = 2 * t - 1 + py, kx = 2 * j - 1 + px;
+        if (ky >= 0 && ky < 7 && kx >= 0 && kx < 7) v = w[((n * 3 + c) * 7 + ky) * 7 + kx];
+    }
+    b2p_split_half(v, hi[i], lo[i]);
+}
+
+// images [B][3][H][W] x 2 -> operand planes [NI][H/2][W/2][64]: normalised 2 (x / 255) - 1 (CFNet.py:42-43), zero outside the image
+// (the convolution pads the NORMALISED image) and in the 16 pad channels.  One thread per output pixel: for each (py, colour) the
+// eight consecutive image columns 2 (ox - 2) .. 2 (ox + 1) + 1 are the (j, px) pairs in order, so every index below is a
+// compile-time constant.  The 2 x 128 bytes of a pixel go through shared memory (16-byte chunks XOR-swizzled by the pixel
+// index) so that the block's global stores are linear.
+constexpr int SI_PIX = 128;
+
+__global__ void __launch_bounds__(SI_PIX) enc_stem_im2col_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int B, int H,
+                                                                 int W, int H1, int W1, size_t total_px, __half* __restrict__ hi,
+                                                                 __half* __restrict__ lo) {
+    __shared__ uint4 sh[2][SI_PIX * 8];
+    const size_t pix0 = (size_t)blockIdx.x * SI_PIX;
+    const size_t pix = pix0 + threadIdx.x;
+    if (pix < total_px) {
+        const int ox = (int)(pix % W1);
+        const size_t t = pix / W1;
+        const int qy = (int)(t % H1), n = (int)(t / H1);
+        const float* img = (n < B ? img1 + (size_t)n * 3 * H * W : img2 + (size_t)(n - B) * 3 * H * W);
+        const int ix0 = 2 * (ox - 2);
+        __half vh[64], vl[64];
+#pragma unroll
+        for (int ch = 48; ch < 64; ++ch) { vh[ch] = __float2half_rn(0.f); vl[ch] = __float2half_rn(0.f); }
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* row = img + ((size_t)c * H + (2 * qy + py)) * W;        // 2 qy + py < H always (H even)
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {                                       // k = 2 j + px; ix0 is even: aligned pairs
+                    const int ix = ix0 + k;
+                    float2 v = make_float2(0.f, 0.f);
+                    if (ix >= 0 && ix + 1 < W) {
+                        v = __ldg(reinterpret_cast<const float2*>(row + ix));
+                        v.x = 2.f * (v.x / 255.f) - 1.f; v.y = 2.f * (v.y / 255.f) - 1.f;
+                    }
+                    const int j = k >> 1;
+                    b2p_split_half(v.x, vh[j * 12 + py * 6 + c], vl[j * 12 + py * 6 + c]);
+                    b2p_split_half(v.y, vh[j * 12 + py * 6 + 3 + c], vl[j * 12 + py * 6 + 3 + c]);
+                }
+            }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t a[4], b[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                a[e] = (uint32_t)__half_as_ushort(vh[k * 8 + 2 * e]) | ((uint32_t)__half_as_ushort(vh[k * 8 + 2 * e + 1]) << 16);
+                b[e] = (uint32_t)__half_as_ushort(vl[k * 8 + 2 * e]) | ((uint32_t)__half_as_ushort(vl[k * 8 + 2 * e + 1]) << 16);
+            }
+            const int slot = threadIdx.x * 8 + (k ^ (threadIdx.x & 7));
+            sh[0][slot] = make_uint4(a[0], a[1], a[2], a[3]);
+            sh[1][slot] = make_uint4(b[0], b[1], b[2], b[3]);
+        }
+    }
+    __syncthreads();
+    const size_t left = total_px - pix0 < (size_t)SI_PIX ? total_px - pix0 : (size_t)SI_PIX;
+    uint4* oh = reinterpret_cast<uint4*>(hi) + pix0 * 8;
+    uint4* ol = reinterpret_cast<uint4*>(lo) + pix0 * 8;
+    for (int i = threadIdx.x; i < (int)left * 8; i += SI_PIX) {
+        const int p = i >> 3, k = i & 7;
+        const int slot = p * 8 + (k ^ (p & 7));
+        oh[i] = sh[0][slot];
+        ol[i] = sh[1][slot];
+    }
 }
 
 // dst[tap][n][c] = split(src[n][c][ky][kx]), rows of cin_pad halves (K-major); bias copied to its padded slot
@@ -314,11 +405,13 @@ int enc_conv(const float* packed, int id, __half* const* in, int NI, int in_h, i
     const __half* hbase = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(packed) + enc_half_offset_bytes());
     UmmaConvArgs a;
     memset(&a, 0, sizeof(a));
-    a.seg_hi[0] = in[0]; a.seg_lo[0] = in[1]; a.seg_c[0] = kEnc[id].cin; a.seg_pitch[0] = kEnc[id].cin;
+    const bool stem = id == EC_STEM;                      // the gathered 4x1 form, see enc_stem_im2col_kernel
+    a.seg_hi[0] = in[0]; a.seg_lo[0] = in[1]; a.seg_c[0] = stem ? 64 : kEnc[id].cin; a.seg_pitch[0] = stem ? 64 : kEnc[id].cin;
     a.w_hi = hbase + L.hi[id]; a.w_lo = hbase + L.lo[id]; a.bias = packed + L.bias[id];
     a.cin_pad = L.cin_pad[id]; a.cout_pad = L.cout_pad[id]; a.cout = kEnc[id].cout; a.n_tile = L.n_tile[id];
     a.kh = a.kw = kEnc[id].k;
     a.B = NI; a.h = h; a.w = w; a.stride = kEnc[id].stride; a.in_h = in_h; a.in_w = in_w;
+    if (stem) { a.kh = 4; a.kw = 1; a.stride = 1; }
     a.epi = EPI_SCALE; a.scale = 1.f; a.out_f32 = out; a.out_f32_pitch = kEnc[id].cout;
     a.layer_id = -1;
     return b2p_launch_conv_umma(a, s);
@@ -335,6 +428,8 @@ int b2p_encoder_pack(const float* const* t /*32 device pointers, state-dict orde
     B2P_CUDA(cudaMemsetAsync(packed, 0, b2p_encoder_packed_bytes(), s));
     enc_pack_stem_kernel<<<ceil_div(64 * 147, 256), 256, 0, s>>>(t[0], t[1], f + L.stem_w, f + L.stem_b);
     B2P_LAUNCH_CHECK();
+    enc_pack_stem_tc_kernel<<<ceil_div(4 * 64 * 64, 256), 256, 0, s>>>(t[0], hbase + L.hi[0], hbase + L.lo[0]);
+    B2P_LAUNCH_CHECK();
     for (int i = 1; i < EC_COUNT; ++i) {
         const size_t total = (size_t)kEnc[i].cout * kEnc[i].cin * kEnc[i].k * kEnc[i].k;
         enc_pack_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(t[2 * i], t[2 * i + 1], kEnc[i].cout, kEnc[i].cin, kEnc[i].k,
@@ -347,8 +442,27 @@ int b2p_encoder_pack(const float* const* t /*32 device pointers, state-dict orde
 
 size_t b2p_encoder_ws_bytes(int B, int H, int W) { return enc_ws_layout(2 * B, H, W, nullptr, nullptr); }
 
+static int encoder_pass(const void* packed_v, const float* image1, const float* image2, int B, int H, int W, float* fmap1, float* fmap2,
+                        void* ws, cudaStream_t s);
+
+// The network is HBM-bound on its normalisation passes (every convolution output is written as fp32, read for the statistics, read
+// again to be normalised).  Running it over `enc_chunk` pairs at a time keeps a layer's maps small enough that the statistics and
+// normalisation passes find the convolution output still in the 126 MB L2; InstanceNorm is per image, so chunking is exact.
 int b2p_image_encoder(const void* packed_v, const float* image1, const float* image2, int B, int H, int W, float* fmap1, float* fmap2,
                       void* ws, cudaStream_t s) {
+    int chunk = b2p_options().enc_chunk;
+    if (chunk <= 0 || chunk > B) chunk = B;
+    const size_t img = (size_t)3 * H * W, fm = (size_t)256 * (H / 8) * (W / 8);
+    for (int p0 = 0; p0 < B; p0 += chunk) {
+        const int nb = B - p0 < chunk ? B - p0 : chunk;
+        const int rc = encoder_pass(packed_v, image1 + p0 * img, image2 + p0 * img, nb, H, W, fmap1 + p0 * fm, fmap2 + p0 * fm, ws, s);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static int encoder_pass(const void* packed_v, const float* image1, const float* image2, int B, int H, int W, float* fmap1, float* fmap2,
+                        void* ws, cudaStream_t s) {
     const float* packed = reinterpret_cast<const float*>(packed_v);
     const EncLayout& L = enc_layout();
     const int NI = 2 * B;
@@ -359,11 +473,19 @@ int b2p_image_encoder(const void* packed_v, const float* image1, const float* im
     const int P1 = H1 * W1, P2 = H2 * W2, P3 = H3 * W3;
     // conv1 + norm1 + relu (extractor.py:200-202)
     B2P_CUDA(cudaMemsetAsync(w.counter, 0, (size_t)NI * sizeof(int), s));       // ticket counters of the statistics kernel
-    static const cudaError_t st_attr = cudaFuncSetAttribute(enc_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES);
-    B2P_CUDA(st_attr);
-    enc_stem_kernel<<<dim3((unsigned)ceil_div(W1, ST_TW), (unsigned)ceil_div(H1, ST_TH), (unsigned)NI), 256, ST_SMEM_BYTES, s>>>(
-        image1, image2, B, H, W, H1, W1, packed + L.stem_w, packed + L.stem_b, w.y);
-    B2P_LAUNCH_CHECK();
+    if (b2p_options().enc_stem != 0) {            // tensor cores: gather, then a 4x1 convolution of 64 channels through the engine
+        const size_t total_px = (size_t)NI * P1;
+        enc_stem_im2col_kernel<<<(unsigned)((total_px + SI_PIX - 1) / SI_PIX), SI_PIX, 0, s>>>(image1, image2, B, H, W, H1, W1, total_px, w.xh[0],
+                                                                                              w.xh[1]);
+        B2P_LAUNCH_CHECK();
+        if ((rc = enc_conv(packed, EC_STEM, w.xh, NI, H1, W1, H1, W1, w.y, s))) return rc;
+    } else {                                      // exact fp32 FFMA kernel
+        static const cudaError_t st_attr = cudaFuncSetAttribute(enc_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES);
+        B2P_CUDA(st_attr);
+        enc_stem_kernel<<<dim3((unsigned)ceil_div(W1, ST_TW), (unsigned)ceil_div(H1, ST_TH), (unsigned)NI), 256, ST_SMEM_BYTES, s>>>(
+            image1, image2, B, H, W, H1, W1, packed + L.stem_w, packed + L.stem_b, w.y);
+        B2P_LAUNCH_CHECK();
+    }
     if ((rc = in_stats(w.y, NI, P1, 64, w, w.st_y, s))) return rc;
     if ((rc = in_apply(w.y, w.st_y, 0, nullptr, nullptr, NI, P1, 64, w.r, w.xh[0], w.xh[1], s))) return rc;
     // residual blocks: (first conv id, input dims, output dims, channels, has down-sampling branch)

@@ -37,6 +37,8 @@ const OptDesc kOpts[] = {
     // do not); off by default because a diverged refinement would pull more over PCIe sector by sector than the copy it saves.
     {"sparse_g2", "B200POSE_SPARSE_G2", &B2POptions::sparse_g2, 0},
     {"g2_margin", "B200POSE_G2_MARGIN", &B2POptions::g2_margin, 24},
+    {"enc_chunk", "B200POSE_ENC_CHUNK", &B2POptions::enc_chunk, 0},           // image encoder: crop pairs per pass (0 = the whole batch at once)
+    {"enc_stem", "B200POSE_ENC_STEM", &B2POptions::enc_stem, 1},              // image encoder stem: 1 = tensor cores (gathered 4x1 form), 0 = fp32 FFMA kernel
     {"chain_dynamic", "B200POSE_CHAIN_DYNAMIC", &B2POptions::chain_dynamic, 0},   // chained launch: units from a global queue (1) or static round robin (0)
 };
 constexpr int kNumOpts = (int)(sizeof(kOpts) / sizeof(kOpts[0]));
