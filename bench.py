@@ -121,7 +121,7 @@ def time_encoder(ops, dev, batch, H, W, peaks):
         tf = 2 * batch * encoder_flops_per_image(H, W) / (ms * 1e-3) / 1e12
         return {"ms_per_batch": ms, "pairs_per_s": batch / (ms * 1e-3), "algorithmic_tflops": tf,
                 "frac_of_burst_bf16_peak": tf / float(peaks.get("bf16_tflops")), "batch_pairs": batch,
-                "note": "b200pose_image_encoder (f2): fp32 stem + 15 tcgen05 convolutions (fp16x3 split) + InstanceNorm passes; not part of `value`"}
+                "note": "b200pose_image_encoder (f2): 16 tcgen05 convolutions (fp16x3 split; the 7x7 stem re-indexed as a 4x1 convolution of gathered channels) + InstanceNorm passes; not part of `value`"}
     except Exception as e:  # noqa: BLE001
         return {"error": f"{type(e).__name__}: {e}"}
 

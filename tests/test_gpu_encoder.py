@@ -32,8 +32,10 @@ def _close(a, b, what):
     torch.testing.assert_close(a, b, rtol=RTOL, atol=ATOL * max(1.0, scale))
 
 
-def test_encoder_matches_reference_golden(enc):
+@pytest.mark.parametrize("stem", [1, 0], ids=["stem_tensor_cores", "stem_fp32"])
+def test_encoder_matches_reference_golden(enc, libopt, stem):
     ops, packed = enc
+    libopt("enc_stem", stem)          # the 7x7 stem as a gathered 4x1 tensor-core convolution, or the fp32 FFMA kernel
     g = golden("encoder.npz")
     d = torch.device("cuda:0")
     f1, f2 = ops.image_encoder(packed, T(g["a_img1"]).to(d), T(g["a_img2"]).to(d))
@@ -71,6 +73,13 @@ def test_encoder_batched_vs_oracle_and_batch_invariance(enc):
     g1, g2 = ops.image_encoder(packed, syn[:1].to(d).contiguous(), obs[:1].to(d).contiguous())
     # (small batches run M=128 tiles, the large one CTA pairs with M=256: same products, possibly another summation grouping)
     _close(g1.cpu(), f1[:1], "B=1 vs B=16"); _close(g2.cpu(), f2[:1], "B=1 vs B=16")
+    # the encoder in chunks of pairs (option enc_chunk) is the same arithmetic per image
+    ops.set_option("enc_chunk", 3)
+    try:
+        c1, c2 = ops.image_encoder(packed, a.to(d), b.to(d))
+    finally:
+        ops.set_option("enc_chunk", 0)
+    _close(c1.cpu(), f1, "chunks of 3 pairs vs one pass, fmap1"); _close(c2.cpu(), f2, "chunks of 3 pairs vs one pass, fmap2")
     # the ill-conditioned [0,1] case stays finite and batch-invariant
     h1, h2 = ops.image_encoder(packed, mb["syn_img"].repeat(8, 1, 1, 1).contiguous().to(d), mb["obs_img"].repeat(8, 1, 1, 1).contiguous().to(d))
     assert torch.isfinite(h1).all() and torch.equal(h1[2], h1[0]) and torch.equal(h2[3], h2[1])
