@@ -38,10 +38,145 @@ __device__ __forceinline__ float corner_dot(float s, float a, float t00, float t
 // channel with no address arithmetic), 0 = run-time size.
 // BATCH: 0 = one loop over the channels (the compiler picks the load schedule), 8 / 16 = channels are loaded BATCH at a time into
 // registers before any of them is used (5 * BATCH independent loads in flight per thread).
+template <int NPLANE = 0, int BATCH = 0>
+__device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ flow, const float* __restrict__ mask,
+                                                      const float* __restrict__ g1, const float* __restrict__ g2,
+                                                      const float* __restrict__ depth, float sigma, int b, int Y, int X, int C, int H,
+                                                      int W, float* __restrict__ flow_up, float* __restrict__ target,
+                                                      float* __restrict__ weight) {
+    const int h = H >> 3, w = W >> 3;
+    const size_t N = NPLANE ? (size_t)NPLANE : (size_t)H * W;
+    const int r = Y * W + X;
+    const size_t idx = (size_t)b * N + r;
+    const int y = Y >> 3, i = Y & 7, x = X >> 3, j = X & 7;
+    const size_t p = ((size_t)b * h + y) * w + x;
+    // softmax over the 9 taps of mask[p][k*64 + i*8 + j]
+    const float* mp = mask + p * 576 + i * 8 + j;
+    float mk[9];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { mk[k] = __ldg(mp + k * 64); mx = fmaxf(mx, mk[k]); }
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { mk[k] = expf(mk[k] - mx); den += mk[k]; }
+    float ux = 0.f, uy = 0.f;
+    // (loads are unconditional from clamped addresses and the out-of-image taps are zeroed by a select: a load behind a
+    //  branch cannot be hoisted, and the kernel was serialising on one memory round trip per tap)
+    float2 fl[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int ny = y + k / 3 - 1, nx = x + k % 3 - 1;
+        const int cy = min(max(ny, 0), h - 1), cx = min(max(nx, 0), w - 1);
+        const float2 f = __ldg(reinterpret_cast<const float2*>(flow + (((size_t)b * h + cy) * w + cx) * 2));
+        const bool in = ny >= 0 && ny < h && nx >= 0 && nx < w;
+        fl[k] = in ? f : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float sm = mk[k] / den;
+        ux += sm * (8.f * fl[k].x);
+        uy += sm * (8.f * fl[k].y);
+    }
+    if (flow_up) {
+        flow_up[((size_t)b * 2 + 0) * N + r] = ux;
+        flow_up[((size_t)b * 2 + 1) * N + r] = uy;
+    }
+    const float tx = ux + (float)X, ty = uy + (float)Y;
+    if (target) *reinterpret_cast<float2*>(target + idx * 2) = make_float2(tx, ty);
+    if (!weight) return;
+
+    const float dz = depth[idx];
+    float wgt = 0.f;
+    if (dz > 0.f) {
+        // normalize_coords_grid then grid_sample's align_corners=False un-normalisation
+        const float gx = 2.f * tx / (float)(W - 1) - 1.f;
+        const float gy = 2.f * ty / (float)(H - 1) - 1.f;
+        const float ix = ((gx + 1.f) * (float)W - 1.f) / 2.f;
+        const float iy = ((gy + 1.f) * (float)H - 1.f) / 2.f;
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const int x0 = (int)fx0, y0 = (int)fy0;
+        const float wnw = (fx0 + 1.f - ix) * (fy0 + 1.f - iy);
+        const float wne = (ix - fx0) * (fy0 + 1.f - iy);
+        const float wsw = (fx0 + 1.f - ix) * (iy - fy0);
+        const float wse = (ix - fx0) * (iy - fy0);
+        const bool xa = x0 >= 0 && x0 < W, xb = x0 + 1 >= 0 && x0 + 1 < W;
+        const bool ya = y0 >= 0 && y0 < H, yb = y0 + 1 >= 0 && y0 + 1 < H;
+        // ix may be NaN/inf for degenerate flow: all comparisons false -> zero sample, like grid_sample
+        const bool fin = isfinite(ix) && isfinite(iy);
+        // Branch-free gather: every corner is loaded from an in-image (clamped) address and discarded by a select when
+        // the reference would not sample it (outside the image, or non-finite coordinates -> all four).  Same arithmetic
+        // and order as the conditional form; the 5 x C loads of a pixel are independent and can all be in flight.
+        const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
+        const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
+        const int o00 = yc0 * W + xc0, o01 = yc0 * W + xc1, o10 = yc1 * W + xc0, o11 = yc1 * W + xc1;
+        const bool k00 = fin && ya && xa, k01 = fin && ya && xb, k10 = fin && yb && xa, k11 = fin && yb && xb;
+        const float w00 = k00 ? wnw : 0.f, w01 = k01 ? wne : 0.f, w10 = k10 ? wsw : 0.f, w11 = k11 ? wse : 0.f;
+        float s = 0.f;
+        const float* g1p = g1 + (size_t)b * C * N + r;
+        const float* g2p = g2 + (size_t)b * C * N;
+        int c = 0;
+        if (BATCH > 0) {
+            constexpr int NB = BATCH > 0 ? BATCH : 1;
+            for (; c + NB <= C; c += NB) {
+                float t[NB][4], a[NB];
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+                    const float* pl = g2p + (size_t)(c + k) * N;
+                    t[k][0] = ldg_ordered(pl + o00); t[k][1] = ldg_ordered(pl + o01); t[k][2] = ldg_ordered(pl + o10); t[k][3] = ldg_ordered(pl + o11);
+                    a[k] = ldg_ordered(g1p + (size_t)(c + k) * N);
+                }
+#pragma unroll
+                for (int k = 0; k < NB; ++k)
+                    s = corner_dot(s, a[k], k00 ? t[k][0] : 0.f, k01 ? t[k][1] : 0.f, k10 ? t[k][2] : 0.f, k11 ? t[k][3] : 0.f, w00, w01, w10, w11);
+            }
+        }
+#pragma unroll 8
+        for (; c < C; ++c) {
+            const float* pl = g2p + (size_t)c * N;
+            const float t00 = __ldg(pl + o00), t01 = __ldg(pl + o01), t10 = __ldg(pl + o10), t11 = __ldg(pl + o11);
+            const float a = __ldg(g1p + (size_t)c * N);
+            s = corner_dot(s, a, k00 ? t00 : 0.f, k01 ? t01 : 0.f, k10 ? t10 : 0.f, k11 ? t11 : 0.f, w00, w01, w10, w11);
+        }
+        wgt = expf(-fabsf(1.f - s) / sigma);
+    }
+    weight[idx] = wgt;
+}
+
+template <int NPLANE, int BATCH>
+__global__ void __launch_bounds__(64) upsample_weight_kernel(
+    const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1,
+    const float* __restrict__ g2, const float* __restrict__ depth, float sigma, int B, int C, int H, int W,
+    float* __restrict__ flow_up, float* __restrict__ target, float* __restrict__ weight, int lazy_background) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t N = NPLANE ? (size_t)NPLANE : (size_t)H * W;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * N) return;
+    const int b = (int)(idx / N);
+    const int r = (int)(idx - (size_t)b * N);
+    const int Y = r / W, X = r - Y * W;
+    // Fused-loop shortcut: a background pixel (syn_depth <= 0) has weight exactly 0, so the LM step ignores its target
+    // (any finite value contributes 0 * finite = 0, as in the reference).  When the up-sampled flow itself is not an
+    // output of this iteration, skip the mask softmax and the descriptor warp for it.
+    if (lazy_background && !flow_up && depth[idx] <= 0.f) {
+        if (target) *reinterpret_cast<float2*>(target + idx * 2) = make_float2((float)X, (float)Y);
+        if (weight) weight[idx] = 0.f;
+        return;
+    }
+    upsample_weight_pixel<NPLANE, BATCH>(flow, mask, g1, g2, depth, sigma, b, Y, X, C, H, W, flow_up, target, weight);
+}
+
+// The same pixel routine for the host entry's windowed second descriptor map.  It is a separate copy on purpose: with the
+// window logic as a template flag of upsample_weight_pixel, the DEFAULT build of the kernel came out 20 us slower (108 vs 88 us,
+// same source after dead-code elimination, a different ptxas schedule; A/B on one box in profiles/r2w).
+// NPLANE: H*W when known at compile time (the plane stride of the descriptor loads becomes an immediate offset: 5 loads per
+// channel with no address arithmetic), 0 = run-time size.
+// BATCH: 0 = one loop over the channels (the compiler picks the load schedule), 8 / 16 = channels are loaded BATCH at a time into
+// registers before any of them is used (5 * BATCH independent loads in flight per thread).
 // WINDOW: g2 holds valid data only inside the per-sample window win[b] = (y0, y1, x0, x1) (what the host entry copied over PCIe:
 // the foreground box plus a margin); a corner that is sampled outside it is read from g2_far, the same map in mapped host memory.
-template <int NPLANE = 0, int BATCH = 0, bool WINDOW = false>
-__device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ flow, const float* __restrict__ mask,
+template <int NPLANE = 0, int BATCH = 0, bool WINDOW = true>
+__device__ __forceinline__ void upsample_weight_pixel_win(const float* __restrict__ flow, const float* __restrict__ mask,
                                                       const float* __restrict__ g1, const float* __restrict__ g2,
                                                       const float* __restrict__ depth, float sigma, int b, int Y, int X, int C, int H,
                                                       int W, float* __restrict__ flow_up, float* __restrict__ target,
@@ -138,7 +273,12 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
 #pragma unroll
                 for (int k = 0; k < NB; ++k) {
                     const size_t co = (size_t)(c + k) * N;
-                    t[k][0] = ldg_ordered(q00 + co); t[k][1] = ldg_ordered(q01 + co); t[k][2] = ldg_ordered(q10 + co); t[k][3] = ldg_ordered(q11 + co);
+                    if (WINDOW) {
+                        t[k][0] = ldg_ordered(q00 + co); t[k][1] = ldg_ordered(q01 + co); t[k][2] = ldg_ordered(q10 + co); t[k][3] = ldg_ordered(q11 + co);
+                    } else {                     // one plane pointer + four 32-bit offsets: the form the compiler schedules best (88 vs 96 us)
+                        const float* pl = g2p + co;
+                        t[k][0] = ldg_ordered(pl + o00); t[k][1] = ldg_ordered(pl + o01); t[k][2] = ldg_ordered(pl + o10); t[k][3] = ldg_ordered(pl + o11);
+                    }
                     a[k] = ldg_ordered(g1p + co);
                 }
 #pragma unroll
@@ -149,7 +289,13 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
 #pragma unroll 8
         for (; c < C; ++c) {
             const size_t co = (size_t)c * N;
-            const float t00 = __ldg(q00 + co), t01 = __ldg(q01 + co), t10 = __ldg(q10 + co), t11 = __ldg(q11 + co);
+            float t00, t01, t10, t11;
+            if (WINDOW) {
+                t00 = __ldg(q00 + co); t01 = __ldg(q01 + co); t10 = __ldg(q10 + co); t11 = __ldg(q11 + co);
+            } else {
+                const float* pl = g2p + co;
+                t00 = __ldg(pl + o00); t01 = __ldg(pl + o01); t10 = __ldg(pl + o10); t11 = __ldg(pl + o11);
+            }
             const float a = __ldg(g1p + co);
             s = corner_dot(s, a, k00 ? t00 : 0.f, k01 ? t01 : 0.f, k10 ? t10 : 0.f, k11 ? t11 : 0.f, w00, w01, w10, w11);
         }
@@ -158,8 +304,8 @@ __device__ __forceinline__ void upsample_weight_pixel(const float* __restrict__ 
     weight[idx] = wgt;
 }
 
-template <int NPLANE, int BATCH, bool WINDOW = false>
-__global__ void __launch_bounds__(64) upsample_weight_kernel(
+template <int NPLANE, int BATCH, bool WINDOW = true>
+__global__ void __launch_bounds__(64) upsample_weight_win_kernel(
     const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ g1,
     const float* __restrict__ g2, const float* __restrict__ depth, float sigma, int B, int C, int H, int W,
     float* __restrict__ flow_up, float* __restrict__ target, float* __restrict__ weight, int lazy_background,
@@ -180,7 +326,7 @@ __global__ void __launch_bounds__(64) upsample_weight_kernel(
         if (weight) weight[idx] = 0.f;
         return;
     }
-    upsample_weight_pixel<NPLANE, BATCH, WINDOW>(flow, mask, g1, g2, depth, sigma, b, Y, X, C, H, W, flow_up, target, weight, g2_far, win);
+    upsample_weight_pixel_win<NPLANE, BATCH, WINDOW>(flow, mask, g1, g2, depth, sigma, b, Y, X, C, H, W, flow_up, target, weight, g2_far, win);
 }
 
 // ------------------------------------------------------------------------------------------------ foreground list
@@ -324,8 +470,8 @@ int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, c
     // other crop sizes run variant 0
     const int var = b2p_options().upsample_variant;
     const bool cs = H * W == 240 * 320;
-#define UPW_LAUNCH(NP, BT) B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel<NP, BT>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up, target, weight, lazy_background, (const float*)nullptr, (const int*)nullptr))
-#define UPW_LAUNCH_WIN(NP, BT) B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel<NP, BT, true>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up, target, weight, lazy_background, g2_far, g2_window))
+#define UPW_LAUNCH(NP, BT) B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel<NP, BT>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up, target, weight, lazy_background))
+#define UPW_LAUNCH_WIN(NP, BT) B2P_CUDA(b2p_launch_pdl(upsample_weight_win_kernel<NP, BT>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up, target, weight, lazy_background, g2_far, g2_window))
     if (g2_far && g2_window && g2) {            // host entry: geofea2 is only valid inside a per-sample window
         if (var != 0 && cs) UPW_LAUNCH_WIN(240 * 320, 16);
         else UPW_LAUNCH_WIN(0, 0);
