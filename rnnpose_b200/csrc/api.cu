@@ -816,7 +816,14 @@ struct TexelGather {
         b2p_context_sample_taps(H, h, y0.data(), y1.data());
         done.reset(new std::atomic<int>[nsub]);
         for (int k = 0; k < nsub; ++k) done[k].store(0, std::memory_order_relaxed);
-        for (int t = 0; t < T; ++t) workers.emplace_back([this, t] { run(t); });
+        for (int t = 0; t < T; ++t) {
+            try {
+                workers.emplace_back([this, t] { run(t); });
+            } catch (...) {                          // no more threads to be had: the caller's thread does the remaining shares
+                for (int tt = t; tt < T; ++tt) run(tt);
+                break;
+            }
+        }
     }
     void run(int t) const {
         const size_t P = (size_t)h * w;
