@@ -497,10 +497,11 @@ def run_workload(args, cfg, per_gpu, rank, local_rank, world, dev, numa, want_cp
         del ws
         cores = len(os.sched_getaffinity(0))
         if args.host_gather_threads is not None:
-            variants = [args.host_gather_threads]
-        else:                                      # both ways of not copying the whole context map, the faster one is the line's e2e
-            variants = [-1, max(1, min(8, cores // max(1, world)))]
-        staging = ops.host_staging(chunk, H, W) if any(t >= 0 for t in variants) else None
+            variants = [(args.host_gather_threads, 256)]
+        else:                                      # the ways of not copying the whole context map; the fastest one is the line's e2e
+            tg = max(1, min(8, cores // max(1, world)))
+            variants = [(-1, 0), (tg, 256), (tg, 128)]          # (host threads, context planes per object they gather)
+        staging = ops.host_staging(chunk, H, W) if any(t >= 0 for t, _ in variants) else None
 
         def e2e_step(threads):
             nonlocal scratch
@@ -535,7 +536,9 @@ def run_workload(args, cfg, per_gpu, rank, local_rank, world, dev, numa, want_cp
         other = sum(host[k].numel() * 4 for k in ("fmap1", "fmap2", "depth", "K", "G0")) + g1_bytes + g2_bytes
         d2h = n_chunks * Gh.numel() * 4
         runs = []
-        for threads in variants:
+        for threads, planes in variants:
+            if threads >= 0:
+                ops.set_option("host_gather_planes", planes)
             e2e_step(threads)
             torch.cuda.synchronize(); D.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -546,13 +549,18 @@ def run_workload(args, cfg, per_gpu, rank, local_rank, world, dev, numa, want_cp
             torch.cuda.synchronize(); D.barrier()
             my_ms = e0.elapsed_time(e1)
             ms_e2e = D.max_over_ranks(my_ms, dev)
-            ctx_bytes = chunk * 256 * (len(rows) * W if threads < 0 else (H // 8) * (W // 8) * 4) * 4
+            n_tex = planes if threads >= 0 else 0                      # planes gathered by the host; the rest is read in place, rows only
+            ctx_bytes = chunk * (n_tex * (H // 8) * (W // 8) * 4 + (256 - n_tex) * len(rows) * W) * 4
             h2d = n_chunks * (other + ctx_bytes)
-            runs.append({"context": "mapped rows (zero-copy)" if threads < 0 else f"texels gathered by {threads} host threads",
+            runs.append({"context": "mapped rows (zero-copy)" if threads < 0 else
+                         (f"texels gathered by {threads} host threads" if planes == 256 else
+                          f"{planes} of 256 planes as texels gathered by {threads} host threads, the rest as mapped rows"),
+                         "gathered_planes": n_tex,
                          "host_gather_threads": threads, "value": world * per_gpu * ke / (ms_e2e * 1e-3),
                          "ms_per_step": ms_e2e / ke, "h2d_bytes_per_step": h2d,
                          "h2d_gbs_this_rank": h2d * ke / (my_ms * 1e-3) / 1e9,
                          "max_abs_diff_vs_device_entry": (Gh.to(dev) - G_dev0).abs().max().item()})
+        ops.set_option("host_gather_planes", 256)
         best = max(runs, key=lambda r: r["value"])
         e2e = {"value": best["value"], "unit": "poses/s", "h2d_bytes_per_step": best["h2d_bytes_per_step"], "d2h_bytes_per_step": d2h,
                "steps": ke, "ms_per_step": best["ms_per_step"], "max_abs_diff_vs_device_entry": max(r["max_abs_diff_vs_device_entry"] for r in runs),

@@ -678,7 +678,8 @@ static int refine_iters_impl(const void* packed_weights, const float* fmap1, con
                              const float* geofea1, const float* geofea2, const float* depth, const float* K, float* G,
                              float sigma, int B, int C_geo, int H, int W, int n_iters, int n_lm, double ep_lmbda,
                              double lm_lmbda, int flags, float* flow_first, float* flow_last, float* weight_last,
-                             void* workspace, size_t workspace_bytes, void* stream, const float* g2_far, const int* g2_window);
+                             void* workspace, size_t workspace_bytes, void* stream, const float* g2_far, const int* g2_window,
+                             const float* ctx_texels, int ctx_split);
 
 extern "C" {
 
@@ -689,7 +690,8 @@ int b200pose_refine_iters(const void* packed_weights, const float* fmap1, const 
                           void* workspace, size_t workspace_bytes, void* stream) {
     return refine_iters_impl(packed_weights, fmap1, fmap2, context, geofea1, geofea2, depth, K, G, sigma, B, C_geo, H, W, n_iters,
                              n_lm, ep_lmbda, lm_lmbda, flags, flow_first, flow_last, weight_last, workspace, workspace_bytes, stream,
-                             nullptr, nullptr);
+                             nullptr, nullptr, (flags & B200POSE_FLAG_CONTEXT_TEXELS) ? context : nullptr,
+                             (flags & B200POSE_FLAG_CONTEXT_TEXELS) ? 256 : 0);
 }
 
 }  // extern "C"
@@ -698,7 +700,8 @@ static int refine_iters_impl(const void* packed_weights, const float* fmap1, con
                              const float* geofea1, const float* geofea2, const float* depth, const float* K, float* G,
                              float sigma, int B, int C_geo, int H, int W, int n_iters, int n_lm, double ep_lmbda,
                              double lm_lmbda, int flags, float* flow_first, float* flow_last, float* weight_last,
-                             void* workspace, size_t workspace_bytes, void* stream, const float* g2_far, const int* g2_window) {
+                             void* workspace, size_t workspace_bytes, void* stream, const float* g2_far, const int* g2_window,
+                             const float* ctx_texels, int ctx_split) {
     if (!packed_weights || !fmap1 || !fmap2 || !context || !geofea1 || !geofea2 || !depth || !K || !G || !workspace)
         return B200POSE_E_NULL;
     if (!shape_ok(B, H, W) || C_geo < 1) return B200POSE_E_SHAPE;
@@ -718,9 +721,10 @@ static int refine_iters_impl(const void* packed_weights, const float* fmap1, con
         if ((rc = run_corr_volume_tc(fmap1, fmap2, B, h, w, r.pyr, r.vol, s))) return rc;
         if ((rc = pool_pyramid(r.pyr, B, h, w, s))) return rc;
     } else if ((rc = b200pose_corr_pyramid(fmap1, fmap2, B, 256, h, w, r.pyr, stream))) return rc;
-    const bool ctx_packed = (flags & B200POSE_FLAG_CONTEXT_TEXELS) != 0;
-    if (tc) rc = b2p_context_init(context, B, H, W, r.net, nullptr, u.net_h[0], u.net_h[1], u.x_h[0], u.x_h[1], s, ctx_packed);
-    else rc = b2p_context_init(context, B, H, W, r.net, r.xbuf, nullptr, nullptr, nullptr, nullptr, s, ctx_packed);
+    // ctx_texels / ctx_split: the first ctx_split context planes of every object come as texels (B200POSE_FLAG_CONTEXT_TEXELS:
+    // all 256), the rest from the full map
+    if (tc) rc = b2p_context_init(context, B, H, W, r.net, nullptr, u.net_h[0], u.net_h[1], u.x_h[0], u.x_h[1], s, ctx_texels, ctx_split);
+    else rc = b2p_context_init(context, B, H, W, r.net, r.xbuf, nullptr, nullptr, nullptr, nullptr, s, ctx_texels, ctx_split);
     if (rc) return rc;
     if (tc && (rc = b2p_pxc_to_tiled(r.net, u.rhbuf, B, h, w, 128, s))) return rc;     // hidden state of the tensor-core epilogues
     if (tc && (rc = b2p_pxc_to_tiled(r.net, u.hbuf_x, B, h, w, 128, s, 1))) return rc;  // ... and its x-major copy (chained launch)
@@ -797,13 +801,13 @@ struct HostScratch {
 // are complete when done[k] == T; the workers never wait (the staging buffer holds the whole batch).
 struct TexelGather {
     const float* ctx = nullptr; float* out = nullptr;
-    int B = 0, H = 0, W = 0, h = 0, w = 0, bs = 0, nsub = 0, T = 0, mode = 0;
+    int B = 0, H = 0, W = 0, h = 0, w = 0, bs = 0, nsub = 0, T = 0, mode = 0, planes_per = 256;   // planes_per: gathered planes per object
     std::vector<int> x0, x1, y0, y1;
     std::unique_ptr<std::atomic<int>[]> done;
     std::vector<std::thread> workers;
 
-    void start(const float* ctx_, float* out_, int B_, int H_, int W_, int bs_, int nsub_, int threads) {
-        ctx = ctx_; out = out_; B = B_; H = H_; W = W_; h = H / 8; w = W / 8; bs = bs_; nsub = nsub_;
+    void start(const float* ctx_, float* out_, int B_, int H_, int W_, int bs_, int nsub_, int threads, int planes_per_ = 256) {
+        ctx = ctx_; out = out_; B = B_; H = H_; W = W_; h = H / 8; w = W / 8; bs = bs_; nsub = nsub_; planes_per = planes_per_;
         mode = b2p_options().host_gather;
         if (threads <= 0) {                          // auto: half of the CPUs this process may run on, at most 8
             cpu_set_t set; CPU_ZERO(&set);
@@ -829,10 +833,11 @@ struct TexelGather {
         const size_t P = (size_t)h * w;
         for (int k = 0; k < nsub; ++k) {
             const int b0 = k * bs, nb = (B - b0 < bs) ? (B - b0) : bs;
-            const long planes = (long)nb * 256, lo = planes * t / T, hi = planes * (t + 1) / T;
+            const long planes = (long)nb * planes_per, lo = planes * t / T, hi = planes * (t + 1) / T;
             for (long pl = lo; pl < hi; ++pl) {
-                const float* src = ctx + ((size_t)b0 * 256 + pl) * (size_t)H * W;
-                float* dst = out + ((size_t)b0 * 256 + pl) * P * 4;
+                const long bi = pl / planes_per, ci = pl - bi * planes_per;
+                const float* src = ctx + ((size_t)(b0 + bi) * 256 + ci) * (size_t)H * W;
+                float* dst = out + ((size_t)b0 * planes_per + pl) * P * 4;
                 for (int y = 0; y < h; ++y) {
                     const float* r0 = src + (size_t)y0[y] * W;
                     const float* r1 = src + (size_t)y1[y] * W;
@@ -970,7 +975,7 @@ int b200pose_refine_iters_host2(const void* packed_weights, const float* fmap1_h
     //  * else, when context_host is pinned (device-accessible through UVA), the context-init kernel reads the rows straight
     //    from host memory (every 32-byte sector of 2 rows in 8 is touched: 1/4 of the bytes).
     const float* ctx_mapped = nullptr;
-    if (!gather) {
+    {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, context_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
             attr.devicePointer != nullptr)
@@ -1007,10 +1012,15 @@ int b200pose_refine_iters_host2(const void* packed_weights, const float* fmap1_h
     const int h = H / 8, w = W / 8, bs = hs.bs;
     const int nsub = (B + bs - 1) / bs;
     const size_t f = sizeof(float);
-    const int loop_flags = gather ? (flags | B200POSE_FLAG_CONTEXT_TEXELS) : flags;
+    // gathered planes per object: all 256, or (option host_gather_planes, needs the mapped pointer for the rest) the first c_split
+    int c_split = 0;
+    if (gather) {
+        c_split = b2p_options().host_gather_planes;
+        c_split = ctx_mapped ? (c_split < 32 ? 32 : (c_split > 256 ? 256 : (c_split / 32) * 32)) : 256;
+    }
 
     TexelGather tg;
-    if (gather) tg.start(context_host, reinterpret_cast<float*>(host_staging), B, H, W, bs, nsub, n_host_threads);
+    if (gather) tg.start(context_host, reinterpret_cast<float*>(host_staging), B, H, W, bs, nsub, n_host_threads, c_split);
 
     cudaStream_t cs = nullptr;                     // internal copy stream + events, created and destroyed per call
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_start = nullptr;
@@ -1061,16 +1071,16 @@ int b200pose_refine_iters_host2(const void* packed_weights, const float* fmap1_h
         B2P_TRY(cudaMemcpyAsync(st.G, G_host + (size_t)b0 * 16, (size_t)nb * 16 * f, cudaMemcpyHostToDevice, cs));
         if (gather) {                               // the workers ran ahead while the copies above were queued / in flight
             tg.wait(k);
-            const size_t per = (size_t)256 * h * w * 4;
+            const size_t per = (size_t)c_split * h * w * 4;
             B2P_TRY(cudaMemcpyAsync(st.context, reinterpret_cast<const float*>(host_staging) + (size_t)b0 * per, (size_t)nb * per * f, cudaMemcpyHostToDevice, cs));
         }
         B2P_TRY(cudaEventRecord(ev_copy[k & 1], cs));
         B2P_TRY(cudaStreamWaitEvent(s, ev_copy[k & 1], 0));
-        const float* ctx = ctx_mapped ? ctx_mapped + (size_t)b0 * 256 * H * W : st.context;
+        const float* ctx = ctx_mapped ? ctx_mapped + (size_t)b0 * 256 * H * W : st.context;      // (unused when all 256 planes are gathered)
         rc = refine_iters_impl(packed_weights, st.fmap1, st.fmap2, ctx, st.geo1, st.geo2, st.depth, st.K, st.G, sigma, nb,
-                               C_geo, H, W, n_iters, n_lm, ep_lmbda, lm_lmbda, loop_flags, nullptr, nullptr, nullptr, hs.ws,
+                               C_geo, H, W, n_iters, n_lm, ep_lmbda, lm_lmbda, flags, nullptr, nullptr, nullptr, hs.ws,
                                hs.ws_bytes, stream, g2_mapped ? g2_mapped + (size_t)b0 * C_geo * H * W : nullptr,
-                               g2_mapped ? st.win : nullptr);
+                               g2_mapped ? st.win : nullptr, gather ? st.context : nullptr, c_split);
         if (rc) goto cleanup;
         B2P_TRY(cudaMemcpyAsync(G_host + (size_t)b0 * 16, st.G, (size_t)nb * 16 * f, cudaMemcpyDeviceToHost, s));
         B2P_TRY(cudaEventRecord(ev_done[k & 1], s));

@@ -42,7 +42,7 @@ inline cudaError_t b2p_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 // into the library, changed afterwards only through b200pose_set_option.
 struct B2POptions {
     int conv_mode, fg_list, fg_pipeline, fg_upsample, sparse_g1, fg_blocks, tail_min_n, conv_debug, lookup_mode, pool_mode,
-        lm_debug, chain_rings, chain_dynamic, chain_xmajor, lm_cluster, chain_merge, upsample_variant, host_gather, sparse_g2, g2_margin, enc_chunk, enc_stem;
+        lm_debug, chain_rings, chain_dynamic, chain_xmajor, lm_cluster, chain_merge, upsample_variant, host_gather, sparse_g2, g2_margin, enc_chunk, enc_stem, host_gather_planes;
 };
 B2POptions& b2p_options();
 
@@ -188,7 +188,7 @@ int b2p_fmap_to_pxc_half(const float* f, int B, int D, int P, __half* hi, __half
 int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, __half* out_hi,
                     __half* out_lo, cudaStream_t s);
 int b2p_context_init(const float* ctx, int B, int H, int W, float* net, float* xbuf, __half* net_hi, __half* net_lo,
-                     __half* x_hi, __half* x_lo, cudaStream_t s, bool packed = false);
+                     __half* x_hi, __half* x_lo, cudaStream_t s, const float* texels = nullptr, int c_split = 0);
 void b2p_context_sample_taps(int in, int out, int* i0, int* i1);
 int b2p_flow_init(const float* depth, const float* K, const float* G, int B, int H, int W,
                   float* coords1, float* flow, cudaStream_t s);

@@ -232,8 +232,11 @@ __global__ void __launch_bounds__(128) corr_pool3_kernel(const float* __restrict
 // xbuf[:, 0:128] = relu(ch 128..255).   32 low-res pixels x 32 channels per block, smem transpose.
 // PACKED: ctx holds only the four texels of each low-res sample, [B,256,P] float4 = (v00, v01, v10, v11), as gathered on the
 // host by b200pose_refine_iters_host2 (api.cu: gather_context_texels) -- same arithmetic, 1/16 of the bytes.
+// MIXED (the host entry's split between host-thread gather and in-place reads): channels below c_split come from `tex`
+// ([B][c_split][P] float4), the others from the full map `ctx`; a block handles one 32-channel tile, so the choice is block-uniform.
 template <bool PACKED>
-__global__ void __launch_bounds__(256) context_init_kernel(const float* __restrict__ ctx, int B, int H, int W, int h, int w,
+__global__ void __launch_bounds__(256) context_init_kernel(const float* __restrict__ ctx, const float* __restrict__ tex, int c_split,
+                                                           int B, int H, int W, int h, int w,
                                                            float sy, float sx, float* __restrict__ net,
                                                            float* __restrict__ xbuf, __half* __restrict__ net_hi,
                                                            __half* __restrict__ net_lo, __half* __restrict__ x_hi,
@@ -255,8 +258,8 @@ __global__ void __launch_bounds__(256) context_init_kernel(const float* __restri
         const float ly = fy - (float)y0, lx = fxx - (float)x0;
         for (int cc = tyy; cc < 32; cc += 8) {
             float v00, v01, v10, v11;
-            if (PACKED) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(ctx) + ((size_t)b * 256 + c0 + cc) * (size_t)P + p);
+            if (PACKED && c0 < c_split) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(tex) + ((size_t)b * c_split + c0 + cc) * (size_t)P + p);
                 v00 = t.x; v01 = t.y; v10 = t.z; v11 = t.w;
             } else {
                 const float* pl = ctx + ((size_t)b * 256 + c0 + cc) * (size_t)H * W;
@@ -386,15 +389,15 @@ int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int
 static inline float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
 
 int b2p_context_init(const float* ctx, int B, int H, int W, float* net, float* xbuf, __half* net_hi, __half* net_lo,
-                     __half* x_hi, __half* x_lo, cudaStream_t s, bool packed) {
+                     __half* x_hi, __half* x_lo, cudaStream_t s, const float* texels, int c_split) {
     const int h = H / 8, w = W / 8;
     dim3 grid(ceil_div(h * w, 32), 8, B);
-    if (packed)
-        context_init_kernel<true><<<grid, 256, 0, s>>>(ctx, B, H, W, h, w, ac_scale(H, h), ac_scale(W, w), net, xbuf, net_hi,
-                                                         net_lo, x_hi, x_lo);
+    if (texels && c_split > 0)             // c_split (a multiple of 32) channels from the texel layout, the rest from the map
+        context_init_kernel<true><<<grid, 256, 0, s>>>(ctx, texels, c_split, B, H, W, h, w, ac_scale(H, h), ac_scale(W, w), net, xbuf,
+                                                         net_hi, net_lo, x_hi, x_lo);
     else
-        context_init_kernel<false><<<grid, 256, 0, s>>>(ctx, B, H, W, h, w, ac_scale(H, h), ac_scale(W, w), net, xbuf, net_hi,
-                                                          net_lo, x_hi, x_lo);
+        context_init_kernel<false><<<grid, 256, 0, s>>>(ctx, nullptr, 0, B, H, W, h, w, ac_scale(H, h), ac_scale(W, w), net, xbuf,
+                                                          net_hi, net_lo, x_hi, x_lo);
     B2P_LAUNCH_CHECK();
     return 0;
 }

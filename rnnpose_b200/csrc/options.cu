@@ -39,6 +39,10 @@ const OptDesc kOpts[] = {
     {"g2_margin", "B200POSE_G2_MARGIN", &B2POptions::g2_margin, 24},
     {"enc_chunk", "B200POSE_ENC_CHUNK", &B2POptions::enc_chunk, 0},           // image encoder: crop pairs per pass (0 = the whole batch at once)
     {"enc_stem", "B200POSE_ENC_STEM", &B2POptions::enc_stem, 1},              // image encoder stem: 1 = tensor cores (gathered 4x1 form), 0 = fp32 FFMA kernel
+    // host entry with a staging buffer: how many of the 256 context planes per object the host threads gather (a multiple of 32);
+    // the kernel reads the rest in place from the mapped buffer.  256 when one GPU has the host to itself; fewer when several
+    // ranks share the host's cores (bench.py tries both)
+    {"host_gather_planes", "B200POSE_HOST_GATHER_PLANES", &B2POptions::host_gather_planes, 256},
     {"chain_dynamic", "B200POSE_CHAIN_DYNAMIC", &B2POptions::chain_dynamic, 0},   // chained launch: units from a global queue (1) or static round robin (0)
 };
 constexpr int kNumOpts = (int)(sizeof(kOpts) / sizeof(kOpts[0]));

@@ -204,6 +204,26 @@ def test_refine_host_entry_windowed_second_descriptor_map(ops, packed, libopt, m
         assert torch.equal(Gh2, Gd), f"sparse_g2={sparse} after poisoning the staging buffers"
 
 
+@pytest.mark.parametrize("planes", [32, 96, 224])
+def test_refine_host_entry_partial_gather(ops, packed, libopt, planes):
+    """Option host_gather_planes: the host threads gather only the first `planes` context planes of every object, the kernel
+    reads the others in place from the pinned map (ranks sharing a host's cores).  Bit-identical to the device entry."""
+    H, W, B = 128, 160, 5
+    mb = S.make_batch(list(range(50, 50 + B)), H, W, with_images=False)
+    f1 = S.hash_features((B, 256, H // 8, W // 8), 89); f2 = S.hash_features((B, 256, H // 8, W // 8), 90)
+    G0 = torch.eye(4)[None].repeat(B, 1, 1)
+    Gd = run_gpu(ops, packed, f1, f2, mb, G0, 2, 2)["G"].cpu()
+    pin = {k: mb[k].contiguous().pin_memory() for k in ("context", "geofea1", "geofea2", "K")}
+    libopt("host_gather_planes", planes)
+    staging = ops.host_staging(B, H, W); staging.fill_(float("nan"))
+    Gh = G0.clone().pin_memory()
+    ops.refine_iters_host(packed, f1.pin_memory(), f2.pin_memory(), pin["context"], pin["geofea1"], pin["geofea2"],
+                          mb["depth"][:, 0].contiguous().pin_memory(), pin["K"], Gh, 1.0, 2, 2, staging=staging, threads=3)
+    assert torch.equal(Gh, Gd)
+    n_used = B * planes * (H // 8) * (W // 8) * 4
+    assert torch.isfinite(staging[:n_used]).all() and torch.isnan(staging[n_used:]).all()     # exactly the gathered planes were written
+
+
 def test_refine_iters_cuda_graph_capture(ops, packed):
     """b200pose_refine_iters is stream-ordered and allocation-free: captured into a CUDA graph (PDL and cluster launches
     included) and replayed, it reproduces the eager result bit for bit, also after the inputs change in place."""
