@@ -20,13 +20,15 @@
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline int& b2p_pdl_next_allowed() { static thread_local int v = 1; return v; }     // consumed by the next b2p_launch_pdl
 template <typename... KArgs, typename... Args>
 inline cudaError_t b2p_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = b2p_pdl_next_allowed();
+    b2p_pdl_next_allowed() = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
@@ -42,9 +44,12 @@ inline cudaError_t b2p_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 // into the library, changed afterwards only through b200pose_set_option.
 struct B2POptions {
     int conv_mode, fg_list, fg_pipeline, fg_upsample, sparse_g1, fg_blocks, tail_min_n, conv_debug, lookup_mode, pool_mode,
-        lm_debug, chain_rings, chain_dynamic, chain_xmajor, lm_cluster, chain_merge, upsample_variant, host_gather, sparse_g2, g2_margin, enc_chunk, enc_stem, host_gather_planes;
+        lm_debug, chain_rings, chain_dynamic, chain_xmajor, lm_cluster, chain_merge, upsample_variant, host_gather, sparse_g2, g2_margin, enc_chunk, enc_stem, host_gather_planes, pdl_off;
 };
 B2POptions& b2p_options();
+// A/B switch (option pdl_off, bit mask): launch the tagged kernel WITHOUT the programmatic-dependent-launch attribute.
+// tags: 0 flow_init, 1 lookup, 2 im2col_f1, 3 chained convolution launch, 4 upsample + weight, 5 LM
+inline int b2p_pdl_allowed(int tag) { return (b2p_options().pdl_off >> tag) & 1 ? 0 : 1; }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -359,6 +359,85 @@ int b2p_corr_pool(const float* src, int NP, int hs, int ws, float* dst, cudaStre
     return 0;
 }
 
+// lookup_mode 2: one thread per (pixel, level, window row j).  The thread loads the two texel rows j and j + 1 of its level's 10x10
+// window straight from the pyramid (2 x 10 contiguous floats: clamped addresses + selects, zeros outside the level like the
+// reference's grid_sample) and blends the 9 samples of its row from registers -- 20 loads per 9 outputs instead of the window
+// kernel's 100 staged texels + 4 shared-memory reads per output; same weights, same blend order.  The 328-wide row of a pixel is
+// assembled in shared memory and leaves as 128-bit stores as before.  36 threads per pixel, LR_PIX pixels per block.
+template <int LR_PIX>
+__global__ void __launch_bounds__(LR_PIX * 36) corr_lookup_row_kernel(const float* __restrict__ pyr, const float* __restrict__ coords,
+                                                                       int B, int h, int w, float* __restrict__ out,
+                                                                       __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+    __shared__ __align__(16) float row[LR_PIX][B200POSE_CORR_PITCH];
+    pdl_trigger();
+    pdl_wait();
+    const int P = h * w;
+    const int total = B * P;
+    const int pl = threadIdx.x / 36, r = threadIdx.x - pl * 36;
+    const int l = r / 9, j = r - l * 9;
+    const int pix = blockIdx.x * LR_PIX + pl;
+    if (pix < total) {
+        const int b = pix / P, p = pix - b * P;
+        size_t lvl_off = 0;
+        int hl = h, wl = w;
+        float inv = 1.f;
+        for (int k = 0; k < l; ++k) { lvl_off += (size_t)B * P * (size_t)(hl * wl); hl >>= 1; wl >>= 1; inv *= 0.5f; }
+        const float* img = pyr + lvl_off + ((size_t)b * P + p) * (size_t)(hl * wl);
+        const float x0c = coords[(size_t)pix * 2 + 0] * inv, y0c = coords[(size_t)pix * 2 + 1] * inv;    // / 2^l, exact
+        const float xb = floorf(x0c - 4.0f), yb = floorf(y0c - 4.0f);
+        const bool fin = isfinite(x0c) && isfinite(y0c);
+        const float fx = fin ? (x0c - 4.0f) - xb : 0.f, fy = fin ? (y0c - 4.0f) - yb : 0.f;          // non-finite centre: exact zeros
+        const int xi0 = fin ? (int)fmaxf(fminf(xb, 1e6f), -1e6f) : -1000000;
+        const int yi0 = fin ? (int)fmaxf(fminf(yb, 1e6f), -1e6f) : -1000000;
+        const int ya = yi0 + j, yn = ya + 1;
+        const bool oka = ya >= 0 && ya < hl, okn = yn >= 0 && yn < hl;
+        const float* ra = img + min(max(ya, 0), hl - 1) * wl;
+        const float* rn = img + min(max(yn, 0), hl - 1) * wl;
+        float va[10], vn[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            const int xx = xi0 + k;
+            const bool okx = xx >= 0 && xx < wl;
+            const int xc = min(max(xx, 0), wl - 1);
+            const float a = __ldg(ra + xc), c = __ldg(rn + xc);
+            va[k] = (okx && oka) ? a : 0.f;
+            vn[k] = (okx && okn) ? c : 0.f;
+        }
+        const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
+        float* dst = &row[pl][l * 81 + j];                        // channel = l*81 + i*9 + j: i moves x, j moves y
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            dst[i * 9] = __fmaf_rn(vn[i + 1], w11, __fmaf_rn(vn[i], w10, __fmaf_rn(va[i + 1], w01, __fmul_rn(va[i], w00))));
+        if (r < B200POSE_CORR_PITCH - B200POSE_CORR_CH) row[pl][B200POSE_CORR_CH + r] = 0.f;
+    }
+    __syncthreads();
+    const int npix = min(LR_PIX, total - blockIdx.x * LR_PIX);
+    const size_t base = (size_t)blockIdx.x * LR_PIX * B200POSE_CORR_PITCH;
+    const float* flat = &row[0][0];
+    if (out) {
+        float4* o4 = reinterpret_cast<float4*>(out + base);
+        const float4* r4 = reinterpret_cast<const float4*>(flat);
+        for (int c = threadIdx.x; c < npix * (B200POSE_CORR_PITCH / 4); c += LR_PIX * 36) o4[c] = r4[c];
+    }
+    if (out_hi) {
+        uint4* oh = reinterpret_cast<uint4*>(out_hi + base);
+        uint4* ol = reinterpret_cast<uint4*>(out_lo + base);
+        for (int c = threadIdx.x; c < npix * (B200POSE_CORR_PITCH / 8); c += LR_PIX * 36) {
+            uint32_t wh[4], wlw[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                __half h0, l0, h1, l1;
+                b2p_split_half(flat[c * 8 + 2 * t], h0, l0);
+                b2p_split_half(flat[c * 8 + 2 * t + 1], h1, l1);
+                wh[t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                wlw[t] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            oh[c] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+            ol[c] = make_uint4(wlw[0], wlw[1], wlw[2], wlw[3]);
+        }
+    }
+}
+
 // levels 1..3 from level 0 in one pass; -1 if the level-0 image does not fit the shared-memory budget (caller falls back)
 int b2p_corr_pool3(float* pyramid, int B, int h, int w, cudaStream_t s) {
     const int P = h * w;
@@ -375,6 +454,22 @@ int b2p_corr_pool3(float* pyramid, int B, int h, int w, cudaStream_t s) {
 int b2p_corr_lookup(const float* pyramid, const float* coords, int B, int h, int w, float* out, __half* out_hi,
                     __half* out_lo, cudaStream_t s) {
     const int warps = B * h * w;
+    const int lm = b2p_options().lookup_mode;
+    // 2 (default): the row kernel as a plain launch.  Launched with the programmatic-dependent-launch attribute (mode 3) the same
+    // kernel makes the step 0.15 ms SLOWER although it is 17 us faster than the window kernel in isolation: its 4800 blocks become
+    // resident behind the early triggers of the two tiny kernels in front of it and sit on the SMs while the LM kernel of the
+    // previous iteration is still running (profiles/r3e: 3.535 ms with, 3.388 ms without the attribute; window kernel 3.455).
+    if (lm == 2) {
+        corr_lookup_row_kernel<8><<<ceil_div(warps, 8), 8 * 36, 0, s>>>(pyramid, coords, B, h, w, out, out_hi, out_lo);
+        B2P_LAUNCH_CHECK();
+        return 0;
+    }
+    if (lm == 3) {
+        B2P_CUDA(b2p_launch_pdl(corr_lookup_row_kernel<8>, dim3(ceil_div(warps, 8)), dim3(8 * 36), 0, s, pyramid, coords, B, h, w,
+                                out, out_hi, out_lo));
+        B2P_LAUNCH_CHECK();
+        return 0;
+    }
     if (b2p_options().lookup_mode == 1) {
         B2P_CUDA(b2p_launch_pdl(corr_lookup_win_kernel, dim3(ceil_div(warps, LK_WARPS)), dim3(LK_WARPS * 32), 0, s, pyramid, coords, B, h, w,
                                 out, out_hi, out_lo));
@@ -418,6 +513,7 @@ void b2p_context_sample_taps(int in, int out, int* i0, int* i1) {
 int b2p_flow_init(const float* depth, const float* K, const float* G, int B, int H, int W, float* coords1, float* flow,
                   cudaStream_t s) {
     const int h = H / 8, w = W / 8;
+    b2p_pdl_next_allowed() = b2p_pdl_allowed(0);
     B2P_CUDA(b2p_launch_pdl(flow_init_kernel, dim3(ceil_div(B * h * w, 256)), dim3(256), 0, s, depth, K, G, B, H, W, h, w, ac_scale(H, h),
                             ac_scale(W, w), coords1, flow));
     B2P_LAUNCH_CHECK();

@@ -744,7 +744,7 @@ int b2p_lm_cluster(const float4* rec, const float* depth, const float* target, c
     cfg.gridDim = dim3((unsigned)(B * LMC_CTAS)); cfg.blockDim = dim3(LM_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = b2p_pdl_allowed(5);
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = LMC_CTAS; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 2;

@@ -23,7 +23,7 @@ const OptDesc kOpts[] = {
     {"fg_blocks", "B200POSE_FG_BLOCKS", &B2POptions::fg_blocks, 8},
     {"tail_min_n", "B200POSE_TAIL_MIN_N", &B2POptions::tail_min_n, 32},     // smallest channel count of a split tail unit
     {"conv_debug", "B200POSE_V2_DEBUG", &B2POptions::conv_debug, 0},        // timing experiments (results garbage unless 0 / 16)
-    {"lookup_mode", "B200POSE_LOOKUP_MODE", &B2POptions::lookup_mode, 1},   // 1 = shared-memory window lookup, 0 = round-1 kernel
+    {"lookup_mode", "B200POSE_LOOKUP_MODE", &B2POptions::lookup_mode, 2},   // 2 = one thread per window row (3: the same with PDL), 1 = shared-memory window lookup, 0 = round-1 kernel
     {"pool_mode", "B200POSE_POOL_MODE", &B2POptions::pool_mode, 1},         // 1 = three pyramid levels in one pass
     {"lm_cluster", "B200POSE_LM_CLUSTER", &B2POptions::lm_cluster, 1},      // LM over the list: cluster kernel (1) or spin-barrier kernel (0)
     {"lm_debug", "B200POSE_LM_DEBUG", &B2POptions::lm_debug, 0},            // 1 = drop the fp64 contraction (timing A/B only)
@@ -43,6 +43,7 @@ const OptDesc kOpts[] = {
     // the kernel reads the rest in place from the mapped buffer.  256 when one GPU has the host to itself; fewer when several
     // ranks share the host's cores (bench.py tries both)
     {"host_gather_planes", "B200POSE_HOST_GATHER_PLANES", &B2POptions::host_gather_planes, 256},
+    {"pdl_off", "B200POSE_PDL_OFF", &B2POptions::pdl_off, 0},                 // A/B: bit mask of loop kernels launched without PDL (tags in common.cuh)
     {"chain_dynamic", "B200POSE_CHAIN_DYNAMIC", &B2POptions::chain_dynamic, 0},   // chained launch: units from a global queue (1) or static round robin (0)
 };
 constexpr int kNumOpts = (int)(sizeof(kOpts) / sizeof(kOpts[0]));

@@ -395,6 +395,7 @@ size_t b2p_half_section_offset_bytes() { return align_up(b2p_weight_layout().tot
 int b2p_im2col_f1(const float* flow, int B, int h, int w, float* col, float* xbuf, __half* col_hi, __half* col_lo,
                   __half* x_hi, __half* x_lo, cudaStream_t s) {
     const size_t total = (size_t)B * h * w * 56;
+    b2p_pdl_next_allowed() = b2p_pdl_allowed(2);
     B2P_CUDA(b2p_launch_pdl(im2col_f1_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, flow, B, h, w, col, xbuf, col_hi, col_lo, x_hi, x_lo));
     B2P_LAUNCH_CHECK();
     return 0;

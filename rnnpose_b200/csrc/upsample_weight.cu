@@ -470,6 +470,7 @@ int b2p_upsample_weight(const float* flow, const float* mask, const float* g1, c
     // other crop sizes run variant 0
     const int var = b2p_options().upsample_variant;
     const bool cs = H * W == 240 * 320;
+    b2p_pdl_next_allowed() = b2p_pdl_allowed(4);
 #define UPW_LAUNCH(NP, BT) B2P_CUDA(b2p_launch_pdl(upsample_weight_kernel<NP, BT>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up, target, weight, lazy_background))
 #define UPW_LAUNCH_WIN(NP, BT) B2P_CUDA(b2p_launch_pdl(upsample_weight_win_kernel<NP, BT>, grid, dim3(64), 0, s, flow, mask, g1, g2, depth, sigma, B, C, H, W, flow_up, target, weight, lazy_background, g2_far, g2_window))
     if (g2_far && g2_window && g2) {            // host entry: geofea2 is only valid inside a per-sample window

@@ -40,7 +40,7 @@ def packed(ops):
     return ops.pack_weights(load_update_weights(), dev())
 
 
-@pytest.mark.parametrize("variant", [(1, 1), (0, 0)], ids=["window-lookup+pool3", "round1-kernels"])
+@pytest.mark.parametrize("variant", [(2, 1), (1, 1), (0, 0)], ids=["row-lookup+pool3", "window-lookup+pool3", "round1-kernels"])
 def test_corr_pyramid_and_lookup_golden(ops, libopt, variant):
     libopt("lookup_mode", variant[0]); libopt("pool_mode", variant[1])
     g = golden("corr_lookup.npz")
@@ -80,13 +80,18 @@ def test_corr_lookup_window_kernel_edge_coordinates(ops):
         new = ops.corr_lookup(pyr, cd, B, h, w).cpu()
     assert torch.all(new[:, 324:] == 0)
     torch.testing.assert_close(new, old, rtol=1e-5, atol=5e-6)
+    with ops.options(lookup_mode=2):                                   # one thread per window row
+        row = ops.corr_lookup(pyr, cd, B, h, w).cpu()
+    assert torch.all(row[:, 324:] == 0)
+    torch.testing.assert_close(row, old, rtol=1e-5, atol=5e-6)
     ref = O.corr_lookup(O.corr_pyramid(f1.cpu(), f2.cpu()), from_pxc(c, B, h, w))
     torch.testing.assert_close(from_pxc(new[:, :324].contiguous(), B, h, w), ref, rtol=1e-5, atol=5e-6)
     # non-finite coordinates: the reference's grid_sample yields zeros there; both kernels must agree and stay finite
     c2 = c.clone(); c2[9] = torch.tensor([float("nan"), 3.0]); c2[10] = torch.tensor([float("inf"), 3.0])
-    with ops.options(lookup_mode=1):
-        nf = ops.corr_lookup(pyr, c2.to(dev()), B, h, w).cpu()
-    assert torch.all(nf[9:11] == 0) and torch.isfinite(nf).all()
+    for mode in (1, 2):
+        with ops.options(lookup_mode=mode):
+            nf = ops.corr_lookup(pyr, c2.to(dev()), B, h, w).cpu()
+        assert torch.all(nf[9:11] == 0) and torch.isfinite(nf).all()
 
 
 def test_corr_pyramid_full_size_vs_oracle(ops):
