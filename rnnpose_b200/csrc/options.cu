@@ -43,7 +43,10 @@ const OptDesc kOpts[] = {
     // the kernel reads the rest in place from the mapped buffer.  256 when one GPU has the host to itself; fewer when several
     // ranks share the host's cores (bench.py tries both)
     {"host_gather_planes", "B200POSE_HOST_GATHER_PLANES", &B2POptions::host_gather_planes, 256},
-    {"pdl_off", "B200POSE_PDL_OFF", &B2POptions::pdl_off, 0},                 // A/B: bit mask of loop kernels launched without PDL (tags in common.cuh)
+    // bit mask of loop kernels launched WITHOUT the PDL attribute (tags in common.cuh).  Default 16 = the dense upsample + weight
+    // kernel: launched early its 38 400 blocks sit on the SMs during the chained convolution launch (3.387 -> 3.307 ms per batch
+    // without; LM, flow_init, im2col and the chained launch itself keep it: no gain or a loss without, profiles/r3f)
+    {"pdl_off", "B200POSE_PDL_OFF", &B2POptions::pdl_off, 16},
     {"chain_dynamic", "B200POSE_CHAIN_DYNAMIC", &B2POptions::chain_dynamic, 0},   // chained launch: units from a global queue (1) or static round robin (0)
 };
 constexpr int kNumOpts = (int)(sizeof(kOpts) / sizeof(kOpts[0]));
