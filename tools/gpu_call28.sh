@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU call 28: HEAD: full GPU suite, smoke, default bench (the driver's sequence).
 cd "$(dirname "$0")/.."
-O=gpurun_out/r3b; mkdir -p $O
+O=gpurun_out/r3g; mkdir -p $O
 export PYTHONDONTWRITEBYTECODE=1
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $O/suite.txt 2>&1; tail -4 $O/suite.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.txt 2>&1; tail -1 $O/smoke.txt
