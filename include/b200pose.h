@@ -74,7 +74,7 @@ const char* b200pose_error_string(int code);
  *   fg_pipeline (B200POSE_FG_PIPELINE, 2)  channels-last target / weight kernels + cluster LM kernel: 0 off, 1 on, 2 only when
  *                                      geofea2 arrives channels-last (B200POSE_FLAG_GEO2_CHANNELS_LAST)
  *   fg_upsample, fg_blocks, sparse_g1, sparse_g2, g2_margin, host_gather, host_gather_planes, upsample_variant, enc_stem, enc_chunk,
- *   tail_min_n, lookup_mode, pool_mode,
+ *   tail_min_n, lookup_mode, pool_mode, pdl_off,
  *   chain_rings, chain_dynamic, chain_xmajor, chain_merge, lm_cluster, conv_debug, lm_debug: see csrc/options.cu
  * Returns 0, B200POSE_E_NULL or B200POSE_E_ARG (unknown name).  Not synchronised against launches in flight on other
  * threads.                                                                                         */
